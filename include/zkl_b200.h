@@ -1,0 +1,226 @@
+/*
+ * zkl_b200.h — C ABI of the B200-native zk-lisp / Winterfell proving hot path.
+ *
+ * Drop-in boundary. The reference has no FFI: its seam is the Rust trait
+ * `winterfell::Prover` implemented at
+ *   /root/reference/zk-lisp-proof-winterfell/src/prove.rs:425-517   (ZkWinterfellProver)
+ * whose three hooks forward to Winterfell's CPU defaults:
+ *   new_trace_lde                 prove.rs:454-474  -> zkl_trace_lde_commit
+ *   new_evaluator (+ evaluate)    prove.rs:476-492  -> zkl_eval_constraints
+ *   build_constraint_commitment   prove.rs:494-516  -> zkl_constraint_commit
+ * plus the hook types' query methods (TraceLde::query, ConstraintCommitment::query)
+ *                                                    -> zkl_trace_query / zkl_constraint_query
+ * and, because OOD/DEEP/FRI/grinding live in the provided method `Prover::prove`
+ * (prove.rs:225 calls it), a whole-proof entry point          -> zkl_prove_segment.
+ * INTEGRATION.md shows the Rust-side binding (cc/bindgen shim) a maintainer would add.
+ *
+ * Conventions
+ *  - every field element is winter-math f128 `BaseElement`: canonical value < p,
+ *    p = 2^128 - 45*2^40 + 1, stored as 16 little-endian bytes (`zkl_fe`);
+ *  - digests are the reference's 32-byte PoseidonDigest (poseidon/hasher.rs:25-26): the
+ *    16 LE bytes of one field element followed by 16 zero bytes (utils.rs:375-381);
+ *  - all pointers are HOST pointers unless the name ends in `_dev`;
+ *  - every call returns 0 on success, non-zero on failure; zkl_last_error() gives the text.
+ *    There is NO CPU fallback: without a CUDA device zkl_ctx_create fails.
+ *  - threading: one zkl_ctx per host thread (prove.rs:1020-1048 runs one prover per rayon
+ *    worker); a ctx owns one CUDA stream and is pinned to the device given at creation.
+ */
+#ifndef ZKL_B200_H
+#define ZKL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct { uint64_t lo, hi; } zkl_fe; /* canonical u128, little-endian limbs */
+
+#define ZKL_ROUNDS 27        /* vm/layout.rs:22 POSEIDON_ROUNDS */
+#define ZKL_NR 8             /* vm/layout.rs NR */
+#define ZKL_NUM_OPS 17       /* op_const .. op_store, vm/layout.rs:208-226 */
+#define ZKL_NUM_PERIODIC 32  /* vm/air/mod.rs:526 */
+
+/* Poseidon-style 12-lane suite (poseidon/mod.rs:33-38) */
+typedef struct {
+  zkl_fe dom[2];
+  zkl_fe mds[12][12];
+  zkl_fe rc[ZKL_ROUNDS][12];
+} zkl_suite;
+
+/* t=3 ROM suite (poseidon/mod.rs:186-197,219-251) */
+typedef struct {
+  zkl_fe mds[3][3];
+  zkl_fe rc[ZKL_ROUNDS][3];
+} zkl_rom_suite;
+
+/* One `Assertion::single(column, step, value)` (vm/air/mod.rs:380-504). */
+typedef struct {
+  uint32_t column;
+  uint32_t step;
+  zkl_fe value;
+} zkl_assertion;
+
+/* Column map = vm/layout.rs `Columns` (for_config, :183-314) */
+typedef struct {
+  uint32_t width;
+  uint32_t lanes_start, g_map, g_final, g_r_start, mask, r_start;
+  uint32_t op_start;                 /* op_const; the 17 op columns are consecutive */
+  uint32_t sel_dst0_start, sel_a_start, sel_b_start, sel_c_start, sel_dst1_start;
+  uint32_t sel_s_bits_start, sel_s_active_start;
+  uint32_t imm, eq_inv;
+  uint32_t ram_start;                /* ram_sorted; 8 consecutive columns */
+  uint32_t merkle_start;             /* merkle_g; 7 consecutive columns */
+  uint32_t pi_prog, pc, rom_op_start, pose_active, gadget_b_start, rom_s_start;
+} zkl_columns;
+
+/* Everything ZkLispAir::new (vm/air/mod.rs:114-318) derives from AirPublicInputs that the
+ * constraint kernel needs. Built by the host layer (zk-lisp_b200/air.py mirrors the Rust). */
+typedef struct {
+  zkl_columns cols;
+  /* FeaturesMap (zk-lisp-proof/src/pi.rs) + rom gate (program_commitment != 0) */
+  uint32_t f_poseidon, f_vm, f_sponge, f_merkle, f_ram, rom_enabled;
+  uint32_t vm_usage_mask;            /* vm/layout.rs VM_USAGE_* bits */
+  uint32_t ram_delta_clk_bits;
+  uint32_t num_transition;           /* len(degrees), vm/air/mod.rs:216-238 */
+  uint32_t ce_blowup;                /* AirContext::ce_blowup_factor  (8 for this AIR) */
+  uint32_t num_composition_cols;     /* AirContext::num_constraint_composition_columns (7) */
+  uint32_t num_assertions;
+  const zkl_assertion *assertions;   /* get_assertions() order, already de-duplicated */
+  zkl_suite pose;                    /* suite_id = program_id (vm/air/mod.rs:129-138) */
+  zkl_rom_suite rom;                 /* vm/air/mod.rs:169-176 */
+  zkl_fe rom_w_enc0[59], rom_w_enc1[59]; /* utils.rs:114-141 */
+  zkl_fe program_fe0;                /* RAM compressor pi (vm/air/ram.rs:109) */
+  zkl_fe merkle_root_fe;             /* be_from_le8(merkle_root) (vm/air/merkle.rs:121) */
+} zkl_air_params;
+
+/* winterfell::ProofOptions as zk-lisp builds them (prove.rs:963-972, :1106-1107) */
+typedef struct {
+  uint32_t num_queries;      /* 64 */
+  uint32_t blowup;           /* 16 */
+  uint32_t grinding;         /* 16 */
+  uint32_t num_partitions;   /* utils.rs:394-409 */
+  uint32_t hash_rate;
+  uint32_t fri_folding;      /* 2  (only 2 is supported) */
+  uint32_t fri_remainder_max_degree; /* 1 */
+} zkl_options;
+
+typedef struct zkl_ctx zkl_ctx;
+typedef struct zkl_trace_lde zkl_trace_lde;               /* replaces DefaultTraceLde (prove.rs:432) */
+typedef struct zkl_constraint_commitment zkl_constraint_commitment; /* DefaultConstraintCommitment (:436) */
+
+/* ---- context ------------------------------------------------------------------------- */
+int zkl_ctx_create(int device, zkl_ctx **out);
+void zkl_ctx_destroy(zkl_ctx *ctx);
+const char *zkl_last_error(const zkl_ctx *ctx); /* ctx may be NULL: last create error */
+/* Commitment/coin hasher constants: suite_id = [0;32] (poseidon/hasher.rs:23). The host
+ * computes them exactly as poseidon/mod.rs does and hands them over. */
+int zkl_suite_load(zkl_ctx *ctx, const zkl_suite *suite);
+/* number of kernels launched on this ctx since creation (bench.py's gpu_launches) */
+uint64_t zkl_launch_count(const zkl_ctx *ctx);
+
+/* ---- hasher primitives (poseidon/hasher.rs:57-140), batched ----------------------------
+ * Exposed so parity tests can check each PoseidonHasher entry point separately. */
+int zkl_permute_batch(zkl_ctx *ctx, zkl_fe *states /* count*12, in/out */, size_t count);
+int zkl_hash_elements_batch(zkl_ctx *ctx, const zkl_fe *elems /* count*len */, size_t len,
+                            size_t count, uint8_t *out_digests /* count*32 */);
+int zkl_merge_batch(zkl_ctx *ctx, const uint8_t *pairs /* count*64 */, size_t count,
+                    uint8_t *out_digests);
+int zkl_merge_with_int_batch(zkl_ctx *ctx, const uint8_t seed[32], const uint64_t *values,
+                             size_t count, uint8_t *out_digests);
+int zkl_hash_bytes(zkl_ctx *ctx, const uint8_t *data, size_t len, uint8_t out[32]);
+int zkl_merge_many(zkl_ctx *ctx, const uint8_t *digests, size_t count, uint8_t out[32]);
+/* MerkleTree::new over `count` leaves (power of two); out_nodes[i], i in 1..count, is the
+ * Winterfell node array (nodes[1] = root); out_nodes may be NULL. */
+int zkl_merkle_build(zkl_ctx *ctx, const uint8_t *leaves, size_t count, uint8_t out_root[32],
+                     uint8_t *out_nodes /* count*32 or NULL */);
+
+/* ---- NTT primitives (winter-math fft) --------------------------------------------------
+ * cols: `ncols` columns of `n` elements, column-major. */
+int zkl_interpolate_columns(zkl_ctx *ctx, zkl_fe *cols, size_t ncols, size_t n);
+/* out[c][i] = poly_c(offset * w_N^i), N = n*blowup, natural order */
+int zkl_evaluate_columns(zkl_ctx *ctx, const zkl_fe *polys, size_t ncols, size_t n,
+                         size_t blowup, zkl_fe offset, zkl_fe *out /* ncols*N */);
+
+/* ---- hook 1: new_trace_lde (prove.rs:454-474 -> DefaultTraceLde::new) -------------------
+ * trace: W columns x n rows, column-major (winterfell ColMatrix). Computes the trace
+ * polynomials, the blowup-`blowup` LDE over the coset GENERATOR*<w_N>, row hashes with the
+ * given partition options and the Merkle tree. out_polys (W*n, column-major) may be NULL. */
+int zkl_trace_lde_commit(zkl_ctx *ctx, const zkl_fe *trace, size_t width, size_t n,
+                         const zkl_options *opts, uint8_t out_root[32], zkl_fe *out_polys,
+                         zkl_trace_lde **out_handle);
+void zkl_trace_lde_free(zkl_ctx *ctx, zkl_trace_lde *h);
+/* TraceLde::read_main_trace_frame_into(lde_step): current = LDE row lde_step,
+ * next = row (lde_step + blowup) mod N. out_cur/out_next: width elements each. */
+int zkl_trace_lde_read_frame(zkl_ctx *ctx, const zkl_trace_lde *h, size_t lde_step,
+                             zkl_fe *out_cur, zkl_fe *out_next);
+/* TraceLde::query(positions): rows (k*width elements) and the Winterfell BatchMerkleProof
+ * node lists flattened as out_nodes with per-position counts (see zkl_batch_proof). */
+typedef struct {
+  uint8_t depth;
+  uint32_t num_lists;      /* number of node vectors */
+  uint32_t *list_len;      /* num_lists entries (caller-allocated, capacity >= k) */
+  uint8_t *nodes;          /* concatenated 32-byte digests (capacity >= k*depth*32) */
+  uint32_t total_nodes;
+} zkl_batch_proof;
+int zkl_trace_query(zkl_ctx *ctx, const zkl_trace_lde *h, const uint32_t *positions, size_t k,
+                    zkl_fe *out_rows, zkl_batch_proof *out_proof);
+
+/* ---- hook 2: new_evaluator + ConstraintEvaluator::evaluate (prove.rs:476-492) -----------
+ * coeffs: ConstraintCompositionCoefficients, `num_transition` transition coefficients
+ * followed by `num_assertions` boundary coefficients in Winterfell's sorted-assertion order.
+ * out: the CompositionPolyTrace, n*ce_blowup combined evaluations over GENERATOR*<w_{8n}>. */
+int zkl_eval_constraints(zkl_ctx *ctx, const zkl_trace_lde *h, const zkl_air_params *air,
+                         const zkl_fe *coeffs, zkl_fe *out_ce_evals);
+
+/* ---- hook 3: build_constraint_commitment (prove.rs:494-516) ------------------------------
+ * ce_evals: n*ce_blowup evaluations. Interpolates, splits into num_cols columns of n
+ * coefficients (out_poly, column-major num_cols*n, may be NULL), evaluates over the LDE
+ * domain, hashes rows and builds the Merkle tree. */
+int zkl_constraint_commit(zkl_ctx *ctx, const zkl_fe *ce_evals, size_t n, size_t ce_blowup,
+                          size_t num_cols, const zkl_options *opts, uint8_t out_root[32],
+                          zkl_fe *out_poly, zkl_constraint_commitment **out_handle);
+void zkl_constraint_commitment_free(zkl_ctx *ctx, zkl_constraint_commitment *h);
+int zkl_constraint_query(zkl_ctx *ctx, const zkl_constraint_commitment *h,
+                         const uint32_t *positions, size_t k, zkl_fe *out_rows,
+                         zkl_batch_proof *out_proof);
+
+/* ---- whole segment proof: winterfell::Prover::prove (prove.rs:225) ----------------------
+ * trace: W x n column-major; seed_elems: Context::to_elements() ++ AirPublicInputs::to_elements()
+ * (lib.rs:116-160), i.e. the public-coin seed (agg/fs.rs:69-73). Runs stages 1-11 of
+ * SURVEY.md §3.2 on the device and writes the serialized winterfell::Proof.
+ * out_proof/out_len: caller buffer and capacity in, bytes written out. */
+typedef struct {
+  uint8_t trace_root[32];
+  uint8_t constraint_root[32];
+  uint8_t fri_roots[32 * 40];   /* num_fri_layers + 1 (remainder commitment) */
+  uint32_t num_fri_roots;
+  zkl_fe z;                     /* OOD point */
+  uint64_t pow_nonce;
+  uint32_t num_unique_queries;
+  uint32_t positions[256];
+  float stage_ms[12];           /* device time per stage, see zkl_stage_name */
+} zkl_proof_summary;
+int zkl_prove_segment(zkl_ctx *ctx, const zkl_fe *trace, size_t width, size_t n,
+                      const zkl_air_params *air, const zkl_fe *seed_elems, size_t num_seed,
+                      const zkl_options *opts, uint8_t *out_proof, size_t *out_len,
+                      zkl_proof_summary *summary /* may be NULL */);
+/* Same, with the trace already resident in device memory (bench.py `value` leg). */
+int zkl_prove_segment_dev(zkl_ctx *ctx, const void *trace_dev, size_t width, size_t n,
+                          const zkl_air_params *air, const zkl_fe *seed_elems, size_t num_seed,
+                          const zkl_options *opts, uint8_t *out_proof, size_t *out_len,
+                          zkl_proof_summary *summary);
+const char *zkl_stage_name(int stage);
+
+/* device memory helpers for callers that keep traces resident (torch tensors' data_ptr()
+ * can be passed instead) */
+int zkl_dev_alloc(zkl_ctx *ctx, size_t bytes, void **out_dev);
+int zkl_dev_free(zkl_ctx *ctx, void *dev);
+int zkl_dev_upload(zkl_ctx *ctx, void *dev, const void *host, size_t bytes);
+int zkl_sync(zkl_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZKL_B200_H */

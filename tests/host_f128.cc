@@ -1,0 +1,27 @@
+// Host build of the DEVICE limb arithmetic (zk-lisp_b200/csrc/f128.cuh compiled with g++): the
+// carry primitives fall back to plain C so the limb algorithms can be checked on the CPU.
+#include "../zk-lisp_b200/csrc/f128.cuh"
+extern "C" {
+void h_binop(int op, const fe *a, const fe *b, fe *out, long n) {
+  for (long i = 0; i < n; i++) {
+    switch (op) {
+      case 0: out[i] = fe_add(a[i], b[i]); break;
+      case 1: out[i] = fe_sub(a[i], b[i]); break;
+      case 2: out[i] = fe_mul(a[i], b[i]); break;
+      case 3: out[i] = fe_inv(a[i]); break;
+      case 4: out[i] = fe_cube(a[i]); break;
+      case 5: out[i] = fe_fold_pair(a[i], b[i]); break;
+      case 6: out[i] = fe_from_u128_mod(a[i]); break;
+    }
+  }
+}
+// out = sum_k a[k]*b[k] + rc  (12 terms, lazy reduction) — the MDS row pattern
+void h_dot12(const fe *a, const fe *b, const fe *rc, fe *out, long n) {
+  for (long i = 0; i < n; i++) {
+    wide_acc w; wacc_zero(w);
+    for (int k = 0; k < 12; k++) wacc_mad(w, a[12 * i + k], b[12 * i + k]);
+    wacc_add_fe(w, rc[i]);
+    out[i] = wacc_reduce(w);
+  }
+}
+}

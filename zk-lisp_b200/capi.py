@@ -1,0 +1,176 @@
+"""ctypes mirror of include/zkl_b200.h and the loader of the CUDA library.
+
+There is NO CPU fallback: if libzkl_b200.so is missing or no CUDA device is present, loading /
+context creation raises. The oracle (oracle/liboracle.so) is loaded only by tests/, smoke() and
+bench.py's cpu_baseline legs through `tests/oracle_lib.py`, never from here.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "csrc", "libzkl_b200.so")
+
+ROUNDS, NR, NUM_OPS = 27, 8, 17
+
+
+class Fe(C.Structure):
+    _fields_ = [("lo", C.c_uint64), ("hi", C.c_uint64)]
+
+    @staticmethod
+    def of(x: int) -> "Fe":
+        return Fe(x & 0xFFFFFFFFFFFFFFFF, x >> 64)
+
+    def int(self) -> int:
+        return self.lo | (self.hi << 64)
+
+
+class Suite(C.Structure):
+    _fields_ = [("dom", Fe * 2), ("mds", (Fe * 12) * 12), ("rc", (Fe * 12) * ROUNDS)]
+
+
+class RomSuite(C.Structure):
+    _fields_ = [("mds", (Fe * 3) * 3), ("rc", (Fe * 3) * ROUNDS)]
+
+
+class Assertion(C.Structure):
+    _fields_ = [("column", C.c_uint32), ("step", C.c_uint32), ("value", Fe)]
+
+
+COLUMN_FIELDS = [
+    "width", "lanes_start", "g_map", "g_final", "g_r_start", "mask", "r_start", "op_start",
+    "sel_dst0_start", "sel_a_start", "sel_b_start", "sel_c_start", "sel_dst1_start",
+    "sel_s_bits_start", "sel_s_active_start", "imm", "eq_inv", "ram_start", "merkle_start",
+    "pi_prog", "pc", "rom_op_start", "pose_active", "gadget_b_start", "rom_s_start",
+]
+
+
+class Columns(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in COLUMN_FIELDS]
+
+
+class AirParams(C.Structure):
+    _fields_ = [
+        ("cols", Columns),
+        ("f_poseidon", C.c_uint32), ("f_vm", C.c_uint32), ("f_sponge", C.c_uint32),
+        ("f_merkle", C.c_uint32), ("f_ram", C.c_uint32), ("rom_enabled", C.c_uint32),
+        ("vm_usage_mask", C.c_uint32), ("ram_delta_clk_bits", C.c_uint32),
+        ("num_transition", C.c_uint32), ("ce_blowup", C.c_uint32),
+        ("num_composition_cols", C.c_uint32), ("num_assertions", C.c_uint32),
+        ("assertions", C.POINTER(Assertion)),
+        ("pose", Suite), ("rom", RomSuite),
+        ("rom_w_enc0", Fe * 59), ("rom_w_enc1", Fe * 59),
+        ("program_fe0", Fe), ("merkle_root_fe", Fe),
+    ]
+
+
+class Options(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in (
+        "num_queries", "blowup", "grinding", "num_partitions", "hash_rate", "fri_folding",
+        "fri_remainder_max_degree")]
+
+
+class BatchProof(C.Structure):
+    _fields_ = [("depth", C.c_uint8), ("num_lists", C.c_uint32), ("list_len", C.POINTER(C.c_uint32)),
+                ("nodes", C.POINTER(C.c_uint8)), ("total_nodes", C.c_uint32)]
+
+
+class ProofSummary(C.Structure):
+    _fields_ = [
+        ("trace_root", C.c_uint8 * 32), ("constraint_root", C.c_uint8 * 32),
+        ("fri_roots", C.c_uint8 * (32 * 40)), ("num_fri_roots", C.c_uint32),
+        ("z", Fe), ("pow_nonce", C.c_uint64), ("num_unique_queries", C.c_uint32),
+        ("positions", C.c_uint32 * 256), ("stage_ms", C.c_float * 12),
+    ]
+
+
+def suite_to_c(suite) -> Suite:
+    s = Suite()
+    for i in range(2):
+        s.dom[i] = Fe.of(suite.dom[i])
+    for i in range(12):
+        for j in range(12):
+            s.mds[i][j] = Fe.of(suite.mds[i][j])
+    for r in range(ROUNDS):
+        for j in range(12):
+            s.rc[r][j] = Fe.of(suite.rc[r][j])
+    return s
+
+
+def rom_suite_to_c(mds, rc) -> RomSuite:
+    s = RomSuite()
+    for i in range(3):
+        for j in range(3):
+            s.mds[i][j] = Fe.of(mds[i][j])
+    for r in range(ROUNDS):
+        for j in range(3):
+            s.rc[r][j] = Fe.of(rc[r][j])
+    return s
+
+
+_lib = None
+
+
+class ZklError(RuntimeError):
+    pass
+
+
+def load_library():
+    """Load the CUDA shared library; fail loudly when it is absent (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ZklError(f"{LIB_PATH} not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                       "(nvcc, sm_100a). There is no CPU fallback for the proving path.")
+    lib = C.CDLL(LIB_PATH)
+    vp, sz, u8p, fep = C.c_void_p, C.c_size_t, C.POINTER(C.c_uint8), C.POINTER(Fe)
+
+    def sig(name, res, *args):
+        f = getattr(lib, name)
+        f.restype, f.argtypes = res, list(args)
+
+    sig("zkl_ctx_create", C.c_int, C.c_int, C.POINTER(vp))
+    sig("zkl_ctx_destroy", None, vp)
+    sig("zkl_last_error", C.c_char_p, vp)
+    sig("zkl_suite_load", C.c_int, vp, C.POINTER(Suite))
+    sig("zkl_launch_count", C.c_uint64, vp)
+    sig("zkl_permute_batch", C.c_int, vp, vp, sz)
+    sig("zkl_hash_elements_batch", C.c_int, vp, vp, sz, sz, vp)
+    sig("zkl_merge_batch", C.c_int, vp, vp, sz, vp)
+    sig("zkl_merge_with_int_batch", C.c_int, vp, vp, vp, sz, vp)
+    sig("zkl_hash_bytes", C.c_int, vp, vp, sz, vp)
+    sig("zkl_merge_many", C.c_int, vp, vp, sz, vp)
+    sig("zkl_merkle_build", C.c_int, vp, vp, sz, vp, vp)
+    sig("zkl_interpolate_columns", C.c_int, vp, vp, sz, sz)
+    sig("zkl_evaluate_columns", C.c_int, vp, vp, sz, sz, sz, Fe, vp)
+    sig("zkl_trace_lde_commit", C.c_int, vp, vp, sz, sz, C.POINTER(Options), vp, vp, C.POINTER(vp))
+    sig("zkl_trace_lde_free", None, vp, vp)
+    sig("zkl_trace_lde_read_frame", C.c_int, vp, vp, sz, vp, vp)
+    sig("zkl_trace_query", C.c_int, vp, vp, vp, sz, vp, C.POINTER(BatchProof))
+    sig("zkl_eval_constraints", C.c_int, vp, vp, C.POINTER(AirParams), vp, vp)
+    sig("zkl_constraint_commit", C.c_int, vp, vp, sz, sz, sz, C.POINTER(Options), vp, vp, C.POINTER(vp))
+    sig("zkl_constraint_commitment_free", None, vp, vp)
+    sig("zkl_constraint_query", C.c_int, vp, vp, vp, sz, vp, C.POINTER(BatchProof))
+    sig("zkl_prove_segment", C.c_int, vp, vp, sz, sz, C.POINTER(AirParams), vp, sz, C.POINTER(Options), vp,
+        C.POINTER(sz), C.POINTER(ProofSummary))
+    sig("zkl_prove_segment_dev", C.c_int, vp, vp, sz, sz, C.POINTER(AirParams), vp, sz, C.POINTER(Options), vp,
+        C.POINTER(sz), C.POINTER(ProofSummary))
+    sig("zkl_stage_name", C.c_char_p, C.c_int)
+    sig("zkl_dev_alloc", C.c_int, vp, sz, C.POINTER(vp))
+    sig("zkl_dev_free", C.c_int, vp, vp)
+    sig("zkl_dev_upload", C.c_int, vp, vp, vp, sz)
+    sig("zkl_sync", C.c_int, vp)
+    _lib = lib
+    return lib
+
+
+EXPORTED_SYMBOLS = [
+    "zkl_ctx_create", "zkl_ctx_destroy", "zkl_last_error", "zkl_suite_load", "zkl_launch_count",
+    "zkl_permute_batch", "zkl_hash_elements_batch", "zkl_merge_batch", "zkl_merge_with_int_batch",
+    "zkl_hash_bytes", "zkl_merge_many", "zkl_merkle_build", "zkl_interpolate_columns",
+    "zkl_evaluate_columns", "zkl_trace_lde_commit", "zkl_trace_lde_free", "zkl_trace_lde_read_frame",
+    "zkl_trace_query", "zkl_eval_constraints", "zkl_constraint_commit",
+    "zkl_constraint_commitment_free", "zkl_constraint_query", "zkl_prove_segment",
+    "zkl_prove_segment_dev", "zkl_stage_name", "zkl_dev_alloc", "zkl_dev_free", "zkl_dev_upload",
+    "zkl_sync",
+]

@@ -1,0 +1,649 @@
+// api_stark.inl — hook-level entry points and the whole-segment prover (included by zkl_b200.cu).
+
+// ------------------------------------------------------------------------------------------------
+// committed matrix = coset-major LDE + Merkle tree (DefaultTraceLde / DefaultConstraintCommitment)
+// ------------------------------------------------------------------------------------------------
+struct committed_matrix {
+  size_t width = 0, n = 0, blowup = 0, N = 0;
+  dev_buf<fe> polys;   // width x n coefficients
+  dev_buf<fe> lde;     // width x N, coset-major
+  dev_buf<fe> leaves;  // N digests (as elements), natural row order
+  dev_buf<fe> nodes;   // N entries, nodes[1] = root
+  dev_buf<fe> scratch;
+};
+struct zkl_trace_lde { committed_matrix m; };
+struct zkl_constraint_commitment { committed_matrix m; };
+
+// polys must already hold width x n coefficients
+static int commit_matrix(zkl_ctx *ctx, committed_matrix &m, const zkl_options *o) {
+  ZKL_CHECK(ctx, m.lde.alloc(m.width * m.N));
+  ZKL_CHECK(ctx, m.leaves.alloc(m.N));
+  ZKL_CHECK(ctx, m.nodes.alloc(m.N));
+  ZKL_TRY(dev_lde(ctx, m.polys.p, m.lde.p, m.width, m.n, m.blowup));
+  ZKL_TRY(dev_hash_rows(ctx, m.lde.p, m.width, m.n, m.blowup, o, m.leaves.p, m.scratch));
+  ZKL_TRY(dev_merkle(ctx, m.leaves.p, m.nodes.p, m.N));
+  return 0;
+}
+static int check_opts(zkl_ctx *ctx, const zkl_options *o, size_t n) {
+  if (o->fri_folding != 2) { ctx->set_error("only FRI folding factor 2 is supported (prove.rs:968)"); return 1; }
+  if (o->blowup < 2 || (o->blowup & (o->blowup - 1)) || o->blowup > 128) { ctx->set_error("blowup must be a power of two in [2,128]"); return 1; }
+  if (n < 8 || n > 8192 || (n & (n - 1))) { ctx->set_error("trace length must be a power of two in [8, 8192]"); return 1; }
+  return 0;
+}
+
+static int trace_commit_dev(zkl_ctx *ctx, const fe *trace_dev, size_t width, size_t n, const zkl_options *o, zkl_trace_lde *h) {
+  committed_matrix &m = h->m;
+  m.width = width; m.n = n; m.blowup = o->blowup; m.N = n * o->blowup;
+  ZKL_CHECK(ctx, m.polys.alloc(width * n));
+  ZKL_TRY(dev_interpolate(ctx, trace_dev, m.polys.p, width, n));
+  return commit_matrix(ctx, m, o);
+}
+
+extern "C" int zkl_trace_lde_commit(zkl_ctx *ctx, const zkl_fe *trace, size_t width, size_t n, const zkl_options *o,
+                                    uint8_t out_root[32], zkl_fe *out_polys, zkl_trace_lde **out_handle) {
+  ZKL_TRY(need_suite(ctx));
+  ZKL_TRY(check_opts(ctx, o, n));
+  zkl_trace_lde *h = new zkl_trace_lde();
+  dev_buf<fe> tr;
+  int rc = 0;
+  do {
+    if (tr.alloc(width * n) != cudaSuccess) { ctx->set_error("cudaMalloc(trace) failed"); rc = 1; break; }
+    if (cudaMemcpyAsync(tr.p, trace, width * n * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) { ctx->set_error("H2D failed"); rc = 1; break; }
+    if ((rc = trace_commit_dev(ctx, tr.p, width, n, o, h))) break;
+    fe root;
+    if (cudaMemcpyAsync(&root, h->m.nodes.p + 1, sizeof(fe), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) { ctx->set_error("D2H failed"); rc = 1; break; }
+    if (out_polys && cudaMemcpyAsync(out_polys, h->m.polys.p, width * n * sizeof(fe), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) { ctx->set_error("D2H failed"); rc = 1; break; }
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { ctx->set_error(std::string("trace commit: ") + cudaGetErrorString(cudaGetLastError())); rc = 1; break; }
+    digest_from_fe_host(root, out_root);
+  } while (0);
+  if (rc) { delete h; return rc; }
+  *out_handle = h;
+  return 0;
+}
+extern "C" void zkl_trace_lde_free(zkl_ctx *ctx, zkl_trace_lde *h) {
+  if (!h) return;
+  cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream);
+  delete h;
+}
+extern "C" int zkl_trace_lde_read_frame(zkl_ctx *ctx, const zkl_trace_lde *h, size_t lde_step, zkl_fe *out_cur, zkl_fe *out_next) {
+  ZKL_CHECK(ctx, cudaSetDevice(ctx->device));
+  const committed_matrix &m = h->m;
+  if (lde_step >= m.N) { ctx->set_error("lde_step out of range"); return 1; }
+  uint32_t pos[2] = {(uint32_t)lde_step, (uint32_t)((lde_step + m.blowup) % m.N)};
+  dev_buf<uint32_t> dp; dev_buf<fe> rows; ZKL_CHECK(ctx, dp.alloc(2)); ZKL_CHECK(ctx, rows.alloc(2 * m.width));
+  ZKL_CHECK(ctx, cudaMemcpyAsync(dp.p, pos, sizeof pos, cudaMemcpyHostToDevice, ctx->stream));
+  LAUNCH(ctx, k_gather_rows, ceil_div(2 * m.width, 128), 128, 0, m.lde.p, m.N, m.n, (int)m.blowup, (int)m.width, dp.p, 2, rows.p);
+  ZKL_CHECK(ctx, cudaMemcpyAsync(out_cur, rows.p, m.width * sizeof(fe), cudaMemcpyDeviceToHost, ctx->stream));
+  ZKL_CHECK(ctx, cudaMemcpyAsync(out_next, rows.p + m.width, m.width * sizeof(fe), cudaMemcpyDeviceToHost, ctx->stream));
+  ZKL_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Merkle batch openings (winter-crypto MerkleTree::prove_batch [WF-mem]) — pure index logic on the host.
+// Returns, per normalized leaf pair, the list of node references to ship: (is_leaf, index).
+// ------------------------------------------------------------------------------------------------
+struct node_ref { bool leaf; uint32_t index; };
+static std::vector<std::vector<node_ref>> batch_proof_plan(const std::vector<uint32_t> &indexes, size_t n_leaves) {
+  int depth = ilog2_sz(n_leaves);
+  std::vector<uint32_t> norm;
+  for (uint32_t i : indexes) norm.push_back(i & ~1u);
+  std::sort(norm.begin(), norm.end());
+  norm.erase(std::unique(norm.begin(), norm.end()), norm.end());
+  std::vector<std::vector<node_ref>> lists(norm.size());
+  std::vector<size_t> next;
+  for (size_t i = 0; i < norm.size(); i++) {
+    for (uint32_t j = norm[i]; j < norm[i] + 2; j++)
+      if (std::find(indexes.begin(), indexes.end(), j) == indexes.end()) lists[i].push_back({true, j});
+    next.push_back(((size_t)norm[i] + n_leaves) >> 1);
+  }
+  for (int d = 1; d < depth; d++) {
+    std::vector<size_t> cur = next; next.clear();
+    size_t i = 0;
+    while (i < cur.size()) {
+      size_t sib = cur[i] ^ 1;
+      if (i + 1 < cur.size() && cur[i + 1] == sib) i++;
+      else lists[i].push_back({false, (uint32_t)sib});
+      next.push_back(sib >> 1);
+      i++;
+    }
+  }
+  return lists;
+}
+// fetch the planned nodes from device (leaves / nodes arrays of elements) into digests
+static int fetch_batch_proof(zkl_ctx *ctx, const fe *leaves_dev, const fe *nodes_dev, const std::vector<std::vector<node_ref>> &plan,
+                             std::vector<std::vector<fe>> &out) {
+  // single gather over a concatenated index list: leaves and nodes live in separate buffers -> two gathers
+  std::vector<uint32_t> li, ni;
+  for (auto &l : plan) for (auto &r : l) (r.leaf ? li : ni).push_back(r.index);
+  std::vector<fe> lv(li.size()), nv(ni.size());
+  dev_buf<uint32_t> di; dev_buf<fe> dv;
+  auto gather = [&](const fe *src, std::vector<uint32_t> &idx, std::vector<fe> &dst) -> int {
+    if (idx.empty()) return 0;
+    ZKL_CHECK(ctx, di.alloc(idx.size())); ZKL_CHECK(ctx, dv.alloc(idx.size()));
+    ZKL_CHECK(ctx, cudaMemcpyAsync(di.p, idx.data(), idx.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    LAUNCH(ctx, k_gather_fe, ceil_div(idx.size(), 128), 128, 0, src, di.p, (int)idx.size(), dv.p);
+    ZKL_CHECK(ctx, cudaMemcpyAsync(dst.data(), dv.p, idx.size() * sizeof(fe), cudaMemcpyDeviceToHost, ctx->stream));
+    ZKL_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+  };
+  ZKL_TRY(gather(leaves_dev, li, lv));
+  ZKL_TRY(gather(nodes_dev, ni, nv));
+  size_t a = 0, b = 0;
+  out.clear();
+  for (auto &l : plan) {
+    std::vector<fe> v;
+    for (auto &r : l) v.push_back(r.leaf ? lv[a++] : nv[b++]);
+    out.push_back(v);
+  }
+  return 0;
+}
+
+static int query_matrix(zkl_ctx *ctx, const committed_matrix &m, const uint32_t *positions, size_t k, zkl_fe *out_rows,
+                        zkl_batch_proof *bp) {
+  ZKL_CHECK(ctx, cudaSetDevice(ctx->device));
+  std::vector<uint32_t> pos(positions, positions + k);
+  for (auto p : pos) if (p >= m.N) { ctx->set_error("query position out of range"); return 1; }
+  dev_buf<uint32_t> dp; dev_buf<fe> rows; ZKL_CHECK(ctx, dp.alloc(k)); ZKL_CHECK(ctx, rows.alloc(k * m.width));
+  ZKL_CHECK(ctx, cudaMemcpyAsync(dp.p, pos.data(), k * 4, cudaMemcpyHostToDevice, ctx->stream));
+  LAUNCH(ctx, k_gather_rows, ceil_div(k * m.width, 128), 128, 0, m.lde.p, m.N, m.n, (int)m.blowup, (int)m.width, dp.p, (int)k, rows.p);
+  ZKL_CHECK(ctx, cudaMemcpyAsync(out_rows, rows.p, k * m.width * sizeof(fe), cudaMemcpyDeviceToHost, ctx->stream));
+  ZKL_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  auto plan = batch_proof_plan(pos, m.N);
+  std::vector<std::vector<fe>> lists;
+  ZKL_TRY(fetch_batch_proof(ctx, m.leaves.p, m.nodes.p, plan, lists));
+  bp->depth = (uint8_t)ilog2_sz(m.N);
+  bp->num_lists = (uint32_t)lists.size();
+  uint32_t total = 0;
+  for (size_t i = 0; i < lists.size(); i++) {
+    bp->list_len[i] = (uint32_t)lists[i].size();
+    for (auto &d : lists[i]) { digest_from_fe_host(d, bp->nodes + 32 * (size_t)total); total++; }
+  }
+  bp->total_nodes = total;
+  return 0;
+}
+extern "C" int zkl_trace_query(zkl_ctx *ctx, const zkl_trace_lde *h, const uint32_t *positions, size_t k, zkl_fe *out_rows,
+                               zkl_batch_proof *out_proof) {
+  return query_matrix(ctx, h->m, positions, k, out_rows, out_proof);
+}
+extern "C" int zkl_constraint_query(zkl_ctx *ctx, const zkl_constraint_commitment *h, const uint32_t *positions, size_t k,
+                                    zkl_fe *out_rows, zkl_batch_proof *out_proof) {
+  return query_matrix(ctx, h->m, positions, k, out_rows, out_proof);
+}
+
+// ------------------------------------------------------------------------------------------------
+// constraint evaluation (hook 2)
+// ------------------------------------------------------------------------------------------------
+struct air_device_state {
+  dev_buf<air_dev> air;
+  dev_buf<assertion_dev> as;
+  dev_buf<uint32_t> group_start, slot_col;
+  dev_buf<fe> per, coset_consts, u, bpoly_coef, bpoly;
+  int nslots = 0, ngroups = 0;
+};
+
+static int upload_air(zkl_ctx *ctx, const zkl_air_params *a, size_t n, air_device_state &st) {
+  if (a->cols.width > 255) { ctx->set_error("trace width must fit in u8 (winterfell TraceInfo)"); return 1; }
+  air_dev h; memset(&h, 0, sizeof h);
+  h.cols = a->cols;
+  h.f_poseidon = a->f_poseidon; h.f_vm = a->f_vm; h.f_sponge = a->f_sponge; h.f_merkle = a->f_merkle; h.f_ram = a->f_ram;
+  h.rom_enabled = a->rom_enabled; h.vm_usage_mask = a->vm_usage_mask; h.ram_delta_clk_bits = a->ram_delta_clk_bits;
+  h.num_transition = a->num_transition;
+  for (int i = 0; i < 12; i++) for (int j = 0; j < 12; j++) h.pose_mds[i][j] = fe_from_abi(a->pose.mds[i][j]);
+  for (int r = 0; r < ZKL_ROUNDS; r++) for (int j = 0; j < 12; j++) h.pose_rc[r][j] = fe_from_abi(a->pose.rc[r][j]);
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) h.rom_mds[i][j] = fe_from_abi(a->rom.mds[i][j]);
+  for (int r = 0; r < ZKL_ROUNDS; r++) for (int j = 0; j < 3; j++) h.rom_rc[r][j] = fe_from_abi(a->rom.rc[r][j]);
+  for (int k = 0; k < 59; k++) { h.rom_w0[k] = fe_from_abi(a->rom_w_enc0[k]); h.rom_w1[k] = fe_from_abi(a->rom_w_enc1[k]); }
+  h.program_fe0 = fe_from_abi(a->program_fe0); h.merkle_root_fe = fe_from_abi(a->merkle_root_fe);
+  ZKL_CHECK(ctx, st.air.alloc(1));
+  ZKL_CHECK(ctx, cudaMemcpyAsync(st.air.p, &h, sizeof h, cudaMemcpyHostToDevice, ctx->stream));
+  // assertions: Winterfell order = sorted by (stride, first_step, column); single assertions have stride 0 [WF-mem]
+  std::vector<uint32_t> order(a->num_assertions);
+  for (uint32_t i = 0; i < a->num_assertions; i++) order[i] = i;
+  std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) {
+    const zkl_assertion &p = a->assertions[x], &q = a->assertions[y];
+    return p.step != q.step ? p.step < q.step : p.column < q.column;
+  });
+  std::map<uint32_t, uint32_t> slot_of;  // column -> slot
+  std::vector<uint32_t> slot_col;
+  std::vector<assertion_dev> as(a->num_assertions);
+  std::vector<uint32_t> gs;
+  for (uint32_t q = 0; q < a->num_assertions; q++) {
+    const zkl_assertion &x = a->assertions[order[q]];
+    if (x.column >= a->cols.width || x.step >= n) { ctx->set_error("assertion outside the trace"); return 1; }
+    auto it = slot_of.find(x.column);
+    if (it == slot_of.end()) { it = slot_of.emplace(x.column, (uint32_t)slot_col.size()).first; slot_col.push_back(x.column); }
+    as[q].slot = it->second; as[q].step = x.step; as[q].cc_index = a->num_transition + q; as[q].pad = 0;
+    as[q].value = fe_from_abi(x.value);
+    if (q == 0 || x.step != a->assertions[order[q - 1]].step) gs.push_back(q);
+  }
+  gs.push_back(a->num_assertions);
+  st.nslots = (int)slot_col.size(); st.ngroups = (int)gs.size() - 1;
+  ZKL_CHECK(ctx, st.as.alloc(std::max<size_t>(as.size(), 1)));
+  ZKL_CHECK(ctx, st.group_start.alloc(gs.size()));
+  ZKL_CHECK(ctx, st.slot_col.alloc(std::max<size_t>(slot_col.size(), 1)));
+  if (!as.empty()) ZKL_CHECK(ctx, cudaMemcpyAsync(st.as.p, as.data(), as.size() * sizeof(assertion_dev), cudaMemcpyHostToDevice, ctx->stream));
+  ZKL_CHECK(ctx, cudaMemcpyAsync(st.group_start.p, gs.data(), gs.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+  if (!slot_col.empty()) ZKL_CHECK(ctx, cudaMemcpyAsync(st.slot_col.p, slot_col.data(), slot_col.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+  // the host vectors must outlive the async copies
+  ZKL_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+// cc_dev: num_transition + num_assertions coefficients on the device. ce_out: ce*n evaluations, coset-major.
+static int dev_eval_constraints(zkl_ctx *ctx, const committed_matrix &t, const zkl_air_params *a, air_device_state &st, const fe *cc_dev,
+                                fe *ce_out) {
+  size_t n = t.n, ce = a->ce_blowup, M = n * ce, N = t.N;
+  if (ce > t.blowup || ce > 16 || (ce & (ce - 1))) { ctx->set_error("ce_blowup must be a power of two <= min(blowup, 16)"); return 1; }
+  if (n < 32) { ctx->set_error("trace length must be >= 32 (one schedule level)"); return 1; }
+  domain_tables *tN, *tM, *tn;
+  ZKL_TRY(get_tables(ctx, N, &tN)); ZKL_TRY(get_tables(ctx, M, &tM)); ZKL_TRY(get_tables(ctx, n, &tn));
+  // periodic table
+  ZKL_CHECK(ctx, st.per.alloc(ce * 32 * 31));
+  fe g = fe_from_u64(3);
+  LAUNCH(ctx, k_periodic_table, ceil_div(ce * 32, 64), 64, 0, st.per.p, (int)ce, (int)n, tM->wpow, M, fe_pow(g, n / 32), fe_inv(fe_from_u64(32)));
+  // per-coset constants: x^n = g^n * w_ce^k'
+  std::vector<fe> cconst(2 * ce + 2);
+  fe gn = fe_pow(g, n), wce = host_root_of_unity(ilog2_sz(ce)), wk = fe_one();
+  for (size_t k = 0; k < ce; k++) {
+    fe xn1 = fe_sub(fe_mul(gn, wk), fe_one());
+    cconst[2 * k] = fe_inv(xn1); cconst[2 * k + 1] = xn1;
+    wk = fe_mul(wk, wce);
+  }
+  cconst[2 * ce] = fe_inv(fe_from_u64(n)); cconst[2 * ce + 1] = fe_from_u64(n);
+  ZKL_CHECK(ctx, st.coset_consts.alloc(cconst.size()));
+  ZKL_CHECK(ctx, cudaMemcpyAsync(st.coset_consts.p, cconst.data(), cconst.size() * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream));
+  ZKL_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  // boundary polynomials: scatter -> iNTT -> coset LDE over the CE domain
+  size_t nb = (size_t)st.nslots + 1;
+  ZKL_CHECK(ctx, st.u.alloc(nb * n)); ZKL_CHECK(ctx, st.bpoly.alloc(nb * M));
+  ZKL_CHECK(ctx, cudaMemsetAsync(st.u.p, 0, nb * n * sizeof(fe), ctx->stream));
+  if (st.ngroups) LAUNCH(ctx, k_boundary_scatter, ceil_div(st.ngroups, 128), 128, 0, st.as.p, st.group_start.p, st.ngroups, cc_dev, tn->wpow, (int)n, st.nslots, st.u.p);
+  ZKL_TRY(dev_interpolate(ctx, st.u.p, st.u.p, nb, n));
+  ZKL_TRY(dev_lde(ctx, st.u.p, st.bpoly.p, nb, n, ce));
+  boundary_dev bd{st.slot_col.p, st.bpoly.p, st.nslots};
+  LAUNCH(ctx, k_eval_constraints, ceil_div(M, 128), 128, 0, st.air.p, t.lde.p, N, (int)n, (int)t.blowup, (int)ce, st.per.p, tN->wpow, cc_dev, bd,
+         st.coset_consts.p, ce_out);
+  return 0;
+}
+
+// coset-major CE evaluations -> natural order (CompositionPolyTrace order) and back
+__global__ void k_ce_to_natural(const fe *__restrict__ cm, fe *__restrict__ nat, int n, int ce, int to_natural) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * ce) return;
+  int kp = t / n, i = t - kp * n;
+  int j = kp + ce * i;
+  if (to_natural) st_fe(nat + j, ld_fe(cm + t)); else st_fe(nat + t, ld_fe(cm + j));
+}
+
+extern "C" int zkl_eval_constraints(zkl_ctx *ctx, const zkl_trace_lde *h, const zkl_air_params *air, const zkl_fe *coeffs, zkl_fe *out_ce) {
+  ZKL_TRY(need_suite(ctx));
+  const committed_matrix &t = h->m;
+  if (air->cols.width != t.width) { ctx->set_error("air width does not match the committed trace"); return 1; }
+  air_device_state st;
+  ZKL_TRY(upload_air(ctx, air, t.n, st));
+  size_t ncc = (size_t)air->num_transition + air->num_assertions, M = t.n * air->ce_blowup;
+  dev_buf<fe> cc, ce, nat; ZKL_CHECK(ctx, cc.alloc(ncc)); ZKL_CHECK(ctx, ce.alloc(M)); ZKL_CHECK(ctx, nat.alloc(M));
+  ZKL_CHECK(ctx, cudaMemcpyAsync(cc.p, coeffs, ncc * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream));
+  ZKL_TRY(dev_eval_constraints(ctx, t, air, st, cc.p, ce.p));
+  LAUNCH(ctx, k_ce_to_natural, ceil_div(M, 256), 256, 0, ce.p, nat.p, (int)t.n, (int)air->ce_blowup, 1);
+  ZKL_CHECK(ctx, cudaMemcpyAsync(out_ce, nat.p, M * sizeof(fe), cudaMemcpyDeviceToHost, ctx->stream));
+  ZKL_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// constraint commitment (hook 3)
+// ------------------------------------------------------------------------------------------------
+// ce_cm: coset-major CE evaluations (ce x n) on device; fills m.polys (num_cols x n) and commits.
+static int dev_constraint_commit(zkl_ctx *ctx, fe *ce_cm, size_t n, size_t ce, size_t num_cols, const zkl_options *o, committed_matrix &m,
+                                 fe *overflow_flag) {
+  size_t M = n * ce;
+  domain_tables *tM; ZKL_TRY(get_tables(ctx, M, &tM));
+  m.width = num_cols; m.n = n; m.blowup = o->blowup; m.N = n * o->blowup;
+  ZKL_CHECK(ctx, m.polys.alloc(num_cols * n));
+  ZKL_TRY(dev_interpolate(ctx, ce_cm, ce_cm, ce, n));  // per-coset inverse NTT in place
+  auto it = ctx->opow.find(n | ((size_t)1 << 62));
+  if (it == ctx->opow.end()) {
+    fe *p; ZKL_CHECK(ctx, cudaMalloc((void **)&p, n * sizeof(fe)));
+    LAUNCH(ctx, k_fill_powers, ceil_div(n, 256), 256, 0, fe_inv(fe_from_u64(3)), p, n);
+    it = ctx->opow.emplace(n | ((size_t)1 << 62), p).first;
+  }
+  fe ginv_n = fe_pow(fe_inv(fe_from_u64(3)), n);
+  LAUNCH(ctx, k_composition_finish, ceil_div(n, 128), 128, 0, ce_cm, (int)n, (int)ce, (int)num_cols, tM->wpow, M, it->second, ginv_n,
+         fe_inv(fe_from_u64(ce)), m.polys.p, overflow_flag);
+  return commit_matrix(ctx, m, o);
+}
+
+extern "C" int zkl_constraint_commit(zkl_ctx *ctx, const zkl_fe *ce_evals, size_t n, size_t ce_blowup, size_t num_cols, const zkl_options *o,
+                                     uint8_t out_root[32], zkl_fe *out_poly, zkl_constraint_commitment **out_handle) {
+  ZKL_TRY(need_suite(ctx));
+  ZKL_TRY(check_opts(ctx, o, n));
+  if (num_cols > ce_blowup || ce_blowup > 16) { ctx->set_error("num_cols must be <= ce_blowup <= 16"); return 1; }
+  size_t M = n * ce_blowup;
+  zkl_constraint_commitment *h = new zkl_constraint_commitment();
+  dev_buf<fe> nat, cm, flag;
+  int rc = 1;
+  do {
+    if (nat.alloc(M) != cudaSuccess || cm.alloc(M) != cudaSuccess || flag.alloc(1) != cudaSuccess) { ctx->set_error("cudaMalloc failed"); break; }
+    if (cudaMemcpyAsync(nat.p, ce_evals, M * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) { ctx->set_error("H2D failed"); break; }
+    cudaMemsetAsync(flag.p, 0, sizeof(fe), ctx->stream);
+    k_ce_to_natural<<<ceil_div(M, 256), 256, 0, ctx->stream>>>(nat.p, cm.p, (int)n, (int)ce_blowup, 0); ctx->launches++;
+    if ((rc = dev_constraint_commit(ctx, cm.p, n, ce_blowup, num_cols, o, h->m, flag.p))) break;
+    rc = 1;
+    fe root;
+    if (cudaMemcpyAsync(&root, h->m.nodes.p + 1, sizeof(fe), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) { ctx->set_error("D2H failed"); break; }
+    if (out_poly && cudaMemcpyAsync(out_poly, h->m.polys.p, num_cols * n * sizeof(fe), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) { ctx->set_error("D2H failed"); break; }
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { ctx->set_error(std::string("constraint commit: ") + cudaGetErrorString(cudaGetLastError())); break; }
+    digest_from_fe_host(root, out_root);
+    rc = 0;
+  } while (0);
+  if (rc) { delete h; return rc; }
+  *out_handle = h;
+  return 0;
+}
+extern "C" void zkl_constraint_commitment_free(zkl_ctx *ctx, zkl_constraint_commitment *h) {
+  if (!h) return;
+  cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream);
+  delete h;
+}
+
+// ------------------------------------------------------------------------------------------------
+// winterfell::Proof serialization (winter-air / winter-utils byte formats [WF-mem]) — byte shuffling only
+// ------------------------------------------------------------------------------------------------
+struct byte_writer {
+  std::vector<uint8_t> b;
+  void u8(uint8_t v) { b.push_back(v); }
+  void u16(uint16_t v) { u8((uint8_t)v); u8((uint8_t)(v >> 8)); }
+  void u32(uint32_t v) { for (int i = 0; i < 4; i++) u8((uint8_t)(v >> (8 * i))); }
+  void u64(uint64_t v) { for (int i = 0; i < 8; i++) u8((uint8_t)(v >> (8 * i))); }
+  void bytes(const void *p, size_t n) { const uint8_t *q = (const uint8_t *)p; b.insert(b.end(), q, q + n); }
+  void usize(uint64_t value) {  // winter-utils write_usize (vint64)
+    int zeros = value == 0 ? 64 : __builtin_clzll(value);
+    int len = (zeros > 0 ? zeros - 1 : 0) / 7; if (len > 8) len = 8;
+    int length = 9 - len;
+    if (length == 9) { u8(0); u64(value); }
+    else { uint64_t enc = ((value << 1) | 1) << (length - 1); for (int i = 0; i < length; i++) u8((uint8_t)(enc >> (8 * i))); }
+  }
+  void digest(const fe &x) { bytes(x.l, 16); for (int i = 0; i < 16; i++) u8(0); }
+  void felt(const fe &x) { bytes(x.l, 16); }
+};
+static void write_batch_proof_bytes(byte_writer &w, int depth, const std::vector<std::vector<fe>> &lists) {
+  w.u8((uint8_t)depth); w.usize(lists.size());
+  for (auto &l : lists) { w.usize(l.size()); for (auto &d : l) w.digest(d); }
+}
+static void write_context_bytes(byte_writer &w, size_t W, size_t n, const zkl_options &o, size_t num_constraints) {
+  static const uint8_t modulus_le[16] = {0x01, 0x00, 0x00, 0x00, 0x00, 0xd3, 0xff, 0xff, 0xff, 0xff, 0xff, 0xff, 0xff, 0xff, 0xff, 0xff};
+  w.u8((uint8_t)W); w.u8(0); w.u8((uint8_t)ilog2_sz(n)); w.u16(0);
+  w.u8(16); w.bytes(modulus_le, 16);
+  w.usize(num_constraints);
+  w.u8((uint8_t)o.num_queries); w.u8((uint8_t)o.blowup); w.u8((uint8_t)o.grinding); w.u8(1);
+  w.u8((uint8_t)o.fri_folding); w.u8((uint8_t)o.fri_remainder_max_degree); w.u8(0); w.u8(0);
+  w.u8((uint8_t)o.num_partitions); w.u8((uint8_t)o.hash_rate);
+}
+static size_t fri_num_layers(size_t domain, const zkl_options &o) {  // FriOptions::num_fri_layers [WF-mem]
+  size_t max_rem = (size_t)(o.fri_remainder_max_degree + 1) * o.blowup, r = 0;
+  while (domain > max_rem) { domain /= o.fri_folding; r++; }
+  return r;
+}
+static std::vector<uint32_t> fold_positions_host(const std::vector<uint32_t> &pos, size_t src_domain) {  // agg/child.rs:1072-1099
+  size_t tgt = src_domain / 2;
+  std::vector<uint32_t> r;
+  for (uint32_t p : pos) { uint32_t i = (uint32_t)(p % tgt); if (std::find(r.begin(), r.end(), i) == r.end()) r.push_back(i); }
+  return r;
+}
+
+static const char *k_stage_names[12] = {"coin_seed", "trace_lde_commit", "constraint_eval", "constraint_commit", "ood", "deep",
+                                        "fri", "grind", "queries_serialize", "", "", ""};
+extern "C" const char *zkl_stage_name(int s) { return (s >= 0 && s < 12) ? k_stage_names[s] : ""; }
+
+// ------------------------------------------------------------------------------------------------
+// whole-segment prover: winterfell::Prover::prove, stages 1-11, everything on the device
+// ------------------------------------------------------------------------------------------------
+static int prove_segment_impl(zkl_ctx *ctx, const fe *trace_dev, size_t W, size_t n, const zkl_air_params *air, const zkl_fe *seed_elems,
+                              size_t num_seed, const zkl_options *o, uint8_t *out_proof, size_t *out_len, zkl_proof_summary *summary) {
+  ZKL_TRY(need_suite(ctx));
+  ZKL_TRY(check_opts(ctx, o, n));
+  if (air->cols.width != W) { ctx->set_error("air width does not match the trace"); return 1; }
+  if (o->num_queries == 0 || o->num_queries > 255) { ctx->set_error("num_queries must be in [1,255]"); return 1; }
+  const size_t B = o->blowup, N = n * B, ce = air->ce_blowup, M = n * ce, C = air->num_composition_cols;
+  const size_t ncc = (size_t)air->num_transition + air->num_assertions;
+  const size_t nl = fri_num_layers(N, *o);
+  if (nl + 1 > 40) { ctx->set_error("too many FRI layers"); return 1; }
+  while (ctx->ev.size() < 12) { cudaEvent_t e; ZKL_CHECK(ctx, cudaEventCreate(&e)); ctx->ev.push_back(e); }
+  domain_tables *tN; ZKL_TRY(get_tables(ctx, N, &tN));
+  fe *opow; ZKL_TRY(get_offset_powers(ctx, n, &opow)); (void)opow;
+  cudaStream_t st = ctx->stream;
+  int evi = 0;
+#define STAGE_MARK() ZKL_CHECK(ctx, cudaEventRecord(ctx->ev[evi++], st))
+  STAGE_MARK();
+
+  // ---- 1. public coin seed (agg/fs.rs:69-73)
+  dev_buf<fe> seed_in, coin, tmp;
+  ZKL_CHECK(ctx, seed_in.alloc(num_seed)); ZKL_CHECK(ctx, coin.alloc(1)); ZKL_CHECK(ctx, tmp.alloc(8));
+  ZKL_CHECK(ctx, cudaMemcpyAsync(seed_in.p, seed_elems, num_seed * sizeof(fe), cudaMemcpyHostToDevice, st));
+  LAUNCH(ctx, k_coin_init, 1, ZKL_COOP_GROUP, 0, seed_in.p, (int)num_seed, coin.p);
+  STAGE_MARK();
+
+  // ---- 2. trace LDE + commitment (hook new_trace_lde), reseed with the root
+  zkl_trace_lde tl;
+  ZKL_TRY(trace_commit_dev(ctx, trace_dev, W, n, o, &tl));
+  LAUNCH(ctx, k_coin_reseed, 1, ZKL_COOP_GROUP, 0, coin.p, tl.m.nodes.p + 1);
+  STAGE_MARK();
+
+  // ---- 4/5. composition coefficients (transition then boundary) and constraint evaluation
+  air_device_state ast;
+  ZKL_TRY(upload_air(ctx, air, n, ast));
+  dev_buf<fe> cc, ce_ev, flag;
+  ZKL_CHECK(ctx, cc.alloc(ncc)); ZKL_CHECK(ctx, ce_ev.alloc(M)); ZKL_CHECK(ctx, flag.alloc(1));
+  ZKL_CHECK(ctx, cudaMemsetAsync(flag.p, 0, sizeof(fe), st));
+  LAUNCH(ctx, k_coin_draw, ceil_div(ncc * ZKL_COOP_GROUP, ZKL_COOP_THREADS), ZKL_COOP_THREADS, 0, coin.p, (uint64_t)0, (int)ncc, cc.p);
+  ZKL_TRY(dev_eval_constraints(ctx, tl.m, air, ast, cc.p, ce_ev.p));
+  STAGE_MARK();
+
+  // ---- 6. constraint commitment (hook build_constraint_commitment), reseed
+  zkl_constraint_commitment cmt;
+  ZKL_TRY(dev_constraint_commit(ctx, ce_ev.p, n, ce, C, o, cmt.m, flag.p));
+  LAUNCH(ctx, k_coin_reseed, 1, ZKL_COOP_GROUP, 0, coin.p, cmt.m.nodes.p + 1);
+  STAGE_MARK();
+
+  // ---- 7. OOD point z, evaluations at z and z*g, reseed with hash_elements(cur(z)||quot(z)||next(zg)||quot(zg))
+  dev_buf<fe> z, zpow, ood, ood_digest;
+  ZKL_CHECK(ctx, z.alloc(1)); ZKL_CHECK(ctx, zpow.alloc(2 * n)); ZKL_CHECK(ctx, ood.alloc(2 * (W + C))); ZKL_CHECK(ctx, ood_digest.alloc(1));
+  LAUNCH(ctx, k_coin_draw, 1, ZKL_COOP_THREADS, 0, coin.p, (uint64_t)0, 1, z.p);
+  fe g_n = host_root_of_unity(ilog2_sz(n));
+  LAUNCH(ctx, k_powers_dev, ceil_div(n, 128), 128, 0, z.p, fe_one(), zpow.p, (int)n);
+  LAUNCH(ctx, k_powers_dev, ceil_div(n, 128), 128, 0, z.p, g_n, zpow.p + n, (int)n);
+  LAUNCH(ctx, k_poly_eval, (unsigned)W, 256, 0, tl.m.polys.p, (int)n, zpow.p, ood.p);
+  LAUNCH(ctx, k_poly_eval, (unsigned)C, 256, 0, cmt.m.polys.p, (int)n, zpow.p, ood.p + W);
+  LAUNCH(ctx, k_poly_eval, (unsigned)W, 256, 0, tl.m.polys.p, (int)n, zpow.p + n, ood.p + W + C);
+  LAUNCH(ctx, k_poly_eval, (unsigned)C, 256, 0, cmt.m.polys.p, (int)n, zpow.p + n, ood.p + 2 * W + C);
+  LAUNCH(ctx, k_hash_elements_single, 1, ZKL_COOP_GROUP, 0, ood.p, (int)(2 * (W + C)), ood_digest.p);
+  LAUNCH(ctx, k_coin_reseed, 1, ZKL_COOP_GROUP, 0, coin.p, ood_digest.p);
+  STAGE_MARK();
+
+  // ---- 8. DEEP coefficients + composition over the LDE domain
+  dev_buf<fe> dc, az, deep;
+  ZKL_CHECK(ctx, dc.alloc(W + C)); ZKL_CHECK(ctx, az.alloc(2)); ZKL_CHECK(ctx, deep.alloc(N));
+  LAUNCH(ctx, k_coin_draw, ceil_div((W + C) * ZKL_COOP_GROUP, ZKL_COOP_THREADS), ZKL_COOP_THREADS, 0, coin.p, (uint64_t)0, (int)(W + C), dc.p);
+  LAUNCH(ctx, k_deep_consts, 1, 32, 0, ood.p, dc.p, (int)W, (int)C, az.p);
+  LAUNCH(ctx, k_deep, ceil_div(N, 256), 256, 0, tl.m.lde.p, cmt.m.lde.p, N, (int)n, (int)B, (int)W, (int)C, dc.p, az.p, z.p, g_n, tN->wpow, deep.p);
+  STAGE_MARK();
+
+  // ---- 9. FRI layers
+  std::vector<dev_buf<fe>> f_ev(nl + 1), f_leaves(nl), f_nodes(nl);
+  dev_buf<fe> alphas, fri_roots, rem_rev;
+  ZKL_CHECK(ctx, alphas.alloc(nl + 1)); ZKL_CHECK(ctx, fri_roots.alloc(nl + 1));
+  fe g_inv_half = fe_inv(fe_from_u64(6));
+  const fe *cur_ev = deep.p;
+  size_t nd = n;
+  for (size_t d = 0; d < nl; d++) {
+    size_t half = nd * B / 2;
+    ZKL_CHECK(ctx, f_leaves[d].alloc(half)); ZKL_CHECK(ctx, f_nodes[d].alloc(half)); ZKL_CHECK(ctx, f_ev[d + 1].alloc(half));
+    LAUNCH(ctx, k_fri_leaves, ceil_div(half * ZKL_COOP_GROUP, ZKL_COOP_THREADS), ZKL_COOP_THREADS, 0, cur_ev, (int)nd, (int)B, f_leaves[d].p);
+    ZKL_TRY(dev_merkle(ctx, f_leaves[d].p, f_nodes[d].p, half));
+    ZKL_CHECK(ctx, cudaMemcpyAsync(fri_roots.p + d, f_nodes[d].p + 1, sizeof(fe), cudaMemcpyDeviceToDevice, st));
+    LAUNCH(ctx, k_coin_reseed, 1, ZKL_COOP_GROUP, 0, coin.p, f_nodes[d].p + 1);
+    LAUNCH(ctx, k_coin_draw, 1, ZKL_COOP_THREADS, 0, coin.p, (uint64_t)0, 1, alphas.p + d);
+    LAUNCH(ctx, k_fri_fold, ceil_div(half, 256), 256, 0, cur_ev, (int)nd, (int)B, (int)d, alphas.p + d, tN->wpow, N, g_inv_half, f_ev[d + 1].p);
+    cur_ev = f_ev[d + 1].p;
+    nd /= 2;
+  }
+  size_t rem_len = nd;  // (B*nd)/B coefficients
+  ZKL_CHECK(ctx, rem_rev.alloc(rem_len));
+  if (nd * B > 256) { ctx->set_error("FRI remainder domain too large"); return 1; }
+  LAUNCH(ctx, k_fri_remainder, 1, 32 > (int)nd ? 32 : (int)nd, 0, cur_ev, (int)nd, (int)B, tN->wpow, N, fe_inv(fe_from_u64(3)),
+         fe_inv(fe_from_u64(nd * B)), rem_rev.p);
+  LAUNCH(ctx, k_hash_elements_single, 1, ZKL_COOP_GROUP, 0, rem_rev.p, (int)rem_len, fri_roots.p + nl);
+  LAUNCH(ctx, k_coin_reseed, 1, ZKL_COOP_GROUP, 0, coin.p, fri_roots.p + nl);
+  STAGE_MARK();
+
+  // ---- 10. grinding (smallest nonce >= 1)
+  dev_buf<unsigned long long> nonce;
+  ZKL_CHECK(ctx, nonce.alloc(1));
+  unsigned long long nonce_h = 0;
+  if (o->grinding > 0) {
+    if (o->grinding > 40) { ctx->set_error("grinding factor too large"); return 1; }
+    ZKL_CHECK(ctx, cudaMemsetAsync(nonce.p, 0xFF, 8, st));
+    const uint32_t batch = 1u << 15;
+    uint64_t base = 1;
+    for (;;) {
+      // enough back-to-back batches to cover 16x the expected nonce without a host round trip
+      uint64_t target = (uint64_t)16 << o->grinding;
+      int nb = (int)std::min<uint64_t>(std::max<uint64_t>(target / batch, 1), 512);
+      for (int b = 0; b < nb; b++, base += batch)
+        LAUNCH(ctx, k_grind, ceil_div((size_t)batch * ZKL_COOP_GROUP, ZKL_COOP_THREADS), ZKL_COOP_THREADS, 0, coin.p, base, batch, o->grinding, nonce.p);
+      ZKL_CHECK(ctx, cudaMemcpyAsync(&nonce_h, nonce.p, 8, cudaMemcpyDeviceToHost, st));
+      ZKL_CHECK(ctx, cudaStreamSynchronize(st));
+      if (nonce_h != ~0ull) break;
+    }
+  } else {
+    ZKL_CHECK(ctx, cudaMemsetAsync(nonce.p, 0, 8, st));
+  }
+  STAGE_MARK();
+
+  // ---- 11. query positions, openings, serialization
+  dev_buf<uint32_t> pos_dev, pos_cnt;
+  ZKL_CHECK(ctx, pos_dev.alloc(256)); ZKL_CHECK(ctx, pos_cnt.alloc(1));
+  LAUNCH(ctx, k_draw_positions, 1, ZKL_COOP_THREADS, 0, coin.p, nonce.p, (int)o->num_queries, (uint32_t)(N - 1), pos_dev.p, pos_cnt.p);
+  uint32_t pos_h[256], cnt_h = 0;
+  std::vector<fe> ood_h(2 * (W + C)), roots_h(nl + 1), rem_h(rem_len);
+  fe troot, croot, z_h, flag_h;
+  ZKL_CHECK(ctx, cudaMemcpyAsync(pos_h, pos_dev.p, sizeof pos_h, cudaMemcpyDeviceToHost, st));
+  ZKL_CHECK(ctx, cudaMemcpyAsync(&cnt_h, pos_cnt.p, 4, cudaMemcpyDeviceToHost, st));
+  ZKL_CHECK(ctx, cudaMemcpyAsync(ood_h.data(), ood.p, ood_h.size() * sizeof(fe), cudaMemcpyDeviceToHost, st));
+  ZKL_CHECK(ctx, cudaMemcpyAsync(roots_h.data(), fri_roots.p, roots_h.size() * sizeof(fe), cudaMemcpyDeviceToHost, st));
+  ZKL_CHECK(ctx, cudaMemcpyAsync(rem_h.data(), rem_rev.p, rem_len * sizeof(fe), cudaMemcpyDeviceToHost, st));
+  ZKL_CHECK(ctx, cudaMemcpyAsync(&troot, tl.m.nodes.p + 1, sizeof(fe), cudaMemcpyDeviceToHost, st));
+  ZKL_CHECK(ctx, cudaMemcpyAsync(&croot, cmt.m.nodes.p + 1, sizeof(fe), cudaMemcpyDeviceToHost, st));
+  ZKL_CHECK(ctx, cudaMemcpyAsync(&z_h, z.p, sizeof(fe), cudaMemcpyDeviceToHost, st));
+  ZKL_CHECK(ctx, cudaMemcpyAsync(&flag_h, flag.p, sizeof(fe), cudaMemcpyDeviceToHost, st));
+  ZKL_CHECK(ctx, cudaStreamSynchronize(st));
+  std::vector<uint32_t> pos(pos_h, pos_h + cnt_h);
+
+  byte_writer wr;
+  write_context_bytes(wr, W, n, *o, ncc);
+  wr.u8((uint8_t)pos.size());
+  wr.u16((uint16_t)(32 * (2 + nl + 1)));
+  wr.digest(troot); wr.digest(croot);
+  for (auto &r : roots_h) wr.digest(r);
+  auto write_queries = [&](const committed_matrix &m) -> int {
+    std::vector<fe> rows(pos.size() * m.width);
+    dev_buf<fe> drows; ZKL_CHECK(ctx, drows.alloc(rows.size()));
+    LAUNCH(ctx, k_gather_rows, ceil_div(rows.size(), 128), 128, 0, m.lde.p, m.N, m.n, (int)m.blowup, (int)m.width, pos_dev.p, (int)pos.size(), drows.p);
+    ZKL_CHECK(ctx, cudaMemcpyAsync(rows.data(), drows.p, rows.size() * sizeof(fe), cudaMemcpyDeviceToHost, st));
+    ZKL_CHECK(ctx, cudaStreamSynchronize(st));
+    std::vector<std::vector<fe>> lists;
+    ZKL_TRY(fetch_batch_proof(ctx, m.leaves.p, m.nodes.p, batch_proof_plan(pos, m.N), lists));
+    byte_writer pw; write_batch_proof_bytes(pw, ilog2_sz(m.N), lists);
+    wr.usize(rows.size() * 16); wr.bytes(rows.data(), rows.size() * 16);
+    wr.usize(pw.b.size()); wr.bytes(pw.b.data(), pw.b.size());
+    return 0;
+  };
+  ZKL_TRY(write_queries(tl.m));
+  ZKL_TRY(write_queries(cmt.m));
+  // OodFrame: trace states (current || next), constraint evaluations (current || next)
+  wr.u16((uint16_t)(2 * W * 16));
+  wr.bytes(ood_h.data(), W * 16); wr.bytes(ood_h.data() + W + C, W * 16);
+  wr.u16((uint16_t)(2 * C * 16));
+  wr.bytes(ood_h.data() + W, C * 16); wr.bytes(ood_h.data() + 2 * W + C, C * 16);
+  // FriProof
+  wr.u8((uint8_t)nl);
+  {
+    std::vector<uint32_t> fp = pos; size_t dom = N;
+    const fe *ev = deep.p; size_t ndl = n;
+    for (size_t d = 0; d < nl; d++) {
+      fp = fold_positions_host(fp, dom);
+      size_t half = dom / 2, half_rows = ndl / 2;
+      // values: for position p (natural, < half): ev[p], ev[p + half] ; storage index of natural r: (r % B)*ndl + r / B
+      std::vector<uint32_t> idx;
+      for (uint32_t p : fp) {
+        uint32_t s0 = (uint32_t)((p % B) * ndl + p / B);
+        idx.push_back(s0); idx.push_back(s0 + (uint32_t)half_rows);
+      }
+      std::vector<fe> vals(idx.size());
+      dev_buf<uint32_t> di; dev_buf<fe> dv; ZKL_CHECK(ctx, di.alloc(idx.size())); ZKL_CHECK(ctx, dv.alloc(idx.size()));
+      ZKL_CHECK(ctx, cudaMemcpyAsync(di.p, idx.data(), idx.size() * 4, cudaMemcpyHostToDevice, st));
+      LAUNCH(ctx, k_gather_fe, ceil_div(idx.size(), 128), 128, 0, ev, di.p, (int)idx.size(), dv.p);
+      ZKL_CHECK(ctx, cudaMemcpyAsync(vals.data(), dv.p, vals.size() * sizeof(fe), cudaMemcpyDeviceToHost, st));
+      ZKL_CHECK(ctx, cudaStreamSynchronize(st));
+      std::vector<std::vector<fe>> lists;
+      ZKL_TRY(fetch_batch_proof(ctx, f_leaves[d].p, f_nodes[d].p, batch_proof_plan(fp, half), lists));
+      byte_writer pw; write_batch_proof_bytes(pw, ilog2_sz(half), lists);
+      wr.u32((uint32_t)(vals.size() * 16)); wr.bytes(vals.data(), vals.size() * 16);
+      wr.u32((uint32_t)pw.b.size()); wr.bytes(pw.b.data(), pw.b.size());
+      ev = f_ev[d + 1].p; dom = half; ndl = half_rows;
+    }
+  }
+  wr.u16((uint16_t)(rem_len * 16));
+  for (auto &c : rem_h) wr.felt(c);
+  wr.u8(1);
+  wr.u64(nonce_h);
+  STAGE_MARK();
+#undef STAGE_MARK
+
+  if (summary) {
+    memset(summary, 0, sizeof *summary);
+    digest_from_fe_host(troot, summary->trace_root);
+    digest_from_fe_host(croot, summary->constraint_root);
+    summary->num_fri_roots = (uint32_t)(nl + 1);
+    for (size_t i = 0; i <= nl; i++) digest_from_fe_host(roots_h[i], summary->fri_roots + 32 * i);
+    memcpy(&summary->z, z_h.l, 16);
+    summary->pow_nonce = nonce_h;
+    summary->num_unique_queries = (uint32_t)pos.size();
+    for (size_t i = 0; i < pos.size(); i++) summary->positions[i] = pos[i];
+    ZKL_CHECK(ctx, cudaEventSynchronize(ctx->ev[evi - 1]));
+    for (int i = 0; i + 1 < evi && i < 12; i++) cudaEventElapsedTime(&summary->stage_ms[i], ctx->ev[i], ctx->ev[i + 1]);
+    // composition degree overflow (constraints not satisfied): reported, not fatal — Winterfell only checks it in debug builds
+    if (!fe_is_zero(flag_h)) summary->stage_ms[11] = -1.0f;
+  }
+  if (out_len) {
+    if (out_proof && wr.b.size() > *out_len) { *out_len = wr.b.size(); ctx->set_error("proof buffer too small"); return 2; }
+    if (out_proof) memcpy(out_proof, wr.b.data(), wr.b.size());
+    *out_len = wr.b.size();
+  }
+  return 0;
+}
+
+extern "C" int zkl_prove_segment_dev(zkl_ctx *ctx, const void *trace_dev, size_t width, size_t n, const zkl_air_params *air,
+                                     const zkl_fe *seed_elems, size_t num_seed, const zkl_options *opts, uint8_t *out_proof, size_t *out_len,
+                                     zkl_proof_summary *summary) {
+  return prove_segment_impl(ctx, (const fe *)trace_dev, width, n, air, seed_elems, num_seed, opts, out_proof, out_len, summary);
+}
+extern "C" int zkl_prove_segment(zkl_ctx *ctx, const zkl_fe *trace, size_t width, size_t n, const zkl_air_params *air, const zkl_fe *seed_elems,
+                                 size_t num_seed, const zkl_options *opts, uint8_t *out_proof, size_t *out_len, zkl_proof_summary *summary) {
+  ZKL_CHECK(ctx, cudaSetDevice(ctx->device));
+  dev_buf<fe> tr; ZKL_CHECK(ctx, tr.alloc(width * n));
+  ZKL_CHECK(ctx, cudaMemcpyAsync(tr.p, trace, width * n * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream));
+  return prove_segment_impl(ctx, tr.p, width, n, air, seed_elems, num_seed, opts, out_proof, out_len, summary);
+}
+
+extern "C" int zkl_dev_alloc(zkl_ctx *ctx, size_t bytes, void **out_dev) { ZKL_CHECK(ctx, cudaSetDevice(ctx->device)); ZKL_CHECK(ctx, cudaMalloc(out_dev, bytes)); return 0; }
+extern "C" int zkl_dev_free(zkl_ctx *ctx, void *dev) { ZKL_CHECK(ctx, cudaSetDevice(ctx->device)); ZKL_CHECK(ctx, cudaFree(dev)); return 0; }
+extern "C" int zkl_dev_upload(zkl_ctx *ctx, void *dev, const void *host, size_t bytes) {
+  ZKL_CHECK(ctx, cudaSetDevice(ctx->device));
+  ZKL_CHECK(ctx, cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  ZKL_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+extern "C" int zkl_sync(zkl_ctx *ctx) { ZKL_CHECK(ctx, cudaSetDevice(ctx->device)); ZKL_CHECK(ctx, cudaStreamSynchronize(ctx->stream)); return 0; }

@@ -1,0 +1,77 @@
+// common.cuh — context, error handling and launch helpers shared by the kernel files.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/zkl_b200.h"
+#include "f128.cuh"
+#include "poseidon.cuh"
+
+#define ZKL_CHECK(ctx, expr)                                                                         \
+  do {                                                                                               \
+    cudaError_t _e = (expr);                                                                         \
+    if (_e != cudaSuccess) {                                                                         \
+      (ctx)->set_error(std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" __FILE__ ":" +      \
+                       std::to_string(__LINE__) + ")");                                              \
+      return 1;                                                                                      \
+    }                                                                                                \
+  } while (0)
+#define ZKL_TRY(expr)          \
+  do {                         \
+    int _r = (expr);           \
+    if (_r) return _r;         \
+  } while (0)
+
+// per-(N) device tables
+struct domain_tables {
+  size_t N = 0;
+  fe *wpow = nullptr;  // wpow[m] = w_N^m, m in [0, N)
+};
+
+struct zkl_ctx {
+  int device = 0;
+  int num_sms = 148;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  uint64_t launches = 0;
+  bool suite_loaded = false;
+  // sponge count from which the thread-per-sponge kernels are used instead of the cooperative ones
+  long bulk_threshold = 1 << 17;
+  std::map<size_t, domain_tables> tables;  // by N
+  std::map<size_t, fe *> opow;             // GENERATOR^j tables by n
+  std::vector<cudaEvent_t> ev;             // stage timing events
+  void set_error(const std::string &e) { err = e; }
+};
+
+static inline int ceil_div(size_t a, size_t b) { return (int)((a + b - 1) / b); }
+static inline int ilog2_sz(size_t n) { int k = 0; while (((size_t)1 << k) < n) k++; return k; }
+
+// device scratch with RAII (stream-ordered frees are not needed: buffers live until the handle dies)
+template <typename T>
+struct dev_buf {
+  T *p = nullptr; size_t n = 0;
+  dev_buf() {}
+  dev_buf(const dev_buf &) = delete;
+  dev_buf &operator=(const dev_buf &) = delete;
+  ~dev_buf() { if (p) cudaFree(p); }
+  cudaError_t alloc(size_t count) {
+    if (p) { cudaFree(p); p = nullptr; }
+    n = count;
+    return cudaMalloc((void **)&p, count * sizeof(T) + 16);
+  }
+};
+
+// host-side u128 helpers for CONSTANT derivation only (domain labels, roots of unity seeds)
+typedef unsigned __int128 hu128;
+static const hu128 H_P = ((hu128)0xffffffffffffffffULL << 64) | 0xffffd30000000001ULL;
+static inline fe h_to_fe(hu128 x) {
+  fe r; r.l[0] = (uint32_t)x; r.l[1] = (uint32_t)(x >> 32); r.l[2] = (uint32_t)(x >> 64); r.l[3] = (uint32_t)(x >> 96); return r;
+}
+static inline fe fe_from_abi(const zkl_fe &x) {
+  fe r; r.l[0] = (uint32_t)x.lo; r.l[1] = (uint32_t)(x.lo >> 32); r.l[2] = (uint32_t)x.hi; r.l[3] = (uint32_t)(x.hi >> 32); return r;
+}

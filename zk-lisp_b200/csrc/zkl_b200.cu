@@ -1,0 +1,304 @@
+// zkl_b200.cu — C ABI (include/zkl_b200.h) over the sm_100a kernels. Single translation unit so the
+// __constant__ hasher suite is shared by every kernel without relocatable device code.
+// No CPU fallback: every entry point launches device work; a missing device fails at ctx creation.
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+
+#include "kernels_air.cuh"
+#include "kernels_hash.cuh"
+#include "kernels_ntt.cuh"
+#include "kernels_stark.cuh"
+
+static std::string g_create_error;
+static std::mutex g_suite_mutex;
+
+#define LAUNCH(ctx, kernel, grid, block, smem, ...)                                 \
+  do {                                                                              \
+    kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                \
+    (ctx)->launches++;                                                              \
+    ZKL_CHECK(ctx, cudaGetLastError());                                             \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+static fe host_label(const char *s) {  // hasher.rs:155-160: label zero-padded to 32 bytes, folded
+  uint8_t b[32]; memset(b, 0, 32);
+  size_t l = strlen(s); if (l > 32) l = 32;
+  memcpy(b, s, l);
+  fe lo, hi; memcpy(lo.l, b, 16); memcpy(hi.l, b + 16, 16);
+  return fe_fold_pair(fe_from_u128_mod(lo), fe_from_u128_mod(hi));
+}
+
+extern "C" int zkl_ctx_create(int device, zkl_ctx **out) {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    g_create_error = std::string("no CUDA device available (") + cudaGetErrorString(e) + "); there is no CPU fallback";
+    return 1;
+  }
+  if (device < 0 || device >= count) { g_create_error = "device index out of range"; return 1; }
+  zkl_ctx *c = new zkl_ctx();
+  c->device = device;
+  if ((e = cudaSetDevice(device)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete c; return 1; }
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete c; return 1; }
+  c->num_sms = prop.multiProcessorCount;
+  if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+    g_create_error = cudaGetErrorString(e); delete c; return 1;
+  }
+  // opt in to large dynamic shared memory for the single-pass column transforms
+  cudaFuncSetAttribute(k_interpolate, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+  cudaFuncSetAttribute(k_lde, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+  label_consts lc;
+  lc.elements = host_label("winter/hash/elements");
+  lc.merge = host_label("zkl/winter/hash/merge");
+  lc.merge_many = host_label("zkl/winter/hash/merge_many");
+  lc.merge_with_int = host_label("zkl/winter/hash/merge_with_int");
+  lc.bytes = host_label("zkl/winter/hash/bytes");
+  {
+    std::lock_guard<std::mutex> g(g_suite_mutex);
+    if ((e = cudaMemcpyToSymbol(c_labels, &lc, sizeof lc)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete c; return 1; }
+  }
+  *out = c;
+  return 0;
+}
+
+extern "C" void zkl_ctx_destroy(zkl_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (auto &kv : ctx->tables) { cudaFree(kv.second.wpow); }
+  for (auto &kv : ctx->opow) cudaFree(kv.second);
+  for (auto e : ctx->ev) cudaEventDestroy(e);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+extern "C" const char *zkl_last_error(const zkl_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+extern "C" uint64_t zkl_launch_count(const zkl_ctx *ctx) { return ctx->launches; }
+
+extern "C" int zkl_suite_load(zkl_ctx *ctx, const zkl_suite *s) {
+  ZKL_CHECK(ctx, cudaSetDevice(ctx->device));
+  suite_consts h;
+  for (int i = 0; i < 2; i++) h.dom[i] = fe_from_abi(s->dom[i]);
+  for (int i = 0; i < 12; i++) for (int j = 0; j < 12; j++) h.mds[i][j] = fe_from_abi(s->mds[i][j]);
+  for (int r = 0; r < ZKL_ROUNDS; r++) for (int j = 0; j < 12; j++) h.rc[r][j] = fe_from_abi(s->rc[r][j]);
+  std::lock_guard<std::mutex> g(g_suite_mutex);
+  ZKL_CHECK(ctx, cudaMemcpyToSymbol(c_suite, &h, sizeof h));
+  ZKL_CHECK(ctx, cudaMemcpyToSymbol(g_suite, &h, sizeof h));
+  ctx->suite_loaded = true;
+  return 0;
+}
+static int need_suite(zkl_ctx *ctx) {
+  if (!ctx->suite_loaded) { ctx->set_error("zkl_suite_load has not been called on this context"); return 1; }
+  return cudaSetDevice(ctx->device) == cudaSuccess ? 0 : (ctx->set_error("cudaSetDevice failed"), 1);
+}
+
+// w_N^m table and offset powers -------------------------------------------------------------------
+static fe host_root_of_unity(int logn) {  // G^(2^(40-logn)), G = 3^((p-1)/2^40)
+  // (p-1)/2^40 = 2^88 - 45 ; 3^(2^88-45) computed as 3^(2^88) * inv(3^45)
+  fe g = fe_from_u64(3), a = g;
+  for (int i = 0; i < 88; i++) a = fe_sqr(a);
+  fe G = fe_mul(a, fe_inv(fe_pow(g, 45)));
+  for (int i = logn; i < 40; i++) G = fe_sqr(G);
+  return G;
+}
+static int get_tables(zkl_ctx *ctx, size_t N, domain_tables **out) {
+  auto it = ctx->tables.find(N);
+  if (it == ctx->tables.end()) {
+    domain_tables t; t.N = N;
+    ZKL_CHECK(ctx, cudaMalloc((void **)&t.wpow, N * sizeof(fe)));
+    fe w = host_root_of_unity(ilog2_sz(N));
+    LAUNCH(ctx, k_fill_powers, ceil_div(N, 256), 256, 0, w, t.wpow, N);
+    it = ctx->tables.emplace(N, t).first;
+  }
+  *out = &it->second;
+  return 0;
+}
+// opow[j] = offset^j, j < n, for offset = GENERATOR (the only offset Winterfell uses)
+static int get_offset_powers(zkl_ctx *ctx, size_t n, fe **out) {
+  auto it = ctx->opow.find(n);
+  if (it == ctx->opow.end()) {
+    fe *p;
+    ZKL_CHECK(ctx, cudaMalloc((void **)&p, n * sizeof(fe)));
+    LAUNCH(ctx, k_fill_powers, ceil_div(n, 256), 256, 0, fe_from_u64(3), p, n);
+    it = ctx->opow.emplace(n, p).first;
+  }
+  *out = it->second;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// device-side building blocks (all stream-ordered, no host sync)
+// ------------------------------------------------------------------------------------------------
+static const int NTT_THREADS = 512;
+
+// cols (ncols x n, evaluations over <w_n>) -> coefficients, in place or out of place
+static int dev_interpolate(zkl_ctx *ctx, const fe *src, fe *dst, size_t ncols, size_t n) {
+  if (n > 8192 || (n & (n - 1)) || n < 2) { ctx->set_error("trace length must be a power of two in [2, 8192] (single-pass shared-memory NTT)"); return 1; }
+  domain_tables *t; ZKL_TRY(get_tables(ctx, n, &t));
+  fe n_inv = fe_inv(fe_from_u64(n));
+  LAUNCH(ctx, k_interpolate, (unsigned)ncols, NTT_THREADS, n * sizeof(fe), src, dst, (int)n, ilog2_sz(n), t->wpow, n, n_inv);
+  return 0;
+}
+// polys (ncols x n) -> coset-major LDE (ncols x blowup x n) over GENERATOR * <w_N>
+static int dev_lde(zkl_ctx *ctx, const fe *polys, fe *out, size_t ncols, size_t n, size_t blowup) {
+  if (n > 8192 || (n & (n - 1)) || n < 2) { ctx->set_error("trace length must be a power of two in [2, 8192]"); return 1; }
+  size_t N = n * blowup;
+  domain_tables *t; ZKL_TRY(get_tables(ctx, N, &t));
+  fe *opow; ZKL_TRY(get_offset_powers(ctx, n, &opow));
+  dim3 grid((unsigned)blowup, (unsigned)ncols);
+  LAUNCH(ctx, k_lde, grid, NTT_THREADS, n * sizeof(fe), polys, (int)n, ilog2_sz(n), (int)blowup, t->wpow, N, opow, out);
+  return 0;
+}
+// leaves[r] for the coset-major matrix `lde` (ncols x N); partition size per PartitionOptions
+static size_t partition_size_of(const zkl_options *o, size_t cols) {  // [WF-mem] PartitionOptions::partition_size
+  if (o->num_partitions == 1 && o->hash_rate == 0) return cols;
+  size_t ps = (cols + o->num_partitions - 1) / o->num_partitions;
+  return std::max<size_t>(ps, o->hash_rate);
+}
+static int dev_hash_rows(zkl_ctx *ctx, const fe *lde, size_t ncols, size_t n, size_t blowup, const zkl_options *o, fe *leaves,
+                         dev_buf<fe> &scratch) {
+  size_t N = n * blowup, ps = partition_size_of(o, ncols);
+  size_t nchunks = (ncols + ps - 1) / ps;
+  // thread-per-sponge kernel when the sponges alone fill the GPU, the 16-thread cooperative one otherwise
+  size_t sponges = N * nchunks;
+  bool bulk = sponges >= (size_t)ctx->bulk_threshold;
+  fe *dst = nchunks == 1 ? leaves : nullptr;
+  if (nchunks > 1) { ZKL_CHECK(ctx, scratch.alloc(N * nchunks)); dst = scratch.p; }
+  if (bulk) LAUNCH(ctx, k_hash_rows, ceil_div(sponges, 128), 128, 0, lde, N, n, (int)blowup, (int)ncols, (int)ps, (int)nchunks, dst);
+  else LAUNCH(ctx, k_coop_hash_rows, ceil_div(sponges * ZKL_COOP_GROUP, ZKL_COOP_THREADS), ZKL_COOP_THREADS, 0, lde, N, n, (int)blowup, (int)ncols, (int)ps, (int)nchunks, dst);
+  if (nchunks > 1) {
+    if (N >= (size_t)ctx->bulk_threshold) LAUNCH(ctx, k_merge_many_rows, ceil_div(N, 128), 128, 0, scratch.p, N, (int)nchunks, leaves);
+    else LAUNCH(ctx, k_coop_merge_many_rows, ceil_div(N * ZKL_COOP_GROUP, ZKL_COOP_THREADS), ZKL_COOP_THREADS, 0, scratch.p, N, (int)nchunks, leaves);
+  }
+  return 0;
+}
+// MerkleTree::new: nodes[count + i] = leaves[i] conceptually; we store nodes[1..count) and keep leaves
+// separately. nodes has `count` entries (nodes[0] unused), nodes[1] = root.
+static int dev_merkle(zkl_ctx *ctx, const fe *leaves, fe *nodes, size_t count) {
+  if (count < 2 || (count & (count - 1))) { ctx->set_error("Merkle leaf count must be a power of two >= 2"); return 1; }
+  const fe *in = leaves;
+  for (size_t lvl = count / 2; lvl >= 1; lvl >>= 1) {
+    if (lvl >= (size_t)ctx->bulk_threshold) LAUNCH(ctx, k_merkle_level, ceil_div(lvl, 128), 128, 0, in, nodes + lvl, lvl);
+    else LAUNCH(ctx, k_coop_merkle_level, ceil_div(lvl * ZKL_COOP_GROUP, ZKL_COOP_THREADS), ZKL_COOP_THREADS, 0, in, nodes + lvl, lvl);
+    in = nodes + lvl;
+  }
+  return 0;
+}
+
+static void digest_from_fe_host(const fe &x, uint8_t out[32]) { memset(out, 0, 32); memcpy(out, x.l, 16); }
+
+// ------------------------------------------------------------------------------------------------
+// batched hasher primitives
+// ------------------------------------------------------------------------------------------------
+extern "C" int zkl_permute_batch(zkl_ctx *ctx, zkl_fe *states, size_t count) {
+  ZKL_TRY(need_suite(ctx));
+  dev_buf<fe> d; ZKL_CHECK(ctx, d.alloc(count * 12));
+  ZKL_CHECK(ctx, cudaMemcpyAsync(d.p, states, count * 12 * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream));
+  LAUNCH(ctx, k_permute_batch, ceil_div(count, 128), 128, 0, d.p, count);
+  ZKL_CHECK(ctx, cudaMemcpyAsync(states, d.p, count * 12 * sizeof(fe), cudaMemcpyDeviceToHost, ctx->stream));
+  ZKL_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+static int download_digests(zkl_ctx *ctx, const fe *dev, size_t count, uint8_t *out) {
+  std::vector<fe> h(count);
+  ZKL_CHECK(ctx, cudaMemcpyAsync(h.data(), dev, count * sizeof(fe), cudaMemcpyDeviceToHost, ctx->stream));
+  ZKL_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  for (size_t i = 0; i < count; i++) digest_from_fe_host(h[i], out + 32 * i);
+  return 0;
+}
+extern "C" int zkl_hash_elements_batch(zkl_ctx *ctx, const zkl_fe *elems, size_t len, size_t count, uint8_t *out) {
+  ZKL_TRY(need_suite(ctx));
+  dev_buf<fe> d, o; ZKL_CHECK(ctx, d.alloc(std::max<size_t>(count * len, 1))); ZKL_CHECK(ctx, o.alloc(count));
+  if (len) ZKL_CHECK(ctx, cudaMemcpyAsync(d.p, elems, count * len * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream));
+  LAUNCH(ctx, k_hash_elements_batch, ceil_div(count, 128), 128, 0, d.p, (int)len, count, o.p);
+  return download_digests(ctx, o.p, count, out);
+}
+// a 32-byte digest as the element its sponge chunk folds to (utils.rs:359-371): lo16 mod p + (hi16 mod p)*2^64
+static fe fold_digest_host(const uint8_t *b) {
+  fe lo, hi; memcpy(lo.l, b, 16); memcpy(hi.l, b + 16, 16);
+  return fe_fold_pair(fe_from_u128_mod(lo), fe_from_u128_mod(hi));
+}
+extern "C" int zkl_merge_batch(zkl_ctx *ctx, const uint8_t *pairs, size_t count, uint8_t *out) {
+  ZKL_TRY(need_suite(ctx));
+  std::vector<fe> h(2 * count);
+  for (size_t i = 0; i < 2 * count; i++) h[i] = fold_digest_host(pairs + 32 * i);
+  dev_buf<fe> d, o; ZKL_CHECK(ctx, d.alloc(2 * count)); ZKL_CHECK(ctx, o.alloc(count));
+  ZKL_CHECK(ctx, cudaMemcpyAsync(d.p, h.data(), 2 * count * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream));
+  LAUNCH(ctx, k_merkle_level, ceil_div(count, 128), 128, 0, d.p, o.p, count);
+  return download_digests(ctx, o.p, count, out);
+}
+extern "C" int zkl_merge_with_int_batch(zkl_ctx *ctx, const uint8_t seed[32], const uint64_t *values, size_t count, uint8_t *out) {
+  ZKL_TRY(need_suite(ctx));
+  dev_buf<uint64_t> v; dev_buf<fe> o; ZKL_CHECK(ctx, v.alloc(count)); ZKL_CHECK(ctx, o.alloc(count));
+  ZKL_CHECK(ctx, cudaMemcpyAsync(v.p, values, count * 8, cudaMemcpyHostToDevice, ctx->stream));
+  LAUNCH(ctx, k_merge_with_int_batch, ceil_div(count, 128), 128, 0, fold_digest_host(seed), v.p, count, o.p);
+  return download_digests(ctx, o.p, count, out);
+}
+static int sponge_chunks(zkl_ctx *ctx, const uint8_t *data, size_t len, int kind, uint8_t out[32]) {
+  size_t nch = (len + 31) / 32;
+  std::vector<fe> h(std::max<size_t>(nch, 1));
+  for (size_t i = 0; i < nch; i++) {  // hasher.rs:205-224: 32-byte chunks, zero padded, folded
+    uint8_t c[32]; memset(c, 0, 32);
+    memcpy(c, data + 32 * i, std::min<size_t>(32, len - 32 * i));
+    h[i] = fold_digest_host(c);
+  }
+  dev_buf<fe> d, o; ZKL_CHECK(ctx, d.alloc(h.size())); ZKL_CHECK(ctx, o.alloc(1));
+  ZKL_CHECK(ctx, cudaMemcpyAsync(d.p, h.data(), h.size() * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream));
+  LAUNCH(ctx, k_sponge_single, 1, 32, 0, d.p, (int)nch, kind, o.p);
+  return download_digests(ctx, o.p, 1, out);
+}
+extern "C" int zkl_hash_bytes(zkl_ctx *ctx, const uint8_t *data, size_t len, uint8_t out[32]) {
+  ZKL_TRY(need_suite(ctx));
+  return sponge_chunks(ctx, data, len, 0, out);
+}
+extern "C" int zkl_merge_many(zkl_ctx *ctx, const uint8_t *digests, size_t count, uint8_t out[32]) {
+  ZKL_TRY(need_suite(ctx));
+  if (count == 0) { memset(out, 0, 32); return 0; }  // hasher.rs:88-90
+  return sponge_chunks(ctx, digests, count * 32, 1, out);
+}
+extern "C" int zkl_merkle_build(zkl_ctx *ctx, const uint8_t *leaves, size_t count, uint8_t out_root[32], uint8_t *out_nodes) {
+  ZKL_TRY(need_suite(ctx));
+  std::vector<fe> h(count);
+  for (size_t i = 0; i < count; i++) h[i] = fold_digest_host(leaves + 32 * i);
+  dev_buf<fe> l, nd; ZKL_CHECK(ctx, l.alloc(count)); ZKL_CHECK(ctx, nd.alloc(count));
+  ZKL_CHECK(ctx, cudaMemcpyAsync(l.p, h.data(), count * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream));
+  ZKL_CHECK(ctx, cudaMemsetAsync(nd.p, 0, sizeof(fe), ctx->stream));
+  ZKL_TRY(dev_merkle(ctx, l.p, nd.p, count));
+  std::vector<uint8_t> nodes(32 * count);
+  ZKL_TRY(download_digests(ctx, nd.p, count, nodes.data()));
+  memcpy(out_root, nodes.data() + 32, 32);
+  if (out_nodes) memcpy(out_nodes, nodes.data(), 32 * count);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// NTT primitives
+// ------------------------------------------------------------------------------------------------
+extern "C" int zkl_interpolate_columns(zkl_ctx *ctx, zkl_fe *cols, size_t ncols, size_t n) {
+  ZKL_CHECK(ctx, cudaSetDevice(ctx->device));
+  dev_buf<fe> d; ZKL_CHECK(ctx, d.alloc(ncols * n));
+  ZKL_CHECK(ctx, cudaMemcpyAsync(d.p, cols, ncols * n * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream));
+  ZKL_TRY(dev_interpolate(ctx, d.p, d.p, ncols, n));
+  ZKL_CHECK(ctx, cudaMemcpyAsync(cols, d.p, ncols * n * sizeof(fe), cudaMemcpyDeviceToHost, ctx->stream));
+  ZKL_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+extern "C" int zkl_evaluate_columns(zkl_ctx *ctx, const zkl_fe *polys, size_t ncols, size_t n, size_t blowup, zkl_fe offset,
+                                    zkl_fe *out) {
+  ZKL_CHECK(ctx, cudaSetDevice(ctx->device));
+  if (!(offset.lo == 3 && offset.hi == 0)) { ctx->set_error("only the Winterfell domain offset GENERATOR = 3 is supported"); return 1; }
+  size_t N = n * blowup;
+  dev_buf<fe> p, cm, nat; ZKL_CHECK(ctx, p.alloc(ncols * n)); ZKL_CHECK(ctx, cm.alloc(ncols * N)); ZKL_CHECK(ctx, nat.alloc(ncols * N));
+  ZKL_CHECK(ctx, cudaMemcpyAsync(p.p, polys, ncols * n * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream));
+  ZKL_TRY(dev_lde(ctx, p.p, cm.p, ncols, n, blowup));
+  LAUNCH(ctx, k_coset_to_natural, ceil_div(ncols * N, 256), 256, 0, cm.p, nat.p, N, n, (int)blowup, ncols * N);
+  ZKL_CHECK(ctx, cudaMemcpyAsync(out, nat.p, ncols * N * sizeof(fe), cudaMemcpyDeviceToHost, ctx->stream));
+  ZKL_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+#include "api_stark.inl"

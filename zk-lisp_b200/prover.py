@@ -1,0 +1,277 @@
+"""Host-side mirror of the reference's prover interface over the C ABI (include/zkl_b200.h).
+
+`ZkProver.prove(trace)` mirrors zk-lisp-proof-winterfell/src/prove.rs:174-242 (ZkProver::prove ->
+winterfell::Prover::prove); the three hook-level methods mirror prove.rs:454-516. All arithmetic
+happens on the GPU; this module only marshals buffers (numpy) and builds plain parameter structs.
+"""
+import ctypes as C
+import threading
+
+import numpy as np
+
+from . import air as air_mod
+from . import capi, params
+
+
+def hasher_suite():
+    """Commitment/coin suite, suite_id = [0;32] (poseidon/hasher.rs:23)."""
+    return params.get_poseidon_suite(params.HASHER_SUITE_ID)
+
+
+def as_fe_array(a) -> np.ndarray:
+    """Field elements as a C-contiguous uint64 array with a trailing axis of 2 (lo, hi)."""
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    assert a.shape[-1] == 2
+    return a
+
+
+def ints_to_fe(xs) -> np.ndarray:
+    out = np.empty((len(xs), 2), dtype=np.uint64)
+    for i, x in enumerate(xs):
+        out[i, 0] = x & 0xFFFFFFFFFFFFFFFF
+        out[i, 1] = x >> 64
+    return out
+
+
+def fe_to_ints(a: np.ndarray):
+    a = a.reshape(-1, 2)
+    return [int(lo) | (int(hi) << 64) for lo, hi in a]
+
+
+class Context:
+    """One CUDA stream pinned to one device (SURVEY.md §8b thread rule: one ctx per host thread)."""
+
+    def __init__(self, device: int = 0, load_suite: bool = True):
+        self.lib = capi.load_library()
+        h = C.c_void_p()
+        if self.lib.zkl_ctx_create(device, C.byref(h)):
+            raise capi.ZklError(self.lib.zkl_last_error(None).decode())
+        self.h = h
+        self.device = device
+        self._lock = threading.Lock()
+        if load_suite:
+            s = capi.suite_to_c(hasher_suite())
+            self._check(self.lib.zkl_suite_load(self.h, C.byref(s)))
+
+    def _check(self, rc):
+        if rc:
+            raise capi.ZklError(self.lib.zkl_last_error(self.h).decode())
+
+    def close(self):
+        if self.h:
+            self.lib.zkl_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.zkl_launch_count(self.h))
+
+    # ---- hasher primitives (poseidon/hasher.rs:57-140) ----------------------------------------
+    def permute(self, states: np.ndarray) -> np.ndarray:
+        st = as_fe_array(states).copy()
+        self._check(self.lib.zkl_permute_batch(self.h, st.ctypes.data, st.shape[0]))
+        return st
+
+    def hash_elements(self, elems: np.ndarray) -> np.ndarray:
+        e = as_fe_array(elems)
+        count, length = e.shape[0], e.shape[1]
+        out = np.zeros((count, 32), dtype=np.uint8)
+        self._check(self.lib.zkl_hash_elements_batch(self.h, e.ctypes.data, length, count, out.ctypes.data))
+        return out
+
+    def merge(self, pairs: np.ndarray) -> np.ndarray:
+        p = np.ascontiguousarray(pairs, dtype=np.uint8).reshape(-1, 64)
+        out = np.zeros((p.shape[0], 32), dtype=np.uint8)
+        self._check(self.lib.zkl_merge_batch(self.h, p.ctypes.data, p.shape[0], out.ctypes.data))
+        return out
+
+    def merge_with_int(self, seed: bytes, values) -> np.ndarray:
+        v = np.ascontiguousarray(values, dtype=np.uint64)
+        s = np.frombuffer(bytes(seed), dtype=np.uint8).copy()
+        out = np.zeros((v.shape[0], 32), dtype=np.uint8)
+        self._check(self.lib.zkl_merge_with_int_batch(self.h, s.ctypes.data, v.ctypes.data, v.shape[0], out.ctypes.data))
+        return out
+
+    def hash_bytes(self, data: bytes) -> bytes:
+        d = np.frombuffer(bytes(data), dtype=np.uint8).copy() if data else np.zeros(1, dtype=np.uint8)
+        out = np.zeros(32, dtype=np.uint8)
+        self._check(self.lib.zkl_hash_bytes(self.h, d.ctypes.data, len(data), out.ctypes.data))
+        return out.tobytes()
+
+    def merge_many(self, digests: np.ndarray) -> bytes:
+        d = np.ascontiguousarray(digests, dtype=np.uint8).reshape(-1, 32)
+        out = np.zeros(32, dtype=np.uint8)
+        self._check(self.lib.zkl_merge_many(self.h, d.ctypes.data if d.size else None, d.shape[0], out.ctypes.data))
+        return out.tobytes()
+
+    def merkle_build(self, leaves: np.ndarray):
+        lv = np.ascontiguousarray(leaves, dtype=np.uint8).reshape(-1, 32)
+        root = np.zeros(32, dtype=np.uint8)
+        nodes = np.zeros((lv.shape[0], 32), dtype=np.uint8)
+        self._check(self.lib.zkl_merkle_build(self.h, lv.ctypes.data, lv.shape[0], root.ctypes.data, nodes.ctypes.data))
+        return root.tobytes(), nodes
+
+    # ---- NTT primitives ---------------------------------------------------------------------------
+    def interpolate_columns(self, cols: np.ndarray) -> np.ndarray:
+        c = as_fe_array(cols).copy()
+        self._check(self.lib.zkl_interpolate_columns(self.h, c.ctypes.data, c.shape[0], c.shape[1]))
+        return c
+
+    def evaluate_columns(self, polys: np.ndarray, blowup: int, offset: int = 3) -> np.ndarray:
+        p = as_fe_array(polys)
+        out = np.zeros((p.shape[0], p.shape[1] * blowup, 2), dtype=np.uint64)
+        self._check(self.lib.zkl_evaluate_columns(self.h, p.ctypes.data, p.shape[0], p.shape[1], blowup,
+                                                  capi.Fe.of(offset), out.ctypes.data))
+        return out
+
+
+class TraceLde:
+    """Replacement for winterfell's DefaultTraceLde returned by `new_trace_lde` (prove.rs:432-433)."""
+
+    def __init__(self, ctx: Context, handle, width, n, blowup, root: bytes, polys: np.ndarray):
+        self.ctx, self.h, self.width, self.n, self.blowup = ctx, handle, width, n, blowup
+        self.root, self.polys = root, polys
+
+    def trace_len(self):
+        return self.n
+
+    def get_main_trace_commitment(self) -> bytes:
+        return self.root
+
+    def read_main_trace_frame(self, lde_step: int):
+        cur = np.zeros((self.width, 2), dtype=np.uint64)
+        nxt = np.zeros((self.width, 2), dtype=np.uint64)
+        self.ctx._check(self.ctx.lib.zkl_trace_lde_read_frame(self.ctx.h, self.h, lde_step, cur.ctypes.data, nxt.ctypes.data))
+        return cur, nxt
+
+    def query(self, positions):
+        return _query(self.ctx, self.ctx.lib.zkl_trace_query, self.h, positions, self.width)
+
+    def free(self):
+        if self.h:
+            self.ctx.lib.zkl_trace_lde_free(self.ctx.h, self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class ConstraintCommitment:
+    """Replacement for DefaultConstraintCommitment (prove.rs:436-437)."""
+
+    def __init__(self, ctx, handle, num_cols, root, poly):
+        self.ctx, self.h, self.num_cols, self.root, self.poly = ctx, handle, num_cols, root, poly
+
+    def commitment(self) -> bytes:
+        return self.root
+
+    def query(self, positions):
+        return _query(self.ctx, self.ctx.lib.zkl_constraint_query, self.h, positions, self.num_cols)
+
+    def free(self):
+        if self.h:
+            self.ctx.lib.zkl_constraint_commitment_free(self.ctx.h, self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def _query(ctx, fn, handle, positions, width):
+    pos = np.ascontiguousarray(positions, dtype=np.uint32)
+    k = pos.shape[0]
+    rows = np.zeros((k, width, 2), dtype=np.uint64)
+    list_len = np.zeros(max(k, 1), dtype=np.uint32)
+    nodes = np.zeros((max(k, 1) * 64, 32), dtype=np.uint8)
+    bp = capi.BatchProof()
+    bp.list_len = list_len.ctypes.data_as(C.POINTER(C.c_uint32))
+    bp.nodes = nodes.ctypes.data_as(C.POINTER(C.c_uint8))
+    ctx._check(fn(ctx.h, handle, pos.ctypes.data, k, rows.ctypes.data, C.byref(bp)))
+    lists, off = [], 0
+    for i in range(bp.num_lists):
+        ln = int(list_len[i])
+        lists.append([nodes[off + j].tobytes() for j in range(ln)])
+        off += ln
+    return rows, {"depth": int(bp.depth), "nodes": lists}
+
+
+class ZkProver:
+    """Mirror of `ZkProver` / `ZkWinterfellProver` (prove.rs:104-242, 425-517) over the GPU path."""
+
+    def __init__(self, ctx: Context, options: air_mod.ProofOptions, air_pi: air_mod.AirPublicInputs):
+        self.ctx, self.options, self.air_pi = ctx, options, air_pi
+        self.last_summary = None
+
+    def _air(self, width, n) -> air_mod.Air:
+        return air_mod.Air(width, n, self.air_pi, self.options)
+
+    # hook 1 (prove.rs:454-474)
+    def new_trace_lde(self, trace: np.ndarray):
+        t = as_fe_array(trace)
+        width, n = t.shape[0], t.shape[1]
+        root = np.zeros(32, dtype=np.uint8)
+        polys = np.zeros((width, n, 2), dtype=np.uint64)
+        h = C.c_void_p()
+        o = self.options.to_c()
+        self.ctx._check(self.ctx.lib.zkl_trace_lde_commit(self.ctx.h, t.ctypes.data, width, n, C.byref(o), root.ctypes.data,
+                                                          polys.ctypes.data, C.byref(h)))
+        return TraceLde(self.ctx, h, width, n, self.options.blowup, root.tobytes(), polys), polys
+
+    # hook 2 (prove.rs:476-492) + ConstraintEvaluator::evaluate
+    def evaluate_constraints(self, trace_lde: TraceLde, coeffs: np.ndarray) -> np.ndarray:
+        a = self._air(trace_lde.width, trace_lde.n)
+        ap = a.to_c()
+        cc = as_fe_array(coeffs)
+        assert cc.shape[0] == a.num_constraints
+        out = np.zeros((trace_lde.n * a.ce_blowup, 2), dtype=np.uint64)
+        self.ctx._check(self.ctx.lib.zkl_eval_constraints(self.ctx.h, trace_lde.h, C.byref(ap), cc.ctypes.data, out.ctypes.data))
+        return out
+
+    # hook 3 (prove.rs:494-516)
+    def build_constraint_commitment(self, ce_evals: np.ndarray, n: int, ce_blowup: int, num_cols: int):
+        e = as_fe_array(ce_evals)
+        root = np.zeros(32, dtype=np.uint8)
+        poly = np.zeros((num_cols, n, 2), dtype=np.uint64)
+        h = C.c_void_p()
+        o = self.options.to_c()
+        self.ctx._check(self.ctx.lib.zkl_constraint_commit(self.ctx.h, e.ctypes.data, n, ce_blowup, num_cols, C.byref(o),
+                                                           root.ctypes.data, poly.ctypes.data, C.byref(h)))
+        return ConstraintCommitment(self.ctx, h, num_cols, root.tobytes(), poly), poly
+
+    # whole proof (prove.rs:174-242)
+    def prove(self, trace, dev_ptr=None, shape=None) -> bytes:
+        """`trace`: (W, n, 2) uint64 host array, column-major like winterfell's ColMatrix; or pass
+        `dev_ptr` + `shape=(W, n)` for a trace already resident in device memory."""
+        if dev_ptr is None:
+            t = as_fe_array(trace)
+            width, n = t.shape[0], t.shape[1]
+        else:
+            width, n = shape
+        a = self._air(width, n)
+        ap = a.to_c()
+        seed = ints_to_fe(a.seed_elements())
+        o = self.options.to_c()
+        cap = C.c_size_t(4 << 20)
+        buf = np.zeros(cap.value, dtype=np.uint8)
+        summ = capi.ProofSummary()
+        if dev_ptr is None:
+            rc = self.ctx.lib.zkl_prove_segment(self.ctx.h, t.ctypes.data, width, n, C.byref(ap), seed.ctypes.data,
+                                                seed.shape[0], C.byref(o), buf.ctypes.data, C.byref(cap), C.byref(summ))
+        else:
+            rc = self.ctx.lib.zkl_prove_segment_dev(self.ctx.h, dev_ptr, width, n, C.byref(ap), seed.ctypes.data,
+                                                    seed.shape[0], C.byref(o), buf.ctypes.data, C.byref(cap), C.byref(summ))
+        self.ctx._check(rc)
+        self.last_summary = summ
+        return buf[:cap.value].tobytes()
