@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""bench.py — rollup-bench proving throughput on B200 (BASELINE.json metric).
+
+A "step" is one pass of the hot path over one batch: the 16 execution segments of rollup-bench
+(n = 4096 trace rows, W = 204 columns, blowup 16, 64 queries, grinding 16; README.md:186-194 of the
+reference) are proven, i.e. 65 536 trace rows per step per GPU. Segments are independent
+(prove.rs:1020-1048), so with N GPUs every rank proves its own 16 segments (weak scaling, no collective
+on the data path). The synthetic traces satisfy the zk-lisp VM AIR (tests/synth.py), so every proof is
+a real, verifiable proof.
+
+  value : trace rows / s, traces already resident in HBM when the timed region starts
+  e2e   : same through the C-ABI call with HOST buffers (pinned), H2D of the trace and D2H of the proof
+          bytes inside the timed region
+Timing: CUDA events on the proving streams (max over streams, then max over ranks), barrier +
+synchronize on both sides; wall clock is reported beside it as a cross-check.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+SEGMENTS, ROWS, QUERIES, BLOWUP, GRIND = 16, 4096, 64, 16, 16
+METRIC, UNIT = "rollup-bench prove throughput (trace rows/s)", "trace rows/s"
+WORKLOAD = "rollup-bench: 16 segments x (n=4096, W=204, blowup=16, q=64, grind=16), synthetic AIR-valid traces"
+# algorithmic work of the dominant kernel (trace row hashing), SURVEY.md §8(d):
+# W=204 -> 1 + 102 absorbs -> 11 permutations per LDE row; one permutation = 27 rounds x (12 cubes = 24
+# products + 12x12 MDS = 144 products) = 4536 field products = 4536*16 32x32->64 multiply-accumulates.
+PERMS_PER_ROW = 11
+WIDE_MACS_PER_PERM = 27 * (24 + 144) * 16
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--streams", type=int, default=4, help="concurrent segment streams per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--bulk-threshold", type=int, default=0)
+    return ap.parse_args()
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+class ClockSampler:
+    """nvidia-smi clocks during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], None, set()
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_workload(zkl, count, rows, grind=GRIND, seed0=0x5A4B4C):
+    import synth
+    segs = []
+    for i in range(count):
+        trace, air_pi, opts = synth.valid_segment(n=rows, queries=QUERIES, blowup=BLOWUP, grind=grind, seed=seed0 + i,
+                                                  start_level=(i * (rows // 32)))
+        segs.append((trace, air_pi, opts))
+    return segs
+
+
+def cpu_reference_run(zkl, threads, rows, grind):
+    """The CPU restatement of the same pipeline (oracle/), one thread per segment, `threads` segments in
+    flight — the shape of the reference's rayon pool over segments (prove.rs:1020-1048)."""
+    import oracle_lib
+    oracle_lib.build()
+    segs = make_workload(zkl, threads, rows, grind=grind)
+    a = zkl.air.Air(segs[0][0].shape[0], rows, segs[0][1], segs[0][2])
+    # all segments share the AIR shape; each has its own public inputs -> run them as separate calls in threads
+    times = []
+
+    def work(i):
+        trace, air_pi, opts = segs[i]
+        ai = zkl.air.Air(trace.shape[0], rows, air_pi, opts)
+        oracle_lib.prove_segment(trace, ai.to_c(), zkl.prover.ints_to_fe(ai.seed_elements()), opts.to_c())
+
+    t0 = time.time()
+    th = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    dt = time.time() - t0
+    del a, times
+    return threads * rows / dt, dt
+
+
+def run_reference(args, zkl, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    threads = min(cores, 64)
+    rows, grind = 512, 13
+    vals = []
+    for _ in range(max(1, min(args.steps, 2))):
+        v, dt = cpu_reference_run(zkl, threads, rows, grind)
+        vals.append((v, dt))
+    v = float(np.mean([x[0] for x in vals]))
+    sample = (f"{threads} segments in flight (one thread each), n={rows} rows, W=204, blowup=16, q=64, grind={grind} "
+              f"(grinding work per row kept proportional to the n=4096/grind=16 workload); CPU port of the reference pipeline")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals), "warmup": 0,
+        "ms_per_step": float(np.mean([x[1] for x in vals])) * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u128 (f128 field)", "data": "synthetic", "config": {"workload": WORKLOAD, "reference_sample": sample},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+class Worker:
+    """One CUDA stream (zkl_ctx) proving a share of the step's segments."""
+
+    def __init__(self, zkl, device, segs, bulk_threshold):
+        self.zkl, self.ctx = zkl, zkl.Context(device)
+        if bulk_threshold:
+            self.ctx.lib.zkl_set_bulk_threshold(self.ctx.h, bulk_threshold)
+        self.items = []
+        for trace, air_pi, opts in segs:
+            prover = zkl.ZkProver(self.ctx, opts, air_pi)
+            dev = C.c_void_p()
+            self.ctx._check(self.ctx.lib.zkl_dev_alloc(self.ctx.h, trace.nbytes, C.byref(dev)))
+            self.ctx._check(self.ctx.lib.zkl_dev_upload(self.ctx.h, dev, trace.ctypes.data, trace.nbytes))
+            self.items.append((prover, trace, dev))
+        self.ms, self.summaries, self.proof_bytes = 0.0, [], 0
+
+    def run(self, resident: bool):
+        ms = C.c_float()
+        self.summaries, self.proof_bytes = [], 0
+        self.ctx._check(self.ctx.lib.zkl_timer_start(self.ctx.h))
+        for prover, trace, dev in self.items:
+            proof = prover.prove(None, dev_ptr=dev, shape=trace.shape[:2]) if resident else prover.prove(trace)
+            self.proof_bytes += len(proof)
+            self.summaries.append(prover.last_summary)
+        self.ctx._check(self.ctx.lib.zkl_timer_stop(self.ctx.h, C.byref(ms)))
+        self.ms = ms.value
+
+
+def run_step(workers, resident):
+    th = [threading.Thread(target=w.run, args=(resident,)) for w in workers]
+    t0 = time.time()
+    [t.start() for t in th]
+    [t.join() for t in th]
+    wall = (time.time() - t0) * 1e3
+    return max(w.ms for w in workers), wall
+
+
+def main():
+    args = parse_args()
+    rank, world, local = dist_env()
+    import __graft_entry__ as graft
+    zkl = graft.import_zkl()
+    if args.impl == "reference":
+        run_reference(args, zkl, rank, world)
+        return
+    import torch
+    import torch.distributed as dist
+    if world > 1:
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the proving path has no CPU fallback")
+    device = local
+
+    segs = make_workload(zkl, SEGMENTS, ROWS, seed0=0x5A4B4C + 1000 * rank)
+    S = max(1, min(args.streams, SEGMENTS))
+    workers = [Worker(zkl, device, segs[i::S], args.bulk_threshold) for i in range(S)]
+    # pinned host buffers for the e2e leg
+    for w in workers:
+        for _, trace, _ in w.items:
+            torch.cuda.cudart().cudaHostRegister(trace.ctypes.data, trace.nbytes, 0)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(resident, steps, sampler=None):
+        barrier()
+        if sampler:
+            sampler.start()
+        ev_ms, wall_ms = [], []
+        launches0 = sum(w.ctx.launches for w in workers)
+        for _ in range(steps):
+            e, wl = run_step(workers, resident)
+            ev_ms.append(e); wall_ms.append(wl)
+        barrier()
+        clocks = sampler.stop() if sampler else None
+        tot_ev, tot_wall = float(np.sum(ev_ms)), float(np.sum(wall_ms))
+        if world > 1:
+            t = torch.tensor([tot_ev, tot_wall], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            tot_ev, tot_wall = float(t[0]), float(t[1])
+        return tot_ev, tot_wall, sum(w.ctx.launches for w in workers) - launches0, clocks
+
+    for _ in range(args.warmup):
+        run_step(workers, True)
+    sampler = ClockSampler(device)
+    ev_total, wall_total, launches, clocks = timed(True, args.steps, sampler)
+    stage = np.zeros(12)
+    cnt = 0
+    for w in workers:
+        for s in w.summaries:
+            stage += np.array(list(s.stage_ms)); cnt += 1
+    stage /= max(cnt, 1)
+    run_step(workers, False)  # warm the host-buffer path
+    e2e_ev, e2e_wall, _, _ = timed(False, args.steps)
+    h2d = sum(t.nbytes for w in workers for _, t, _ in w.items)
+    d2h = sum(w.proof_bytes for w in workers)
+
+    rows_total = world * SEGMENTS * ROWS * args.steps
+    value = rows_total / (ev_total * 1e-3)
+    e2e_value = rows_total / (e2e_ev * 1e-3)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak, hbm_src = (peaks.get("hbm_gbs"), "measured (MEASURED_PEAKS.json)") if peaks.get("hbm_gbs") else (6650.0, "fallback (B200_PROFILING.md)")
+        imad = C.c_double()
+        workers[0].ctx._check(workers[0].ctx.lib.zkl_imad_peak(workers[0].ctx.h, C.byref(imad)))
+        N = ROWS * BLOWUP
+        hash_ms, lde_ms = float(stage[10]), float(stage[9])
+        hash_macs = N * PERMS_PER_ROW * WIDE_MACS_PER_PERM
+        lde_bytes = 16 * 204 * ROWS * (1 + BLOWUP)
+        roofline = {
+            "kernel": "k_hash_rows (trace row hashing, 11 permutations per LDE row)",
+            "bound": "int32-multiply pipe (IMAD.WIDE.U32); not hbm/tensor: 4536 field products per 3.3 KB row",
+            "achieved": hash_macs / (hash_ms * 1e-3) / 1e12, "peak": imad.value / 1e12, "unit": "T wide-MAC/s (32x32+64)",
+            "frac": (hash_macs / (hash_ms * 1e-3)) / imad.value, "peak_source": "zkl_imad_peak probe measured in this run",
+            "traffic": None, "ms_per_launch": hash_ms, "timing": "concurrent with other segment streams" if S > 1 else "stream-exclusive",
+        }
+        roofline_lde = {
+            "kernel": "k_lde (trace coset LDE, one CTA per column x coset, single pass over HBM)",
+            "bound": "hbm", "achieved": lde_bytes / (lde_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+            "frac": lde_bytes / (lde_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src, "traffic": None, "ms_per_launch": lde_ms,
+            "note": "f128: 14 modmuls (~1400 instructions) per 16-byte element written, so the kernel is integer-bound far below the HBM roof",
+        }
+        cpu = None
+        if not args.no_cpu_baseline and world == 1:
+            cores = min(os.cpu_count() or 1, 64)
+            v, dt = cpu_reference_run(zkl, cores, 512, 13)
+            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": f"{cores} segments in flight, n=512, W=204, blowup=16, q=64, grind=13 ({dt:.1f} s of wall time)"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ev_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u128 (f128 field, 4x u32 limbs)", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "segments_per_gpu_per_step": SEGMENTS, "streams_per_gpu": S,
+                       "l2": "per-step working set 16 x 250 MB LDE matrices >> 126 MB L2 (no flush needed)",
+                       "published_reference": "109.567 s on Apple M3 Max for the same 65536 rows (BASELINE.md), different hardware"},
+            "wall_ms_per_step": wall_total / args.steps,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ev / args.steps, "wall_ms_per_step": e2e_wall / args.steps},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roofline, "roofline_lde": roofline_lde,
+            "stage_ms_per_segment": {zkl.capi.load_library().zkl_stage_name(i).decode(): float(stage[i]) for i in range(11)},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -200,7 +200,9 @@ typedef struct {
   uint64_t pow_nonce;
   uint32_t num_unique_queries;
   uint32_t positions[256];
-  float stage_ms[12];           /* device time per stage, see zkl_stage_name */
+  float stage_ms[12];           /* [0..8] device ms per stage, [9] trace k_lde ms, [10] trace k_hash_rows ms,
+                                   [11] -1 if the composition polynomial overflowed its degree (invalid trace);
+                                   see zkl_stage_name */
 } zkl_proof_summary;
 int zkl_prove_segment(zkl_ctx *ctx, const zkl_fe *trace, size_t width, size_t n,
                       const zkl_air_params *air, const zkl_fe *seed_elems, size_t num_seed,
@@ -219,6 +221,13 @@ int zkl_dev_alloc(zkl_ctx *ctx, size_t bytes, void **out_dev);
 int zkl_dev_free(zkl_ctx *ctx, void *dev);
 int zkl_dev_upload(zkl_ctx *ctx, void *dev, const void *host, size_t bytes);
 int zkl_sync(zkl_ctx *ctx);
+
+/* ---- measurement helpers (bench.py) -------------------------------------------------------- */
+int zkl_timer_start(zkl_ctx *ctx);             /* CUDA event on the ctx stream */
+int zkl_timer_stop(zkl_ctx *ctx, float *ms);   /* second event, synchronised; elapsed device time */
+int zkl_imad_peak(zkl_ctx *ctx, double *wide_macs_per_s); /* dependency-free IMAD.WIDE.U32 probe */
+/* sponge count from which thread-per-sponge kernels replace the 16-thread cooperative ones */
+int zkl_set_bulk_threshold(zkl_ctx *ctx, long sponges);
 
 #ifdef __cplusplus
 }

@@ -60,15 +60,16 @@ static inline void mul_wide(u128 a, u128 b, u128 &hi, u128 &lo) {
 
 // reduce hi*2^128 + lo  (mod p) using 2^128 ≡ C128 (46 bits)
 static inline F f_reduce256(u128 hi, u128 lo) {
-  // hi*C128: hi < 2^128, C128 < 2^46 -> up to 174 bits
-  u128 h2, l2;
-  mul_wide(hi, C128, h2, l2);           // h2 < 2^46
-  u128 s = lo + l2; u128 c = s < lo;    // carry
-  h2 += c;                              // h2 < 2^47
-  // now value = h2*2^128 + s ; h2*C128 < 2^93
-  u128 t = h2 * C128;
-  u128 s2 = s + t; bool c2 = s2 < s;
-  if (c2) s2 += C128;                   // s2 was < 2^93 after wrap, cannot wrap again
+  // hi*C128 with hi = h1*2^64 + h0: two 64x46-bit products (each < 2^110)
+  const uint64_t C = (uint64_t)C128;
+  u128 p0 = (u128)(uint64_t)hi * C, p1 = (u128)(uint64_t)(hi >> 64) * C;
+  // value = lo + p0 + p1*2^64
+  u128 s = lo + p0; u128 c = s < lo;
+  u128 t = p1 << 64; u128 s1 = s + t; c += s1 < s;
+  u128 h2 = (p1 >> 64) + c;             // < 2^47
+  // fold again: h2*2^128 ≡ h2*C (< 2^93)
+  u128 s2 = s1 + h2 * C128; bool c2 = s2 < s1;
+  if (c2) s2 += C128;                   // wrapped value is < 2^93, cannot wrap again
   if (s2 >= P) s2 -= P;
   F r; r.v = s2; return r;
 }

@@ -22,30 +22,55 @@ from zk_lisp_b200.field import P
 OPS = A.OPS
 
 
+class _Table:
+    """Sparse column-major table: dict[(col,row)] -> int, materialised once into a (W, n, 2) uint64 array."""
+
+    def __init__(self, cols: A.Columns, n: int):
+        self.W, self.n, self.d = cols.width, n, {}
+        for row in range(n):
+            pos = row % 32
+            if pos == 0:
+                self.d[(cols.g_map, row)] = 1
+            if pos == 28:
+                self.d[(cols.g_final, row)] = 1
+            if 1 <= pos <= 27:
+                self.d[(cols.g_r_index(pos - 1), row)] = 1
+
+    def __getitem__(self, c):
+        return _Col(self, c)
+
+    def to_np(self):
+        out = np.zeros((self.W, self.n, 2), dtype=np.uint64)
+        if self.d:
+            keys = np.array(list(self.d.keys()), dtype=np.int64)
+            vals = list(self.d.values())
+            lo = np.array([v & 0xFFFFFFFFFFFFFFFF for v in vals], dtype=np.uint64)
+            hi = np.array([v >> 64 for v in vals], dtype=np.uint64)
+            out[keys[:, 0], keys[:, 1], 0] = lo
+            out[keys[:, 0], keys[:, 1], 1] = hi
+        return out
+
+
+class _Col:
+    def __init__(self, t, c):
+        self.t, self.c = t, c
+
+    def __getitem__(self, r):
+        return self.t.d.get((self.c, r), 0)
+
+    def __setitem__(self, r, v):
+        if v:
+            self.t.d[(self.c, r)] = v
+        else:
+            self.t.d.pop((self.c, r), None)
+
+
 def _empty(cols: A.Columns, n: int):
-    t = [[0] * n for _ in range(cols.width)]
-    for row in range(n):
-        pos = row % 32
-        if pos == 0:
-            t[cols.g_map][row] = 1
-        if pos == 28:
-            t[cols.g_final][row] = 1
-        if 1 <= pos <= 27:
-            t[cols.g_r_index(pos - 1)][row] = 1
-    return t
+    return _Table(cols, n)
 
 
 def _to_np(t, n):
-    W = len(t)
-    out = np.zeros((W, n, 2), dtype=np.uint64)
-    for c in range(W):
-        col = t[c]
-        for r in range(n):
-            v = col[r]
-            if v:
-                out[c, r, 0] = v & 0xFFFFFFFFFFFFFFFF
-                out[c, r, 1] = v >> 64
-    return out
+    return t.to_np()
 
 
 def valid_segment(n=64, queries=8, blowup=16, grind=4, seed=1, poseidon_levels=True, start_level=0):

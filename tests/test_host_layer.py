@@ -1,0 +1,48 @@
+"""CPU tests of the host layer: the C-ABI library loads and exports every declared symbol, and the
+product path refuses to run without a CUDA device (no fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+import __graft_entry__ as graft
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _has_cuda():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def test_library_exports_every_declared_symbol(zkl):
+    graft.build()
+    header = open(os.path.join(ROOT, "include", "zkl_b200.h")).read()
+    declared = set(re.findall(r"\b(zkl_[a-z0-9_]+)\s*\(", header))
+    declared -= {"zkl_batch_proof"}
+    lib = ctypes.CDLL(zkl.capi.LIB_PATH)
+    for sym in sorted(declared):
+        assert hasattr(lib, sym), sym
+    assert declared == set(zkl.capi.EXPORTED_SYMBOLS)
+
+
+def test_no_cpu_fallback(zkl):
+    if _has_cuda():
+        pytest.skip("CUDA device present")
+    with pytest.raises(zkl.capi.ZklError) as e:
+        zkl.Context(0)
+    assert "no CPU fallback" in str(e.value)
+
+
+def test_product_does_not_import_oracle():
+    """The product package must never reference oracle/ (parity claims depend on it)."""
+    pkg = os.path.join(ROOT, "zk-lisp_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".inl", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.lower(), f

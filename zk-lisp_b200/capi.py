@@ -1,8 +1,8 @@
 """ctypes mirror of include/zkl_b200.h and the loader of the CUDA library.
 
 There is NO CPU fallback: if libzkl_b200.so is missing or no CUDA device is present, loading /
-context creation raises. The oracle (oracle/liboracle.so) is loaded only by tests/, smoke() and
-bench.py's cpu_baseline legs through `tests/oracle_lib.py`, never from here.
+context creation raises. The CPU checker used by tests/, smoke() and bench.py's cpu_baseline legs lives
+outside this package and is never loaded from here.
 """
 import ctypes as C
 import os
@@ -160,6 +160,10 @@ def load_library():
     sig("zkl_dev_free", C.c_int, vp, vp)
     sig("zkl_dev_upload", C.c_int, vp, vp, vp, sz)
     sig("zkl_sync", C.c_int, vp)
+    sig("zkl_timer_start", C.c_int, vp)
+    sig("zkl_timer_stop", C.c_int, vp, C.POINTER(C.c_float))
+    sig("zkl_imad_peak", C.c_int, vp, C.POINTER(C.c_double))
+    sig("zkl_set_bulk_threshold", C.c_int, vp, C.c_long)
     _lib = lib
     return lib
 
@@ -172,5 +176,5 @@ EXPORTED_SYMBOLS = [
     "zkl_trace_query", "zkl_eval_constraints", "zkl_constraint_commit",
     "zkl_constraint_commitment_free", "zkl_constraint_query", "zkl_prove_segment",
     "zkl_prove_segment_dev", "zkl_stage_name", "zkl_dev_alloc", "zkl_dev_free", "zkl_dev_upload",
-    "zkl_sync",
+    "zkl_sync", "zkl_timer_start", "zkl_timer_stop", "zkl_imad_peak", "zkl_set_bulk_threshold",
 ]

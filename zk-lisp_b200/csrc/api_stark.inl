@@ -15,12 +15,16 @@ struct zkl_trace_lde { committed_matrix m; };
 struct zkl_constraint_commitment { committed_matrix m; };
 
 // polys must already hold width x n coefficients
-static int commit_matrix(zkl_ctx *ctx, committed_matrix &m, const zkl_options *o) {
+// kev: optional 3 events recorded before the LDE kernel, between LDE and row hashing, and after row hashing
+static int commit_matrix(zkl_ctx *ctx, committed_matrix &m, const zkl_options *o, cudaEvent_t *kev = nullptr) {
   ZKL_CHECK(ctx, m.lde.alloc(m.width * m.N));
   ZKL_CHECK(ctx, m.leaves.alloc(m.N));
   ZKL_CHECK(ctx, m.nodes.alloc(m.N));
+  if (kev) ZKL_CHECK(ctx, cudaEventRecord(kev[0], ctx->stream));
   ZKL_TRY(dev_lde(ctx, m.polys.p, m.lde.p, m.width, m.n, m.blowup));
+  if (kev) ZKL_CHECK(ctx, cudaEventRecord(kev[1], ctx->stream));
   ZKL_TRY(dev_hash_rows(ctx, m.lde.p, m.width, m.n, m.blowup, o, m.leaves.p, m.scratch));
+  if (kev) ZKL_CHECK(ctx, cudaEventRecord(kev[2], ctx->stream));
   ZKL_TRY(dev_merkle(ctx, m.leaves.p, m.nodes.p, m.N));
   return 0;
 }
@@ -31,12 +35,13 @@ static int check_opts(zkl_ctx *ctx, const zkl_options *o, size_t n) {
   return 0;
 }
 
-static int trace_commit_dev(zkl_ctx *ctx, const fe *trace_dev, size_t width, size_t n, const zkl_options *o, zkl_trace_lde *h) {
+static int trace_commit_dev(zkl_ctx *ctx, const fe *trace_dev, size_t width, size_t n, const zkl_options *o, zkl_trace_lde *h,
+                            cudaEvent_t *kev = nullptr) {
   committed_matrix &m = h->m;
   m.width = width; m.n = n; m.blowup = o->blowup; m.N = n * o->blowup;
   ZKL_CHECK(ctx, m.polys.alloc(width * n));
   ZKL_TRY(dev_interpolate(ctx, trace_dev, m.polys.p, width, n));
-  return commit_matrix(ctx, m, o);
+  return commit_matrix(ctx, m, o, kev);
 }
 
 extern "C" int zkl_trace_lde_commit(zkl_ctx *ctx, const zkl_fe *trace, size_t width, size_t n, const zkl_options *o,
@@ -62,11 +67,11 @@ extern "C" int zkl_trace_lde_commit(zkl_ctx *ctx, const zkl_fe *trace, size_t wi
 }
 extern "C" void zkl_trace_lde_free(zkl_ctx *ctx, zkl_trace_lde *h) {
   if (!h) return;
-  cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream);
+  enter(ctx); cudaStreamSynchronize(ctx->stream);
   delete h;
 }
 extern "C" int zkl_trace_lde_read_frame(zkl_ctx *ctx, const zkl_trace_lde *h, size_t lde_step, zkl_fe *out_cur, zkl_fe *out_next) {
-  ZKL_CHECK(ctx, cudaSetDevice(ctx->device));
+  ZKL_TRY(enter(ctx));
   const committed_matrix &m = h->m;
   if (lde_step >= m.N) { ctx->set_error("lde_step out of range"); return 1; }
   uint32_t pos[2] = {(uint32_t)lde_step, (uint32_t)((lde_step + m.blowup) % m.N)};
@@ -141,7 +146,7 @@ static int fetch_batch_proof(zkl_ctx *ctx, const fe *leaves_dev, const fe *nodes
 
 static int query_matrix(zkl_ctx *ctx, const committed_matrix &m, const uint32_t *positions, size_t k, zkl_fe *out_rows,
                         zkl_batch_proof *bp) {
-  ZKL_CHECK(ctx, cudaSetDevice(ctx->device));
+  ZKL_TRY(enter(ctx));
   std::vector<uint32_t> pos(positions, positions + k);
   for (auto p : pos) if (p >= m.N) { ctx->set_error("query position out of range"); return 1; }
   dev_buf<uint32_t> dp; dev_buf<fe> rows; ZKL_CHECK(ctx, dp.alloc(k)); ZKL_CHECK(ctx, rows.alloc(k * m.width));
@@ -344,7 +349,7 @@ extern "C" int zkl_constraint_commit(zkl_ctx *ctx, const zkl_fe *ce_evals, size_
 }
 extern "C" void zkl_constraint_commitment_free(zkl_ctx *ctx, zkl_constraint_commitment *h) {
   if (!h) return;
-  cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream);
+  enter(ctx); cudaStreamSynchronize(ctx->stream);
   delete h;
 }
 
@@ -394,7 +399,8 @@ static std::vector<uint32_t> fold_positions_host(const std::vector<uint32_t> &po
 }
 
 static const char *k_stage_names[12] = {"coin_seed", "trace_lde_commit", "constraint_eval", "constraint_commit", "ood", "deep",
-                                        "fri", "grind", "queries_serialize", "", "", ""};
+                                        "fri", "grind", "queries_serialize", "kernel:k_lde(trace)", "kernel:k_hash_rows(trace)",
+                                        "flag:composition_degree_overflow"};
 extern "C" const char *zkl_stage_name(int s) { return (s >= 0 && s < 12) ? k_stage_names[s] : ""; }
 
 // ------------------------------------------------------------------------------------------------
@@ -410,7 +416,7 @@ static int prove_segment_impl(zkl_ctx *ctx, const fe *trace_dev, size_t W, size_
   const size_t ncc = (size_t)air->num_transition + air->num_assertions;
   const size_t nl = fri_num_layers(N, *o);
   if (nl + 1 > 40) { ctx->set_error("too many FRI layers"); return 1; }
-  while (ctx->ev.size() < 12) { cudaEvent_t e; ZKL_CHECK(ctx, cudaEventCreate(&e)); ctx->ev.push_back(e); }
+  while (ctx->ev.size() < 16) { cudaEvent_t e; ZKL_CHECK(ctx, cudaEventCreate(&e)); ctx->ev.push_back(e); }
   domain_tables *tN; ZKL_TRY(get_tables(ctx, N, &tN));
   fe *opow; ZKL_TRY(get_offset_powers(ctx, n, &opow)); (void)opow;
   cudaStream_t st = ctx->stream;
@@ -427,7 +433,7 @@ static int prove_segment_impl(zkl_ctx *ctx, const fe *trace_dev, size_t W, size_
 
   // ---- 2. trace LDE + commitment (hook new_trace_lde), reseed with the root
   zkl_trace_lde tl;
-  ZKL_TRY(trace_commit_dev(ctx, trace_dev, W, n, o, &tl));
+  ZKL_TRY(trace_commit_dev(ctx, trace_dev, W, n, o, &tl, &ctx->ev[12]));
   LAUNCH(ctx, k_coin_reseed, 1, ZKL_COOP_GROUP, 0, coin.p, tl.m.nodes.p + 1);
   STAGE_MARK();
 
@@ -541,27 +547,70 @@ static int prove_segment_impl(zkl_ctx *ctx, const fe *trace_dev, size_t W, size_
   ZKL_CHECK(ctx, cudaStreamSynchronize(st));
   std::vector<uint32_t> pos(pos_h, pos_h + cnt_h);
 
+  // One gather for everything the proof opens: queried rows, FRI layer values and all Merkle nodes.
+  // Phase 1 lists (source buffer, element index) in the exact order the serializer consumes them.
+  std::vector<const fe *> g_src; std::vector<uint32_t> g_idx;
+  auto want = [&](const fe *src, uint32_t idx) { g_src.push_back(src); g_idx.push_back(idx); };
+  struct tree_job { std::vector<std::vector<node_ref>> plan; int depth; };
+  auto plan_matrix = [&](const committed_matrix &m, tree_job &tj) {
+    for (uint32_t p : pos) {
+      uint32_t s = (uint32_t)((p % m.blowup) * m.n + p / m.blowup);
+      for (size_t c = 0; c < m.width; c++) want(m.lde.p, (uint32_t)(c * m.N + s));
+    }
+    tj.plan = batch_proof_plan(pos, m.N); tj.depth = ilog2_sz(m.N);
+    for (auto &l : tj.plan) for (auto &r : l) want(r.leaf ? m.leaves.p : m.nodes.p, r.index);
+  };
+  tree_job tj_trace, tj_cons; std::vector<tree_job> tj_fri(nl);
+  std::vector<size_t> fri_counts(nl);
+  plan_matrix(tl.m, tj_trace);
+  plan_matrix(cmt.m, tj_cons);
+  {
+    std::vector<uint32_t> fp = pos; size_t dom = N; const fe *ev = deep.p; size_t ndl = n;
+    for (size_t d = 0; d < nl; d++) {
+      fp = fold_positions_host(fp, dom);
+      size_t half = dom / 2, half_rows = ndl / 2;
+      for (uint32_t p : fp) {  // values ev[p], ev[p + half]; storage index of natural r: (r % B)*ndl + r / B
+        uint32_t s0 = (uint32_t)((p % B) * ndl + p / B);
+        want(ev, s0); want(ev, s0 + (uint32_t)half_rows);
+      }
+      fri_counts[d] = fp.size();
+      tj_fri[d].plan = batch_proof_plan(fp, half); tj_fri[d].depth = ilog2_sz(half);
+      for (auto &l : tj_fri[d].plan) for (auto &r : l) want(r.leaf ? f_leaves[d].p : f_nodes[d].p, r.index);
+      ev = f_ev[d + 1].p; dom = half; ndl = half_rows;
+    }
+  }
+  std::vector<fe> got(g_idx.size());
+  {
+    dev_buf<const fe *> dsrc; dev_buf<uint32_t> didx; dev_buf<fe> dout;
+    ZKL_CHECK(ctx, dsrc.alloc(g_src.size())); ZKL_CHECK(ctx, didx.alloc(g_idx.size())); ZKL_CHECK(ctx, dout.alloc(g_idx.size()));
+    ZKL_CHECK(ctx, cudaMemcpyAsync(dsrc.p, g_src.data(), g_src.size() * sizeof(fe *), cudaMemcpyHostToDevice, st));
+    ZKL_CHECK(ctx, cudaMemcpyAsync(didx.p, g_idx.data(), g_idx.size() * 4, cudaMemcpyHostToDevice, st));
+    LAUNCH(ctx, k_gather_multi, ceil_div(g_idx.size(), 256), 256, 0, dsrc.p, didx.p, (int)g_idx.size(), dout.p);
+    ZKL_CHECK(ctx, cudaMemcpyAsync(got.data(), dout.p, got.size() * sizeof(fe), cudaMemcpyDeviceToHost, st));
+    ZKL_CHECK(ctx, cudaStreamSynchronize(st));
+  }
+  size_t gp = 0;  // consumption cursor
+
   byte_writer wr;
   write_context_bytes(wr, W, n, *o, ncc);
   wr.u8((uint8_t)pos.size());
   wr.u16((uint16_t)(32 * (2 + nl + 1)));
   wr.digest(troot); wr.digest(croot);
   for (auto &r : roots_h) wr.digest(r);
-  auto write_queries = [&](const committed_matrix &m) -> int {
-    std::vector<fe> rows(pos.size() * m.width);
-    dev_buf<fe> drows; ZKL_CHECK(ctx, drows.alloc(rows.size()));
-    LAUNCH(ctx, k_gather_rows, ceil_div(rows.size(), 128), 128, 0, m.lde.p, m.N, m.n, (int)m.blowup, (int)m.width, pos_dev.p, (int)pos.size(), drows.p);
-    ZKL_CHECK(ctx, cudaMemcpyAsync(rows.data(), drows.p, rows.size() * sizeof(fe), cudaMemcpyDeviceToHost, st));
-    ZKL_CHECK(ctx, cudaStreamSynchronize(st));
+  auto take_lists = [&](const tree_job &tj) {
     std::vector<std::vector<fe>> lists;
-    ZKL_TRY(fetch_batch_proof(ctx, m.leaves.p, m.nodes.p, batch_proof_plan(pos, m.N), lists));
-    byte_writer pw; write_batch_proof_bytes(pw, ilog2_sz(m.N), lists);
-    wr.usize(rows.size() * 16); wr.bytes(rows.data(), rows.size() * 16);
-    wr.usize(pw.b.size()); wr.bytes(pw.b.data(), pw.b.size());
-    return 0;
+    for (auto &l : tj.plan) { lists.emplace_back(got.begin() + gp, got.begin() + gp + l.size()); gp += l.size(); }
+    return lists;
   };
-  ZKL_TRY(write_queries(tl.m));
-  ZKL_TRY(write_queries(cmt.m));
+  auto write_queries = [&](const committed_matrix &m, const tree_job &tj) {
+    size_t cnt = pos.size() * m.width;
+    const fe *rows = got.data() + gp; gp += cnt;
+    byte_writer pw; write_batch_proof_bytes(pw, tj.depth, take_lists(tj));
+    wr.usize(cnt * 16); wr.bytes(rows, cnt * 16);
+    wr.usize(pw.b.size()); wr.bytes(pw.b.data(), pw.b.size());
+  };
+  write_queries(tl.m, tj_trace);
+  write_queries(cmt.m, tj_cons);
   // OodFrame: trace states (current || next), constraint evaluations (current || next)
   wr.u16((uint16_t)(2 * W * 16));
   wr.bytes(ood_h.data(), W * 16); wr.bytes(ood_h.data() + W + C, W * 16);
@@ -569,31 +618,12 @@ static int prove_segment_impl(zkl_ctx *ctx, const fe *trace_dev, size_t W, size_
   wr.bytes(ood_h.data() + W, C * 16); wr.bytes(ood_h.data() + 2 * W + C, C * 16);
   // FriProof
   wr.u8((uint8_t)nl);
-  {
-    std::vector<uint32_t> fp = pos; size_t dom = N;
-    const fe *ev = deep.p; size_t ndl = n;
-    for (size_t d = 0; d < nl; d++) {
-      fp = fold_positions_host(fp, dom);
-      size_t half = dom / 2, half_rows = ndl / 2;
-      // values: for position p (natural, < half): ev[p], ev[p + half] ; storage index of natural r: (r % B)*ndl + r / B
-      std::vector<uint32_t> idx;
-      for (uint32_t p : fp) {
-        uint32_t s0 = (uint32_t)((p % B) * ndl + p / B);
-        idx.push_back(s0); idx.push_back(s0 + (uint32_t)half_rows);
-      }
-      std::vector<fe> vals(idx.size());
-      dev_buf<uint32_t> di; dev_buf<fe> dv; ZKL_CHECK(ctx, di.alloc(idx.size())); ZKL_CHECK(ctx, dv.alloc(idx.size()));
-      ZKL_CHECK(ctx, cudaMemcpyAsync(di.p, idx.data(), idx.size() * 4, cudaMemcpyHostToDevice, st));
-      LAUNCH(ctx, k_gather_fe, ceil_div(idx.size(), 128), 128, 0, ev, di.p, (int)idx.size(), dv.p);
-      ZKL_CHECK(ctx, cudaMemcpyAsync(vals.data(), dv.p, vals.size() * sizeof(fe), cudaMemcpyDeviceToHost, st));
-      ZKL_CHECK(ctx, cudaStreamSynchronize(st));
-      std::vector<std::vector<fe>> lists;
-      ZKL_TRY(fetch_batch_proof(ctx, f_leaves[d].p, f_nodes[d].p, batch_proof_plan(fp, half), lists));
-      byte_writer pw; write_batch_proof_bytes(pw, ilog2_sz(half), lists);
-      wr.u32((uint32_t)(vals.size() * 16)); wr.bytes(vals.data(), vals.size() * 16);
-      wr.u32((uint32_t)pw.b.size()); wr.bytes(pw.b.data(), pw.b.size());
-      ev = f_ev[d + 1].p; dom = half; ndl = half_rows;
-    }
+  for (size_t d = 0; d < nl; d++) {
+    size_t cnt = 2 * fri_counts[d];
+    const fe *vals = got.data() + gp; gp += cnt;
+    byte_writer pw; write_batch_proof_bytes(pw, tj_fri[d].depth, take_lists(tj_fri[d]));
+    wr.u32((uint32_t)(cnt * 16)); wr.bytes(vals, cnt * 16);
+    wr.u32((uint32_t)pw.b.size()); wr.bytes(pw.b.data(), pw.b.size());
   }
   wr.u16((uint16_t)(rem_len * 16));
   for (auto &c : rem_h) wr.felt(c);
@@ -613,7 +643,9 @@ static int prove_segment_impl(zkl_ctx *ctx, const fe *trace_dev, size_t W, size_
     summary->num_unique_queries = (uint32_t)pos.size();
     for (size_t i = 0; i < pos.size(); i++) summary->positions[i] = pos[i];
     ZKL_CHECK(ctx, cudaEventSynchronize(ctx->ev[evi - 1]));
-    for (int i = 0; i + 1 < evi && i < 12; i++) cudaEventElapsedTime(&summary->stage_ms[i], ctx->ev[i], ctx->ev[i + 1]);
+    for (int i = 0; i + 1 < evi && i < 9; i++) cudaEventElapsedTime(&summary->stage_ms[i], ctx->ev[i], ctx->ev[i + 1]);
+    cudaEventElapsedTime(&summary->stage_ms[9], ctx->ev[12], ctx->ev[13]);   // trace LDE kernel alone
+    cudaEventElapsedTime(&summary->stage_ms[10], ctx->ev[13], ctx->ev[14]);  // trace row-hash kernel alone
     // composition degree overflow (constraints not satisfied): reported, not fatal — Winterfell only checks it in debug builds
     if (!fe_is_zero(flag_h)) summary->stage_ms[11] = -1.0f;
   }
@@ -632,7 +664,7 @@ extern "C" int zkl_prove_segment_dev(zkl_ctx *ctx, const void *trace_dev, size_t
 }
 extern "C" int zkl_prove_segment(zkl_ctx *ctx, const zkl_fe *trace, size_t width, size_t n, const zkl_air_params *air, const zkl_fe *seed_elems,
                                  size_t num_seed, const zkl_options *opts, uint8_t *out_proof, size_t *out_len, zkl_proof_summary *summary) {
-  ZKL_CHECK(ctx, cudaSetDevice(ctx->device));
+  ZKL_TRY(enter(ctx));
   dev_buf<fe> tr; ZKL_CHECK(ctx, tr.alloc(width * n));
   ZKL_CHECK(ctx, cudaMemcpyAsync(tr.p, trace, width * n * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream));
   return prove_segment_impl(ctx, tr.p, width, n, air, seed_elems, num_seed, opts, out_proof, out_len, summary);
@@ -647,3 +679,52 @@ extern "C" int zkl_dev_upload(zkl_ctx *ctx, void *dev, const void *host, size_t 
   return 0;
 }
 extern "C" int zkl_sync(zkl_ctx *ctx) { ZKL_CHECK(ctx, cudaSetDevice(ctx->device)); ZKL_CHECK(ctx, cudaStreamSynchronize(ctx->stream)); return 0; }
+
+// ------------------------------------------------------------------------------------------------
+// measurement helpers (bench.py): stream timers and an IMAD.WIDE peak probe
+// ------------------------------------------------------------------------------------------------
+extern "C" int zkl_timer_start(zkl_ctx *ctx) {
+  ZKL_TRY(enter(ctx));
+  while (ctx->ev.size() < 18) { cudaEvent_t e; ZKL_CHECK(ctx, cudaEventCreate(&e)); ctx->ev.push_back(e); }
+  ZKL_CHECK(ctx, cudaEventRecord(ctx->ev[16], ctx->stream));
+  return 0;
+}
+extern "C" int zkl_timer_stop(zkl_ctx *ctx, float *ms) {
+  ZKL_CHECK(ctx, cudaSetDevice(ctx->device));
+  ZKL_CHECK(ctx, cudaEventRecord(ctx->ev[17], ctx->stream));
+  ZKL_CHECK(ctx, cudaEventSynchronize(ctx->ev[17]));
+  ZKL_CHECK(ctx, cudaEventElapsedTime(ms, ctx->ev[16], ctx->ev[17]));
+  return 0;
+}
+// dependency-free 32x32+64 multiply-accumulate chains: the integer-pipe roofline denominator
+__global__ void __launch_bounds__(256) k_imad_probe(uint32_t seed, int iters, unsigned long long *sink) {
+  unsigned long long a[8];
+  uint32_t x = seed + threadIdx.x, y = seed * 2654435761u + blockIdx.x;
+#pragma unroll
+  for (int i = 0; i < 8; i++) a[i] = i + x;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) a[i] = (unsigned long long)x * (uint32_t)(y + i) + a[i];   // IMAD.WIDE.U32
+    x ^= (uint32_t)a[0];
+  }
+  unsigned long long s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) s ^= a[i];
+  if (s == 0x123456789ull) *sink = s;
+}
+// returns wide multiply-accumulates per second (whole GPU)
+extern "C" int zkl_imad_peak(zkl_ctx *ctx, double *wide_macs_per_s) {
+  ZKL_TRY(enter(ctx));
+  dev_buf<unsigned long long> sink; ZKL_CHECK(ctx, sink.alloc(1));
+  const int iters = 4096, blocks = ctx->num_sms * 8;
+  float best = 1e30f, ms = 0;
+  for (int rep = 0; rep < 4; rep++) {
+    ZKL_TRY(zkl_timer_start(ctx));
+    LAUNCH(ctx, k_imad_probe, blocks, 256, 0, 12345u + rep, iters, sink.p);
+    ZKL_TRY(zkl_timer_stop(ctx, &ms));
+    if (rep && ms < best) best = ms;
+  }
+  *wide_macs_per_s = (double)blocks * 256.0 * iters * 8.0 / (best * 1e-3);
+  return 0;
+}
+extern "C" int zkl_set_bulk_threshold(zkl_ctx *ctx, long sponges) { ctx->bulk_threshold = sponges; return 0; }

@@ -51,17 +51,29 @@ struct zkl_ctx {
 static inline int ceil_div(size_t a, size_t b) { return (int)((a + b - 1) / b); }
 static inline int ilog2_sz(size_t n) { int k = 0; while (((size_t)1 << k) < n) k++; return k; }
 
-// device scratch with RAII (stream-ordered frees are not needed: buffers live until the handle dies)
+// device scratch with RAII. Allocation is STREAM-ORDERED (cudaMallocAsync / cudaFreeAsync on the calling
+// context's stream, pool release threshold = unlimited), so concurrent segment streams never hit the
+// device-wide synchronisation of cudaMalloc/cudaFree.
+static thread_local cudaStream_t tl_stream = nullptr;
+static thread_local bool tl_stream_set = false;
 template <typename T>
 struct dev_buf {
-  T *p = nullptr; size_t n = 0;
+  T *p = nullptr; size_t n = 0; cudaStream_t s = nullptr; bool async = false;
   dev_buf() {}
   dev_buf(const dev_buf &) = delete;
   dev_buf &operator=(const dev_buf &) = delete;
-  ~dev_buf() { if (p) cudaFree(p); }
+  dev_buf(dev_buf &&o) noexcept : p(o.p), n(o.n), s(o.s), async(o.async) { o.p = nullptr; }
+  ~dev_buf() { release(); }
+  void release() {
+    if (!p) return;
+    if (async) cudaFreeAsync(p, s); else cudaFree(p);
+    p = nullptr;
+  }
   cudaError_t alloc(size_t count) {
-    if (p) { cudaFree(p); p = nullptr; }
+    release();
     n = count;
+    if (tl_stream_set) { async = true; s = tl_stream; return cudaMallocAsync((void **)&p, count * sizeof(T) + 16, s); }
+    async = false;
     return cudaMalloc((void **)&p, count * sizeof(T) + 16);
   }
 };

@@ -37,6 +37,19 @@ ZKL_HD uint32_t sub_bio(uint32_t a, uint32_t b, uint32_t &bw) {
   uint64_t t = (uint64_t)a - b - bw; bw = (uint32_t)(t >> 63); return (uint32_t)t;
 }
 
+#if defined(__CUDA_ARCH__)
+// PTX carry-flag primitives. Consecutive asm volatile statements keep their order, and nothing the
+// compiler generates itself touches CC, so a chain add_cc -> addc_cc -> ... -> addc is one IADD3/IADD3.X
+// ripple on the ALU pipe (keeping carry arithmetic OFF the multiply pipe, which is the bottleneck).
+__device__ __forceinline__ uint32_t p_add_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ uint32_t p_addc_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ uint32_t p_addc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("addc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ uint32_t p_sub_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("sub.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ uint32_t p_subc_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("subc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ uint32_t p_subc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("subc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ uint32_t p_shf_l(uint32_t lo, uint32_t hi, uint32_t n) { uint32_t r; asm("shf.l.clamp.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(lo), "r"(hi), "r"(n)); return r; }
+#endif
+
 ZKL_HD fe fe_zero() { fe r; r.l[0] = r.l[1] = r.l[2] = r.l[3] = 0; return r; }
 ZKL_HD fe fe_one() { fe r; r.l[0] = 1; r.l[1] = r.l[2] = r.l[3] = 0; return r; }
 ZKL_HD fe fe_from_u64(uint64_t x) { fe r; r.l[0] = (uint32_t)x; r.l[1] = (uint32_t)(x >> 32); r.l[2] = r.l[3] = 0; return r; }
@@ -184,6 +197,36 @@ ZKL_HD void wacc_mad(wide_acc &w, const fe &a, const fe &b) {
 //   hi*C = (hi*45 << 40) - hi                      (non-negative, < 2^182)
 //   y = lo + hi*C = lo2 + hi2*2^128, hi2 < 2^55    -> second fold, then one conditional fix-up.
 ZKL_HD fe reduce9(const uint32_t x[9]) {
+#if defined(__CUDA_ARCH__)
+  // t = hi * 45 (hi = x[4..8]): five independent wide products, then one ripple add
+  uint64_t P0 = (uint64_t)x[4] * 45u, P1 = (uint64_t)x[5] * 45u, P2 = (uint64_t)x[6] * 45u, P3 = (uint64_t)x[7] * 45u,
+           P4 = (uint64_t)x[8] * 45u;
+  uint32_t t0 = (uint32_t)P0;
+  uint32_t t1 = p_add_cc((uint32_t)P1, (uint32_t)(P0 >> 32));
+  uint32_t t2 = p_addc_cc((uint32_t)P2, (uint32_t)(P1 >> 32));
+  uint32_t t3 = p_addc_cc((uint32_t)P3, (uint32_t)(P2 >> 32));
+  uint32_t t4 = p_addc_cc((uint32_t)P4, (uint32_t)(P3 >> 32));
+  uint32_t t5 = p_addc((uint32_t)(P4 >> 32), 0);
+  // s = t << 40 (limbs 1..7), u = s - hi, y = lo + u   (u >= 0; y < 2^183)
+  uint32_t s1 = t0 << 8, s2 = p_shf_l(t0, t1, 8), s3 = p_shf_l(t1, t2, 8), s4 = p_shf_l(t2, t3, 8), s5 = p_shf_l(t3, t4, 8),
+           s6 = p_shf_l(t4, t5, 8), s7 = t5 >> 24;
+  uint32_t u0 = p_sub_cc(0, x[4]), u1 = p_subc_cc(s1, x[5]), u2 = p_subc_cc(s2, x[6]), u3 = p_subc_cc(s3, x[7]),
+           u4 = p_subc_cc(s4, x[8]), u5 = p_subc_cc(s5, 0), u6 = p_subc_cc(s6, 0), u7 = p_subc(s7, 0);
+  (void)u6; (void)u7;  // zero by the bound above
+  uint32_t y0 = p_add_cc(x[0], u0), y1 = p_addc_cc(x[1], u1), y2 = p_addc_cc(x[2], u2), y3 = p_addc_cc(x[3], u3),
+           y4 = p_addc_cc(u4, 0), y5 = p_addc(u5, 0);
+  // second fold: hi2 = y5:y4 (< 2^55); v = hi2 * 45 (< 2^61); a = y_lo + (v << 40) ; z = a - hi2 (>= 0), 129 bits
+  uint64_t v = (((uint64_t)y5 << 32) | y4) * 45u;
+  uint32_t v0 = (uint32_t)v, v1 = (uint32_t)(v >> 32);
+  uint32_t a0 = y0;
+  uint32_t a1 = p_add_cc(y1, v0 << 8), a2 = p_addc_cc(y2, p_shf_l(v0, v1, 8)), a3 = p_addc_cc(y3, v1 >> 24), a4 = p_addc(0, 0);
+  uint32_t z0 = p_sub_cc(a0, y4), z1 = p_subc_cc(a1, y5), z2 = p_subc_cc(a2, 0), z3 = p_subc_cc(a3, 0), c3 = p_subc(a4, 0);
+  // Z = z + c3*2^128 ≡ z + c3*C. If c3: z is tiny and z + C is the answer; else subtract p iff z + C overflows.
+  uint32_t q0 = p_add_cc(z0, ZKL_C0), q1 = p_addc_cc(z1, ZKL_C1), q2 = p_addc_cc(z2, 0), q3 = p_addc_cc(z3, 0), c5 = p_addc(0, 0);
+  bool take = (c3 | c5) != 0;
+  fe r; r.l[0] = take ? q0 : z0; r.l[1] = take ? q1 : z1; r.l[2] = take ? q2 : z2; r.l[3] = take ? q3 : z3;
+  return r;
+#else
   // t = hi * 45 : 6 limbs (hi 5 limbs -> up to 142 bits)
   uint32_t t[6];
   {
@@ -231,10 +274,20 @@ ZKL_HD fe reduce9(const uint32_t x[9]) {
   fe r;
   r.l[0] = c5 ? q.l[0] : z.l[0]; r.l[1] = c5 ? q.l[1] : z.l[1]; r.l[2] = c5 ? q.l[2] : z.l[2]; r.l[3] = c5 ? q.l[3] : z.l[3];
   return r;
+#endif
 }
 
 // merge the even/odd accumulators and the carry counters into 9 plain limbs
 ZKL_HD void wacc_merge(const wide_acc &w, uint32_t x[9]) {
+#if defined(__CUDA_ARCH__)
+  x[0] = w.ev[0];
+  x[1] = p_add_cc(w.ev[1], w.od[0]); x[2] = p_addc_cc(w.ev[2], w.od[1]); x[3] = p_addc_cc(w.ev[3], w.od[2]);
+  uint32_t m4 = p_addc_cc(w.ev[4], w.od[3]), m5 = p_addc_cc(w.ev[5], w.od[4]), m6 = p_addc_cc(w.ev[6], w.od[5]),
+           m7 = p_addc_cc(w.ev[7], 0), m8 = p_addc(0, 0);
+  x[4] = p_add_cc(m4, w.cnt[0]); x[5] = p_addc_cc(m5, w.cnt[1]); x[6] = p_addc_cc(m6, w.cnt[2]); x[7] = p_addc_cc(m7, w.cnt[3]);
+  x[8] = p_addc(m8, w.cnt[4]);
+  return;
+#else
   uint32_t c;
   x[0] = w.ev[0];
   x[1] = add_co(w.ev[1], w.od[0], c);
@@ -243,16 +296,23 @@ ZKL_HD void wacc_merge(const wide_acc &w, uint32_t x[9]) {
   x[8] = c;
   x[4] = add_co(x[4], w.cnt[0], c); x[5] = add_cio(x[5], w.cnt[1], c); x[6] = add_cio(x[6], w.cnt[2], c);
   x[7] = add_cio(x[7], w.cnt[3], c); x[8] = add_cio(x[8], w.cnt[4], c);
+#endif
 }
 ZKL_HD fe wacc_reduce(const wide_acc &w) {
   uint32_t x[9]; wacc_merge(w, x); return reduce9(x);
 }
 // add a canonical element to the accumulator (round constants): goes through the even limbs
 ZKL_HD void wacc_add_fe(wide_acc &w, const fe &a) {
+#if defined(__CUDA_ARCH__)
+  w.ev[0] = p_add_cc(w.ev[0], a.l[0]); w.ev[1] = p_addc_cc(w.ev[1], a.l[1]);
+  w.ev[2] = p_addc_cc(w.ev[2], a.l[2]); w.ev[3] = p_addc_cc(w.ev[3], a.l[3]);
+  w.cnt[0] = p_addc(w.cnt[0], 0);
+#else
   uint32_t c;
   w.ev[0] = add_co(w.ev[0], a.l[0], c); w.ev[1] = add_cio(w.ev[1], a.l[1], c);
   w.ev[2] = add_cio(w.ev[2], a.l[2], c); w.ev[3] = add_cio(w.ev[3], a.l[3], c);
   w.cnt[0] += c;
+#endif
 }
 
 ZKL_HD fe fe_mul(const fe &a, const fe &b) {
@@ -280,6 +340,14 @@ ZKL_HD fe fe_inv(const fe &a) {
 
 // x mod p for an arbitrary 128-bit value (x < 2^128 < 2p): utils.rs:50-66 be_from_u128
 ZKL_HD fe fe_from_u128_mod(const fe &x) {
+#if defined(__CUDA_ARCH__)
+  {
+    uint32_t q0 = p_add_cc(x.l[0], ZKL_C0), q1 = p_addc_cc(x.l[1], ZKL_C1), q2 = p_addc_cc(x.l[2], 0), q3 = p_addc_cc(x.l[3], 0),
+             c = p_addc(0, 0);
+    fe r; r.l[0] = c ? q0 : x.l[0]; r.l[1] = c ? q1 : x.l[1]; r.l[2] = c ? q2 : x.l[2]; r.l[3] = c ? q3 : x.l[3];
+    return r;
+  }
+#endif
   fe q; uint32_t c;
   q.l[0] = add_co(x.l[0], ZKL_C0, c); q.l[1] = add_cio(x.l[1], ZKL_C1, c);
   q.l[2] = add_cio(x.l[2], 0, c); q.l[3] = add_cio(x.l[3], 0, c);
@@ -287,6 +355,15 @@ ZKL_HD fe fe_from_u128_mod(const fe &x) {
 }
 // lo + hi * 2^64 mod p for canonical lo, hi: utils.rs:359-371 fold_bytes32_to_fe (after per-half reduction)
 ZKL_HD fe fe_fold_pair(const fe &lo, const fe &hi) {
+#if defined(__CUDA_ARCH__)
+  {
+    uint32_t x[9];
+    x[0] = lo.l[0]; x[1] = lo.l[1];
+    x[2] = p_add_cc(lo.l[2], hi.l[0]); x[3] = p_addc_cc(lo.l[3], hi.l[1]); x[4] = p_addc_cc(hi.l[2], 0); x[5] = p_addc_cc(hi.l[3], 0);
+    x[6] = p_addc(0, 0); x[7] = 0; x[8] = 0;
+    return reduce9(x);
+  }
+#endif
   uint32_t x[9], c;
   x[0] = lo.l[0]; x[1] = lo.l[1];
   x[2] = add_co(lo.l[2], hi.l[0], c); x[3] = add_cio(lo.l[3], hi.l[1], c);

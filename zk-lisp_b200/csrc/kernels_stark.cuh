@@ -23,6 +23,13 @@ __global__ void k_gather_fe(const fe *__restrict__ src, const uint32_t *__restri
   st_fe(out + t, ld_fe(src + idx[t]));
 }
 
+// out[i] = src[i][idx[i]] — one launch gathers every opened row, FRI value and Merkle node of a proof
+__global__ void k_gather_multi(const fe *const *__restrict__ src, const uint32_t *__restrict__ idx, int count, fe *__restrict__ out) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= count) return;
+  st_fe(out + t, ld_fe(src[t] + idx[t]));
+}
+
 // ---------------------------------------------------------------- Fiat-Shamir coin (winter-crypto DefaultRandomCoin [WF-mem])
 // The seed lives on the device; the draw counter is tracked by the host (it is data independent).
 __global__ void k_coin_init(const fe *__restrict__ elems, int count, fe *seed) {  // seed = hash_elements(elems)

@@ -49,6 +49,13 @@ extern "C" int zkl_ctx_create(int device, zkl_ctx **out) {
   if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) {
     g_create_error = cudaGetErrorString(e); delete c; return 1;
   }
+  {  // keep freed blocks in the pool: no trimming at synchronisation points
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      uint64_t thr = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+  }
   // opt in to large dynamic shared memory for the single-pass column transforms
   cudaFuncSetAttribute(k_interpolate, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
   cudaFuncSetAttribute(k_lde, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
@@ -69,6 +76,7 @@ extern "C" int zkl_ctx_create(int device, zkl_ctx **out) {
 extern "C" void zkl_ctx_destroy(zkl_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
+  if (tl_stream == ctx->stream) { tl_stream = nullptr; tl_stream_set = false; }
   cudaStreamSynchronize(ctx->stream);
   for (auto &kv : ctx->tables) { cudaFree(kv.second.wpow); }
   for (auto &kv : ctx->opow) cudaFree(kv.second);
@@ -91,9 +99,15 @@ extern "C" int zkl_suite_load(zkl_ctx *ctx, const zkl_suite *s) {
   ctx->suite_loaded = true;
   return 0;
 }
+// every entry point binds the calling thread to the context's device and stream (stream-ordered allocator)
+static int enter(zkl_ctx *ctx) {
+  if (cudaSetDevice(ctx->device) != cudaSuccess) { ctx->set_error("cudaSetDevice failed"); return 1; }
+  tl_stream = ctx->stream; tl_stream_set = true;
+  return 0;
+}
 static int need_suite(zkl_ctx *ctx) {
   if (!ctx->suite_loaded) { ctx->set_error("zkl_suite_load has not been called on this context"); return 1; }
-  return cudaSetDevice(ctx->device) == cudaSuccess ? 0 : (ctx->set_error("cudaSetDevice failed"), 1);
+  return enter(ctx);
 }
 
 // w_N^m table and offset powers -------------------------------------------------------------------
@@ -279,7 +293,7 @@ extern "C" int zkl_merkle_build(zkl_ctx *ctx, const uint8_t *leaves, size_t coun
 // NTT primitives
 // ------------------------------------------------------------------------------------------------
 extern "C" int zkl_interpolate_columns(zkl_ctx *ctx, zkl_fe *cols, size_t ncols, size_t n) {
-  ZKL_CHECK(ctx, cudaSetDevice(ctx->device));
+  ZKL_TRY(enter(ctx));
   dev_buf<fe> d; ZKL_CHECK(ctx, d.alloc(ncols * n));
   ZKL_CHECK(ctx, cudaMemcpyAsync(d.p, cols, ncols * n * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream));
   ZKL_TRY(dev_interpolate(ctx, d.p, d.p, ncols, n));
@@ -289,7 +303,7 @@ extern "C" int zkl_interpolate_columns(zkl_ctx *ctx, zkl_fe *cols, size_t ncols,
 }
 extern "C" int zkl_evaluate_columns(zkl_ctx *ctx, const zkl_fe *polys, size_t ncols, size_t n, size_t blowup, zkl_fe offset,
                                     zkl_fe *out) {
-  ZKL_CHECK(ctx, cudaSetDevice(ctx->device));
+  ZKL_TRY(enter(ctx));
   if (!(offset.lo == 3 && offset.hi == 0)) { ctx->set_error("only the Winterfell domain offset GENERATOR = 3 is supported"); return 1; }
   size_t N = n * blowup;
   dev_buf<fe> p, cm, nat; ZKL_CHECK(ctx, p.alloc(ncols * n)); ZKL_CHECK(ctx, cm.alloc(ncols * N)); ZKL_CHECK(ctx, nat.alloc(ncols * N));

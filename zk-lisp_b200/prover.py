@@ -213,9 +213,15 @@ class ZkProver:
     def __init__(self, ctx: Context, options: air_mod.ProofOptions, air_pi: air_mod.AirPublicInputs):
         self.ctx, self.options, self.air_pi = ctx, options, air_pi
         self.last_summary = None
+        self._cache = {}
 
-    def _air(self, width, n) -> air_mod.Air:
-        return air_mod.Air(width, n, self.air_pi, self.options)
+    def _air(self, width, n):
+        """(Air, zkl_air_params, seed elements) for this trace shape; built once per prover like `Air::new`."""
+        key = (width, n)
+        if key not in self._cache:
+            a = air_mod.Air(width, n, self.air_pi, self.options)
+            self._cache[key] = (a, a.to_c(), ints_to_fe(a.seed_elements()))
+        return self._cache[key]
 
     # hook 1 (prove.rs:454-474)
     def new_trace_lde(self, trace: np.ndarray):
@@ -231,8 +237,7 @@ class ZkProver:
 
     # hook 2 (prove.rs:476-492) + ConstraintEvaluator::evaluate
     def evaluate_constraints(self, trace_lde: TraceLde, coeffs: np.ndarray) -> np.ndarray:
-        a = self._air(trace_lde.width, trace_lde.n)
-        ap = a.to_c()
+        a, ap, _ = self._air(trace_lde.width, trace_lde.n)
         cc = as_fe_array(coeffs)
         assert cc.shape[0] == a.num_constraints
         out = np.zeros((trace_lde.n * a.ce_blowup, 2), dtype=np.uint64)
@@ -259,9 +264,7 @@ class ZkProver:
             width, n = t.shape[0], t.shape[1]
         else:
             width, n = shape
-        a = self._air(width, n)
-        ap = a.to_c()
-        seed = ints_to_fe(a.seed_elements())
+        a, ap, seed = self._air(width, n)
         o = self.options.to_c()
         cap = C.c_size_t(4 << 20)
         buf = np.zeros(cap.value, dtype=np.uint8)
