@@ -37,6 +37,10 @@ WORKLOAD = "rollup-bench: 16 segments x (n=4096, W=204, blowup=16, q=64, grind=1
 # products + 12x12 MDS = 144 products) = 4536 field products = 4536*16 32x32->64 multiply-accumulates.
 PERMS_PER_ROW = 11
 WIDE_MACS_PER_PERM = 27 * (24 + 144) * 16
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full captures under profiles/
+# (r01: k_hash_rows 216.2 MB + 9.0 MB; algorithmic 16*204*65536 = 213.9 MB read + 1 MB written)
+TRAFFIC_HASH_ROWS_BYTES = 225.1e6
+TRAFFIC_LDE_BYTES = None
 
 
 def parse_args():
@@ -45,7 +49,9 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--streams", type=int, default=4, help="concurrent segment streams per GPU")
+    ap.add_argument("--streams", type=int, default=8, help="concurrent segment streams per GPU")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: 16 segments per GPU per step; strong: the 16 segments of one rollup-bench split over the GPUs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--bulk-threshold", type=int, default=0)
     return ap.parse_args()
@@ -209,8 +215,14 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the proving path has no CPU fallback")
     device = local
 
-    segs = make_workload(zkl, SEGMENTS, ROWS, seed0=0x5A4B4C + 1000 * rank)
-    S = max(1, min(args.streams, SEGMENTS))
+    if args.scaling == "weak":
+        my_ids = zkl.sharding.weak_scaling_segments(SEGMENTS, rank)
+    else:
+        my_ids = zkl.sharding.segments_for_rank(SEGMENTS, rank, world)
+    import synth
+    segs = [synth.valid_segment(n=ROWS, queries=QUERIES, blowup=BLOWUP, grind=GRIND, seed=0x5A4B4C + i, start_level=(i % 16) * (ROWS // 32))
+            for i in my_ids]
+    S = max(1, min(args.streams, len(segs)))
     workers = [Worker(zkl, device, segs[i::S], args.bulk_threshold) for i in range(S)]
     # pinned host buffers for the e2e leg
     for w in workers:
@@ -256,9 +268,16 @@ def main():
     h2d = sum(t.nbytes for w in workers for _, t, _ in w.items)
     d2h = sum(w.proof_bytes for w in workers)
 
-    rows_total = world * SEGMENTS * ROWS * args.steps
+    rows_local = len(segs) * ROWS * args.steps
+    rows_total, _ = zkl.sharding.aggregate(rows_local, 0.0, dist if world > 1 else None, "cuda")
     value = rows_total / (ev_total * 1e-3)
     e2e_value = rows_total / (e2e_ev * 1e-3)
+    # stream-exclusive pass (nothing else on the GPU) for the per-kernel roofline numbers
+    barrier()
+    workers[0].items = workers[0].items[:1]
+    workers[0].run(True)
+    excl = np.array(list(workers[0].summaries[0].stage_ms))
+    barrier()
 
     if rank == 0:
         peaks = {}
@@ -270,7 +289,7 @@ def main():
         imad = C.c_double()
         workers[0].ctx._check(workers[0].ctx.lib.zkl_imad_peak(workers[0].ctx.h, C.byref(imad)))
         N = ROWS * BLOWUP
-        hash_ms, lde_ms = float(stage[10]), float(stage[9])
+        hash_ms, lde_ms = float(excl[10]), float(excl[9])
         hash_macs = N * PERMS_PER_ROW * WIDE_MACS_PER_PERM
         lde_bytes = 16 * 204 * ROWS * (1 + BLOWUP)
         roofline = {
@@ -278,12 +297,13 @@ def main():
             "bound": "int32-multiply pipe (IMAD.WIDE.U32); not hbm/tensor: 4536 field products per 3.3 KB row",
             "achieved": hash_macs / (hash_ms * 1e-3) / 1e12, "peak": imad.value / 1e12, "unit": "T wide-MAC/s (32x32+64)",
             "frac": (hash_macs / (hash_ms * 1e-3)) / imad.value, "peak_source": "zkl_imad_peak probe measured in this run",
-            "traffic": None, "ms_per_launch": hash_ms, "timing": "concurrent with other segment streams" if S > 1 else "stream-exclusive",
+            "traffic": TRAFFIC_HASH_ROWS_BYTES, "ms_per_launch": hash_ms, "ms_per_launch_in_timed_region": float(stage[10]),
+            "timing": "ms_per_launch is taken on an otherwise idle GPU right after the timed region; inside it the kernel shares the SMs with the other streams",
         }
         roofline_lde = {
             "kernel": "k_lde (trace coset LDE, one CTA per column x coset, single pass over HBM)",
             "bound": "hbm", "achieved": lde_bytes / (lde_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-            "frac": lde_bytes / (lde_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src, "traffic": None, "ms_per_launch": lde_ms,
+            "frac": lde_bytes / (lde_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src, "traffic": TRAFFIC_LDE_BYTES, "ms_per_launch": lde_ms,
             "note": "f128: 14 modmuls (~1400 instructions) per 16-byte element written, so the kernel is integer-bound far below the HBM roof",
         }
         cpu = None
@@ -294,9 +314,9 @@ def main():
                    "sample": f"{cores} segments in flight, n=512, W=204, blowup=16, q=64, grind=13 ({dt:.1f} s of wall time)"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ev_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ev_total / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "u128 (f128 field, 4x u32 limbs)", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "segments_per_gpu_per_step": SEGMENTS, "streams_per_gpu": S,
+            "config": {"workload": WORKLOAD, "segments_per_gpu_per_step": len(segs), "streams_per_gpu": S,
                        "l2": "per-step working set 16 x 250 MB LDE matrices >> 126 MB L2 (no flush needed)",
                        "published_reference": "109.567 s on Apple M3 Max for the same 65536 rows (BASELINE.md), different hardware"},
             "wall_ms_per_step": wall_total / args.steps,

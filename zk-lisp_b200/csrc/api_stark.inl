@@ -243,10 +243,19 @@ static int dev_eval_constraints(zkl_ctx *ctx, const committed_matrix &t, const z
   if (n < 32) { ctx->set_error("trace length must be >= 32 (one schedule level)"); return 1; }
   domain_tables *tN, *tM, *tn;
   ZKL_TRY(get_tables(ctx, N, &tN)); ZKL_TRY(get_tables(ctx, M, &tM)); ZKL_TRY(get_tables(ctx, n, &tn));
-  // periodic table
-  ZKL_CHECK(ctx, st.per.alloc(ce * 32 * 31));
+  // periodic table: data independent, cached per (n, ce)
   fe g = fe_from_u64(3);
-  LAUNCH(ctx, k_periodic_table, ceil_div(ce * 32, 64), 64, 0, st.per.p, (int)ce, (int)n, tM->wpow, M, fe_pow(g, n / 32), fe_inv(fe_from_u64(32)));
+  fe *per_tab;
+  {
+    size_t key = (n << 8) | ce;
+    auto it = ctx->periodic.find(key);
+    if (it == ctx->periodic.end()) {
+      fe *p; ZKL_CHECK(ctx, cudaMalloc((void **)&p, ce * 32 * 31 * sizeof(fe)));
+      LAUNCH(ctx, k_periodic_table, ceil_div(ce * 32, 64), 64, 0, p, (int)ce, (int)n, tM->wpow, M, fe_pow(g, n / 32), fe_inv(fe_from_u64(32)));
+      it = ctx->periodic.emplace(key, p).first;
+    }
+    per_tab = it->second;
+  }
   // per-coset constants: x^n = g^n * w_ce^k'
   std::vector<fe> cconst(2 * ce + 2);
   fe gn = fe_pow(g, n), wce = host_root_of_unity(ilog2_sz(ce)), wk = fe_one();
@@ -267,7 +276,7 @@ static int dev_eval_constraints(zkl_ctx *ctx, const committed_matrix &t, const z
   ZKL_TRY(dev_interpolate(ctx, st.u.p, st.u.p, nb, n));
   ZKL_TRY(dev_lde(ctx, st.u.p, st.bpoly.p, nb, n, ce));
   boundary_dev bd{st.slot_col.p, st.bpoly.p, st.nslots};
-  LAUNCH(ctx, k_eval_constraints, ceil_div(M, 128), 128, 0, st.air.p, t.lde.p, N, (int)n, (int)t.blowup, (int)ce, st.per.p, tN->wpow, cc_dev, bd,
+  LAUNCH(ctx, k_eval_constraints, ceil_div(M, 128), 128, 0, st.air.p, t.lde.p, N, (int)n, (int)t.blowup, (int)ce, per_tab, tN->wpow, cc_dev, bd,
          st.coset_consts.p, ce_out);
   return 0;
 }

@@ -44,6 +44,7 @@ struct zkl_ctx {
   long bulk_threshold = 1 << 17;
   std::map<size_t, domain_tables> tables;  // by N
   std::map<size_t, fe *> opow;             // GENERATOR^j tables by n
+  std::map<size_t, fe *> periodic;         // periodic-column tables by (n << 8 | ce)
   std::vector<cudaEvent_t> ev;             // stage timing events
   void set_error(const std::string &e) { err = e; }
 };

@@ -60,12 +60,17 @@ __device__ __noinline__ void permute(fe *st) {
 #pragma unroll
     for (int i = 0; i < 12; i++) c[i] = fe_cube(lds_fe(st + i * ZKL_HASH_THREADS));
 #pragma unroll 1
-    for (int i = 0; i < 12; i++) {
-      wide_acc w; wacc_zero(w);
+    for (int i = 0; i < 12; i += 2) {  // two output lanes per iteration: two independent carry chains in flight
+      wide_acc w0, w1; wacc_zero(w0); wacc_zero(w1);
 #pragma unroll
-      for (int k = 0; k < 12; k++) wacc_mad(w, c[k], ldc_fe(&c_suite.mds[i][k]));
-      wacc_add_fe(w, ldc_fe(&c_suite.rc[r][i]));
-      sts_fe(st + i * ZKL_HASH_THREADS, wacc_reduce(w));
+      for (int k = 0; k < 12; k++) {
+        wacc_mad(w0, c[k], ldc_fe(&c_suite.mds[i][k]));
+        wacc_mad(w1, c[k], ldc_fe(&c_suite.mds[i + 1][k]));
+      }
+      wacc_add_fe(w0, ldc_fe(&c_suite.rc[r][i]));
+      wacc_add_fe(w1, ldc_fe(&c_suite.rc[r][i + 1]));
+      sts_fe(st + i * ZKL_HASH_THREADS, wacc_reduce(w0));
+      sts_fe(st + (i + 1) * ZKL_HASH_THREADS, wacc_reduce(w1));
     }
   }
 }

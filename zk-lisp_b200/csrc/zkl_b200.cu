@@ -80,6 +80,7 @@ extern "C" void zkl_ctx_destroy(zkl_ctx *ctx) {
   cudaStreamSynchronize(ctx->stream);
   for (auto &kv : ctx->tables) { cudaFree(kv.second.wpow); }
   for (auto &kv : ctx->opow) cudaFree(kv.second);
+  for (auto &kv : ctx->periodic) cudaFree(kv.second);
   for (auto e : ctx->ev) cudaEventDestroy(e);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
