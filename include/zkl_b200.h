@@ -228,6 +228,8 @@ int zkl_timer_stop(zkl_ctx *ctx, float *ms);   /* second event, synchronised; el
 int zkl_imad_peak(zkl_ctx *ctx, double *wide_macs_per_s); /* dependency-free IMAD.WIDE.U32 probe */
 /* sponge count from which thread-per-sponge kernels replace the 16-thread cooperative ones */
 int zkl_set_bulk_threshold(zkl_ctx *ctx, long sponges);
+/* permutation throughput probe on device-resident states: kind 0 = thread-per-state kernel, 1 = cooperative */
+int zkl_bench_permute(zkl_ctx *ctx, int kind, size_t count, int iters, float *ms_per_iter);
 
 #ifdef __cplusplus
 }

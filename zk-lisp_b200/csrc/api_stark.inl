@@ -737,3 +737,30 @@ extern "C" int zkl_imad_peak(zkl_ctx *ctx, double *wide_macs_per_s) {
   return 0;
 }
 extern "C" int zkl_set_bulk_threshold(zkl_ctx *ctx, long sponges) { ctx->bulk_threshold = sponges; return 0; }
+
+// permutation throughput probes on device-resident data: kind 0 = thread-per-state kernel, 1 = cooperative kernel
+__global__ void __launch_bounds__(ZKL_COOP_THREADS) k_coop_permute_batch(fe *states, size_t count) {
+  __shared__ fe s_xch[(ZKL_COOP_THREADS / ZKL_COOP_GROUP) * 24];
+  size_t g = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) / ZKL_COOP_GROUP;
+  const int l = threadIdx.x & (ZKL_COOP_GROUP - 1);
+  size_t gi = g < count ? g : count - 1;
+  fe st = l < 12 ? ld_fe(states + 12 * gi + l) : fe_zero();
+  coop_permute(st, l, s_xch + (threadIdx.x / ZKL_COOP_GROUP) * 24, 0xFFFFu << (threadIdx.x & 16));
+  if (g < count && l < 12) st_fe(states + 12 * g + l, st);
+}
+extern "C" int zkl_bench_permute(zkl_ctx *ctx, int kind, size_t count, int iters, float *ms_per_iter) {
+  ZKL_TRY(need_suite(ctx));
+  dev_buf<fe> d; ZKL_CHECK(ctx, d.alloc(count * 12));
+  ZKL_CHECK(ctx, cudaMemsetAsync(d.p, 0x11, count * 12 * sizeof(fe), ctx->stream));
+  float ms = 0;
+  for (int rep = 0; rep < 2; rep++) {
+    ZKL_TRY(zkl_timer_start(ctx));
+    for (int i = 0; i < iters; i++) {
+      if (kind == 0) LAUNCH(ctx, k_permute_batch, ceil_div(count, ZKL_HASH_THREADS), ZKL_HASH_THREADS, 0, d.p, count);
+      else LAUNCH(ctx, k_coop_permute_batch, ceil_div(count * ZKL_COOP_GROUP, ZKL_COOP_THREADS), ZKL_COOP_THREADS, 0, d.p, count);
+    }
+    ZKL_TRY(zkl_timer_stop(ctx, &ms));
+  }
+  *ms_per_iter = ms / iters;
+  return 0;
+}

@@ -41,7 +41,7 @@ struct zkl_ctx {
   uint64_t launches = 0;
   bool suite_loaded = false;
   // sponge count from which the thread-per-sponge kernels are used instead of the cooperative ones
-  long bulk_threshold = 1 << 17;
+  long bulk_threshold = 60000;
   std::map<size_t, domain_tables> tables;  // by N
   std::map<size_t, fe *> opow;             // GENERATOR^j tables by n
   std::map<size_t, fe *> periodic;         // periodic-column tables by (n << 8 | ce)

@@ -89,7 +89,7 @@ __device__ __forceinline__ fe merge_many_dev(const fe *d, size_t stride, int cou
 // Row hashing over a coset-major LDE: column c lives at lde + c*N, storage index s = k*n + i holds
 // the natural LDE row r = k + blowup*i. Thread (s, q) hashes columns [q*psize, min(W,(q+1)*psize))
 // of row r and writes digest to out[q*N + r].
-__global__ void __launch_bounds__(128) k_hash_rows(const fe *__restrict__ lde, size_t N, size_t n, int blowup, int W, int psize,
+__global__ void __launch_bounds__(ZKL_HASH_THREADS) k_hash_rows(const fe *__restrict__ lde, size_t N, size_t n, int blowup, int W, int psize,
                                                    int nchunks, fe *__restrict__ out) {
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= N * (size_t)nchunks) return;
@@ -100,19 +100,19 @@ __global__ void __launch_bounds__(128) k_hash_rows(const fe *__restrict__ lde, s
   st_fe(out + (size_t)q * N + r, d);
 }
 // leaf = merge_many(partition digests) (agg/child.rs:1040-1044)
-__global__ void __launch_bounds__(128) k_merge_many_rows(const fe *__restrict__ parts, size_t N, int nchunks, fe *__restrict__ out) {
+__global__ void __launch_bounds__(ZKL_HASH_THREADS) k_merge_many_rows(const fe *__restrict__ parts, size_t N, int nchunks, fe *__restrict__ out) {
   size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= N) return;
   st_fe(out + r, merge_many_dev(parts + r, N, nchunks));
 }
 // one Merkle level: out[i] = merge(in[2i], in[2i+1]), i < count
-__global__ void __launch_bounds__(128) k_merkle_level(const fe *__restrict__ in, fe *__restrict__ out, size_t count) {
+__global__ void __launch_bounds__(ZKL_HASH_THREADS) k_merkle_level(const fe *__restrict__ in, fe *__restrict__ out, size_t count) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= count) return;
   st_fe(out + i, merge_dev(ld_fe(in + 2 * i), ld_fe(in + 2 * i + 1)));
 }
 // batched primitives for the parity tests
-__global__ void __launch_bounds__(128) k_permute_batch(fe *states, size_t count) {
+__global__ void __launch_bounds__(ZKL_HASH_THREADS) k_permute_batch(fe *states, size_t count) {
   __shared__ fe s_state[12 * ZKL_HASH_THREADS];
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= count) return;
@@ -123,12 +123,12 @@ __global__ void __launch_bounds__(128) k_permute_batch(fe *states, size_t count)
 #pragma unroll
   for (int l = 0; l < 12; l++) st_fe(states + 12 * i + l, lds_fe(st + l * ZKL_HASH_THREADS));
 }
-__global__ void __launch_bounds__(128) k_hash_elements_batch(const fe *elems, int len, size_t count, fe *out) {
+__global__ void __launch_bounds__(ZKL_HASH_THREADS) k_hash_elements_batch(const fe *elems, int len, size_t count, fe *out) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= count) return;
   st_fe(out + i, hash_elements_dev(elems + i * (size_t)len, 1, len));
 }
-__global__ void __launch_bounds__(128) k_merge_with_int_batch(fe seed, const uint64_t *vals, size_t count, fe *out) {
+__global__ void __launch_bounds__(ZKL_HASH_THREADS) k_merge_with_int_batch(fe seed, const uint64_t *vals, size_t count, fe *out) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= count) return;
   st_fe(out + i, merge_with_int_dev(seed, vals[i]));

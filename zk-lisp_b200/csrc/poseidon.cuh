@@ -37,7 +37,9 @@ __constant__ label_consts c_labels;
 // state out of registers lets the MDS loop run over output lanes without unrolling (dynamic lane
 // index), which keeps the round body ~400 instructions (inside the L0/L1 instruction caches) and the
 // register count near 100 instead of 255 with spills.
-#define ZKL_HASH_THREADS 128
+#ifndef ZKL_HASH_THREADS
+#define ZKL_HASH_THREADS 64
+#endif
 
 __device__ __forceinline__ fe lds_fe(const fe *p) {
   uint4 v = *reinterpret_cast<const uint4 *>(p);
