@@ -87,6 +87,23 @@ void zo_merkle_build(const uint8_t *leaves, size_t count, uint8_t root[32], uint
   if (nodes) memcpy(nodes, t.nodes.data(), 32 * count);
 }
 
+int zo_batch_root(int depth, size_t num_lists, const uint32_t *list_len, const uint8_t *nodes, const uint8_t *leaves,
+                  const uint32_t *positions, size_t k, uint8_t out[32]) {
+  BatchMerkleProof bp; bp.depth = (uint8_t)depth;
+  size_t off = 0;
+  for (size_t i = 0; i < num_lists; i++) {
+    std::vector<Digest> v(list_len[i]);
+    for (auto &d : v) { memcpy(d.b, nodes + 32 * off, 32); off++; }
+    bp.nodes.push_back(v);
+  }
+  std::vector<Digest> lv(k); std::vector<size_t> pos(k);
+  for (size_t i = 0; i < k; i++) { memcpy(lv[i].b, leaves + 32 * i, 32); pos[i] = positions[i]; }
+  Digest root;
+  if (!batch_root(H(), bp, lv, pos, root)) return 1;
+  memcpy(out, root.b, 32);
+  return 0;
+}
+
 // ---- fft --------------------------------------------------------------------------
 void zo_interpolate_columns(zkl_fe *cols, size_t ncols, size_t n) {
   for (size_t c = 0; c < ncols; c++) {

@@ -175,3 +175,15 @@ def prove_many(traces: np.ndarray, air_c, seed: np.ndarray, opts_c, threads: int
     s = np.ascontiguousarray(seed, dtype=np.uint64)
     return load().zo_prove_many(_p(t), C.c_size_t(count), C.c_size_t(W), C.c_size_t(n), C.byref(air_c), _p(s),
                                 C.c_size_t(s.shape[0]), C.byref(opts_c), C.c_int(threads))
+
+
+def batch_root(bp: dict, leaves: np.ndarray, positions) -> bytes:
+    """Root recomputed from a batch Merkle opening (depth, node lists) for `leaves` at `positions`; b"" if malformed."""
+    lv = np.ascontiguousarray(leaves, dtype=np.uint8).reshape(-1, 32)
+    pos = np.ascontiguousarray(positions, dtype=np.uint32)
+    lens = np.array([len(l) for l in bp["nodes"]], dtype=np.uint32)
+    flat = np.frombuffer(b"".join(b"".join(l) for l in bp["nodes"]) or bytes(32), dtype=np.uint8).copy()
+    out = C.create_string_buffer(32)
+    rc = load().zo_batch_root(C.c_int(bp["depth"]), C.c_size_t(len(bp["nodes"])), _p(lens), _p(flat), _p(lv), _p(pos),
+                              C.c_size_t(pos.shape[0]), out)
+    return out.raw if rc == 0 else b""

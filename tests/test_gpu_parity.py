@@ -99,6 +99,14 @@ def test_trace_lde_commit(ctx, zkl, oracle, width, n, parts):
     for q, p in enumerate(pos):
         assert np.array_equal(rows[q], olde[:, p])
     assert bp["depth"] == N.bit_length() - 1
+    # the batch opening folds back to the committed root (winter-crypto BatchMerkleProof::get_root restated in the oracle)
+    leaves = ctx.hash_elements(rows) if parts == (1, 16) or width <= parts[1] else None
+    if leaves is not None:
+        assert oracle.batch_root(bp, leaves, pos) == root
+        bad = {"depth": bp["depth"], "nodes": [list(l) for l in bp["nodes"]]}
+        first = next(i for i, l in enumerate(bad["nodes"]) if l)
+        bad["nodes"][first][0] = bytes(32)
+        assert oracle.batch_root(bad, leaves, pos) != root
     lde.free()
 
 
@@ -113,6 +121,10 @@ def test_splitmix_generator_is_canonical():
     dict(n=128, ram=True, merkle=False, usage_mask=0x155, ram_bits=0x1),
     dict(n=64, ram=False, merkle=True, usage_mask=0xAA, ram_bits=0, pc_init=5),
     dict(n=64, ram=True, merkle=True, usage_mask=0x1FF, ram_bits=0xFFFFFFFF, main_args=(("u64", 10), ("bytes32", bytes(range(32)))), vm_expect=True),
+    # ROM accumulator only: constraint degrees 3+1 cycle -> ce_blowup 4, 3 composition columns
+    dict(n=64, ram=False, merkle=False, usage_mask=0, ram_bits=0, poseidon=False, vm=False, sponge=False),
+    # no VM: poseidon + ram + merkle + rom
+    dict(n=64, ram=True, merkle=True, usage_mask=0x100, ram_bits=0x5, vm=False, sponge=False),
 ])
 def test_constraint_evaluation(ctx, zkl, oracle, cfg):
     """Every transition and boundary constraint on random frames (all terms non-trivial), incl. the
