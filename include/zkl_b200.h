@@ -222,6 +222,17 @@ int zkl_dev_free(zkl_ctx *ctx, void *dev);
 int zkl_dev_upload(zkl_ctx *ctx, void *dev, const void *host, size_t bytes);
 int zkl_sync(zkl_ctx *ctx);
 
+/* ---- segment driver helpers (callers of the hot path: prove.rs:954-1175) ------------
+ * The reference builds the full trace once and, per segment, slices it on the host
+ * (vm/trace/mod.rs:367-384), reads boundary cells (prove.rs:1197-1287) and scans every row for gadget usage
+ * (prove.rs:1289-1392). With the full trace resident in HBM these are one kernel each. */
+int zkl_slice_segment_dev(zkl_ctx *ctx, const void *full_dev, size_t full_rows, const uint32_t *seg_to_full,
+                          size_t seg_width, size_t r_start, size_t seg_rows, void *out_dev);
+int zkl_usage_mask_dev(zkl_ctx *ctx, const void *trace_dev, size_t width, size_t n, const zkl_columns *cols,
+                       int has_ram, uint32_t *out_mask, uint32_t *out_ram_bits);
+int zkl_read_cells_dev(zkl_ctx *ctx, const void *trace_dev, size_t n, const uint32_t *cols, const uint32_t *rows,
+                       size_t k, zkl_fe *out);
+
 /* ---- measurement helpers (bench.py) -------------------------------------------------------- */
 int zkl_timer_start(zkl_ctx *ctx);             /* CUDA event on the ctx stream */
 int zkl_timer_stop(zkl_ctx *ctx, float *ms);   /* second event, synchronised; elapsed device time */

@@ -73,12 +73,12 @@ def _to_np(t, n):
     return t.to_np()
 
 
-def valid_segment(n=64, queries=8, blowup=16, grind=4, seed=1, poseidon_levels=True, start_level=0):
+def valid_segment(n=64, queries=8, blowup=16, grind=4, seed=1, poseidon_levels=True, start_level=0, full_layout=False):
     rng = random.Random(seed)
     program_id = blake3(b"zkl-b200/synth/program-id/%d" % seed)
     program_commitment = blake3(b"zkl-b200/synth/program-commitment/%d" % seed)
     fm = A.FM_POSEIDON | A.FM_VM | A.FM_SPONGE
-    cfg = A.LayoutConfig(vm=True, ram=False, sponge=True, merkle=False, rom=True)
+    cfg = A.LayoutConfig() if full_layout else A.LayoutConfig(vm=True, ram=False, sponge=True, merkle=False, rom=True)
     cols = A.Columns(cfg)
     t = _empty(cols, n)
     suite = params.get_poseidon_suite(program_id)

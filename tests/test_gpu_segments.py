@@ -1,0 +1,129 @@
+"""GPU tests of the segment driver (mirror of prove.rs:954-1175): device-side slicing, boundary cells, usage-mask
+scan and multi-context proving, checked against numpy restatements and the restated verifier."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import synth
+from util import fast_random_trace, from_fe
+
+pytestmark = pytest.mark.gpu
+
+
+def _usage_mask_numpy(t, cols, has_ram):
+    """prove.rs:1289-1392 restated on a (W, n, 2) uint64 array."""
+    nz = lambda c: (t[c, :, 0] != 0) | (t[c, :, 1] != 0)
+    n = t.shape[1]
+    fin = (np.arange(n) % 32) == 28
+    o = cols.op_start
+    mask = 0
+    for bit, cs in ((0, (o + 9, o + 7)), (1, (o + 10,)), (2, (o + 11,)), (3, (o + 12,)), (4, (o + 14,)), (5, (o + 13,)), (6, (o + 6,))):
+        if any((nz(c) & fin).any() for c in cs):
+            mask |= 1 << bit
+    if nz(o + 8).any():
+        mask |= 1 << 7
+    bits = 0
+    if has_ram:
+        s = nz(cols.ram_start)
+        same = (t[cols.ram_start + 1, :-1] == t[cols.ram_start + 1, 1:]).all(axis=1)
+        pair = s[:-1] & s[1:] & same
+        if pair.any():
+            mask |= 1 << 8
+            for i in range(32):
+                if (nz(cols.gadget_b_start + i)[:-1] & pair).any():
+                    bits |= 1 << i
+    return mask, bits
+
+
+def test_slice_and_usage_mask_match_numpy(ctx, zkl):
+    A, S = zkl.air, zkl.segments
+    full_cols = A.Columns.baseline()
+    n_full = 256
+    full = fast_random_trace(full_cols.width, n_full, seed=3)
+    # sparsify the columns the scan looks at so that both outcomes occur
+    for c in list(range(full_cols.op_start, full_cols.op_start + 17)) + [full_cols.ram_start]:
+        full[c, ::3] = 0
+    full[full_cols.ram_start + 1, 10:14] = full[full_cols.ram_start + 1, 10]
+    full[full_cols.ram_start, 8:16] = 1
+    dt = S.DeviceTrace(ctx, full)
+    for cfg in (A.LayoutConfig(ram=False, merkle=False), A.LayoutConfig(merkle=False), A.LayoutConfig()):
+        lay = S.SegmentLayout(full_cols, cfg)
+        W, r0, n = lay.cols.width, 64, 128
+        dev = C.c_void_p()
+        ctx._check(ctx.lib.zkl_dev_alloc(ctx.h, W * n * 16, C.byref(dev)))
+        ctx._check(ctx.lib.zkl_slice_segment_dev(ctx.h, dt.dev, n_full, lay.seg_to_full.ctypes.data, W, r0, n, dev))
+        exp = full[lay.seg_to_full.astype(np.int64), r0:r0 + n]
+        cells = [(c, r) for c in (0, 5, W - 1) for r in (0, 7, n - 1)]
+        got = S.read_cells(ctx, dev, n, cells)
+        assert got == [int(exp[c, r, 0]) | (int(exp[c, r, 1]) << 64) for c, r in cells]
+        m, b = C.c_uint32(), C.c_uint32()
+        cc = lay.cols.to_c()
+        ctx._check(ctx.lib.zkl_usage_mask_dev(ctx.h, dev, W, n, C.byref(cc), int(cfg.ram), C.byref(m), C.byref(b)))
+        assert (m.value, b.value) == _usage_mask_numpy(exp, lay.cols, cfg.ram)
+        ctx._check(ctx.lib.zkl_dev_free(ctx.h, dev))
+    dt.free()
+
+
+def test_prove_program_multi_segment(ctx, zkl, oracle):
+    """A 4-segment program proven on two contexts (streams); every step proof verifies and equals the proof of the
+    host-sliced segment (agg_multiseg.rs-style: max_segment_rows shrunk, max_concurrent_segments = 2)."""
+    A, S = zkl.air, zkl.segments
+    n_full, seg_rows = 512, 128
+    full, air_pi_full, opts = synth.valid_segment(n=n_full, queries=8, blowup=16, grind=4, seed=21, full_layout=True)
+    core = air_pi_full.core
+    segs = S.plan_fixed_segments(n_full, seg_rows)
+    feats = [S.SegmentFeatures(vm=True, sponge=True)] * len(segs)
+    ctx2 = zkl.Context(0)
+    steps = S.prove_program([ctx, ctx2], full, segs, core, feats, opts)
+    assert [s.segment_index for s in steps] == [0, 1, 2, 3]
+    full_cols = A.Columns.baseline()
+    for s, seg in zip(steps, segs):
+        assert s.width == 204 and s.rows == seg_rows
+        a = A.Air(s.width, s.rows, s.air_pi, s.options)
+        ac, oc, seed = a.to_c(), s.options.to_c(), zkl.prover.ints_to_fe(a.seed_elements())
+        rc, msg = oracle.verify_segment(s.proof, s.width, s.rows, ac, seed, oc)
+        assert rc == 0, (s.segment_index, msg)
+        # boundary values: pc at the first map row, ROM state in/out (prove.rs:1197-1287)
+        fi = lambda c, r: int(full[c, r, 0]) | (int(full[c, r, 1]) << 64)
+        assert s.air_pi.pc_init == fi(full_cols.pc, seg.r_start) == seg.r_start // 32
+        assert list(s.air_pi.rom_s_in) == [fi(full_cols.rom_s_start + i, seg.r_start) for i in range(3)]
+        assert list(s.air_pi.rom_s_out) == [fi(full_cols.rom_s_start + i, seg.r_end - 4) for i in range(3)]
+        # same bytes as proving the host-sliced segment through the host-buffer entry point
+        lay = S.SegmentLayout(full_cols, A.LayoutConfig(ram=False, merkle=False))
+        host_seg = np.ascontiguousarray(full[lay.seg_to_full.astype(np.int64), seg.r_start:seg.r_end])
+        assert zkl.ZkProver(ctx, s.options, s.air_pi).prove(host_seg) == s.proof
+    # the pi_prog binding exists only in the segment that starts at pc = 0 (schedule.rs:117-131)
+    assert len(A.Air(204, seg_rows, steps[0].air_pi, steps[0].options).assertions) == len(A.Air(204, seg_rows, steps[1].air_pi, steps[1].options).assertions) + 1
+    ctx2.close()
+
+
+def test_child_replay_helpers(ctx, zkl, oracle):
+    """agg/child.rs:1025-1068 on the GPU: leaf digests (with and without partitions) and path folding reproduce the
+    committed root, like tests/agg_child.rs:60-146 does against live proofs."""
+    import pyref
+    W, n = 40, 64
+    trace = fast_random_trace(W, n, seed=5)
+    for parts in ((1, 16), (4, 8)):
+        opts = zkl.air.ProofOptions(num_queries=8, blowup=16, grinding=0, num_partitions=parts[0], hash_rate=parts[1])
+        prover = zkl.ZkProver(ctx, opts, None)
+        lde, _ = prover.new_trace_lde(trace)
+        root, _, olde = oracle.trace_lde_commit(trace, opts.to_c(), want_lde=True)
+        N = n * 16
+        psize = W if parts == (1, 16) else max(-(-W // parts[0]), parts[1])
+        pos = [1, 2, 77, N - 1]
+        rows = np.stack([olde[:, p] for p in pos])
+        leaves = zkl.child.hash_row_poseidon(ctx, rows, psize)
+        # full tree from all leaves (oracle) gives the sibling paths
+        all_leaves = zkl.child.hash_row_poseidon(ctx, np.ascontiguousarray(olde.transpose(1, 0, 2)), psize)
+        oroot, nodes = oracle.merkle_build(all_leaves)
+        assert oroot == root == lde.get_main_trace_commitment()
+        sibs = []
+        for p in pos:
+            path, i = [all_leaves[p ^ 1]], (p + N) >> 1
+            while i > 1:
+                path.append(nodes[i ^ 1]); i >>= 1
+            sibs.append(np.stack(path))
+        roots = zkl.child.merkle_roots_from_leaves(ctx, leaves, pos, sibs)
+        assert all(r.tobytes() == root for r in roots)
+        lde.free()

@@ -160,6 +160,9 @@ def load_library():
     sig("zkl_dev_free", C.c_int, vp, vp)
     sig("zkl_dev_upload", C.c_int, vp, vp, vp, sz)
     sig("zkl_sync", C.c_int, vp)
+    sig("zkl_slice_segment_dev", C.c_int, vp, vp, sz, vp, sz, sz, sz, vp)
+    sig("zkl_usage_mask_dev", C.c_int, vp, vp, sz, sz, C.POINTER(Columns), C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32))
+    sig("zkl_read_cells_dev", C.c_int, vp, vp, sz, vp, vp, sz, vp)
     sig("zkl_timer_start", C.c_int, vp)
     sig("zkl_timer_stop", C.c_int, vp, C.POINTER(C.c_float))
     sig("zkl_imad_peak", C.c_int, vp, C.POINTER(C.c_double))
@@ -177,5 +180,5 @@ EXPORTED_SYMBOLS = [
     "zkl_trace_query", "zkl_eval_constraints", "zkl_constraint_commit",
     "zkl_constraint_commitment_free", "zkl_constraint_query", "zkl_prove_segment",
     "zkl_prove_segment_dev", "zkl_stage_name", "zkl_dev_alloc", "zkl_dev_free", "zkl_dev_upload",
-    "zkl_sync", "zkl_timer_start", "zkl_timer_stop", "zkl_imad_peak", "zkl_set_bulk_threshold", "zkl_bench_permute",
+    "zkl_sync", "zkl_slice_segment_dev", "zkl_usage_mask_dev", "zkl_read_cells_dev", "zkl_timer_start", "zkl_timer_stop", "zkl_imad_peak", "zkl_set_bulk_threshold", "zkl_bench_permute",
 ]

@@ -764,3 +764,92 @@ extern "C" int zkl_bench_permute(zkl_ctx *ctx, int kind, size_t count, int iters
   *ms_per_iter = ms / iters;
   return 0;
 }
+
+// ------------------------------------------------------------------------------------------------
+// segment driver helpers (callers of the hot path): the reference slices the full trace
+// per segment on the host (vm/trace/mod.rs:367-384) and scans every row for gadget usage (prove.rs:1289-1392).
+// With the full trace resident in HBM both become one kernel each.
+// ------------------------------------------------------------------------------------------------
+// out[c][row] = full[seg_to_full[c]][r_start + row]
+__global__ void k_slice_segment(const fe *__restrict__ full, size_t full_rows, const uint32_t *__restrict__ seg_to_full, int seg_width,
+                                size_t r_start, size_t seg_rows, fe *__restrict__ out) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t)seg_width * seg_rows) return;
+  size_t c = t / seg_rows, row = t - c * seg_rows;
+  st_fe(out + t, ld_fe(full + (size_t)seg_to_full[c] * full_rows + r_start + row));
+}
+extern "C" int zkl_slice_segment_dev(zkl_ctx *ctx, const void *full_dev, size_t full_rows, const uint32_t *seg_to_full, size_t seg_width,
+                                     size_t r_start, size_t seg_rows, void *out_dev) {
+  ZKL_TRY(enter(ctx));
+  if (r_start + seg_rows > full_rows) { ctx->set_error("segment out of bounds for the full trace"); return 1; }
+  dev_buf<uint32_t> map; ZKL_CHECK(ctx, map.alloc(seg_width));
+  ZKL_CHECK(ctx, cudaMemcpyAsync(map.p, seg_to_full, seg_width * 4, cudaMemcpyHostToDevice, ctx->stream));
+  LAUNCH(ctx, k_slice_segment, ceil_div(seg_width * seg_rows, 256), 256, 0, (const fe *)full_dev, full_rows, map.p, (int)seg_width, r_start,
+         seg_rows, (fe *)out_dev);
+  ZKL_CHECK(ctx, cudaStreamSynchronize(ctx->stream));  // `seg_to_full` is caller memory
+  return 0;
+}
+// compute_vm_usage_mask_for_trace (prove.rs:1289-1392): out[0] = vm usage mask, out[1] = ram delta_clk bit mask
+struct usage_cols {
+  uint32_t op_assert, op_select, op_assert_bit, op_assert_range, op_divmod, op_mulwide, op_div128, op_eq, op_sponge;
+  uint32_t ram_sorted, ram_s_addr, gadget_b_start, has_ram;
+};
+__global__ void k_usage_mask(const fe *__restrict__ tr, size_t n, usage_cols c, unsigned int *out) {
+  size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned int mask = 0, bits = 0;
+  if (row < n) {
+    auto nz = [&](uint32_t col, size_t r) { return !fe_is_zero(ld_fe(tr + (size_t)col * n + r)); };
+    bool at_final = (row % 32) == 28;
+    if (at_final && (nz(c.op_assert, row) || nz(c.op_select, row))) mask |= 1u << 0;
+    if (at_final && nz(c.op_assert_bit, row)) mask |= 1u << 1;
+    if (at_final && nz(c.op_assert_range, row)) mask |= 1u << 2;
+    if (at_final && nz(c.op_divmod, row)) mask |= 1u << 3;
+    if (at_final && nz(c.op_mulwide, row)) mask |= 1u << 4;
+    if (at_final && nz(c.op_div128, row)) mask |= 1u << 5;
+    if (at_final && nz(c.op_eq, row)) mask |= 1u << 6;
+    if (nz(c.op_sponge, row)) mask |= 1u << 7;
+    if (c.has_ram && row + 1 < n && nz(c.ram_sorted, row) && nz(c.ram_sorted, row + 1) &&
+        fe_eq(ld_fe(tr + (size_t)c.ram_s_addr * n + row), ld_fe(tr + (size_t)c.ram_s_addr * n + row + 1))) {
+      mask |= 1u << 8;
+      for (int i = 0; i < 32; i++) if (nz(c.gadget_b_start + i, row)) bits |= 1u << i;
+    }
+  }
+  mask = __reduce_or_sync(0xffffffffu, mask); bits = __reduce_or_sync(0xffffffffu, bits);
+  if ((threadIdx.x & 31) == 0) { if (mask) atomicOr(out, mask); if (bits) atomicOr(out + 1, bits); }
+}
+extern "C" int zkl_usage_mask_dev(zkl_ctx *ctx, const void *trace_dev, size_t width, size_t n, const zkl_columns *cols, int has_ram,
+                                  uint32_t *out_mask, uint32_t *out_ram_bits) {
+  ZKL_TRY(enter(ctx));
+  (void)width;
+  usage_cols c;
+  const uint32_t o = cols->op_start;
+  c.op_eq = o + 6; c.op_select = o + 7; c.op_sponge = o + 8; c.op_assert = o + 9; c.op_assert_bit = o + 10; c.op_assert_range = o + 11;
+  c.op_divmod = o + 12; c.op_div128 = o + 13; c.op_mulwide = o + 14;
+  c.ram_sorted = cols->ram_start; c.ram_s_addr = cols->ram_start + 1; c.gadget_b_start = cols->gadget_b_start; c.has_ram = has_ram ? 1 : 0;
+  dev_buf<unsigned int> d; ZKL_CHECK(ctx, d.alloc(2));
+  ZKL_CHECK(ctx, cudaMemsetAsync(d.p, 0, 8, ctx->stream));
+  LAUNCH(ctx, k_usage_mask, ceil_div(n, 256), 256, 0, (const fe *)trace_dev, n, c, d.p);
+  unsigned int h[2];
+  ZKL_CHECK(ctx, cudaMemcpyAsync(h, d.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  ZKL_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  *out_mask = h[0]; *out_ram_bits = h[1];
+  return 0;
+}
+// out[i] = trace[cols[i]][rows[i]] (boundary values: prove.rs:1197-1287 compute_segment_boundary_bytes)
+__global__ void k_read_cells(const fe *__restrict__ tr, size_t n, const uint32_t *__restrict__ cols, const uint32_t *__restrict__ rows, int k,
+                             fe *__restrict__ out) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < k) st_fe(out + t, ld_fe(tr + (size_t)cols[t] * n + rows[t]));
+}
+extern "C" int zkl_read_cells_dev(zkl_ctx *ctx, const void *trace_dev, size_t n, const uint32_t *cols, const uint32_t *rows, size_t k,
+                                  zkl_fe *out) {
+  ZKL_TRY(enter(ctx));
+  dev_buf<uint32_t> dc, dr; dev_buf<fe> o;
+  ZKL_CHECK(ctx, dc.alloc(k)); ZKL_CHECK(ctx, dr.alloc(k)); ZKL_CHECK(ctx, o.alloc(k));
+  ZKL_CHECK(ctx, cudaMemcpyAsync(dc.p, cols, k * 4, cudaMemcpyHostToDevice, ctx->stream));
+  ZKL_CHECK(ctx, cudaMemcpyAsync(dr.p, rows, k * 4, cudaMemcpyHostToDevice, ctx->stream));
+  LAUNCH(ctx, k_read_cells, ceil_div(k, 128), 128, 0, (const fe *)trace_dev, n, dc.p, dr.p, (int)k, o.p);
+  ZKL_CHECK(ctx, cudaMemcpyAsync(out, o.p, k * sizeof(fe), cudaMemcpyDeviceToHost, ctx->stream));
+  ZKL_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
