@@ -179,15 +179,72 @@ extern "C" int zkl_constraint_query(zkl_ctx *ctx, const zkl_constraint_commitmen
 // ------------------------------------------------------------------------------------------------
 // constraint evaluation (hook 2)
 // ------------------------------------------------------------------------------------------------
-struct air_device_state {
-  dev_buf<air_dev> air;
-  dev_buf<assertion_dev> as;
-  dev_buf<uint32_t> group_start, slot_col;
-  dev_buf<fe> per, coset_consts, u, bpoly_coef, bpoly;
+// AIR parameters on the device. The static part (constants, sorted assertions) depends only on the AIR instance and
+// is cached per context, keyed by a hash of the parameter bytes: proving many segments of one program re-uses it.
+struct air_static {
+  air_dev *air = nullptr;
+  assertion_dev *as = nullptr;
+  uint32_t *group_start = nullptr, *slot_col = nullptr;
   int nslots = 0, ngroups = 0;
 };
+struct air_device_state {
+  air_static s;
+  struct view { air_dev *p; } air;
+  struct view_as { assertion_dev *p; } as;
+  struct view_u32 { uint32_t *p; } group_start, slot_col;
+  dev_buf<fe> coset_consts, u, bpoly;
+  int nslots = 0, ngroups = 0;
+};
+static std::mutex g_air_cache_mutex;
+static std::map<std::pair<const zkl_ctx *, uint64_t>, air_static> g_air_cache;
+static uint64_t fnv1a(uint64_t h, const void *p, size_t n) {
+  const uint8_t *b = (const uint8_t *)p;
+  for (size_t i = 0; i < n; i++) { h ^= b[i]; h *= 0x100000001b3ull; }
+  return h;
+}
+static void air_cache_drop(const zkl_ctx *ctx) {
+  std::lock_guard<std::mutex> g(g_air_cache_mutex);
+  for (auto it = g_air_cache.begin(); it != g_air_cache.end();) {
+    if (it->first.first == ctx) {
+      cudaFree(it->second.air); cudaFree(it->second.as); cudaFree(it->second.group_start); cudaFree(it->second.slot_col);
+      it = g_air_cache.erase(it);
+    } else ++it;
+  }
+}
 
+static int upload_air_static(zkl_ctx *ctx, const zkl_air_params *a, size_t n, air_static &st);
 static int upload_air(zkl_ctx *ctx, const zkl_air_params *a, size_t n, air_device_state &st) {
+  uint64_t h = 0xcbf29ce484222325ull;
+  zkl_air_params tmp = *a; tmp.assertions = nullptr;
+  h = fnv1a(h, &tmp, sizeof tmp);
+  h = fnv1a(h, a->assertions, sizeof(zkl_assertion) * a->num_assertions);
+  h = fnv1a(h, &n, sizeof n);
+  {
+    std::lock_guard<std::mutex> g(g_air_cache_mutex);
+    auto it = g_air_cache.find({ctx, h});
+    if (it != g_air_cache.end()) st.s = it->second;
+  }
+  if (!st.s.air) {
+    ZKL_TRY(upload_air_static(ctx, a, n, st.s));
+    std::lock_guard<std::mutex> g(g_air_cache_mutex);
+    size_t mine = 0;
+    for (auto &kv : g_air_cache) mine += kv.first.first == ctx;
+    if (mine >= 64) {  // bounded: drop this context's entries (all in-flight work on its stream is ordered before reuse)
+      cudaStreamSynchronize(ctx->stream);
+      for (auto it = g_air_cache.begin(); it != g_air_cache.end();) {
+        if (it->first.first == ctx) {
+          cudaFree(it->second.air); cudaFree(it->second.as); cudaFree(it->second.group_start); cudaFree(it->second.slot_col);
+          it = g_air_cache.erase(it);
+        } else ++it;
+      }
+    }
+    g_air_cache[{ctx, h}] = st.s;
+  }
+  st.air.p = st.s.air; st.as.p = st.s.as; st.group_start.p = st.s.group_start; st.slot_col.p = st.s.slot_col;
+  st.nslots = st.s.nslots; st.ngroups = st.s.ngroups;
+  return 0;
+}
+static int upload_air_static(zkl_ctx *ctx, const zkl_air_params *a, size_t n, air_static &st) {
   if (a->cols.width > 255) { ctx->set_error("trace width must fit in u8 (winterfell TraceInfo)"); return 1; }
   air_dev h; memset(&h, 0, sizeof h);
   h.cols = a->cols;
@@ -200,8 +257,8 @@ static int upload_air(zkl_ctx *ctx, const zkl_air_params *a, size_t n, air_devic
   for (int r = 0; r < ZKL_ROUNDS; r++) for (int j = 0; j < 3; j++) h.rom_rc[r][j] = fe_from_abi(a->rom.rc[r][j]);
   for (int k = 0; k < 59; k++) { h.rom_w0[k] = fe_from_abi(a->rom_w_enc0[k]); h.rom_w1[k] = fe_from_abi(a->rom_w_enc1[k]); }
   h.program_fe0 = fe_from_abi(a->program_fe0); h.merkle_root_fe = fe_from_abi(a->merkle_root_fe);
-  ZKL_CHECK(ctx, st.air.alloc(1));
-  ZKL_CHECK(ctx, cudaMemcpyAsync(st.air.p, &h, sizeof h, cudaMemcpyHostToDevice, ctx->stream));
+  ZKL_CHECK(ctx, cudaMalloc((void **)&st.air, sizeof h));
+  ZKL_CHECK(ctx, cudaMemcpyAsync(st.air, &h, sizeof h, cudaMemcpyHostToDevice, ctx->stream));
   // assertions: Winterfell order = sorted by (stride, first_step, column); single assertions have stride 0 [WF-mem]
   std::vector<uint32_t> order(a->num_assertions);
   for (uint32_t i = 0; i < a->num_assertions; i++) order[i] = i;
@@ -224,12 +281,12 @@ static int upload_air(zkl_ctx *ctx, const zkl_air_params *a, size_t n, air_devic
   }
   gs.push_back(a->num_assertions);
   st.nslots = (int)slot_col.size(); st.ngroups = (int)gs.size() - 1;
-  ZKL_CHECK(ctx, st.as.alloc(std::max<size_t>(as.size(), 1)));
-  ZKL_CHECK(ctx, st.group_start.alloc(gs.size()));
-  ZKL_CHECK(ctx, st.slot_col.alloc(std::max<size_t>(slot_col.size(), 1)));
-  if (!as.empty()) ZKL_CHECK(ctx, cudaMemcpyAsync(st.as.p, as.data(), as.size() * sizeof(assertion_dev), cudaMemcpyHostToDevice, ctx->stream));
-  ZKL_CHECK(ctx, cudaMemcpyAsync(st.group_start.p, gs.data(), gs.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
-  if (!slot_col.empty()) ZKL_CHECK(ctx, cudaMemcpyAsync(st.slot_col.p, slot_col.data(), slot_col.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+  ZKL_CHECK(ctx, cudaMalloc((void **)&st.as, std::max<size_t>(as.size(), 1) * sizeof(assertion_dev)));
+  ZKL_CHECK(ctx, cudaMalloc((void **)&st.group_start, gs.size() * 4));
+  ZKL_CHECK(ctx, cudaMalloc((void **)&st.slot_col, std::max<size_t>(slot_col.size(), 1) * 4));
+  if (!as.empty()) ZKL_CHECK(ctx, cudaMemcpyAsync(st.as, as.data(), as.size() * sizeof(assertion_dev), cudaMemcpyHostToDevice, ctx->stream));
+  ZKL_CHECK(ctx, cudaMemcpyAsync(st.group_start, gs.data(), gs.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+  if (!slot_col.empty()) ZKL_CHECK(ctx, cudaMemcpyAsync(st.slot_col, slot_col.data(), slot_col.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
   // the host vectors must outlive the async copies
   ZKL_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
   return 0;
@@ -256,18 +313,27 @@ static int dev_eval_constraints(zkl_ctx *ctx, const committed_matrix &t, const z
     }
     per_tab = it->second;
   }
-  // per-coset constants: x^n = g^n * w_ce^k'
-  std::vector<fe> cconst(2 * ce + 2);
-  fe gn = fe_pow(g, n), wce = host_root_of_unity(ilog2_sz(ce)), wk = fe_one();
-  for (size_t k = 0; k < ce; k++) {
-    fe xn1 = fe_sub(fe_mul(gn, wk), fe_one());
-    cconst[2 * k] = fe_inv(xn1); cconst[2 * k + 1] = xn1;
-    wk = fe_mul(wk, wce);
+  // per-coset constants: x^n = g^n * w_ce^k' (data independent, cached per (n, ce))
+  fe *coset_consts;
+  {
+    size_t key = (n << 8) | ce | ((size_t)1 << 60);
+    auto it = ctx->periodic.find(key);
+    if (it == ctx->periodic.end()) {
+      std::vector<fe> cconst(2 * ce + 2);
+      fe gn = fe_pow(g, n), wce = host_root_of_unity(ilog2_sz(ce)), wk = fe_one();
+      for (size_t k = 0; k < ce; k++) {
+        fe xn1 = fe_sub(fe_mul(gn, wk), fe_one());
+        cconst[2 * k] = fe_inv(xn1); cconst[2 * k + 1] = xn1;
+        wk = fe_mul(wk, wce);
+      }
+      cconst[2 * ce] = fe_inv(fe_from_u64(n)); cconst[2 * ce + 1] = fe_from_u64(n);
+      fe *p; ZKL_CHECK(ctx, cudaMalloc((void **)&p, cconst.size() * sizeof(fe)));
+      ZKL_CHECK(ctx, cudaMemcpyAsync(p, cconst.data(), cconst.size() * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream));
+      ZKL_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+      it = ctx->periodic.emplace(key, p).first;
+    }
+    coset_consts = it->second;
   }
-  cconst[2 * ce] = fe_inv(fe_from_u64(n)); cconst[2 * ce + 1] = fe_from_u64(n);
-  ZKL_CHECK(ctx, st.coset_consts.alloc(cconst.size()));
-  ZKL_CHECK(ctx, cudaMemcpyAsync(st.coset_consts.p, cconst.data(), cconst.size() * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream));
-  ZKL_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
   // boundary polynomials: scatter -> iNTT -> coset LDE over the CE domain
   size_t nb = (size_t)st.nslots + 1;
   ZKL_CHECK(ctx, st.u.alloc(nb * n)); ZKL_CHECK(ctx, st.bpoly.alloc(nb * M));
@@ -277,7 +343,7 @@ static int dev_eval_constraints(zkl_ctx *ctx, const committed_matrix &t, const z
   ZKL_TRY(dev_lde(ctx, st.u.p, st.bpoly.p, nb, n, ce));
   boundary_dev bd{st.slot_col.p, st.bpoly.p, st.nslots};
   LAUNCH(ctx, k_eval_constraints, ceil_div(M, 128), 128, 0, st.air.p, t.lde.p, N, (int)n, (int)t.blowup, (int)ce, per_tab, tN->wpow, cc_dev, bd,
-         st.coset_consts.p, ce_out);
+         coset_consts, ce_out);
   return 0;
 }
 

@@ -37,6 +37,7 @@ struct zkl_ctx {
   int device = 0;
   int num_sms = 148;
   cudaStream_t stream = nullptr;
+  cudaMemPool_t pool = nullptr;            // private stream-ordered memory pool
   std::string err;
   uint64_t launches = 0;
   bool suite_loaded = false;
@@ -56,6 +57,7 @@ static inline int ilog2_sz(size_t n) { int k = 0; while (((size_t)1 << k) < n) k
 // context's stream, pool release threshold = unlimited), so concurrent segment streams never hit the
 // device-wide synchronisation of cudaMalloc/cudaFree.
 static thread_local cudaStream_t tl_stream = nullptr;
+static thread_local cudaMemPool_t tl_pool = nullptr;
 static thread_local bool tl_stream_set = false;
 template <typename T>
 struct dev_buf {
@@ -73,7 +75,13 @@ struct dev_buf {
   cudaError_t alloc(size_t count) {
     release();
     n = count;
-    if (tl_stream_set) { async = true; s = tl_stream; return cudaMallocAsync((void **)&p, count * sizeof(T) + 16, s); }
+    if (tl_stream_set) {
+      // each context allocates from its OWN pool: blocks freed on one stream are never handed to another stream,
+      // so the allocator never inserts cross-stream dependencies between concurrently proving segments
+      async = true; s = tl_stream;
+      return tl_pool ? cudaMallocFromPoolAsync((void **)&p, count * sizeof(T) + 16, tl_pool, s)
+                     : cudaMallocAsync((void **)&p, count * sizeof(T) + 16, s);
+    }
     async = false;
     return cudaMalloc((void **)&p, count * sizeof(T) + 16);
   }

@@ -49,11 +49,17 @@ extern "C" int zkl_ctx_create(int device, zkl_ctx **out) {
   if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) {
     g_create_error = cudaGetErrorString(e); delete c; return 1;
   }
-  {  // keep freed blocks in the pool: no trimming at synchronisation points
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+  {  // private pool per context, freed blocks are kept (no trimming at synchronisation points)
+    cudaMemPoolProps props; memset(&props, 0, sizeof props);
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = device;
+    if (cudaMemPoolCreate(&c->pool, &props) == cudaSuccess) {
       uint64_t thr = ~0ull;
-      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+      cudaMemPoolSetAttribute(c->pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    } else {
+      c->pool = nullptr; (void)cudaGetLastError();
     }
   }
   // opt in to large dynamic shared memory for the single-pass column transforms
@@ -73,16 +79,20 @@ extern "C" int zkl_ctx_create(int device, zkl_ctx **out) {
   return 0;
 }
 
+static void air_cache_drop(const zkl_ctx *ctx);
 extern "C" void zkl_ctx_destroy(zkl_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  if (tl_stream == ctx->stream) { tl_stream = nullptr; tl_stream_set = false; }
+  cudaStreamSynchronize(ctx->stream);
+  air_cache_drop(ctx);
+  if (tl_stream == ctx->stream) { tl_stream = nullptr; tl_pool = nullptr; tl_stream_set = false; }
   cudaStreamSynchronize(ctx->stream);
   for (auto &kv : ctx->tables) { cudaFree(kv.second.wpow); }
   for (auto &kv : ctx->opow) cudaFree(kv.second);
   for (auto &kv : ctx->periodic) cudaFree(kv.second);
   for (auto e : ctx->ev) cudaEventDestroy(e);
   cudaStreamDestroy(ctx->stream);
+  if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
   delete ctx;
 }
 extern "C" const char *zkl_last_error(const zkl_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
@@ -103,7 +113,7 @@ extern "C" int zkl_suite_load(zkl_ctx *ctx, const zkl_suite *s) {
 // every entry point binds the calling thread to the context's device and stream (stream-ordered allocator)
 static int enter(zkl_ctx *ctx) {
   if (cudaSetDevice(ctx->device) != cudaSuccess) { ctx->set_error("cudaSetDevice failed"); return 1; }
-  tl_stream = ctx->stream; tl_stream_set = true;
+  tl_stream = ctx->stream; tl_pool = ctx->pool; tl_stream_set = true;
   return 0;
 }
 static int need_suite(zkl_ctx *ctx) {
