@@ -1,0 +1,131 @@
+// kernels_tc.cuh — bulk sponge kernels on the tensor-core permutation (tcperm.cuh): row hashing over the
+// coset-major LDE, Merkle levels, FRI leaves, grinding and the batched primitives used by the parity tests.
+// Reference semantics: zk-lisp-proof-winterfell/src/poseidon/hasher.rs:57-140 (entry points), :144-231 (sponge);
+// row hashing with partitions src/agg/child.rs:1025-1045.
+//
+// Every kernel is persistent: grid = min(#tiles, #SMs) CTAs of 512 threads, one CTA per SM (the B matrix image,
+// two A tiles and all 512 TMEM columns are per CTA), each looping over tiles of 256 sponges (2 sets x 128).
+// Thread (set, sponge, half) owns lanes 6*half .. 6*half+5 of its sponge; the absorb of item l (state lane l,
+// l < 10) is done by the thread that owns lane l.
+#pragma once
+#include "kernels_hash.cuh"
+#include "tcperm.cuh"
+
+// Generic sponge over a lazily produced item stream: the same contract as sponge_run (kernels_hash.cuh), but all
+// 256 threads of a set run the same number of permutations (`total` must be uniform across the set).
+// Returns lane 0 (canonical) in the half-0 thread of each sponge.
+template <typename Src>
+__device__ __forceinline__ fe tc_sponge_run(const Src &src, int total, tc_ctx &c) {
+  fe st[6];
+#pragma unroll
+  for (int j = 0; j < 6; j++) st[j] = fe_zero();
+  if (c.half) { st[4] = ldc_fe(&c_suite.dom[0]); st[5] = ldc_fe(&c_suite.dom[1]); }
+  const int lane0 = 6 * c.half;
+#pragma unroll 1
+  for (int m = 0; m < total; m += ZKL_RATE) {
+#pragma unroll
+    for (int j = 0; j < 6; j++) {
+      int l = lane0 + j;
+      if (l < ZKL_RATE && m + l < total) st[j] = lazy_add(st[j], src.item(m + l));
+    }
+    tc_permute(st, c);
+  }
+  return lazy_canon(st[0]);
+}
+
+// sponge index handled by this thread in tile `tile`
+__device__ __forceinline__ size_t tc_index(const tc_ctx &c, size_t tile) { return tile * TC_CTA_SPONGES + (size_t)c.set * TC_SPONGES + c.sponge; }
+
+// ---------------------------------------------------------------- kernels
+__global__ void __launch_bounds__(TC_THREADS, 1) k_tc_permute_batch(fe *states, size_t count) {
+  extern __shared__ unsigned char tc_smem[];
+  tc_ctx c = tc_setup(tc_smem);
+  size_t tiles = (count + TC_CTA_SPONGES - 1) / TC_CTA_SPONGES;
+  for (size_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    size_t i = tc_index(c, tile), ic = i < count ? i : count - 1;
+    fe st[6];
+#pragma unroll
+    for (int j = 0; j < 6; j++) st[j] = ld_fe(states + 12 * ic + 6 * c.half + j);
+    tc_permute(st, c);
+    if (i < count) {
+#pragma unroll
+      for (int j = 0; j < 6; j++) st_fe(states + 12 * i + 6 * c.half + j, lazy_canon(st[j]));
+    }
+  }
+  tc_teardown(tc_smem);
+}
+
+// Row hashing over a coset-major LDE — same contract as k_hash_rows: sponge t = (s, q) hashes columns
+// [q*psize, min(W,(q+1)*psize)) of storage row s (natural row r = s/n + blowup*(s%n)) and writes out[q*N + r].
+// Sponges of one tile may straddle two partitions only if their lengths agree, so tiles are formed per partition:
+// tile index = q * tiles_per_part + tile_in_part.
+__global__ void __launch_bounds__(TC_THREADS, 1) k_tc_hash_rows(const fe *__restrict__ lde, size_t N, size_t n, int blowup, int W, int psize,
+                                                                int nchunks, fe *__restrict__ out) {
+  extern __shared__ unsigned char tc_smem[];
+  tc_ctx c = tc_setup(tc_smem);
+  size_t tiles_per_part = (N + TC_CTA_SPONGES - 1) / TC_CTA_SPONGES;
+  size_t tiles = tiles_per_part * (size_t)nchunks;
+  for (size_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    int q = (int)(tile / tiles_per_part);
+    size_t s = tc_index(c, tile % tiles_per_part), sc = s < N ? s : N - 1;
+    int first = q * psize, len = min(psize, W - first);
+    elems_src src{lde + (size_t)first * N + sc, N, len};
+    fe d = tc_sponge_run(src, 1 + (len + 1) / 2, c);
+    if (s < N && c.half == 0) {
+      size_t r = (s / n) + (size_t)blowup * (s % n);
+      st_fe(out + (size_t)q * N + r, d);
+    }
+  }
+  tc_teardown(tc_smem);
+}
+// leaf = merge_many(partition digests)
+__global__ void __launch_bounds__(TC_THREADS, 1) k_tc_merge_many_rows(const fe *__restrict__ parts, size_t N, int nchunks, fe *__restrict__ out) {
+  extern __shared__ unsigned char tc_smem[];
+  tc_ctx c = tc_setup(tc_smem);
+  size_t tiles = (N + TC_CTA_SPONGES - 1) / TC_CTA_SPONGES;
+  for (size_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    size_t r = tc_index(c, tile), rc = r < N ? r : N - 1;
+    many_src src{parts + rc, N};
+    fe d = tc_sponge_run(src, 1 + nchunks, c);
+    if (r < N && c.half == 0) st_fe(out + r, d);
+  }
+  tc_teardown(tc_smem);
+}
+// one Merkle level: out[i] = merge(in[2i], in[2i+1])
+__global__ void __launch_bounds__(TC_THREADS, 1) k_tc_merkle_level(const fe *__restrict__ in, fe *__restrict__ out, size_t count) {
+  extern __shared__ unsigned char tc_smem[];
+  tc_ctx c = tc_setup(tc_smem);
+  size_t tiles = (count + TC_CTA_SPONGES - 1) / TC_CTA_SPONGES;
+  for (size_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    size_t i = tc_index(c, tile), ic = i < count ? i : count - 1;
+    merge_src src{fe_zero(), fe_zero()};
+    if (c.half == 0) { src.a = ld_fe(in + 2 * ic); src.b = ld_fe(in + 2 * ic + 1); }   // items 1, 2 live in lanes 1, 2
+    fe d = tc_sponge_run(src, 3, c);
+    if (i < count && c.half == 0) st_fe(out + i, d);
+  }
+  tc_teardown(tc_smem);
+}
+__global__ void __launch_bounds__(TC_THREADS, 1) k_tc_hash_elements_batch(const fe *elems, int len, size_t count, fe *out) {
+  extern __shared__ unsigned char tc_smem[];
+  tc_ctx c = tc_setup(tc_smem);
+  size_t tiles = (count + TC_CTA_SPONGES - 1) / TC_CTA_SPONGES;
+  for (size_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    size_t i = tc_index(c, tile), ic = i < count ? i : count - 1;
+    elems_src src{elems + ic * (size_t)len, 1, len};
+    fe d = tc_sponge_run(src, 1 + (len + 1) / 2, c);
+    if (i < count && c.half == 0) st_fe(out + i, d);
+  }
+  tc_teardown(tc_smem);
+}
+__global__ void __launch_bounds__(TC_THREADS, 1) k_tc_merge_with_int_batch(fe seed, const uint64_t *vals, size_t count, fe *out) {
+  extern __shared__ unsigned char tc_smem[];
+  tc_ctx c = tc_setup(tc_smem);
+  size_t tiles = (count + TC_CTA_SPONGES - 1) / TC_CTA_SPONGES;
+  for (size_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    size_t i = tc_index(c, tile), ic = i < count ? i : count - 1;
+    mwi_src src{seed, vals[ic]};
+    fe d = tc_sponge_run(src, 3, c);
+    if (i < count && c.half == 0) st_fe(out + i, d);
+  }
+  tc_teardown(tc_smem);
+}
