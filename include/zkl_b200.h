@@ -237,9 +237,13 @@ int zkl_read_cells_dev(zkl_ctx *ctx, const void *trace_dev, size_t n, const uint
 int zkl_timer_start(zkl_ctx *ctx);             /* CUDA event on the ctx stream */
 int zkl_timer_stop(zkl_ctx *ctx, float *ms);   /* second event, synchronised; elapsed device time */
 int zkl_imad_peak(zkl_ctx *ctx, double *wide_macs_per_s); /* dependency-free IMAD.WIDE.U32 probe */
-/* sponge count from which thread-per-sponge kernels replace the 16-thread cooperative ones */
+/* sponge count from which the bulk sponge kernels replace the 16-thread cooperative ones */
 int zkl_set_bulk_threshold(zkl_ctx *ctx, long sponges);
-/* permutation throughput probe on device-resident states: kind 0 = thread-per-state kernel, 1 = cooperative */
+/* bulk hashing path: 0 = tensor-core MDS product (tcgen05 kind::i8, default), 1 = integer-pipe thread-per-sponge
+ * kernels. Both are bit-identical; 1 exists for A/B measurements and parity tests. */
+int zkl_set_hash_path(zkl_ctx *ctx, int path);
+/* permutation throughput probe on device-resident states: kind 0 = thread-per-state kernel, 1 = cooperative,
+ * 2 = tensor-core MDS kernel */
 int zkl_bench_permute(zkl_ctx *ctx, int kind, size_t count, int iters, float *ms_per_iter);
 
 #ifdef __cplusplus

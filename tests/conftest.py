@@ -29,8 +29,21 @@ def oracle():
     return oracle_lib
 
 
-@pytest.fixture(scope="session")
-def ctx(zkl):
+# Bulk hashing modes every GPU parity test runs under (all three must be bit-identical to the oracle):
+#   default   tensor-core sponge kernels from 4096 sponges up, 16-thread cooperative kernels below
+#   tc-forced tensor-core kernels for every bulk call site (threshold 1): small test sizes reach tcperm.cuh
+#   int-pipe  the integer-pipe thread-per-sponge kernels for every bulk call site
+HASH_MODES = {"default": (None, 0), "tc-forced": (1, 0), "int-pipe": (1, 1)}
+
+
+@pytest.fixture(scope="session", params=list(HASH_MODES))
+def ctx(zkl, request):
     """GPU context; fails loudly if the CUDA library or device is missing (no fallback)."""
     graft.build()
-    return zkl.Context(0)
+    c = zkl.Context(0)
+    thr, path = HASH_MODES[request.param]
+    if thr is not None:
+        c._check(c.lib.zkl_set_bulk_threshold(c.h, thr))
+    c._check(c.lib.zkl_set_hash_path(c.h, path))
+    c.hash_mode = request.param
+    return c

@@ -1,6 +1,6 @@
 // Host build of the DEVICE limb arithmetic (zk-lisp_b200/csrc/f128.cuh compiled with g++): the
 // carry primitives fall back to plain C so the limb algorithms can be checked on the CPU.
-#include "../zk-lisp_b200/csrc/f128.cuh"
+#include "../zk-lisp_b200/csrc/f128_lazy.cuh"
 extern "C" {
 void h_binop(int op, const fe *a, const fe *b, fe *out, long n) {
   for (long i = 0; i < n; i++) {
@@ -12,6 +12,10 @@ void h_binop(int op, const fe *a, const fe *b, fe *out, long n) {
       case 4: out[i] = fe_cube(a[i]); break;
       case 5: out[i] = fe_fold_pair(a[i], b[i]); break;
       case 6: out[i] = fe_from_u128_mod(a[i]); break;
+      // lazy arithmetic (tcperm.cuh): inputs are ANY 128-bit values, outputs are 128-bit representatives
+      case 7: out[i] = lazy_mul(a[i], b[i]); break;
+      case 8: out[i] = lazy_add(a[i], b[i]); break;
+      case 9: out[i] = lazy_canon(a[i]); break;
     }
   }
 }
@@ -23,5 +27,13 @@ void h_dot12(const fe *a, const fe *b, const fe *rc, fe *out, long n) {
     wacc_add_fe(w, rc[i]);
     out[i] = wacc_reduce(w);
   }
+}
+// tensor-core epilogue: 16 byte-position accumulators + round constant -> lazy element
+void h_tc_epilogue(const uint32_t *acc, const fe *rc, fe *out, long n) {
+  for (long i = 0; i < n; i++) out[i] = tc_epilogue(acc + 16 * i, rc[i]);
+}
+// raw 256-bit product (the cube bytes fed to the MMA)
+void h_mul_wide(const fe *a, const fe *b, uint32_t *out, long n) {
+  for (long i = 0; i < n; i++) lazy_mul_wide(a[i], b[i], out + 8 * i);
 }
 }

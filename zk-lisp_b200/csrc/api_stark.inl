@@ -561,7 +561,8 @@ static int prove_segment_impl(zkl_ctx *ctx, const fe *trace_dev, size_t W, size_
   for (size_t d = 0; d < nl; d++) {
     size_t half = nd * B / 2;
     ZKL_CHECK(ctx, f_leaves[d].alloc(half)); ZKL_CHECK(ctx, f_nodes[d].alloc(half)); ZKL_CHECK(ctx, f_ev[d + 1].alloc(half));
-    LAUNCH(ctx, k_fri_leaves, ceil_div(half * ZKL_COOP_GROUP, ZKL_COOP_THREADS), ZKL_COOP_THREADS, 0, cur_ev, (int)nd, (int)B, f_leaves[d].p);
+    if (half >= (size_t)ctx->bulk_threshold && ctx->hash_path == 0) LAUNCH_TC(ctx, k_tc_fri_leaves, half, cur_ev, (int)nd, (int)B, f_leaves[d].p);
+    else LAUNCH(ctx, k_fri_leaves, ceil_div(half * ZKL_COOP_GROUP, ZKL_COOP_THREADS), ZKL_COOP_THREADS, 0, cur_ev, (int)nd, (int)B, f_leaves[d].p);
     ZKL_TRY(dev_merkle(ctx, f_leaves[d].p, f_nodes[d].p, half));
     ZKL_CHECK(ctx, cudaMemcpyAsync(fri_roots.p + d, f_nodes[d].p + 1, sizeof(fe), cudaMemcpyDeviceToDevice, st));
     LAUNCH(ctx, k_coin_reseed, 1, ZKL_COOP_GROUP, 0, coin.p, f_nodes[d].p + 1);
@@ -593,7 +594,8 @@ static int prove_segment_impl(zkl_ctx *ctx, const fe *trace_dev, size_t W, size_
       uint64_t target = (uint64_t)16 << o->grinding;
       int nb = (int)std::min<uint64_t>(std::max<uint64_t>(target / batch, 1), 512);
       for (int b = 0; b < nb; b++, base += batch)
-        LAUNCH(ctx, k_grind, ceil_div((size_t)batch * ZKL_COOP_GROUP, ZKL_COOP_THREADS), ZKL_COOP_THREADS, 0, coin.p, base, batch, o->grinding, nonce.p);
+        if (ctx->hash_path == 0) LAUNCH_TC(ctx, k_tc_grind, batch, coin.p, base, batch, o->grinding, nonce.p);
+        else LAUNCH(ctx, k_grind, ceil_div((size_t)batch * ZKL_COOP_GROUP, ZKL_COOP_THREADS), ZKL_COOP_THREADS, 0, coin.p, base, batch, o->grinding, nonce.p);
       ZKL_CHECK(ctx, cudaMemcpyAsync(&nonce_h, nonce.p, 8, cudaMemcpyDeviceToHost, st));
       ZKL_CHECK(ctx, cudaStreamSynchronize(st));
       if (nonce_h != ~0ull) break;
@@ -803,8 +805,13 @@ extern "C" int zkl_imad_peak(zkl_ctx *ctx, double *wide_macs_per_s) {
   return 0;
 }
 extern "C" int zkl_set_bulk_threshold(zkl_ctx *ctx, long sponges) { ctx->bulk_threshold = sponges; return 0; }
+extern "C" int zkl_set_hash_path(zkl_ctx *ctx, int path) {
+  if (path != 0 && path != 1) { ctx->set_error("hash path must be 0 (tensor-core MDS) or 1 (integer pipe)"); return 1; }
+  ctx->hash_path = path; return 0;
+}
 
-// permutation throughput probes on device-resident data: kind 0 = thread-per-state kernel, 1 = cooperative kernel
+// permutation throughput probes on device-resident data: kind 0 = thread-per-state kernel, 1 = cooperative kernel,
+// 2 = tensor-core MDS kernel
 __global__ void __launch_bounds__(ZKL_COOP_THREADS) k_coop_permute_batch(fe *states, size_t count) {
   __shared__ fe s_xch[(ZKL_COOP_THREADS / ZKL_COOP_GROUP) * 24];
   size_t g = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) / ZKL_COOP_GROUP;
@@ -822,7 +829,8 @@ extern "C" int zkl_bench_permute(zkl_ctx *ctx, int kind, size_t count, int iters
   for (int rep = 0; rep < 2; rep++) {
     ZKL_TRY(zkl_timer_start(ctx));
     for (int i = 0; i < iters; i++) {
-      if (kind == 0) LAUNCH(ctx, k_permute_batch, ceil_div(count, ZKL_HASH_THREADS), ZKL_HASH_THREADS, 0, d.p, count);
+      if (kind == 2) LAUNCH_TC(ctx, k_tc_permute_batch, count, d.p, count);
+      else if (kind == 0) LAUNCH(ctx, k_permute_batch, ceil_div(count, ZKL_HASH_THREADS), ZKL_HASH_THREADS, 0, d.p, count);
       else LAUNCH(ctx, k_coop_permute_batch, ceil_div(count * ZKL_COOP_GROUP, ZKL_COOP_THREADS), ZKL_COOP_THREADS, 0, d.p, count);
     }
     ZKL_TRY(zkl_timer_stop(ctx, &ms));

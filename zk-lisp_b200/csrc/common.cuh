@@ -41,8 +41,10 @@ struct zkl_ctx {
   std::string err;
   uint64_t launches = 0;
   bool suite_loaded = false;
-  // sponge count from which the thread-per-sponge kernels are used instead of the cooperative ones
-  long bulk_threshold = 60000;
+  // sponge count from which the bulk kernels are used instead of the 16-thread cooperative ones
+  long bulk_threshold = 4096;
+  // bulk hashing path: 0 = tensor-core MDS (tcperm.cuh, the default), 1 = integer-pipe thread-per-sponge kernels
+  int hash_path = 0;
   std::map<size_t, domain_tables> tables;  // by N
   std::map<size_t, fe *> opow;             // GENERATOR^j tables by n
   std::map<size_t, fe *> periodic;         // periodic-column tables by (n << 8 | ce)

@@ -129,3 +129,41 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_merge_with_int_batch(fe se
   }
   tc_teardown(tc_smem);
 }
+
+// FRI layer leaves (same contract as k_fri_leaves, kernels_stark.cuh): leaf[k + B*i'] = hash_elements([ev[k][i'], ev[k][i' + nd/2]])
+__global__ void __launch_bounds__(TC_THREADS, 1) k_tc_fri_leaves(const fe *__restrict__ ev, int nd, int B, fe *__restrict__ leaves) {
+  extern __shared__ unsigned char tc_smem[];
+  tc_ctx c = tc_setup(tc_smem);
+  size_t half_rows = (size_t)nd / 2, total = half_rows * B;
+  size_t tiles = (total + TC_CTA_SPONGES - 1) / TC_CTA_SPONGES;
+  for (size_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    size_t g = tc_index(c, tile), t = g < total ? g : total - 1;
+    size_t k = t / half_rows, ip = t % half_rows;
+    elems_src src{ev + k * nd + ip, half_rows, 2};
+    fe d = tc_sponge_run(src, 2, c);
+    if (g < total && c.half == 0) st_fe(leaves + (k + (size_t)B * ip), d);
+  }
+  tc_teardown(tc_smem);
+}
+// grinding (same contract as k_grind): atomicMin over nonces in [nonce_base, nonce_base + count) whose digest has
+// >= bits trailing zeros in its first 8 little-endian bytes (agg/fs.rs:202-207)
+__global__ void __launch_bounds__(TC_THREADS, 1) k_tc_grind(const fe *__restrict__ seed, uint64_t nonce_base, uint32_t count, uint32_t bits,
+                                                            unsigned long long *result) {
+  if (*(volatile unsigned long long *)result < nonce_base) return;
+  extern __shared__ unsigned char tc_smem[];
+  tc_ctx c = tc_setup(tc_smem);
+  const fe sd = ld_fe(seed);
+  size_t tiles = ((size_t)count + TC_CTA_SPONGES - 1) / TC_CTA_SPONGES;
+  for (size_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    size_t g = tc_index(c, tile);
+    uint64_t nonce = nonce_base + (g < count ? g : count - 1);
+    mwi_src src{sd, nonce};
+    fe d = tc_sponge_run(src, 3, c);
+    if (g < count && c.half == 0) {
+      uint64_t head = ((uint64_t)d.l[1] << 32) | d.l[0];
+      uint32_t tz = head == 0 ? 64 : (uint32_t)__ffsll((long long)head) - 1;
+      if (tz >= bits) atomicMin(result, (unsigned long long)nonce);
+    }
+  }
+  tc_teardown(tc_smem);
+}

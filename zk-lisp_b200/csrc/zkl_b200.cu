@@ -10,6 +10,7 @@
 #include "kernels_hash.cuh"
 #include "kernels_ntt.cuh"
 #include "kernels_stark.cuh"
+#include "kernels_tc.cuh"
 
 static std::string g_create_error;
 static std::mutex g_suite_mutex;
@@ -20,6 +21,10 @@ static std::mutex g_suite_mutex;
     (ctx)->launches++;                                                              \
     ZKL_CHECK(ctx, cudaGetLastError());                                             \
   } while (0)
+// tensor-core sponge kernels: persistent, one 512-thread CTA per SM, `sponges` = number of sponges in the launch
+#define LAUNCH_TC(ctx, kernel, sponges, ...)                                                                        \
+  LAUNCH(ctx, kernel, std::min<size_t>(((size_t)(sponges) + TC_CTA_SPONGES - 1) / TC_CTA_SPONGES, (size_t)(ctx)->num_sms), TC_THREADS, \
+         TC_SMEM_BYTES, __VA_ARGS__)
 
 // ------------------------------------------------------------------------------------------------
 // context
@@ -65,6 +70,14 @@ extern "C" int zkl_ctx_create(int device, zkl_ctx **out) {
   // opt in to large dynamic shared memory for the single-pass column transforms
   cudaFuncSetAttribute(k_interpolate, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
   cudaFuncSetAttribute(k_lde, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+  cudaFuncSetAttribute(k_tc_permute_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+  cudaFuncSetAttribute(k_tc_hash_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+  cudaFuncSetAttribute(k_tc_merge_many_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+  cudaFuncSetAttribute(k_tc_merkle_level, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+  cudaFuncSetAttribute(k_tc_hash_elements_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+  cudaFuncSetAttribute(k_tc_merge_with_int_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+  cudaFuncSetAttribute(k_tc_fri_leaves, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+  cudaFuncSetAttribute(k_tc_grind, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
   label_consts lc;
   lc.elements = host_label("winter/hash/elements");
   lc.merge = host_label("zkl/winter/hash/merge");
@@ -107,6 +120,11 @@ extern "C" int zkl_suite_load(zkl_ctx *ctx, const zkl_suite *s) {
   std::lock_guard<std::mutex> g(g_suite_mutex);
   ZKL_CHECK(ctx, cudaMemcpyToSymbol(c_suite, &h, sizeof h));
   ZKL_CHECK(ctx, cudaMemcpyToSymbol(g_suite, &h, sizeof h));
+  {  // byte image of the MDS matrix for the tensor-core permutation (tcperm.cuh)
+    suite_consts *gs; ZKL_CHECK(ctx, cudaGetSymbolAddress((void **)&gs, g_suite));
+    LAUNCH(ctx, k_build_mds_bytes, ceil_div(TC_KCH * TC_N, 128), 128, 0, gs);
+    ZKL_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  }
   ctx->suite_loaded = true;
   return 0;
 }
@@ -193,10 +211,12 @@ static int dev_hash_rows(zkl_ctx *ctx, const fe *lde, size_t ncols, size_t n, si
   bool bulk = sponges >= (size_t)ctx->bulk_threshold;
   fe *dst = nchunks == 1 ? leaves : nullptr;
   if (nchunks > 1) { ZKL_CHECK(ctx, scratch.alloc(N * nchunks)); dst = scratch.p; }
-  if (bulk) LAUNCH(ctx, k_hash_rows, ceil_div(sponges, ZKL_HASH_THREADS), ZKL_HASH_THREADS, 0, lde, N, n, (int)blowup, (int)ncols, (int)ps, (int)nchunks, dst);
+  if (bulk && ctx->hash_path == 0) LAUNCH_TC(ctx, k_tc_hash_rows, sponges, lde, N, n, (int)blowup, (int)ncols, (int)ps, (int)nchunks, dst);
+  else if (bulk) LAUNCH(ctx, k_hash_rows, ceil_div(sponges, ZKL_HASH_THREADS), ZKL_HASH_THREADS, 0, lde, N, n, (int)blowup, (int)ncols, (int)ps, (int)nchunks, dst);
   else LAUNCH(ctx, k_coop_hash_rows, ceil_div(sponges * ZKL_COOP_GROUP, ZKL_COOP_THREADS), ZKL_COOP_THREADS, 0, lde, N, n, (int)blowup, (int)ncols, (int)ps, (int)nchunks, dst);
   if (nchunks > 1) {
-    if (N >= (size_t)ctx->bulk_threshold) LAUNCH(ctx, k_merge_many_rows, ceil_div(N, ZKL_HASH_THREADS), ZKL_HASH_THREADS, 0, scratch.p, N, (int)nchunks, leaves);
+    if (N >= (size_t)ctx->bulk_threshold && ctx->hash_path == 0) LAUNCH_TC(ctx, k_tc_merge_many_rows, N, scratch.p, N, (int)nchunks, leaves);
+    else if (N >= (size_t)ctx->bulk_threshold) LAUNCH(ctx, k_merge_many_rows, ceil_div(N, ZKL_HASH_THREADS), ZKL_HASH_THREADS, 0, scratch.p, N, (int)nchunks, leaves);
     else LAUNCH(ctx, k_coop_merge_many_rows, ceil_div(N * ZKL_COOP_GROUP, ZKL_COOP_THREADS), ZKL_COOP_THREADS, 0, scratch.p, N, (int)nchunks, leaves);
   }
   return 0;
@@ -207,7 +227,8 @@ static int dev_merkle(zkl_ctx *ctx, const fe *leaves, fe *nodes, size_t count) {
   if (count < 2 || (count & (count - 1))) { ctx->set_error("Merkle leaf count must be a power of two >= 2"); return 1; }
   const fe *in = leaves;
   for (size_t lvl = count / 2; lvl >= 1; lvl >>= 1) {
-    if (lvl >= (size_t)ctx->bulk_threshold) LAUNCH(ctx, k_merkle_level, ceil_div(lvl, ZKL_HASH_THREADS), ZKL_HASH_THREADS, 0, in, nodes + lvl, lvl);
+    if (lvl >= (size_t)ctx->bulk_threshold && ctx->hash_path == 0) LAUNCH_TC(ctx, k_tc_merkle_level, lvl, in, nodes + lvl, lvl);
+    else if (lvl >= (size_t)ctx->bulk_threshold) LAUNCH(ctx, k_merkle_level, ceil_div(lvl, ZKL_HASH_THREADS), ZKL_HASH_THREADS, 0, in, nodes + lvl, lvl);
     else LAUNCH(ctx, k_coop_merkle_level, ceil_div(lvl * ZKL_COOP_GROUP, ZKL_COOP_THREADS), ZKL_COOP_THREADS, 0, in, nodes + lvl, lvl);
     in = nodes + lvl;
   }
@@ -223,7 +244,8 @@ extern "C" int zkl_permute_batch(zkl_ctx *ctx, zkl_fe *states, size_t count) {
   ZKL_TRY(need_suite(ctx));
   dev_buf<fe> d; ZKL_CHECK(ctx, d.alloc(count * 12));
   ZKL_CHECK(ctx, cudaMemcpyAsync(d.p, states, count * 12 * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream));
-  LAUNCH(ctx, k_permute_batch, ceil_div(count, ZKL_HASH_THREADS), ZKL_HASH_THREADS, 0, d.p, count);
+  if (ctx->hash_path == 0) LAUNCH_TC(ctx, k_tc_permute_batch, count, d.p, count);
+  else LAUNCH(ctx, k_permute_batch, ceil_div(count, ZKL_HASH_THREADS), ZKL_HASH_THREADS, 0, d.p, count);
   ZKL_CHECK(ctx, cudaMemcpyAsync(states, d.p, count * 12 * sizeof(fe), cudaMemcpyDeviceToHost, ctx->stream));
   ZKL_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
   return 0;
@@ -239,7 +261,8 @@ extern "C" int zkl_hash_elements_batch(zkl_ctx *ctx, const zkl_fe *elems, size_t
   ZKL_TRY(need_suite(ctx));
   dev_buf<fe> d, o; ZKL_CHECK(ctx, d.alloc(std::max<size_t>(count * len, 1))); ZKL_CHECK(ctx, o.alloc(count));
   if (len) ZKL_CHECK(ctx, cudaMemcpyAsync(d.p, elems, count * len * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream));
-  LAUNCH(ctx, k_hash_elements_batch, ceil_div(count, ZKL_HASH_THREADS), ZKL_HASH_THREADS, 0, d.p, (int)len, count, o.p);
+  if (ctx->hash_path == 0) LAUNCH_TC(ctx, k_tc_hash_elements_batch, count, d.p, (int)len, count, o.p);
+  else LAUNCH(ctx, k_hash_elements_batch, ceil_div(count, ZKL_HASH_THREADS), ZKL_HASH_THREADS, 0, d.p, (int)len, count, o.p);
   return download_digests(ctx, o.p, count, out);
 }
 // a 32-byte digest as the element its sponge chunk folds to (utils.rs:359-371): lo16 mod p + (hi16 mod p)*2^64
@@ -253,14 +276,16 @@ extern "C" int zkl_merge_batch(zkl_ctx *ctx, const uint8_t *pairs, size_t count,
   for (size_t i = 0; i < 2 * count; i++) h[i] = fold_digest_host(pairs + 32 * i);
   dev_buf<fe> d, o; ZKL_CHECK(ctx, d.alloc(2 * count)); ZKL_CHECK(ctx, o.alloc(count));
   ZKL_CHECK(ctx, cudaMemcpyAsync(d.p, h.data(), 2 * count * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream));
-  LAUNCH(ctx, k_merkle_level, ceil_div(count, ZKL_HASH_THREADS), ZKL_HASH_THREADS, 0, d.p, o.p, count);
+  if (ctx->hash_path == 0) LAUNCH_TC(ctx, k_tc_merkle_level, count, d.p, o.p, count);
+  else LAUNCH(ctx, k_merkle_level, ceil_div(count, ZKL_HASH_THREADS), ZKL_HASH_THREADS, 0, d.p, o.p, count);
   return download_digests(ctx, o.p, count, out);
 }
 extern "C" int zkl_merge_with_int_batch(zkl_ctx *ctx, const uint8_t seed[32], const uint64_t *values, size_t count, uint8_t *out) {
   ZKL_TRY(need_suite(ctx));
   dev_buf<uint64_t> v; dev_buf<fe> o; ZKL_CHECK(ctx, v.alloc(count)); ZKL_CHECK(ctx, o.alloc(count));
   ZKL_CHECK(ctx, cudaMemcpyAsync(v.p, values, count * 8, cudaMemcpyHostToDevice, ctx->stream));
-  LAUNCH(ctx, k_merge_with_int_batch, ceil_div(count, ZKL_HASH_THREADS), ZKL_HASH_THREADS, 0, fold_digest_host(seed), v.p, count, o.p);
+  if (ctx->hash_path == 0) LAUNCH_TC(ctx, k_tc_merge_with_int_batch, count, fold_digest_host(seed), v.p, count, o.p);
+  else LAUNCH(ctx, k_merge_with_int_batch, ceil_div(count, ZKL_HASH_THREADS), ZKL_HASH_THREADS, 0, fold_digest_host(seed), v.p, count, o.p);
   return download_digests(ctx, o.p, count, out);
 }
 static int sponge_chunks(zkl_ctx *ctx, const uint8_t *data, size_t len, int kind, uint8_t out[32]) {
