@@ -16,6 +16,7 @@ void h_binop(int op, const fe *a, const fe *b, fe *out, long n) {
       case 7: out[i] = lazy_mul(a[i], b[i]); break;
       case 8: out[i] = lazy_add(a[i], b[i]); break;
       case 9: out[i] = lazy_canon(a[i]); break;
+      case 10: out[i] = lazy_sqr(a[i]); break;
     }
   }
 }
@@ -36,4 +37,8 @@ void h_tc_epilogue(const uint32_t *acc, const fe *rc, fe *out, long n) {
 void h_mul_wide(const fe *a, const fe *b, uint32_t *out, long n) {
   for (long i = 0; i < n; i++) lazy_mul_wide(a[i], b[i], out + 8 * i);
 }
+void h_sqr_wide(const fe *a, uint32_t *out, long n) {
+  for (long i = 0; i < n; i++) lazy_sqr_wide(a[i], out + 8 * i);
+}
+uint32_t h_tc_acc_max() { return TC_ACC_MAX; }
 }

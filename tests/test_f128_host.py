@@ -76,10 +76,24 @@ def test_mul_wide_is_the_exact_256_bit_product(hostlib):
     assert got == [x * y for x, y in zip(a, b)]
 
 
+def test_sqr_wide_matches_product(hostlib):
+    rng = random.Random(16)
+    a = rand_u128(rng, 8000) + [M128 - k for k in range(32)] + [((1 << 32) - 1) << (32 * k) for k in range(4)]
+    A = to_fe(a)
+    out = np.empty((len(a), 8), dtype=np.uint32)
+    hostlib.h_sqr_wide(A.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), C.c_long(len(a)))
+    got = [sum(int(out[i, j]) << (32 * j) for j in range(8)) for i in range(len(a))]
+    assert got == [x * x for x in a]
+    assert [g % P for g in binop(hostlib, 10, a, a)] == [x * x % P for x in a]
+
+
 def test_tc_epilogue_folds_byte_accumulators(hostlib):
-    """acc[u] < 384 * 255^2 (K = 384 products of two bytes); result ≡ sum acc[u] 2^(8u) + rc (mod p)."""
+    """acc[u] <= TC_ACC_MAX (pairs fit 32 bits; checked against the loaded constants by zkl_suite_load);
+    result ≡ sum acc[u] 2^(8u) + rc (mod p)."""
     rng = random.Random(14)
-    n, amax = 20000, 384 * 255 * 255
+    hostlib.h_tc_acc_max.restype = C.c_uint32
+    n, amax = 20000, int(hostlib.h_tc_acc_max())
+    assert (amax << 8) + amax < 2**32
     acc = np.empty((n, 16), dtype=np.uint32)
     for i in range(n):
         mode = rng.random()

@@ -59,6 +59,8 @@ int main(int argc, char **argv) {
   CK(cudaFuncSetAttribute(k_tc_merkle_level, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
   CK(cudaFuncSetAttribute(k_tc_hash_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
   int fails = 0;
+  printf("largest possible MMA accumulator %u (bound %u)\n", tc_max_accumulator(su), TC_ACC_MAX);
+  if (tc_max_accumulator(su) > TC_ACC_MAX) { printf("random MDS exceeds the accumulator bound\n"); return 3; }
 
   {  // 1. permutation vs host
     const size_t count = 1000;

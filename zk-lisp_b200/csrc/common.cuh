@@ -45,6 +45,7 @@ struct zkl_ctx {
   long bulk_threshold = 4096;
   // bulk hashing path: 0 = tensor-core MDS (tcperm.cuh, the default), 1 = integer-pipe thread-per-sponge kernels
   int hash_path = 0;
+  bool tc_ok = true;   // the loaded MDS constants satisfy the tensor-core epilogue's accumulator bound
   std::map<size_t, domain_tables> tables;  // by N
   std::map<size_t, fe *> opow;             // GENERATOR^j tables by n
   std::map<size_t, fe *> periodic;         // periodic-column tables by (n << 8 | ce)

@@ -29,6 +29,31 @@ ZKL_HD void lazy_mul_wide(const fe &a, const fe &b, uint32_t x[8]) {
   for (int i = 0; i < 8; i++) x[i] = t[i];
 }
 
+// 256-bit square: 4 squares + 6 cross products (10 wide multiplies instead of 16). Squares and the cross products
+// of one parity sit at disjoint limb positions, so they are assembled by concatenation; x^2 = S + 2 X.
+ZKL_HD void lazy_sqr_wide(const fe &a, uint32_t x[8]) {
+  const uint64_t s0 = (uint64_t)a.l[0] * a.l[0], s1 = (uint64_t)a.l[1] * a.l[1], s2 = (uint64_t)a.l[2] * a.l[2], s3 = (uint64_t)a.l[3] * a.l[3];
+  const uint64_t o12 = (uint64_t)a.l[0] * a.l[1], o34 = (uint64_t)a.l[0] * a.l[3], o56 = (uint64_t)a.l[2] * a.l[3];   // limbs 1, 3, 5
+  const uint64_t m34 = (uint64_t)a.l[1] * a.l[2];                                                                      // limb 3
+  const uint64_t e23 = (uint64_t)a.l[0] * a.l[2], e45 = (uint64_t)a.l[1] * a.l[3];                                     // limbs 2, 4
+  // X = O + M + E (limbs 1..7), X < 2^255
+  uint32_t x1 = (uint32_t)o12;
+  uint32_t x2 = p_add_cc((uint32_t)(o12 >> 32), (uint32_t)e23);
+  uint32_t x3 = p_addc_cc((uint32_t)o34, (uint32_t)(e23 >> 32));
+  uint32_t x4 = p_addc_cc((uint32_t)(o34 >> 32), (uint32_t)e45);
+  uint32_t x5 = p_addc_cc((uint32_t)o56, (uint32_t)(e45 >> 32));
+  uint32_t x6 = p_addc_cc((uint32_t)(o56 >> 32), 0);
+  uint32_t x7 = p_addc(0, 0);
+  x3 = p_add_cc(x3, (uint32_t)m34); x4 = p_addc_cc(x4, (uint32_t)(m34 >> 32)); x5 = p_addc_cc(x5, 0); x6 = p_addc_cc(x6, 0); x7 = p_addc(x7, 0);
+  // 2X
+  uint32_t d1 = x1 << 1, d2 = p_shf_l(x1, x2, 1), d3 = p_shf_l(x2, x3, 1), d4 = p_shf_l(x3, x4, 1), d5 = p_shf_l(x4, x5, 1),
+           d6 = p_shf_l(x5, x6, 1), d7 = p_shf_l(x6, x7, 1);
+  x[0] = (uint32_t)s0;
+  x[1] = p_add_cc((uint32_t)(s0 >> 32), d1); x[2] = p_addc_cc((uint32_t)s1, d2); x[3] = p_addc_cc((uint32_t)(s1 >> 32), d3);
+  x[4] = p_addc_cc((uint32_t)s2, d4); x[5] = p_addc_cc((uint32_t)(s2 >> 32), d5); x[6] = p_addc_cc((uint32_t)s3, d6);
+  x[7] = p_addc((uint32_t)(s3 >> 32), d7);
+}
+
 // conditional "+C" after an addition that overflowed 2^128 (2^128 ≡ C = 45*2^40 - 1): the wrapped value is
 // small enough in every caller (< 2^96) that the correction cannot overflow again and never reaches limb 3.
 ZKL_HD void lazy_fix_carry(uint32_t &z0, uint32_t &z1, uint32_t &z2, uint32_t cout) {
@@ -66,6 +91,7 @@ ZKL_HD fe lazy_reduce8(const uint32_t x[8]) {
   return r;
 }
 ZKL_HD fe lazy_mul(const fe &a, const fe &b) { uint32_t x[8]; lazy_mul_wide(a, b, x); return lazy_reduce8(x); }
+ZKL_HD fe lazy_sqr(const fe &a) { uint32_t x[8]; lazy_sqr_wide(a, x); return lazy_reduce8(x); }
 
 // a + b for lazy a, b (sponge absorb). The sum wraps at most once; the wrapped value + C stays below 2^128
 // unless both inputs were within 2^46 of 2^128, in which case a second (exact) wrap is applied.
@@ -82,26 +108,21 @@ ZKL_HD fe lazy_add(const fe &a, const fe &b) {
 // lazy -> canonical (v < 2^128 < 2p: one conditional subtraction)
 ZKL_HD fe lazy_canon(const fe &a) { return fe_from_u128_mod(a); }
 
-// Tensor-core MDS epilogue: acc[u] = sum over (k, v) of byte_u(M[i][k] * 2^(8v) mod p) * byte_v(cube_k), u = 0..15,
-// each < 2^25. V = sum_u acc[u] * 2^(8u) + rc  (< 2^146) is folded once to a lazy element.
+// Tensor-core MDS epilogue: acc[u] = sum over (k, v) of byte_u(M[i][k] * 2^(8v) mod p) * byte_v(cube_k), u = 0..15.
+// PRECONDITION acc[u] <= TC_ACC_MAX = 2^24 - 2^16 - 1, so that a pair acc[2j] + acc[2j+1]*2^8 fits 32 bits. The bound
+// holds iff 255 * (largest row sum of the byte matrix) <= TC_ACC_MAX, which zkl_suite_load verifies for the loaded
+// constants (hasher suite: 13 497 915). V = sum_u acc[u] * 2^(8u) + rc (< 2^146) is folded once to a lazy element.
+//   pairs P_j at bit 16 j: even j concatenate into limbs 0..3, odd j concatenate and shift by 16 — no multiplies.
+#define TC_ACC_MAX 16711679u
 ZKL_HD fe tc_epilogue(const uint32_t acc[16], const fe &rc) {
-  // G_j = acc[4j] + acc[4j+1]*2^8 + acc[4j+2]*2^16 + acc[4j+3]*2^24  (< 2^50)
-  uint64_t G[4];
+  uint32_t P[8];
 #pragma unroll
-  for (int j = 0; j < 4; j++) {
-    uint64_t g = (uint64_t)acc[4 * j + 3] * (1u << 24) + acc[4 * j];
-    g = (uint64_t)acc[4 * j + 2] * (1u << 16) + g;
-    g = (uint64_t)acc[4 * j + 1] * (1u << 8) + g;
-    G[j] = g;
-  }
-  uint32_t w0 = (uint32_t)G[0];
-  uint32_t w1 = p_add_cc((uint32_t)(G[0] >> 32), (uint32_t)G[1]);
-  uint32_t w2 = p_addc_cc((uint32_t)(G[1] >> 32), (uint32_t)G[2]);
-  uint32_t w3 = p_addc_cc((uint32_t)(G[2] >> 32), (uint32_t)G[3]);
-  uint32_t w4 = p_addc((uint32_t)(G[3] >> 32), 0);
+  for (int j = 0; j < 8; j++) P[j] = acc[2 * j] + (acc[2 * j + 1] << 8);
+  uint32_t o0 = P[1] << 16, o1 = p_shf_l(P[1], P[3], 16), o2 = p_shf_l(P[3], P[5], 16), o3 = p_shf_l(P[5], P[7], 16), o4 = P[7] >> 16;
+  uint32_t w0 = p_add_cc(P[0], o0), w1 = p_addc_cc(P[2], o1), w2 = p_addc_cc(P[4], o2), w3 = p_addc_cc(P[6], o3), w4 = p_addc(o4, 0);
   w0 = p_add_cc(w0, rc.l[0]); w1 = p_addc_cc(w1, rc.l[1]); w2 = p_addc_cc(w2, rc.l[2]); w3 = p_addc_cc(w3, rc.l[3]);
-  w4 = p_addc(w4, 0);                                   // < 2^19
-  // fold: V ≡ lo + (w4*45 << 40) - w4 ; t = w4*45 < 2^24 so (t << 40) lives in limb 1 only
+  w4 = p_addc(w4, 0);                                   // < 2^17
+  // fold: V ≡ lo + (w4*45 << 40) - w4 ; t = w4*45 < 2^23 so (t << 40) lives in limb 1 only
   uint32_t t = w4 * 45u;
   uint32_t d0 = p_sub_cc(0, w4), d1 = p_subc(t << 8, 0);
   uint32_t z0 = p_add_cc(w0, d0), z1 = p_addc_cc(w1, d1), z2 = p_addc_cc(w2, 0), z3 = p_addc_cc(w3, 0), c = p_addc(0, 0);

@@ -118,6 +118,25 @@ __global__ void k_build_mds_bytes(const suite_consts *suite) {
   g_mds_bytes[t] = make_uint4(out[0], out[1], out[2], out[3]);
 }
 
+#endif  // __CUDACC__ (device part 1)
+// Host-side check of tc_epilogue's precondition for a given MDS matrix: the largest accumulator any state can
+// produce is 255 * (largest row sum of the byte matrix). Returns that bound.
+static inline uint32_t tc_max_accumulator(const suite_consts &su) {
+  uint32_t best = 0;
+  for (int i = 0; i < 12; i++) {
+    uint32_t sum[16] = {0};
+    for (int k = 0; k < 12; k++) {
+      fe cur = su.mds[i][k];
+      for (int v = 0; v < 32; v++) {
+        for (int u = 0; u < 16; u++) sum[u] += (cur.l[u >> 2] >> (8 * (u & 3))) & 0xFF;
+        cur = fe_mul(cur, fe_from_u64(256));
+      }
+    }
+    for (int u = 0; u < 16; u++) if (sum[u] > best) best = sum[u];
+  }
+  return best * 255u;
+}
+#if defined(__CUDACC__)
 // ---------------------------------------------------------------- per-thread context
 struct tc_ctx {
   uint32_t a_addr;    // shared address of this sponge's 16-byte slot in chunk 0 of the set's A tile
@@ -188,7 +207,7 @@ __device__ __forceinline__ void tc_permute(fe (&st)[6], tc_ctx &c) {
     // cubes: x^2 reduced lazily, x^2 * x left as 256 raw bits = two K chunks of this sponge's A row
 #pragma unroll
     for (int j = 0; j < 6; j++) {
-      fe sq = lazy_mul(st[j], st[j]);
+      fe sq = lazy_sqr(st[j]);
       uint32_t x[8]; lazy_mul_wide(sq, st[j], x);
       uint32_t a = c.a_addr + (uint32_t)(2 * (lane0 + j)) * (TC_SPONGES * 16);
       sts_u4(a, x[0], x[1], x[2], x[3]);

@@ -120,6 +120,9 @@ extern "C" int zkl_suite_load(zkl_ctx *ctx, const zkl_suite *s) {
   std::lock_guard<std::mutex> g(g_suite_mutex);
   ZKL_CHECK(ctx, cudaMemcpyToSymbol(c_suite, &h, sizeof h));
   ZKL_CHECK(ctx, cudaMemcpyToSymbol(g_suite, &h, sizeof h));
+  // tc_epilogue packs accumulator pairs into 32 bits: verify the bound for these constants, else use the integer pipe
+  ctx->tc_ok = tc_max_accumulator(h) <= TC_ACC_MAX;
+  if (!ctx->tc_ok) ctx->hash_path = 1;
   {  // byte image of the MDS matrix for the tensor-core permutation (tcperm.cuh)
     suite_consts *gs; ZKL_CHECK(ctx, cudaGetSymbolAddress((void **)&gs, g_suite));
     LAUNCH(ctx, k_build_mds_bytes, ceil_div(TC_KCH * TC_N, 128), 128, 0, gs);
