@@ -66,6 +66,8 @@ ZKL_HD void lazy_fix_carry(uint32_t &z0, uint32_t &z1, uint32_t &z2, uint32_t co
 // x (256 bits) -> lazy element. Two folds of the high part with 2^128 ≡ 45*2^40 - 1.
 //   y = lo + (hi*45 << 40) - hi            < 2^175   (never negative: hi*45*2^40 >= hi)
 //   z = y_lo + (hi2*45 << 40) - hi2        hi2 = y >> 128 < 2^47 ; z < 2^128 + 2^93, one conditional +C
+// (Measured on B200: the word-aligned form 2^128 ≡ 11520*2^32 - 1, which needs no funnel shifts and 7 fewer instructions per
+//  reduction, runs the permutation kernel 6% SLOWER (316 vs 337 M perm/s, tools/tc_probe A/B run) — ptxas schedules it worse.)
 ZKL_HD fe lazy_reduce8(const uint32_t x[8]) {
   // t = hi * 45 : four independent wide products, one ripple add
   uint64_t P0 = (uint64_t)x[4] * 45u, P1 = (uint64_t)x[5] * 45u, P2 = (uint64_t)x[6] * 45u, P3 = (uint64_t)x[7] * 45u;

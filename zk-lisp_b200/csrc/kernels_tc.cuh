@@ -3,7 +3,7 @@
 // Reference semantics: zk-lisp-proof-winterfell/src/poseidon/hasher.rs:57-140 (entry points), :144-231 (sponge);
 // row hashing with partitions src/agg/child.rs:1025-1045.
 //
-// Every kernel is persistent: grid = min(#tiles, #SMs) CTAs of 512 threads, one CTA per SM (the B matrix image,
+// Every kernel is persistent: grid = min(#tiles, #SMs) CTAs of 576 threads (512 compute + 2 MMA warps), one CTA per SM (the B matrix image,
 // two A tiles and all 512 TMEM columns are per CTA), each looping over tiles of 256 sponges (2 sets x 128).
 // Thread (set, sponge, half) owns lanes 6*half .. 6*half+5 of its sponge; the absorb of item l (state lane l,
 // l < 10) is done by the thread that owns lane l.
@@ -16,15 +16,15 @@
 // Returns lane 0 (canonical) in the half-0 thread of each sponge.
 template <typename Src>
 __device__ __forceinline__ fe tc_sponge_run(const Src &src, int total, tc_ctx &c) {
-  fe st[6];
+  fe st[TC_LPT];
 #pragma unroll
-  for (int j = 0; j < 6; j++) st[j] = fe_zero();
-  if (c.half) { st[4] = ldc_fe(&c_suite.dom[0]); st[5] = ldc_fe(&c_suite.dom[1]); }
-  const int lane0 = 6 * c.half;
+  for (int j = 0; j < TC_LPT; j++) st[j] = fe_zero();
+  if (c.half == TC_SPLIT - 1) { st[TC_LPT - 2] = ldc_fe(&c_suite.dom[0]); st[TC_LPT - 1] = ldc_fe(&c_suite.dom[1]); }
+  const int lane0 = TC_LPT * c.half;
 #pragma unroll 1
   for (int m = 0; m < total; m += ZKL_RATE) {
 #pragma unroll
-    for (int j = 0; j < 6; j++) {
+    for (int j = 0; j < TC_LPT; j++) {
       int l = lane0 + j;
       if (l < ZKL_RATE && m + l < total) st[j] = lazy_add(st[j], src.item(m + l));
     }
@@ -32,6 +32,10 @@ __device__ __forceinline__ fe tc_sponge_run(const Src &src, int total, tc_ctx &c
   }
   return lazy_canon(st[0]);
 }
+
+// number of tiles the persistent CTA `blockIdx.x` processes
+__device__ __forceinline__ uint64_t tc_my_tiles(size_t tiles) { return blockIdx.x < tiles ? (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0; }
+__device__ __forceinline__ uint64_t tc_perms(int total_items) { return (uint64_t)((total_items + ZKL_RATE - 1) / ZKL_RATE); }
 
 // sponge index handled by this thread in tile `tile`
 __device__ __forceinline__ size_t tc_index(const tc_ctx &c, size_t tile) { return tile * TC_CTA_SPONGES + (size_t)c.set * TC_SPONGES + c.sponge; }
@@ -41,15 +45,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_permute_batch(fe *states, 
   extern __shared__ unsigned char tc_smem[];
   tc_ctx c = tc_setup(tc_smem);
   size_t tiles = (count + TC_CTA_SPONGES - 1) / TC_CTA_SPONGES;
-  for (size_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+  if (c.is_mma) tc_mma_loop(c, tc_my_tiles(tiles) * ZKL_ROUNDS);
+  else for (size_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     size_t i = tc_index(c, tile), ic = i < count ? i : count - 1;
-    fe st[6];
+    fe st[TC_LPT];
 #pragma unroll
-    for (int j = 0; j < 6; j++) st[j] = ld_fe(states + 12 * ic + 6 * c.half + j);
+    for (int j = 0; j < TC_LPT; j++) st[j] = ld_fe(states + 12 * ic + TC_LPT * c.half + j);
     tc_permute(st, c);
     if (i < count) {
 #pragma unroll
-      for (int j = 0; j < 6; j++) st_fe(states + 12 * i + 6 * c.half + j, lazy_canon(st[j]));
+      for (int j = 0; j < TC_LPT; j++) st_fe(states + 12 * i + TC_LPT * c.half + j, lazy_canon(st[j]));
     }
   }
   tc_teardown(tc_smem);
@@ -65,7 +70,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_hash_rows(const fe *__rest
   tc_ctx c = tc_setup(tc_smem);
   size_t tiles_per_part = (N + TC_CTA_SPONGES - 1) / TC_CTA_SPONGES;
   size_t tiles = tiles_per_part * (size_t)nchunks;
-  for (size_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+  if (c.is_mma) {
+    uint64_t perms = 0;
+    for (size_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) perms += tc_perms(1 + (min(psize, W - (int)(tile / tiles_per_part) * psize) + 1) / 2);
+    tc_mma_loop(c, perms * ZKL_ROUNDS);
+  } else for (size_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     int q = (int)(tile / tiles_per_part);
     size_t s = tc_index(c, tile % tiles_per_part), sc = s < N ? s : N - 1;
     int first = q * psize, len = min(psize, W - first);
@@ -83,7 +92,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_merge_many_rows(const fe *
   extern __shared__ unsigned char tc_smem[];
   tc_ctx c = tc_setup(tc_smem);
   size_t tiles = (N + TC_CTA_SPONGES - 1) / TC_CTA_SPONGES;
-  for (size_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+  if (c.is_mma) tc_mma_loop(c, tc_my_tiles(tiles) * tc_perms(1 + nchunks) * ZKL_ROUNDS);
+  else for (size_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     size_t r = tc_index(c, tile), rc = r < N ? r : N - 1;
     many_src src{parts + rc, N};
     fe d = tc_sponge_run(src, 1 + nchunks, c);
@@ -96,10 +106,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_merkle_level(const fe *__r
   extern __shared__ unsigned char tc_smem[];
   tc_ctx c = tc_setup(tc_smem);
   size_t tiles = (count + TC_CTA_SPONGES - 1) / TC_CTA_SPONGES;
-  for (size_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+  if (c.is_mma) tc_mma_loop(c, tc_my_tiles(tiles) * ZKL_ROUNDS);
+  else for (size_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     size_t i = tc_index(c, tile), ic = i < count ? i : count - 1;
     merge_src src{fe_zero(), fe_zero()};
-    if (c.half == 0) { src.a = ld_fe(in + 2 * ic); src.b = ld_fe(in + 2 * ic + 1); }   // items 1, 2 live in lanes 1, 2
+    if (c.half == 0) { src.a = ld_fe(in + 2 * ic); src.b = ld_fe(in + 2 * ic + 1); }   // items 1, 2 live in lanes 1, 2 (TC_LPT >= 3)
     fe d = tc_sponge_run(src, 3, c);
     if (i < count && c.half == 0) st_fe(out + i, d);
   }
@@ -109,7 +120,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_hash_elements_batch(const 
   extern __shared__ unsigned char tc_smem[];
   tc_ctx c = tc_setup(tc_smem);
   size_t tiles = (count + TC_CTA_SPONGES - 1) / TC_CTA_SPONGES;
-  for (size_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+  if (c.is_mma) tc_mma_loop(c, tc_my_tiles(tiles) * tc_perms(1 + (len + 1) / 2) * ZKL_ROUNDS);
+  else for (size_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     size_t i = tc_index(c, tile), ic = i < count ? i : count - 1;
     elems_src src{elems + ic * (size_t)len, 1, len};
     fe d = tc_sponge_run(src, 1 + (len + 1) / 2, c);
@@ -121,7 +133,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_merge_with_int_batch(fe se
   extern __shared__ unsigned char tc_smem[];
   tc_ctx c = tc_setup(tc_smem);
   size_t tiles = (count + TC_CTA_SPONGES - 1) / TC_CTA_SPONGES;
-  for (size_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+  if (c.is_mma) tc_mma_loop(c, tc_my_tiles(tiles) * ZKL_ROUNDS);
+  else for (size_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     size_t i = tc_index(c, tile), ic = i < count ? i : count - 1;
     mwi_src src{seed, vals[ic]};
     fe d = tc_sponge_run(src, 3, c);
@@ -136,7 +149,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_fri_leaves(const fe *__res
   tc_ctx c = tc_setup(tc_smem);
   size_t half_rows = (size_t)nd / 2, total = half_rows * B;
   size_t tiles = (total + TC_CTA_SPONGES - 1) / TC_CTA_SPONGES;
-  for (size_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+  if (c.is_mma) tc_mma_loop(c, tc_my_tiles(tiles) * ZKL_ROUNDS);
+  else for (size_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     size_t g = tc_index(c, tile), t = g < total ? g : total - 1;
     size_t k = t / half_rows, ip = t % half_rows;
     elems_src src{ev + k * nd + ip, half_rows, 2};
@@ -154,7 +168,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_grind(const fe *__restrict
   tc_ctx c = tc_setup(tc_smem);
   const fe sd = ld_fe(seed);
   size_t tiles = ((size_t)count + TC_CTA_SPONGES - 1) / TC_CTA_SPONGES;
-  for (size_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+  if (c.is_mma) tc_mma_loop(c, tc_my_tiles(tiles) * ZKL_ROUNDS);
+  else for (size_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     size_t g = tc_index(c, tile);
     uint64_t nonce = nonce_base + (g < count ? g : count - 1);
     mwi_src src{sd, nonce};

@@ -12,25 +12,35 @@
 // (tc_epilogue). Per state and round this replaces 144 field products (2304 IMAD.WIDE + carries) by a tensor-core
 // tile, leaving 24 products on the integer pipe.
 //
-// Organisation: a CTA of 512 threads runs TWO independent sets of 128 sponges (one sponge per TMEM lane, two
-// threads per sponge owning lanes 0..5 / 6..11), so one set's integer work overlaps the other set's MMA.
+// Organisation: a CTA runs TWO independent sets of 128 sponges (one sponge per TMEM lane, two compute threads per
+// sponge owning lanes 0..5 / 6..11: 2 x 256 compute threads) plus one MMA-issuing warp per set (576 threads).
 //   shared memory: B (24 x 192 x 16 B = 72 KB, K-major, no swizzle) + per set A (24 x 128 x 16 B = 48 KB)
 //   TMEM: 512 columns, set s uses columns [256 s, 256 s + 192): D[sponge][16 i + u]
-// Per round and set: cubes -> st.shared (A) -> fence.proxy.async -> named barrier -> one thread issues
-// 12 tcgen05.mma (M 128, N 192, K 32) + tcgen05.commit -> mbarrier wait -> tcgen05.ld 6 x 16 columns -> epilogue.
+// Per round and set (producer/consumer over mbarriers, no CTA-wide barrier): for j = 0..5 each compute warp writes its
+// cubes of lanes j and 6 + j to A (st.shared, fence.proxy.async) and arrives on full[j]; the MMA warp waits on
+// full[j] and issues the two tcgen05.mma (M 128, N 192, K 32) of those lanes, after j = 5 a tcgen05.commit on
+// dready; compute warps wait on dready, tcgen05.ld their 6 x 16 columns and run the epilogue.
 #pragma once
 #include "f128_lazy.cuh"
 #include "poseidon.cuh"
 
 #define TC_KCH 24                 // 16-byte K chunks: 12 lanes x 32 cube bytes
 #define TC_SPONGES 128            // per set = TMEM lanes = MMA M
-#define TC_SET_THREADS 256
+#ifndef TC_LPT
+#define TC_LPT 6                  // state lanes per compute thread: 6 (two threads per sponge) or 4 (three threads per sponge)
+#endif
+#define TC_SPLIT (12 / TC_LPT)    // compute threads per sponge
+#ifndef TC_GRP
+#define TC_GRP 1                  // lanes a thread cubes between two publishes to the MMA warp (divides TC_LPT)
+#endif
+#define TC_NGRP (TC_LPT / TC_GRP)
+#define TC_SET_THREADS (TC_SPONGES * TC_SPLIT)
 #define TC_SETS 2
-#define TC_THREADS (TC_SETS * TC_SET_THREADS)
+#define TC_THREADS (TC_SETS * TC_SET_THREADS + 32 * TC_SETS)   // compute warps + one MMA warp per set
 #define TC_N 192                  // MMA N = 12 output lanes x 16 bytes
 #define TC_B_BYTES (TC_KCH * TC_N * 16)
 #define TC_A_BYTES (TC_KCH * TC_SPONGES * 16)
-#define TC_CTL_BYTES 128          // mbarriers + TMEM base address
+#define TC_CTL_BYTES 256          // mbarriers + TMEM base address
 #define TC_SMEM_BYTES (TC_B_BYTES + TC_SETS * TC_A_BYTES + TC_CTL_BYTES + 128)
 #define TC_TMEM_COLS 512
 #define TC_SET_COLS 256
@@ -138,17 +148,27 @@ static inline uint32_t tc_max_accumulator(const suite_consts &su) {
 }
 #if defined(__CUDACC__)
 // ---------------------------------------------------------------- per-thread context
+// Warp roles: warps 0..15 compute (set = warp / 8; sponge = 32 (warp & 3) + lane — the TMEM lane quadrant a warp may
+// read is warp % 4; half = (warp >> 2) & 1), warps 16 and 17 issue the MMAs of set 0 and set 1.
+// Shared-memory control block per set (64 bytes): full[j], j < TC_LPT (one arrival per compute warp, after the
+// warp's cubes of lanes j, TC_LPT + j, ... are in A), then dready (tcgen05.commit of the round's last MMA).
 struct tc_ctx {
   uint32_t a_addr;    // shared address of this sponge's 16-byte slot in chunk 0 of the set's A tile
   uint32_t a_tile;    // shared address of the set's A tile
   uint32_t b_tile;    // shared address of B
   uint32_t tmem;      // TMEM address: lane quadrant of this warp, first column of this thread's 6 output lanes
   uint32_t tmem_d;    // TMEM address of the set's accumulator (lane 0)
-  uint32_t mbar;      // shared address of the set's mbarrier
-  uint32_t phase;     // mbarrier phase parity to wait for next
-  int set, half, sponge;  // set index, lane half (0: lanes 0..5, 1: lanes 6..11), sponge index within the set
-  bool issuer;
+  uint32_t full;      // shared address of full[0] of the set
+  uint32_t dready;    // shared address of the set's accumulator-ready barrier
+  uint32_t phase;     // phase parity of the current round (all barriers of a set flip once per round)
+  int set, half, sponge;
+  bool is_mma;        // MMA-issuing warp (no sponge)
 };
+#define TC_COMPUTE_WARPS_PER_SET (TC_SET_THREADS / 32)
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 
 // CTA prologue: copies B, allocates TMEM, initialises the barriers. `smem` = dynamic shared memory base (>= TC_SMEM_BYTES).
 __device__ __forceinline__ tc_ctx tc_setup(unsigned char *smem_raw) {
@@ -160,31 +180,35 @@ __device__ __forceinline__ tc_ctx tc_setup(unsigned char *smem_raw) {
   for (int i = threadIdx.x; i < TC_B_BYTES / 16; i += TC_THREADS) bdst[i] = g_mds_bytes[i];
   uint32_t *ctl_gen = reinterpret_cast<uint32_t *>(gen + TC_B_BYTES + TC_SETS * TC_A_BYTES);
   if (threadIdx.x < 32) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ctl + 64), "n"(TC_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ctl + 128), "n"(TC_TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (threadIdx.x == 32) {
-    mbar_init(ctl, 1); mbar_init(ctl + 8, 1);
+    for (int s = 0; s < TC_SETS; s++) {
+      for (int j = 0; j < TC_NGRP; j++) mbar_init(ctl + 64 * s + 8 * j, TC_COMPUTE_WARPS_PER_SET);
+      mbar_init(ctl + 64 * s + 48, 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   fence_proxy_async_smem();   // B was written through the generic proxy, the MMA reads it through the async proxy
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  uint32_t tmem_base = ctl_gen[16];
+  uint32_t tmem_base = ctl_gen[32];
   tc_ctx c;
-  int tid = threadIdx.x % TC_SET_THREADS, warp = tid >> 5, lane = tid & 31;
-  c.set = threadIdx.x / TC_SET_THREADS;
-  c.half = warp >> 2;
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  c.is_mma = warp >= TC_SETS * TC_COMPUTE_WARPS_PER_SET;
+  c.set = c.is_mma ? warp - TC_SETS * TC_COMPUTE_WARPS_PER_SET : warp / TC_COMPUTE_WARPS_PER_SET;
+  c.half = (warp % TC_COMPUTE_WARPS_PER_SET) >> 2;   // which group of TC_LPT lanes this thread owns
   c.sponge = 32 * (warp & 3) + lane;
   c.a_tile = a0 + c.set * TC_A_BYTES;
   c.a_addr = c.a_tile + c.sponge * 16;
   c.b_tile = b_tile;
   c.tmem_d = tmem_base + c.set * TC_SET_COLS;
-  c.tmem = c.tmem_d + ((uint32_t)(32 * (warp & 3)) << 16) + 96 * c.half;
-  c.mbar = ctl + 8 * c.set;
+  c.tmem = c.tmem_d + ((uint32_t)(32 * (warp & 3)) << 16) + 16 * TC_LPT * c.half;
+  c.full = ctl + 64 * c.set;
+  c.dready = c.full + 48;
   c.phase = 0;
-  c.issuer = tid == 0;
   return c;
 }
 // CTA epilogue (all threads)
@@ -194,47 +218,72 @@ __device__ __forceinline__ void tc_teardown(unsigned char *smem_raw) {
   if (threadIdx.x < 32) {
     uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
     const uint32_t *ctl_gen = reinterpret_cast<const uint32_t *>(smem_raw + (base - smem_u32(smem_raw)) + TC_B_BYTES + TC_SETS * TC_A_BYTES);
-    uint32_t tmem_base = ctl_gen[16];
+    uint32_t tmem_base = ctl_gen[32];
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TC_TMEM_COLS) : "memory");
   }
 }
 
-// The permutation. Called by all 256 threads of a set together; st[j] = lazy lane 6*half + j of this thread's sponge.
-__device__ __forceinline__ void tc_permute(fe (&st)[6], tc_ctx &c) {
-  const int lane0 = 6 * c.half;
+// MMA warp: `rounds` = 27 x (number of permutations the set's compute warps will run in this kernel). Per round the
+// MMAs of lanes j, TC_LPT + j, ... (one MMA = one lane = 32 cube bytes of K) are issued as soon as all compute warps
+// have published those cubes, so only the last group is exposed latency; the commit after the last group signals dready.
+__device__ __forceinline__ void tc_mma_loop(const tc_ctx &c, uint64_t rounds) {
+  const uint64_t adesc = tc_smem_desc(c.a_tile, TC_SPONGES * 16, 128);
+  const uint64_t bdesc = tc_smem_desc(c.b_tile, TC_N * 16, 128);
+  const bool leader = (threadIdx.x & 31) == 0;
+  uint32_t phase = 0;
+#pragma unroll 1
+  for (uint64_t r = 0; r < rounds; r++) {
+#pragma unroll
+    for (int q = 0; q < TC_NGRP; q++) {
+      mbar_wait(c.full + 8 * q, phase);
+      tc_fence_after();
+      if (leader) {
+#pragma unroll
+        for (int jj = 0; jj < TC_GRP; jj++) {
+#pragma unroll
+          for (int g = 0; g < TC_SPLIT; g++) {   // one MMA = one state lane = 32 cube bytes of K
+            const int l = g * TC_LPT + q * TC_GRP + jj;
+            tc_mma_i8(c.tmem_d, adesc + (uint64_t)((2 * l * TC_SPONGES * 16) >> 4), bdesc + (uint64_t)((2 * l * TC_N * 16) >> 4), TC_IDESC, (q | jj | g) > 0);
+          }
+        }
+        if (q == TC_NGRP - 1) tc_commit(c.dready);
+      }
+      __syncwarp();
+    }
+    phase ^= 1;
+  }
+}
+
+// The permutation, compute side. Called by all compute threads of a set together; st[j] = lazy lane TC_LPT*half + j.
+__device__ __forceinline__ void tc_permute(fe (&st)[TC_LPT], tc_ctx &c) {
+  const int lane0 = TC_LPT * c.half;
+  const bool leader = (threadIdx.x & 31) == 0;
 #pragma unroll 1
   for (int r = 0; r < ZKL_ROUNDS; r++) {
+    tc_fence_before();              // this thread's tcgen05.ld of the previous round are complete (wait::ld) and ordered
     // cubes: x^2 reduced lazily, x^2 * x left as 256 raw bits = two K chunks of this sponge's A row
 #pragma unroll
-    for (int j = 0; j < 6; j++) {
+    for (int j = 0; j < TC_LPT; j++) {
       fe sq = lazy_sqr(st[j]);
       uint32_t x[8]; lazy_mul_wide(sq, st[j], x);
       uint32_t a = c.a_addr + (uint32_t)(2 * (lane0 + j)) * (TC_SPONGES * 16);
       sts_u4(a, x[0], x[1], x[2], x[3]);
       sts_u4(a + TC_SPONGES * 16, x[4], x[5], x[6], x[7]);
+      if ((j + 1) % TC_GRP == 0) {
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (leader) mbar_arrive(c.full + 8 * (j / TC_GRP));
+      }
     }
-    fence_proxy_async_smem();
-    tc_fence_before();              // this thread's tcgen05.ld of the previous round are complete (wait::ld) and ordered
-    named_bar_sync(1 + c.set, TC_SET_THREADS);
-    if (c.issuer) {
-      tc_fence_after();
-      const uint64_t adesc = tc_smem_desc(c.a_tile, TC_SPONGES * 16, 128);
-      const uint64_t bdesc = tc_smem_desc(c.b_tile, TC_N * 16, 128);
-#pragma unroll
-      for (int k = 0; k < TC_KCH / 2; k++)   // each MMA consumes two 16-byte K chunks
-        tc_mma_i8(c.tmem_d, adesc + (uint64_t)((2 * k * TC_SPONGES * 16) >> 4), bdesc + (uint64_t)((2 * k * TC_N * 16) >> 4), TC_IDESC, k > 0);
-      tc_commit(c.mbar);
-    }
-    __syncwarp();                   // reconverge the issuer's warp before it spins on the barrier
-    mbar_wait(c.mbar, c.phase);
+    mbar_wait(c.dready, c.phase);
     c.phase ^= 1;
     tc_fence_after();
     uint32_t acc[2][16];
     tmem_ld16(c.tmem, acc[0]);
 #pragma unroll
-    for (int j = 0; j < 6; j++) {
+    for (int j = 0; j < TC_LPT; j++) {
       tmem_wait_ld(acc[j & 1]);
-      if (j < 5) tmem_ld16(c.tmem + 16 * (j + 1), acc[(j + 1) & 1]);
+      if (j < TC_LPT - 1) tmem_ld16(c.tmem + 16 * (j + 1), acc[(j + 1) & 1]);
       st[j] = tc_epilogue(acc[j & 1], ldc_fe(&c_suite.rc[r][lane0 + j]));
     }
   }
