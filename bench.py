@@ -32,14 +32,16 @@ import numpy as np  # noqa: E402
 SEGMENTS, ROWS, QUERIES, BLOWUP, GRIND = 16, 4096, 64, 16, 16
 METRIC, UNIT = "rollup-bench prove throughput (trace rows/s)", "trace rows/s"
 WORKLOAD = "rollup-bench: 16 segments x (n=4096, W=204, blowup=16, q=64, grind=16), synthetic AIR-valid traces"
-# algorithmic work of the dominant kernel (trace row hashing), SURVEY.md §8(d):
-# W=204 -> 1 + 102 absorbs -> 11 permutations per LDE row; one permutation = 27 rounds x (12 cubes = 24
-# products + 12x12 MDS = 144 products) = 4536 field products = 4536*16 32x32->64 multiply-accumulates.
+# algorithmic work of the dominant kernel (trace row hashing, k_tc_hash_rows), SURVEY.md §8(d):
+# W=204 -> 1 + 102 absorbs -> 11 permutations per LDE row; one permutation = 27 rounds; per round the 12x12 MDS
+# product over f128 runs on the tensor cores as a u8 x u8 -> s32 GEMM tile: 192 output byte-rows x 384 cube bytes
+# per sponge (zk-lisp_b200/csrc/tcperm.cuh) = 73 728 MACs, plus 12 cubes (24 128x128-bit products) on the integer pipe.
 PERMS_PER_ROW = 11
-WIDE_MACS_PER_PERM = 27 * (24 + 144) * 16
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full captures under profiles/
-# (r01: k_hash_rows 216.2 MB + 9.0 MB; algorithmic 16*204*65536 = 213.9 MB read + 1 MB written)
-TRAFFIC_HASH_ROWS_BYTES = 225.1e6
+TENSOR_OPS_PER_PERM = 27 * 2 * 192 * 384
+FIELD_PRODUCTS_PER_PERM = 27 * (24 + 144)
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture under profiles/
+# (r01 prof_tc_hash_rows: 214.3 MB + 5.7 MB; algorithmic 16*204*65536 = 213.9 MB read + 1 MB written)
+TRAFFIC_HASH_ROWS_BYTES = 220.0e6
 TRAFFIC_LDE_BYTES = None
 
 
@@ -286,25 +288,31 @@ def main():
         except Exception:
             pass
         hbm_peak, hbm_src = (peaks.get("hbm_gbs"), "measured (MEASURED_PEAKS.json)") if peaks.get("hbm_gbs") else (6650.0, "fallback (B200_PROFILING.md)")
-        imad = C.c_double()
-        workers[0].ctx._check(workers[0].ctx.lib.zkl_imad_peak(workers[0].ctx.h, C.byref(imad)))
         N = ROWS * BLOWUP
         hash_ms, lde_ms = float(excl[10]), float(excl[9])
-        hash_macs = N * PERMS_PER_ROW * WIDE_MACS_PER_PERM
-        lde_bytes = 16 * 204 * ROWS * (1 + BLOWUP)
+        perms = N * PERMS_PER_ROW
+        tensor_ops = perms * TENSOR_OPS_PER_PERM
+        # int8 dense tensor peak = 2 x the bf16 dense peak on B200 (4.5 vs 2.25 PFLOP/s nominal); the bf16 figure is measured
+        bf16_peak = peaks.get("bf16_tflops")
+        int8_peak, int8_src = (2.0 * bf16_peak, "2 x measured cuBLAS bf16 burst (MEASURED_PEAKS.json); int8 dense = 2 x bf16 on sm_100") if bf16_peak \
+            else (2.0 * 1590.0, "2 x fallback bf16 (B200_PROFILING.md)")
         roofline = {
-            "kernel": "k_hash_rows (trace row hashing, 11 permutations per LDE row)",
-            "bound": "int32-multiply pipe (IMAD.WIDE.U32); not hbm/tensor: 4536 field products per 3.3 KB row",
-            "achieved": hash_macs / (hash_ms * 1e-3) / 1e12, "peak": imad.value / 1e12, "unit": "T wide-MAC/s (32x32+64)",
-            "frac": (hash_macs / (hash_ms * 1e-3)) / imad.value, "peak_source": "zkl_imad_peak probe measured in this run",
+            "kernel": "k_tc_hash_rows (trace row hashing: 11 sponge permutations per LDE row, MDS product on tcgen05 kind::i8)",
+            "bound": "tensor",
+            "achieved": tensor_ops / (hash_ms * 1e-3) / 1e12, "peak": int8_peak, "unit": "TOP/s (int8 dense)",
+            "frac": tensor_ops / (hash_ms * 1e-3) / 1e12 / int8_peak, "peak_source": int8_src,
             "traffic": TRAFFIC_HASH_ROWS_BYTES, "ms_per_launch": hash_ms, "ms_per_launch_in_timed_region": float(stage[10]),
+            "permutations_per_s": perms / (hash_ms * 1e-3),
+            "field_products_per_s": perms * FIELD_PRODUCTS_PER_PERM / (hash_ms * 1e-3),
+            "co_bound": "integer issue: the S-box cubes and the accumulator carry propagation stay on the CUDA cores; ncu (profiles/) shows "
+                        "issue slots 49-52 % busy, at the 0.5 warp-instruction/clk/scheduler rate of half-rate 32-bit integer ops, tensor pipe 24-28 % active",
             "timing": "ms_per_launch is taken on an otherwise idle GPU right after the timed region; inside it the kernel shares the SMs with the other streams",
         }
         roofline_lde = {
             "kernel": "k_lde (trace coset LDE, one CTA per column x coset, single pass over HBM)",
             "bound": "hbm", "achieved": lde_bytes / (lde_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
             "frac": lde_bytes / (lde_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src, "traffic": TRAFFIC_LDE_BYTES, "ms_per_launch": lde_ms,
-            "note": "f128: 14 modmuls (~1400 instructions) per 16-byte element written, so the kernel is integer-bound far below the HBM roof",
+            "note": "f128: ~7 modular products (~160 instructions each incl. butterfly adds) per 16-byte element written, so the kernel is integer-issue-bound far below the HBM roof",
         }
         cpu = None
         if not args.no_cpu_baseline and world == 1:
