@@ -291,6 +291,7 @@ def main():
         N = ROWS * BLOWUP
         hash_ms, lde_ms = float(excl[10]), float(excl[9])
         perms = N * PERMS_PER_ROW
+        lde_bytes = 16 * 204 * ROWS * (1 + BLOWUP)
         tensor_ops = perms * TENSOR_OPS_PER_PERM
         # int8 dense tensor peak = 2 x the bf16 dense peak on B200 (4.5 vs 2.25 PFLOP/s nominal); the bf16 figure is measured
         bf16_peak = peaks.get("bf16_tflops")

@@ -30,7 +30,7 @@ def oracle():
 
 
 # Bulk hashing modes every GPU parity test runs under (all three must be bit-identical to the oracle):
-#   default   tensor-core sponge kernels from 4096 sponges up, 16-thread cooperative kernels below
+#   default   tensor-core sponge kernels from 1024 sponges up, 16-thread cooperative kernels below
 #   tc-forced tensor-core kernels for every bulk call site (threshold 1): small test sizes reach tcperm.cuh
 #   int-pipe  the integer-pipe thread-per-sponge kernels for every bulk call site
 HASH_MODES = {"default": (None, 0), "tc-forced": (1, 0), "int-pipe": (1, 1)}

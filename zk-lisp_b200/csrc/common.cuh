@@ -42,7 +42,7 @@ struct zkl_ctx {
   uint64_t launches = 0;
   bool suite_loaded = false;
   // sponge count from which the bulk kernels are used instead of the 16-thread cooperative ones
-  long bulk_threshold = 4096;
+  long bulk_threshold = 1024;
   // bulk hashing path: 0 = tensor-core MDS (tcperm.cuh, the default), 1 = integer-pipe thread-per-sponge kernels
   int hash_path = 0;
   bool tc_ok = true;   // the loaded MDS constants satisfy the tensor-core epilogue's accumulator bound
