@@ -334,6 +334,17 @@ static int dev_eval_constraints(zkl_ctx *ctx, const committed_matrix &t, const z
     }
     coset_consts = it->second;
   }
+  fe *plast;
+  {
+    size_t key = (n << 8) | ce | ((size_t)1 << 59) | ((size_t)t.blowup << 40);
+    auto it = ctx->periodic.find(key);
+    if (it == ctx->periodic.end()) {
+      fe *p; ZKL_CHECK(ctx, cudaMalloc((void **)&p, M * sizeof(fe)));
+      LAUNCH(ctx, k_plast_table, ceil_div(M, 128), 128, 0, tN->wpow, N, (int)n, (int)t.blowup, (int)ce, coset_consts, p);
+      it = ctx->periodic.emplace(key, p).first;
+    }
+    plast = it->second;
+  }
   // boundary polynomials: scatter -> iNTT -> coset LDE over the CE domain
   size_t nb = (size_t)st.nslots + 1;
   ZKL_CHECK(ctx, st.u.alloc(nb * n)); ZKL_CHECK(ctx, st.bpoly.alloc(nb * M));
@@ -343,7 +354,7 @@ static int dev_eval_constraints(zkl_ctx *ctx, const committed_matrix &t, const z
   ZKL_TRY(dev_lde(ctx, st.u.p, st.bpoly.p, nb, n, ce));
   boundary_dev bd{st.slot_col.p, st.bpoly.p, st.nslots};
   LAUNCH(ctx, k_eval_constraints, ceil_div(M, 128), 128, 0, st.air.p, t.lde.p, N, (int)n, (int)t.blowup, (int)ce, per_tab, tN->wpow, cc_dev, bd,
-         coset_consts, ce_out);
+         coset_consts, plast, ce_out);
   return 0;
 }
 
@@ -587,15 +598,20 @@ static int prove_segment_impl(zkl_ctx *ctx, const fe *trace_dev, size_t W, size_
   if (o->grinding > 0) {
     if (o->grinding > 40) { ctx->set_error("grinding factor too large"); return 1; }
     ZKL_CHECK(ctx, cudaMemsetAsync(nonce.p, 0xFF, 8, st));
-    const uint32_t batch = 1u << 15;
     uint64_t base = 1;
     for (;;) {
-      // enough back-to-back batches to cover 16x the expected nonce without a host round trip
-      uint64_t target = (uint64_t)16 << o->grinding;
-      int nb = (int)std::min<uint64_t>(std::max<uint64_t>(target / batch, 1), 512);
-      for (int b = 0; b < nb; b++, base += batch)
-        if (ctx->hash_path == 0) LAUNCH_TC(ctx, k_tc_grind, batch, coin.p, base, batch, o->grinding, nonce.p);
-        else LAUNCH(ctx, k_grind, ceil_div((size_t)batch * ZKL_COOP_GROUP, ZKL_COOP_THREADS), ZKL_COOP_THREADS, 0, coin.p, base, batch, o->grinding, nonce.p);
+      // search window = 16x the expected nonce, without a host round trip
+      uint64_t target = std::min<uint64_t>((uint64_t)16 << o->grinding, (uint64_t)1 << 30);
+      if (ctx->hash_path == 0) {
+        // one persistent launch; CTAs stop at the first tile above the best nonce found so far
+        LAUNCH_TC(ctx, k_tc_grind, target, coin.p, base, (uint32_t)target, o->grinding, nonce.p);
+        base += target;
+      } else {
+        const uint32_t batch = 1u << 15;
+        int nb = (int)std::min<uint64_t>(std::max<uint64_t>(target / batch, 1), 512);
+        for (int b = 0; b < nb; b++, base += batch)
+          LAUNCH(ctx, k_grind, ceil_div((size_t)batch * ZKL_COOP_GROUP, ZKL_COOP_THREADS), ZKL_COOP_THREADS, 0, coin.p, base, batch, o->grinding, nonce.p);
+      }
       ZKL_CHECK(ctx, cudaMemcpyAsync(&nonce_h, nonce.p, 8, cudaMemcpyDeviceToHost, st));
       ZKL_CHECK(ctx, cudaStreamSynchronize(st));
       if (nonce_h != ~0ull) break;

@@ -398,11 +398,23 @@ struct boundary_dev {
   int nslots;
 };
 
+// p_last table (data independent, cached per (n, ce)): plast[k'*n + i] = L_{n-1}(x) = g_last (x^n - 1) / (n (x - g_last)) at the
+// CE point x = g w_N^(k + blowup i) — takes the per-point field inversion out of k_eval_constraints.
+__global__ void k_plast_table(const fe *__restrict__ wpowN, size_t N, int n, int blowup, int ce, const fe *__restrict__ coset_consts, fe *__restrict__ plast) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if ((size_t)t >= (size_t)ce * n) return;
+  int kp = t / n, i = t - kp * n, k = kp * (blowup / ce);
+  fe x = fe_mul(fe_from_u64(3), ld_fe(wpowN + ((size_t)k + (size_t)blowup * i)));
+  fe g_last = ld_fe(wpowN + (N - (size_t)blowup));
+  fe xn1 = ld_fe(coset_consts + 2 * kp + 1), ninv = ld_fe(coset_consts + 2 * ce);
+  st_fe(plast + t, fe_mul(fe_mul(fe_mul(g_last, xn1), ninv), fe_inv(fe_sub(x, g_last))));
+}
+
 // ce_out[k'*n + i] = transition/Z + boundary   (coset-major over the CE domain)
 __global__ void __launch_bounds__(128) k_eval_constraints(const air_dev *__restrict__ air, const fe *__restrict__ lde, size_t N, int n, int blowup,
                                                           int ce, const fe *__restrict__ per, const fe *__restrict__ wpowN,
                                                           const fe *__restrict__ cc, boundary_dev bd, const fe *__restrict__ coset_consts,
-                                                          fe *__restrict__ ce_out) {
+                                                          const fe *__restrict__ plast, fe *__restrict__ ce_out) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   size_t M = (size_t)ce * n;
   if ((size_t)t >= M) return;
@@ -414,10 +426,11 @@ __global__ void __launch_bounds__(128) k_eval_constraints(const air_dev *__restr
   // per-coset constants: [0] = (x^n - 1)^-1, [1] = x^n - 1 ; global: g_n^-1 = w_N^(N - blowup), n^-1
   fe zinv = ld_fe(coset_consts + 2 * kp), xn1 = ld_fe(coset_consts + 2 * kp + 1);
   fe g_last = ld_fe(wpowN + (N - (size_t)blowup));           // g_n^(n-1)
-  fe ninv = ld_fe(coset_consts + 2 * ce), nfe = ld_fe(coset_consts + 2 * ce + 1);
+  fe nfe = ld_fe(coset_consts + 2 * ce + 1);
   fe xm = fe_sub(x, g_last);
-  // p_last(x) = L_{n-1}(x) = g_last * (x^n - 1) / (n * (x - g_last))
-  fe p_last = fe_mul(fe_mul(fe_mul(g_last, xn1), ninv), fe_inv(xm));
+  // p_last(x) = L_{n-1}(x) = g_last * (x^n - 1) / (n * (x - g_last))   (k_plast_table)
+  fe p_last = ld_fe(plast + t);
+  (void)xn1;
   const fe *per31 = per + ((size_t)kp * 32 + (i & 31)) * 31;
   fe tr = eval_transition_combined(air, f, per31, p_last, cc);
   // transition divisor z(x) = (x^n - 1)/(x - g^(n-1))

@@ -54,19 +54,23 @@ __global__ void k_interpolate(const fe *src, fe *dst, int n, int logn, const fe 
   for (int j = threadIdx.x; j < n; j += blockDim.x) st_fe(o + j, fe_mul(sm[bitrev(j, logn)], n_inv));
 }
 
+// coset scaling table: scale[k][j] = (offset * w_N^k)^j = opow[j] * w_N^(j k), k < blowup, j < n (built once per (n, blowup))
+__global__ void k_lde_scale_table(const fe *__restrict__ opow, const fe *__restrict__ wpow, size_t N, int n, int blowup, fe *__restrict__ scale) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t)n * blowup) return;
+  size_t k = t / n, j = t % n;
+  st_fe(scale + t, fe_mul(ld_fe(opow + j), ld_fe(wpow + (j * k) % N)));
+}
+
 // coset LDE: grid = (blowup, ncols). out[c][k][i] = poly_c(offset * w_N^k * w_n^i).
-// opow[j] = offset^j (n entries).
 __global__ void k_lde(const fe *__restrict__ polys, int n, int logn, int blowup, const fe *__restrict__ wpow, size_t N,
-                      const fe *__restrict__ opow, fe *__restrict__ out) {
+                      const fe *__restrict__ scale, fe *__restrict__ out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   fe *sm = reinterpret_cast<fe *>(smem_raw);
   int k = blockIdx.x; size_t c = blockIdx.y;
   const fe *poly = polys + c * n;
-  for (int j = threadIdx.x; j < n; j += blockDim.x) {
-    fe v = fe_mul(ld_fe(poly + j), ld_fe(opow + j));
-    if (k) v = fe_mul(v, ld_fe(wpow + ((size_t)j * k) % N));
-    sm[j] = v;
-  }
+  const fe *sc = scale + (size_t)k * n;
+  for (int j = threadIdx.x; j < n; j += blockDim.x) sm[j] = fe_mul(ld_fe(poly + j), ld_fe(sc + j));
   __syncthreads();
   smem_ntt_dif(sm, n, logn, wpow, N, blowup, false);
   fe *dst = out + c * N + (size_t)k * n;

@@ -160,7 +160,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_fri_leaves(const fe *__res
   tc_teardown(tc_smem);
 }
 // grinding (same contract as k_grind): atomicMin over nonces in [nonce_base, nonce_base + count) whose digest has
-// >= bits trailing zeros in its first 8 little-endian bytes (agg/fs.rs:202-207)
+// >= bits trailing zeros in its first 8 little-endian bytes (agg/fs.rs:202-207). ONE launch covers the whole search
+// window: a CTA walks its tiles in increasing nonce order and stops at the first tile that starts above the best
+// nonce found so far, so at most one wave of tiles is wasted. The stop decision is data dependent, so one thread per
+// set takes it and broadcasts it through shared memory to the set's compute warps AND its MMA warp (named barrier).
 __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_grind(const fe *__restrict__ seed, uint64_t nonce_base, uint32_t count, uint32_t bits,
                                                             unsigned long long *result) {
   if (*(volatile unsigned long long *)result < nonce_base) return;
@@ -168,8 +171,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_grind(const fe *__restrict
   tc_ctx c = tc_setup(tc_smem);
   const fe sd = ld_fe(seed);
   size_t tiles = ((size_t)count + TC_CTA_SPONGES - 1) / TC_CTA_SPONGES;
-  if (c.is_mma) tc_mma_loop(c, tc_my_tiles(tiles) * ZKL_ROUNDS);
-  else for (size_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+  const bool decider = !c.is_mma && c.half == 0 && c.sponge == 0;
+  int it = 0;
+  for (size_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, it ^= 1) {
+    if (decider) c.flags[it] = *(volatile unsigned long long *)result < nonce_base + tile * TC_CTA_SPONGES ? 1u : 0u;
+    named_bar_sync(1 + c.set, TC_SET_THREADS + 32);
+    if (c.flags[it]) break;
+    if (c.is_mma) { tc_mma_loop(c, ZKL_ROUNDS); continue; }
     size_t g = tc_index(c, tile);
     uint64_t nonce = nonce_base + (g < count ? g : count - 1);
     mwi_src src{sd, nonce};

@@ -161,6 +161,7 @@ struct tc_ctx {
   uint32_t full;      // shared address of full[0] of the set
   uint32_t dready;    // shared address of the set's accumulator-ready barrier
   uint32_t phase;     // phase parity of the current round (all barriers of a set flip once per round)
+  volatile uint32_t *flags;   // generic pointer to the set's two control words (tile-level decisions broadcast to the MMA warp)
   int set, half, sponge;
   bool is_mma;        // MMA-issuing warp (no sponge)
 };
@@ -209,6 +210,7 @@ __device__ __forceinline__ tc_ctx tc_setup(unsigned char *smem_raw) {
   c.full = ctl + 64 * c.set;
   c.dready = c.full + 48;
   c.phase = 0;
+  c.flags = ctl_gen + 48 + 2 * c.set;
   return c;
 }
 // CTA epilogue (all threads)
@@ -226,11 +228,11 @@ __device__ __forceinline__ void tc_teardown(unsigned char *smem_raw) {
 // MMA warp: `rounds` = 27 x (number of permutations the set's compute warps will run in this kernel). Per round the
 // MMAs of lanes j, TC_LPT + j, ... (one MMA = one lane = 32 cube bytes of K) are issued as soon as all compute warps
 // have published those cubes, so only the last group is exposed latency; the commit after the last group signals dready.
-__device__ __forceinline__ void tc_mma_loop(const tc_ctx &c, uint64_t rounds) {
+__device__ __forceinline__ void tc_mma_loop(tc_ctx &c, uint64_t rounds) {
   const uint64_t adesc = tc_smem_desc(c.a_tile, TC_SPONGES * 16, 128);
   const uint64_t bdesc = tc_smem_desc(c.b_tile, TC_N * 16, 128);
   const bool leader = (threadIdx.x & 31) == 0;
-  uint32_t phase = 0;
+  uint32_t phase = c.phase;
 #pragma unroll 1
   for (uint64_t r = 0; r < rounds; r++) {
 #pragma unroll
@@ -252,6 +254,7 @@ __device__ __forceinline__ void tc_mma_loop(const tc_ctx &c, uint64_t rounds) {
     }
     phase ^= 1;
   }
+  c.phase = phase;
 }
 
 // The permutation, compute side. Called by all compute threads of a set together; st[j] = lazy lane TC_LPT*half + j.

@@ -194,9 +194,17 @@ static int dev_lde(zkl_ctx *ctx, const fe *polys, fe *out, size_t ncols, size_t 
   if (n > 8192 || (n & (n - 1)) || n < 2) { ctx->set_error("trace length must be a power of two in [2, 8192]"); return 1; }
   size_t N = n * blowup;
   domain_tables *t; ZKL_TRY(get_tables(ctx, N, &t));
-  fe *opow; ZKL_TRY(get_offset_powers(ctx, n, &opow));
+  // scale[k][j] = (GENERATOR * w_N^k)^j, cached per (n, blowup)
+  const size_t key = n | (blowup << 32) | ((size_t)1 << 61);
+  auto it = ctx->opow.find(key);
+  if (it == ctx->opow.end()) {
+    fe *opow; ZKL_TRY(get_offset_powers(ctx, n, &opow));
+    fe *p; ZKL_CHECK(ctx, cudaMalloc((void **)&p, N * sizeof(fe)));
+    LAUNCH(ctx, k_lde_scale_table, ceil_div(N, 256), 256, 0, opow, t->wpow, N, (int)n, (int)blowup, p);
+    it = ctx->opow.emplace(key, p).first;
+  }
   dim3 grid((unsigned)blowup, (unsigned)ncols);
-  LAUNCH(ctx, k_lde, grid, NTT_THREADS, n * sizeof(fe), polys, (int)n, ilog2_sz(n), (int)blowup, t->wpow, N, opow, out);
+  LAUNCH(ctx, k_lde, grid, NTT_THREADS, n * sizeof(fe), polys, (int)n, ilog2_sz(n), (int)blowup, t->wpow, N, it->second, out);
   return 0;
 }
 // leaves[r] for the coset-major matrix `lde` (ncols x N); partition size per PartitionOptions
