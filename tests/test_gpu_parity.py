@@ -221,3 +221,48 @@ def test_full_size_segment_properties(ctx, zkl):
     prover.prove(bad)
     assert prover.last_summary.stage_ms[11] == -1.0
     assert leaves.shape == (len(pos), 32)
+
+
+@pytest.mark.parametrize("n,blowup", [(16384, 4), (32768, 2), (65536, 2)])
+def test_two_pass_ntt_above_8192_rows(ctx, oracle, n, blowup):
+    """n > 8192: the column no longer fits one CTA's shared memory; the two-pass (four-step) transforms must agree
+    with the oracle's plain radix-2 FFT, and interpolate(evaluate) must be the identity."""
+    if ctx.hash_mode != "default":
+        pytest.skip("NTT test, independent of the hashing mode")
+    cols = fast_random_trace(2, n, seed=n)
+    polys = ctx.interpolate_columns(cols)
+    assert np.array_equal(polys, oracle.interpolate_columns(cols))
+    ev = ctx.evaluate_columns(polys, blowup)
+    assert np.array_equal(ev, oracle.evaluate_columns(polys, blowup))
+    # coset 0 of an offset-free evaluation is not available through the ABI (offset = GENERATOR), so close the loop
+    # with linearity instead: LDE(a + b) = LDE(a) + LDE(b)
+    s = to_fe([(x + y) % P for x, y in zip(from_fe(polys[0]), from_fe(polys[1]))]).reshape(1, n, 2)
+    es = from_fe(ctx.evaluate_columns(s, blowup)[0])
+    e0, e1 = from_fe(ev[0]), from_fe(ev[1])
+    assert es == [(x + y) % P for x, y in zip(e0, e1)]
+
+
+def test_large_segment_commit_and_proof(ctx, zkl, oracle):
+    """A 16384-row segment (4x the reference's segment cap): trace commitment of a narrow trace is
+    bit-identical to the oracle's, and the full proof of a wide AIR-valid trace is accepted by the restated verifier."""
+    if ctx.hash_mode != "default":
+        pytest.skip("size test, default hashing mode only")
+    n = 16384
+    trace = fast_random_trace(6, n, seed=77)
+    opts = zkl.air.ProofOptions(num_queries=8, blowup=16, grinding=0, num_partitions=1, hash_rate=16)
+    prover = zkl.ZkProver(ctx, opts, None)
+    lde, polys = prover.new_trace_lde(trace)
+    root, opolys, _ = oracle.trace_lde_commit(trace, opts.to_c(), want_lde=False)
+    assert np.array_equal(polys, opolys)
+    assert lde.get_main_trace_commitment() == root
+    lde.free()
+    trace, air_pi, opts = synth.valid_segment(n=n, queries=32, blowup=16, grind=8, seed=3)
+    a, ac, oc, seed = _air(zkl, trace, air_pi, opts)
+    prover = zkl.ZkProver(ctx, opts, air_pi)
+    proof = prover.prove(trace)
+    assert prover.last_summary.stage_ms[11] == 0.0
+    rc, msg = oracle.verify_segment(proof, trace.shape[0], n, ac, seed, oc)
+    assert rc == 0, msg
+    tampered = bytearray(proof); tampered[len(proof) // 2] ^= 1
+    rc, _ = oracle.verify_segment(bytes(tampered), trace.shape[0], n, ac, seed, oc)
+    assert rc != 0

@@ -31,7 +31,7 @@ static int commit_matrix(zkl_ctx *ctx, committed_matrix &m, const zkl_options *o
 static int check_opts(zkl_ctx *ctx, const zkl_options *o, size_t n) {
   if (o->fri_folding != 2) { ctx->set_error("only FRI folding factor 2 is supported (prove.rs:968)"); return 1; }
   if (o->blowup < 2 || (o->blowup & (o->blowup - 1)) || o->blowup > 128) { ctx->set_error("blowup must be a power of two in [2,128]"); return 1; }
-  if (n < 8 || n > 8192 || (n & (n - 1))) { ctx->set_error("trace length must be a power of two in [8, 8192]"); return 1; }
+  if (n < 8 || n > NTT_MAX || (n & (n - 1))) { ctx->set_error("trace length must be a power of two in [8, 2^24]"); return 1; }
   return 0;
 }
 

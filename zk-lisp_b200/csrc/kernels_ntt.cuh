@@ -85,3 +85,82 @@ __global__ void k_coset_to_natural(const fe *__restrict__ cm, fe *__restrict__ n
   size_t r = (s / n) + (size_t)blowup * (s % n);
   st_fe(nat + c * N + r, ld_fe(cm + t));
 }
+
+// ================================================================= n > 8192: two-pass (four-step) transforms
+// A column no longer fits one CTA's shared memory, so n = n1 * n2 and with j = j1 + n1 j2, i = n2 i1 + i2:
+//   y[n2 i1 + i2] = sum_j1 w_n1^(i1 j1) * ( w_n^(i2 j1) * sum_j2 x[j1 + n1 j2] w_n2^(i2 j2) )
+// pass 1: T consecutive j1 per CTA, T size-n2 transforms in shared memory, twiddle, B[j1][i2] (unit stride in i2)
+// pass 2: T consecutive i2 per CTA, T size-n1 transforms, y[n2 i1 + i2] — the same address set the CTA read, so
+//         pass 2 runs IN PLACE on B. Every global access moves T*16-byte contiguous pieces (T >= 4: full sectors).
+// Two passes over HBM instead of one; used only above 8192 rows (larger segments).
+// `sign`: forward transforms use w, inverse ones w^-1 (exponent e -> Ntab - e). wtab has Ntab = n * tstride entries.
+
+// T independent DIF transforms of length m over sm[t * m + .]; natural in, bit-reversed out
+__device__ __forceinline__ void smem_ntt_dif_batch(fe *sm, int T, int m, int logm, const fe *__restrict__ wtab, size_t Ntab, size_t stride_m,
+                                                   bool inverse) {
+  const int per = m / 2;
+  for (int s = 0; s < logm; s++) {
+    int half = m >> (s + 1);
+    for (int q = threadIdx.x; q < T * per; q += blockDim.x) {
+      int t = q / per, b = q - t * per;
+      int blk = b / half, j = b - blk * half;
+      fe *row = sm + (size_t)t * m;
+      int i0 = blk * 2 * half + j, i1 = i0 + half;
+      fe a = row[i0], c = row[i1];
+      size_t e = (size_t)j * ((size_t)m / (2 * half)) * stride_m;
+      if (inverse && e) e = Ntab - e;
+      row[i0] = fe_add(a, c);
+      row[i1] = fe_mul(fe_sub(a, c), ld_fe(wtab + e));
+    }
+    __syncthreads();
+  }
+}
+// pass 1. grid = (n1 / T, ncols, cosets). src column c: src + c*n (natural order). scale (optional): scale + z*n, multiplied in.
+// dst slab (c, z): dst + (c * cosets + z) * n, written as B[j1][i2].
+__global__ void k_ntt_pass1(const fe *__restrict__ src, fe *__restrict__ dst, int n1, int n2, int logn2, int T, const fe *__restrict__ wtab, size_t Ntab,
+                            const fe *__restrict__ scale, bool inverse) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  fe *sm = reinterpret_cast<fe *>(smem_raw);
+  const size_t n = (size_t)n1 * n2;
+  const int j1_0 = blockIdx.x * T; const size_t c = blockIdx.y, z = blockIdx.z, cosets = gridDim.z;
+  const fe *col = src + c * n;
+  const fe *sc = scale ? scale + z * n : nullptr;
+  for (int q = threadIdx.x; q < T * n2; q += blockDim.x) {
+    int t = q % T, j2 = q / T;
+    size_t j = (size_t)(j1_0 + t) + (size_t)n1 * j2;
+    fe v = ld_fe(col + j);
+    if (sc) v = fe_mul(v, ld_fe(sc + j));
+    sm[(size_t)t * n2 + j2] = v;
+  }
+  __syncthreads();
+  smem_ntt_dif_batch(sm, T, n2, logn2, wtab, Ntab, Ntab / n2, inverse);
+  fe *out = dst + (c * cosets + z) * n;
+  const size_t stride_n = Ntab / n;
+  for (int q = threadIdx.x; q < T * n2; q += blockDim.x) {
+    int t = q / n2, i2 = q - t * n2;
+    size_t e = ((size_t)i2 * (size_t)(j1_0 + t) * stride_n) % Ntab;
+    if (inverse && e) e = Ntab - e;
+    st_fe(out + (size_t)(j1_0 + t) * n2 + i2, fe_mul(sm[(size_t)t * n2 + bitrev(i2, logn2)], ld_fe(wtab + e)));
+  }
+}
+// pass 2, in place. grid = (n2 / T, nslabs). slab s: buf + s*n. Optional final factor (1/n for inverse transforms).
+__global__ void k_ntt_pass2(fe *__restrict__ buf, int n1, int n2, int logn1, int T, const fe *__restrict__ wtab, size_t Ntab, bool inverse,
+                            bool has_factor, fe factor) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  fe *sm = reinterpret_cast<fe *>(smem_raw);
+  const size_t n = (size_t)n1 * n2;
+  const int i2_0 = blockIdx.x * T;
+  fe *slab = buf + (size_t)blockIdx.y * n;
+  for (int q = threadIdx.x; q < T * n1; q += blockDim.x) {
+    int t = q % T, j1 = q / T;
+    sm[(size_t)t * n1 + j1] = ld_fe(slab + (size_t)j1 * n2 + i2_0 + t);
+  }
+  __syncthreads();
+  smem_ntt_dif_batch(sm, T, n1, logn1, wtab, Ntab, Ntab / n1, inverse);
+  for (int q = threadIdx.x; q < T * n1; q += blockDim.x) {
+    int t = q % T, i1 = q / T;
+    fe v = sm[(size_t)t * n1 + bitrev(i1, logn1)];
+    if (has_factor) v = fe_mul(v, factor);
+    st_fe(slab + (size_t)i1 * n2 + i2_0 + t, v);
+  }
+}

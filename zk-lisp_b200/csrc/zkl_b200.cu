@@ -70,6 +70,8 @@ extern "C" int zkl_ctx_create(int device, zkl_ctx **out) {
   // opt in to large dynamic shared memory for the single-pass column transforms
   cudaFuncSetAttribute(k_interpolate, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
   cudaFuncSetAttribute(k_lde, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+  cudaFuncSetAttribute(k_ntt_pass1, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+  cudaFuncSetAttribute(k_ntt_pass2, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
   cudaFuncSetAttribute(k_tc_permute_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
   cudaFuncSetAttribute(k_tc_hash_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
   cudaFuncSetAttribute(k_tc_merge_many_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
@@ -181,17 +183,38 @@ static int get_offset_powers(zkl_ctx *ctx, size_t n, fe **out) {
 // ------------------------------------------------------------------------------------------------
 static const int NTT_THREADS = 512;
 
+// split of a large transform: n = n1 * n2, T columns per CTA (T * max(n1, n2) elements = 128 KB of shared memory)
+struct ntt_split { int n1, n2, T; };
+static ntt_split split_for(size_t n) {
+  int logn = ilog2_sz(n);
+  ntt_split s; s.n2 = 1 << ((logn + 1) / 2); s.n1 = (int)(n / s.n2);
+  s.T = std::min(8192 / std::max(s.n1, s.n2), std::min(s.n1, s.n2));
+  return s;
+}
+static const size_t NTT_SINGLE_PASS_MAX = 8192, NTT_MAX = (size_t)1 << 24;
+
 // cols (ncols x n, evaluations over <w_n>) -> coefficients, in place or out of place
 static int dev_interpolate(zkl_ctx *ctx, const fe *src, fe *dst, size_t ncols, size_t n) {
-  if (n > 8192 || (n & (n - 1)) || n < 2) { ctx->set_error("trace length must be a power of two in [2, 8192] (single-pass shared-memory NTT)"); return 1; }
+  if (n > NTT_MAX || (n & (n - 1)) || n < 2) { ctx->set_error("trace length must be a power of two in [2, 2^24]"); return 1; }
   domain_tables *t; ZKL_TRY(get_tables(ctx, n, &t));
   fe n_inv = fe_inv(fe_from_u64(n));
-  LAUNCH(ctx, k_interpolate, (unsigned)ncols, NTT_THREADS, n * sizeof(fe), src, dst, (int)n, ilog2_sz(n), t->wpow, n, n_inv);
+  if (n <= NTT_SINGLE_PASS_MAX) {
+    LAUNCH(ctx, k_interpolate, (unsigned)ncols, NTT_THREADS, n * sizeof(fe), src, dst, (int)n, ilog2_sz(n), t->wpow, n, n_inv);
+    return 0;
+  }
+  // two passes over HBM (kernels_ntt.cuh); pass 1 goes through a scratch buffer when the call is in place
+  ntt_split sp = split_for(n);
+  dev_buf<fe> tmp; fe *mid = dst;
+  if (src == dst) { ZKL_CHECK(ctx, tmp.alloc(ncols * n)); mid = tmp.p; }
+  size_t smem = (size_t)sp.T * std::max(sp.n1, sp.n2) * sizeof(fe);
+  LAUNCH(ctx, k_ntt_pass1, dim3(sp.n1 / sp.T, (unsigned)ncols, 1), NTT_THREADS, smem, src, mid, sp.n1, sp.n2, ilog2_sz(sp.n2), sp.T, t->wpow, n, (const fe *)nullptr, true);
+  LAUNCH(ctx, k_ntt_pass2, dim3(sp.n2 / sp.T, (unsigned)ncols), NTT_THREADS, smem, mid, sp.n1, sp.n2, ilog2_sz(sp.n1), sp.T, t->wpow, n, true, true, n_inv);
+  if (mid != dst) ZKL_CHECK(ctx, cudaMemcpyAsync(dst, mid, ncols * n * sizeof(fe), cudaMemcpyDeviceToDevice, ctx->stream));
   return 0;
 }
 // polys (ncols x n) -> coset-major LDE (ncols x blowup x n) over GENERATOR * <w_N>
 static int dev_lde(zkl_ctx *ctx, const fe *polys, fe *out, size_t ncols, size_t n, size_t blowup) {
-  if (n > 8192 || (n & (n - 1)) || n < 2) { ctx->set_error("trace length must be a power of two in [2, 8192]"); return 1; }
+  if (n > NTT_MAX || (n & (n - 1)) || n < 2) { ctx->set_error("trace length must be a power of two in [2, 2^24]"); return 1; }
   size_t N = n * blowup;
   domain_tables *t; ZKL_TRY(get_tables(ctx, N, &t));
   // scale[k][j] = (GENERATOR * w_N^k)^j, cached per (n, blowup)
@@ -203,8 +226,15 @@ static int dev_lde(zkl_ctx *ctx, const fe *polys, fe *out, size_t ncols, size_t 
     LAUNCH(ctx, k_lde_scale_table, ceil_div(N, 256), 256, 0, opow, t->wpow, N, (int)n, (int)blowup, p);
     it = ctx->opow.emplace(key, p).first;
   }
-  dim3 grid((unsigned)blowup, (unsigned)ncols);
-  LAUNCH(ctx, k_lde, grid, NTT_THREADS, n * sizeof(fe), polys, (int)n, ilog2_sz(n), (int)blowup, t->wpow, N, it->second, out);
+  if (n <= NTT_SINGLE_PASS_MAX) {
+    dim3 grid((unsigned)blowup, (unsigned)ncols);
+    LAUNCH(ctx, k_lde, grid, NTT_THREADS, n * sizeof(fe), polys, (int)n, ilog2_sz(n), (int)blowup, t->wpow, N, it->second, out);
+    return 0;
+  }
+  ntt_split sp = split_for(n);
+  size_t smem = (size_t)sp.T * std::max(sp.n1, sp.n2) * sizeof(fe);
+  LAUNCH(ctx, k_ntt_pass1, dim3(sp.n1 / sp.T, (unsigned)ncols, (unsigned)blowup), NTT_THREADS, smem, polys, out, sp.n1, sp.n2, ilog2_sz(sp.n2), sp.T, t->wpow, N, it->second, false);
+  LAUNCH(ctx, k_ntt_pass2, dim3(sp.n2 / sp.T, (unsigned)(ncols * blowup)), NTT_THREADS, smem, out, sp.n1, sp.n2, ilog2_sz(sp.n1), sp.T, t->wpow, N, false, false, fe_zero());
   return 0;
 }
 // leaves[r] for the coset-major matrix `lde` (ncols x N); partition size per PartitionOptions
