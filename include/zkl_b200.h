@@ -233,6 +233,28 @@ int zkl_usage_mask_dev(zkl_ctx *ctx, const void *trace_dev, size_t width, size_t
 int zkl_read_cells_dev(zkl_ctx *ctx, const void *trace_dev, size_t n, const uint32_t *cols, const uint32_t *rows,
                        size_t k, zkl_fe *out);
 
+/* ---- column-sharded trace commitment: device-pointer building blocks (single huge segment) ----
+ * The reference hashes a row as merge_many(hash_elements(partition_k)) when PartitionOptions asks for several
+ * partitions (agg/child.rs:1025-1045). A rank that owns whole partitions therefore runs iNTT, LDE and partition
+ * hashing locally; the ranks exchange one 16-byte digest per (row, partition) (NCCL all-gather in
+ * zk-lisp_b200/sharded.py), then merge_many + MerkleTree::new. Elements are 16 bytes (zkl_fe layout); a digest
+ * is carried as ONE element (its upper 16 bytes are zero, utils.rs:375-381). Calls enqueue on the ctx stream. */
+size_t zkl_partition_size(const zkl_options *opts, size_t width);   /* PartitionOptions::partition_size */
+/* cols_dev: ncols x n evaluations (column-major) -> out_polys_dev (ncols x n) and the coset-major LDE
+ * out_lde_dev[c][k][i] = T_c(GENERATOR w_N^(k + blowup i)) (ncols x n*blowup) */
+int zkl_lde_dev(zkl_ctx *ctx, const void *cols_dev, size_t ncols, size_t n, size_t blowup,
+                void *out_polys_dev, void *out_lde_dev);
+/* out_digests_dev[q*N + r] = hash_elements(LDE row r, local columns [q*psize, min(ncols,(q+1)*psize))), natural r */
+int zkl_hash_partitions_dev(zkl_ctx *ctx, const void *lde_dev, size_t ncols, size_t n, size_t blowup,
+                            size_t partition_size, void *out_digests_dev);
+/* out_leaves_dev[r] = merge_many(digests[0][first_row + r], ..., digests[nparts-1][first_row + r]), r < rows;
+ * digests[q] starts at digests_dev + q*row_stride elements */
+int zkl_merge_partition_digests_dev(zkl_ctx *ctx, const void *digests_dev, size_t nparts, size_t row_stride,
+                                    size_t first_row, size_t rows, void *out_leaves_dev);
+/* MerkleTree::new on the device: out_nodes_dev[1] = root, out_nodes_dev[count/2 .. count) = parents of the leaves */
+int zkl_merkle_dev(zkl_ctx *ctx, const void *leaves_dev, size_t count, void *out_nodes_dev);
+int zkl_dev_download(zkl_ctx *ctx, void *host, const void *dev, size_t bytes);
+
 /* ---- measurement helpers (bench.py) -------------------------------------------------------- */
 int zkl_timer_start(zkl_ctx *ctx);             /* CUDA event on the ctx stream */
 int zkl_timer_stop(zkl_ctx *ctx, float *ms);   /* second event, synchronised; elapsed device time */

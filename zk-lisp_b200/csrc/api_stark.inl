@@ -771,6 +771,43 @@ extern "C" int zkl_dev_upload(zkl_ctx *ctx, void *dev, const void *host, size_t 
   ZKL_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
   return 0;
 }
+extern "C" int zkl_dev_download(zkl_ctx *ctx, void *host, const void *dev, size_t bytes) {
+  ZKL_CHECK(ctx, cudaSetDevice(ctx->device));
+  ZKL_CHECK(ctx, cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  ZKL_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// column-sharded trace commitment (SURVEY.md §8e "single huge segment"): building blocks on device pointers.
+// A rank owns whole column partitions (agg/child.rs:1031-1044: leaf = merge_many(hash_elements(partition_k))), so
+// iNTT, LDE and partition hashing are local; what crosses NVLink is one 16-byte digest per (row, partition).
+// All calls are stream-ordered on the context's stream and return after enqueueing (zkl_sync to wait).
+// ------------------------------------------------------------------------------------------------
+extern "C" int zkl_lde_dev(zkl_ctx *ctx, const void *cols_dev, size_t ncols, size_t n, size_t blowup, void *out_polys_dev, void *out_lde_dev) {
+  ZKL_TRY(enter(ctx));
+  ZKL_TRY(dev_interpolate(ctx, (const fe *)cols_dev, (fe *)out_polys_dev, ncols, n));
+  return dev_lde(ctx, (const fe *)out_polys_dev, (fe *)out_lde_dev, ncols, n, blowup);
+}
+extern "C" int zkl_hash_partitions_dev(zkl_ctx *ctx, const void *lde_dev, size_t ncols, size_t n, size_t blowup, size_t partition_size,
+                                       void *out_digests_dev) {
+  ZKL_TRY(need_suite(ctx));
+  if (partition_size == 0 || ncols == 0) { ctx->set_error("empty partition"); return 1; }
+  return dev_hash_partitions(ctx, (const fe *)lde_dev, ncols, n, blowup, partition_size, (fe *)out_digests_dev);
+}
+extern "C" int zkl_merge_partition_digests_dev(zkl_ctx *ctx, const void *digests_dev, size_t nparts, size_t row_stride, size_t first_row,
+                                               size_t rows, void *out_leaves_dev) {
+  ZKL_TRY(need_suite(ctx));
+  if (nparts < 2) { ctx->set_error("merge_many leaves need at least two partitions (a single partition digest IS the leaf)"); return 1; }
+  return dev_merge_partitions(ctx, (const fe *)digests_dev + first_row, row_stride, rows, nparts, (fe *)out_leaves_dev);
+}
+extern "C" int zkl_merkle_dev(zkl_ctx *ctx, const void *leaves_dev, size_t count, void *out_nodes_dev) {
+  ZKL_TRY(need_suite(ctx));
+  ZKL_CHECK(ctx, cudaMemsetAsync(out_nodes_dev, 0, sizeof(fe), ctx->stream));
+  return dev_merkle(ctx, (const fe *)leaves_dev, (fe *)out_nodes_dev, count);
+}
+extern "C" size_t zkl_partition_size(const zkl_options *opts, size_t width) { return partition_size_of(opts, width); }
+
 extern "C" int zkl_sync(zkl_ctx *ctx) { ZKL_CHECK(ctx, cudaSetDevice(ctx->device)); ZKL_CHECK(ctx, cudaStreamSynchronize(ctx->stream)); return 0; }
 
 // ------------------------------------------------------------------------------------------------

@@ -100,10 +100,11 @@ __global__ void __launch_bounds__(ZKL_HASH_THREADS) k_hash_rows(const fe *__rest
   st_fe(out + (size_t)q * N + r, d);
 }
 // leaf = merge_many(partition digests) (agg/child.rs:1040-1044)
-__global__ void __launch_bounds__(ZKL_HASH_THREADS) k_merge_many_rows(const fe *__restrict__ parts, size_t N, int nchunks, fe *__restrict__ out) {
+// parts[q * stride + r], r < rows
+__global__ void __launch_bounds__(ZKL_HASH_THREADS) k_merge_many_rows(const fe *__restrict__ parts, size_t stride, size_t rows, int nchunks, fe *__restrict__ out) {
   size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= N) return;
-  st_fe(out + r, merge_many_dev(parts + r, N, nchunks));
+  if (r >= rows) return;
+  st_fe(out + r, merge_many_dev(parts + r, stride, nchunks));
 }
 // one Merkle level: out[i] = merge(in[2i], in[2i+1]), i < count
 __global__ void __launch_bounds__(ZKL_HASH_THREADS) k_merkle_level(const fe *__restrict__ in, fe *__restrict__ out, size_t count) {
@@ -221,10 +222,10 @@ __global__ void __launch_bounds__(ZKL_COOP_THREADS) k_coop_hash_rows(const fe *_
   fe d = coop_hash_elements(lde + (size_t)first * N + s, N, len);
   if (g < total && (threadIdx.x & (ZKL_COOP_GROUP - 1)) == 0) st_fe(out + (size_t)q * N + r, d);
 }
-__global__ void __launch_bounds__(ZKL_COOP_THREADS) k_coop_merge_many_rows(const fe *__restrict__ parts, size_t N, int nchunks, fe *__restrict__ out) {
+__global__ void __launch_bounds__(ZKL_COOP_THREADS) k_coop_merge_many_rows(const fe *__restrict__ parts, size_t stride, size_t rows, int nchunks, fe *__restrict__ out) {
   size_t g = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) / ZKL_COOP_GROUP;
-  size_t r = g < N ? g : N - 1;
-  many_src s{parts + r, N};
+  size_t r = g < rows ? g : rows - 1;
+  many_src s{parts + r, stride};
   fe d = coop_sponge_run(s, 1 + nchunks);
-  if (g < N && (threadIdx.x & (ZKL_COOP_GROUP - 1)) == 0) st_fe(out + r, d);
+  if (g < rows && (threadIdx.x & (ZKL_COOP_GROUP - 1)) == 0) st_fe(out + r, d);
 }

@@ -88,14 +88,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_hash_rows(const fe *__rest
   tc_teardown(tc_smem);
 }
 // leaf = merge_many(partition digests)
-__global__ void __launch_bounds__(TC_THREADS, 1) k_tc_merge_many_rows(const fe *__restrict__ parts, size_t N, int nchunks, fe *__restrict__ out) {
+__global__ void __launch_bounds__(TC_THREADS, 1) k_tc_merge_many_rows(const fe *__restrict__ parts, size_t stride, size_t N, int nchunks, fe *__restrict__ out) {
   extern __shared__ unsigned char tc_smem[];
   tc_ctx c = tc_setup(tc_smem);
   size_t tiles = (N + TC_CTA_SPONGES - 1) / TC_CTA_SPONGES;
   if (c.is_mma) tc_mma_loop(c, tc_my_tiles(tiles) * tc_perms(1 + nchunks) * ZKL_ROUNDS);
   else for (size_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     size_t r = tc_index(c, tile), rc = r < N ? r : N - 1;
-    many_src src{parts + rc, N};
+    many_src src{parts + rc, stride};
     fe d = tc_sponge_run(src, 1 + nchunks, c);
     if (r < N && c.half == 0) st_fe(out + r, d);
   }

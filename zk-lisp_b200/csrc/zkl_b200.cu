@@ -243,24 +243,32 @@ static size_t partition_size_of(const zkl_options *o, size_t cols) {  // [WF-mem
   size_t ps = (cols + o->num_partitions - 1) / o->num_partitions;
   return std::max<size_t>(ps, o->hash_rate);
 }
+// partition digests of a coset-major matrix: out[q * N + r] = hash_elements(row r, columns [q*ps, min(ncols, (q+1)*ps)))
+static int dev_hash_partitions(zkl_ctx *ctx, const fe *lde, size_t ncols, size_t n, size_t blowup, size_t ps, fe *out) {
+  size_t N = n * blowup, nchunks = (ncols + ps - 1) / ps;
+  // bulk (tensor-core or thread-per-sponge) kernel when the sponges fill SMs, the 16-thread cooperative one otherwise
+  size_t sponges = N * nchunks;
+  bool bulk = sponges >= (size_t)ctx->bulk_threshold;
+  if (bulk && ctx->hash_path == 0) LAUNCH_TC(ctx, k_tc_hash_rows, sponges, lde, N, n, (int)blowup, (int)ncols, (int)ps, (int)nchunks, out);
+  else if (bulk) LAUNCH(ctx, k_hash_rows, ceil_div(sponges, ZKL_HASH_THREADS), ZKL_HASH_THREADS, 0, lde, N, n, (int)blowup, (int)ncols, (int)ps, (int)nchunks, out);
+  else LAUNCH(ctx, k_coop_hash_rows, ceil_div(sponges * ZKL_COOP_GROUP, ZKL_COOP_THREADS), ZKL_COOP_THREADS, 0, lde, N, n, (int)blowup, (int)ncols, (int)ps, (int)nchunks, out);
+  return 0;
+}
+// leaves[r] = merge_many(parts[0][r0 + r], ..., parts[nchunks-1][r0 + r]), r < rows (agg/child.rs:1040-1044); parts[q] at parts + q*stride
+static int dev_merge_partitions(zkl_ctx *ctx, const fe *parts, size_t stride, size_t rows, size_t nchunks, fe *leaves) {
+  if (rows >= (size_t)ctx->bulk_threshold && ctx->hash_path == 0) LAUNCH_TC(ctx, k_tc_merge_many_rows, rows, parts, stride, rows, (int)nchunks, leaves);
+  else if (rows >= (size_t)ctx->bulk_threshold) LAUNCH(ctx, k_merge_many_rows, ceil_div(rows, ZKL_HASH_THREADS), ZKL_HASH_THREADS, 0, parts, stride, rows, (int)nchunks, leaves);
+  else LAUNCH(ctx, k_coop_merge_many_rows, ceil_div(rows * ZKL_COOP_GROUP, ZKL_COOP_THREADS), ZKL_COOP_THREADS, 0, parts, stride, rows, (int)nchunks, leaves);
+  return 0;
+}
 static int dev_hash_rows(zkl_ctx *ctx, const fe *lde, size_t ncols, size_t n, size_t blowup, const zkl_options *o, fe *leaves,
                          dev_buf<fe> &scratch) {
   size_t N = n * blowup, ps = partition_size_of(o, ncols);
   size_t nchunks = (ncols + ps - 1) / ps;
-  // thread-per-sponge kernel when the sponges alone fill the GPU, the 16-thread cooperative one otherwise
-  size_t sponges = N * nchunks;
-  bool bulk = sponges >= (size_t)ctx->bulk_threshold;
-  fe *dst = nchunks == 1 ? leaves : nullptr;
-  if (nchunks > 1) { ZKL_CHECK(ctx, scratch.alloc(N * nchunks)); dst = scratch.p; }
-  if (bulk && ctx->hash_path == 0) LAUNCH_TC(ctx, k_tc_hash_rows, sponges, lde, N, n, (int)blowup, (int)ncols, (int)ps, (int)nchunks, dst);
-  else if (bulk) LAUNCH(ctx, k_hash_rows, ceil_div(sponges, ZKL_HASH_THREADS), ZKL_HASH_THREADS, 0, lde, N, n, (int)blowup, (int)ncols, (int)ps, (int)nchunks, dst);
-  else LAUNCH(ctx, k_coop_hash_rows, ceil_div(sponges * ZKL_COOP_GROUP, ZKL_COOP_THREADS), ZKL_COOP_THREADS, 0, lde, N, n, (int)blowup, (int)ncols, (int)ps, (int)nchunks, dst);
-  if (nchunks > 1) {
-    if (N >= (size_t)ctx->bulk_threshold && ctx->hash_path == 0) LAUNCH_TC(ctx, k_tc_merge_many_rows, N, scratch.p, N, (int)nchunks, leaves);
-    else if (N >= (size_t)ctx->bulk_threshold) LAUNCH(ctx, k_merge_many_rows, ceil_div(N, ZKL_HASH_THREADS), ZKL_HASH_THREADS, 0, scratch.p, N, (int)nchunks, leaves);
-    else LAUNCH(ctx, k_coop_merge_many_rows, ceil_div(N * ZKL_COOP_GROUP, ZKL_COOP_THREADS), ZKL_COOP_THREADS, 0, scratch.p, N, (int)nchunks, leaves);
-  }
-  return 0;
+  if (nchunks == 1) return dev_hash_partitions(ctx, lde, ncols, n, blowup, ps, leaves);
+  ZKL_CHECK(ctx, scratch.alloc(N * nchunks));
+  ZKL_TRY(dev_hash_partitions(ctx, lde, ncols, n, blowup, ps, scratch.p));
+  return dev_merge_partitions(ctx, scratch.p, N, N, nchunks, leaves);
 }
 // MerkleTree::new: nodes[count + i] = leaves[i] conceptually; we store nodes[1..count) and keep leaves
 // separately. nodes has `count` entries (nodes[0] unused), nodes[1] = root.

@@ -1,0 +1,139 @@
+"""Column-sharded trace commitment of ONE segment across the GPUs of a box ("single huge segment").
+
+The reference commits to a trace row as `merge_many(hash_elements(partition_0), ..., hash_elements(partition_{P-1}))`
+when `PartitionOptions` asks for several partitions (restated at zk-lisp-proof-winterfell/src/agg/child.rs:1025-1045;
+partition selection src/utils.rs:394-409). Partitions are column ranges, so a rank that owns WHOLE partitions can run
+the column transforms (iNTT, blowup LDE) and the partition hashes without seeing any other column. The only data
+that has to cross NVLink is one 16-byte digest per (LDE row, partition):
+
+    rank g:  columns of its partitions -> iNTT -> LDE -> partition digests [p_g][N]          (local, C ABI)
+    all ranks: all_gather(partition digests)                                                  (NCCL, 16 B per row/partition
+                                                                                               instead of 16*W B per row)
+    rank g:  leaves[rows_g] = merge_many(digests[:, rows_g])                                  (row-sharded, local)
+    all ranks: all_gather(leaves) -> MerkleTree::new -> root                                   (NCCL + local)
+
+`plan()` and `assemble()` are pure index logic (tested on CPU with gloo, tests/test_multi_rank_gloo.py); the device
+work goes through include/zkl_b200.h (`zkl_lde_dev`, `zkl_hash_partitions_dev`, `zkl_merge_partition_digests_dev`,
+`zkl_merkle_dev`). The root is bit-identical to the single-GPU `zkl_trace_lde_commit` and to the oracle
+(tests/test_gpu_sharded.py, tools/sharded_commit_check.py under torchrun).
+"""
+from dataclasses import dataclass
+from typing import List
+
+
+@dataclass
+class ShardPlan:
+    width: int
+    partition_size: int
+    num_partitions: int          # P
+    world: int
+    parts_per_rank: int          # ceil(P / world): slots every rank contributes to the all-gather (padded)
+    first_part: List[int]        # per rank: first owned partition
+    num_parts: List[int]         # per rank: owned partitions (0 for ranks beyond P)
+
+    def columns(self, rank: int):
+        """[first, last) trace columns owned by `rank`."""
+        lo = min(self.width, self.first_part[rank] * self.partition_size)
+        hi = min(self.width, (self.first_part[rank] + self.num_parts[rank]) * self.partition_size)
+        return lo, max(lo, hi)
+
+    def slot_of_partition(self, q: int) -> int:
+        """Index of global partition q in the gathered [world * parts_per_rank] digest array."""
+        r = min(q // self.parts_per_rank, self.world - 1)
+        return r * self.parts_per_rank + (q - self.first_part[r])
+
+
+def plan(width: int, partition_size: int, world: int) -> ShardPlan:
+    """Contiguous blocks of whole partitions per rank."""
+    if partition_size <= 0 or width <= 0 or world <= 0:
+        raise ValueError("bad shard plan arguments")
+    P = (width + partition_size - 1) // partition_size
+    if P < 2:
+        raise ValueError("column sharding needs at least two partitions (PartitionOptions (1, 0) hashes whole rows)")
+    per = (P + world - 1) // world
+    first = [min(r * per, P) for r in range(world)]
+    cnt = [max(0, min(P, (r + 1) * per) - first[r]) for r in range(world)]
+    return ShardPlan(width, partition_size, P, world, per, first, cnt)
+
+
+def row_range(N: int, rank: int, world: int):
+    """Rows whose leaves `rank` merges (N is a power of two >= world)."""
+    per = (N + world - 1) // world
+    lo = min(N, rank * per)
+    return lo, min(N, lo + per)
+
+
+def assemble(gathered, p: ShardPlan):
+    """gathered: array-like [world * parts_per_rank][N] (rank-major, padded slots at the end of each rank block).
+    Returns the list of row arrays in global partition order (views, no copy)."""
+    return [gathered[p.slot_of_partition(q)] for q in range(p.num_partitions)]
+
+
+class ShardedTraceCommit:
+    """Runs the flow above on the calling rank. `dist` is torch.distributed (nccl backend), `ctx` a zk_lisp_b200 Context
+    pinned to this rank's GPU."""
+
+    def __init__(self, ctx, dist, opts):
+        self.ctx, self.dist, self.opts = ctx, dist, opts
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+
+    def commit(self, local_cols, width: int, n: int):
+        """local_cols: numpy (ncols_local, n, 2) uint64 — this rank's columns per plan(). Returns (root bytes, plan)."""
+        import ctypes as C
+        import numpy as np
+        import torch
+        lib, h = self.ctx.lib, self.ctx.h
+        oc = self.opts.to_c()
+        ps = int(lib.zkl_partition_size(C.byref(oc), width))
+        p = plan(width, ps, self.world)
+        B = int(self.opts.blowup)
+        N = n * B
+        lo, hi = p.columns(self.rank)
+        ncols = hi - lo
+        assert local_cols.shape[0] == ncols, (local_cols.shape, lo, hi)
+        dev = torch.device("cuda", self.ctx.device)
+        u8 = torch.uint8
+
+        def buf(elems):
+            return torch.empty(max(elems, 1) * 16, dtype=u8, device=dev)
+
+        # local: upload, iNTT, LDE, partition digests
+        mine = buf(p.parts_per_rank * N)
+        mine.zero_()
+        torch.cuda.synchronize(dev)   # torch's stream and the context's stream are independent
+        if ncols:
+            cols_d, polys_d, lde_d = buf(ncols * n), buf(ncols * n), buf(ncols * N)
+            host = np.ascontiguousarray(local_cols, dtype=np.uint64)
+            self.ctx._check(lib.zkl_dev_upload(h, C.c_void_p(cols_d.data_ptr()), host.ctypes.data, host.nbytes))
+            self.ctx._check(lib.zkl_lde_dev(h, C.c_void_p(cols_d.data_ptr()), ncols, n, B, C.c_void_p(polys_d.data_ptr()), C.c_void_p(lde_d.data_ptr())))
+            self.ctx._check(lib.zkl_hash_partitions_dev(h, C.c_void_p(lde_d.data_ptr()), ncols, n, B, ps, C.c_void_p(mine.data_ptr())))
+        self.ctx._check(lib.zkl_sync(h))
+        # exchange 1: partition digests (16 B per row and partition)
+        allp = buf(self.world * p.parts_per_rank * N)
+        self.dist.all_gather_into_tensor(allp, mine)
+        torch.cuda.synchronize(dev)
+        # compact to global partition order if the last rank blocks are padded
+        if p.num_partitions != self.world * p.parts_per_rank:
+            view = allp.view(self.world * p.parts_per_rank, N * 16)
+            allp = torch.stack(assemble(view, p)).contiguous().view(-1)
+        # local: leaves of this rank's rows
+        r0, r1 = row_range(N, self.rank, self.world)
+        per = (N + self.world - 1) // self.world
+        leaves_mine = buf(per)
+        leaves_mine.zero_()
+        torch.cuda.synchronize(dev)
+        if r1 > r0:
+            self.ctx._check(lib.zkl_merge_partition_digests_dev(h, C.c_void_p(allp.data_ptr()), p.num_partitions, N, r0, r1 - r0,
+                                                                C.c_void_p(leaves_mine.data_ptr())))
+        self.ctx._check(lib.zkl_sync(h))
+        # exchange 2: leaves, then the tree on every rank
+        leaves = buf(self.world * per)
+        self.dist.all_gather_into_tensor(leaves, leaves_mine)
+        torch.cuda.synchronize(dev)
+        nodes = buf(N)
+        self.ctx._check(lib.zkl_merkle_dev(h, C.c_void_p(leaves.data_ptr()), N, C.c_void_p(nodes.data_ptr())))
+        root = np.zeros(16, dtype=np.uint8)
+        self.ctx._check(lib.zkl_dev_download(h, root.ctypes.data, C.c_void_p(nodes.data_ptr() + 16), 16))
+        self.bytes_exchanged = (self.world - 1) * (p.parts_per_rank * N * 16 + per * 16)
+        self.bytes_unsharded_rows = (self.world - 1) * ncols * N * 16
+        return root.tobytes() + bytes(16), p
