@@ -266,3 +266,27 @@ def test_large_segment_commit_and_proof(ctx, zkl, oracle):
     tampered = bytearray(proof); tampered[len(proof) // 2] ^= 1
     rc, _ = oracle.verify_segment(bytes(tampered), trace.shape[0], n, ac, seed, oc)
     assert rc != 0
+
+
+@pytest.mark.parametrize("case", [
+    dict(n=64, full_layout=True),                                  # W = 219: 12 permutations per row
+    dict(n=64, blowup=32, queries=20),                             # 12 FRI layers over 2048 points, remainder domain 64
+    dict(n=128, queries=255, grind=0),                             # maximum query count, heavy de-duplication, no grinding
+    dict(n=64, partitions=(4, 8)),                                 # partitioned leaves in both commitments
+    dict(n=128, partitions=(16, 16), full_layout=True),            # 14 partitions x 16 columns (the X-config shape)
+    dict(n=32, queries=4, grind=2),                                # one schedule level: the smallest legal segment
+])
+def test_prove_segment_option_matrix(ctx, zkl, oracle, case):
+    """Proof bytes equal to the oracle's across layouts / blowups / query counts / partition options."""
+    kw = dict(n=case["n"], queries=case.get("queries", 8), blowup=case.get("blowup", 16), grind=case.get("grind", 4), seed=11,
+              full_layout=case.get("full_layout", False))
+    trace, air_pi, opts = synth.valid_segment(**kw)
+    if "partitions" in case:
+        opts.num_partitions, opts.hash_rate = case["partitions"]
+    a, ac, oc, seed = _air(zkl, trace, air_pi, opts)
+    prover = zkl.ZkProver(ctx, opts, air_pi)
+    proof = prover.prove(trace)
+    ref = oracle.prove_segment(trace, ac, seed, oc)
+    assert proof == ref
+    rc, msg = oracle.verify_segment(proof, trace.shape[0], case["n"], ac, seed, oc)
+    assert rc == 0, msg
