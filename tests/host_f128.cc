@@ -17,6 +17,7 @@ void h_binop(int op, const fe *a, const fe *b, fe *out, long n) {
       case 8: out[i] = lazy_add(a[i], b[i]); break;
       case 9: out[i] = lazy_canon(a[i]); break;
       case 10: out[i] = lazy_sqr(a[i]); break;
+      case 11: { uint32_t x[8]; lazy_mul_wide(a[i], b[i], x); out[i] = lazy_reduce8_mac(x); } break;
     }
   }
 }

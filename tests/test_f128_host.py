@@ -55,12 +55,16 @@ def test_lazy_ops_accept_any_128_bit_value(hostlib):
     got = binop(hostlib, 7, a, b)
     assert all(g <= M128 for g in got)
     assert [g % P for g in got] == [(x * y) % P for x, y in zip(a, b)]
+    got = binop(hostlib, 11, a, b)          # multiply-accumulate form of the first fold
+    assert [g % P for g in got] == [(x * y) % P for x, y in zip(a, b)]
     got = binop(hostlib, 8, a, b)
     assert [g % P for g in got] == [(x + y) % P for x, y in zip(a, b)]
     assert binop(hostlib, 9, a, a) == [x % P for x in a]
     # worst cases for the carry fix-ups: everything at the top of the range
     top = [M128 - k for k in range(64)]
     got = binop(hostlib, 7, top, top[::-1])
+    assert [g % P for g in got] == [(x * y) % P for x, y in zip(top, top[::-1])]
+    got = binop(hostlib, 11, top, top[::-1])
     assert [g % P for g in got] == [(x * y) % P for x, y in zip(top, top[::-1])]
     got = binop(hostlib, 8, top, top[::-1])
     assert [g % P for g in got] == [(x + y) % P for x, y in zip(top, top[::-1])]
