@@ -264,6 +264,9 @@ int zkl_set_bulk_threshold(zkl_ctx *ctx, long sponges);
 /* bulk hashing path: 0 = tensor-core MDS product (tcgen05 kind::i8, default), 1 = integer-pipe thread-per-sponge
  * kernels. Both are bit-identical; 1 exists for A/B measurements and parity tests. */
 int zkl_set_hash_path(zkl_ctx *ctx, int path);
+/* 4096-row coset LDE: 0 = radix-16 stages on the tensor cores (default), 1 = radix-2 butterflies in shared memory.
+ * Bit-identical; 1 exists for A/B measurements and parity tests. */
+int zkl_set_ntt_path(zkl_ctx *ctx, int path);
 /* permutation throughput probe on device-resident states: kind 0 = thread-per-state kernel, 1 = cooperative,
  * 2 = tensor-core MDS kernel */
 int zkl_bench_permute(zkl_ctx *ctx, int kind, size_t count, int iters, float *ms_per_iter);

@@ -32,7 +32,7 @@ void h_dot12(const fe *a, const fe *b, const fe *rc, fe *out, long n) {
 }
 // tensor-core epilogue: 16 byte-position accumulators + round constant -> lazy element
 void h_tc_epilogue(const uint32_t *acc, const fe *rc, fe *out, long n) {
-  for (long i = 0; i < n; i++) out[i] = tc_epilogue(acc + 16 * i, rc[i]);
+  for (long i = 0; i < n; i++) out[i] = rc ? tc_epilogue(acc + 16 * i, rc[i]) : tc_epilogue_plain(acc + 16 * i);
 }
 // raw 256-bit product (the cube bytes fed to the MMA)
 void h_mul_wide(const fe *a, const fe *b, uint32_t *out, long n) {

@@ -290,3 +290,30 @@ def test_prove_segment_option_matrix(ctx, zkl, oracle, case):
     assert proof == ref
     rc, msg = oracle.verify_segment(proof, trace.shape[0], case["n"], ac, seed, oc)
     assert rc == 0, msg
+
+
+def test_lde_4096_on_tensor_cores(ctx, oracle):
+    """n = 4096 (the rollup-bench segment size): the radix-16 tensor-core LDE (kernels_tcntt.cuh) against the oracle's
+    radix-2 FFT and against the integer-pipe kernel, for blowups 16 (trace), 8 (boundary polynomials) and 2."""
+    if ctx.hash_mode != "default":
+        pytest.skip("NTT test, independent of the hashing mode")
+    n = 4096
+    cols = fast_random_trace(5, n, seed=4096)
+    cols[0] = 0                      # zero column
+    cols[1, :, 0] = 1; cols[1, :, 1] = 0   # constant one
+    polys = ctx.interpolate_columns(cols)
+    for blowup in (16, 8, 2):
+        ctx._check(ctx.lib.zkl_set_ntt_path(ctx.h, 0))
+        ev_tc = ctx.evaluate_columns(polys, blowup)
+        ctx._check(ctx.lib.zkl_set_ntt_path(ctx.h, 1))
+        ev_int = ctx.evaluate_columns(polys, blowup)
+        ctx._check(ctx.lib.zkl_set_ntt_path(ctx.h, 0))
+        assert np.array_equal(ev_tc, ev_int), blowup
+        if blowup <= 8:
+            assert np.array_equal(ev_tc, oracle.evaluate_columns(polys, blowup)), blowup
+    # more columns than SMs x 1: the persistent CTAs loop over (column, coset) problems
+    many = fast_random_trace(40, n, seed=5)
+    ctx._check(ctx.lib.zkl_set_ntt_path(ctx.h, 0)); a = ctx.evaluate_columns(many, 16)
+    ctx._check(ctx.lib.zkl_set_ntt_path(ctx.h, 1)); b = ctx.evaluate_columns(many, 16)
+    ctx._check(ctx.lib.zkl_set_ntt_path(ctx.h, 0))
+    assert np.array_equal(a, b)

@@ -858,6 +858,10 @@ extern "C" int zkl_imad_peak(zkl_ctx *ctx, double *wide_macs_per_s) {
   return 0;
 }
 extern "C" int zkl_set_bulk_threshold(zkl_ctx *ctx, long sponges) { ctx->bulk_threshold = sponges; return 0; }
+extern "C" int zkl_set_ntt_path(zkl_ctx *ctx, int path) {
+  if (path != 0 && path != 1) { ctx->set_error("ntt path must be 0 (tensor-core radix-16 LDE) or 1 (integer pipe)"); return 1; }
+  ctx->ntt_path = path; return 0;
+}
 extern "C" int zkl_set_hash_path(zkl_ctx *ctx, int path) {
   if (path != 0 && path != 1) { ctx->set_error("hash path must be 0 (tensor-core MDS) or 1 (integer pipe)"); return 1; }
   if (path == 0 && !ctx->tc_ok) { ctx->set_error("the loaded MDS constants exceed the tensor-core accumulator bound (TC_ACC_MAX)"); return 1; }

@@ -36,6 +36,7 @@ struct domain_tables {
 struct zkl_ctx {
   int device = 0;
   int num_sms = 148;
+  int tc_grid_cap = 148;                   // persistent tensor-core sponge kernels launch at most this many CTAs
   cudaStream_t stream = nullptr;
   cudaMemPool_t pool = nullptr;            // private stream-ordered memory pool
   std::string err;
@@ -45,6 +46,7 @@ struct zkl_ctx {
   long bulk_threshold = 1024;
   // bulk hashing path: 0 = tensor-core MDS (tcperm.cuh, the default), 1 = integer-pipe thread-per-sponge kernels
   int hash_path = 0;
+  int ntt_path = 0;    // 4096-row coset LDE: 0 = radix-16 stages on the tensor cores (kernels_tcntt.cuh), 1 = radix-2 in shared memory
   bool tc_ok = true;   // the loaded MDS constants satisfy the tensor-core epilogue's accumulator bound
   std::map<size_t, domain_tables> tables;  // by N
   std::map<size_t, fe *> opow;             // GENERATOR^j tables by n

@@ -147,6 +147,20 @@ ZKL_HD fe lazy_canon(const fe &a) { return fe_from_u128_mod(a); }
 // constants (hasher suite: 13 497 915). V = sum_u acc[u] * 2^(8u) + rc (< 2^146) is folded once to a lazy element.
 //   pairs P_j at bit 16 j: even j concatenate into limbs 0..3, odd j concatenate and shift by 16 — no multiplies.
 #define TC_ACC_MAX 16711679u
+// same without an addend (radix-16 NTT stages, kernels_tcntt.cuh)
+ZKL_HD fe tc_epilogue_plain(const uint32_t acc[16]) {
+  uint32_t P[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) P[j] = acc[2 * j] + (acc[2 * j + 1] << 8);
+  uint32_t o0 = P[1] << 16, o1 = p_shf_l(P[1], P[3], 16), o2 = p_shf_l(P[3], P[5], 16), o3 = p_shf_l(P[5], P[7], 16), o4 = P[7] >> 16;
+  uint32_t w0 = p_add_cc(P[0], o0), w1 = p_addc_cc(P[2], o1), w2 = p_addc_cc(P[4], o2), w3 = p_addc_cc(P[6], o3), w4 = p_addc(o4, 0);
+  uint32_t t = w4 * 45u;
+  uint32_t d0 = p_sub_cc(0, w4), d1 = p_subc(t << 8, 0);
+  uint32_t z0 = p_add_cc(w0, d0), z1 = p_addc_cc(w1, d1), z2 = p_addc_cc(w2, 0), z3 = p_addc_cc(w3, 0), c = p_addc(0, 0);
+  lazy_fix_carry(z0, z1, z2, c);
+  fe r; r.l[0] = z0; r.l[1] = z1; r.l[2] = z2; r.l[3] = z3;
+  return r;
+}
 ZKL_HD fe tc_epilogue(const uint32_t acc[16], const fe &rc) {
   uint32_t P[8];
 #pragma unroll

@@ -1,6 +1,7 @@
 // zkl_b200.cu — C ABI (include/zkl_b200.h) over the sm_100a kernels. Single translation unit so the
 // __constant__ hasher suite is shared by every kernel without relocatable device code.
 // No CPU fallback: every entry point launches device work; a missing device fails at ctx creation.
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -11,6 +12,7 @@
 #include "kernels_ntt.cuh"
 #include "kernels_stark.cuh"
 #include "kernels_tc.cuh"
+#include "kernels_tcntt.cuh"
 
 static std::string g_create_error;
 static std::mutex g_suite_mutex;
@@ -23,12 +25,13 @@ static std::mutex g_suite_mutex;
   } while (0)
 // tensor-core sponge kernels: persistent, one 512-thread CTA per SM, `sponges` = number of sponges in the launch
 #define LAUNCH_TC(ctx, kernel, sponges, ...)                                                                        \
-  LAUNCH(ctx, kernel, std::min<size_t>(((size_t)(sponges) + TC_CTA_SPONGES - 1) / TC_CTA_SPONGES, (size_t)(ctx)->num_sms), TC_THREADS, \
+  LAUNCH(ctx, kernel, std::min<size_t>(((size_t)(sponges) + TC_CTA_SPONGES - 1) / TC_CTA_SPONGES, (size_t)(ctx)->tc_grid_cap), TC_THREADS, \
          TC_SMEM_BYTES, __VA_ARGS__)
 
 // ------------------------------------------------------------------------------------------------
 // context
 // ------------------------------------------------------------------------------------------------
+static fe host_root_of_unity(int logn);
 static fe host_label(const char *s) {  // hasher.rs:155-160: label zero-padded to 32 bytes, folded
   uint8_t b[32]; memset(b, 0, 32);
   size_t l = strlen(s); if (l > 32) l = 32;
@@ -51,6 +54,8 @@ extern "C" int zkl_ctx_create(int device, zkl_ctx **out) {
   cudaDeviceProp prop;
   if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete c; return 1; }
   c->num_sms = prop.multiProcessorCount;
+  c->tc_grid_cap = c->num_sms;
+  if (const char *e = getenv("ZKL_TC_GRID_CAP")) { int v = atoi(e); if (v > 0 && v <= c->num_sms) c->tc_grid_cap = v; }   // experiment knob
   if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) {
     g_create_error = cudaGetErrorString(e); delete c; return 1;
   }
@@ -70,6 +75,7 @@ extern "C" int zkl_ctx_create(int device, zkl_ctx **out) {
   // opt in to large dynamic shared memory for the single-pass column transforms
   cudaFuncSetAttribute(k_interpolate, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
   cudaFuncSetAttribute(k_lde, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+  cudaFuncSetAttribute(k_tc_lde4096, cudaFuncAttributeMaxDynamicSharedMemorySize, NTT16_SMEM_BYTES);
   cudaFuncSetAttribute(k_ntt_pass1, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
   cudaFuncSetAttribute(k_ntt_pass2, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
   cudaFuncSetAttribute(k_tc_permute_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
@@ -89,6 +95,9 @@ extern "C" int zkl_ctx_create(int device, zkl_ctx **out) {
   {
     std::lock_guard<std::mutex> g(g_suite_mutex);
     if ((e = cudaMemcpyToSymbol(c_labels, &lc, sizeof lc)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete c; return 1; }
+    // byte image of the DFT-16 matrix for the tensor-core LDE (kernels_tcntt.cuh); w16 = primitive 16th root of unity
+    k_build_dft16_bytes<<<16, 256, 0, c->stream>>>(host_root_of_unity(4));
+    if ((e = cudaStreamSynchronize(c->stream)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete c; return 1; }
   }
   *out = c;
   return 0;
@@ -225,6 +234,11 @@ static int dev_lde(zkl_ctx *ctx, const fe *polys, fe *out, size_t ncols, size_t 
     fe *p; ZKL_CHECK(ctx, cudaMalloc((void **)&p, N * sizeof(fe)));
     LAUNCH(ctx, k_lde_scale_table, ceil_div(N, 256), 256, 0, opow, t->wpow, N, (int)n, (int)blowup, p);
     it = ctx->opow.emplace(key, p).first;
+  }
+  if (n == NTT16_N && ctx->ntt_path == 0) {   // radix-16 stages on the tensor cores (kernels_tcntt.cuh)
+    LAUNCH(ctx, k_tc_lde4096, (unsigned)std::min<size_t>(ncols * blowup, (size_t)ctx->num_sms), NTT16_THREADS, NTT16_SMEM_BYTES, polys, (int)ncols, (int)blowup,
+           it->second, t->wpow, out);
+    return 0;
   }
   if (n <= NTT_SINGLE_PASS_MAX) {
     dim3 grid((unsigned)blowup, (unsigned)ncols);

@@ -14,7 +14,7 @@ that has to cross NVLink is one 16-byte digest per (LDE row, partition):
 
 `plan()` and `assemble()` are pure index logic (tested on CPU with gloo, tests/test_multi_rank_gloo.py); the device
 work goes through include/zkl_b200.h (`zkl_lde_dev`, `zkl_hash_partitions_dev`, `zkl_merge_partition_digests_dev`,
-`zkl_merkle_dev`). The root is bit-identical to the single-GPU `zkl_trace_lde_commit` and to the oracle
+`zkl_merkle_dev`). The root is bit-identical to the single-GPU `zkl_trace_lde_commit` and to the CPU restatement
 (tests/test_gpu_sharded.py, tools/sharded_commit_check.py under torchrun).
 """
 from dataclasses import dataclass
