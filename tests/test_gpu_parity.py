@@ -302,6 +302,12 @@ def test_lde_4096_on_tensor_cores(ctx, oracle):
     cols[0] = 0                      # zero column
     cols[1, :, 0] = 1; cols[1, :, 1] = 0   # constant one
     polys = ctx.interpolate_columns(cols)
+    ctx._check(ctx.lib.zkl_set_ntt_path(ctx.h, 1))
+    polys_int = ctx.interpolate_columns(cols)
+    ctx._check(ctx.lib.zkl_set_ntt_path(ctx.h, 0))
+    assert np.array_equal(polys, polys_int)                       # inverse transform: tensor-core vs radix-2 kernel
+    assert np.array_equal(polys, oracle.interpolate_columns(cols))
+    assert from_fe(polys[0]) == [0] * n and from_fe(polys[1]) == [1] + [0] * (n - 1)
     for blowup in (16, 8, 2):
         ctx._check(ctx.lib.zkl_set_ntt_path(ctx.h, 0))
         ev_tc = ctx.evaluate_columns(polys, blowup)

@@ -31,13 +31,15 @@
 #define NTT16_SMEM_BYTES (NTT16_B_BYTES + 2 * NTT16_BUF_BYTES + 256 + 128)
 #define NTT16_IDESC ((2u << 4) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24))
 
-// byte image of the DFT-16 matrix: entry (chunk j, row 16 i + u) = 16 bytes b: byte_u(w16^(ij) * 2^(8b) mod p)
-__device__ uint4 g_dft16_bytes[NTT16_B_BYTES / 16];
-__global__ void k_build_dft16_bytes(fe w16) {
+// byte images of the DFT-16 matrix for w16 (forward) and w16^-1 (inverse): entry (chunk j, row 16 i + u) = 16 bytes b:
+// byte_u(w16^(± i j) * 2^(8b) mod p)
+__device__ uint4 g_dft16_bytes[2][NTT16_B_BYTES / 16];
+__global__ void k_build_dft16_bytes(fe w16, fe w16_inv) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= 16 * 256) return;
+  if (t >= 2 * 16 * 256) return;
+  const int inv = t >> 12; t &= 4095;
   int j = t >> 8, row = t & 255, i = row >> 4, u = row & 15;
-  fe cur = fe_pow(w16, (uint64_t)(i * j));
+  fe cur = fe_pow(inv ? w16_inv : w16, (uint64_t)(i * j));
   fe two8 = fe_from_u64(256);
   uint32_t out[4] = {0, 0, 0, 0};
   for (int b = 0; b < 16; b++) {
@@ -45,13 +47,16 @@ __global__ void k_build_dft16_bytes(fe w16) {
     out[b >> 2] |= ((limb >> (8 * (u & 3))) & 0xFF) << (8 * (b & 3));
     cur = fe_mul(cur, two8);
   }
-  g_dft16_bytes[t] = make_uint4(out[0], out[1], out[2], out[3]);
+  g_dft16_bytes[inv][t] = make_uint4(out[0], out[1], out[2], out[3]);
 }
 
-// grid = min(ncols * blowup, #SMs), persistent. polys: ncols x 4096 coefficients; scale[k][j] = (offset w_N^k)^j;
-// wpow: w_N^e, N = 4096 * blowup; out[c][k][i] coset-major.
-__global__ void __launch_bounds__(NTT16_THREADS, 1) k_tc_lde4096(const fe *__restrict__ polys, int ncols, int blowup, const fe *__restrict__ scale,
-                                                                const fe *__restrict__ wpow, fe *__restrict__ out) {
+// grid = min(ncols * blowup, #SMs), persistent.
+//   forward (coset LDE):  polys: ncols x 4096 coefficients; scale[k][j] = (offset w_N^k)^j; out[c][k][i] coset-major
+//   inverse (interpolate): polys: ncols x 4096 evaluations over <w_4096>, blowup = 1, scale = nullptr, every output is
+//                          multiplied by `factor` = 4096^-1; in place allowed (a CTA reads its whole column before it writes)
+// wpow: w_N^e, N = 4096 * blowup.
+__global__ void __launch_bounds__(NTT16_THREADS, 1) k_tc_lde4096(const fe *polys, int ncols, int blowup, const fe *__restrict__ scale,
+                                                                const fe *__restrict__ wpow, fe *out, bool inverse, fe factor) {
   extern __shared__ unsigned char ntt_smem[];
   const uint32_t base = (smem_u32(ntt_smem) + 127u) & ~127u;
   unsigned char *gen = ntt_smem + (base - smem_u32(ntt_smem));
@@ -59,7 +64,7 @@ __global__ void __launch_bounds__(NTT16_THREADS, 1) k_tc_lde4096(const fe *__res
   uint32_t *ctl_gen = reinterpret_cast<uint32_t *>(gen + NTT16_B_BYTES + 2 * NTT16_BUF_BYTES);
   {
     uint4 *bdst = reinterpret_cast<uint4 *>(gen);
-    for (int i = threadIdx.x; i < NTT16_B_BYTES / 16; i += NTT16_THREADS) bdst[i] = g_dft16_bytes[i];
+    for (int i = threadIdx.x; i < NTT16_B_BYTES / 16; i += NTT16_THREADS) bdst[i] = g_dft16_bytes[inverse ? 1 : 0][i];
   }
   if (threadIdx.x < 32) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ctl + 64), "n"(512) : "memory");
@@ -92,7 +97,8 @@ __global__ void __launch_bounds__(NTT16_THREADS, 1) k_tc_lde4096(const fe *__res
 #pragma unroll 2
       for (int q = 0; q < 8; q++) {
         int j = threadIdx.x + 512 * q;
-        fe v = lazy_mul(ld_fe(poly + j), ld_fe(sc + j));
+        fe v = ld_fe(poly + j);
+        if (scale) v = lazy_mul(v, ld_fe(sc + j));
         sts_u4(src + (uint32_t)(j >> 8) * NTT16_PITCH + (uint32_t)(j & 255) * 16, v.l[0], v.l[1], v.l[2], v.l[3]);
       }
     }
@@ -128,13 +134,14 @@ __global__ void __launch_bounds__(NTT16_THREADS, 1) k_tc_lde4096(const fe *__res
           fe v = tc_epilogue_plain(acc[q & 1]);
           if (stage == 0) {          // m = jA + 16 jC, i = iD
             const int jA = m & 15, jC = m >> 4;
-            v = lazy_mul(v, ld_fe(wpow + (size_t)(i * jC) * s256));
+            { size_t e = (size_t)(i * jC) * s256; if (inverse && e) e = N - e; v = lazy_mul(v, ld_fe(wpow + e)); }
             sts_u4(dst + (uint32_t)jC * NTT16_PITCH + (uint32_t)(jA + 16 * i) * 16, v.l[0], v.l[1], v.l[2], v.l[3]);
           } else if (stage == 1) {   // m = jA + 16 iD, i = iC
             const int jA = m & 15, iB = 16 * i + (m >> 4);
-            v = lazy_mul(v, ld_fe(wpow + (size_t)(iB * jA) * s4096));
+            { size_t e = (size_t)(iB * jA) * s4096; if (inverse && e) e = N - e; v = lazy_mul(v, ld_fe(wpow + e)); }
             sts_u4(dst + (uint32_t)jA * NTT16_PITCH + (uint32_t)iB * 16, v.l[0], v.l[1], v.l[2], v.l[3]);
           } else {                   // m = iB, i = iA
+            if (inverse) v = lazy_mul(v, factor);
             st_fe(out + ((size_t)c * blowup + k) * NTT16_N + 256 * i + m, lazy_canon(v));
           }
         }

@@ -96,7 +96,7 @@ extern "C" int zkl_ctx_create(int device, zkl_ctx **out) {
     std::lock_guard<std::mutex> g(g_suite_mutex);
     if ((e = cudaMemcpyToSymbol(c_labels, &lc, sizeof lc)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete c; return 1; }
     // byte image of the DFT-16 matrix for the tensor-core LDE (kernels_tcntt.cuh); w16 = primitive 16th root of unity
-    k_build_dft16_bytes<<<16, 256, 0, c->stream>>>(host_root_of_unity(4));
+    k_build_dft16_bytes<<<32, 256, 0, c->stream>>>(host_root_of_unity(4), fe_inv(host_root_of_unity(4)));
     if ((e = cudaStreamSynchronize(c->stream)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete c; return 1; }
   }
   *out = c;
@@ -207,6 +207,11 @@ static int dev_interpolate(zkl_ctx *ctx, const fe *src, fe *dst, size_t ncols, s
   if (n > NTT_MAX || (n & (n - 1)) || n < 2) { ctx->set_error("trace length must be a power of two in [2, 2^24]"); return 1; }
   domain_tables *t; ZKL_TRY(get_tables(ctx, n, &t));
   fe n_inv = fe_inv(fe_from_u64(n));
+  if (n == NTT16_N && ctx->ntt_path == 0) {   // inverse radix-16 stages on the tensor cores (kernels_tcntt.cuh)
+    LAUNCH(ctx, k_tc_lde4096, (unsigned)std::min<size_t>(ncols, (size_t)ctx->num_sms), NTT16_THREADS, NTT16_SMEM_BYTES, src, (int)ncols, 1, (const fe *)nullptr,
+           t->wpow, dst, true, n_inv);
+    return 0;
+  }
   if (n <= NTT_SINGLE_PASS_MAX) {
     LAUNCH(ctx, k_interpolate, (unsigned)ncols, NTT_THREADS, n * sizeof(fe), src, dst, (int)n, ilog2_sz(n), t->wpow, n, n_inv);
     return 0;
@@ -237,7 +242,7 @@ static int dev_lde(zkl_ctx *ctx, const fe *polys, fe *out, size_t ncols, size_t 
   }
   if (n == NTT16_N && ctx->ntt_path == 0) {   // radix-16 stages on the tensor cores (kernels_tcntt.cuh)
     LAUNCH(ctx, k_tc_lde4096, (unsigned)std::min<size_t>(ncols * blowup, (size_t)ctx->num_sms), NTT16_THREADS, NTT16_SMEM_BYTES, polys, (int)ncols, (int)blowup,
-           it->second, t->wpow, out);
+           it->second, t->wpow, out, false, fe_zero());
     return 0;
   }
   if (n <= NTT_SINGLE_PASS_MAX) {
