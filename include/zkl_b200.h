@@ -264,11 +264,15 @@ int zkl_set_bulk_threshold(zkl_ctx *ctx, long sponges);
 /* bulk hashing path: 0 = tensor-core MDS product (tcgen05 kind::i8, default), 1 = integer-pipe thread-per-sponge
  * kernels. Both are bit-identical; 1 exists for A/B measurements and parity tests. */
 int zkl_set_hash_path(zkl_ctx *ctx, int path);
-/* 4096-row coset LDE: 0 = radix-16 stages on the tensor cores (default), 1 = radix-2 butterflies in shared memory.
- * Bit-identical; 1 exists for A/B measurements and parity tests. */
+/* Small sponge batches (tree levels, FRI layer tails, the Fiat-Shamir coin, the OOD digest): 0 = 64-thread groups
+ * (lowest latency, default), 1 = 16-thread groups. Bit-identical; 1 exists for A/B measurements and parity tests. */
+int zkl_set_coop_path(zkl_ctx *ctx, int path);
+/* 4096-row coset LDE: 0 = radix-16 stages on the tensor cores with the coset shift folded into the constant matrix
+ * (default), 1 = radix-2 butterflies in shared memory, 2 = tensor cores with a separate coset-shift product.
+ * Bit-identical; 1 and 2 exist for A/B measurements and parity tests. */
 int zkl_set_ntt_path(zkl_ctx *ctx, int path);
 /* permutation throughput probe on device-resident states: kind 0 = thread-per-state kernel, 1 = cooperative,
- * 2 = tensor-core MDS kernel */
+ * 2 = tensor-core MDS kernel, 3 = 64-thread groups */
 int zkl_bench_permute(zkl_ctx *ctx, int kind, size_t count, int iters, float *ms_per_iter);
 
 #ifdef __cplusplus

@@ -30,10 +30,11 @@ def oracle():
 
 
 # Bulk hashing modes every GPU parity test runs under (all three must be bit-identical to the oracle):
-#   default   tensor-core sponge kernels from 1024 sponges up, 16-thread cooperative kernels below
+#   default   tensor-core sponge kernels from 1024 sponges up, 64-thread-group kernels (kernels_quad.cuh) below and for the coin
 #   tc-forced tensor-core kernels for every bulk call site (threshold 1): small test sizes reach tcperm.cuh
-#   int-pipe  the integer-pipe thread-per-sponge kernels for every bulk call site
-HASH_MODES = {"default": (None, 0), "tc-forced": (1, 0), "int-pipe": (1, 1)}
+#   int-pipe  the integer-pipe thread-per-sponge kernels for every bulk call site, 16-thread groups for the coin
+#   coop16    like default with the 16-thread cooperative kernels instead of the 64-thread groups
+HASH_MODES = {"default": (None, 0, 0), "tc-forced": (1, 0, 0), "int-pipe": (1, 1, 1), "coop16": (None, 0, 1)}
 
 
 @pytest.fixture(scope="session", params=list(HASH_MODES))
@@ -41,9 +42,10 @@ def ctx(zkl, request):
     """GPU context; fails loudly if the CUDA library or device is missing (no fallback)."""
     graft.build()
     c = zkl.Context(0)
-    thr, path = HASH_MODES[request.param]
+    thr, path, coop = HASH_MODES[request.param]
     if thr is not None:
         c._check(c.lib.zkl_set_bulk_threshold(c.h, thr))
     c._check(c.lib.zkl_set_hash_path(c.h, path))
+    c._check(c.lib.zkl_set_coop_path(c.h, coop))
     c.hash_mode = request.param
     return c

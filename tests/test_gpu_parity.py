@@ -306,6 +306,10 @@ def test_lde_4096_on_tensor_cores(ctx, oracle):
     polys_int = ctx.interpolate_columns(cols)
     ctx._check(ctx.lib.zkl_set_ntt_path(ctx.h, 0))
     assert np.array_equal(polys, polys_int)                       # inverse transform: tensor-core vs radix-2 kernel
+    ctx._check(ctx.lib.zkl_set_ntt_path(ctx.h, 2))
+    polys_v1 = ctx.interpolate_columns(cols)                      # v1 tensor-core kernel (separate 1/n product)
+    ctx._check(ctx.lib.zkl_set_ntt_path(ctx.h, 0))
+    assert np.array_equal(polys, polys_v1)
     assert np.array_equal(polys, oracle.interpolate_columns(cols))
     assert from_fe(polys[0]) == [0] * n and from_fe(polys[1]) == [1] + [0] * (n - 1)
     for blowup in (16, 8, 2):
@@ -313,13 +317,22 @@ def test_lde_4096_on_tensor_cores(ctx, oracle):
         ev_tc = ctx.evaluate_columns(polys, blowup)
         ctx._check(ctx.lib.zkl_set_ntt_path(ctx.h, 1))
         ev_int = ctx.evaluate_columns(polys, blowup)
+        ctx._check(ctx.lib.zkl_set_ntt_path(ctx.h, 2))
+        ev_v1 = ctx.evaluate_columns(polys, blowup)
         ctx._check(ctx.lib.zkl_set_ntt_path(ctx.h, 0))
         assert np.array_equal(ev_tc, ev_int), blowup
+        assert np.array_equal(ev_tc, ev_v1), blowup
         if blowup <= 8:
             assert np.array_equal(ev_tc, oracle.evaluate_columns(polys, blowup)), blowup
     # more columns than SMs x 1: the persistent CTAs loop over (column, coset) problems
     many = fast_random_trace(40, n, seed=5)
     ctx._check(ctx.lib.zkl_set_ntt_path(ctx.h, 0)); a = ctx.evaluate_columns(many, 16)
     ctx._check(ctx.lib.zkl_set_ntt_path(ctx.h, 1)); b = ctx.evaluate_columns(many, 16)
+    ctx._check(ctx.lib.zkl_set_ntt_path(ctx.h, 0))
+    assert np.array_equal(a, b)
+    # more columns than CTAs for the in-place inverse transform (prefetch of the next column while one is written back)
+    wide = fast_random_trace(300, n, seed=6)
+    ctx._check(ctx.lib.zkl_set_ntt_path(ctx.h, 0)); a = ctx.interpolate_columns(wide)
+    ctx._check(ctx.lib.zkl_set_ntt_path(ctx.h, 1)); b = ctx.interpolate_columns(wide)
     ctx._check(ctx.lib.zkl_set_ntt_path(ctx.h, 0))
     assert np.array_equal(a, b)

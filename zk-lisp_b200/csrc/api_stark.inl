@@ -506,21 +506,40 @@ static int prove_segment_impl(zkl_ctx *ctx, const fe *trace_dev, size_t W, size_
   domain_tables *tN; ZKL_TRY(get_tables(ctx, N, &tN));
   fe *opow; ZKL_TRY(get_offset_powers(ctx, n, &opow)); (void)opow;
   cudaStream_t st = ctx->stream;
+  dev_buf<fe> coin;
+  const bool quad = ctx->coop_path == 0;   // low-latency sponges on 64-thread groups (kernels_quad.cuh)
+  // coin.reseed(digest) followed by `draws` draws, counter restarting at 1 (DefaultRandomCoin [WF-mem]); the digest is
+  // also copied to *copy_to when given
+  auto reseed_draw = [&](const fe *digest, fe *copy_to, size_t draws, fe *out) -> int {
+    if (quad && draws <= 8) {
+      LAUNCH(ctx, k_quad_reseed_draw, 1, ZKL_QUAD_THREADS, 0, coin.p, digest, copy_to, (int)draws, out);
+      return 0;
+    }
+    if (copy_to) ZKL_CHECK(ctx, cudaMemcpyAsync(copy_to, digest, sizeof(fe), cudaMemcpyDeviceToDevice, st));
+    if (quad) {
+      LAUNCH(ctx, k_quad_reseed_draw, 1, ZKL_QUAD_THREADS, 0, coin.p, digest, (fe *)nullptr, 0, (fe *)nullptr);
+      if (draws) LAUNCH_QUAD(ctx, k_quad_coin_draw, draws, coin.p, (uint64_t)0, (int)draws, out);
+    } else {
+      LAUNCH(ctx, k_coin_reseed, 1, ZKL_COOP_GROUP, 0, coin.p, digest);
+      if (draws) LAUNCH_COOP(ctx, k_coin_draw, draws, coin.p, (uint64_t)0, (int)draws, out);
+    }
+    return 0;
+  };
   int evi = 0;
 #define STAGE_MARK() ZKL_CHECK(ctx, cudaEventRecord(ctx->ev[evi++], st))
   STAGE_MARK();
 
   // ---- 1. public coin seed (agg/fs.rs:69-73)
-  dev_buf<fe> seed_in, coin, tmp;
+  dev_buf<fe> seed_in, tmp;
   ZKL_CHECK(ctx, seed_in.alloc(num_seed)); ZKL_CHECK(ctx, coin.alloc(1)); ZKL_CHECK(ctx, tmp.alloc(8));
   ZKL_CHECK(ctx, cudaMemcpyAsync(seed_in.p, seed_elems, num_seed * sizeof(fe), cudaMemcpyHostToDevice, st));
-  LAUNCH(ctx, k_coin_init, 1, ZKL_COOP_GROUP, 0, seed_in.p, (int)num_seed, coin.p);
+  if (quad) LAUNCH(ctx, k_quad_coin_init, 1, ZKL_QUAD_GROUP, 0, seed_in.p, (int)num_seed, coin.p);
+  else LAUNCH(ctx, k_coin_init, 1, ZKL_COOP_GROUP, 0, seed_in.p, (int)num_seed, coin.p);
   STAGE_MARK();
 
   // ---- 2. trace LDE + commitment (hook new_trace_lde), reseed with the root
   zkl_trace_lde tl;
   ZKL_TRY(trace_commit_dev(ctx, trace_dev, W, n, o, &tl, &ctx->ev[12]));
-  LAUNCH(ctx, k_coin_reseed, 1, ZKL_COOP_GROUP, 0, coin.p, tl.m.nodes.p + 1);
   STAGE_MARK();
 
   // ---- 4/5. composition coefficients (transition then boundary) and constraint evaluation
@@ -529,20 +548,19 @@ static int prove_segment_impl(zkl_ctx *ctx, const fe *trace_dev, size_t W, size_
   dev_buf<fe> cc, ce_ev, flag;
   ZKL_CHECK(ctx, cc.alloc(ncc)); ZKL_CHECK(ctx, ce_ev.alloc(M)); ZKL_CHECK(ctx, flag.alloc(1));
   ZKL_CHECK(ctx, cudaMemsetAsync(flag.p, 0, sizeof(fe), st));
-  LAUNCH(ctx, k_coin_draw, ceil_div(ncc * ZKL_COOP_GROUP, ZKL_COOP_THREADS), ZKL_COOP_THREADS, 0, coin.p, (uint64_t)0, (int)ncc, cc.p);
+  ZKL_TRY(reseed_draw(tl.m.nodes.p + 1, nullptr, ncc, cc.p));   // reseed with the trace root, draw the composition coefficients
   ZKL_TRY(dev_eval_constraints(ctx, tl.m, air, ast, cc.p, ce_ev.p));
   STAGE_MARK();
 
   // ---- 6. constraint commitment (hook build_constraint_commitment), reseed
   zkl_constraint_commitment cmt;
   ZKL_TRY(dev_constraint_commit(ctx, ce_ev.p, n, ce, C, o, cmt.m, flag.p));
-  LAUNCH(ctx, k_coin_reseed, 1, ZKL_COOP_GROUP, 0, coin.p, cmt.m.nodes.p + 1);
   STAGE_MARK();
 
   // ---- 7. OOD point z, evaluations at z and z*g, reseed with hash_elements(cur(z)||quot(z)||next(zg)||quot(zg))
   dev_buf<fe> z, zpow, ood, ood_digest;
   ZKL_CHECK(ctx, z.alloc(1)); ZKL_CHECK(ctx, zpow.alloc(2 * n)); ZKL_CHECK(ctx, ood.alloc(2 * (W + C))); ZKL_CHECK(ctx, ood_digest.alloc(1));
-  LAUNCH(ctx, k_coin_draw, 1, ZKL_COOP_THREADS, 0, coin.p, (uint64_t)0, 1, z.p);
+  ZKL_TRY(reseed_draw(cmt.m.nodes.p + 1, nullptr, 1, z.p));   // reseed with the constraint root, draw z
   fe g_n = host_root_of_unity(ilog2_sz(n));
   LAUNCH(ctx, k_powers_dev, ceil_div(n, 128), 128, 0, z.p, fe_one(), zpow.p, (int)n);
   LAUNCH(ctx, k_powers_dev, ceil_div(n, 128), 128, 0, z.p, g_n, zpow.p + n, (int)n);
@@ -550,14 +568,14 @@ static int prove_segment_impl(zkl_ctx *ctx, const fe *trace_dev, size_t W, size_
   LAUNCH(ctx, k_poly_eval, (unsigned)C, 256, 0, cmt.m.polys.p, (int)n, zpow.p, ood.p + W);
   LAUNCH(ctx, k_poly_eval, (unsigned)W, 256, 0, tl.m.polys.p, (int)n, zpow.p + n, ood.p + W + C);
   LAUNCH(ctx, k_poly_eval, (unsigned)C, 256, 0, cmt.m.polys.p, (int)n, zpow.p + n, ood.p + 2 * W + C);
-  LAUNCH(ctx, k_hash_elements_single, 1, ZKL_COOP_GROUP, 0, ood.p, (int)(2 * (W + C)), ood_digest.p);
-  LAUNCH(ctx, k_coin_reseed, 1, ZKL_COOP_GROUP, 0, coin.p, ood_digest.p);
+  if (quad) LAUNCH(ctx, k_quad_hash_elements_single, 1, ZKL_QUAD_GROUP, 0, ood.p, (int)(2 * (W + C)), ood_digest.p);
+  else LAUNCH(ctx, k_hash_elements_single, 1, ZKL_COOP_GROUP, 0, ood.p, (int)(2 * (W + C)), ood_digest.p);
   STAGE_MARK();
 
   // ---- 8. DEEP coefficients + composition over the LDE domain
   dev_buf<fe> dc, az, deep;
   ZKL_CHECK(ctx, dc.alloc(W + C)); ZKL_CHECK(ctx, az.alloc(2)); ZKL_CHECK(ctx, deep.alloc(N));
-  LAUNCH(ctx, k_coin_draw, ceil_div((W + C) * ZKL_COOP_GROUP, ZKL_COOP_THREADS), ZKL_COOP_THREADS, 0, coin.p, (uint64_t)0, (int)(W + C), dc.p);
+  ZKL_TRY(reseed_draw(ood_digest.p, nullptr, W + C, dc.p));   // reseed with the OOD digest, draw the DEEP coefficients
   LAUNCH(ctx, k_deep_consts, 1, 32, 0, ood.p, dc.p, (int)W, (int)C, az.p);
   LAUNCH(ctx, k_deep, ceil_div(N, 256), 256, 0, tl.m.lde.p, cmt.m.lde.p, N, (int)n, (int)B, (int)W, (int)C, dc.p, az.p, z.p, g_n, tN->wpow, deep.p);
   STAGE_MARK();
@@ -573,11 +591,10 @@ static int prove_segment_impl(zkl_ctx *ctx, const fe *trace_dev, size_t W, size_
     size_t half = nd * B / 2;
     ZKL_CHECK(ctx, f_leaves[d].alloc(half)); ZKL_CHECK(ctx, f_nodes[d].alloc(half)); ZKL_CHECK(ctx, f_ev[d + 1].alloc(half));
     if (half >= (size_t)ctx->bulk_threshold && ctx->hash_path == 0) LAUNCH_TC(ctx, k_tc_fri_leaves, half, cur_ev, (int)nd, (int)B, f_leaves[d].p);
-    else LAUNCH(ctx, k_fri_leaves, ceil_div(half * ZKL_COOP_GROUP, ZKL_COOP_THREADS), ZKL_COOP_THREADS, 0, cur_ev, (int)nd, (int)B, f_leaves[d].p);
+    else if (quad) LAUNCH_QUAD(ctx, k_quad_fri_leaves, half, cur_ev, (int)nd, (int)B, f_leaves[d].p);
+    else LAUNCH_COOP(ctx, k_fri_leaves, half, cur_ev, (int)nd, (int)B, f_leaves[d].p);
     ZKL_TRY(dev_merkle(ctx, f_leaves[d].p, f_nodes[d].p, half));
-    ZKL_CHECK(ctx, cudaMemcpyAsync(fri_roots.p + d, f_nodes[d].p + 1, sizeof(fe), cudaMemcpyDeviceToDevice, st));
-    LAUNCH(ctx, k_coin_reseed, 1, ZKL_COOP_GROUP, 0, coin.p, f_nodes[d].p + 1);
-    LAUNCH(ctx, k_coin_draw, 1, ZKL_COOP_THREADS, 0, coin.p, (uint64_t)0, 1, alphas.p + d);
+    ZKL_TRY(reseed_draw(f_nodes[d].p + 1, fri_roots.p + d, 1, alphas.p + d));   // commit the layer root, draw alpha
     LAUNCH(ctx, k_fri_fold, ceil_div(half, 256), 256, 0, cur_ev, (int)nd, (int)B, (int)d, alphas.p + d, tN->wpow, N, g_inv_half, f_ev[d + 1].p);
     cur_ev = f_ev[d + 1].p;
     nd /= 2;
@@ -587,8 +604,9 @@ static int prove_segment_impl(zkl_ctx *ctx, const fe *trace_dev, size_t W, size_
   if (nd * B > 256) { ctx->set_error("FRI remainder domain too large"); return 1; }
   LAUNCH(ctx, k_fri_remainder, 1, 32 > (int)nd ? 32 : (int)nd, 0, cur_ev, (int)nd, (int)B, tN->wpow, N, fe_inv(fe_from_u64(3)),
          fe_inv(fe_from_u64(nd * B)), rem_rev.p);
-  LAUNCH(ctx, k_hash_elements_single, 1, ZKL_COOP_GROUP, 0, rem_rev.p, (int)rem_len, fri_roots.p + nl);
-  LAUNCH(ctx, k_coin_reseed, 1, ZKL_COOP_GROUP, 0, coin.p, fri_roots.p + nl);
+  if (quad) LAUNCH(ctx, k_quad_hash_elements_single, 1, ZKL_QUAD_GROUP, 0, rem_rev.p, (int)rem_len, fri_roots.p + nl);
+  else LAUNCH(ctx, k_hash_elements_single, 1, ZKL_COOP_GROUP, 0, rem_rev.p, (int)rem_len, fri_roots.p + nl);
+  ZKL_TRY(reseed_draw(fri_roots.p + nl, nullptr, 0, nullptr));
   STAGE_MARK();
 
   // ---- 10. grinding (smallest nonce >= 1)
@@ -624,7 +642,8 @@ static int prove_segment_impl(zkl_ctx *ctx, const fe *trace_dev, size_t W, size_
   // ---- 11. query positions, openings, serialization
   dev_buf<uint32_t> pos_dev, pos_cnt;
   ZKL_CHECK(ctx, pos_dev.alloc(256)); ZKL_CHECK(ctx, pos_cnt.alloc(1));
-  LAUNCH(ctx, k_draw_positions, 1, ZKL_COOP_THREADS, 0, coin.p, nonce.p, (int)o->num_queries, (uint32_t)(N - 1), pos_dev.p, pos_cnt.p);
+  if (quad) LAUNCH(ctx, k_quad_draw_positions, 1, ZKL_QUAD_THREADS, 0, coin.p, nonce.p, (int)o->num_queries, (uint32_t)(N - 1), pos_dev.p, pos_cnt.p);
+  else LAUNCH(ctx, k_draw_positions, 1, ZKL_COOP_THREADS, 0, coin.p, nonce.p, (int)o->num_queries, (uint32_t)(N - 1), pos_dev.p, pos_cnt.p);
   uint32_t pos_h[256], cnt_h = 0;
   std::vector<fe> ood_h(2 * (W + C)), roots_h(nl + 1), rem_h(rem_len);
   fe troot, croot, z_h, flag_h;
@@ -858,8 +877,12 @@ extern "C" int zkl_imad_peak(zkl_ctx *ctx, double *wide_macs_per_s) {
   return 0;
 }
 extern "C" int zkl_set_bulk_threshold(zkl_ctx *ctx, long sponges) { ctx->bulk_threshold = sponges; return 0; }
+extern "C" int zkl_set_coop_path(zkl_ctx *ctx, int path) {
+  if (path != 0 && path != 1) { ctx->set_error("coop path must be 0 (64-thread groups) or 1 (16-thread groups)"); return 1; }
+  ctx->coop_path = path; return 0;
+}
 extern "C" int zkl_set_ntt_path(zkl_ctx *ctx, int path) {
-  if (path != 0 && path != 1) { ctx->set_error("ntt path must be 0 (tensor-core radix-16 LDE) or 1 (integer pipe)"); return 1; }
+  if (path < 0 || path > 2) { ctx->set_error("ntt path must be 0 (tensor-core radix-16 LDE), 1 (integer pipe) or 2 (tensor-core, separate coset shift)"); return 1; }
   ctx->ntt_path = path; return 0;
 }
 extern "C" int zkl_set_hash_path(zkl_ctx *ctx, int path) {
@@ -869,7 +892,7 @@ extern "C" int zkl_set_hash_path(zkl_ctx *ctx, int path) {
 }
 
 // permutation throughput probes on device-resident data: kind 0 = thread-per-state kernel, 1 = cooperative kernel,
-// 2 = tensor-core MDS kernel
+// 2 = tensor-core MDS kernel, 3 = 64-thread groups (kernels_quad.cuh)
 __global__ void __launch_bounds__(ZKL_COOP_THREADS) k_coop_permute_batch(fe *states, size_t count) {
   __shared__ fe s_xch[(ZKL_COOP_THREADS / ZKL_COOP_GROUP) * 24];
   size_t g = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) / ZKL_COOP_GROUP;
@@ -878,6 +901,14 @@ __global__ void __launch_bounds__(ZKL_COOP_THREADS) k_coop_permute_batch(fe *sta
   fe st = l < 12 ? ld_fe(states + 12 * gi + l) : fe_zero();
   coop_permute(st, l, s_xch + (threadIdx.x / ZKL_COOP_GROUP) * 24, 0xFFFFu << (threadIdx.x & 16));
   if (g < count && l < 12) st_fe(states + 12 * g + l, st);
+}
+__global__ void __launch_bounds__(ZKL_QUAD_THREADS) k_quad_permute_batch(fe *states, size_t count) {
+  __shared__ fe s_xch[(ZKL_QUAD_THREADS / ZKL_QUAD_GROUP) * 24];
+  const quad_ctx q = quad_setup(s_xch);
+  size_t g = quad_index(), gi = g < count ? g : count - 1;
+  fe st = ld_fe(states + 12 * gi + q.l);
+  quad_permute(st, q);
+  if (g < count && q.writer) st_fe(states + 12 * g + q.l, st);
 }
 extern "C" int zkl_bench_permute(zkl_ctx *ctx, int kind, size_t count, int iters, float *ms_per_iter) {
   ZKL_TRY(need_suite(ctx));
@@ -889,6 +920,7 @@ extern "C" int zkl_bench_permute(zkl_ctx *ctx, int kind, size_t count, int iters
     for (int i = 0; i < iters; i++) {
       if (kind == 2) LAUNCH_TC(ctx, k_tc_permute_batch, count, d.p, count);
       else if (kind == 0) LAUNCH(ctx, k_permute_batch, ceil_div(count, ZKL_HASH_THREADS), ZKL_HASH_THREADS, 0, d.p, count);
+      else if (kind == 3) LAUNCH_QUAD(ctx, k_quad_permute_batch, count, d.p, count);
       else LAUNCH(ctx, k_coop_permute_batch, ceil_div(count * ZKL_COOP_GROUP, ZKL_COOP_THREADS), ZKL_COOP_THREADS, 0, d.p, count);
     }
     ZKL_TRY(zkl_timer_stop(ctx, &ms));

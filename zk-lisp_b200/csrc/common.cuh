@@ -46,10 +46,13 @@ struct zkl_ctx {
   long bulk_threshold = 1024;
   // bulk hashing path: 0 = tensor-core MDS (tcperm.cuh, the default), 1 = integer-pipe thread-per-sponge kernels
   int hash_path = 0;
-  int ntt_path = 0;    // 4096-row coset LDE: 0 = radix-16 stages on the tensor cores (kernels_tcntt.cuh), 1 = radix-2 in shared memory
+  int coop_path = 0;   // small sponge batches: 0 = 64-thread groups (kernels_quad.cuh, lowest latency), 1 = 16-thread groups (kernels_hash.cuh)
+  int ntt_path = 0;    // 4096-row coset LDE: 0 = radix-16 stages on the tensor cores, coset shift folded into the matrix (kernels_tcntt.cuh v2),
+                       // 1 = radix-2 in shared memory, 2 = tensor cores with a separate coset-shift product (v1)
   bool tc_ok = true;   // the loaded MDS constants satisfy the tensor-core epilogue's accumulator bound
   std::map<size_t, domain_tables> tables;  // by N
   std::map<size_t, fe *> opow;             // GENERATOR^j tables by n
+  std::map<size_t, std::pair<void *, void *>> lde16;   // tensor-core LDE constants (byte matrices, twiddles) by (blowup, direction)
   std::map<size_t, fe *> periodic;         // periodic-column tables by (n << 8 | ce)
   std::vector<cudaEvent_t> ev;             // stage timing events
   void set_error(const std::string &e) { err = e; }

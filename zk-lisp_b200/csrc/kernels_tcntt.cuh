@@ -154,3 +154,170 @@ __global__ void __launch_bounds__(NTT16_THREADS, 1) k_tc_lde4096(const fe *polys
   __syncthreads();
   if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
 }
+
+
+// ================================================================= version 2: coset shift folded into the constant matrix
+// x[j] = a_j s^j with s = offset * w_N^k; for j = jA + 16 jC + 256 jD:  s^j = s^(jA + 16 jC) * (s^256)^jD.  The second
+// factor depends on the stage-1 INPUT index only, so stage 1 of coset k uses the constant matrix
+//   B_k[(iD,u),(jD,v)] = byte_u((s^256)^jD * w16^(iD jD) * 2^(8v) mod p)
+// on the RAW coefficients, and the first factor joins the stage-1 output twiddle: tw0_k[iD][m1] = s^(m1) * w_256^(iD jC),
+// m1 = jA + 16 jC. (Shared memory holds ONE matrix, so stages 2 and 3 run with B_k as well; the factors (s^256)^jC and
+// (s^256)^jA this adds are constants of m1 and are divided out of tw0_k.) One of the three modular products per element disappears, and because the MMA A operand is now the
+// coefficient column itself the next column is fetched by TMA bulk copies (16 x 4 KB into the chunk layout) while the
+// current one is in its last stage. For the inverse transform B = 4096^-1 * w16^(-iD jD) (the final scaling disappears too)
+// and tw0[iD][m1] = w_256^(-iD jC). A CTA serves ONE coset (k = blockIdx.x % blowup): B_k is loaded once.
+//
+// consts layout per coset k: bmat[k][4096] uint4 (shared-memory image, as g_dft16_bytes), tw0[k][16][256] fe.
+__global__ void k_build_lde16_consts(const fe *__restrict__ scale /* [blowup][4096] or null (inverse) */, const fe *__restrict__ wpow, size_t N,
+                                     int blowup, bool inverse, fe factor, uint4 *__restrict__ bmat, fe *__restrict__ tw0) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= blowup * 4096) return;
+  const int k = t >> 12, e = t & 4095;
+  const size_t s16 = N / 16, s256 = N / 256;
+  {  // B image entry (chunk j = jD, row = 16 i + u)
+    const int j = e >> 8, row = e & 255, i = row >> 4, u = row & 15;
+    size_t ex = (size_t)((i * j) & 15) * s16; if (inverse && ex) ex = N - ex;
+    fe cur = ld_fe(wpow + ex);
+    if (scale) cur = fe_mul(cur, ld_fe(scale + (size_t)k * NTT16_N + 256 * j));
+    if (inverse) cur = fe_mul(cur, factor);
+    const fe two8 = fe_from_u64(256);
+    uint32_t out[4] = {0, 0, 0, 0};
+    for (int b = 0; b < 16; b++) {
+      uint32_t limb = u < 4 ? cur.l[0] : (u < 8 ? cur.l[1] : (u < 12 ? cur.l[2] : cur.l[3]));
+      out[b >> 2] |= ((limb >> (8 * (u & 3))) & 0xFF) << (8 * (b & 3));
+      cur = fe_mul(cur, two8);
+    }
+    bmat[(size_t)k * 4096 + e] = make_uint4(out[0], out[1], out[2], out[3]);
+  }
+  {  // tw0[k][iD][m1]. B_k also serves stages 2 and 3 (one matrix fits shared memory), whose input indices are jC and jA:
+     // they pick up (s^256)^jC and (s^256)^jA — resp. 4096^-1 twice — which this twiddle takes out again.
+    const int iD = e >> 8, m1 = e & 255, jA = m1 & 15, jC = m1 >> 4;
+    size_t ex = (size_t)(iD * jC) * s256; if (inverse && ex) ex = N - ex;
+    fe v = ld_fe(wpow + ex);
+    if (scale) {
+      v = fe_mul(v, ld_fe(scale + (size_t)k * NTT16_N + m1));
+      v = fe_mul(v, fe_pow(fe_inv(ld_fe(scale + (size_t)k * NTT16_N + 256)), (uint64_t)(jA + jC)));
+    }
+    if (inverse) { fe f1 = fe_inv(factor); v = fe_mul(v, fe_mul(f1, f1)); }
+    st_fe(tw0 + (size_t)k * 4096 + e, v);
+  }
+}
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+
+// grid >= blowup CTAs; CTA b serves coset b % blowup and every (gridDim.x / blowup)-th column of it.
+__global__ void __launch_bounds__(NTT16_THREADS, 1) k_tc_lde4096_v2(const fe *polys, int ncols, int blowup, const uint4 *__restrict__ bmat,
+                                                                   const fe *__restrict__ tw0, const fe *__restrict__ wpow, fe *out, bool inverse, bool use_tma) {
+  extern __shared__ unsigned char ntt_smem[];
+  const uint32_t base = (smem_u32(ntt_smem) + 127u) & ~127u;
+  unsigned char *gen = ntt_smem + (base - smem_u32(ntt_smem));
+  const uint32_t b_tile = base, buf0 = base + NTT16_B_BYTES, buf1 = buf0 + NTT16_BUF_BYTES, ctl = buf1 + NTT16_BUF_BYTES;
+  uint32_t *ctl_gen = reinterpret_cast<uint32_t *>(gen + NTT16_B_BYTES + 2 * NTT16_BUF_BYTES);
+  const int k = blockIdx.x % blowup, rank = blockIdx.x / blowup;
+  const int peers = (gridDim.x - k + blowup - 1) / blowup;      // CTAs serving coset k
+  {
+    uint4 *bdst = reinterpret_cast<uint4 *>(gen);
+    const uint4 *bsrc = bmat + (size_t)k * 4096;
+    for (int i = threadIdx.x; i < NTT16_B_BYTES / 16; i += NTT16_THREADS) bdst[i] = bsrc[i];
+  }
+  if (threadIdx.x < 32) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ctl + 64), "n"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (threadIdx.x == 32) {
+    mbar_init(ctl, 1); mbar_init(ctl + 8, 1); mbar_init(ctl + 16, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = ctl_gen[16];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool is_mma = warp >= 16;
+  const int tile = (warp >> 3) & 1, half = (warp >> 2) & 1;
+  const int m = 128 * tile + 32 * (warp & 3) + lane;
+  const uint32_t tmem_mine = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + 256 * tile + 128 * half;
+  const size_t N = (size_t)NTT16_N * blowup;
+  const size_t s4096 = N / NTT16_N;
+  const fe *tw0k = tw0 + (size_t)k * 4096;
+  uint32_t phase = 0, ld_phase = 0;
+  uint32_t src = buf0, dst = buf1;
+  // column c as 16 chunks of 256 coefficients: chunk jD -> src + jD * PITCH (instance m1 = j & 255 at 16 B pitch)
+  auto fetch = [&](int c, uint32_t to) {
+    mbar_expect_tx(ctl + 16, NTT16_N * 16);
+    const fe *poly = polys + (size_t)c * NTT16_N;
+#pragma unroll 1
+    for (int jD = 0; jD < 16; jD++) bulk_g2s(to + (uint32_t)jD * NTT16_PITCH, poly + 256 * jD, 4096, ctl + 16);
+  };
+  if (use_tma && is_mma && lane == 0 && rank < ncols) fetch(rank, src);
+  for (int c = rank; c < ncols; c += peers) {
+    if (!use_tma && !is_mma) {   // debug path: generic loads
+      const fe *poly = polys + (size_t)c * NTT16_N;
+      for (int q = 0; q < 8; q++) {
+        int j = threadIdx.x + 512 * q;
+        fe v = ld_fe(poly + j);
+        sts_u4(src + (uint32_t)(j >> 8) * NTT16_PITCH + (uint32_t)(j & 255) * 16, v.l[0], v.l[1], v.l[2], v.l[3]);
+      }
+    }
+#pragma unroll 1
+    for (int stage = 0; stage < 3; stage++) {
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncthreads();
+      if (is_mma) {
+        tc_fence_after();
+        if (lane == 0) {
+          if (use_tma && stage == 0) mbar_wait(ctl + 16, ld_phase);   // the column has landed (async proxy -> async proxy: no fence)
+#pragma unroll
+          for (int t = 0; t < 2; t++) {
+            const uint64_t adesc = tc_smem_desc(src + t * 2048, NTT16_PITCH, 128);
+            const uint64_t bdesc = tc_smem_desc(b_tile, 4096, 128);
+#pragma unroll
+            for (int kk = 0; kk < 8; kk++)
+              tc_mma_i8(tmem_base + 256 * t, adesc + (uint64_t)((2 * kk * NTT16_PITCH) >> 4), bdesc + (uint64_t)((2 * kk * 4096) >> 4), NTT16_IDESC, kk > 0);
+            tc_commit(ctl + 8 * t);
+          }
+          // `dst` is idle in the last stage (results go to HBM; its last readers were the MMAs of stage 2): prefetch into it
+          if (use_tma && stage == 2 && c + peers < ncols) fetch(c + peers, dst);
+        }
+        __syncwarp();
+      } else {
+        mbar_wait(ctl + 8 * tile, phase);
+        tc_fence_after();
+        uint32_t acc[2][16];
+        tmem_ld16(tmem_mine, acc[0]);
+#pragma unroll 2
+        for (int q = 0; q < 8; q++) {
+          tmem_wait_ld(acc[q & 1]);
+          if (q < 7) tmem_ld16(tmem_mine + 16 * (q + 1), acc[(q + 1) & 1]);
+          const int i = 8 * half + q;
+          fe v = tc_epilogue_plain(acc[q & 1]);
+          if (stage == 0) {          // m = jA + 16 jC, i = iD
+            const int jA = m & 15, jC = m >> 4;
+            v = lazy_mul(v, ld_fe(tw0k + 256 * i + m));
+            sts_u4(dst + (uint32_t)jC * NTT16_PITCH + (uint32_t)(jA + 16 * i) * 16, v.l[0], v.l[1], v.l[2], v.l[3]);
+          } else if (stage == 1) {   // m = jA + 16 iD, i = iC
+            const int jA = m & 15, iB = 16 * i + (m >> 4);
+            { size_t e = (size_t)(iB * jA) * s4096; if (inverse && e) e = N - e; v = lazy_mul(v, ld_fe(wpow + e)); }
+            sts_u4(dst + (uint32_t)jA * NTT16_PITCH + (uint32_t)iB * 16, v.l[0], v.l[1], v.l[2], v.l[3]);
+          } else {                   // m = iB, i = iA
+            st_fe(out + ((size_t)c * blowup + k) * NTT16_N + 256 * i + m, lazy_canon(v));
+          }
+        }
+      }
+      phase ^= 1;
+      uint32_t t = src; src = dst; dst = t;
+    }
+    ld_phase ^= 1;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+}

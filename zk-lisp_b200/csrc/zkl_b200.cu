@@ -10,6 +10,7 @@
 #include "kernels_air.cuh"
 #include "kernels_hash.cuh"
 #include "kernels_ntt.cuh"
+#include "kernels_quad.cuh"
 #include "kernels_stark.cuh"
 #include "kernels_tc.cuh"
 #include "kernels_tcntt.cuh"
@@ -27,6 +28,10 @@ static std::mutex g_suite_mutex;
 #define LAUNCH_TC(ctx, kernel, sponges, ...)                                                                        \
   LAUNCH(ctx, kernel, std::min<size_t>(((size_t)(sponges) + TC_CTA_SPONGES - 1) / TC_CTA_SPONGES, (size_t)(ctx)->tc_grid_cap), TC_THREADS, \
          TC_SMEM_BYTES, __VA_ARGS__)
+
+// low-latency sponge kernels: one 64-thread group per sponge (kernels_quad.cuh) or the older 16-thread groups (coop_path 1)
+#define LAUNCH_QUAD(ctx, kernel, sponges, ...) LAUNCH(ctx, kernel, ceil_div((size_t)(sponges) * ZKL_QUAD_GROUP, ZKL_QUAD_THREADS), ZKL_QUAD_THREADS, 0, __VA_ARGS__)
+#define LAUNCH_COOP(ctx, kernel, sponges, ...) LAUNCH(ctx, kernel, ceil_div((size_t)(sponges) * ZKL_COOP_GROUP, ZKL_COOP_THREADS), ZKL_COOP_THREADS, 0, __VA_ARGS__)
 
 // ------------------------------------------------------------------------------------------------
 // context
@@ -56,6 +61,8 @@ extern "C" int zkl_ctx_create(int device, zkl_ctx **out) {
   c->num_sms = prop.multiProcessorCount;
   c->tc_grid_cap = c->num_sms;
   if (const char *e = getenv("ZKL_TC_GRID_CAP")) { int v = atoi(e); if (v > 0 && v <= c->num_sms) c->tc_grid_cap = v; }   // experiment knob
+  if (const char *e = getenv("ZKL_COOP_PATH")) c->coop_path = atoi(e) == 1 ? 1 : 0;   // experiment knobs (A/B runs of bench.py)
+  if (const char *e = getenv("ZKL_NTT_PATH")) { int v = atoi(e); if (v >= 0 && v <= 2) c->ntt_path = v; }
   if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) {
     g_create_error = cudaGetErrorString(e); delete c; return 1;
   }
@@ -76,6 +83,7 @@ extern "C" int zkl_ctx_create(int device, zkl_ctx **out) {
   cudaFuncSetAttribute(k_interpolate, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
   cudaFuncSetAttribute(k_lde, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
   cudaFuncSetAttribute(k_tc_lde4096, cudaFuncAttributeMaxDynamicSharedMemorySize, NTT16_SMEM_BYTES);
+  cudaFuncSetAttribute(k_tc_lde4096_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, NTT16_SMEM_BYTES);
   cudaFuncSetAttribute(k_ntt_pass1, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
   cudaFuncSetAttribute(k_ntt_pass2, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
   cudaFuncSetAttribute(k_tc_permute_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
@@ -114,6 +122,7 @@ extern "C" void zkl_ctx_destroy(zkl_ctx *ctx) {
   for (auto &kv : ctx->tables) { cudaFree(kv.second.wpow); }
   for (auto &kv : ctx->opow) cudaFree(kv.second);
   for (auto &kv : ctx->periodic) cudaFree(kv.second);
+  for (auto &kv : ctx->lde16) { cudaFree(kv.second.first); cudaFree(kv.second.second); }
   for (auto e : ctx->ev) cudaEventDestroy(e);
   cudaStreamDestroy(ctx->stream);
   if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
@@ -202,12 +211,36 @@ static ntt_split split_for(size_t n) {
 }
 static const size_t NTT_SINGLE_PASS_MAX = 8192, NTT_MAX = (size_t)1 << 24;
 
+// constants of the v2 tensor-core transform (kernels_tcntt.cuh): per-coset byte matrices and stage-1 twiddles
+static int get_lde16_consts(zkl_ctx *ctx, size_t blowup, bool inverse, const fe *scale, const domain_tables *t, fe factor, const uint4 **bmat, const fe **tw0) {
+  const size_t key = blowup * 2 + (inverse ? 1 : 0);
+  auto it = ctx->lde16.find(key);
+  if (it == ctx->lde16.end()) {
+    void *b, *w;
+    ZKL_CHECK(ctx, cudaMalloc(&b, blowup * 4096 * sizeof(uint4)));
+    ZKL_CHECK(ctx, cudaMalloc(&w, blowup * 4096 * sizeof(fe)));
+    LAUNCH(ctx, k_build_lde16_consts, ceil_div(blowup * 4096, 256), 256, 0, scale, t->wpow, t->N, (int)blowup, inverse, factor, (uint4 *)b, (fe *)w);
+    it = ctx->lde16.emplace(key, std::make_pair(b, w)).first;
+  }
+  *bmat = (const uint4 *)it->second.first; *tw0 = (const fe *)it->second.second;
+  return 0;
+}
+static unsigned lde16_grid(const zkl_ctx *ctx, size_t ncols, size_t blowup) {
+  return (unsigned)std::min<size_t>(ncols * blowup, std::max<size_t>((size_t)ctx->num_sms, blowup));
+}
+
 // cols (ncols x n, evaluations over <w_n>) -> coefficients, in place or out of place
 static int dev_interpolate(zkl_ctx *ctx, const fe *src, fe *dst, size_t ncols, size_t n) {
   if (n > NTT_MAX || (n & (n - 1)) || n < 2) { ctx->set_error("trace length must be a power of two in [2, 2^24]"); return 1; }
   domain_tables *t; ZKL_TRY(get_tables(ctx, n, &t));
   fe n_inv = fe_inv(fe_from_u64(n));
-  if (n == NTT16_N && ctx->ntt_path == 0) {   // inverse radix-16 stages on the tensor cores (kernels_tcntt.cuh)
+  if (n == NTT16_N && ctx->ntt_path == 0) {   // inverse radix-16 stages on the tensor cores, 1/n folded into the matrix (kernels_tcntt.cuh v2)
+    const uint4 *bmat; const fe *tw0;
+    ZKL_TRY(get_lde16_consts(ctx, 1, true, nullptr, t, n_inv, &bmat, &tw0));
+    LAUNCH(ctx, k_tc_lde4096_v2, lde16_grid(ctx, ncols, 1), NTT16_THREADS, NTT16_SMEM_BYTES, src, (int)ncols, 1, bmat, tw0, t->wpow, dst, true, getenv("ZKL_LDE_NO_TMA") == nullptr);
+    return 0;
+  }
+  if (n == NTT16_N && ctx->ntt_path == 2) {   // v1: separate 1/n product
     LAUNCH(ctx, k_tc_lde4096, (unsigned)std::min<size_t>(ncols, (size_t)ctx->num_sms), NTT16_THREADS, NTT16_SMEM_BYTES, src, (int)ncols, 1, (const fe *)nullptr,
            t->wpow, dst, true, n_inv);
     return 0;
@@ -240,7 +273,13 @@ static int dev_lde(zkl_ctx *ctx, const fe *polys, fe *out, size_t ncols, size_t 
     LAUNCH(ctx, k_lde_scale_table, ceil_div(N, 256), 256, 0, opow, t->wpow, N, (int)n, (int)blowup, p);
     it = ctx->opow.emplace(key, p).first;
   }
-  if (n == NTT16_N && ctx->ntt_path == 0) {   // radix-16 stages on the tensor cores (kernels_tcntt.cuh)
+  if (n == NTT16_N && ctx->ntt_path == 0) {   // radix-16 stages on the tensor cores, coset shift folded into the matrix (kernels_tcntt.cuh v2)
+    const uint4 *bmat; const fe *tw0;
+    ZKL_TRY(get_lde16_consts(ctx, blowup, false, it->second, t, fe_zero(), &bmat, &tw0));
+    LAUNCH(ctx, k_tc_lde4096_v2, lde16_grid(ctx, ncols, blowup), NTT16_THREADS, NTT16_SMEM_BYTES, polys, (int)ncols, (int)blowup, bmat, tw0, t->wpow, out, false, getenv("ZKL_LDE_NO_TMA") == nullptr);
+    return 0;
+  }
+  if (n == NTT16_N && ctx->ntt_path == 2) {   // v1: separate coset-shift product
     LAUNCH(ctx, k_tc_lde4096, (unsigned)std::min<size_t>(ncols * blowup, (size_t)ctx->num_sms), NTT16_THREADS, NTT16_SMEM_BYTES, polys, (int)ncols, (int)blowup,
            it->second, t->wpow, out, false, fe_zero());
     return 0;
@@ -270,14 +309,16 @@ static int dev_hash_partitions(zkl_ctx *ctx, const fe *lde, size_t ncols, size_t
   bool bulk = sponges >= (size_t)ctx->bulk_threshold;
   if (bulk && ctx->hash_path == 0) LAUNCH_TC(ctx, k_tc_hash_rows, sponges, lde, N, n, (int)blowup, (int)ncols, (int)ps, (int)nchunks, out);
   else if (bulk) LAUNCH(ctx, k_hash_rows, ceil_div(sponges, ZKL_HASH_THREADS), ZKL_HASH_THREADS, 0, lde, N, n, (int)blowup, (int)ncols, (int)ps, (int)nchunks, out);
-  else LAUNCH(ctx, k_coop_hash_rows, ceil_div(sponges * ZKL_COOP_GROUP, ZKL_COOP_THREADS), ZKL_COOP_THREADS, 0, lde, N, n, (int)blowup, (int)ncols, (int)ps, (int)nchunks, out);
+  else if (ctx->coop_path == 0) LAUNCH_QUAD(ctx, k_quad_hash_rows, sponges, lde, N, n, (int)blowup, (int)ncols, (int)ps, (int)nchunks, out);
+  else LAUNCH_COOP(ctx, k_coop_hash_rows, sponges, lde, N, n, (int)blowup, (int)ncols, (int)ps, (int)nchunks, out);
   return 0;
 }
 // leaves[r] = merge_many(parts[0][r0 + r], ..., parts[nchunks-1][r0 + r]), r < rows (agg/child.rs:1040-1044); parts[q] at parts + q*stride
 static int dev_merge_partitions(zkl_ctx *ctx, const fe *parts, size_t stride, size_t rows, size_t nchunks, fe *leaves) {
   if (rows >= (size_t)ctx->bulk_threshold && ctx->hash_path == 0) LAUNCH_TC(ctx, k_tc_merge_many_rows, rows, parts, stride, rows, (int)nchunks, leaves);
   else if (rows >= (size_t)ctx->bulk_threshold) LAUNCH(ctx, k_merge_many_rows, ceil_div(rows, ZKL_HASH_THREADS), ZKL_HASH_THREADS, 0, parts, stride, rows, (int)nchunks, leaves);
-  else LAUNCH(ctx, k_coop_merge_many_rows, ceil_div(rows * ZKL_COOP_GROUP, ZKL_COOP_THREADS), ZKL_COOP_THREADS, 0, parts, stride, rows, (int)nchunks, leaves);
+  else if (ctx->coop_path == 0) LAUNCH_QUAD(ctx, k_quad_merge_many_rows, rows, parts, stride, rows, (int)nchunks, leaves);
+  else LAUNCH_COOP(ctx, k_coop_merge_many_rows, rows, parts, stride, rows, (int)nchunks, leaves);
   return 0;
 }
 static int dev_hash_rows(zkl_ctx *ctx, const fe *lde, size_t ncols, size_t n, size_t blowup, const zkl_options *o, fe *leaves,
@@ -297,7 +338,13 @@ static int dev_merkle(zkl_ctx *ctx, const fe *leaves, fe *nodes, size_t count) {
   for (size_t lvl = count / 2; lvl >= 1; lvl >>= 1) {
     if (lvl >= (size_t)ctx->bulk_threshold && ctx->hash_path == 0) LAUNCH_TC(ctx, k_tc_merkle_level, lvl, in, nodes + lvl, lvl);
     else if (lvl >= (size_t)ctx->bulk_threshold) LAUNCH(ctx, k_merkle_level, ceil_div(lvl, ZKL_HASH_THREADS), ZKL_HASH_THREADS, 0, in, nodes + lvl, lvl);
-    else LAUNCH(ctx, k_coop_merkle_level, ceil_div(lvl * ZKL_COOP_GROUP, ZKL_COOP_THREADS), ZKL_COOP_THREADS, 0, in, nodes + lvl, lvl);
+    else if (ctx->coop_path == 0) {
+      if (lvl <= ZKL_QUAD_MAX_GROUPS) {   // the remaining levels in one launch
+        LAUNCH(ctx, k_quad_tree_top, 1, (unsigned)(lvl * ZKL_QUAD_GROUP), 0, in, nodes, (int)lvl);
+        break;
+      }
+      LAUNCH_QUAD(ctx, k_quad_merkle_level, lvl, in, nodes + lvl, lvl);
+    } else LAUNCH_COOP(ctx, k_coop_merkle_level, lvl, in, nodes + lvl, lvl);
     in = nodes + lvl;
   }
   return 0;
