@@ -264,8 +264,9 @@ int zkl_set_bulk_threshold(zkl_ctx *ctx, long sponges);
 /* bulk hashing path: 0 = tensor-core MDS product (tcgen05 kind::i8, default), 1 = integer-pipe thread-per-sponge
  * kernels. Both are bit-identical; 1 exists for A/B measurements and parity tests. */
 int zkl_set_hash_path(zkl_ctx *ctx, int path);
-/* Small sponge batches (tree levels, FRI layer tails, the Fiat-Shamir coin, the OOD digest): 0 = 64-thread groups
- * (lowest latency, default), 1 = 16-thread groups. Bit-identical; 1 exists for A/B measurements and parity tests. */
+/* Small sponge batches (tree levels, FRI layer tails, the Fiat-Shamir coin, the OOD digest): 1 = 16-thread groups per
+ * sponge (least SM time: a pool of provers sharing the GPU), 2 = 64-thread groups (lowest latency: a lone prover),
+ * 0 = choose by the number of contexts alive on the device (default; fewer than 4 -> 2). Bit-identical. */
 int zkl_set_coop_path(zkl_ctx *ctx, int path);
 /* 4096-row coset LDE: 0 = radix-16 stages on the tensor cores with the coset shift folded into the constant matrix
  * (default), 1 = radix-2 butterflies in shared memory, 2 = tensor cores with a separate coset-shift product.

@@ -34,7 +34,7 @@ def oracle():
 #   tc-forced tensor-core kernels for every bulk call site (threshold 1): small test sizes reach tcperm.cuh
 #   int-pipe  the integer-pipe thread-per-sponge kernels for every bulk call site, 16-thread groups for the coin
 #   coop16    like default with the 16-thread cooperative kernels instead of the 64-thread groups
-HASH_MODES = {"default": (None, 0, 0), "tc-forced": (1, 0, 0), "int-pipe": (1, 1, 1), "coop16": (None, 0, 1)}
+HASH_MODES = {"default": (None, 0, 2), "tc-forced": (1, 0, 2), "int-pipe": (1, 1, 1), "coop16": (None, 0, 1)}
 
 
 @pytest.fixture(scope="session", params=list(HASH_MODES))

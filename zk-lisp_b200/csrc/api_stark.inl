@@ -507,21 +507,17 @@ static int prove_segment_impl(zkl_ctx *ctx, const fe *trace_dev, size_t W, size_
   fe *opow; ZKL_TRY(get_offset_powers(ctx, n, &opow)); (void)opow;
   cudaStream_t st = ctx->stream;
   dev_buf<fe> coin;
-  const bool quad = ctx->coop_path == 0;   // low-latency sponges on 64-thread groups (kernels_quad.cuh)
+  const bool quad = use_quad(ctx);   // low-latency sponges on 64-thread groups (kernels_quad.cuh), else 16-thread groups
   // coin.reseed(digest) followed by `draws` draws, counter restarting at 1 (DefaultRandomCoin [WF-mem]); the digest is
   // also copied to *copy_to when given
   auto reseed_draw = [&](const fe *digest, fe *copy_to, size_t draws, fe *out) -> int {
-    if (quad && draws <= 8) {
-      LAUNCH(ctx, k_quad_reseed_draw, 1, ZKL_QUAD_THREADS, 0, coin.p, digest, copy_to, (int)draws, out);
-      return 0;
-    }
-    if (copy_to) ZKL_CHECK(ctx, cudaMemcpyAsync(copy_to, digest, sizeof(fe), cudaMemcpyDeviceToDevice, st));
-    if (quad) {
-      LAUNCH(ctx, k_quad_reseed_draw, 1, ZKL_QUAD_THREADS, 0, coin.p, digest, (fe *)nullptr, 0, (fe *)nullptr);
-      if (draws) LAUNCH_QUAD(ctx, k_quad_coin_draw, draws, coin.p, (uint64_t)0, (int)draws, out);
-    } else {
-      LAUNCH(ctx, k_coin_reseed, 1, ZKL_COOP_GROUP, 0, coin.p, digest);
-      if (draws) LAUNCH_COOP(ctx, k_coin_draw, draws, coin.p, (uint64_t)0, (int)draws, out);
+    const size_t fused = draws <= ZKL_GRP_MAX_GROUPS ? draws : 0;   // few draws ride in the reseed launch
+    const unsigned groups = (unsigned)std::max<size_t>(fused, 1);
+    if (quad) LAUNCH(ctx, k_reseed_draw<ZKL_QUAD_GROUP>, 1, groups * ZKL_QUAD_GROUP, 0, coin.p, digest, copy_to, (int)fused, out);
+    else LAUNCH(ctx, k_reseed_draw<ZKL_COOP_GROUP>, 1, groups * ZKL_COOP_GROUP, 0, coin.p, digest, copy_to, (int)fused, out);
+    if (draws > fused) {
+      if (quad) LAUNCH_QUAD(ctx, k_quad_coin_draw, draws, coin.p, (uint64_t)0, (int)draws, out);
+      else LAUNCH_COOP(ctx, k_coin_draw, draws, coin.p, (uint64_t)0, (int)draws, out);
     }
     return 0;
   };
@@ -878,7 +874,7 @@ extern "C" int zkl_imad_peak(zkl_ctx *ctx, double *wide_macs_per_s) {
 }
 extern "C" int zkl_set_bulk_threshold(zkl_ctx *ctx, long sponges) { ctx->bulk_threshold = sponges; return 0; }
 extern "C" int zkl_set_coop_path(zkl_ctx *ctx, int path) {
-  if (path != 0 && path != 1) { ctx->set_error("coop path must be 0 (64-thread groups) or 1 (16-thread groups)"); return 1; }
+  if (path < 0 || path > 2) { ctx->set_error("coop path must be 0 (automatic), 1 (16-thread groups) or 2 (64-thread groups)"); return 1; }
   ctx->coop_path = path; return 0;
 }
 extern "C" int zkl_set_ntt_path(zkl_ctx *ctx, int path) {

@@ -46,7 +46,8 @@ struct zkl_ctx {
   long bulk_threshold = 1024;
   // bulk hashing path: 0 = tensor-core MDS (tcperm.cuh, the default), 1 = integer-pipe thread-per-sponge kernels
   int hash_path = 0;
-  int coop_path = 0;   // small sponge batches: 0 = 64-thread groups (kernels_quad.cuh, lowest latency), 1 = 16-thread groups (kernels_hash.cuh)
+  int coop_path = 0;   // small sponge batches: 0 = automatic (by the number of contexts sharing the device), 1 = 16-thread groups
+                       // (kernels_hash.cuh, least SM time), 2 = 64-thread groups (kernels_quad.cuh, lowest latency)
   int ntt_path = 0;    // 4096-row coset LDE: 0 = radix-16 stages on the tensor cores, coset shift folded into the matrix (kernels_tcntt.cuh v2),
                        // 1 = radix-2 in shared memory, 2 = tensor cores with a separate coset-shift product (v1)
   bool tc_ok = true;   // the loaded MDS constants satisfy the tensor-core epilogue's accumulator bound

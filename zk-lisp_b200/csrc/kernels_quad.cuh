@@ -20,7 +20,7 @@
 
 #define ZKL_QUAD_GROUP 64
 #define ZKL_QUAD_THREADS 256   // 4 sponges per CTA (named barriers 1..4)
-#define ZKL_QUAD_MAX_GROUPS 8  // k_quad_tree_top runs 8 groups in one CTA
+#define ZKL_QUAD_MAX_GROUPS 8  // the fused kernels (k_tree_top, k_reseed_draw) run up to 8 groups in one CTA
 
 struct quad_ctx {
   int l, h;        // state lane (clamped to 11), quarter
@@ -95,21 +95,33 @@ __device__ __forceinline__ fe quad_hash_elements(const fe *base, size_t stride, 
 __device__ __forceinline__ bool quad_leader() { return (threadIdx.x & (ZKL_QUAD_GROUP - 1)) == 0; }
 __device__ __forceinline__ size_t quad_index() { return ((size_t)blockIdx.x * blockDim.x + threadIdx.x) / ZKL_QUAD_GROUP; }
 
+// Group-size generic helpers for the fused kernels: G = 64 (this file) or G = 16 (coop_sponge_run, kernels_hash.cuh — 4x fewer
+// warp instructions per permutation: the choice when many segment streams share the GPU and SM time, not latency, is scarce).
+template <int G, typename Src>
+__device__ __forceinline__ fe grp_sponge_run(const Src &src, int total) {
+  if constexpr (G == ZKL_QUAD_GROUP) return quad_sponge_run(src, total);
+  else return coop_sponge_run(src, total);
+}
+template <int G> __device__ __forceinline__ fe grp_merge(const fe &a, const fe &b) { merge_src s{a, b}; return grp_sponge_run<G>(s, 3); }
+template <int G> __device__ __forceinline__ fe grp_merge_with_int(const fe &seed, uint64_t v) { mwi_src s{seed, v}; return grp_sponge_run<G>(s, 3); }
+#define ZKL_GRP_MAX_GROUPS 8   // groups per CTA of the fused kernels (both sizes: 8 x 16 = ZKL_COOP_THREADS, 8 x 64 = 512)
+
 // ---------------------------------------------------------------- kernels (one group per sponge; out-of-range groups run on clamped inputs)
 __global__ void __launch_bounds__(ZKL_QUAD_THREADS) k_quad_merkle_level(const fe *__restrict__ in, fe *__restrict__ out, size_t count) {
   size_t g = quad_index(), gi = g < count ? g : count - 1;
   fe d = quad_merge(ld_fe(in + 2 * gi), ld_fe(in + 2 * gi + 1));
   if (g < count && quad_leader()) st_fe(out + g, d);
 }
-// The top of a Merkle tree in ONE launch: levels count, count/2, ..., 1 (count <= ZKL_QUAD_MAX_GROUPS), single CTA of
-// 64 * count threads. in: 2*count digests; nodes as in dev_merkle (nodes[lvl + i] = node i of the level with lvl nodes).
-__global__ void __launch_bounds__(ZKL_QUAD_MAX_GROUPS * ZKL_QUAD_GROUP) k_quad_tree_top(const fe *__restrict__ in, fe *__restrict__ nodes, int count) {
-  const int g = threadIdx.x / ZKL_QUAD_GROUP;
+// The top of a Merkle tree in ONE launch: levels count, count/2, ..., 1 (count <= ZKL_GRP_MAX_GROUPS), single CTA of
+// G * count threads. in: 2*count digests; nodes as in dev_merkle (nodes[lvl + i] = node i of the level with lvl nodes).
+template <int G>
+__global__ void __launch_bounds__(ZKL_GRP_MAX_GROUPS * G) k_tree_top(const fe *__restrict__ in, fe *__restrict__ nodes, int count) {
+  const int g = threadIdx.x / G;
   const fe *src = in;
   for (int lvl = count; lvl >= 1; lvl >>= 1) {
-    if (g < lvl) {   // whole groups skip: the named barrier inside is per group
-      fe d = quad_merge(ld_fe(src + 2 * g), ld_fe(src + 2 * g + 1));
-      if (quad_leader()) st_fe(nodes + lvl + g, d);
+    if (g < lvl) {   // whole groups skip: the barriers inside the sponge are per group
+      fe d = grp_merge<G>(ld_fe(src + 2 * g), ld_fe(src + 2 * g + 1));
+      if ((threadIdx.x & (G - 1)) == 0) st_fe(nodes + lvl + g, d);
     }
     __syncthreads();   // orders the level's global stores before the next level's loads (same CTA)
     src = nodes + lvl;
@@ -147,21 +159,22 @@ __global__ void __launch_bounds__(ZKL_QUAD_THREADS) k_quad_coin_init(const fe *_
   if (threadIdx.x == 0) st_fe(seed, d);
 }
 // seed = merge(seed, digest) [digest also copied to *copy_to when given], then out[i] = merge_with_int(seed, 1 + i), i < draws:
-// a reseed followed by the draws that depend on it, in one launch. One CTA; the draws are dealt to its groups.
-__global__ void __launch_bounds__(ZKL_QUAD_THREADS) k_quad_reseed_draw(fe *seed, const fe *__restrict__ digest, fe *copy_to, int draws, fe *__restrict__ out) {
+// a reseed followed by the draws that depend on it, in one launch. One CTA of G * (1..8) threads; the draws are dealt to its groups.
+template <int G>
+__global__ void __launch_bounds__(ZKL_GRP_MAX_GROUPS * G) k_reseed_draw(fe *seed, const fe *__restrict__ digest, fe *copy_to, int draws, fe *__restrict__ out) {
   __shared__ fe s_seed;
-  const int groups = blockDim.x / ZKL_QUAD_GROUP, g = threadIdx.x / ZKL_QUAD_GROUP;
+  const int groups = blockDim.x / G, g = threadIdx.x / G;
   const fe dg = ld_fe(digest);
   if (g == 0) {
-    fe d = quad_merge(ld_fe(seed), dg);
+    fe d = grp_merge<G>(ld_fe(seed), dg);
     if (threadIdx.x == 0) { s_seed = d; st_fe(seed, d); if (copy_to) st_fe(copy_to, dg); }
   }
   __syncthreads();
   for (int base = 0; base < draws; base += groups) {   // uniform trip count; whole groups without a draw skip the sponge
     int i = base + g;
     if (i < draws) {
-      fe d = quad_merge_with_int(s_seed, (uint64_t)i + 1);
-      if (quad_leader()) st_fe(out + i, d);
+      fe d = grp_merge_with_int<G>(s_seed, (uint64_t)i + 1);
+      if ((threadIdx.x & (G - 1)) == 0) st_fe(out + i, d);
     }
   }
 }

@@ -5,6 +5,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <mutex>
 
 #include "kernels_air.cuh"
@@ -32,6 +33,15 @@ static std::mutex g_suite_mutex;
 // low-latency sponge kernels: one 64-thread group per sponge (kernels_quad.cuh) or the older 16-thread groups (coop_path 1)
 #define LAUNCH_QUAD(ctx, kernel, sponges, ...) LAUNCH(ctx, kernel, ceil_div((size_t)(sponges) * ZKL_QUAD_GROUP, ZKL_QUAD_THREADS), ZKL_QUAD_THREADS, 0, __VA_ARGS__)
 #define LAUNCH_COOP(ctx, kernel, sponges, ...) LAUNCH(ctx, kernel, ceil_div((size_t)(sponges) * ZKL_COOP_GROUP, ZKL_COOP_THREADS), ZKL_COOP_THREADS, 0, __VA_ARGS__)
+
+// Which low-latency sponge a context uses (coop_path 0 = decide by how many contexts share the device: a lone prover is
+// latency-bound and takes the 64-thread groups, a pool of provers is SM-time-bound and takes the 16-thread groups).
+static std::atomic<int> g_ctx_per_device[64];
+static inline bool use_quad(const zkl_ctx *ctx) {
+  if (ctx->coop_path == 1) return false;
+  if (ctx->coop_path == 2) return true;
+  return g_ctx_per_device[ctx->device & 63].load(std::memory_order_relaxed) < 4;
+}
 
 // ------------------------------------------------------------------------------------------------
 // context
@@ -61,7 +71,7 @@ extern "C" int zkl_ctx_create(int device, zkl_ctx **out) {
   c->num_sms = prop.multiProcessorCount;
   c->tc_grid_cap = c->num_sms;
   if (const char *e = getenv("ZKL_TC_GRID_CAP")) { int v = atoi(e); if (v > 0 && v <= c->num_sms) c->tc_grid_cap = v; }   // experiment knob
-  if (const char *e = getenv("ZKL_COOP_PATH")) c->coop_path = atoi(e) == 1 ? 1 : 0;   // experiment knobs (A/B runs of bench.py)
+  if (const char *e = getenv("ZKL_COOP_PATH")) { int v = atoi(e); if (v >= 0 && v <= 2) c->coop_path = v; }   // experiment knobs (A/B runs of bench.py)
   if (const char *e = getenv("ZKL_NTT_PATH")) { int v = atoi(e); if (v >= 0 && v <= 2) c->ntt_path = v; }
   if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) {
     g_create_error = cudaGetErrorString(e); delete c; return 1;
@@ -107,6 +117,7 @@ extern "C" int zkl_ctx_create(int device, zkl_ctx **out) {
     k_build_dft16_bytes<<<32, 256, 0, c->stream>>>(host_root_of_unity(4), fe_inv(host_root_of_unity(4)));
     if ((e = cudaStreamSynchronize(c->stream)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete c; return 1; }
   }
+  g_ctx_per_device[device & 63]++;
   *out = c;
   return 0;
 }
@@ -114,6 +125,7 @@ extern "C" int zkl_ctx_create(int device, zkl_ctx **out) {
 static void air_cache_drop(const zkl_ctx *ctx);
 extern "C" void zkl_ctx_destroy(zkl_ctx *ctx) {
   if (!ctx) return;
+  g_ctx_per_device[ctx->device & 63]--;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   air_cache_drop(ctx);
@@ -309,7 +321,7 @@ static int dev_hash_partitions(zkl_ctx *ctx, const fe *lde, size_t ncols, size_t
   bool bulk = sponges >= (size_t)ctx->bulk_threshold;
   if (bulk && ctx->hash_path == 0) LAUNCH_TC(ctx, k_tc_hash_rows, sponges, lde, N, n, (int)blowup, (int)ncols, (int)ps, (int)nchunks, out);
   else if (bulk) LAUNCH(ctx, k_hash_rows, ceil_div(sponges, ZKL_HASH_THREADS), ZKL_HASH_THREADS, 0, lde, N, n, (int)blowup, (int)ncols, (int)ps, (int)nchunks, out);
-  else if (ctx->coop_path == 0) LAUNCH_QUAD(ctx, k_quad_hash_rows, sponges, lde, N, n, (int)blowup, (int)ncols, (int)ps, (int)nchunks, out);
+  else if (use_quad(ctx)) LAUNCH_QUAD(ctx, k_quad_hash_rows, sponges, lde, N, n, (int)blowup, (int)ncols, (int)ps, (int)nchunks, out);
   else LAUNCH_COOP(ctx, k_coop_hash_rows, sponges, lde, N, n, (int)blowup, (int)ncols, (int)ps, (int)nchunks, out);
   return 0;
 }
@@ -317,7 +329,7 @@ static int dev_hash_partitions(zkl_ctx *ctx, const fe *lde, size_t ncols, size_t
 static int dev_merge_partitions(zkl_ctx *ctx, const fe *parts, size_t stride, size_t rows, size_t nchunks, fe *leaves) {
   if (rows >= (size_t)ctx->bulk_threshold && ctx->hash_path == 0) LAUNCH_TC(ctx, k_tc_merge_many_rows, rows, parts, stride, rows, (int)nchunks, leaves);
   else if (rows >= (size_t)ctx->bulk_threshold) LAUNCH(ctx, k_merge_many_rows, ceil_div(rows, ZKL_HASH_THREADS), ZKL_HASH_THREADS, 0, parts, stride, rows, (int)nchunks, leaves);
-  else if (ctx->coop_path == 0) LAUNCH_QUAD(ctx, k_quad_merge_many_rows, rows, parts, stride, rows, (int)nchunks, leaves);
+  else if (use_quad(ctx)) LAUNCH_QUAD(ctx, k_quad_merge_many_rows, rows, parts, stride, rows, (int)nchunks, leaves);
   else LAUNCH_COOP(ctx, k_coop_merge_many_rows, rows, parts, stride, rows, (int)nchunks, leaves);
   return 0;
 }
@@ -338,13 +350,13 @@ static int dev_merkle(zkl_ctx *ctx, const fe *leaves, fe *nodes, size_t count) {
   for (size_t lvl = count / 2; lvl >= 1; lvl >>= 1) {
     if (lvl >= (size_t)ctx->bulk_threshold && ctx->hash_path == 0) LAUNCH_TC(ctx, k_tc_merkle_level, lvl, in, nodes + lvl, lvl);
     else if (lvl >= (size_t)ctx->bulk_threshold) LAUNCH(ctx, k_merkle_level, ceil_div(lvl, ZKL_HASH_THREADS), ZKL_HASH_THREADS, 0, in, nodes + lvl, lvl);
-    else if (ctx->coop_path == 0) {
-      if (lvl <= ZKL_QUAD_MAX_GROUPS) {   // the remaining levels in one launch
-        LAUNCH(ctx, k_quad_tree_top, 1, (unsigned)(lvl * ZKL_QUAD_GROUP), 0, in, nodes, (int)lvl);
-        break;
-      }
-      LAUNCH_QUAD(ctx, k_quad_merkle_level, lvl, in, nodes + lvl, lvl);
-    } else LAUNCH_COOP(ctx, k_coop_merkle_level, lvl, in, nodes + lvl, lvl);
+    else if (lvl <= ZKL_GRP_MAX_GROUPS) {   // the remaining levels in one launch
+      if (use_quad(ctx)) LAUNCH(ctx, k_tree_top<ZKL_QUAD_GROUP>, 1, (unsigned)(lvl * ZKL_QUAD_GROUP), 0, in, nodes, (int)lvl);
+      else LAUNCH(ctx, k_tree_top<ZKL_COOP_GROUP>, 1, (unsigned)(lvl * ZKL_COOP_GROUP), 0, in, nodes, (int)lvl);
+      break;
+    }
+    else if (use_quad(ctx)) LAUNCH_QUAD(ctx, k_quad_merkle_level, lvl, in, nodes + lvl, lvl);
+    else LAUNCH_COOP(ctx, k_coop_merkle_level, lvl, in, nodes + lvl, lvl);
     in = nodes + lvl;
   }
   return 0;
