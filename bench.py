@@ -42,7 +42,9 @@ FIELD_PRODUCTS_PER_PERM = 27 * (24 + 144)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture under profiles/
 # (r01 prof_tc_hash_rows: 214.3 MB + 5.7 MB; algorithmic 16*204*65536 = 213.9 MB read + 1 MB written)
 TRAFFIC_HASH_ROWS_BYTES = 220.0e6
-TRAFFIC_LDE_BYTES = None
+# r01b prof_tc_lde4096_v2: 15.8 MB read (the 13.4 MB coefficient matrix is re-read from L2 by the 16 cosets) + 156.0 MB written inside
+# the kernel's window (the rest of the 213.9 MB output is still in the 126 MB L2 when the kernel ends); algorithmic 227.3 MB
+TRAFFIC_LDE_BYTES = 171.8e6
 
 
 def parse_args():
@@ -277,6 +279,7 @@ def main():
     # stream-exclusive pass (nothing else on the GPU) for the per-kernel roofline numbers
     barrier()
     workers[0].items = workers[0].items[:1]
+    workers[0].ctx._check(workers[0].ctx.lib.zkl_set_coop_path(workers[0].ctx.h, 2))  # a lone prover: lowest-latency small-sponge kernels
     workers[0].run(True)
     excl = np.array(list(workers[0].summaries[0].stage_ms))
     barrier()
@@ -310,10 +313,12 @@ def main():
             "timing": "ms_per_launch is taken on an otherwise idle GPU right after the timed region; inside it the kernel shares the SMs with the other streams",
         }
         roofline_lde = {
-            "kernel": "k_lde (trace coset LDE, one CTA per column x coset, single pass over HBM)",
+            "kernel": "k_tc_lde4096_v2 (trace coset LDE, 204 columns x 16 cosets of 4096 rows: three radix-16 stages as u8 GEMM tiles on tcgen05, "
+                      "coset shift folded into per-coset byte matrices, columns fetched by TMA bulk copies; one pass over HBM)",
             "bound": "hbm", "achieved": lde_bytes / (lde_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
             "frac": lde_bytes / (lde_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src, "traffic": TRAFFIC_LDE_BYTES, "ms_per_launch": lde_ms,
-            "note": "f128: ~7 modular products (~160 instructions each incl. butterfly adds) per 16-byte element written, so the kernel is integer-issue-bound far below the HBM roof",
+            "note": "f128: per 16-byte element written the CUDA cores still run 3 accumulator carry propagations and 2 modular products "
+                    "(~400 integer instructions), so the kernel is integer-issue-bound far below the HBM roof; the radix-2 integer-pipe kernel it replaced ran at 0.735 ms",
         }
         cpu = None
         if not args.no_cpu_baseline and world == 1:
@@ -332,6 +337,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ev / args.steps, "wall_ms_per_step": e2e_wall / args.steps},
             "gpu_launches": int(launches),
+            "prove_wall_ms": {"step_of_16_segments": ev_total / args.steps, "one_segment_alone_on_the_gpu": float(np.sum(excl[:9]))},
             "clocks": clocks,
             "roofline": roofline, "roofline_lde": roofline_lde,
             "stage_ms_per_segment": {zkl.capi.load_library().zkl_stage_name(i).decode(): float(stage[i]) for i in range(11)},

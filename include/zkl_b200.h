@@ -259,7 +259,8 @@ int zkl_dev_download(zkl_ctx *ctx, void *host, const void *dev, size_t bytes);
 int zkl_timer_start(zkl_ctx *ctx);             /* CUDA event on the ctx stream */
 int zkl_timer_stop(zkl_ctx *ctx, float *ms);   /* second event, synchronised; elapsed device time */
 int zkl_imad_peak(zkl_ctx *ctx, double *wide_macs_per_s); /* dependency-free IMAD.WIDE.U32 probe */
-/* sponge count from which the bulk sponge kernels replace the 16-thread cooperative ones */
+/* sponge count from which the bulk (tensor-core) sponge kernels replace the small-batch ones; 0 = automatic
+ * (4096 for a lone prover on the 64-thread groups, 1024 when several contexts share the device) */
 int zkl_set_bulk_threshold(zkl_ctx *ctx, long sponges);
 /* bulk hashing path: 0 = tensor-core MDS product (tcgen05 kind::i8, default), 1 = integer-pipe thread-per-sponge
  * kernels. Both are bit-identical; 1 exists for A/B measurements and parity tests. */

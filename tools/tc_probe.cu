@@ -123,15 +123,6 @@ int main(int argc, char **argv) {
       CK(cudaFree(d));
     }
   }
-  {  // 4. pass time against the number of active 32-sponge warp units per CTA (one pass, every SM the same load)
-    fe *d; CK(cudaMalloc(&d, (size_t)sms * 32 * 16 * 12 * sizeof(fe))); CK(cudaMemset(d, 0x11, (size_t)sms * 32 * 16 * 12 * sizeof(fe)));
-    for (int u : {1, 2, 3, 4, 6, 8, 12, 16}) {
-      size_t count = (size_t)sms * 32 * u;
-      float t = time_ms([&] { k_tc_permute_batch<<<sms, TC_THREADS, TC_SMEM_BYTES>>>(d, count); }, 5);
-      printf("units/CTA %2d: %8.1f us per launch  (%.1f M perm/s)\n", u, t * 1e3, count / t / 1e3);
-    }
-    CK(cudaFree(d));
-  }
   CK(cudaDeviceSynchronize());
   printf(fails ? "TC PROBE FAILED\n" : "TC PROBE OK\n");
   return fails != 0;

@@ -586,7 +586,7 @@ static int prove_segment_impl(zkl_ctx *ctx, const fe *trace_dev, size_t W, size_
   for (size_t d = 0; d < nl; d++) {
     size_t half = nd * B / 2;
     ZKL_CHECK(ctx, f_leaves[d].alloc(half)); ZKL_CHECK(ctx, f_nodes[d].alloc(half)); ZKL_CHECK(ctx, f_ev[d + 1].alloc(half));
-    if (half >= (size_t)ctx->bulk_threshold && ctx->hash_path == 0) LAUNCH_TC(ctx, k_tc_fri_leaves, half, cur_ev, (int)nd, (int)B, f_leaves[d].p);
+    if (half >= bulk_min(ctx) && ctx->hash_path == 0) LAUNCH_TC(ctx, k_tc_fri_leaves, half, cur_ev, (int)nd, (int)B, f_leaves[d].p);
     else if (quad) LAUNCH_QUAD(ctx, k_quad_fri_leaves, half, cur_ev, (int)nd, (int)B, f_leaves[d].p);
     else LAUNCH_COOP(ctx, k_fri_leaves, half, cur_ev, (int)nd, (int)B, f_leaves[d].p);
     ZKL_TRY(dev_merkle(ctx, f_leaves[d].p, f_nodes[d].p, half));

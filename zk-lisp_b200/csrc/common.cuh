@@ -43,7 +43,7 @@ struct zkl_ctx {
   uint64_t launches = 0;
   bool suite_loaded = false;
   // sponge count from which the bulk kernels are used instead of the 16-thread cooperative ones
-  long bulk_threshold = 1024;
+  long bulk_threshold = 0;   // 0 = automatic (bulk_min in zkl_b200.cu)
   // bulk hashing path: 0 = tensor-core MDS (tcperm.cuh, the default), 1 = integer-pipe thread-per-sponge kernels
   int hash_path = 0;
   int coop_path = 0;   // small sponge batches: 0 = automatic (by the number of contexts sharing the device), 1 = 16-thread groups

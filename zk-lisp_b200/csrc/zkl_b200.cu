@@ -43,6 +43,14 @@ static inline bool use_quad(const zkl_ctx *ctx) {
   return g_ctx_per_device[ctx->device & 63].load(std::memory_order_relaxed) < 4;
 }
 
+// sponge count from which the bulk (tensor-core) kernels take over from the small-batch kernels: one dependent permutation
+// step costs ~117 us on the tensor-core kernel at any size, 29 / 43 / 78 us on the 64-thread groups at <= 512 / 1024 / 2048
+// sponges and 35 / 37 / 45 us on the 16-thread groups (profiles/perm_latency_r01.log)
+static inline size_t bulk_min(const zkl_ctx *ctx) {
+  if (ctx->bulk_threshold > 0) return (size_t)ctx->bulk_threshold;   // set explicitly (zkl_set_bulk_threshold)
+  return use_quad(ctx) ? 4096 : 1024;
+}
+
 // ------------------------------------------------------------------------------------------------
 // context
 // ------------------------------------------------------------------------------------------------
@@ -318,7 +326,7 @@ static int dev_hash_partitions(zkl_ctx *ctx, const fe *lde, size_t ncols, size_t
   size_t N = n * blowup, nchunks = (ncols + ps - 1) / ps;
   // bulk (tensor-core or thread-per-sponge) kernel when the sponges fill SMs, the 16-thread cooperative one otherwise
   size_t sponges = N * nchunks;
-  bool bulk = sponges >= (size_t)ctx->bulk_threshold;
+  bool bulk = sponges >= bulk_min(ctx);
   if (bulk && ctx->hash_path == 0) LAUNCH_TC(ctx, k_tc_hash_rows, sponges, lde, N, n, (int)blowup, (int)ncols, (int)ps, (int)nchunks, out);
   else if (bulk) LAUNCH(ctx, k_hash_rows, ceil_div(sponges, ZKL_HASH_THREADS), ZKL_HASH_THREADS, 0, lde, N, n, (int)blowup, (int)ncols, (int)ps, (int)nchunks, out);
   else if (use_quad(ctx)) LAUNCH_QUAD(ctx, k_quad_hash_rows, sponges, lde, N, n, (int)blowup, (int)ncols, (int)ps, (int)nchunks, out);
@@ -327,8 +335,8 @@ static int dev_hash_partitions(zkl_ctx *ctx, const fe *lde, size_t ncols, size_t
 }
 // leaves[r] = merge_many(parts[0][r0 + r], ..., parts[nchunks-1][r0 + r]), r < rows (agg/child.rs:1040-1044); parts[q] at parts + q*stride
 static int dev_merge_partitions(zkl_ctx *ctx, const fe *parts, size_t stride, size_t rows, size_t nchunks, fe *leaves) {
-  if (rows >= (size_t)ctx->bulk_threshold && ctx->hash_path == 0) LAUNCH_TC(ctx, k_tc_merge_many_rows, rows, parts, stride, rows, (int)nchunks, leaves);
-  else if (rows >= (size_t)ctx->bulk_threshold) LAUNCH(ctx, k_merge_many_rows, ceil_div(rows, ZKL_HASH_THREADS), ZKL_HASH_THREADS, 0, parts, stride, rows, (int)nchunks, leaves);
+  if (rows >= bulk_min(ctx) && ctx->hash_path == 0) LAUNCH_TC(ctx, k_tc_merge_many_rows, rows, parts, stride, rows, (int)nchunks, leaves);
+  else if (rows >= bulk_min(ctx)) LAUNCH(ctx, k_merge_many_rows, ceil_div(rows, ZKL_HASH_THREADS), ZKL_HASH_THREADS, 0, parts, stride, rows, (int)nchunks, leaves);
   else if (use_quad(ctx)) LAUNCH_QUAD(ctx, k_quad_merge_many_rows, rows, parts, stride, rows, (int)nchunks, leaves);
   else LAUNCH_COOP(ctx, k_coop_merge_many_rows, rows, parts, stride, rows, (int)nchunks, leaves);
   return 0;
@@ -348,8 +356,8 @@ static int dev_merkle(zkl_ctx *ctx, const fe *leaves, fe *nodes, size_t count) {
   if (count < 2 || (count & (count - 1))) { ctx->set_error("Merkle leaf count must be a power of two >= 2"); return 1; }
   const fe *in = leaves;
   for (size_t lvl = count / 2; lvl >= 1; lvl >>= 1) {
-    if (lvl >= (size_t)ctx->bulk_threshold && ctx->hash_path == 0) LAUNCH_TC(ctx, k_tc_merkle_level, lvl, in, nodes + lvl, lvl);
-    else if (lvl >= (size_t)ctx->bulk_threshold) LAUNCH(ctx, k_merkle_level, ceil_div(lvl, ZKL_HASH_THREADS), ZKL_HASH_THREADS, 0, in, nodes + lvl, lvl);
+    if (lvl >= bulk_min(ctx) && ctx->hash_path == 0) LAUNCH_TC(ctx, k_tc_merkle_level, lvl, in, nodes + lvl, lvl);
+    else if (lvl >= bulk_min(ctx)) LAUNCH(ctx, k_merkle_level, ceil_div(lvl, ZKL_HASH_THREADS), ZKL_HASH_THREADS, 0, in, nodes + lvl, lvl);
     else if (lvl <= ZKL_GRP_MAX_GROUPS) {   // the remaining levels in one launch
       if (use_quad(ctx)) LAUNCH(ctx, k_tree_top<ZKL_QUAD_GROUP>, 1, (unsigned)(lvl * ZKL_QUAD_GROUP), 0, in, nodes, (int)lvl);
       else LAUNCH(ctx, k_tree_top<ZKL_COOP_GROUP>, 1, (unsigned)(lvl * ZKL_COOP_GROUP), 0, in, nodes, (int)lvl);
