@@ -638,8 +638,18 @@ static int prove_segment_impl(zkl_ctx *ctx, const fe *trace_dev, size_t W, size_
   // ---- 11. query positions, openings, serialization
   dev_buf<uint32_t> pos_dev, pos_cnt;
   ZKL_CHECK(ctx, pos_dev.alloc(256)); ZKL_CHECK(ctx, pos_cnt.alloc(1));
-  if (quad) LAUNCH(ctx, k_quad_draw_positions, 1, ZKL_QUAD_THREADS, 0, coin.p, nonce.p, (int)o->num_queries, (uint32_t)(N - 1), pos_dev.p, pos_cnt.p);
-  else LAUNCH(ctx, k_draw_positions, 1, ZKL_COOP_THREADS, 0, coin.p, nonce.p, (int)o->num_queries, (uint32_t)(N - 1), pos_dev.p, pos_cnt.p);
+  {  // seed' = merge_with_int(seed, nonce); the draws in parallel; mask + sort + de-duplicate
+    dev_buf<fe> qseed, qdraw;
+    ZKL_CHECK(ctx, qseed.alloc(1)); ZKL_CHECK(ctx, qdraw.alloc(o->num_queries));
+    if (quad) {
+      LAUNCH(ctx, k_seed_with_nonce<ZKL_QUAD_GROUP>, 1, ZKL_QUAD_GROUP, 0, coin.p, nonce.p, qseed.p);
+      LAUNCH_QUAD(ctx, k_quad_coin_draw, o->num_queries, qseed.p, (uint64_t)0, (int)o->num_queries, qdraw.p);
+    } else {
+      LAUNCH(ctx, k_seed_with_nonce<ZKL_COOP_GROUP>, 1, ZKL_COOP_GROUP, 0, coin.p, nonce.p, qseed.p);
+      LAUNCH_COOP(ctx, k_coin_draw, o->num_queries, qseed.p, (uint64_t)0, (int)o->num_queries, qdraw.p);
+    }
+    LAUNCH(ctx, k_positions_finish, 1, 64, 0, qdraw.p, (int)o->num_queries, (uint32_t)(N - 1), pos_dev.p, pos_cnt.p);
+  }
   uint32_t pos_h[256], cnt_h = 0;
   std::vector<fe> ood_h(2 * (W + C)), roots_h(nl + 1), rem_h(rem_len);
   fe troot, croot, z_h, flag_h;

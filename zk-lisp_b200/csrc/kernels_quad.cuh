@@ -178,34 +178,18 @@ __global__ void __launch_bounds__(ZKL_GRP_MAX_GROUPS * G) k_reseed_draw(fe *seed
     }
   }
 }
-// out[i] = merge_with_int(seed, counter_base + 1 + i), i < count (many draws: composition / DEEP coefficients)
-__global__ void __launch_bounds__(ZKL_QUAD_THREADS) k_quad_coin_draw(const fe *__restrict__ seed, uint64_t counter_base, int count, fe *__restrict__ out) {
-  int g = (int)quad_index(), gi = g < count ? g : count - 1;
-  fe d = quad_merge_with_int(ld_fe(seed), counter_base + 1 + (uint64_t)gi);
-  if (g < count && quad_leader()) st_fe(out + g, d);
+// Query positions in three short launches instead of one CTA walking the 64 draws in turn (agg/fs.rs:223-228):
+//   k_seed_with_nonce: seed' = merge_with_int(seed, nonce);  k_*_coin_draw: value_i = next() in parallel;
+//   k_positions_finish: mask, sort, de-duplicate.
+template <int G>
+__global__ void __launch_bounds__(G) k_seed_with_nonce(const fe *__restrict__ seed, const unsigned long long *__restrict__ nonce, fe *__restrict__ out_seed) {
+  fe d = grp_merge_with_int<G>(ld_fe(seed), (uint64_t)*nonce);
+  if (threadIdx.x == 0) st_fe(out_seed, d);
 }
-__global__ void __launch_bounds__(ZKL_QUAD_THREADS) k_quad_hash_elements_single(const fe *__restrict__ elems, int count, fe *out) {
-  fe d = quad_hash_elements(elems, 1, count);
-  if (threadIdx.x == 0) st_fe(out, d);
-}
-// query positions — same contract as k_draw_positions (agg/fs.rs:223-228). One CTA.
-__global__ void __launch_bounds__(ZKL_QUAD_THREADS) k_quad_draw_positions(const fe *__restrict__ seed, const unsigned long long *__restrict__ nonce,
-                                                                          int num_queries, uint32_t mask, uint32_t *positions, uint32_t *count) {
-  __shared__ fe s_seed;
+// positions[0..*count) = sorted, de-duplicated (u64_le(draw_i[..8]) & mask), i < num_queries <= 255; one warp
+__global__ void k_positions_finish(const fe *__restrict__ draws, int num_queries, uint32_t mask, uint32_t *positions, uint32_t *count) {
   __shared__ uint32_t s_vals[256];
-  const int groups = blockDim.x / ZKL_QUAD_GROUP, g = threadIdx.x / ZKL_QUAD_GROUP;
-  if (g == 0) {
-    fe s2 = quad_merge_with_int(ld_fe(seed), (uint64_t)*nonce);
-    if (threadIdx.x == 0) s_seed = s2;
-  }
-  __syncthreads();
-  for (int base = 0; base < num_queries; base += groups) {
-    int i = base + g;
-    if (i < num_queries) {
-      fe d = quad_merge_with_int(s_seed, (uint64_t)i + 1);
-      if (quad_leader()) s_vals[i] = d.l[0] & mask;  // N <= 2^32
-    }
-  }
+  for (int i = threadIdx.x; i < num_queries; i += blockDim.x) s_vals[i] = ld_fe(draws + i).l[0] & mask;  // N <= 2^32
   __syncthreads();
   if (threadIdx.x == 0) {
     for (int i = 1; i < num_queries; i++) {  // insertion sort
@@ -217,4 +201,14 @@ __global__ void __launch_bounds__(ZKL_QUAD_THREADS) k_quad_draw_positions(const 
     for (int i = 0; i < num_queries; i++) if (i == 0 || s_vals[i] != s_vals[i - 1]) positions[c++] = s_vals[i];
     *count = c;
   }
+}
+// out[i] = merge_with_int(seed, counter_base + 1 + i), i < count (many draws: composition / DEEP coefficients)
+__global__ void __launch_bounds__(ZKL_QUAD_THREADS) k_quad_coin_draw(const fe *__restrict__ seed, uint64_t counter_base, int count, fe *__restrict__ out) {
+  int g = (int)quad_index(), gi = g < count ? g : count - 1;
+  fe d = quad_merge_with_int(ld_fe(seed), counter_base + 1 + (uint64_t)gi);
+  if (g < count && quad_leader()) st_fe(out + g, d);
+}
+__global__ void __launch_bounds__(ZKL_QUAD_THREADS) k_quad_hash_elements_single(const fe *__restrict__ elems, int count, fe *out) {
+  fe d = quad_hash_elements(elems, 1, count);
+  if (threadIdx.x == 0) st_fe(out, d);
 }

@@ -36,10 +36,6 @@ __global__ void k_coin_init(const fe *__restrict__ elems, int count, fe *seed) {
   fe d = coop_hash_elements(elems, 1, count);
   if (threadIdx.x == 0) st_fe(seed, d);
 }
-__global__ void k_coin_reseed(fe *seed, const fe *__restrict__ digest) {  // seed = merge(seed, digest)
-  fe d = coop_merge(ld_fe(seed), ld_fe(digest));
-  if (threadIdx.x == 0) st_fe(seed, d);
-}
 // out[i] = merge_with_int(seed, counter_base + 1 + i) as a field element (draw::<BaseElement>), i < count
 __global__ void __launch_bounds__(ZKL_COOP_THREADS) k_coin_draw(const fe *__restrict__ seed, uint64_t counter_base, int count, fe *__restrict__ out) {
   int g = (blockIdx.x * blockDim.x + threadIdx.x) / ZKL_COOP_GROUP;
@@ -68,35 +64,6 @@ __global__ void __launch_bounds__(ZKL_COOP_THREADS) k_grind(const fe *__restrict
     if (tz >= bits) atomicMin(result, (unsigned long long)nonce);
   }
 }
-// query positions (agg/fs.rs:223-228): seed' = merge_with_int(seed, nonce); value_i = u64_le(next()[..8]) & (N-1);
-// sorted + de-duplicated. One block of ZKL_COOP_THREADS threads. positions[0..*count) ascending.
-__global__ void __launch_bounds__(ZKL_COOP_THREADS) k_draw_positions(const fe *__restrict__ seed, const unsigned long long *__restrict__ nonce,
-                                                                     int num_queries, uint32_t mask, uint32_t *positions, uint32_t *count) {
-  __shared__ fe s_seed;
-  __shared__ uint32_t s_vals[256];
-  fe s2 = coop_merge_with_int(ld_fe(seed), (uint64_t)*nonce);
-  if (threadIdx.x == 0) s_seed = s2;
-  __syncthreads();
-  const int groups = blockDim.x / ZKL_COOP_GROUP, g = threadIdx.x / ZKL_COOP_GROUP;
-  for (int base = 0; base < num_queries; base += groups) {
-    int i = base + g;
-    int ii = i < num_queries ? i : num_queries - 1;
-    fe d = coop_merge_with_int(s_seed, (uint64_t)ii + 1);
-    if (i < num_queries && (threadIdx.x & (ZKL_COOP_GROUP - 1)) == 0) s_vals[i] = d.l[0] & mask;  // N <= 2^32
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int i = 1; i < num_queries; i++) {  // insertion sort
-      uint32_t v = s_vals[i]; int j = i - 1;
-      while (j >= 0 && s_vals[j] > v) { s_vals[j + 1] = s_vals[j]; j--; }
-      s_vals[j + 1] = v;
-    }
-    uint32_t c = 0;
-    for (int i = 0; i < num_queries; i++) if (i == 0 || s_vals[i] != s_vals[i - 1]) positions[c++] = s_vals[i];
-    *count = c;
-  }
-}
-
 // ---------------------------------------------------------------- composition polynomial (CompositionPoly::new [WF-mem])
 // After the per-coset inverse NTT, a[j1][m2] = w_M^(j1*m2) * sum_m1 w_ce^(j1*m1) * (h_{m1*n+m2} g^{m1*n+m2}).
 // Thread m2 undoes the twiddle, runs the size-ce inverse DFT over j1 and removes the offset:
