@@ -242,6 +242,34 @@ def test_two_pass_ntt_above_8192_rows(ctx, oracle, n, blowup):
     assert es == [(x + y) % P for x, y in zip(e0, e1)]
 
 
+def test_lde_65536_on_tensor_cores(ctx):
+    """n = 65536 (fib-2pow16, BASELINE.json configs[1-2]): cross radix-16 stage + 4096-point transforms on the tensor
+    cores (k_tc_cross16 + k_tc_lde4096_v2) against the radix-2 two-pass kernels, which the previous test pins to the
+    oracle; more columns than one scratch chunk holds, and the in-place inverse."""
+    if ctx.hash_mode != "default":
+        pytest.skip("NTT test, independent of the hashing mode")
+    n = 65536
+    cols = fast_random_trace(5, n, seed=65536)
+    cols[0] = 0
+    cols[1, :, 0] = 1; cols[1, :, 1] = 0
+    ctx._check(ctx.lib.zkl_set_ntt_path(ctx.h, 0)); polys = ctx.interpolate_columns(cols)
+    ctx._check(ctx.lib.zkl_set_ntt_path(ctx.h, 1)); polys_r2 = ctx.interpolate_columns(cols)
+    ctx._check(ctx.lib.zkl_set_ntt_path(ctx.h, 0))
+    assert np.array_equal(polys, polys_r2)
+    assert not polys[0].any() and int(polys[1, 0, 0]) == 1 and not polys[1, 1:].any()
+    for blowup in (16, 8, 2):
+        few = polys[:3] if blowup == 16 else polys
+        ctx._check(ctx.lib.zkl_set_ntt_path(ctx.h, 0)); a = ctx.evaluate_columns(few, blowup)
+        ctx._check(ctx.lib.zkl_set_ntt_path(ctx.h, 1)); b = ctx.evaluate_columns(few, blowup)
+        ctx._check(ctx.lib.zkl_set_ntt_path(ctx.h, 0))
+        assert np.array_equal(a, b), blowup
+    many = fast_random_trace(70, n, seed=7)          # > 64 columns: two scratch chunks at blowup 16
+    ctx._check(ctx.lib.zkl_set_ntt_path(ctx.h, 0)); a = ctx.evaluate_columns(many, 16)
+    ctx._check(ctx.lib.zkl_set_ntt_path(ctx.h, 1)); b = ctx.evaluate_columns(many, 16)
+    ctx._check(ctx.lib.zkl_set_ntt_path(ctx.h, 0))
+    assert np.array_equal(a, b)
+
+
 def test_large_segment_commit_and_proof(ctx, zkl, oracle):
     """A 16384-row segment (4x the reference's segment cap): trace commitment of a narrow trace is
     bit-identical to the oracle's, and the full proof of a wide AIR-valid trace is accepted by the restated verifier."""

@@ -673,7 +673,7 @@ static int prove_segment_impl(zkl_ctx *ctx, const fe *trace_dev, size_t W, size_
   auto plan_matrix = [&](const committed_matrix &m, tree_job &tj) {
     for (uint32_t p : pos) {
       uint32_t s = (uint32_t)((p % m.blowup) * m.n + p / m.blowup);
-      for (size_t c = 0; c < m.width; c++) want(m.lde.p, (uint32_t)(c * m.N + s));
+      for (size_t c = 0; c < m.width; c++) want(m.lde.p + c * m.N, s);   // per-column base: width * N exceeds 32 bits for large segments
     }
     tj.plan = batch_proof_plan(pos, m.N); tj.depth = ilog2_sz(m.N);
     for (auto &l : tj.plan) for (auto &r : l) want(r.leaf ? m.leaves.p : m.nodes.p, r.index);

@@ -24,6 +24,7 @@
 #include "tcperm.cuh"
 
 #define NTT16_N 4096
+#define NTT16_CROSS_N 65536                     // two-pass tensor-core transform: 16 blocks of NTT16_N
 #define NTT16_PITCH 4112                       // bytes between input chunks: 256 instances x 16 B + 16 B pad
 #define NTT16_BUF_BYTES (16 * NTT16_PITCH)
 #define NTT16_B_BYTES (16 * 256 * 16)
@@ -168,7 +169,7 @@ __global__ void __launch_bounds__(NTT16_THREADS, 1) k_tc_lde4096(const fe *polys
 // and tw0[iD][m1] = w_256^(-iD jC). A CTA serves ONE coset (k = blockIdx.x % blowup): B_k is loaded once.
 //
 // consts layout per coset k: bmat[k][4096] uint4 (shared-memory image, as g_dft16_bytes), tw0[k][16][256] fe.
-__global__ void k_build_lde16_consts(const fe *__restrict__ scale /* [blowup][4096] or null (inverse) */, const fe *__restrict__ wpow, size_t N,
+__global__ void k_build_lde16_consts(const fe *__restrict__ scale /* [blowup][scale_n] or null (no coset shift) */, size_t scale_n, const fe *__restrict__ wpow, size_t N,
                                      int blowup, bool inverse, fe factor, uint4 *__restrict__ bmat, fe *__restrict__ tw0) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= blowup * 4096) return;
@@ -178,7 +179,7 @@ __global__ void k_build_lde16_consts(const fe *__restrict__ scale /* [blowup][40
     const int j = e >> 8, row = e & 255, i = row >> 4, u = row & 15;
     size_t ex = (size_t)((i * j) & 15) * s16; if (inverse && ex) ex = N - ex;
     fe cur = ld_fe(wpow + ex);
-    if (scale) cur = fe_mul(cur, ld_fe(scale + (size_t)k * NTT16_N + 256 * j));
+    if (scale) cur = fe_mul(cur, ld_fe(scale + (size_t)k * scale_n + 256 * j));
     if (inverse) cur = fe_mul(cur, factor);
     const fe two8 = fe_from_u64(256);
     uint32_t out[4] = {0, 0, 0, 0};
@@ -195,8 +196,8 @@ __global__ void k_build_lde16_consts(const fe *__restrict__ scale /* [blowup][40
     size_t ex = (size_t)(iD * jC) * s256; if (inverse && ex) ex = N - ex;
     fe v = ld_fe(wpow + ex);
     if (scale) {
-      v = fe_mul(v, ld_fe(scale + (size_t)k * NTT16_N + m1));
-      v = fe_mul(v, fe_pow(fe_inv(ld_fe(scale + (size_t)k * NTT16_N + 256)), (uint64_t)(jA + jC)));
+      v = fe_mul(v, ld_fe(scale + (size_t)k * scale_n + m1));
+      v = fe_mul(v, fe_pow(fe_inv(ld_fe(scale + (size_t)k * scale_n + 256)), (uint64_t)(jA + jC)));
     }
     if (inverse) { fe f1 = fe_inv(factor); v = fe_mul(v, fe_mul(f1, f1)); }
     st_fe(tw0 + (size_t)k * 4096 + e, v);
@@ -213,7 +214,7 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 
 // grid >= blowup CTAs; CTA b serves coset b % blowup and every (gridDim.x / blowup)-th column of it.
 __global__ void __launch_bounds__(NTT16_THREADS, 1) k_tc_lde4096_v2(const fe *polys, int ncols, int blowup, const uint4 *__restrict__ bmat,
-                                                                   const fe *__restrict__ tw0, const fe *__restrict__ wpow, fe *out, bool inverse, bool use_tma) {
+                                                                   const fe *__restrict__ tw0, const fe *__restrict__ wpow, fe *out, bool inverse, bool use_tma, int cross, size_t Ntab /* entries of wpow: w_Ntab^e */) {
   extern __shared__ unsigned char ntt_smem[];
   const uint32_t base = (smem_u32(ntt_smem) + 127u) & ~127u;
   unsigned char *gen = ntt_smem + (base - smem_u32(ntt_smem));
@@ -244,22 +245,27 @@ __global__ void __launch_bounds__(NTT16_THREADS, 1) k_tc_lde4096_v2(const fe *po
   const int tile = (warp >> 3) & 1, half = (warp >> 2) & 1;
   const int m = 128 * tile + 32 * (warp & 3) + lane;
   const uint32_t tmem_mine = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + 256 * tile + 128 * half;
-  const size_t N = (size_t)NTT16_N * blowup;
+  const size_t N = Ntab;
   const size_t s4096 = N / NTT16_N;
   const fe *tw0k = tw0 + (size_t)k * 4096;
   uint32_t phase = 0, ld_phase = 0;
   uint32_t src = buf0, dst = buf1;
   // column c as 16 chunks of 256 coefficients: chunk jD -> src + jD * PITCH (instance m1 = j & 255 at 16 B pitch)
+  // cross mode (65536-row columns, second pass): problem q = 16 c + i2 reads block i2 of slab (c, k) of the first pass's output
+  // and writes y[i2 + 16 i1] of the 65536-point transform of that slab
+  auto in_block = [&](int q) -> const fe * {
+    return cross ? polys + ((size_t)((q >> 4) * blowup + k) * 16 + (q & 15)) * NTT16_N : polys + (size_t)q * NTT16_N;
+  };
   auto fetch = [&](int c, uint32_t to) {
     mbar_expect_tx(ctl + 16, NTT16_N * 16);
-    const fe *poly = polys + (size_t)c * NTT16_N;
+    const fe *poly = in_block(c);
 #pragma unroll 1
     for (int jD = 0; jD < 16; jD++) bulk_g2s(to + (uint32_t)jD * NTT16_PITCH, poly + 256 * jD, 4096, ctl + 16);
   };
   if (use_tma && is_mma && lane == 0 && rank < ncols) fetch(rank, src);
   for (int c = rank; c < ncols; c += peers) {
     if (!use_tma && !is_mma) {   // debug path: generic loads
-      const fe *poly = polys + (size_t)c * NTT16_N;
+      const fe *poly = in_block(c);
       for (int q = 0; q < 8; q++) {
         int j = threadIdx.x + 512 * q;
         fe v = ld_fe(poly + j);
@@ -308,7 +314,8 @@ __global__ void __launch_bounds__(NTT16_THREADS, 1) k_tc_lde4096_v2(const fe *po
             { size_t e = (size_t)(iB * jA) * s4096; if (inverse && e) e = N - e; v = lazy_mul(v, ld_fe(wpow + e)); }
             sts_u4(dst + (uint32_t)jA * NTT16_PITCH + (uint32_t)iB * 16, v.l[0], v.l[1], v.l[2], v.l[3]);
           } else {                   // m = iB, i = iA
-            st_fe(out + ((size_t)c * blowup + k) * NTT16_N + 256 * i + m, lazy_canon(v));
+            if (cross) st_fe(out + ((size_t)(c >> 4) * blowup + k) * (16 * NTT16_N) + (c & 15) + 16 * (256 * i + m), lazy_canon(v));
+            else st_fe(out + ((size_t)c * blowup + k) * NTT16_N + 256 * i + m, lazy_canon(v));
           }
         }
       }
@@ -316,6 +323,130 @@ __global__ void __launch_bounds__(NTT16_THREADS, 1) k_tc_lde4096_v2(const fe *po
       uint32_t t = src; src = dst; dst = t;
     }
     ld_phase ^= 1;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+}
+
+
+// ================================================================= 65536-row columns: two passes, both on the tensor cores
+// n = 16 m, m = 4096, j = j1 + m j2, i = i2 + 16 i1:
+//   y[i2 + 16 i1] = sum_j1 [s^j1 w_m^(j1 i1)] * w_n^(j1 i2) * sum_j2 a[j1 + m j2] (s^m)^j2 w16^(j2 i2)
+// pass 1 (k_tc_cross16): ONE radix-16 stage across the 16 blocks of m coefficients with the per-coset matrix
+//   C_k[(i2,u),(j2,v)] = byte_u((s^m)^j2 w16^(i2 j2) 2^(8v) mod p), then the twiddle w_n^(j1 i2); a CTA takes slices of 256
+//   consecutive j1 (16 TMA bulk copies of 4 KB, double-buffered: the next slice lands while this one is multiplied) and
+//   writes block i2 of the slab (c, k) with unit stride in j1;
+// pass 2 (k_tc_lde4096_v2, cross = 1): the coset LDE of every block — its B_k / tw0_k carry exactly the s^j1 factor —
+//   scattered to y[i2 + 16 i1].
+// Inverse (interpolation): s = 1, inverse roots, 1/n folded into C.
+__global__ void k_build_cross16_consts(const fe *__restrict__ scale /* [blowup][16 m] or null */, const fe *__restrict__ wpow, size_t N, size_t m,
+                                       int blowup, bool inverse, fe factor, uint4 *__restrict__ cmat) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= blowup * 4096) return;
+  const int k = t >> 12, e = t & 4095;
+  const int j = e >> 8, row = e & 255, i = row >> 4, u = row & 15;
+  size_t ex = (size_t)((i * j) & 15) * (N / 16); if (inverse && ex) ex = N - ex;
+  fe cur = ld_fe(wpow + ex);
+  if (scale) cur = fe_mul(cur, ld_fe(scale + (size_t)k * 16 * m + m * j));
+  if (inverse) cur = fe_mul(cur, factor);
+  const fe two8 = fe_from_u64(256);
+  uint32_t out[4] = {0, 0, 0, 0};
+  for (int b = 0; b < 16; b++) {
+    uint32_t limb = u < 4 ? cur.l[0] : (u < 8 ? cur.l[1] : (u < 12 ? cur.l[2] : cur.l[3]));
+    out[b >> 2] |= ((limb >> (8 * (u & 3))) & 0xFF) << (8 * (b & 3));
+    cur = fe_mul(cur, two8);
+  }
+  cmat[(size_t)k * 4096 + e] = make_uint4(out[0], out[1], out[2], out[3]);
+}
+
+// src: ncols columns of n = 16 m elements (column stride n). dst: slabs (c, k) of n elements, block i2 at offset i2 * m.
+// wpow: w_Ntab^e; wstep = Ntab / n (w_n = w_Ntab^wstep). grid >= blowup CTAs, CTA b serves coset b % blowup.
+__global__ void __launch_bounds__(NTT16_THREADS, 1) k_tc_cross16(const fe *__restrict__ src, int ncols, int blowup, size_t m, const uint4 *__restrict__ cmat,
+                                                                const fe *__restrict__ wpow, size_t Ntab, size_t wstep, fe *__restrict__ dst, bool inverse) {
+  extern __shared__ unsigned char ntt_smem[];
+  const uint32_t base = (smem_u32(ntt_smem) + 127u) & ~127u;
+  unsigned char *gen = ntt_smem + (base - smem_u32(ntt_smem));
+  const uint32_t b_tile = base, buf0 = base + NTT16_B_BYTES, buf1 = buf0 + NTT16_BUF_BYTES, ctl = buf1 + NTT16_BUF_BYTES;
+  uint32_t *ctl_gen = reinterpret_cast<uint32_t *>(gen + NTT16_B_BYTES + 2 * NTT16_BUF_BYTES);
+  const int k = blockIdx.x % blowup, rank = blockIdx.x / blowup;
+  const int peers = (gridDim.x - k + blowup - 1) / blowup;
+  {
+    uint4 *bdst = reinterpret_cast<uint4 *>(gen);
+    const uint4 *bsrc = cmat + (size_t)k * 4096;
+    for (int i = threadIdx.x; i < NTT16_B_BYTES / 16; i += NTT16_THREADS) bdst[i] = bsrc[i];
+  }
+  if (threadIdx.x < 32) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ctl + 64), "n"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (threadIdx.x == 32) {
+    mbar_init(ctl, 1); mbar_init(ctl + 8, 1); mbar_init(ctl + 16, 1); mbar_init(ctl + 24, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = ctl_gen[16];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool is_mma = warp >= 16;
+  const int tile = (warp >> 3) & 1, half = (warp >> 2) & 1;
+  const int inst = 128 * tile + 32 * (warp & 3) + lane;          // j1 - j1_0
+  const uint32_t tmem_mine = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + 256 * tile + 128 * half;
+  const size_t n = 16 * m;
+  const int slices = (int)(m / 256);
+  const int problems = ncols * slices;
+  auto fetch = [&](int p, int which) {   // slice p -> buffer `which`: chunk j2 = 256 coefficients of block j2
+    const uint32_t to = which ? buf1 : buf0, bar = ctl + 16 + 8 * which;
+    mbar_expect_tx(bar, NTT16_N * 16);
+    const fe *col = src + (size_t)(p / slices) * n + (size_t)(p % slices) * 256;
+#pragma unroll 1
+    for (int j2 = 0; j2 < 16; j2++) bulk_g2s(to + (uint32_t)j2 * NTT16_PITCH, col + m * j2, 4096, bar);
+  };
+  if (is_mma && lane == 0 && rank < problems) fetch(rank, 0);
+  int it = 0;
+  for (int p = rank; p < problems; p += peers, it++) {
+    const int cur = it & 1;
+    tc_fence_before();
+    __syncthreads();          // every epilogue of the previous slice has read its accumulators
+    if (is_mma) {
+      tc_fence_after();
+      if (lane == 0) {
+        if (p + peers < problems) fetch(p + peers, cur ^ 1);   // the other buffer's readers (MMAs of the previous slice) are complete
+        mbar_wait(ctl + 16 + 8 * cur, (uint32_t)(it >> 1) & 1);
+        const uint32_t a = cur ? buf1 : buf0;
+#pragma unroll
+        for (int t = 0; t < 2; t++) {
+          const uint64_t adesc = tc_smem_desc(a + t * 2048, NTT16_PITCH, 128);
+          const uint64_t bdesc = tc_smem_desc(b_tile, 4096, 128);
+#pragma unroll
+          for (int kk = 0; kk < 8; kk++)
+            tc_mma_i8(tmem_base + 256 * t, adesc + (uint64_t)((2 * kk * NTT16_PITCH) >> 4), bdesc + (uint64_t)((2 * kk * 4096) >> 4), NTT16_IDESC, kk > 0);
+          tc_commit(ctl + 8 * t);
+        }
+      }
+      __syncwarp();
+    } else {
+      mbar_wait(ctl + 8 * tile, (uint32_t)it & 1);
+      tc_fence_after();
+      const int c = p / slices;
+      const size_t j1 = (size_t)(p % slices) * 256 + inst;
+      fe *slab = dst + ((size_t)c * blowup + k) * n;
+      uint32_t acc[2][16];
+      tmem_ld16(tmem_mine, acc[0]);
+#pragma unroll 2
+      for (int q = 0; q < 8; q++) {
+        tmem_wait_ld(acc[q & 1]);
+        if (q < 7) tmem_ld16(tmem_mine + 16 * (q + 1), acc[(q + 1) & 1]);
+        const int i2 = 8 * half + q;
+        fe v = tc_epilogue_plain(acc[q & 1]);
+        size_t e = (j1 * (size_t)i2 * wstep) & (Ntab - 1);
+        if (inverse && e) e = Ntab - e;
+        if (i2) v = lazy_mul(v, ld_fe(wpow + e));
+        st_fe(slab + (size_t)i2 * m + j1, v);   // any 128-bit representative: pass 2 feeds the bytes to the tensor cores
+      }
+    }
   }
   tc_fence_before();
   __syncthreads();

@@ -102,6 +102,7 @@ extern "C" int zkl_ctx_create(int device, zkl_ctx **out) {
   cudaFuncSetAttribute(k_lde, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
   cudaFuncSetAttribute(k_tc_lde4096, cudaFuncAttributeMaxDynamicSharedMemorySize, NTT16_SMEM_BYTES);
   cudaFuncSetAttribute(k_tc_lde4096_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, NTT16_SMEM_BYTES);
+  cudaFuncSetAttribute(k_tc_cross16, cudaFuncAttributeMaxDynamicSharedMemorySize, NTT16_SMEM_BYTES);
   cudaFuncSetAttribute(k_ntt_pass1, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
   cudaFuncSetAttribute(k_ntt_pass2, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
   cudaFuncSetAttribute(k_tc_permute_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
@@ -142,7 +143,7 @@ extern "C" void zkl_ctx_destroy(zkl_ctx *ctx) {
   for (auto &kv : ctx->tables) { cudaFree(kv.second.wpow); }
   for (auto &kv : ctx->opow) cudaFree(kv.second);
   for (auto &kv : ctx->periodic) cudaFree(kv.second);
-  for (auto &kv : ctx->lde16) { cudaFree(kv.second.first); cudaFree(kv.second.second); }
+  for (auto &kv : ctx->lde16) { cudaFree(kv.second.first); if (kv.second.second) cudaFree(kv.second.second); }
   for (auto e : ctx->ev) cudaEventDestroy(e);
   cudaStreamDestroy(ctx->stream);
   if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
@@ -231,18 +232,33 @@ static ntt_split split_for(size_t n) {
 }
 static const size_t NTT_SINGLE_PASS_MAX = 8192, NTT_MAX = (size_t)1 << 24;
 
-// constants of the v2 tensor-core transform (kernels_tcntt.cuh): per-coset byte matrices and stage-1 twiddles
-static int get_lde16_consts(zkl_ctx *ctx, size_t blowup, bool inverse, const fe *scale, const domain_tables *t, fe factor, const uint4 **bmat, const fe **tw0) {
-  const size_t key = blowup * 2 + (inverse ? 1 : 0);
+// constants of the v2 tensor-core transform (kernels_tcntt.cuh): per-coset byte matrices and stage-1 twiddles.
+// `scale` (optional) = [blowup][scale_n] coset-shift powers; `variant` tells cache entries with different factors apart.
+static int get_lde16_consts(zkl_ctx *ctx, size_t blowup, bool inverse, const fe *scale, size_t scale_n, const domain_tables *t, fe factor, int variant,
+                            const uint4 **bmat, const fe **tw0) {
+  const size_t key = (t->N << 10) | (blowup << 3) | ((size_t)variant << 1) | (inverse ? 1 : 0);
   auto it = ctx->lde16.find(key);
   if (it == ctx->lde16.end()) {
     void *b, *w;
     ZKL_CHECK(ctx, cudaMalloc(&b, blowup * 4096 * sizeof(uint4)));
     ZKL_CHECK(ctx, cudaMalloc(&w, blowup * 4096 * sizeof(fe)));
-    LAUNCH(ctx, k_build_lde16_consts, ceil_div(blowup * 4096, 256), 256, 0, scale, t->wpow, t->N, (int)blowup, inverse, factor, (uint4 *)b, (fe *)w);
+    LAUNCH(ctx, k_build_lde16_consts, ceil_div(blowup * 4096, 256), 256, 0, scale, scale_n, t->wpow, t->N, (int)blowup, inverse, factor, (uint4 *)b, (fe *)w);
     it = ctx->lde16.emplace(key, std::make_pair(b, w)).first;
   }
   *bmat = (const uint4 *)it->second.first; *tw0 = (const fe *)it->second.second;
+  return 0;
+}
+// per-coset matrices of the cross stage of a 65536-point transform (k_tc_cross16)
+static int get_cross16_consts(zkl_ctx *ctx, size_t blowup, bool inverse, const fe *scale, size_t m, const domain_tables *t, fe factor, const uint4 **cmat) {
+  const size_t key = (t->N << 10) | (blowup << 3) | (3u << 1) | (inverse ? 1 : 0);
+  auto it = ctx->lde16.find(key);
+  if (it == ctx->lde16.end()) {
+    void *b;
+    ZKL_CHECK(ctx, cudaMalloc(&b, blowup * 4096 * sizeof(uint4)));
+    LAUNCH(ctx, k_build_cross16_consts, ceil_div(blowup * 4096, 256), 256, 0, scale, t->wpow, t->N, m, (int)blowup, inverse, factor, (uint4 *)b);
+    it = ctx->lde16.emplace(key, std::make_pair(b, (void *)nullptr)).first;
+  }
+  *cmat = (const uint4 *)it->second.first;
   return 0;
 }
 static unsigned lde16_grid(const zkl_ctx *ctx, size_t ncols, size_t blowup) {
@@ -256,8 +272,17 @@ static int dev_interpolate(zkl_ctx *ctx, const fe *src, fe *dst, size_t ncols, s
   fe n_inv = fe_inv(fe_from_u64(n));
   if (n == NTT16_N && ctx->ntt_path == 0) {   // inverse radix-16 stages on the tensor cores, 1/n folded into the matrix (kernels_tcntt.cuh v2)
     const uint4 *bmat; const fe *tw0;
-    ZKL_TRY(get_lde16_consts(ctx, 1, true, nullptr, t, n_inv, &bmat, &tw0));
-    LAUNCH(ctx, k_tc_lde4096_v2, lde16_grid(ctx, ncols, 1), NTT16_THREADS, NTT16_SMEM_BYTES, src, (int)ncols, 1, bmat, tw0, t->wpow, dst, true, getenv("ZKL_LDE_NO_TMA") == nullptr);
+    ZKL_TRY(get_lde16_consts(ctx, 1, true, nullptr, 0, t, n_inv, 0, &bmat, &tw0));
+    LAUNCH(ctx, k_tc_lde4096_v2, lde16_grid(ctx, ncols, 1), NTT16_THREADS, NTT16_SMEM_BYTES, src, (int)ncols, 1, bmat, tw0, t->wpow, dst, true, true, 0, t->N);
+    return 0;
+  }
+  if (n == NTT16_CROSS_N && ctx->ntt_path == 0) {   // 65536 rows: cross stage + 4096-point transforms, both on the tensor cores
+    const uint4 *cmat, *bmat; const fe *tw0;
+    ZKL_TRY(get_cross16_consts(ctx, 1, true, nullptr, NTT16_N, t, n_inv, &cmat));
+    ZKL_TRY(get_lde16_consts(ctx, 1, true, nullptr, 0, t, fe_one(), 1, &bmat, &tw0));
+    dev_buf<fe> scratch; ZKL_CHECK(ctx, scratch.alloc(ncols * n));
+    LAUNCH(ctx, k_tc_cross16, lde16_grid(ctx, ncols * 16, 1), NTT16_THREADS, NTT16_SMEM_BYTES, src, (int)ncols, 1, (size_t)NTT16_N, cmat, t->wpow, t->N, (size_t)1, scratch.p, true);
+    LAUNCH(ctx, k_tc_lde4096_v2, lde16_grid(ctx, ncols * 16, 1), NTT16_THREADS, NTT16_SMEM_BYTES, scratch.p, (int)(ncols * 16), 1, bmat, tw0, t->wpow, dst, true, true, 1, t->N);
     return 0;
   }
   if (n == NTT16_N && ctx->ntt_path == 2) {   // v1: separate 1/n product
@@ -295,8 +320,23 @@ static int dev_lde(zkl_ctx *ctx, const fe *polys, fe *out, size_t ncols, size_t 
   }
   if (n == NTT16_N && ctx->ntt_path == 0) {   // radix-16 stages on the tensor cores, coset shift folded into the matrix (kernels_tcntt.cuh v2)
     const uint4 *bmat; const fe *tw0;
-    ZKL_TRY(get_lde16_consts(ctx, blowup, false, it->second, t, fe_zero(), &bmat, &tw0));
-    LAUNCH(ctx, k_tc_lde4096_v2, lde16_grid(ctx, ncols, blowup), NTT16_THREADS, NTT16_SMEM_BYTES, polys, (int)ncols, (int)blowup, bmat, tw0, t->wpow, out, false, getenv("ZKL_LDE_NO_TMA") == nullptr);
+    ZKL_TRY(get_lde16_consts(ctx, blowup, false, it->second, n, t, fe_zero(), 0, &bmat, &tw0));
+    LAUNCH(ctx, k_tc_lde4096_v2, lde16_grid(ctx, ncols, blowup), NTT16_THREADS, NTT16_SMEM_BYTES, polys, (int)ncols, (int)blowup, bmat, tw0, t->wpow, out, false, true, 0, t->N);
+    return 0;
+  }
+  if (n == NTT16_CROSS_N && ctx->ntt_path == 0) {   // 65536 rows: cross stage + coset LDE of the 16 blocks, both on the tensor cores
+    const uint4 *cmat, *bmat; const fe *tw0;
+    ZKL_TRY(get_cross16_consts(ctx, blowup, false, it->second, NTT16_N, t, fe_zero(), &cmat));
+    ZKL_TRY(get_lde16_consts(ctx, blowup, false, it->second, n, t, fe_zero(), 0, &bmat, &tw0));
+    const size_t chunk = std::max<size_t>(1, ((size_t)1 << 30) / (blowup * n * sizeof(fe)));   // columns per pass: <= 1 GB of scratch
+    dev_buf<fe> scratch; ZKL_CHECK(ctx, scratch.alloc(std::min(chunk, ncols) * blowup * n));
+    for (size_t c0 = 0; c0 < ncols; c0 += chunk) {
+      const size_t nc = std::min(chunk, ncols - c0);
+      LAUNCH(ctx, k_tc_cross16, lde16_grid(ctx, nc * 16, blowup), NTT16_THREADS, NTT16_SMEM_BYTES, polys + c0 * n, (int)nc, (int)blowup, (size_t)NTT16_N, cmat, t->wpow, t->N,
+             blowup, scratch.p, false);
+      LAUNCH(ctx, k_tc_lde4096_v2, lde16_grid(ctx, nc * 16, blowup), NTT16_THREADS, NTT16_SMEM_BYTES, scratch.p, (int)(nc * 16), (int)blowup, bmat, tw0, t->wpow,
+             out + c0 * blowup * n, false, true, 1, t->N);
+    }
     return 0;
   }
   if (n == NTT16_N && ctx->ntt_path == 2) {   // v1: separate coset-shift product
