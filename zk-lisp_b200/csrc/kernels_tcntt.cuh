@@ -24,7 +24,7 @@
 #include "tcperm.cuh"
 
 #define NTT16_N 4096
-#define NTT16_CROSS_N 65536                     // two-pass tensor-core transform: 16 blocks of NTT16_N
+#define NTT16_CROSS_MAX_R 16                    // two-pass tensor-core transform: R blocks of NTT16_N, R in {2, 4, 8, 16}
 #define NTT16_PITCH 4112                       // bytes between input chunks: 256 instances x 16 B + 16 B pad
 #define NTT16_BUF_BYTES (16 * NTT16_PITCH)
 #define NTT16_B_BYTES (16 * 256 * 16)
@@ -251,10 +251,10 @@ __global__ void __launch_bounds__(NTT16_THREADS, 1) k_tc_lde4096_v2(const fe *po
   uint32_t phase = 0, ld_phase = 0;
   uint32_t src = buf0, dst = buf1;
   // column c as 16 chunks of 256 coefficients: chunk jD -> src + jD * PITCH (instance m1 = j & 255 at 16 B pitch)
-  // cross mode (65536-row columns, second pass): problem q = 16 c + i2 reads block i2 of slab (c, k) of the first pass's output
-  // and writes y[i2 + 16 i1] of the 65536-point transform of that slab
+  // cross mode (columns of R * 4096 rows, second pass; cross = R): problem q = R c + i2 reads block i2 of slab (c, k) of the first
+  // pass's output and writes y[i2 + R i1] of the slab's transform
   auto in_block = [&](int q) -> const fe * {
-    return cross ? polys + ((size_t)((q >> 4) * blowup + k) * 16 + (q & 15)) * NTT16_N : polys + (size_t)q * NTT16_N;
+    return cross ? polys + ((size_t)((q / cross) * blowup + k) * cross + (q % cross)) * NTT16_N : polys + (size_t)q * NTT16_N;
   };
   auto fetch = [&](int c, uint32_t to) {
     mbar_expect_tx(ctl + 16, NTT16_N * 16);
@@ -314,7 +314,7 @@ __global__ void __launch_bounds__(NTT16_THREADS, 1) k_tc_lde4096_v2(const fe *po
             { size_t e = (size_t)(iB * jA) * s4096; if (inverse && e) e = N - e; v = lazy_mul(v, ld_fe(wpow + e)); }
             sts_u4(dst + (uint32_t)jA * NTT16_PITCH + (uint32_t)iB * 16, v.l[0], v.l[1], v.l[2], v.l[3]);
           } else {                   // m = iB, i = iA
-            if (cross) st_fe(out + ((size_t)(c >> 4) * blowup + k) * (16 * NTT16_N) + (c & 15) + 16 * (256 * i + m), lazy_canon(v));
+            if (cross) st_fe(out + ((size_t)(c / cross) * blowup + k) * ((size_t)cross * NTT16_N) + (c % cross) + (size_t)cross * (256 * i + m), lazy_canon(v));
             else st_fe(out + ((size_t)c * blowup + k) * NTT16_N + 256 * i + m, lazy_canon(v));
           }
         }
@@ -340,29 +340,31 @@ __global__ void __launch_bounds__(NTT16_THREADS, 1) k_tc_lde4096_v2(const fe *po
 // pass 2 (k_tc_lde4096_v2, cross = 1): the coset LDE of every block — its B_k / tw0_k carry exactly the s^j1 factor —
 //   scattered to y[i2 + 16 i1].
 // Inverse (interpolation): s = 1, inverse roots, 1/n folded into C.
-__global__ void k_build_cross16_consts(const fe *__restrict__ scale /* [blowup][16 m] or null */, const fe *__restrict__ wpow, size_t N, size_t m,
+__global__ void k_build_cross16_consts(const fe *__restrict__ scale /* [blowup][R m] or null */, const fe *__restrict__ wpow, size_t N, size_t m, int R,
                                        int blowup, bool inverse, fe factor, uint4 *__restrict__ cmat) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= blowup * 4096) return;
   const int k = t >> 12, e = t & 4095;
   const int j = e >> 8, row = e & 255, i = row >> 4, u = row & 15;
-  size_t ex = (size_t)((i * j) & 15) * (N / 16); if (inverse && ex) ex = N - ex;
-  fe cur = ld_fe(wpow + ex);
-  if (scale) cur = fe_mul(cur, ld_fe(scale + (size_t)k * 16 * m + m * j));
-  if (inverse) cur = fe_mul(cur, factor);
-  const fe two8 = fe_from_u64(256);
   uint32_t out[4] = {0, 0, 0, 0};
-  for (int b = 0; b < 16; b++) {
-    uint32_t limb = u < 4 ? cur.l[0] : (u < 8 ? cur.l[1] : (u < 12 ? cur.l[2] : cur.l[3]));
-    out[b >> 2] |= ((limb >> (8 * (u & 3))) & 0xFF) << (8 * (b & 3));
-    cur = fe_mul(cur, two8);
+  if (i < R && j < R) {   // a radix-R stage (R | 16) is the radix-16 tile with zero rows / columns: unused inputs may hold anything
+    size_t ex = (size_t)((i * j) % R) * (N / R); if (inverse && ex) ex = N - ex;
+    fe cur = ld_fe(wpow + ex);
+    if (scale) cur = fe_mul(cur, ld_fe(scale + (size_t)k * R * m + m * j));
+    if (inverse) cur = fe_mul(cur, factor);
+    const fe two8 = fe_from_u64(256);
+    for (int b = 0; b < 16; b++) {
+      uint32_t limb = u < 4 ? cur.l[0] : (u < 8 ? cur.l[1] : (u < 12 ? cur.l[2] : cur.l[3]));
+      out[b >> 2] |= ((limb >> (8 * (u & 3))) & 0xFF) << (8 * (b & 3));
+      cur = fe_mul(cur, two8);
+    }
   }
   cmat[(size_t)k * 4096 + e] = make_uint4(out[0], out[1], out[2], out[3]);
 }
 
-// src: ncols columns of n = 16 m elements (column stride n). dst: slabs (c, k) of n elements, block i2 at offset i2 * m.
+// src: ncols columns of n = R m elements (column stride n), R in {2, 4, 8, 16}. dst: slabs (c, k) of n elements, block i2 at offset i2 * m.
 // wpow: w_Ntab^e; wstep = Ntab / n (w_n = w_Ntab^wstep). grid >= blowup CTAs, CTA b serves coset b % blowup.
-__global__ void __launch_bounds__(NTT16_THREADS, 1) k_tc_cross16(const fe *__restrict__ src, int ncols, int blowup, size_t m, const uint4 *__restrict__ cmat,
+__global__ void __launch_bounds__(NTT16_THREADS, 1) k_tc_cross16(const fe *__restrict__ src, int ncols, int blowup, size_t m, int R, const uint4 *__restrict__ cmat,
                                                                 const fe *__restrict__ wpow, size_t Ntab, size_t wstep, fe *__restrict__ dst, bool inverse) {
   extern __shared__ unsigned char ntt_smem[];
   const uint32_t base = (smem_u32(ntt_smem) + 127u) & ~127u;
@@ -394,15 +396,15 @@ __global__ void __launch_bounds__(NTT16_THREADS, 1) k_tc_cross16(const fe *__res
   const int tile = (warp >> 3) & 1, half = (warp >> 2) & 1;
   const int inst = 128 * tile + 32 * (warp & 3) + lane;          // j1 - j1_0
   const uint32_t tmem_mine = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + 256 * tile + 128 * half;
-  const size_t n = 16 * m;
+  const size_t n = (size_t)R * m;
   const int slices = (int)(m / 256);
   const int problems = ncols * slices;
   auto fetch = [&](int p, int which) {   // slice p -> buffer `which`: chunk j2 = 256 coefficients of block j2
     const uint32_t to = which ? buf1 : buf0, bar = ctl + 16 + 8 * which;
-    mbar_expect_tx(bar, NTT16_N * 16);
+    mbar_expect_tx(bar, (uint32_t)R * 4096);
     const fe *col = src + (size_t)(p / slices) * n + (size_t)(p % slices) * 256;
 #pragma unroll 1
-    for (int j2 = 0; j2 < 16; j2++) bulk_g2s(to + (uint32_t)j2 * NTT16_PITCH, col + m * j2, 4096, bar);
+    for (int j2 = 0; j2 < R; j2++) bulk_g2s(to + (uint32_t)j2 * NTT16_PITCH, col + m * j2, 4096, bar);
   };
   if (is_mma && lane == 0 && rank < problems) fetch(rank, 0);
   int it = 0;
@@ -440,6 +442,7 @@ __global__ void __launch_bounds__(NTT16_THREADS, 1) k_tc_cross16(const fe *__res
         tmem_wait_ld(acc[q & 1]);
         if (q < 7) tmem_ld16(tmem_mine + 16 * (q + 1), acc[(q + 1) & 1]);
         const int i2 = 8 * half + q;
+        if (i2 >= R) continue;                       // warp-uniform
         fe v = tc_epilogue_plain(acc[q & 1]);
         size_t e = (j1 * (size_t)i2 * wstep) & (Ntab - 1);
         if (inverse && e) e = Ntab - e;

@@ -249,13 +249,13 @@ static int get_lde16_consts(zkl_ctx *ctx, size_t blowup, bool inverse, const fe 
   return 0;
 }
 // per-coset matrices of the cross stage of a 65536-point transform (k_tc_cross16)
-static int get_cross16_consts(zkl_ctx *ctx, size_t blowup, bool inverse, const fe *scale, size_t m, const domain_tables *t, fe factor, const uint4 **cmat) {
+static int get_cross16_consts(zkl_ctx *ctx, size_t blowup, bool inverse, const fe *scale, size_t m, int R, const domain_tables *t, fe factor, const uint4 **cmat) {
   const size_t key = (t->N << 10) | (blowup << 3) | (3u << 1) | (inverse ? 1 : 0);
   auto it = ctx->lde16.find(key);
   if (it == ctx->lde16.end()) {
     void *b;
     ZKL_CHECK(ctx, cudaMalloc(&b, blowup * 4096 * sizeof(uint4)));
-    LAUNCH(ctx, k_build_cross16_consts, ceil_div(blowup * 4096, 256), 256, 0, scale, t->wpow, t->N, m, (int)blowup, inverse, factor, (uint4 *)b);
+    LAUNCH(ctx, k_build_cross16_consts, ceil_div(blowup * 4096, 256), 256, 0, scale, t->wpow, t->N, m, R, (int)blowup, inverse, factor, (uint4 *)b);
     it = ctx->lde16.emplace(key, std::make_pair(b, (void *)nullptr)).first;
   }
   *cmat = (const uint4 *)it->second.first;
@@ -263,6 +263,13 @@ static int get_cross16_consts(zkl_ctx *ctx, size_t blowup, bool inverse, const f
 }
 static unsigned lde16_grid(const zkl_ctx *ctx, size_t ncols, size_t blowup) {
   return (unsigned)std::min<size_t>(ncols * blowup, std::max<size_t>((size_t)ctx->num_sms, blowup));
+}
+
+// n = R * 4096 with R in {4, 8, 16}: the two-pass tensor-core transform applies (returns R, else 0); 8192 rows still fit one
+// CTA's shared memory and stay on the single-pass kernel
+static int cross_radix(size_t n) {
+  for (int R = 4; R <= NTT16_CROSS_MAX_R; R <<= 1) if (n == (size_t)R * NTT16_N) return R;
+  return 0;
 }
 
 // cols (ncols x n, evaluations over <w_n>) -> coefficients, in place or out of place
@@ -276,13 +283,13 @@ static int dev_interpolate(zkl_ctx *ctx, const fe *src, fe *dst, size_t ncols, s
     LAUNCH(ctx, k_tc_lde4096_v2, lde16_grid(ctx, ncols, 1), NTT16_THREADS, NTT16_SMEM_BYTES, src, (int)ncols, 1, bmat, tw0, t->wpow, dst, true, true, 0, t->N);
     return 0;
   }
-  if (n == NTT16_CROSS_N && ctx->ntt_path == 0) {   // 65536 rows: cross stage + 4096-point transforms, both on the tensor cores
+  if (const int R = ctx->ntt_path == 0 ? cross_radix(n) : 0) {   // 8192..65536 rows: cross stage + 4096-point transforms, both on the tensor cores
     const uint4 *cmat, *bmat; const fe *tw0;
-    ZKL_TRY(get_cross16_consts(ctx, 1, true, nullptr, NTT16_N, t, n_inv, &cmat));
+    ZKL_TRY(get_cross16_consts(ctx, 1, true, nullptr, NTT16_N, R, t, n_inv, &cmat));
     ZKL_TRY(get_lde16_consts(ctx, 1, true, nullptr, 0, t, fe_one(), 1, &bmat, &tw0));
     dev_buf<fe> scratch; ZKL_CHECK(ctx, scratch.alloc(ncols * n));
-    LAUNCH(ctx, k_tc_cross16, lde16_grid(ctx, ncols * 16, 1), NTT16_THREADS, NTT16_SMEM_BYTES, src, (int)ncols, 1, (size_t)NTT16_N, cmat, t->wpow, t->N, (size_t)1, scratch.p, true);
-    LAUNCH(ctx, k_tc_lde4096_v2, lde16_grid(ctx, ncols * 16, 1), NTT16_THREADS, NTT16_SMEM_BYTES, scratch.p, (int)(ncols * 16), 1, bmat, tw0, t->wpow, dst, true, true, 1, t->N);
+    LAUNCH(ctx, k_tc_cross16, lde16_grid(ctx, ncols * 16, 1), NTT16_THREADS, NTT16_SMEM_BYTES, src, (int)ncols, 1, (size_t)NTT16_N, R, cmat, t->wpow, t->N, (size_t)1, scratch.p, true);
+    LAUNCH(ctx, k_tc_lde4096_v2, lde16_grid(ctx, ncols * R, 1), NTT16_THREADS, NTT16_SMEM_BYTES, scratch.p, (int)(ncols * R), 1, bmat, tw0, t->wpow, dst, true, true, R, t->N);
     return 0;
   }
   if (n == NTT16_N && ctx->ntt_path == 2) {   // v1: separate 1/n product
@@ -324,18 +331,18 @@ static int dev_lde(zkl_ctx *ctx, const fe *polys, fe *out, size_t ncols, size_t 
     LAUNCH(ctx, k_tc_lde4096_v2, lde16_grid(ctx, ncols, blowup), NTT16_THREADS, NTT16_SMEM_BYTES, polys, (int)ncols, (int)blowup, bmat, tw0, t->wpow, out, false, true, 0, t->N);
     return 0;
   }
-  if (n == NTT16_CROSS_N && ctx->ntt_path == 0) {   // 65536 rows: cross stage + coset LDE of the 16 blocks, both on the tensor cores
+  if (const int R = ctx->ntt_path == 0 ? cross_radix(n) : 0) {   // 8192..65536 rows: cross stage + coset LDE of the R blocks, both on the tensor cores
     const uint4 *cmat, *bmat; const fe *tw0;
-    ZKL_TRY(get_cross16_consts(ctx, blowup, false, it->second, NTT16_N, t, fe_zero(), &cmat));
+    ZKL_TRY(get_cross16_consts(ctx, blowup, false, it->second, NTT16_N, R, t, fe_zero(), &cmat));
     ZKL_TRY(get_lde16_consts(ctx, blowup, false, it->second, n, t, fe_zero(), 0, &bmat, &tw0));
     const size_t chunk = std::max<size_t>(1, ((size_t)1 << 30) / (blowup * n * sizeof(fe)));   // columns per pass: <= 1 GB of scratch
     dev_buf<fe> scratch; ZKL_CHECK(ctx, scratch.alloc(std::min(chunk, ncols) * blowup * n));
     for (size_t c0 = 0; c0 < ncols; c0 += chunk) {
       const size_t nc = std::min(chunk, ncols - c0);
-      LAUNCH(ctx, k_tc_cross16, lde16_grid(ctx, nc * 16, blowup), NTT16_THREADS, NTT16_SMEM_BYTES, polys + c0 * n, (int)nc, (int)blowup, (size_t)NTT16_N, cmat, t->wpow, t->N,
+      LAUNCH(ctx, k_tc_cross16, lde16_grid(ctx, nc * 16, blowup), NTT16_THREADS, NTT16_SMEM_BYTES, polys + c0 * n, (int)nc, (int)blowup, (size_t)NTT16_N, R, cmat, t->wpow, t->N,
              blowup, scratch.p, false);
-      LAUNCH(ctx, k_tc_lde4096_v2, lde16_grid(ctx, nc * 16, blowup), NTT16_THREADS, NTT16_SMEM_BYTES, scratch.p, (int)(nc * 16), (int)blowup, bmat, tw0, t->wpow,
-             out + c0 * blowup * n, false, true, 1, t->N);
+      LAUNCH(ctx, k_tc_lde4096_v2, lde16_grid(ctx, nc * R, blowup), NTT16_THREADS, NTT16_SMEM_BYTES, scratch.p, (int)(nc * R), (int)blowup, bmat, tw0, t->wpow,
+             out + c0 * blowup * n, false, true, R, t->N);
     }
     return 0;
   }
