@@ -54,10 +54,10 @@ int main(int argc, char **argv) {
   suite_consts *gs; CK(cudaGetSymbolAddress((void **)&gs, g_suite));
   k_build_mds_bytes<<<(TC_KCH * TC_N + 127) / 128, 128>>>(gs);
   CK(cudaDeviceSynchronize());
-  CK(cudaFuncSetAttribute(k_tc_permute_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-  CK(cudaFuncSetAttribute(k_tc_hash_elements_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-  CK(cudaFuncSetAttribute(k_tc_merkle_level, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-  CK(cudaFuncSetAttribute(k_tc_hash_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+  CK(cudaFuncSetAttribute(k_tc_permute_batch<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+  CK(cudaFuncSetAttribute(k_tc_hash_elements_batch<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+  CK(cudaFuncSetAttribute(k_tc_merkle_level<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+  CK(cudaFuncSetAttribute(k_tc_hash_rows<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
   int fails = 0;
   printf("largest possible MMA accumulator %u (bound %u)\n", tc_max_accumulator(su), TC_ACC_MAX);
   if (tc_max_accumulator(su) > TC_ACC_MAX) { printf("random MDS exceeds the accumulator bound\n"); return 3; }
@@ -71,7 +71,7 @@ int main(int argc, char **argv) {
     for (size_t i = 0; i < count; i++) host_permute(&ref[12 * i], su);
     fe *d; CK(cudaMalloc(&d, count * 12 * sizeof(fe)));
     CK(cudaMemcpy(d, h.data(), count * 12 * sizeof(fe), cudaMemcpyHostToDevice));
-    k_tc_permute_batch<<<2, TC_THREADS, TC_SMEM_BYTES>>>(d, count);
+    k_tc_permute_batch<false><<<2, TC_THREADS, TC_SMEM_BYTES>>>(d, count);
     CK(cudaDeviceSynchronize());
     std::vector<fe> got(count * 12);
     CK(cudaMemcpy(got.data(), d, count * 12 * sizeof(fe), cudaMemcpyDeviceToHost));
@@ -88,7 +88,7 @@ int main(int argc, char **argv) {
       fe *d, *o1, *o2; CK(cudaMalloc(&d, h.size() * sizeof(fe))); CK(cudaMalloc(&o1, count * sizeof(fe))); CK(cudaMalloc(&o2, count * sizeof(fe)));
       CK(cudaMemcpy(d, h.data(), h.size() * sizeof(fe), cudaMemcpyHostToDevice));
       k_hash_elements_batch<<<(count + ZKL_HASH_THREADS - 1) / ZKL_HASH_THREADS, ZKL_HASH_THREADS>>>(d, len, count, o1);
-      k_tc_hash_elements_batch<<<3, TC_THREADS, TC_SMEM_BYTES>>>(d, len, count, o2);
+      k_tc_hash_elements_batch<false><<<3, TC_THREADS, TC_SMEM_BYTES>>>(d, len, count, o2);
       CK(cudaDeviceSynchronize());
       std::vector<fe> a(count), b(count);
       CK(cudaMemcpy(a.data(), o1, count * sizeof(fe), cudaMemcpyDeviceToHost)); CK(cudaMemcpy(b.data(), o2, count * sizeof(fe), cudaMemcpyDeviceToHost));
@@ -102,7 +102,7 @@ int main(int argc, char **argv) {
     fe *d, *o1, *o2; CK(cudaMalloc(&d, h.size() * sizeof(fe))); CK(cudaMalloc(&o1, count * sizeof(fe))); CK(cudaMalloc(&o2, count * sizeof(fe)));
     CK(cudaMemcpy(d, h.data(), h.size() * sizeof(fe), cudaMemcpyHostToDevice));
     k_merkle_level<<<(count + ZKL_HASH_THREADS - 1) / ZKL_HASH_THREADS, ZKL_HASH_THREADS>>>(d, o1, count);
-    k_tc_merkle_level<<<sms, TC_THREADS, TC_SMEM_BYTES>>>(d, o2, count);
+    k_tc_merkle_level<false><<<sms, TC_THREADS, TC_SMEM_BYTES>>>(d, o2, count);
     CK(cudaDeviceSynchronize());
     std::vector<fe> a(count), b(count);
     CK(cudaMemcpy(a.data(), o1, count * sizeof(fe), cudaMemcpyDeviceToHost)); CK(cudaMemcpy(b.data(), o2, count * sizeof(fe), cudaMemcpyDeviceToHost));
@@ -117,7 +117,7 @@ int main(int argc, char **argv) {
       size_t tiles = (count + TC_CTA_SPONGES - 1) / TC_CTA_SPONGES;
       int grid = (int)(tiles < (size_t)sms ? tiles : sms);
       float t_old = time_ms([&] { k_permute_batch<<<(count + ZKL_HASH_THREADS - 1) / ZKL_HASH_THREADS, ZKL_HASH_THREADS>>>(d, count); }, 3);
-      float t_tc = time_ms([&] { k_tc_permute_batch<<<grid, TC_THREADS, TC_SMEM_BYTES>>>(d, count); }, 3);
+      float t_tc = time_ms([&] { k_tc_permute_batch<false><<<grid, TC_THREADS, TC_SMEM_BYTES>>>(d, count); }, 3);
       printf("permute %8zu states: integer pipe %8.3f ms (%.1f M/s)   tensor core %8.3f ms (%.1f M/s)   x%.2f\n", count, t_old, count / t_old / 1e3, t_tc,
              count / t_tc / 1e3, t_old / t_tc);
       CK(cudaFree(d));

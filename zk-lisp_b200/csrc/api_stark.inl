@@ -573,7 +573,9 @@ static int prove_segment_impl(zkl_ctx *ctx, const fe *trace_dev, size_t W, size_
   ZKL_CHECK(ctx, dc.alloc(W + C)); ZKL_CHECK(ctx, az.alloc(2)); ZKL_CHECK(ctx, deep.alloc(N));
   ZKL_TRY(reseed_draw(ood_digest.p, nullptr, W + C, dc.p));   // reseed with the OOD digest, draw the DEEP coefficients
   LAUNCH(ctx, k_deep_consts, 1, 32, 0, ood.p, dc.p, (int)W, (int)C, az.p);
-  LAUNCH(ctx, k_deep, ceil_div(N, 256), 256, 0, tl.m.lde.p, cmt.m.lde.p, N, (int)n, (int)B, (int)W, (int)C, dc.p, az.p, z.p, g_n, tN->wpow, deep.p);
+  dev_buf<fe> deep_inv; ZKL_CHECK(ctx, deep_inv.alloc(N));
+  LAUNCH(ctx, k_deep_inverses, ceil_div(N, 256 * DEEP_INV_PER_THREAD), 256, 0, N, (int)n, (int)B, z.p, g_n, tN->wpow, deep_inv.p);
+  LAUNCH(ctx, k_deep, ceil_div(N, 256), 256, 0, tl.m.lde.p, cmt.m.lde.p, N, (int)n, (int)B, (int)W, (int)C, dc.p, az.p, z.p, g_n, tN->wpow, deep_inv.p, deep.p);
   STAGE_MARK();
 
   // ---- 9. FRI layers
@@ -618,7 +620,7 @@ static int prove_segment_impl(zkl_ctx *ctx, const fe *trace_dev, size_t W, size_
       uint64_t target = std::min<uint64_t>((uint64_t)16 << o->grinding, (uint64_t)1 << 30);
       if (ctx->hash_path == 0) {
         // one persistent launch; CTAs stop at the first tile above the best nonce found so far
-        LAUNCH_TC(ctx, k_tc_grind, target, coin.p, base, (uint32_t)target, o->grinding, nonce.p);
+        LAUNCH_TC_TILES(ctx, k_tc_grind, target, coin.p, base, (uint32_t)target, o->grinding, nonce.p);
         base += target;
       } else {
         const uint32_t batch = 1u << 15;

@@ -36,6 +36,7 @@ struct domain_tables {
 struct zkl_ctx {
   int device = 0;
   int num_sms = 148;
+  bool tc_half_tiles = true;               // a lone prover's tensor-core sponge launches use 128-sponge tiles when they fit one wave
   int tc_grid_cap = 148;                   // persistent tensor-core sponge kernels launch at most this many CTAs
   cudaStream_t stream = nullptr;
   cudaMemPool_t pool = nullptr;            // private stream-ordered memory pool

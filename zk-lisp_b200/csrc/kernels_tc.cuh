@@ -11,10 +11,25 @@
 #include "kernels_hash.cuh"
 #include "tcperm.cuh"
 
+// Sponge index handled by this thread in tile `tile` (sets c.active).
+//   full tiles: 256 sponges, every compute warp busy — a pass costs ~119 us (two 32-sponge units per warp scheduler);
+//   half tiles: 128 sponges, TMEM lane quadrant q belongs to set q & 1 and the other set's warps of that quadrant idle —
+//     one unit per scheduler, ~80 us per pass (profiles/tc_pass_time_r01.log). Used by a lone prover for launches that fit one wave
+//     of half tiles: the pass latency, not SM time, is what such a launch costs.
+#define TC_HALF_SPONGES 128
+template <bool HALF> __device__ __forceinline__ constexpr size_t tc_tile_sponges() { return HALF ? TC_HALF_SPONGES : TC_CTA_SPONGES; }
+template <bool HALF>
+__device__ __forceinline__ size_t tc_index(tc_ctx &c, size_t tile) {
+  if constexpr (!HALF) return tile * TC_CTA_SPONGES + (size_t)c.set * TC_SPONGES + c.sponge;
+  c.active = ((c.sponge >> 5) & 1) == c.set;
+  return tile * TC_HALF_SPONGES + c.sponge;
+}
+template <bool HALF> __device__ __forceinline__ bool tc_active(const tc_ctx &c) { if constexpr (HALF) return c.active; else return true; }
+
 // Generic sponge over a lazily produced item stream: the same contract as sponge_run (kernels_hash.cuh), but all
 // 256 threads of a set run the same number of permutations (`total` must be uniform across the set).
 // Returns lane 0 (canonical) in the half-0 thread of each sponge.
-template <typename Src>
+template <bool HALF = false, typename Src>
 __device__ __forceinline__ fe tc_sponge_run(const Src &src, int total, tc_ctx &c) {
   fe st[TC_LPT];
 #pragma unroll
@@ -23,12 +38,14 @@ __device__ __forceinline__ fe tc_sponge_run(const Src &src, int total, tc_ctx &c
   const int lane0 = TC_LPT * c.half;
 #pragma unroll 1
   for (int m = 0; m < total; m += ZKL_RATE) {
+    if (tc_active<HALF>(c)) {
 #pragma unroll
-    for (int j = 0; j < TC_LPT; j++) {
-      int l = lane0 + j;
-      if (l < ZKL_RATE && m + l < total) st[j] = lazy_add(st[j], src.item(m + l));
+      for (int j = 0; j < TC_LPT; j++) {
+        int l = lane0 + j;
+        if (l < ZKL_RATE && m + l < total) st[j] = lazy_add(st[j], src.item(m + l));
+      }
     }
-    tc_permute(st, c);
+    tc_permute<HALF>(st, c);
   }
   return lazy_canon(st[0]);
 }
@@ -37,22 +54,20 @@ __device__ __forceinline__ fe tc_sponge_run(const Src &src, int total, tc_ctx &c
 __device__ __forceinline__ uint64_t tc_my_tiles(size_t tiles) { return blockIdx.x < tiles ? (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0; }
 __device__ __forceinline__ uint64_t tc_perms(int total_items) { return (uint64_t)((total_items + ZKL_RATE - 1) / ZKL_RATE); }
 
-// sponge index handled by this thread in tile `tile`
-__device__ __forceinline__ size_t tc_index(const tc_ctx &c, size_t tile) { return tile * TC_CTA_SPONGES + (size_t)c.set * TC_SPONGES + c.sponge; }
-
 // ---------------------------------------------------------------- kernels
+template <bool HALF>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_permute_batch(fe *states, size_t count) {
   extern __shared__ unsigned char tc_smem[];
   tc_ctx c = tc_setup(tc_smem);
-  size_t tiles = (count + TC_CTA_SPONGES - 1) / TC_CTA_SPONGES;
+  size_t tiles = (count + tc_tile_sponges<HALF>() - 1) / tc_tile_sponges<HALF>();
   if (c.is_mma) tc_mma_loop(c, tc_my_tiles(tiles) * ZKL_ROUNDS);
   else for (size_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-    size_t i = tc_index(c, tile), ic = i < count ? i : count - 1;
+    size_t i = tc_index<HALF>(c, tile), ic = i < count ? i : count - 1;
     fe st[TC_LPT];
 #pragma unroll
     for (int j = 0; j < TC_LPT; j++) st[j] = ld_fe(states + 12 * ic + TC_LPT * c.half + j);
-    tc_permute(st, c);
-    if (i < count) {
+    tc_permute<HALF>(st, c);
+    if (tc_active<HALF>(c) && i < count) {
 #pragma unroll
       for (int j = 0; j < TC_LPT; j++) st_fe(states + 12 * i + TC_LPT * c.half + j, lazy_canon(st[j]));
     }
@@ -64,11 +79,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_permute_batch(fe *states, 
 // [q*psize, min(W,(q+1)*psize)) of storage row s (natural row r = s/n + blowup*(s%n)) and writes out[q*N + r].
 // Sponges of one tile may straddle two partitions only if their lengths agree, so tiles are formed per partition:
 // tile index = q * tiles_per_part + tile_in_part.
+template <bool HALF>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_hash_rows(const fe *__restrict__ lde, size_t N, size_t n, int blowup, int W, int psize,
                                                                 int nchunks, fe *__restrict__ out) {
   extern __shared__ unsigned char tc_smem[];
   tc_ctx c = tc_setup(tc_smem);
-  size_t tiles_per_part = (N + TC_CTA_SPONGES - 1) / TC_CTA_SPONGES;
+  size_t tiles_per_part = (N + tc_tile_sponges<HALF>() - 1) / tc_tile_sponges<HALF>();
   size_t tiles = tiles_per_part * (size_t)nchunks;
   if (c.is_mma) {
     uint64_t perms = 0;
@@ -76,11 +92,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_hash_rows(const fe *__rest
     tc_mma_loop(c, perms * ZKL_ROUNDS);
   } else for (size_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     int q = (int)(tile / tiles_per_part);
-    size_t s = tc_index(c, tile % tiles_per_part), sc = s < N ? s : N - 1;
+    size_t s = tc_index<HALF>(c, tile % tiles_per_part), sc = s < N ? s : N - 1;
     int first = q * psize, len = min(psize, W - first);
     elems_src src{lde + (size_t)first * N + sc, N, len};
-    fe d = tc_sponge_run(src, 1 + (len + 1) / 2, c);
-    if (s < N && c.half == 0) {
+    fe d = tc_sponge_run<HALF>(src, 1 + (len + 1) / 2, c);
+    if (tc_active<HALF>(c) && s < N && c.half == 0) {
       size_t r = (s / n) + (size_t)blowup * (s % n);
       st_fe(out + (size_t)q * N + r, d);
     }
@@ -88,74 +104,79 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_hash_rows(const fe *__rest
   tc_teardown(tc_smem);
 }
 // leaf = merge_many(partition digests)
+template <bool HALF>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_merge_many_rows(const fe *__restrict__ parts, size_t stride, size_t N, int nchunks, fe *__restrict__ out) {
   extern __shared__ unsigned char tc_smem[];
   tc_ctx c = tc_setup(tc_smem);
-  size_t tiles = (N + TC_CTA_SPONGES - 1) / TC_CTA_SPONGES;
+  size_t tiles = (N + tc_tile_sponges<HALF>() - 1) / tc_tile_sponges<HALF>();
   if (c.is_mma) tc_mma_loop(c, tc_my_tiles(tiles) * tc_perms(1 + nchunks) * ZKL_ROUNDS);
   else for (size_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-    size_t r = tc_index(c, tile), rc = r < N ? r : N - 1;
+    size_t r = tc_index<HALF>(c, tile), rc = r < N ? r : N - 1;
     many_src src{parts + rc, stride};
-    fe d = tc_sponge_run(src, 1 + nchunks, c);
-    if (r < N && c.half == 0) st_fe(out + r, d);
+    fe d = tc_sponge_run<HALF>(src, 1 + nchunks, c);
+    if (tc_active<HALF>(c) && r < N && c.half == 0) st_fe(out + r, d);
   }
   tc_teardown(tc_smem);
 }
 // one Merkle level: out[i] = merge(in[2i], in[2i+1])
+template <bool HALF>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_merkle_level(const fe *__restrict__ in, fe *__restrict__ out, size_t count) {
   extern __shared__ unsigned char tc_smem[];
   tc_ctx c = tc_setup(tc_smem);
-  size_t tiles = (count + TC_CTA_SPONGES - 1) / TC_CTA_SPONGES;
+  size_t tiles = (count + tc_tile_sponges<HALF>() - 1) / tc_tile_sponges<HALF>();
   if (c.is_mma) tc_mma_loop(c, tc_my_tiles(tiles) * ZKL_ROUNDS);
   else for (size_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-    size_t i = tc_index(c, tile), ic = i < count ? i : count - 1;
+    size_t i = tc_index<HALF>(c, tile), ic = i < count ? i : count - 1;
     merge_src src{fe_zero(), fe_zero()};
     if (c.half == 0) { src.a = ld_fe(in + 2 * ic); src.b = ld_fe(in + 2 * ic + 1); }   // items 1, 2 live in lanes 1, 2 (TC_LPT >= 3)
-    fe d = tc_sponge_run(src, 3, c);
-    if (i < count && c.half == 0) st_fe(out + i, d);
+    fe d = tc_sponge_run<HALF>(src, 3, c);
+    if (tc_active<HALF>(c) && i < count && c.half == 0) st_fe(out + i, d);
   }
   tc_teardown(tc_smem);
 }
+template <bool HALF>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_hash_elements_batch(const fe *elems, int len, size_t count, fe *out) {
   extern __shared__ unsigned char tc_smem[];
   tc_ctx c = tc_setup(tc_smem);
-  size_t tiles = (count + TC_CTA_SPONGES - 1) / TC_CTA_SPONGES;
+  size_t tiles = (count + tc_tile_sponges<HALF>() - 1) / tc_tile_sponges<HALF>();
   if (c.is_mma) tc_mma_loop(c, tc_my_tiles(tiles) * tc_perms(1 + (len + 1) / 2) * ZKL_ROUNDS);
   else for (size_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-    size_t i = tc_index(c, tile), ic = i < count ? i : count - 1;
+    size_t i = tc_index<HALF>(c, tile), ic = i < count ? i : count - 1;
     elems_src src{elems + ic * (size_t)len, 1, len};
-    fe d = tc_sponge_run(src, 1 + (len + 1) / 2, c);
-    if (i < count && c.half == 0) st_fe(out + i, d);
+    fe d = tc_sponge_run<HALF>(src, 1 + (len + 1) / 2, c);
+    if (tc_active<HALF>(c) && i < count && c.half == 0) st_fe(out + i, d);
   }
   tc_teardown(tc_smem);
 }
+template <bool HALF>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_merge_with_int_batch(fe seed, const uint64_t *vals, size_t count, fe *out) {
   extern __shared__ unsigned char tc_smem[];
   tc_ctx c = tc_setup(tc_smem);
-  size_t tiles = (count + TC_CTA_SPONGES - 1) / TC_CTA_SPONGES;
+  size_t tiles = (count + tc_tile_sponges<HALF>() - 1) / tc_tile_sponges<HALF>();
   if (c.is_mma) tc_mma_loop(c, tc_my_tiles(tiles) * ZKL_ROUNDS);
   else for (size_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-    size_t i = tc_index(c, tile), ic = i < count ? i : count - 1;
+    size_t i = tc_index<HALF>(c, tile), ic = i < count ? i : count - 1;
     mwi_src src{seed, vals[ic]};
-    fe d = tc_sponge_run(src, 3, c);
-    if (i < count && c.half == 0) st_fe(out + i, d);
+    fe d = tc_sponge_run<HALF>(src, 3, c);
+    if (tc_active<HALF>(c) && i < count && c.half == 0) st_fe(out + i, d);
   }
   tc_teardown(tc_smem);
 }
 
 // FRI layer leaves (same contract as k_fri_leaves, kernels_stark.cuh): leaf[k + B*i'] = hash_elements([ev[k][i'], ev[k][i' + nd/2]])
+template <bool HALF>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_fri_leaves(const fe *__restrict__ ev, int nd, int B, fe *__restrict__ leaves) {
   extern __shared__ unsigned char tc_smem[];
   tc_ctx c = tc_setup(tc_smem);
   size_t half_rows = (size_t)nd / 2, total = half_rows * B;
-  size_t tiles = (total + TC_CTA_SPONGES - 1) / TC_CTA_SPONGES;
+  size_t tiles = (total + tc_tile_sponges<HALF>() - 1) / tc_tile_sponges<HALF>();
   if (c.is_mma) tc_mma_loop(c, tc_my_tiles(tiles) * ZKL_ROUNDS);
   else for (size_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-    size_t g = tc_index(c, tile), t = g < total ? g : total - 1;
+    size_t g = tc_index<HALF>(c, tile), t = g < total ? g : total - 1;
     size_t k = t / half_rows, ip = t % half_rows;
     elems_src src{ev + k * nd + ip, half_rows, 2};
-    fe d = tc_sponge_run(src, 2, c);
-    if (g < total && c.half == 0) st_fe(leaves + (k + (size_t)B * ip), d);
+    fe d = tc_sponge_run<HALF>(src, 2, c);
+    if (tc_active<HALF>(c) && g < total && c.half == 0) st_fe(leaves + (k + (size_t)B * ip), d);
   }
   tc_teardown(tc_smem);
 }
@@ -178,10 +199,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_grind(const fe *__restrict
     named_bar_sync(1 + c.set, TC_SET_THREADS + 32);
     if (c.flags[it]) break;
     if (c.is_mma) { tc_mma_loop(c, ZKL_ROUNDS); continue; }
-    size_t g = tc_index(c, tile);
+    size_t g = tc_index<false>(c, tile);
     uint64_t nonce = nonce_base + (g < count ? g : count - 1);
     mwi_src src{sd, nonce};
-    fe d = tc_sponge_run(src, 3, c);
+    fe d = tc_sponge_run<false>(src, 3, c);
     if (g < count && c.half == 0) {
       uint64_t head = ((uint64_t)d.l[1] << 32) | d.l[0];
       uint32_t tz = head == 0 ? 64 : (uint32_t)__ffsll((long long)head) - 1;

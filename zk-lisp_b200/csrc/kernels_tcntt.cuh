@@ -214,7 +214,7 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 
 // grid >= blowup CTAs; CTA b serves coset b % blowup and every (gridDim.x / blowup)-th column of it.
 __global__ void __launch_bounds__(NTT16_THREADS, 1) k_tc_lde4096_v2(const fe *polys, int ncols, int blowup, const uint4 *__restrict__ bmat,
-                                                                   const fe *__restrict__ tw0, const fe *__restrict__ wpow, fe *out, bool inverse, bool use_tma, int cross, size_t Ntab /* entries of wpow: w_Ntab^e */) {
+                                                                   const fe *__restrict__ tw0, const fe *__restrict__ wpow, fe *out, bool inverse, int cross, size_t Ntab /* entries of wpow: w_Ntab^e */) {
   extern __shared__ unsigned char ntt_smem[];
   const uint32_t base = (smem_u32(ntt_smem) + 127u) & ~127u;
   unsigned char *gen = ntt_smem + (base - smem_u32(ntt_smem));
@@ -262,16 +262,8 @@ __global__ void __launch_bounds__(NTT16_THREADS, 1) k_tc_lde4096_v2(const fe *po
 #pragma unroll 1
     for (int jD = 0; jD < 16; jD++) bulk_g2s(to + (uint32_t)jD * NTT16_PITCH, poly + 256 * jD, 4096, ctl + 16);
   };
-  if (use_tma && is_mma && lane == 0 && rank < ncols) fetch(rank, src);
+  if (is_mma && lane == 0 && rank < ncols) fetch(rank, src);
   for (int c = rank; c < ncols; c += peers) {
-    if (!use_tma && !is_mma) {   // debug path: generic loads
-      const fe *poly = in_block(c);
-      for (int q = 0; q < 8; q++) {
-        int j = threadIdx.x + 512 * q;
-        fe v = ld_fe(poly + j);
-        sts_u4(src + (uint32_t)(j >> 8) * NTT16_PITCH + (uint32_t)(j & 255) * 16, v.l[0], v.l[1], v.l[2], v.l[3]);
-      }
-    }
 #pragma unroll 1
     for (int stage = 0; stage < 3; stage++) {
       fence_proxy_async_smem();
@@ -280,7 +272,7 @@ __global__ void __launch_bounds__(NTT16_THREADS, 1) k_tc_lde4096_v2(const fe *po
       if (is_mma) {
         tc_fence_after();
         if (lane == 0) {
-          if (use_tma && stage == 0) mbar_wait(ctl + 16, ld_phase);   // the column has landed (async proxy -> async proxy: no fence)
+          if (stage == 0) mbar_wait(ctl + 16, ld_phase);   // the column has landed (async proxy -> async proxy: no fence)
 #pragma unroll
           for (int t = 0; t < 2; t++) {
             const uint64_t adesc = tc_smem_desc(src + t * 2048, NTT16_PITCH, 128);
@@ -291,7 +283,7 @@ __global__ void __launch_bounds__(NTT16_THREADS, 1) k_tc_lde4096_v2(const fe *po
             tc_commit(ctl + 8 * t);
           }
           // `dst` is idle in the last stage (results go to HBM; its last readers were the MMAs of stage 2): prefetch into it
-          if (use_tma && stage == 2 && c + peers < ncols) fetch(c + peers, dst);
+          if (stage == 2 && c + peers < ncols) fetch(c + peers, dst);
         }
         __syncwarp();
       } else {

@@ -164,6 +164,7 @@ struct tc_ctx {
   volatile uint32_t *flags;   // generic pointer to the set's two control words (tile-level decisions broadcast to the MMA warp)
   int set, half, sponge;
   bool is_mma;        // MMA-issuing warp (no sponge)
+  bool active;        // warp-uniform: this warp's 32 sponges carry work in the current tile (half-tile mode idles every other quadrant)
 };
 #define TC_COMPUTE_WARPS_PER_SET (TC_SET_THREADS / 32)
 
@@ -211,6 +212,7 @@ __device__ __forceinline__ tc_ctx tc_setup(unsigned char *smem_raw) {
   c.dready = c.full + 48;
   c.phase = 0;
   c.flags = ctl_gen + 48 + 2 * c.set;
+  c.active = true;
   return c;
 }
 // CTA epilogue (all threads)
@@ -257,8 +259,28 @@ __device__ __forceinline__ void tc_mma_loop(tc_ctx &c, uint64_t rounds) {
   c.phase = phase;
 }
 
+// A permutation's worth of barrier traffic for a compute warp whose 32 sponges carry no work in this tile: the set's other
+// warps and its MMA warp see the arrivals they count on, nothing is cubed, stored or read back (the warp's rows of the A tile
+// keep stale bytes; the accumulator rows they produce are never loaded).
+__device__ __forceinline__ void tc_permute_idle(tc_ctx &c) {
+  const bool leader = (threadIdx.x & 31) == 0;
+#pragma unroll 1
+  for (int r = 0; r < ZKL_ROUNDS; r++) {
+    __syncwarp();
+    if (leader) {
+#pragma unroll
+      for (int q = 0; q < TC_NGRP; q++) mbar_arrive(c.full + 8 * q);
+    }
+    mbar_wait(c.dready, c.phase);   // one round at a time: full[] must not see two arrivals of one warp in a phase
+    c.phase ^= 1;
+  }
+}
+
 // The permutation, compute side. Called by all compute threads of a set together; st[j] = lazy lane TC_LPT*half + j.
+// HALF (half-tile kernels only): a warp without work idles through the rounds. The full-tile instantiation carries no trace of it.
+template <bool HALF = false>
 __device__ __forceinline__ void tc_permute(fe (&st)[TC_LPT], tc_ctx &c) {
+  if constexpr (HALF) { if (!c.active) { tc_permute_idle(c); return; } }
   const int lane0 = TC_LPT * c.half;
   const bool leader = (threadIdx.x & 31) == 0;
 #pragma unroll 1

@@ -25,8 +25,19 @@ static std::mutex g_suite_mutex;
     (ctx)->launches++;                                                              \
     ZKL_CHECK(ctx, cudaGetLastError());                                             \
   } while (0)
-// tensor-core sponge kernels: persistent, one 512-thread CTA per SM, `sponges` = number of sponges in the launch
-#define LAUNCH_TC(ctx, kernel, sponges, ...)                                                                        \
+// tensor-core sponge kernels: persistent, one 576-thread CTA per SM, `sponges` = number of sponges in the launch. Tiles of 256
+// sponges; a lone prover (use_quad) takes half tiles of 128 when the launch then still fits one wave — the pass is shorter
+// (kernels_tc.cuh: tc_index). The mode is a template parameter: the full-tile kernels carry no trace of it.
+#define LAUNCH_TC(ctx, kernel, sponges, ...)                                                                                        \
+  do {                                                                                                                              \
+    const size_t cap_ = (size_t)(ctx)->tc_grid_cap;                                                                                 \
+    if (tc_half_tiles(ctx, (size_t)(sponges)))                                                                                      \
+      LAUNCH(ctx, kernel<true>, std::min<size_t>(((size_t)(sponges) + TC_HALF_SPONGES - 1) / TC_HALF_SPONGES, cap_), TC_THREADS, TC_SMEM_BYTES, __VA_ARGS__); \
+    else                                                                                                                            \
+      LAUNCH(ctx, kernel<false>, std::min<size_t>(((size_t)(sponges) + TC_CTA_SPONGES - 1) / TC_CTA_SPONGES, cap_), TC_THREADS, TC_SMEM_BYTES, __VA_ARGS__); \
+  } while (0)
+// the grinding kernel walks 256-nonce tiles in increasing order (early exit per tile)
+#define LAUNCH_TC_TILES(ctx, kernel, sponges, ...)                                                                  \
   LAUNCH(ctx, kernel, std::min<size_t>(((size_t)(sponges) + TC_CTA_SPONGES - 1) / TC_CTA_SPONGES, (size_t)(ctx)->tc_grid_cap), TC_THREADS, \
          TC_SMEM_BYTES, __VA_ARGS__)
 
@@ -46,6 +57,9 @@ static inline bool use_quad(const zkl_ctx *ctx) {
 // sponge count from which the bulk (tensor-core) kernels take over from the small-batch kernels: one dependent permutation
 // step costs ~117 us on the tensor-core kernel at any size, 29 / 43 / 78 us on the 64-thread groups at <= 512 / 1024 / 2048
 // sponges and 35 / 37 / 45 us on the 16-thread groups (profiles/perm_latency_r01.log)
+static inline int tc_half_tiles(const zkl_ctx *ctx, size_t sponges) {
+  return ctx->tc_half_tiles && use_quad(ctx) && sponges <= (size_t)TC_HALF_SPONGES * (size_t)ctx->tc_grid_cap;
+}
 static inline size_t bulk_min(const zkl_ctx *ctx) {
   if (ctx->bulk_threshold > 0) return (size_t)ctx->bulk_threshold;   // set explicitly (zkl_set_bulk_threshold)
   return use_quad(ctx) ? 4096 : 1024;
@@ -80,6 +94,7 @@ extern "C" int zkl_ctx_create(int device, zkl_ctx **out) {
   c->tc_grid_cap = c->num_sms;
   if (const char *e = getenv("ZKL_TC_GRID_CAP")) { int v = atoi(e); if (v > 0 && v <= c->num_sms) c->tc_grid_cap = v; }   // experiment knob
   if (const char *e = getenv("ZKL_COOP_PATH")) { int v = atoi(e); if (v >= 0 && v <= 2) c->coop_path = v; }   // experiment knobs (A/B runs of bench.py)
+  if (const char *e = getenv("ZKL_TC_HALF_TILES")) c->tc_half_tiles = atoi(e) != 0;
   if (const char *e = getenv("ZKL_NTT_PATH")) { int v = atoi(e); if (v >= 0 && v <= 2) c->ntt_path = v; }
   if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) {
     g_create_error = cudaGetErrorString(e); delete c; return 1;
@@ -105,13 +120,20 @@ extern "C" int zkl_ctx_create(int device, zkl_ctx **out) {
   cudaFuncSetAttribute(k_tc_cross16, cudaFuncAttributeMaxDynamicSharedMemorySize, NTT16_SMEM_BYTES);
   cudaFuncSetAttribute(k_ntt_pass1, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
   cudaFuncSetAttribute(k_ntt_pass2, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
-  cudaFuncSetAttribute(k_tc_permute_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
-  cudaFuncSetAttribute(k_tc_hash_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
-  cudaFuncSetAttribute(k_tc_merge_many_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
-  cudaFuncSetAttribute(k_tc_merkle_level, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
-  cudaFuncSetAttribute(k_tc_hash_elements_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
-  cudaFuncSetAttribute(k_tc_merge_with_int_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
-  cudaFuncSetAttribute(k_tc_fri_leaves, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+  cudaFuncSetAttribute(k_tc_permute_batch<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+  cudaFuncSetAttribute(k_tc_permute_batch<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+  cudaFuncSetAttribute(k_tc_hash_rows<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+  cudaFuncSetAttribute(k_tc_hash_rows<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+  cudaFuncSetAttribute(k_tc_merge_many_rows<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+  cudaFuncSetAttribute(k_tc_merge_many_rows<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+  cudaFuncSetAttribute(k_tc_merkle_level<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+  cudaFuncSetAttribute(k_tc_merkle_level<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+  cudaFuncSetAttribute(k_tc_hash_elements_batch<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+  cudaFuncSetAttribute(k_tc_hash_elements_batch<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+  cudaFuncSetAttribute(k_tc_merge_with_int_batch<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+  cudaFuncSetAttribute(k_tc_merge_with_int_batch<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+  cudaFuncSetAttribute(k_tc_fri_leaves<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+  cudaFuncSetAttribute(k_tc_fri_leaves<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
   cudaFuncSetAttribute(k_tc_grind, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
   label_consts lc;
   lc.elements = host_label("winter/hash/elements");
@@ -280,7 +302,7 @@ static int dev_interpolate(zkl_ctx *ctx, const fe *src, fe *dst, size_t ncols, s
   if (n == NTT16_N && ctx->ntt_path == 0) {   // inverse radix-16 stages on the tensor cores, 1/n folded into the matrix (kernels_tcntt.cuh v2)
     const uint4 *bmat; const fe *tw0;
     ZKL_TRY(get_lde16_consts(ctx, 1, true, nullptr, 0, t, n_inv, 0, &bmat, &tw0));
-    LAUNCH(ctx, k_tc_lde4096_v2, lde16_grid(ctx, ncols, 1), NTT16_THREADS, NTT16_SMEM_BYTES, src, (int)ncols, 1, bmat, tw0, t->wpow, dst, true, true, 0, t->N);
+    LAUNCH(ctx, k_tc_lde4096_v2, lde16_grid(ctx, ncols, 1), NTT16_THREADS, NTT16_SMEM_BYTES, src, (int)ncols, 1, bmat, tw0, t->wpow, dst, true, 0, t->N);
     return 0;
   }
   if (const int R = ctx->ntt_path == 0 ? cross_radix(n) : 0) {   // 8192..65536 rows: cross stage + 4096-point transforms, both on the tensor cores
@@ -289,7 +311,7 @@ static int dev_interpolate(zkl_ctx *ctx, const fe *src, fe *dst, size_t ncols, s
     ZKL_TRY(get_lde16_consts(ctx, 1, true, nullptr, 0, t, fe_one(), 1, &bmat, &tw0));
     dev_buf<fe> scratch; ZKL_CHECK(ctx, scratch.alloc(ncols * n));
     LAUNCH(ctx, k_tc_cross16, lde16_grid(ctx, ncols * 16, 1), NTT16_THREADS, NTT16_SMEM_BYTES, src, (int)ncols, 1, (size_t)NTT16_N, R, cmat, t->wpow, t->N, (size_t)1, scratch.p, true);
-    LAUNCH(ctx, k_tc_lde4096_v2, lde16_grid(ctx, ncols * R, 1), NTT16_THREADS, NTT16_SMEM_BYTES, scratch.p, (int)(ncols * R), 1, bmat, tw0, t->wpow, dst, true, true, R, t->N);
+    LAUNCH(ctx, k_tc_lde4096_v2, lde16_grid(ctx, ncols * R, 1), NTT16_THREADS, NTT16_SMEM_BYTES, scratch.p, (int)(ncols * R), 1, bmat, tw0, t->wpow, dst, true, R, t->N);
     return 0;
   }
   if (n == NTT16_N && ctx->ntt_path == 2) {   // v1: separate 1/n product
@@ -328,7 +350,7 @@ static int dev_lde(zkl_ctx *ctx, const fe *polys, fe *out, size_t ncols, size_t 
   if (n == NTT16_N && ctx->ntt_path == 0) {   // radix-16 stages on the tensor cores, coset shift folded into the matrix (kernels_tcntt.cuh v2)
     const uint4 *bmat; const fe *tw0;
     ZKL_TRY(get_lde16_consts(ctx, blowup, false, it->second, n, t, fe_zero(), 0, &bmat, &tw0));
-    LAUNCH(ctx, k_tc_lde4096_v2, lde16_grid(ctx, ncols, blowup), NTT16_THREADS, NTT16_SMEM_BYTES, polys, (int)ncols, (int)blowup, bmat, tw0, t->wpow, out, false, true, 0, t->N);
+    LAUNCH(ctx, k_tc_lde4096_v2, lde16_grid(ctx, ncols, blowup), NTT16_THREADS, NTT16_SMEM_BYTES, polys, (int)ncols, (int)blowup, bmat, tw0, t->wpow, out, false, 0, t->N);
     return 0;
   }
   if (const int R = ctx->ntt_path == 0 ? cross_radix(n) : 0) {   // 8192..65536 rows: cross stage + coset LDE of the R blocks, both on the tensor cores
@@ -342,7 +364,7 @@ static int dev_lde(zkl_ctx *ctx, const fe *polys, fe *out, size_t ncols, size_t 
       LAUNCH(ctx, k_tc_cross16, lde16_grid(ctx, nc * 16, blowup), NTT16_THREADS, NTT16_SMEM_BYTES, polys + c0 * n, (int)nc, (int)blowup, (size_t)NTT16_N, R, cmat, t->wpow, t->N,
              blowup, scratch.p, false);
       LAUNCH(ctx, k_tc_lde4096_v2, lde16_grid(ctx, nc * R, blowup), NTT16_THREADS, NTT16_SMEM_BYTES, scratch.p, (int)(nc * R), (int)blowup, bmat, tw0, t->wpow,
-             out + c0 * blowup * n, false, true, R, t->N);
+             out + c0 * blowup * n, false, R, t->N);
     }
     return 0;
   }
