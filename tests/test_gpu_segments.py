@@ -92,7 +92,12 @@ def test_prove_program_multi_segment(ctx, zkl, oracle):
         # same bytes as proving the host-sliced segment through the host-buffer entry point
         lay = S.SegmentLayout(full_cols, A.LayoutConfig(ram=False, merkle=False))
         host_seg = np.ascontiguousarray(full[lay.seg_to_full.astype(np.int64), seg.r_start:seg.r_end])
-        assert zkl.ZkProver(ctx, s.options, s.air_pi).prove(host_seg) == s.proof
+        again = zkl.ZkProver(ctx, s.options, s.air_pi).prove(host_seg)
+        if again != s.proof:   # say what kind of difference it is: a racy kernel yields proofs that still verify
+            diff = [i for i in range(min(len(again), len(s.proof))) if again[i] != s.proof[i]]
+            rc2, msg2 = oracle.verify_segment(again, s.width, s.rows, ac, seed, oc)
+            raise AssertionError(f"segment {s.segment_index}: {len(diff)} bytes differ from byte {diff[:1]}, lengths {len(again)} / {len(s.proof)}; "
+                                 f"host-path proof verifies: {rc2 == 0} ({msg2})")
     # the pi_prog binding exists only in the segment that starts at pc = 0 (schedule.rs:117-131)
     assert len(A.Air(204, seg_rows, steps[0].air_pi, steps[0].options).assertions) == len(A.Air(204, seg_rows, steps[1].air_pi, steps[1].options).assertions) + 1
     ctx2.close()

@@ -158,11 +158,13 @@ __global__ void k_sponge_single(const fe *chunks, int count, int label_kind, fe 
 #define ZKL_COOP_THREADS 128
 __device__ suite_consts g_suite;  // global-memory mirror of c_suite (written by zkl_suite_load)
 
-__device__ __forceinline__ void coop_permute(fe &st, int l, fe *xch /* this group's 2 x 12 slots */, uint32_t gmask) {
+// `parity`: exchange buffer of round 0; flipped per permutation by multi-permutation sponges (ZKL_ROUNDS is odd: the last round
+// of one permutation and the first of the next must not share a buffer, there is no barrier between them)
+__device__ __forceinline__ void coop_permute(fe &st, int l, fe *xch /* this group's 2 x 12 slots */, uint32_t gmask, int parity = 0) {
   const bool active = l < 12;
 #pragma unroll 1
   for (int r = 0; r < ZKL_ROUNDS; r++) {
-    fe *buf = xch + (r & 1) * 12;
+    fe *buf = xch + ((r + parity) & 1) * 12;
     if (active) sts_fe(buf + l, fe_cube(st));
     __syncwarp(gmask);  // group-scoped: the two groups of a warp may run different numbers of permutations
     if (active) {
@@ -184,10 +186,11 @@ __device__ __forceinline__ fe coop_sponge_run(const Src &src, int total) {
   fe st = fe_zero();
   if (l == 10) st = ld_fe(&g_suite.dom[0]);
   if (l == 11) st = ld_fe(&g_suite.dom[1]);
+  int parity = 0;
 #pragma unroll 1
-  for (int m = 0; m < total; m += ZKL_RATE) {
+  for (int m = 0; m < total; m += ZKL_RATE, parity ^= 1) {
     if (l < ZKL_RATE && m + l < total) st = fe_add(st, src.item(m + l));
-    coop_permute(st, l, xch, gmask);
+    coop_permute(st, l, xch, gmask, parity);
   }
   fe out;
   const int src_lane = (threadIdx.x & 31) & ~(ZKL_COOP_GROUP - 1);

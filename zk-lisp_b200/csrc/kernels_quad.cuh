@@ -45,10 +45,14 @@ __device__ __forceinline__ quad_ctx quad_setup(fe *xch_all) {
   return q;
 }
 
-__device__ __forceinline__ void quad_permute(fe &st, const quad_ctx &q) {
+// `parity`: which exchange buffer round 0 uses. ZKL_ROUNDS is odd, so a sponge that runs several permutations must flip it per
+// permutation: otherwise the last round of one permutation and the first round of the next share a buffer with no barrier
+// between the slow warp's reads and the fast warp's writes (a real race with two warps per sponge: it corrupted a few leaf
+// digests per thousand rows under load — the proofs still verified, the bytes differed).
+__device__ __forceinline__ void quad_permute(fe &st, const quad_ctx &q, int parity = 0) {
 #pragma unroll 1
   for (int r = 0; r < ZKL_ROUNDS; r++) {
-    fe *buf = q.xch + (r & 1) * 12;
+    fe *buf = q.xch + ((r + parity) & 1) * 12;
     fe c = lazy_mul(lazy_sqr(st), st);
     if (q.writer) sts_fe(buf + q.l, c);
     quad_bar(q.bar);
@@ -76,10 +80,11 @@ __device__ __forceinline__ fe quad_sponge_run(const Src &src, int total) {
   fe st = fe_zero();
   if (q.l == 10) st = ld_fe(&g_suite.dom[0]);
   if (q.l == 11) st = ld_fe(&g_suite.dom[1]);
+  int parity = 0;
 #pragma unroll 1
-  for (int m = 0; m < total; m += ZKL_RATE) {
+  for (int m = 0; m < total; m += ZKL_RATE, parity ^= 1) {
     if (q.l < ZKL_RATE && m + q.l < total) st = fe_add(st, src.item(m + q.l));
-    quad_permute(st, q);
+    quad_permute(st, q, parity);
   }
   fe out;
 #pragma unroll
