@@ -16,6 +16,7 @@ synchronize on both sides; wall clock is reported beside it as a cross-check.
 """
 import argparse
 import ctypes as C
+import hashlib
 import json
 import os
 import subprocess
@@ -179,18 +180,23 @@ class Worker:
             self.ctx._check(self.ctx.lib.zkl_dev_alloc(self.ctx.h, trace.nbytes, C.byref(dev)))
             self.ctx._check(self.ctx.lib.zkl_dev_upload(self.ctx.h, dev, trace.ctypes.data, trace.nbytes))
             self.items.append((prover, trace, dev))
-        self.ms, self.summaries, self.proof_bytes = 0.0, [], 0
+        self.ms, self.summaries, self.proof_bytes, self.digests = 0.0, [], 0, []
 
     def run(self, resident: bool):
         ms = C.c_float()
         self.summaries, self.proof_bytes = [], 0
+        proofs = []
         self.ctx._check(self.ctx.lib.zkl_timer_start(self.ctx.h))
         for prover, trace, dev in self.items:
             proof = prover.prove(None, dev_ptr=dev, shape=trace.shape[:2]) if resident else prover.prove(trace)
             self.proof_bytes += len(proof)
             self.summaries.append(prover.last_summary)
+            proofs.append(proof)
         self.ctx._check(self.ctx.lib.zkl_timer_stop(self.ctx.h, C.byref(ms)))
         self.ms = ms.value
+        # outside the timed region: the same segment must give the same bytes in every step and through both entry points
+        # (8 streams share the GPU: a racy kernel shows up here as proofs that differ from run to run)
+        self.digests = [hashlib.blake2b(p, digest_size=16).hexdigest() for p in proofs]
 
 
 def run_step(workers, resident):
@@ -245,9 +251,12 @@ def main():
             sampler.start()
         ev_ms, wall_ms = [], []
         launches0 = sum(w.ctx.launches for w in workers)
+        nonlocal deterministic
         for _ in range(steps):
             e, wl = run_step(workers, resident)
             ev_ms.append(e); wall_ms.append(wl)
+            if reference_digests and reference_digests[0]:
+                deterministic = deterministic and [list(w.digests) for w in workers] == reference_digests
         barrier()
         clocks = sampler.stop() if sampler else None
         tot_ev, tot_wall = float(np.sum(ev_ms)), float(np.sum(wall_ms))
@@ -259,6 +268,8 @@ def main():
 
     for _ in range(args.warmup):
         run_step(workers, True)
+    reference_digests = [list(w.digests) for w in workers]   # from the last warm-up step
+    deterministic = True
     sampler = ClockSampler(device)
     ev_total, wall_total, launches, clocks = timed(True, args.steps, sampler)
     stage = np.zeros(12)
@@ -337,6 +348,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ev / args.steps, "wall_ms_per_step": e2e_wall / args.steps},
             "gpu_launches": int(launches),
+            "proofs_identical_across_steps_and_entry_points": bool(deterministic),
             "prove_wall_ms": {"step_of_16_segments": ev_total / args.steps, "one_segment_alone_on_the_gpu": float(np.sum(excl[:9]))},
             "clocks": clocks,
             "roofline": roofline, "roofline_lde": roofline_lde,
