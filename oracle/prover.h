@@ -448,9 +448,11 @@ static inline int verify_segment(const Hasher &h, const uint8_t *proof, size_t l
   if (!read_queries(ncc, crows, cbp)) { msg = "constraint queries"; return 4; }
   if (r.u16() != 2 * W * 16) { msg = "ood trace len"; return 5; }
   std::vector<F> t_z(W), t_zg(W), h_z(ncc), h_zg(ncc);
-  for (auto &x : t_z) x = r.fe(); for (auto &x : t_zg) x = r.fe();
+  for (auto &x : t_z) x = r.fe();
+  for (auto &x : t_zg) x = r.fe();
   if (r.u16() != 2 * ncc * 16) { msg = "ood eval len"; return 5; }
-  for (auto &x : h_z) x = r.fe(); for (auto &x : h_zg) x = r.fe();
+  for (auto &x : h_z) x = r.fe();
+  for (auto &x : h_zg) x = r.fe();
   if (r.u8() != nl) { msg = "fri layer count"; return 6; }
   std::vector<std::vector<F>> fvals(nl); std::vector<BatchMerkleProof> fbp(nl);
   for (size_t d = 0; d < nl; d++) {
