@@ -242,6 +242,27 @@ def test_two_pass_ntt_above_8192_rows(ctx, oracle, n, blowup):
     assert es == [(x + y) % P for x, y in zip(e0, e1)]
 
 
+def test_lone_and_pool_kernel_selections_give_identical_proofs(ctx, zkl, oracle):
+    """The automatic selections (zkl_set_coop_path 0): a lone prover takes the 64-thread sponge groups, the tensor-core kernels
+    from 4096 sponges up and half tiles; a prover pool takes the 16-thread groups, 1024 and full tiles. n = 256 (4096 LDE rows)
+    puts the row hashing on the tensor-core kernels in both, the tree levels on three different kernels. Same bytes, and the
+    oracle's."""
+    if ctx.hash_mode != "default":
+        pytest.skip("builds its own contexts")
+    trace, air_pi, opts = synth.valid_segment(n=256, queries=16, blowup=16, grind=6, seed=31)
+    a, ac, oc, seed = _air(zkl, trace, air_pi, opts)
+    ref = oracle.prove_segment(trace, ac, seed, oc)
+    lone, pool = zkl.Context(0), zkl.Context(0)
+    try:
+        lone._check(lone.lib.zkl_set_coop_path(lone.h, 2))
+        pool._check(pool.lib.zkl_set_coop_path(pool.h, 1))
+        for c in (lone, pool):
+            for _ in range(2):   # twice: the second proof reuses the context's pool memory
+                assert zkl.ZkProver(c, opts, air_pi).prove(trace) == ref
+    finally:
+        lone.close(); pool.close()
+
+
 def test_lde_65536_on_tensor_cores(ctx):
     """n = 65536 (fib-2pow16, BASELINE.json configs[1-2]): cross radix-16 stage + 4096-point transforms on the tensor
     cores (k_tc_cross16 + k_tc_lde4096_v2) against the radix-2 two-pass kernels, which the previous test pins to the
