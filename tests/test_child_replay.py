@@ -1,0 +1,139 @@
+"""CPU tests of the child-proof replay logic (zk-lisp_b200/replay.py) with the CPU checker standing in
+for the device hasher: the Fiat-Shamir replay written after agg/fs.rs must land on the challenges the prover used
+(tests/fs_replay.rs:109-271 does this against a live coin), and every opening must re-hash to its commitment
+(tests/agg_child.rs:60-146). The GPU suite runs the same functions over the C-ABI primitives (test_gpu_segments.py)."""
+from dataclasses import replace
+
+import numpy as np
+import pytest
+
+import synth
+
+
+def _step(zkl, oracle, n, seed, queries=8, parts=None, grind=4):
+    S = zkl.step
+    trace, air_pi, opts = synth.valid_segment(n=n, queries=queries, blowup=16, grind=grind, seed=seed)
+    if parts:
+        opts = replace(opts, num_partitions=parts[0], hash_rate=parts[1])
+    a = zkl.air.Air(trace.shape[0], n, air_pi, opts)
+    summ = zkl.capi.ProofSummary()
+    proof = oracle.prove_segment(trace, a.to_c(), zkl.prover.ints_to_fe(a.seed_elements()), opts.to_c(), summ)
+    meta = S.StepMeta.from_env(n, opts.blowup, opts.num_queries, 64, len(air_pi.to_elements()))
+    f = S.fe_to_bytes_fold
+    b = {"ram_gp_unsorted_in": f(air_pi.ram_gp_unsorted_in), "ram_gp_unsorted_out": f(air_pi.ram_gp_unsorted_out),
+         "ram_gp_sorted_in": f(air_pi.ram_gp_sorted_in), "ram_gp_sorted_out": f(air_pi.ram_gp_sorted_out),
+         "state_in_hash": bytes(32), "state_out_hash": bytes(32)}
+    for i in range(3):
+        b[f"rom_s_in_{i}"], b[f"rom_s_out_{i}"] = f(air_pi.rom_s_in[i]), f(air_pi.rom_s_out[i])
+    zl1 = S.Zl1Proof.new_single_segment(air_pi.core.program_id, meta, air_pi.core, f(air_pi.pc_init), b, proof)
+    return S.StepProof(zl1, air_pi.core, tuple(air_pi.rom_acc), air_pi.vm_usage_mask, air_pi.ram_delta_clk_bits), summ, a
+
+
+@pytest.fixture(scope="module")
+def child(zkl, oracle):
+    return _step(zkl, oracle, 64, 7)
+
+
+def test_fs_replay_lands_on_the_prover_challenges(zkl, oracle, child):
+    R = zkl.replay
+    step, summ, a = child
+    # the replay goes through the ZKLSTP1 bytes, like an aggregator that received the proof
+    step = zkl.step.StepProof.from_bytes(step.to_bytes())
+    assert R.air_public_inputs_of(step).to_elements() == a.air_pi.to_elements()
+    fs = R.replay_fs_from_step(oracle, step)
+    assert fs.z_ood == int.from_bytes(bytes(summ.z), "little")
+    assert fs.pow_nonce == summ.pow_nonce
+    assert fs.query_positions == list(summ.positions[:summ.num_unique_queries])
+    v = step.proof.inner
+    assert len(fs.deep_coeffs) == v.main_width + len(v.constraint_rows()[0])
+    assert len(fs.fri_alphas) == v.num_fri_layers + 1
+    assert len(set(fs.deep_coeffs + fs.fri_alphas + [fs.z_ood])) == len(fs.deep_coeffs) + len(fs.fri_alphas) + 1
+    R.verify_child_openings(oracle, step, fs)
+
+
+def test_replay_with_partitions_and_more_queries(zkl, oracle):
+    """Partitioned row leaves (merge_many of partition digests, agg/child.rs:1031-1044) and duplicate query draws."""
+    R = zkl.replay
+    step, summ, _ = _step(zkl, oracle, 32, 9, queries=40, parts=(4, 8), grind=0)
+    fs = R.replay_fs_from_step(oracle, step)
+    assert fs.query_positions == list(summ.positions[:summ.num_unique_queries])
+    R.verify_child_openings(oracle, step, fs)
+
+
+def test_replay_rejects_tampered_proofs(zkl, oracle, child):
+    R, S = zkl.replay, zkl.step
+    step, _, _ = child
+    v = step.proof.inner
+    fs = R.replay_fs_from_step(oracle, step)
+
+    def with_inner(**kw):
+        return replace(step, proof=replace(step.proof, inner=replace(v, **kw)))
+
+    # a different nonce fails the grinding check or moves the query positions
+    with pytest.raises(S.InvalidInput):
+        bad = with_inner(pow_nonce=v.pow_nonce + 1)
+        fs2 = R.replay_fs_from_step(oracle, bad)
+        R.verify_child_openings(oracle, bad, fs2)
+    # public inputs are part of the coin seed
+    moved = replace(step, vm_usage_mask=step.vm_usage_mask ^ 1)
+    with pytest.raises(S.InvalidInput):
+        R.verify_child_openings(oracle, moved, R.replay_fs_from_step(oracle, moved))
+    # one flipped byte in an opened trace row, a constraint row, a FRI value, a Merkle node, the remainder
+    def flip(b, i):
+        return b[:i] + bytes([b[i] ^ 1]) + b[i + 1:]
+    layers = list(v.fri_layers)
+    layers[1] = (flip(layers[1][0], 5), layers[1][1])
+    cases = [("trace openings", dict(trace_query_values=flip(v.trace_query_values, 100))),
+             ("constraint openings", dict(constraint_query_values=flip(v.constraint_query_values, 3))),
+             ("FRI layer 1", dict(fri_layers=layers)),
+             ("trace openings", dict(trace_query_paths=flip(v.trace_query_paths, len(v.trace_query_paths) - 20))),
+             ("remainder", dict(fri_remainder=flip(v.fri_remainder, 0)))]
+    for msg, kw in cases:
+        with pytest.raises(S.InvalidInput, match=msg):
+            R.verify_child_openings(oracle, with_inner(**kw), fs)
+    with pytest.raises(S.InvalidInput):
+        R.verify_child_openings(oracle, step, replace(fs, query_positions=fs.query_positions[:-1]))
+    # commitments are absorbed by the coin: another constraint root gives another OOD point
+    c = bytearray(v.commitments)
+    c[40] ^= 1
+    try:
+        assert R.replay_fs_from_step(oracle, with_inner(commitments=bytes(c), grinding=0)).z_ood != fs.z_ood
+    except S.InvalidInput:
+        pass   # the moved query positions no longer give the recorded number of unique queries
+
+
+def test_batch_root_and_fold_positions(zkl, oracle):
+    """BatchMerkleProof::get_root against the checker's own implementation on the same openings."""
+    R = zkl.replay
+    rng = np.random.default_rng(5)
+    leaves = rng.integers(0, 256, size=(64, 32), dtype=np.uint8)
+    leaves[:, 16:] = 0
+    root, nodes = oracle.merkle_build(leaves)
+    for pos in ([5], [0, 1], [2, 3, 9, 63], [7, 6, 40], list(range(0, 64, 3))):
+        pos = sorted(pos)
+        # authentication lists built the way MerkleTree::prove_batch lays them out
+        norm = sorted({p & ~1 for p in pos})
+        lists, cur = [], []
+        for e in norm:
+            lists.append([leaves[i].tobytes() for i in (e, e + 1) if i not in pos])
+            cur.append((e + 64) >> 1)
+        for _ in range(1, 6):
+            nxt, i = [], 0
+            while i < len(cur):
+                sib = cur[i] ^ 1
+                if i + 1 < len(cur) and cur[i + 1] == sib:
+                    i += 1
+                else:
+                    lists[i].append(nodes[sib].tobytes())
+                nxt.append(sib >> 1)
+                i += 1
+            cur = nxt
+        got = R.batch_root(oracle, 6, lists, [leaves[p].tobytes() for p in pos], pos)
+        assert got == root
+        assert got == oracle.batch_root({"depth": 6, "nodes": lists}, np.stack([leaves[p] for p in pos]), pos)
+        lists[0] = lists[0][:-1]
+        with pytest.raises(zkl.step.InvalidInput):
+            R.batch_root(oracle, 6, lists, [leaves[p].tobytes() for p in pos], pos)
+    assert R.fold_positions([3, 70, 67, 5, 64 + 5], 128) == [3, 6, 5]
+    assert R.partition_size(1, 0, 204) == 204 and R.partition_size(1, 16, 7) == 16 and R.partition_size(16, 16, 219) == 16
+    assert R.partition_size(4, 8, 204) == 51

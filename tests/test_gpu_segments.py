@@ -78,6 +78,7 @@ def test_prove_program_multi_segment(ctx, zkl, oracle):
     steps = S.prove_program([ctx, ctx2], full, segs, core, feats, opts)
     assert [s.segment_index for s in steps] == [0, 1, 2, 3]
     full_cols = A.Columns.baseline()
+    summaries = {}
     for s, seg in zip(steps, segs):
         assert s.width == 204 and s.rows == seg_rows
         a = A.Air(s.width, s.rows, s.air_pi, s.options)
@@ -92,12 +93,44 @@ def test_prove_program_multi_segment(ctx, zkl, oracle):
         # same bytes as proving the host-sliced segment through the host-buffer entry point
         lay = S.SegmentLayout(full_cols, A.LayoutConfig(ram=False, merkle=False))
         host_seg = np.ascontiguousarray(full[lay.seg_to_full.astype(np.int64), seg.r_start:seg.r_end])
-        again = zkl.ZkProver(ctx, s.options, s.air_pi).prove(host_seg)
+        pv = zkl.ZkProver(ctx, s.options, s.air_pi)
+        again = pv.prove(host_seg)
         if again != s.proof:   # say what kind of difference it is: a racy kernel yields proofs that still verify
             diff = [i for i in range(min(len(again), len(s.proof))) if again[i] != s.proof[i]]
             rc2, msg2 = oracle.verify_segment(again, s.width, s.rows, ac, seed, oc)
             raise AssertionError(f"segment {s.segment_index}: {len(diff)} bytes differ from byte {diff[:1]}, lengths {len(again)} / {len(s.proof)}; "
                                  f"host-path proof verifies: {rc2 == 0} ({msg2})")
+        summaries[s.segment_index] = pv.last_summary
+    # zl1 step containers (proof/step.rs, proof/format.rs, proof/digest.rs): state hashes from the full trace, ZKLSTP1
+    # round trip preserves the digest (step_serialization.rs:48-108), commitments recombine into root_trace
+    # (transcript_basic.rs:48-60), consecutive segments chain (vm/trace/mod.rs:353-359)
+    ST = zkl.step
+    regs = lambda r: [int(full[full_cols.r_index(i), r, 0]) | (int(full[full_cols.r_index(i), r, 1]) << 64) for i in range(8)]
+    for s, seg in zip(steps, segs):
+        c = s.step
+        assert c.proof.inner_bytes == s.proof and c.proof.header.suite_id == core.program_id
+        assert (c.proof.pi.segment_index, c.proof.pi.segments_total) == (s.segment_index, len(segs))
+        assert c.state_in_hash() == ST.vm_state_hash(regs(seg.r_start)) and c.state_out_hash() == ST.vm_state_hash(regs(seg.r_end - 1))
+        assert c.proof.pi.pc_init == ST.fe_to_bytes_fold(seg.r_start // 32)
+        assert c.proof.pi.rom_s_out_1 == ST.fe_to_bytes_fold(s.air_pi.rom_s_out[1])
+        v = c.proof.inner
+        assert (v.main_width, v.trace_len, v.blowup, v.num_queries) == (s.width, s.rows, 16, 8)
+        assert (c.proof.meta.m, c.proof.meta.o, c.proof.meta.pi_len) == (seg_rows, 2, len(s.air_pi.to_elements()))
+        troots, croot, froots = v.parse_commitments()
+        assert c.proof.root_trace == zkl.blake3.blake3(b"zkl/step/root_trace" + core.program_id + troots[0] + croot + b"".join(froots))
+        back = ST.StepProof.from_bytes(c.to_bytes())
+        assert back.digest() == c.digest() and back.proof.pi == c.proof.pi and back.proof.meta == c.proof.meta
+        assert back.to_bytes() == c.to_bytes()
+        # child replay on the device hasher (agg/fs.rs:37-245, agg/child.rs:1025-1099): the challenges re-derived from the
+        # ZKLSTP1 bytes are the ones the prover used, and every opening re-hashes to its commitment
+        fs = zkl.replay.replay_fs_from_step(ctx, back)
+        summ = summaries[s.segment_index]
+        assert fs.z_ood == int.from_bytes(bytes(summ.z), "little") and fs.pow_nonce == summ.pow_nonce
+        assert fs.query_positions == list(summ.positions[:summ.num_unique_queries])
+        zkl.replay.verify_child_openings(ctx, back, fs)
+    ST.verify_chain([s.step for s in steps])
+    assert len({s.step.digest() for s in steps}) == len(steps)
+    assert ST.children_root_from_steps([s.step for s in steps]) == ST.children_root_from_steps([s.step for s in steps[::-1]])
     # the pi_prog binding exists only in the segment that starts at pc = 0 (schedule.rs:117-131)
     assert len(A.Air(204, seg_rows, steps[0].air_pi, steps[0].options).assertions) == len(A.Air(204, seg_rows, steps[1].air_pi, steps[1].options).assertions) + 1
     ctx2.close()

@@ -1,0 +1,264 @@
+"""Child-proof replay for the aggregation layer: Fiat-Shamir challenges re-derived from a step
+proof, and every Merkle opening of the proof re-hashed against its commitment — with the hashing done as batches on
+the device through the C-ABI primitives instead of one CPU sponge call at a time.
+
+Reference: zk-lisp-proof-winterfell/src/agg/fs.rs:37-245 (replay_fs_from_step, mirrors winter_verifier's transcript),
+src/agg/child.rs:162-526 (ZlChildCompact::from_step: roots, FS challenges, Merkle data), :1025-1045 (row leaf hashing
+with partitions), :1049-1068 (path folding), :1072-1099 (FRI position folding); winter-crypto DefaultRandomCoin and
+BatchMerkleProof::get_root [WF-mem].
+
+`hasher` is anything with the batch methods of `prover.Context`: hash_elements((k, len, 2) u64) -> (k, 32) u8,
+merge((k, 64) u8) -> (k, 32) u8, merge_with_int(seed32, values) -> (k, 32) u8, merge_many((k, 32) u8) -> 32 bytes.
+"""
+from dataclasses import dataclass
+from typing import List, Sequence
+
+import numpy as np
+
+from . import air as A
+from .field import P
+from .step import InnerProof, InvalidInput, StepProof, _Reader, fe_from_bytes_fold
+
+
+def _ints_to_fe(xs) -> np.ndarray:
+    out = np.empty((len(xs), 2), dtype=np.uint64)
+    for i, x in enumerate(xs):
+        out[i, 0], out[i, 1] = x & 0xFFFFFFFFFFFFFFFF, x >> 64
+    return out
+
+
+def _digest_fe(d: bytes) -> int:
+    """draw::<BaseElement>: the first 16 digest bytes; always canonical for this hasher (utils.rs:375-381)."""
+    v = int.from_bytes(d[:16], "little")
+    if v >= P:
+        raise InvalidInput("failed to draw a field element in FS replay")
+    return v
+
+
+class Coin:
+    """winter-crypto DefaultRandomCoin over the zk-lisp hasher [WF-mem]."""
+
+    def __init__(self, hasher, seed_elems: Sequence[int]):
+        self.h = hasher
+        self.seed = self.h.hash_elements(_ints_to_fe(seed_elems).reshape(1, -1, 2))[0].tobytes()
+        self.counter = 0
+
+    def reseed(self, digest: bytes):
+        self.seed = self.h.merge(np.frombuffer(self.seed + bytes(digest), dtype=np.uint8).reshape(1, 64))[0].tobytes()
+        self.counter = 0
+
+    def draw_many(self, k: int) -> List[int]:
+        """k consecutive `draw()` calls as ONE batch of merge_with_int(seed, counter + 1 .. counter + k)."""
+        if k == 0:
+            return []
+        ctrs = np.arange(self.counter + 1, self.counter + 1 + k, dtype=np.uint64)
+        self.counter += k
+        return [_digest_fe(d.tobytes()) for d in self.h.merge_with_int(self.seed, ctrs)]
+
+    def draw(self) -> int:
+        return self.draw_many(1)[0]
+
+    def check_leading_zeros(self, value: int) -> int:
+        d = self.h.merge_with_int(self.seed, np.array([value], dtype=np.uint64))[0].tobytes()
+        head = int.from_bytes(d[:8], "little")
+        return 64 if head == 0 else (head & -head).bit_length() - 1
+
+    def draw_integers(self, k: int, domain: int, nonce: int) -> List[int]:
+        self.seed = self.h.merge_with_int(self.seed, np.array([nonce], dtype=np.uint64))[0].tobytes()
+        self.counter = k
+        out = self.h.merge_with_int(self.seed, np.arange(1, k + 1, dtype=np.uint64))
+        return [int.from_bytes(d.tobytes()[:8], "little") & (domain - 1) for d in out]
+
+
+@dataclass
+class FsChallenges:
+    """agg/child.rs ZlFsChallenges."""
+    z_ood: int
+    deep_coeffs: List[int]
+    fri_alphas: List[int]
+    query_positions: List[int]
+    pow_nonce: int
+
+
+def air_public_inputs_of(step: StepProof) -> A.AirPublicInputs:
+    """agg/fs.rs:43-66."""
+    pi = step.proof.pi
+    f = fe_from_bytes_fold
+    return A.AirPublicInputs(core=step.pi_core, segment_feature_mask=0, rom_acc=tuple(step.rom_acc), pc_init=f(pi.pc_init),
+                             ram_gp_unsorted_in=f(pi.ram_gp_unsorted_in), ram_gp_unsorted_out=f(pi.ram_gp_unsorted_out),
+                             ram_gp_sorted_in=f(pi.ram_gp_sorted_in), ram_gp_sorted_out=f(pi.ram_gp_sorted_out),
+                             rom_s_in=(f(pi.rom_s_in_0), f(pi.rom_s_in_1), f(pi.rom_s_in_2)),
+                             rom_s_out=(f(pi.rom_s_out_0), f(pi.rom_s_out_1), f(pi.rom_s_out_2)),
+                             vm_usage_mask=step.vm_usage_mask, ram_delta_clk_bits=step.ram_delta_clk_bits)
+
+
+def _options_of(v: InnerProof) -> A.ProofOptions:
+    return A.ProofOptions(num_queries=v.num_queries, blowup=v.blowup, grinding=v.grinding, num_partitions=v.num_partitions,
+                          hash_rate=v.hash_rate, fri_folding=v.fri_folding, fri_remainder_max_degree=v.fri_remainder_max_degree,
+                          field_extension=v.field_extension)
+
+
+def replay_fs_from_step(hasher, step: StepProof) -> FsChallenges:
+    """agg/fs.rs:37-245. Everything comes from the step-proof bytes: the context elements from the proof's own context,
+    the number of composition columns from the width of the opened constraint rows."""
+    v = step.proof.inner
+    if v.aux_width != 0:
+        raise InvalidInput("multi-segment trace must provide at least two trace commitments")
+    seed = A.context_to_elements(v.main_width, v.trace_len, v.num_constraints, _options_of(v)) + air_public_inputs_of(step).to_elements()
+    coin = Coin(hasher, seed)
+    try:
+        trace_roots, constraint_root, fri_roots = v.parse_commitments()
+    except InvalidInput:
+        raise InvalidInput("invalid Winterfell commitments layout in FS replay")
+    # 1) main trace commitment (the composition coefficients drawn here do not survive the next reseed)
+    coin.reseed(trace_roots[0])
+    # 2) constraint commitment, OOD point
+    coin.reseed(constraint_root)
+    z = coin.draw()
+    # 3) OOD frame: current(z) || quotient(z) || next(zg) || quotient(zg), hashed and absorbed
+    W = v.main_width
+    if len(v.ood_trace) != 2 * 16 * W or len(v.ood_constraints) % 32 or not v.ood_constraints:
+        raise InvalidInput("invalid OOD frame layout in FS replay")
+    C = len(v.ood_constraints) // 32
+    ood = v.ood_trace[:16 * W] + v.ood_constraints[:16 * C] + v.ood_trace[16 * W:] + v.ood_constraints[16 * C:]
+    elems = np.frombuffer(ood, dtype=np.uint64).reshape(1, 2 * (W + C), 2)
+    coin.reseed(hasher.hash_elements(elems)[0].tobytes())
+    # 4) DEEP coefficients: one per trace column, then one per composition column
+    deep = coin.draw_many(W + C)
+    # 5) FRI layer alphas (the last root is the remainder commitment)
+    alphas, max_degree_plus_1 = [], v.trace_len
+    for depth, root in enumerate(fri_roots):
+        coin.reseed(root)
+        alphas.append(coin.draw())
+        if depth != len(fri_roots) - 1 and max_degree_plus_1 % v.fri_folding:
+            raise InvalidInput("FRI degree truncation detected while replaying FS challenges")
+        max_degree_plus_1 //= v.fri_folding
+    # 6) proof of work, query positions
+    if coin.check_leading_zeros(v.pow_nonce) < v.grinding:
+        raise InvalidInput("pow_nonce does not satisfy grinding factor in FS replay")
+    positions = sorted(set(coin.draw_integers(v.num_queries, v.lde_domain_size, v.pow_nonce)))
+    if len(positions) != v.num_unique_queries:
+        raise InvalidInput("unique query positions count does not match proof.num_unique_queries")
+    return FsChallenges(z, deep, alphas, positions, v.pow_nonce)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Merkle openings
+# ---------------------------------------------------------------------------------------------------------------
+def read_batch_proof(data: bytes):
+    """BatchMerkleProof::read_from [WF-mem]: depth u8, number of lists, then per list its length and digests."""
+    r = _Reader(bytes(data))
+    depth = r.u8()
+    lists = [[r.take(32) for _ in range(r.usize())] for _ in range(r.usize())]
+    if r.i != len(r.b):
+        raise InvalidInput("trailing bytes in batch Merkle proof")
+    return depth, lists
+
+
+def fold_positions(positions: Sequence[int], source_domain: int, folding: int = 2) -> List[int]:
+    """agg/child.rs:1072-1099: positions mod the folded domain, first occurrence order, no duplicates."""
+    target = source_domain // folding
+    out = []
+    for p in positions:
+        q = p % target
+        if q not in out:
+            out.append(q)
+    return out
+
+
+def partition_size(num_partitions: int, hash_rate: int, cols: int) -> int:
+    """PartitionOptions::partition_size [WF-mem] (csrc: partition_size_of)."""
+    if num_partitions == 1 and hash_rate == 0:
+        return cols
+    return max(-(-cols // num_partitions), hash_rate)
+
+
+def hash_rows(hasher, rows: np.ndarray, psize: int) -> List[bytes]:
+    """agg/child.rs:1025-1045 for a batch of rows (k, W, 2): one hash_elements batch per partition, then merge_many."""
+    k, W = rows.shape[0], rows.shape[1]
+    digests = [hasher.hash_elements(np.ascontiguousarray(rows[:, i:i + psize])) for i in range(0, W, psize)]
+    if len(digests) == 1:
+        return [d.tobytes() for d in digests[0]]
+    return [hasher.merge_many(np.stack([d[q] for d in digests])) for q in range(k)]
+
+
+def batch_root(hasher, depth: int, lists: List[List[bytes]], leaves: Sequence[bytes], positions: Sequence[int]) -> bytes:
+    """BatchMerkleProof::get_root [WF-mem]: the root implied by `leaves` opened at `positions`; the merges of one tree level
+    are ONE batch."""
+    if depth < 1 or len(leaves) != len(positions) or not positions:
+        raise InvalidInput("malformed batch Merkle opening")
+    n = 1 << depth
+    known = {p: bytes(l) for p, l in zip(positions, leaves)}
+    norm = sorted({p & ~1 for p in positions})
+    if len(norm) != len(lists) or max(positions) >= n:
+        raise InvalidInput("malformed batch Merkle opening")
+    ptr = [0] * len(lists)
+
+    def take(s):
+        if ptr[s] >= len(lists[s]):
+            raise InvalidInput("malformed batch Merkle opening")
+        ptr[s] += 1
+        return lists[s][ptr[s] - 1]
+
+    def merge(pairs):
+        return [d.tobytes() for d in hasher.merge(np.frombuffer(b"".join(pairs), dtype=np.uint8).reshape(-1, 64))]
+
+    pairs = []
+    for i, e in enumerate(norm):
+        lo = known[e] if e in known else take(i)
+        hi = known[e + 1] if e + 1 in known else take(i)
+        pairs.append(lo + hi)
+    cur, vals = [(e + n) >> 1 for e in norm], merge(pairs)
+    for _ in range(1, depth):
+        ncur, pairs, i = [], [], 0
+        while i < len(cur):
+            me, sib, used = vals[i], cur[i] ^ 1, i
+            if i + 1 < len(cur) and cur[i + 1] == sib:
+                sv = vals[i + 1]
+                i += 1
+            else:
+                sv = take(used)
+            pairs.append(sv + me if cur[used] & 1 else me + sv)
+            ncur.append(sib >> 1)
+            i += 1
+        cur, vals = ncur, merge(pairs)
+    if cur != [1] or any(ptr[s] != len(lists[s]) for s in range(len(lists))):
+        raise InvalidInput("malformed batch Merkle opening")
+    return vals[0]
+
+
+def verify_child_openings(hasher, step: StepProof, fs: FsChallenges) -> None:
+    """Every opening of the child proof re-hashed against its commitment: trace rows and constraint rows at the query
+    positions, FRI layer pairs at the folded positions, the remainder against the last FRI commitment."""
+    v = step.proof.inner
+    trace_roots, constraint_root, fri_roots = v.parse_commitments()
+    pos = fs.query_positions
+    k = len(pos)
+    rows = np.frombuffer(v.trace_query_values, dtype=np.uint64)
+    if rows.size != k * v.main_width * 2:
+        raise InvalidInput("invalid trace queries layout in ZlChildTranscript")
+    leaves = hash_rows(hasher, rows.reshape(k, v.main_width, 2), partition_size(v.num_partitions, v.hash_rate, v.main_width))
+    if batch_root(hasher, *read_batch_proof(v.trace_query_paths), leaves, pos) != trace_roots[0]:
+        raise InvalidInput("trace openings do not match the trace commitment")
+    C = len(v.constraint_query_values) // (16 * k)
+    crow = np.frombuffer(v.constraint_query_values, dtype=np.uint64)
+    if C == 0 or crow.size != k * C * 2:
+        raise InvalidInput("failed to decode constraint query values in ZlChildTranscript")
+    leaves = hash_rows(hasher, crow.reshape(k, C, 2), partition_size(v.num_partitions, v.hash_rate, C))
+    if batch_root(hasher, *read_batch_proof(v.constraint_query_paths), leaves, pos) != constraint_root:
+        raise InvalidInput("constraint openings do not match the constraint commitment")
+    if len(v.fri_layers) != v.num_fri_layers:
+        raise InvalidInput("FRI layer count does not match the proof options")
+    domain, positions = v.lde_domain_size, list(pos)
+    for d, (values, paths) in enumerate(v.fri_layers):
+        positions = fold_positions(positions, domain, v.fri_folding)
+        pairs = np.frombuffer(values, dtype=np.uint64)
+        if pairs.size != len(positions) * v.fri_folding * 2:
+            raise InvalidInput("FRI layer value count does not match the folded positions")
+        leaves = [x.tobytes() for x in hasher.hash_elements(pairs.reshape(len(positions), v.fri_folding, 2))]
+        if batch_root(hasher, *read_batch_proof(paths), leaves, positions) != fri_roots[d]:
+            raise InvalidInput(f"FRI layer {d} openings do not match the layer commitment")
+        domain //= v.fri_folding
+    rem = np.frombuffer(v.fri_remainder, dtype=np.uint64)
+    if rem.size == 0 or rem.size % 2 or hasher.hash_elements(rem.reshape(1, -1, 2))[0].tobytes() != fri_roots[-1]:
+        raise InvalidInput("FRI remainder does not match its commitment")

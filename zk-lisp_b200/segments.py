@@ -6,7 +6,7 @@ The reference builds the FULL trace once (prove.rs:983), then per segment slices
 (prove.rs:1289-1392) and proves the segment; segments are independent and run on a rayon pool (prove.rs:1020-1048).
 Here the full trace is uploaded once, slicing / scanning / cell reads are device kernels, and segments are proven on
 a pool of contexts (one CUDA stream each, possibly on different GPUs) — no collective on the data path.
-The segment planner (which rows form a segment) and the compiler's per-level features stay inputs.
+The planner policy lives in planner.py, the zl1 step container in step.py; the compiler's per-level op kinds stay inputs.
 """
 import ctypes as C
 import threading
@@ -17,6 +17,7 @@ import numpy as np
 
 from . import air as A
 from . import capi
+from . import step as S
 from .prover import Context, ZkProver, as_fe_array, fe_to_ints
 
 
@@ -56,7 +57,7 @@ def compute_segment_feature_mask(core_mask: int, f: SegmentFeatures) -> int:
 
 def plan_fixed_segments(total_rows: int, max_segment_rows: int = 4096) -> List[Segment]:
     """Level-aligned fixed-size segments (the shape WinterfellSegmentPlanner produces for a uniform program,
-    segment_planner.rs:24,92; the planner policy itself is out of scope)."""
+    segment_planner.rs:24,92; planner.plan_segments is the general policy)."""
     assert total_rows % 32 == 0 and max_segment_rows % 32 == 0
     return [Segment(r, min(r + max_segment_rows, total_rows)) for r in range(0, total_rows, max_segment_rows)]
 
@@ -109,6 +110,7 @@ class StepProof:
     width: int
     rows: int
     options: A.ProofOptions
+    step: Optional[S.StepProof] = None   # zl1 container: digest, state hashes, ZKLSTP1 bytes (proof/step.rs)
 
 
 class DeviceTrace:
@@ -142,8 +144,10 @@ def read_cells(ctx: Context, dev, n_rows: int, cells) -> List[int]:
 
 
 def prove_segment(ctx: Context, full: DeviceTrace, seg: Segment, index: int, total: int, core: A.PublicInputs,
-                  features: SegmentFeatures, base_opts: A.ProofOptions) -> StepProof:
-    """prove.rs:1057-1175 for one segment; the full trace must live on ctx's device."""
+                  features: SegmentFeatures, base_opts: A.ProofOptions, rom_acc=(0, 0, 0), min_bits: int = 64) -> StepProof:
+    """prove.rs:1057-1175 for one segment; the full trace must live on ctx's device. `rom_acc` is the program's ROM
+    accumulator (romacc.rs, an input like the program itself), `min_bits` the requested security level echoed in the
+    step metadata (prove.rs:959,1135)."""
     full_cols = A.Columns.baseline()
     base_mask = core.feature_mask
     seg_mask = compute_segment_feature_mask(base_mask, features)
@@ -167,6 +171,8 @@ def prove_segment(ctx: Context, full: DeviceTrace, seg: Segment, index: int, tot
                  (fc.ram_start + 6, seg.r_start), (fc.ram_start + 6, seg.r_end - 1),
                  (fc.ram_start + 7, seg.r_start), (fc.ram_start + 7, seg.r_end - 1)]
         cells += [(fc.rom_s_start + i, row_map_first) for i in range(3)] + [(fc.rom_s_start + i, row_final_last) for i in range(3)]
+        # register file at the segment's first map row and at its last row: VM state hashes (vm/trace/mod.rs:344-351)
+        cells += [(fc.r_index(i), seg.r_start) for i in range(A.NR)] + [(fc.r_index(i), seg.r_end - 1) for i in range(A.NR)]
         v = read_cells(ctx, full.dev, full.rows, cells)
         # gadget usage scan over the segment trace (prove.rs:1289-1392)
         mask, bits = C.c_uint32(), C.c_uint32()
@@ -175,19 +181,28 @@ def prove_segment(ctx: Context, full: DeviceTrace, seg: Segment, index: int, tot
         air_pi = A.AirPublicInputs(core=core, segment_feature_mask=eff_mask, pc_init=v[0], ram_gp_unsorted_in=v[1],
                                    ram_gp_unsorted_out=v[2], ram_gp_sorted_in=v[3], ram_gp_sorted_out=v[4],
                                    rom_s_in=tuple(v[5:8]), rom_s_out=tuple(v[8:11]), vm_usage_mask=mask.value,
-                                   ram_delta_clk_bits=bits.value)
+                                   ram_delta_clk_bits=bits.value, rom_acc=tuple(rom_acc))
         num_partitions, hash_rate = A.select_partitions_for_trace(W, n)                  # prove.rs:1106
         opts = replace(base_opts, num_partitions=num_partitions, hash_rate=hash_rate)
         prover = ZkProver(ctx, opts, air_pi)
         proof = prover.prove(None, dev_ptr=seg_dev, shape=(W, n))
     finally:
         ctx.lib.zkl_dev_free(ctx.h, seg_dev)
-    return StepProof(index, total, proof, air_pi, W, n, opts)
+    # zl1 container (prove.rs:1135-1172): suite_id = program_id (prove.rs:985)
+    meta = S.StepMeta.from_env(n, opts.blowup, opts.num_queries, min_bits, len(air_pi.to_elements()))
+    names = ("ram_gp_unsorted_in", "ram_gp_unsorted_out", "ram_gp_sorted_in", "ram_gp_sorted_out", "rom_s_in_0", "rom_s_in_1",
+             "rom_s_in_2", "rom_s_out_0", "rom_s_out_1", "rom_s_out_2")
+    boundaries = {name: S.fe_to_bytes_fold(x) for name, x in zip(names, v[1:11])}
+    boundaries["state_in_hash"] = S.vm_state_hash(v[11:11 + A.NR])
+    boundaries["state_out_hash"] = S.vm_state_hash(v[11 + A.NR:11 + 2 * A.NR])
+    zl1 = S.Zl1Proof.new_multi_segment(core.program_id, meta, core, index, total, S.fe_to_bytes_fold(v[0]), boundaries, proof)
+    step = S.StepProof(zl1, core, tuple(rom_acc), mask.value, bits.value)
+    return StepProof(index, total, proof, air_pi, W, n, opts, step)
 
 
 def prove_program(contexts: Sequence[Context], full_trace: np.ndarray, segments: Sequence[Segment], core: A.PublicInputs,
                   features: Sequence[SegmentFeatures], base_opts: A.ProofOptions,
-                  device_traces: Optional[dict] = None) -> List[StepProof]:
+                  device_traces: Optional[dict] = None, rom_acc=(0, 0, 0), min_bits: int = 64) -> List[StepProof]:
     """prove.rs:954-1051: one worker per context (the rayon pool of `max_concurrent_segments` threads); segment i is
     proven by worker i mod len(contexts). Contexts may live on different GPUs: the full trace is uploaded once per device."""
     if not segments:
@@ -203,7 +218,8 @@ def prove_program(contexts: Sequence[Context], full_trace: np.ndarray, segments:
     def worker(w):
         try:
             for i in range(w, len(segments), len(contexts)):
-                out[i] = prove_segment(contexts[w], traces[contexts[w].device], segments[i], i, len(segments), core, features[i], base_opts)
+                out[i] = prove_segment(contexts[w], traces[contexts[w].device], segments[i], i, len(segments), core, features[i], base_opts,
+                                       rom_acc, min_bits)
         except Exception as e:  # surfaced to the caller like the reference's Error::Backend
             with lock:
                 errors.append(e)
