@@ -8,25 +8,17 @@ import numpy as np
 import pytest
 
 import synth
+from util import single_segment_step
 
 
 def _step(zkl, oracle, n, seed, queries=8, parts=None, grind=4):
-    S = zkl.step
     trace, air_pi, opts = synth.valid_segment(n=n, queries=queries, blowup=16, grind=grind, seed=seed)
     if parts:
         opts = replace(opts, num_partitions=parts[0], hash_rate=parts[1])
     a = zkl.air.Air(trace.shape[0], n, air_pi, opts)
     summ = zkl.capi.ProofSummary()
     proof = oracle.prove_segment(trace, a.to_c(), zkl.prover.ints_to_fe(a.seed_elements()), opts.to_c(), summ)
-    meta = S.StepMeta.from_env(n, opts.blowup, opts.num_queries, 64, len(air_pi.to_elements()))
-    f = S.fe_to_bytes_fold
-    b = {"ram_gp_unsorted_in": f(air_pi.ram_gp_unsorted_in), "ram_gp_unsorted_out": f(air_pi.ram_gp_unsorted_out),
-         "ram_gp_sorted_in": f(air_pi.ram_gp_sorted_in), "ram_gp_sorted_out": f(air_pi.ram_gp_sorted_out),
-         "state_in_hash": bytes(32), "state_out_hash": bytes(32)}
-    for i in range(3):
-        b[f"rom_s_in_{i}"], b[f"rom_s_out_{i}"] = f(air_pi.rom_s_in[i]), f(air_pi.rom_s_out[i])
-    zl1 = S.Zl1Proof.new_single_segment(air_pi.core.program_id, meta, air_pi.core, f(air_pi.pc_init), b, proof)
-    return S.StepProof(zl1, air_pi.core, tuple(air_pi.rom_acc), air_pi.vm_usage_mask, air_pi.ram_delta_clk_bits), summ, a
+    return single_segment_step(zkl, air_pi, opts, n, proof), summ, a
 
 
 @pytest.fixture(scope="module")

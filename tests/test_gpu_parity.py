@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 import synth
-from util import P, fast_random_trace, from_fe, rand_fe, splitmix_trace, to_fe
+from util import P, fast_random_trace, from_fe, rand_fe, single_segment_step, splitmix_trace, to_fe
 
 pytestmark = pytest.mark.gpu
 
@@ -214,8 +214,15 @@ def test_full_size_segment_properties(ctx, zkl):
     pos = [int(x) for x in s1.positions[:s1.num_unique_queries]]
     rows, bp = lde.query(pos)
     leaves = ctx.hash_elements(rows)
-    # recompute the root from one opened leaf and its sibling path taken from the full tree
     lde.free()
+    # every opening of the proof (trace rows, constraint rows, 11 FRI layers, remainder) re-hashed on the device against its
+    # commitment, at the positions a Fiat-Shamir replay of the proof bytes arrives at (replay.py after agg/fs.rs:37-245)
+    step = single_segment_step(zkl, air_pi, opts, n, p1)
+    fs = zkl.replay.replay_fs_from_step(ctx, zkl.step.StepProof.from_bytes(step.to_bytes()))
+    assert fs.query_positions == pos and fs.pow_nonce == nonce1 and fs.z_ood == int.from_bytes(bytes(s1.z), "little")
+    assert len(fs.fri_alphas) == 12 and len(fs.deep_coeffs) == 204 + 7
+    zkl.replay.verify_child_openings(ctx, step, fs)
+    assert [bytes(x) for x in leaves] == zkl.replay.hash_rows(ctx, rows, 204)
     bad = trace.copy()
     bad[43, 100, 0] ^= np.uint64(1)  # register r1 on a carry row
     prover.prove(bad)

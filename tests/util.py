@@ -55,3 +55,18 @@ def fast_random_trace(width: int, n: int, seed: int) -> np.ndarray:
     out[..., 1] = out[..., 1] >> np.uint64(1)  # < 2^63 < p's high limb
     out[..., 0] |= rng.integers(0, 2, size=(width, n), dtype=np.uint64)
     return out
+
+
+def single_segment_step(zkl, air_pi, opts, n, proof, min_bits=64):
+    """zl1 step container of a single-segment proof, boundary values taken from the AIR public inputs
+    (what prove.rs:1108-1172 assembles around the inner proof)."""
+    S = zkl.step
+    f = S.fe_to_bytes_fold
+    meta = S.StepMeta.from_env(n, opts.blowup, opts.num_queries, min_bits, len(air_pi.to_elements()))
+    b = {"ram_gp_unsorted_in": f(air_pi.ram_gp_unsorted_in), "ram_gp_unsorted_out": f(air_pi.ram_gp_unsorted_out),
+         "ram_gp_sorted_in": f(air_pi.ram_gp_sorted_in), "ram_gp_sorted_out": f(air_pi.ram_gp_sorted_out),
+         "state_in_hash": bytes(32), "state_out_hash": bytes(32)}
+    for i in range(3):
+        b[f"rom_s_in_{i}"], b[f"rom_s_out_{i}"] = f(air_pi.rom_s_in[i]), f(air_pi.rom_s_out[i])
+    zl1 = S.Zl1Proof.new_single_segment(air_pi.core.program_id, meta, air_pi.core, f(air_pi.pc_init), b, proof)
+    return S.StepProof(zl1, air_pi.core, tuple(air_pi.rom_acc), air_pi.vm_usage_mask, air_pi.ram_delta_clk_bits)
