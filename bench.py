@@ -146,7 +146,7 @@ def run_reference(args, zkl, rank, world):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    threads = min(cores, 64)
+    threads = min(cores, 256)
     rows, grind = 512, 13
     vals = []
     for _ in range(max(1, min(args.steps, 2))):
@@ -333,7 +333,7 @@ def main():
         }
         cpu = None
         if not args.no_cpu_baseline and world == 1:
-            cores = min(os.cpu_count() or 1, 64)
+            cores = min(os.cpu_count() or 1, 256)
             v, dt = cpu_reference_run(zkl, cores, 512, 13)
             cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": f"{cores} segments in flight, n=512, W=204, blowup=16, q=64, grind=13 ({dt:.1f} s of wall time)"}
