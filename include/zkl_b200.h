@@ -129,6 +129,16 @@ int zkl_merge_batch(zkl_ctx *ctx, const uint8_t *pairs /* count*64 */, size_t co
                     uint8_t *out_digests);
 int zkl_merge_with_int_batch(zkl_ctx *ctx, const uint8_t seed[32], const uint64_t *values,
                              size_t count, uint8_t *out_digests);
+/* Batched Merkle authentication for the child-proof replay (agg/child.rs:1049-1068 `merkle_root_from_leaf` per path and
+ * winter-crypto BatchMerkleProof::get_root per batch opening, here for every tree of every child at once).
+ * A flat digest table starts with the `num_known` given digests (opened leaves and the proofs' nodes); level l appends
+ * level_counts[l] entries, entry i of that level = merge(table[left[k+i]], table[right[k+i]]) with k the running offset
+ * into left/right; indices may only refer to entries that exist before the level starts. The levels run back to back
+ * on the device (one gather + one merge launch each), no host round trip in between; `want` selects the table entries
+ * copied back (the recomputed roots). */
+int zkl_merge_plan(zkl_ctx *ctx, const uint8_t *known /* num_known*32 */, size_t num_known, const uint32_t *left,
+                   const uint32_t *right, const uint32_t *level_counts, size_t num_levels, const uint32_t *want,
+                   size_t num_want, uint8_t *out_digests /* num_want*32 */);
 int zkl_hash_bytes(zkl_ctx *ctx, const uint8_t *data, size_t len, uint8_t out[32]);
 int zkl_merge_many(zkl_ctx *ctx, const uint8_t *digests, size_t count, uint8_t out[32]);
 /* MerkleTree::new over `count` leaves (power of two); out_nodes[i], i in 1..count, is the

@@ -129,3 +129,62 @@ def test_batch_root_and_fold_positions(zkl, oracle):
     assert R.fold_positions([3, 70, 67, 5, 64 + 5], 128) == [3, 6, 5]
     assert R.partition_size(1, 0, 204) == 204 and R.partition_size(1, 16, 7) == 16 and R.partition_size(16, 16, 219) == 16
     assert R.partition_size(4, 8, 204) == 51
+
+
+class _PlanHasher:
+    """The checker's batch methods + `merge_plan` restated with numpy (the contract of zkl_merge_plan in include/zkl_b200.h)."""
+
+    def __init__(self, oracle):
+        self.o = oracle
+        self.hash_elements, self.merge = oracle.hash_elements, oracle.merge
+        self.merge_with_int, self.merge_many = oracle.merge_with_int, oracle.merge_many
+        self.calls = 0
+
+    def merge_plan(self, known, left, right, level_counts, want):
+        self.calls += 1
+        table = [bytes(k) for k in np.asarray(known).reshape(-1, 32)]
+        off = 0
+        for cnt in level_counts:
+            cnt = int(cnt)
+            assert cnt > 0 and max(left[off:off + cnt].max(), right[off:off + cnt].max()) < len(table)
+            pairs = np.frombuffer(b"".join(table[l] + table[r] for l, r in zip(left[off:off + cnt], right[off:off + cnt])), dtype=np.uint8)
+            table += [d.tobytes() for d in self.o.merge(pairs.reshape(cnt, 64))]
+            off += cnt
+        assert off == len(left) == len(right)
+        return np.frombuffer(b"".join(table[w] for w in want), dtype=np.uint8).reshape(-1, 32)
+
+
+def test_children_openings_in_one_merge_plan(zkl, oracle, child):
+    """All trees of all children authenticated by ONE merge schedule (trace, constraint, every FRI layer; children of
+    different sizes and partitionings side by side)."""
+    R, S = zkl.replay, zkl.step
+    h = _PlanHasher(oracle)
+    kids = [child[0], _step(zkl, oracle, 32, 9, queries=40, parts=(4, 8), grind=0)[0], _step(zkl, oracle, 64, 11)[0]]
+    fss = [R.replay_fs_from_step(h, k) for k in kids]
+    R.verify_children_openings(h, kids, fss)
+    assert h.calls == 1
+    # schedule shape: indices only refer to earlier entries, one root per tree
+    plan = R.MergePlan()
+    v = kids[0].proof.inner
+    leaves = R.hash_rows(h, np.frombuffer(v.trace_query_values, dtype=np.uint64).reshape(len(fss[0].query_positions), v.main_width, 2), v.main_width)
+    plan.add_opening(*R.read_batch_proof(v.trace_query_paths), leaves, fss[0].query_positions, v.parse_commitments()[0][0], "trace")
+    known, left, right, counts, want = plan.flatten()
+    assert len(counts) == 10 and counts[-1] == 1 and len(want) == 1          # 1024 LDE rows -> depth 10
+    assert int(counts.sum()) == len(left) and want[0] == len(known) + len(left) - 1
+    plan.run(h)
+    # tampering is reported with the child and the tree it belongs to
+    def flip(b, i):
+        return b[:i] + bytes([b[i] ^ 1]) + b[i + 1:]
+    v2 = kids[2].proof.inner
+    layers = list(v2.fri_layers)
+    layers[3] = (layers[3][0], flip(layers[3][1], len(layers[3][1]) - 5))
+    cases = [(1, dict(trace_query_values=flip(kids[1].proof.inner.trace_query_values, 7)), "child 1: trace openings"),
+             (2, dict(fri_layers=layers), "child 2: FRI layer 3"),
+             (0, dict(constraint_query_paths=flip(v.constraint_query_paths, 40)), "child 0: constraint openings"),
+             (2, dict(fri_remainder=flip(v2.fri_remainder, 17)), "child 2: FRI remainder")]
+    for ci, kw, msg in cases:
+        bad = list(kids)
+        bad[ci] = replace(kids[ci], proof=replace(kids[ci].proof, inner=replace(kids[ci].proof.inner, **kw)))
+        with pytest.raises(S.InvalidInput, match=msg):
+            R.verify_children_openings(h, bad, fss)
+    R.verify_children_openings(h, [], [])

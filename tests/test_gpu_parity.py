@@ -222,12 +222,44 @@ def test_full_size_segment_properties(ctx, zkl):
     assert fs.query_positions == pos and fs.pow_nonce == nonce1 and fs.z_ood == int.from_bytes(bytes(s1.z), "little")
     assert len(fs.fri_alphas) == 12 and len(fs.deep_coeffs) == 204 + 7
     zkl.replay.verify_child_openings(ctx, step, fs)
+    zkl.replay.verify_children_openings(ctx, [step, step], [fs, fs])      # the same through one device merge plan
     assert [bytes(x) for x in leaves] == zkl.replay.hash_rows(ctx, rows, 204)
     bad = trace.copy()
     bad[43, 100, 0] ^= np.uint64(1)  # register r1 on a carry row
     prover.prove(bad)
     assert prover.last_summary.stage_ms[11] == -1.0
     assert leaves.shape == (len(pos), 32)
+
+
+def test_merge_plan_contract(ctx, zkl, oracle):
+    """zkl_merge_plan (include/zkl_b200.h): a full tree written as a merge schedule gives MerkleTree::new's root; a schedule
+    with shared and reordered operands follows the table semantics; malformed schedules are refused before any launch."""
+    rng = np.random.default_rng(11)
+    for count in (2, 8, 4096):
+        leaves = rng.integers(0, 256, size=(count, 32), dtype=np.uint8)
+        leaves[:, 16:] = 0
+        leaves[:, 15] &= 0x7F
+        left, right, counts, base, width = [], [], [], 0, count
+        while width > 1:
+            left += [base + 2 * i for i in range(width // 2)]
+            right += [base + 2 * i + 1 for i in range(width // 2)]
+            counts.append(width // 2)
+            base += width
+            width //= 2
+        got = ctx.merge_plan(leaves, left, right, counts, [base, base - 1 if count > 2 else 0])
+        root, nodes = oracle.merkle_build(leaves)
+        assert got[0].tobytes() == root
+        if count > 2:
+            assert got[1].tobytes() == nodes[3].tobytes()
+    # operands may be reused and taken from any earlier level: t3 = merge(k1, k0), t4 = merge(t3, t3), t5 = merge(k2, t3)
+    k = leaves[:3]
+    got = ctx.merge_plan(k, [1, 3, 2], [0, 3, 3], [1, 2], [3, 4, 5, 0])
+    m = lambda a, b: oracle.merge(np.frombuffer(a + b, dtype=np.uint8).reshape(1, 64))[0].tobytes()
+    t3 = m(k[1].tobytes(), k[0].tobytes())
+    assert [g.tobytes() for g in got] == [t3, m(t3, t3), m(k[2].tobytes(), t3), k[0].tobytes()]
+    for bad in (([3], [0], [1], [3]), ([0], [1], [1], [5]), ([0, 4], [1, 0], [2], [3])):
+        with pytest.raises(zkl.capi.ZklError, match="merge plan"):
+            ctx.merge_plan(k, *bad)
 
 
 @pytest.mark.parametrize("n,blowup", [(16384, 4), (32768, 2), (65536, 2)])

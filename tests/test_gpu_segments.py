@@ -106,6 +106,7 @@ def test_prove_program_multi_segment(ctx, zkl, oracle):
     # (transcript_basic.rs:48-60), consecutive segments chain (vm/trace/mod.rs:353-359)
     ST = zkl.step
     regs = lambda r: [int(full[full_cols.r_index(i), r, 0]) | (int(full[full_cols.r_index(i), r, 1]) << 64) for i in range(8)]
+    challenges = []
     for s, seg in zip(steps, segs):
         c = s.step
         assert c.proof.inner_bytes == s.proof and c.proof.header.suite_id == core.program_id
@@ -128,6 +129,18 @@ def test_prove_program_multi_segment(ctx, zkl, oracle):
         assert fs.z_ood == int.from_bytes(bytes(summ.z), "little") and fs.pow_nonce == summ.pow_nonce
         assert fs.query_positions == list(summ.positions[:summ.num_unique_queries])
         zkl.replay.verify_child_openings(ctx, back, fs)
+        challenges.append(fs)
+    # ... and all four children at once: leaves in three hashing batches, every tree in ONE device merge plan (zkl_merge_plan)
+    before = ctx.launches
+    zkl.replay.verify_children_openings(ctx, [s.step for s in steps], challenges)
+    assert ctx.launches > before
+    tampered = [s.step for s in steps]
+    inner = tampered[2].proof.inner
+    bad_rows = inner.trace_query_values[:9] + bytes([inner.trace_query_values[9] ^ 4]) + inner.trace_query_values[10:]
+    from dataclasses import replace
+    tampered[2] = replace(tampered[2], proof=replace(tampered[2].proof, inner=replace(inner, trace_query_values=bad_rows)))
+    with pytest.raises(ST.InvalidInput, match="child 2: trace openings"):
+        zkl.replay.verify_children_openings(ctx, tampered, challenges)
     ST.verify_chain([s.step for s in steps])
     assert len({s.step.digest() for s in steps}) == len(steps)
     assert ST.children_root_from_steps([s.step for s in steps]) == ST.children_root_from_steps([s.step for s in steps[::-1]])

@@ -484,6 +484,46 @@ extern "C" int zkl_merge_batch(zkl_ctx *ctx, const uint8_t *pairs, size_t count,
   else LAUNCH(ctx, k_merkle_level, ceil_div(count, ZKL_HASH_THREADS), ZKL_HASH_THREADS, 0, d.p, o.p, count);
   return download_digests(ctx, o.p, count, out);
 }
+// Batched Merkle authentication (include/zkl_b200.h): the merge schedule is data independent (it follows from the query
+// positions), so the host sends it once and the levels run back to back on the stream.
+extern "C" int zkl_merge_plan(zkl_ctx *ctx, const uint8_t *known, size_t num_known, const uint32_t *left, const uint32_t *right,
+                              const uint32_t *level_counts, size_t num_levels, const uint32_t *want, size_t num_want, uint8_t *out) {
+  ZKL_TRY(need_suite(ctx));
+  if (num_known == 0 || num_want == 0) { ctx->set_error("merge plan needs known digests and requested outputs"); return 1; }
+  size_t total = 0, avail = num_known;
+  for (size_t l = 0; l < num_levels; l++) {
+    if (level_counts[l] == 0) { ctx->set_error("merge plan level without merges"); return 1; }
+    for (size_t i = 0; i < level_counts[l]; i++)
+      if (left[total + i] >= avail || right[total + i] >= avail) { ctx->set_error("merge plan refers to a digest that does not exist yet"); return 1; }
+    total += level_counts[l]; avail += level_counts[l];
+  }
+  for (size_t i = 0; i < num_want; i++) if (want[i] >= avail) { ctx->set_error("merge plan output index out of range"); return 1; }
+  if (avail > 0xFFFFFFFFull) { ctx->set_error("merge plan too large"); return 1; }
+  std::vector<fe> h(num_known);
+  for (size_t i = 0; i < num_known; i++) h[i] = fold_digest_host(known + 32 * i);
+  std::vector<uint32_t> idx(2 * total + num_want);            // (left, right) interleaved: a gather yields the pairs a Merkle level kernel reads
+  for (size_t i = 0; i < total; i++) { idx[2 * i] = left[i]; idx[2 * i + 1] = right[i]; }
+  for (size_t i = 0; i < num_want; i++) idx[2 * total + i] = want[i];
+  size_t widest = 0;
+  for (size_t l = 0; l < num_levels; l++) widest = std::max<size_t>(widest, level_counts[l]);
+  dev_buf<fe> table, pairs, res; dev_buf<uint32_t> didx;
+  ZKL_CHECK(ctx, table.alloc(avail)); ZKL_CHECK(ctx, pairs.alloc(std::max<size_t>(2 * widest, 1))); ZKL_CHECK(ctx, res.alloc(num_want));
+  ZKL_CHECK(ctx, didx.alloc(idx.size()));
+  ZKL_CHECK(ctx, cudaMemcpyAsync(table.p, h.data(), num_known * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream));
+  ZKL_CHECK(ctx, cudaMemcpyAsync(didx.p, idx.data(), idx.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  size_t off = 0, next = num_known;
+  for (size_t l = 0; l < num_levels; l++) {
+    const size_t cnt = level_counts[l];
+    LAUNCH(ctx, k_gather_fe, ceil_div(2 * cnt, (size_t)256), 256, 0, table.p, didx.p + 2 * off, (int)(2 * cnt), pairs.p);
+    if (cnt >= bulk_min(ctx) && ctx->hash_path == 0) LAUNCH_TC(ctx, k_tc_merkle_level, cnt, pairs.p, table.p + next, cnt);
+    else if (cnt >= bulk_min(ctx)) LAUNCH(ctx, k_merkle_level, ceil_div(cnt, ZKL_HASH_THREADS), ZKL_HASH_THREADS, 0, pairs.p, table.p + next, cnt);
+    else if (use_quad(ctx)) LAUNCH_QUAD(ctx, k_quad_merkle_level, cnt, pairs.p, table.p + next, cnt);
+    else LAUNCH_COOP(ctx, k_coop_merkle_level, cnt, pairs.p, table.p + next, cnt);
+    off += cnt; next += cnt;
+  }
+  LAUNCH(ctx, k_gather_fe, ceil_div(num_want, (size_t)256), 256, 0, table.p, didx.p + 2 * total, (int)num_want, res.p);
+  return download_digests(ctx, res.p, num_want, out);
+}
 extern "C" int zkl_merge_with_int_batch(zkl_ctx *ctx, const uint8_t seed[32], const uint64_t *values, size_t count, uint8_t *out) {
   ZKL_TRY(need_suite(ctx));
   dev_buf<uint64_t> v; dev_buf<fe> o; ZKL_CHECK(ctx, v.alloc(count)); ZKL_CHECK(ctx, o.alloc(count));

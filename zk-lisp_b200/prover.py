@@ -110,6 +110,18 @@ class Context:
         self._check(self.lib.zkl_merge_many(self.h, d.ctypes.data if d.size else None, d.shape[0], out.ctypes.data))
         return out.tobytes()
 
+    def merge_plan(self, known: np.ndarray, left, right, level_counts, want) -> np.ndarray:
+        """Batched Merkle authentication (`zkl_merge_plan`): a digest table seeded with `known` (k, 32) grows level by level,
+        entry = merge(table[left], table[right]); returns the `want`ed entries as (len(want), 32)."""
+        kn = np.ascontiguousarray(known, dtype=np.uint8).reshape(-1, 32)
+        lf, rt = np.ascontiguousarray(left, dtype=np.uint32), np.ascontiguousarray(right, dtype=np.uint32)
+        lc, wt = np.ascontiguousarray(level_counts, dtype=np.uint32), np.ascontiguousarray(want, dtype=np.uint32)
+        assert lf.shape == rt.shape and int(lc.sum()) == lf.shape[0]
+        out = np.zeros((wt.shape[0], 32), dtype=np.uint8)
+        self._check(self.lib.zkl_merge_plan(self.h, kn.ctypes.data, kn.shape[0], lf.ctypes.data, rt.ctypes.data, lc.ctypes.data,
+                                            lc.shape[0], wt.ctypes.data, wt.shape[0], out.ctypes.data))
+        return out
+
     def merkle_build(self, leaves: np.ndarray):
         lv = np.ascontiguousarray(leaves, dtype=np.uint8).reshape(-1, 32)
         root = np.zeros(32, dtype=np.uint8)

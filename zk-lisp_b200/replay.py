@@ -227,6 +227,174 @@ def batch_root(hasher, depth: int, lists: List[List[bytes]], leaves: Sequence[by
     return vals[0]
 
 
+class MergePlan:
+    """The merge schedule of any number of batch openings, laid out for `zkl_merge_plan`: a flat digest table (opened leaves
+    and proof nodes first), per tree level the (left, right) table indices of every merge of every tree, and the table index
+    of each tree's root. The schedule follows from the query positions alone, so it is built before any hashing happens."""
+
+    def __init__(self):
+        self.known: List[bytes] = []
+        self.levels: List[List[tuple]] = []      # levels[l] = [(left, right), ...] with symbolic node ids
+        self.roots: List[tuple] = []             # (symbolic id, expected root, message)
+
+    def _known(self, digest: bytes):
+        self.known.append(bytes(digest))
+        return ("k", len(self.known) - 1)
+
+    def _merge(self, level: int, left, right):
+        while len(self.levels) <= level:
+            self.levels.append([])
+        self.levels[level].append((left, right))
+        return ("m", level, len(self.levels[level]) - 1)
+
+    def add_opening(self, depth: int, lists: List[List[bytes]], leaves: Sequence[bytes], positions: Sequence[int], expected: bytes, what: str):
+        """Same walk as `batch_root`, recording merges instead of performing them."""
+        if depth < 1 or len(leaves) != len(positions) or not positions:
+            raise InvalidInput("malformed batch Merkle opening")
+        n = 1 << depth
+        norm = sorted({p & ~1 for p in positions})
+        if len(norm) != len(lists) or max(positions) >= n:
+            raise InvalidInput("malformed batch Merkle opening")
+        known = {p: self._known(l) for p, l in zip(positions, leaves)}
+        ptr = [0] * len(lists)
+
+        def take(s):
+            if ptr[s] >= len(lists[s]):
+                raise InvalidInput("malformed batch Merkle opening")
+            ptr[s] += 1
+            return self._known(lists[s][ptr[s] - 1])
+
+        cur, vals = [], []
+        for i, e in enumerate(norm):
+            lo = known[e] if e in known else take(i)
+            hi = known[e + 1] if e + 1 in known else take(i)
+            cur.append((e + n) >> 1)
+            vals.append(self._merge(0, lo, hi))
+        for lvl in range(1, depth):
+            ncur, nvals, i = [], [], 0
+            while i < len(cur):
+                me, sib, used = vals[i], cur[i] ^ 1, i
+                if i + 1 < len(cur) and cur[i + 1] == sib:
+                    sv = vals[i + 1]
+                    i += 1
+                else:
+                    sv = take(used)
+                nvals.append(self._merge(lvl, sv, me) if cur[used] & 1 else self._merge(lvl, me, sv))
+                ncur.append(sib >> 1)
+                i += 1
+            cur, vals = ncur, nvals
+        if cur != [1] or any(ptr[s] != len(lists[s]) for s in range(len(lists))):
+            raise InvalidInput("malformed batch Merkle opening")
+        self.roots.append((vals[0], bytes(expected), what))
+
+    def flatten(self):
+        """(known (k, 32) u8, left u32[], right u32[], level_counts u32[], want u32[])."""
+        base, acc = [], len(self.known)
+        for lv in self.levels:
+            base.append(acc)
+            acc += len(lv)
+
+        def index(node):
+            return node[1] if node[0] == "k" else base[node[1]] + node[2]
+
+        left = [index(a) for lv in self.levels for a, _ in lv]
+        right = [index(b) for lv in self.levels for _, b in lv]
+        known = np.frombuffer(b"".join(self.known), dtype=np.uint8).reshape(-1, 32)
+        return (known, np.array(left, dtype=np.uint32), np.array(right, dtype=np.uint32),
+                np.array([len(lv) for lv in self.levels], dtype=np.uint32), np.array([index(r) for r, _, _ in self.roots], dtype=np.uint32))
+
+    def run(self, hasher) -> None:
+        """One device submission for all trees; raises on the first root that does not match its commitment."""
+        if not self.roots:
+            return
+        got = hasher.merge_plan(*self.flatten())
+        for (_, expected, what), g in zip(self.roots, got):
+            if g.tobytes() != expected:
+                raise InvalidInput(what)
+
+
+def verify_children_openings(hasher, steps: Sequence[StepProof], challenges: Sequence[FsChallenges]) -> None:
+    """`verify_child_openings` for a whole batch of children in FOUR device submissions: the leaves of all opened trace rows
+    (one hash_elements batch per partition), of all constraint rows, of all FRI layer pairs and remainders, then ONE merge plan
+    that authenticates every tree of every child (the reference walks each path with one CPU sponge call per node,
+    agg/child.rs:1049-1068)."""
+    plan = MergePlan()
+    trace_rows, cons_rows, fri_pairs, rems = [], [], [], []
+    jobs = []          # (kind, child, rows-slice, ...) resolved after the batched leaf hashing
+    for ci, (step, fs) in enumerate(zip(steps, challenges)):
+        v = step.proof.inner
+        k = len(fs.query_positions)
+        rows = np.frombuffer(v.trace_query_values, dtype=np.uint64)
+        if k == 0 or rows.size != k * v.main_width * 2:
+            raise InvalidInput("invalid trace queries layout in ZlChildTranscript")
+        crow = np.frombuffer(v.constraint_query_values, dtype=np.uint64)
+        C = len(v.constraint_query_values) // (16 * k)
+        if C == 0 or crow.size != k * C * 2:
+            raise InvalidInput("failed to decode constraint query values in ZlChildTranscript")
+        if len(v.fri_layers) != v.num_fri_layers:
+            raise InvalidInput("FRI layer count does not match the proof options")
+        trace_rows.append((ci, rows.reshape(k, v.main_width, 2)))
+        cons_rows.append((ci, crow.reshape(k, C, 2)))
+        domain, positions, layers = v.lde_domain_size, list(fs.query_positions), []
+        for values, _ in v.fri_layers:
+            positions = fold_positions(positions, domain, v.fri_folding)
+            pairs = np.frombuffer(values, dtype=np.uint64)
+            if v.fri_folding != 2 or pairs.size != len(positions) * 4:
+                raise InvalidInput("FRI layer value count does not match the folded positions")
+            layers.append((positions, pairs.reshape(len(positions), 2, 2)))
+            domain //= v.fri_folding
+        fri_pairs.append((ci, layers))
+        rem = np.frombuffer(v.fri_remainder, dtype=np.uint64)
+        if rem.size == 0 or rem.size % 2:
+            raise InvalidInput("FRI remainder does not match its commitment")
+        rems.append(rem.reshape(1, -1, 2))
+
+    def batched(groups, key):
+        """Hash row groups that share a shape (width, partition size) in one call; returns per-group digest lists."""
+        out, by_shape = {}, {}
+        for gi, (ci, rows) in enumerate(groups):
+            by_shape.setdefault(key(ci, rows), []).append(gi)
+        for (width, psize), members in by_shape.items():
+            digests = hash_rows(hasher, np.concatenate([groups[g][1] for g in members]), psize)
+            at = 0
+            for g in members:
+                cnt = groups[g][1].shape[0]
+                out[g] = digests[at:at + cnt]
+                at += cnt
+        return [out[g] for g in range(len(groups))]
+
+    def psize_of(ci, rows):
+        v = steps[ci].proof.inner
+        return rows.shape[1], partition_size(v.num_partitions, v.hash_rate, rows.shape[1])
+
+    t_leaves, c_leaves = batched(trace_rows, psize_of), batched(cons_rows, psize_of)
+    all_pairs = [pairs for _, layers in fri_pairs for _, pairs in layers]
+    f_leaves = [d.tobytes() for d in hasher.hash_elements(np.concatenate(all_pairs))] if all_pairs else []
+    at = 0
+    for ci, (step, fs) in enumerate(zip(steps, challenges)):
+        v = step.proof.inner
+        trace_roots, constraint_root, fri_roots = v.parse_commitments()
+        tag = f"child {ci}: "
+        plan.add_opening(*read_batch_proof(v.trace_query_paths), t_leaves[ci], fs.query_positions, trace_roots[0],
+                         tag + "trace openings do not match the trace commitment")
+        plan.add_opening(*read_batch_proof(v.constraint_query_paths), c_leaves[ci], fs.query_positions, constraint_root,
+                         tag + "constraint openings do not match the constraint commitment")
+        for d, ((positions, pairs), (_, paths)) in enumerate(zip(fri_pairs[ci][1], v.fri_layers)):
+            plan.add_opening(*read_batch_proof(paths), f_leaves[at:at + len(positions)], positions, fri_roots[d],
+                             tag + f"FRI layer {d} openings do not match the layer commitment")
+            at += len(positions)
+    # remainders: equal lengths hash as one batch
+    by_len = {}
+    for ci, rem in enumerate(rems):
+        by_len.setdefault(rem.shape[1], []).append(ci)
+    for _, members in by_len.items():
+        digests = hasher.hash_elements(np.concatenate([rems[ci] for ci in members]))
+        for ci, d in zip(members, digests):
+            if d.tobytes() != steps[ci].proof.inner.parse_commitments()[2][-1]:
+                raise InvalidInput(f"child {ci}: FRI remainder does not match its commitment")
+    plan.run(hasher)
+
+
 def verify_child_openings(hasher, step: StepProof, fs: FsChallenges) -> None:
     """Every opening of the child proof re-hashed against its commitment: trace rows and constraint rows at the query
     positions, FRI layer pairs at the folded positions, the remainder against the last FRI commitment."""
