@@ -238,6 +238,13 @@ int zkl_sync(zkl_ctx *ctx);
  * (prove.rs:1289-1392). With the full trace resident in HBM these are one kernel each. */
 int zkl_slice_segment_dev(zkl_ctx *ctx, const void *full_dev, size_t full_rows, const uint32_t *seg_to_full,
                           size_t seg_width, size_t r_start, size_t seg_rows, void *out_dev);
+/* Poseidon gadget rows of the full trace, batched over levels (vm/trace/poseidon.rs:24-96 apply_level_absorb): for level
+ * L = levels[i], row 32L (map) receives inputs[i][0..10) in lanes 0..9 (zero padded by the caller) and the suite's domain tags
+ * in lanes 10, 11; row 32L+1+j the state before round j (j < 27); row 32L+28 and the pad rows 29..31 the final state.
+ * `trace_dev` is column-major [width][n_rows]; the lanes are columns lanes_start .. lanes_start+11; `suite` is the PROGRAM suite
+ * (suite_id = program_id, prove.rs:985), not the commitment hasher's. */
+int zkl_poseidon_levels_dev(zkl_ctx *ctx, void *trace_dev, size_t n_rows, uint32_t lanes_start, const zkl_suite *suite,
+                            const uint32_t *levels, const zkl_fe *inputs /* count*10 */, size_t count);
 int zkl_usage_mask_dev(zkl_ctx *ctx, const void *trace_dev, size_t width, size_t n, const zkl_columns *cols,
                        int has_ram, uint32_t *out_mask, uint32_t *out_ram_bits);
 int zkl_read_cells_dev(zkl_ctx *ctx, const void *trace_dev, size_t n, const uint32_t *cols, const uint32_t *rows,

@@ -178,3 +178,47 @@ def test_child_replay_helpers(ctx, zkl, oracle):
         roots = zkl.child.merkle_roots_from_leaves(ctx, leaves, pos, sibs)
         assert all(r.tobytes() == root for r in roots)
         lde.free()
+
+
+def test_poseidon_levels_match_trace_builder(ctx, zkl):
+    """zkl_poseidon_levels_dev = vm/trace/poseidon.rs:24-96 `apply_level_absorb` batched over levels: re-filling the blanked
+    Poseidon lanes of an AIR-valid trace reproduces it cell for cell; the reference's own unit cases (0, 2, 10 inputs,
+    poseidon.rs:199-230) give the sponge value in lane 0 of the final row."""
+    if ctx.hash_mode != "default":
+        pytest.skip("trace-builder kernel, independent of the hashing mode")
+    A, SG = zkl.air, zkl.segments
+    n = 512
+    full, air_pi, _ = synth.valid_segment(n=n, seed=33, full_layout=True)
+    cols = A.Columns.baseline()
+    active = [lvl for lvl in range(n // 32) if lvl % 3 == 1]
+    cell = lambda t, c, r: int(t[c, r, 0]) | (int(t[c, r, 1]) << 64)
+    inputs = [[cell(full, cols.lanes_start + i, 32 * lvl) for i in range(10)] for lvl in active]
+    blank = full.copy()
+    for lvl in active:
+        blank[cols.lanes_start:cols.lanes_start + 12, 32 * lvl:32 * lvl + 32] = 0
+    assert not np.array_equal(blank, full)
+    dt = SG.DeviceTrace(ctx, blank)
+    SG.apply_levels_absorb(ctx, dt.dev, n, air_pi.core.program_id, active, inputs, cols.lanes_start)
+    out = np.zeros_like(blank)
+    ctx._check(ctx.lib.zkl_dev_download(ctx.h, out.ctypes.data, dt.dev, out.nbytes))
+    assert np.array_equal(out, full)
+    with pytest.raises(zkl.capi.ZklError, match="level outside the trace"):
+        SG.apply_levels_absorb(ctx, dt.dev, n, air_pi.core.program_id, [n // 32], [[1]], cols.lanes_start)
+    dt.free()
+    # poseidon.rs:199-230
+    sid = bytes([3]) * 32
+    suite = zkl.params.get_poseidon_suite(sid)
+    cases = [[], [1, 2], list(range(10))]
+    empty = np.zeros((cols.width, 32 * len(cases), 2), dtype=np.uint64)
+    dt = SG.DeviceTrace(ctx, empty)
+    SG.apply_levels_absorb(ctx, dt.dev, empty.shape[1], sid, list(range(len(cases))), cases, cols.lanes_start)
+    out = np.zeros_like(empty)
+    ctx._check(ctx.lib.zkl_dev_download(ctx.h, out.ctypes.data, dt.dev, out.nbytes))
+    for lvl, ins in enumerate(cases):
+        st = list(ins) + [0] * (10 - len(ins)) + list(suite.dom)
+        assert [cell(out, i, 32 * lvl) for i in range(12)] == st == [cell(out, i, 32 * lvl + 1) for i in range(12)]
+        fin = zkl.params.permute(suite, st)
+        for r in (28, 29, 30, 31):
+            assert [cell(out, i, 32 * lvl + r) for i in range(12)] == fin
+    assert not out[12:].any()
+    dt.free()

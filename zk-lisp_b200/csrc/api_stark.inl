@@ -961,6 +961,60 @@ extern "C" int zkl_slice_segment_dev(zkl_ctx *ctx, const void *full_dev, size_t 
   ZKL_CHECK(ctx, cudaStreamSynchronize(ctx->stream));  // `seg_to_full` is caller memory
   return 0;
 }
+// Poseidon gadget rows of the execution trace, batched over levels (vm/trace/poseidon.rs:24-96 `apply_level_absorb`): the trace
+// builder's only dense arithmetic (27 rounds x 168 field products per active level). One thread per level; row 32L is the map
+// row (inputs in lanes 0..9, the program suite's domain tags in lanes 10, 11), row 32L+1+j the state BEFORE round j, row 32L+28
+// (final) and the pad rows 29..31 the state after round 26. The suite is the PROGRAM's (suite_id = program_id), not the hasher's.
+struct pose_suite_dev { fe dom[2]; fe mds[12][12]; fe rc[ZKL_ROUNDS][12]; };
+__global__ void __launch_bounds__(64) k_poseidon_levels(fe *__restrict__ trace, size_t n_rows, uint32_t lanes_start, const pose_suite_dev *__restrict__ s,
+                                                        const uint32_t *__restrict__ levels, const fe *__restrict__ inputs, int count) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= count) return;
+  const size_t base = (size_t)levels[t] * 32;
+  fe st[12];
+#pragma unroll
+  for (int i = 0; i < 10; i++) st[i] = ld_fe(inputs + (size_t)t * 10 + i);
+  st[10] = ld_fe(&s->dom[0]); st[11] = ld_fe(&s->dom[1]);
+  fe *lane0 = trace + (size_t)lanes_start * n_rows + base;
+#define PUT_ROW(r) for (int i_ = 0; i_ < 12; i_++) st_fe(lane0 + (size_t)i_ * n_rows + (r), st[i_])
+  PUT_ROW(0);
+#pragma unroll 1
+  for (int j = 0; j < ZKL_ROUNDS; j++) {
+    PUT_ROW(1 + j);
+    fe c3[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) c3[i] = fe_cube(st[i]);
+#pragma unroll 1
+    for (int i = 0; i < 12; i++) {
+      wide_acc w; wacc_zero(w);
+#pragma unroll
+      for (int k = 0; k < 12; k++) wacc_mad(w, c3[k], ld_fe(&s->mds[i][k]));
+      st[i] = fe_add(wacc_reduce(w), ld_fe(&s->rc[j][i]));
+    }
+  }
+  for (int r = 28; r < 32; r++) { PUT_ROW(r); }
+#undef PUT_ROW
+}
+extern "C" int zkl_poseidon_levels_dev(zkl_ctx *ctx, void *trace_dev, size_t n_rows, uint32_t lanes_start, const zkl_suite *suite,
+                                       const uint32_t *levels, const zkl_fe *inputs, size_t count) {
+  ZKL_TRY(enter(ctx));
+  if (count == 0) return 0;
+  if (count > (1u << 30)) { ctx->set_error("too many levels"); return 1; }
+  for (size_t i = 0; i < count; i++)
+    if (((size_t)levels[i] + 1) * 32 > n_rows) { ctx->set_error("level outside the trace"); return 1; }
+  pose_suite_dev h;
+  for (int i = 0; i < 2; i++) h.dom[i] = fe_from_abi(suite->dom[i]);
+  for (int i = 0; i < 12; i++) for (int j = 0; j < 12; j++) h.mds[i][j] = fe_from_abi(suite->mds[i][j]);
+  for (int r = 0; r < ZKL_ROUNDS; r++) for (int j = 0; j < 12; j++) h.rc[r][j] = fe_from_abi(suite->rc[r][j]);
+  dev_buf<pose_suite_dev> ds; dev_buf<uint32_t> dl; dev_buf<fe> di;
+  ZKL_CHECK(ctx, ds.alloc(1)); ZKL_CHECK(ctx, dl.alloc(count)); ZKL_CHECK(ctx, di.alloc(count * 10));
+  ZKL_CHECK(ctx, cudaMemcpyAsync(ds.p, &h, sizeof h, cudaMemcpyHostToDevice, ctx->stream));
+  ZKL_CHECK(ctx, cudaMemcpyAsync(dl.p, levels, count * 4, cudaMemcpyHostToDevice, ctx->stream));
+  ZKL_CHECK(ctx, cudaMemcpyAsync(di.p, inputs, count * 10 * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream));
+  LAUNCH(ctx, k_poseidon_levels, ceil_div(count, (size_t)64), 64, 0, (fe *)trace_dev, n_rows, lanes_start, ds.p, dl.p, di.p, (int)count);
+  ZKL_CHECK(ctx, cudaStreamSynchronize(ctx->stream));  // suite, levels and inputs are caller / stack memory
+  return 0;
+}
 // compute_vm_usage_mask_for_trace (prove.rs:1289-1392): out[0] = vm usage mask, out[1] = ram delta_clk bit mask
 struct usage_cols {
   uint32_t op_assert, op_select, op_assert_bit, op_assert_range, op_divmod, op_mulwide, op_div128, op_eq, op_sponge;

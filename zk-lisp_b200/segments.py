@@ -135,6 +135,27 @@ class DeviceTrace:
             pass
 
 
+def apply_levels_absorb(ctx: Context, trace_dev, n_rows: int, suite_id: bytes, levels: Sequence[int], inputs: Sequence[Sequence[int]],
+                        lanes_start: int = 0) -> None:
+    """vm/trace/poseidon.rs:24-96 `apply_level_absorb` for a batch of levels of a trace resident on the device: the 27-round
+    permutation rows of every listed level in one launch (the trace builder's only dense arithmetic). `inputs[i]` holds up to 10
+    absorbed elements of level `levels[i]`; the suite is the program's (suite_id = program_id)."""
+    from . import params
+    from .prover import ints_to_fe
+    if len(levels) != len(inputs):
+        raise ValueError("one input list per level")
+    if not levels:
+        return
+    lv = np.array(levels, dtype=np.uint32)
+    flat = []
+    for row in inputs:
+        row = list(row)[:10]
+        flat += row + [0] * (10 - len(row))
+    fe = ints_to_fe(flat)
+    suite = capi.suite_to_c(params.get_poseidon_suite(bytes(suite_id)))
+    ctx._check(ctx.lib.zkl_poseidon_levels_dev(ctx.h, trace_dev, n_rows, lanes_start, C.byref(suite), lv.ctypes.data, fe.ctypes.data, len(levels)))
+
+
 def read_cells(ctx: Context, dev, n_rows: int, cells) -> List[int]:
     cols = np.array([c for c, _ in cells], dtype=np.uint32)
     rows = np.array([r for _, r in cells], dtype=np.uint32)
