@@ -20,8 +20,7 @@ def build():
 def load():
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB):
-            build()
+        build()   # no-op when up to date; rebuilds when the library came from a host with another CPU (oracle/Makefile)
         _lib = C.CDLL(LIB)
         _lib.zo_prove_many.restype = C.c_double
     return _lib
