@@ -139,6 +139,10 @@ int zkl_merge_with_int_batch(zkl_ctx *ctx, const uint8_t seed[32], const uint64_
 int zkl_merge_plan(zkl_ctx *ctx, const uint8_t *known /* num_known*32 */, size_t num_known, const uint32_t *left,
                    const uint32_t *right, const uint32_t *level_counts, size_t num_levels, const uint32_t *want,
                    size_t num_want, uint8_t *out_digests /* num_want*32 */);
+/* out[i] = merge_with_int(seeds[i], values[i]) (hasher.rs:107-120): the random coins of many child proofs advanced in lockstep
+ * (agg/fs.rs:37-245 replayed for a whole batch of children, one launch per transcript step instead of one per child). */
+int zkl_merge_with_int_pairs(zkl_ctx *ctx, const uint8_t *seeds /* count*32 */, const uint64_t *values, size_t count,
+                             uint8_t *out_digests /* count*32 */);
 int zkl_hash_bytes(zkl_ctx *ctx, const uint8_t *data, size_t len, uint8_t out[32]);
 int zkl_merge_many(zkl_ctx *ctx, const uint8_t *digests, size_t count, uint8_t out[32]);
 /* MerkleTree::new over `count` leaves (power of two); out_nodes[i], i in 1..count, is the

@@ -140,6 +140,10 @@ class _PlanHasher:
         self.merge_with_int, self.merge_many = oracle.merge_with_int, oracle.merge_many
         self.calls = 0
 
+    def merge_with_int_pairs(self, seeds, values):
+        self.pair_calls = getattr(self, "pair_calls", 0) + 1
+        return np.stack([self.o.merge_with_int(bytes(s), np.array([v], dtype=np.uint64))[0] for s, v in zip(np.asarray(seeds).reshape(-1, 32), values)])
+
     def merge_plan(self, known, left, right, level_counts, want):
         self.calls += 1
         table = [bytes(k) for k in np.asarray(known).reshape(-1, 32)]
@@ -161,6 +165,13 @@ def test_children_openings_in_one_merge_plan(zkl, oracle, child):
     h = _PlanHasher(oracle)
     kids = [child[0], _step(zkl, oracle, 32, 9, queries=40, parts=(4, 8), grind=0)[0], _step(zkl, oracle, 64, 11)[0]]
     fss = [R.replay_fs_from_step(h, k) for k in kids]
+    # the same challenges from the lockstep replay of all children (n = 64 and n = 32 children: different widths of the OOD
+    # frame are not needed here, different numbers of FRI layers are)
+    assert R.replay_fs_from_steps(h, kids) == fss and R.replay_fs_from_steps(h, []) == []
+    assert len({len(f.fri_alphas) for f in fss}) == 2 and h.pair_calls <= 2 * max(len(f.fri_alphas) for f in fss) + 8
+    bad_nonce = replace(kids[1], proof=replace(kids[1].proof, inner=replace(kids[1].proof.inner, grinding=30)))
+    with pytest.raises(S.InvalidInput, match="grinding factor"):
+        R.replay_fs_from_steps(h, [kids[0], bad_nonce])
     R.verify_children_openings(h, kids, fss)
     assert h.calls == 1
     # schedule shape: indices only refer to earlier entries, one root per tree

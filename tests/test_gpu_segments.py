@@ -132,6 +132,7 @@ def test_prove_program_multi_segment(ctx, zkl, oracle):
         challenges.append(fs)
     # ... and all four children at once: leaves in three hashing batches, every tree in ONE device merge plan (zkl_merge_plan)
     before = ctx.launches
+    assert zkl.replay.replay_fs_from_steps(ctx, [s.step for s in steps]) == challenges      # all transcripts in lockstep
     zkl.replay.verify_children_openings(ctx, [s.step for s in steps], challenges)
     assert ctx.launches > before
     tampered = [s.step for s in steps]

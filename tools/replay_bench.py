@@ -26,6 +26,11 @@ for i in range(min(children, 4)):
 steps = [steps[i % len(steps)] for i in range(children)]
 t0 = time.time()
 fss = [zkl.replay.replay_fs_from_step(ctx, s) for s in steps]
+t0b = time.time()
+assert zkl.replay.replay_fs_from_steps(ctx, steps) == fss
+t1a = time.time()
+assert zkl.replay.replay_fs_from_steps(ctx, steps) == fss
+t1b = time.time()
 t1 = time.time()
 l0 = ctx.launches
 for s, fs in zip(steps, fss):
@@ -39,6 +44,7 @@ t4 = time.time()
 l2 = ctx.launches
 hashed = sum(len(fs.query_positions) for fs in fss)
 print(f"children {children}, opened positions {hashed}, proof bytes {sum(len(s.proof.inner_bytes) for s in steps)}")
-print(f"fs replay            {1e3 * (t1 - t0) / children:8.2f} ms/child")
+print(f"fs replay            {1e3 * (t0b - t0) / children:8.2f} ms/child  (per child, one C-ABI call per transcript step)")
+print(f"fs replay, lockstep  {1e3 * (t1b - t1a) / children:8.2f} ms/child  (all children per transcript step)")
 print(f"openings, per child  {1e3 * (t2 - t1) / children:8.2f} ms/child  ({(l1 - l0) // children} launches/child)")
 print(f"openings, one plan   {1e3 * (t4 - t3) / children:8.2f} ms/child  ({(l2 - l1) // 2} launches for all children; first call {1e3 * (t3 - t2):.1f} ms)")

@@ -134,6 +134,13 @@ __global__ void __launch_bounds__(ZKL_HASH_THREADS) k_merge_with_int_batch(fe se
   if (i >= count) return;
   st_fe(out + i, merge_with_int_dev(seed, vals[i]));
 }
+// one seed per value: out[i] = merge_with_int(seeds[i], vals[i]) — the coin draws of many child proofs in lockstep (replay)
+__global__ void __launch_bounds__(ZKL_HASH_THREADS) k_merge_with_int_pairs(const fe *__restrict__ seeds, const uint64_t *__restrict__ vals, size_t count,
+                                                                         fe *__restrict__ out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  st_fe(out + i, merge_with_int_dev(ld_fe(seeds + i), vals[i]));
+}
 // generic byte-chunk sponge: `chunks` = pre-folded chunk elements (label excluded), label selects the entry point
 __global__ void k_sponge_single(const fe *chunks, int count, int label_kind, fe *out) {
   if (threadIdx.x || blockIdx.x) return;

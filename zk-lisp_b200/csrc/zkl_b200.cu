@@ -532,6 +532,19 @@ extern "C" int zkl_merge_with_int_batch(zkl_ctx *ctx, const uint8_t seed[32], co
   else LAUNCH(ctx, k_merge_with_int_batch, ceil_div(count, ZKL_HASH_THREADS), ZKL_HASH_THREADS, 0, fold_digest_host(seed), v.p, count, o.p);
   return download_digests(ctx, o.p, count, out);
 }
+// merge_with_int with one seed per value (the coins of many child proofs advanced in lockstep, replay.py)
+extern "C" int zkl_merge_with_int_pairs(zkl_ctx *ctx, const uint8_t *seeds, const uint64_t *values, size_t count, uint8_t *out) {
+  ZKL_TRY(need_suite(ctx));
+  if (count == 0) return 0;
+  std::vector<fe> h(count);
+  for (size_t i = 0; i < count; i++) h[i] = fold_digest_host(seeds + 32 * i);
+  dev_buf<fe> s, o; dev_buf<uint64_t> v;
+  ZKL_CHECK(ctx, s.alloc(count)); ZKL_CHECK(ctx, o.alloc(count)); ZKL_CHECK(ctx, v.alloc(count));
+  ZKL_CHECK(ctx, cudaMemcpyAsync(s.p, h.data(), count * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream));
+  ZKL_CHECK(ctx, cudaMemcpyAsync(v.p, values, count * 8, cudaMemcpyHostToDevice, ctx->stream));
+  LAUNCH(ctx, k_merge_with_int_pairs, ceil_div(count, ZKL_HASH_THREADS), ZKL_HASH_THREADS, 0, s.p, v.p, count, o.p);
+  return download_digests(ctx, o.p, count, out);
+}
 static int sponge_chunks(zkl_ctx *ctx, const uint8_t *data, size_t len, int kind, uint8_t out[32]) {
   size_t nch = (len + 31) / 32;
   std::vector<fe> h(std::max<size_t>(nch, 1));

@@ -98,6 +98,15 @@ class Context:
         self._check(self.lib.zkl_merge_with_int_batch(self.h, s.ctypes.data, v.ctypes.data, v.shape[0], out.ctypes.data))
         return out
 
+    def merge_with_int_pairs(self, seeds: np.ndarray, values) -> np.ndarray:
+        """out[i] = merge_with_int(seeds[i], values[i]): one seed per value (`zkl_merge_with_int_pairs`)."""
+        s = np.ascontiguousarray(seeds, dtype=np.uint8).reshape(-1, 32)
+        v = np.ascontiguousarray(values, dtype=np.uint64)
+        assert s.shape[0] == v.shape[0]
+        out = np.zeros((v.shape[0], 32), dtype=np.uint8)
+        self._check(self.lib.zkl_merge_with_int_pairs(self.h, s.ctypes.data, v.ctypes.data, v.shape[0], out.ctypes.data))
+        return out
+
     def hash_bytes(self, data: bytes) -> bytes:
         d = np.frombuffer(bytes(data), dtype=np.uint8).copy() if data else np.zeros(1, dtype=np.uint8)
         out = np.zeros(32, dtype=np.uint8)

@@ -142,6 +142,112 @@ def replay_fs_from_step(hasher, step: StepProof) -> FsChallenges:
     return FsChallenges(z, deep, alphas, positions, v.pow_nonce)
 
 
+class CoinBatch:
+    """`Coin` for k transcripts advanced in lockstep: every transcript step is ONE device batch over all children
+    (`merge` for the reseeds, `merge_with_int_pairs` — one seed per value — for the draws)."""
+
+    def __init__(self, hasher, seed_elems: Sequence[Sequence[int]]):
+        self.h, self.k = hasher, len(seed_elems)
+        by_len = {}
+        for i, e in enumerate(seed_elems):
+            by_len.setdefault(len(e), []).append(i)
+        self.seeds: List[bytes] = [b""] * self.k
+        for ln, members in by_len.items():
+            batch = np.stack([_ints_to_fe(seed_elems[i]) for i in members])
+            for i, d in zip(members, self.h.hash_elements(batch)):
+                self.seeds[i] = d.tobytes()
+
+    def reseed(self, digests: Sequence[bytes]):
+        pairs = np.frombuffer(b"".join(s + bytes(d) for s, d in zip(self.seeds, digests)), dtype=np.uint8).reshape(self.k, 64)
+        self.seeds = [d.tobytes() for d in self.h.merge(pairs)]
+
+    def _mwi(self, values_per_child: Sequence[Sequence[int]]) -> List[List[bytes]]:
+        seeds = b"".join(self.seeds[i] * len(v) for i, v in enumerate(values_per_child))
+        flat = np.array([x for v in values_per_child for x in v], dtype=np.uint64)
+        if flat.size == 0:
+            return [[] for _ in values_per_child]
+        out = self.h.merge_with_int_pairs(np.frombuffer(seeds, dtype=np.uint8).reshape(-1, 32), flat)
+        res, at = [], 0
+        for v in values_per_child:
+            res.append([out[at + j].tobytes() for j in range(len(v))])
+            at += len(v)
+        return res
+
+    def draw_many(self, counts: Sequence[int]) -> List[List[int]]:
+        """counts[i] consecutive draws of transcript i (counter restarts at 1 after every reseed)."""
+        return [[_digest_fe(d) for d in ds] for ds in self._mwi([range(1, c + 1) for c in counts])]
+
+    def check_leading_zeros(self, values: Sequence[int]) -> List[int]:
+        heads = [int.from_bytes(ds[0][:8], "little") for ds in self._mwi([[v] for v in values])]
+        return [64 if h == 0 else (h & -h).bit_length() - 1 for h in heads]
+
+    def draw_integers(self, counts: Sequence[int], domains: Sequence[int], nonces: Sequence[int]) -> List[List[int]]:
+        self.seeds = [ds[0] for ds in self._mwi([[n] for n in nonces])]
+        return [[int.from_bytes(d[:8], "little") & (dom - 1) for d in ds]
+                for ds, dom in zip(self._mwi([range(1, c + 1) for c in counts]), domains)]
+
+
+def replay_fs_from_steps(hasher, steps: Sequence[StepProof]) -> List[FsChallenges]:
+    """`replay_fs_from_step` for a batch of children in lockstep (agg/fs.rs:37-245 per child): about 2 x (FRI layers + 4) device
+    submissions for ALL children instead of that many per child. Children may differ in width and trace length; transcripts with
+    fewer FRI layers simply sit out the later reseeds."""
+    k = len(steps)
+    if k == 0:
+        return []
+    views = [s.proof.inner for s in steps]
+    for v in views:
+        if v.aux_width != 0:
+            raise InvalidInput("multi-segment trace must provide at least two trace commitments")
+        if len(v.ood_trace) != 2 * 16 * v.main_width or len(v.ood_constraints) % 32 or not v.ood_constraints:
+            raise InvalidInput("invalid OOD frame layout in FS replay")
+    seeds = [A.context_to_elements(v.main_width, v.trace_len, v.num_constraints, _options_of(v)) + air_public_inputs_of(s).to_elements()
+             for s, v in zip(steps, views)]
+    coin = CoinBatch(hasher, seeds)
+    try:
+        roots = [v.parse_commitments() for v in views]
+    except InvalidInput:
+        raise InvalidInput("invalid Winterfell commitments layout in FS replay")
+    coin.reseed([r[0][0] for r in roots])
+    coin.reseed([r[1] for r in roots])
+    z = [d[0] for d in coin.draw_many([1] * k)]
+    # OOD frames: equal shapes hash as one batch
+    ood_digest, by_shape = [b""] * k, {}
+    for i, v in enumerate(views):
+        W, C = v.main_width, len(v.ood_constraints) // 32
+        ood = v.ood_trace[:16 * W] + v.ood_constraints[:16 * C] + v.ood_trace[16 * W:] + v.ood_constraints[16 * C:]
+        by_shape.setdefault(2 * (W + C), []).append((i, np.frombuffer(ood, dtype=np.uint64).reshape(2 * (W + C), 2)))
+    for _, members in by_shape.items():
+        for (i, _), d in zip(members, hasher.hash_elements(np.stack([m[1] for m in members]))):
+            ood_digest[i] = d.tobytes()
+    coin.reseed(ood_digest)
+    deep = coin.draw_many([v.main_width + len(v.ood_constraints) // 32 for v in views])
+    # FRI alphas: transcript i takes part in round d while it still has a root
+    alphas = [[] for _ in range(k)]
+    degree = [v.trace_len for v in views]
+    for d in range(max(len(r[2]) for r in roots)):
+        live = [i for i in range(k) if d < len(roots[i][2])]
+        sub = CoinBatch.__new__(CoinBatch)
+        sub.h, sub.k, sub.seeds = hasher, len(live), [coin.seeds[i] for i in live]
+        sub.reseed([roots[i][2][d] for i in live])
+        for i, a, sd in zip(live, sub.draw_many([1] * len(live)), sub.seeds):
+            coin.seeds[i] = sd
+            alphas[i].append(a[0])
+            if d != len(roots[i][2]) - 1 and degree[i] % views[i].fri_folding:
+                raise InvalidInput("FRI degree truncation detected while replaying FS challenges")
+            degree[i] //= views[i].fri_folding
+    zeros = coin.check_leading_zeros([v.pow_nonce for v in views])
+    if any(zz < v.grinding for zz, v in zip(zeros, views)):
+        raise InvalidInput("pow_nonce does not satisfy grinding factor in FS replay")
+    drawn = coin.draw_integers([v.num_queries for v in views], [v.lde_domain_size for v in views], [v.pow_nonce for v in views])
+    out = []
+    for i, v in enumerate(views):
+        positions = sorted(set(drawn[i]))
+        if len(positions) != v.num_unique_queries:
+            raise InvalidInput("unique query positions count does not match proof.num_unique_queries")
+        out.append(FsChallenges(z[i], deep[i], alphas[i], positions, v.pow_nonce))
+    return out
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # Merkle openings
 # ---------------------------------------------------------------------------------------------------------------
