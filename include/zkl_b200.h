@@ -236,6 +236,30 @@ int zkl_dev_free(zkl_ctx *ctx, void *dev);
 int zkl_dev_upload(zkl_ctx *ctx, void *dev, const void *host, size_t bytes);
 int zkl_sync(zkl_ctx *ctx);
 
+/* ---- child-proof replay for the aggregation layer -------------------------------------
+ * agg/fs.rs:37-245 (Fiat-Shamir replay of a step proof) and agg/child.rs:1025-1099 (re-hashing of every opening) for a whole
+ * batch of children: transcripts advance in lockstep (one device batch per transcript step), leaves are hashed in three
+ * batches and every tree of every child is authenticated by one merge plan. Per-child results carry a status
+ * (0 = ok, else see zkl_replay_status_name; FRI opening failures carry the layer in bits 8..15). */
+typedef struct {
+  const uint8_t *proof; /* inner winterfell::Proof bytes (as written by zkl_prove_segment) */
+  size_t proof_len;
+  const zkl_fe *pi_elems; /* AirPublicInputs::to_elements() of the child (lib.rs:116-160), rebuilt as in agg/fs.rs:43-66 */
+  size_t num_pi;
+} zkl_child_proof;
+typedef struct {
+  int32_t status;
+  uint32_t num_positions, num_alphas, num_deep;
+  uint64_t pow_nonce;
+  zkl_fe z;
+  zkl_fe alphas[40];
+  uint32_t positions[256];
+} zkl_child_challenges;
+/* out_deep receives the DEEP coefficients of child i at out_deep[i * deep_stride ...] (trace columns, then composition columns). */
+int zkl_replay_children(zkl_ctx *ctx, const zkl_child_proof *children, size_t count, int verify_openings,
+                        zkl_child_challenges *out, zkl_fe *out_deep, size_t deep_stride);
+const char *zkl_replay_status_name(int status);
+
 /* ---- segment driver helpers (callers of the hot path: prove.rs:954-1175) ------------
  * The reference builds the full trace once and, per segment, slices it on the host
  * (vm/trace/mod.rs:367-384), reads boundary cells (prove.rs:1197-1287) and scans every row for gadget usage

@@ -224,6 +224,7 @@ def test_full_size_segment_properties(ctx, zkl):
     zkl.replay.verify_child_openings(ctx, step, fs)
     zkl.replay.verify_children_openings(ctx, [step, step], [fs, fs])      # the same through one device merge plan
     assert zkl.replay.replay_fs_from_steps(ctx, [step, step]) == [fs, fs]   # and the transcripts replayed in lockstep
+    assert zkl.replay.replay_children_native(ctx, [step, step]) == [fs, fs]  # transcripts + openings, host side in native code
     assert [bytes(x) for x in leaves] == zkl.replay.hash_rows(ctx, rows, 204)
     bad = trace.copy()
     bad[43, 100, 0] ^= np.uint64(1)  # register r1 on a carry row

@@ -142,6 +142,16 @@ def test_prove_program_multi_segment(ctx, zkl, oracle):
     tampered[2] = replace(tampered[2], proof=replace(tampered[2].proof, inner=replace(inner, trace_query_values=bad_rows)))
     with pytest.raises(ST.InvalidInput, match="child 2: trace openings"):
         zkl.replay.verify_children_openings(ctx, tampered, challenges)
+    # the same replay with the host side in native code (zkl_replay_children): identical challenges, same verdicts
+    assert zkl.replay.replay_children_native(ctx, [s.step for s in steps]) == challenges
+    with pytest.raises(ST.InvalidInput, match="child 2: trace openings"):
+        zkl.replay.replay_children_native(ctx, tampered)
+    assert zkl.replay.replay_children_native(ctx, tampered, verify_openings=False) == challenges
+    rebuilt = bytearray(steps[1].proof)
+    rebuilt[-20] ^= 1                          # a byte of the FRI remainder (the proof ends: 32 remainder bytes, u8 partitions, u64 nonce)
+    bad_rem = replace(steps[1].step, proof=replace(steps[1].step.proof, inner_bytes=bytes(rebuilt), inner=ST.InnerProof.parse(bytes(rebuilt))))
+    with pytest.raises(ST.InvalidInput, match="child 1: FRI remainder"):
+        zkl.replay.replay_children_native(ctx, [steps[0].step, bad_rem])
     ST.verify_chain([s.step for s in steps])
     assert len({s.step.digest() for s in steps}) == len(steps)
     assert ST.children_root_from_steps([s.step for s in steps]) == ST.children_root_from_steps([s.step for s in steps[::-1]])

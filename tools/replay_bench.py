@@ -42,9 +42,15 @@ t3 = time.time()
 zkl.replay.verify_children_openings(ctx, steps, fss)
 t4 = time.time()
 l2 = ctx.launches
+assert zkl.replay.replay_children_native(ctx, steps) == fss
+t5 = time.time()
+assert zkl.replay.replay_children_native(ctx, steps) == fss
+t6 = time.time()
+l3 = ctx.launches
 hashed = sum(len(fs.query_positions) for fs in fss)
 print(f"children {children}, opened positions {hashed}, proof bytes {sum(len(s.proof.inner_bytes) for s in steps)}")
 print(f"fs replay            {1e3 * (t0b - t0) / children:8.2f} ms/child  (per child, one C-ABI call per transcript step)")
 print(f"fs replay, lockstep  {1e3 * (t1b - t1a) / children:8.2f} ms/child  (all children per transcript step)")
 print(f"openings, per child  {1e3 * (t2 - t1) / children:8.2f} ms/child  ({(l1 - l0) // children} launches/child)")
 print(f"openings, one plan   {1e3 * (t4 - t3) / children:8.2f} ms/child  ({(l2 - l1) // 2} launches for all children; first call {1e3 * (t3 - t2):.1f} ms)")
+print(f"native, everything   {1e3 * (t6 - t5) / children:8.2f} ms/child  (zkl_replay_children: transcripts + openings, {(l3 - l2) // 2} launches for all children)")

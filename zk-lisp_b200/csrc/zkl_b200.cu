@@ -5,7 +5,9 @@
 #include <string.h>
 
 #include <algorithm>
+#include <array>
 #include <atomic>
+#include <map>
 #include <mutex>
 
 #include "kernels_air.cuh"
@@ -609,3 +611,4 @@ extern "C" int zkl_evaluate_columns(zkl_ctx *ctx, const zkl_fe *polys, size_t nc
 }
 
 #include "api_stark.inl"
+#include "api_replay.inl"

@@ -501,6 +501,37 @@ def verify_children_openings(hasher, steps: Sequence[StepProof], challenges: Seq
     plan.run(hasher)
 
 
+def replay_children_native(ctx, steps: Sequence[StepProof], verify_openings: bool = True) -> List[FsChallenges]:
+    """`replay_fs_from_steps` + `verify_children_openings` in ONE C-ABI call (`zkl_replay_children`, csrc/api_replay.inl): proof
+    parsing, transcript bookkeeping and plan building run in native code, the hashing on the device. `ctx` must be a GPU Context."""
+    import ctypes as C
+    from . import capi
+    k = len(steps)
+    if k == 0:
+        return []
+    kids = (capi.ChildProof * k)()
+    keep = []
+    for i, s in enumerate(steps):
+        proof = np.frombuffer(s.proof.inner_bytes, dtype=np.uint8)
+        pi = _ints_to_fe(air_public_inputs_of(s).to_elements())
+        keep += [proof, pi]
+        kids[i].proof, kids[i].proof_len = proof.ctypes.data, proof.shape[0]
+        kids[i].pi_elems, kids[i].num_pi = pi.ctypes.data, pi.shape[0]
+    out = (capi.ChildChallenges * k)()
+    stride = 256 + 16
+    deep = np.zeros((k, stride, 2), dtype=np.uint64)
+    ctx._check(ctx.lib.zkl_replay_children(ctx.h, kids, k, int(verify_openings), out, deep.ctypes.data, stride))
+    res = []
+    for i in range(k):
+        o = out[i]
+        if o.status:
+            layer = f" (layer {o.status >> 8})" if (o.status & 0xFF) == 12 else ""
+            raise InvalidInput(f"child {i}: {ctx.lib.zkl_replay_status_name(o.status & 0xFF).decode()}{layer}")
+        res.append(FsChallenges(o.z.int(), [int(lo) | (int(hi) << 64) for lo, hi in deep[i, :o.num_deep]],
+                                [o.alphas[j].int() for j in range(o.num_alphas)], list(o.positions[:o.num_positions]), int(o.pow_nonce)))
+    return res
+
+
 def verify_child_openings(hasher, step: StepProof, fs: FsChallenges) -> None:
     """Every opening of the child proof re-hashed against its commitment: trace rows and constraint rows at the query
     positions, FRI layer pairs at the folded positions, the remainder against the last FRI commitment."""
