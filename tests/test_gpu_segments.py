@@ -144,6 +144,9 @@ def test_prove_program_multi_segment(ctx, zkl, oracle):
         zkl.replay.verify_children_openings(ctx, tampered, challenges)
     # the same replay with the host side in native code (zkl_replay_children): identical challenges, same verdicts
     assert zkl.replay.replay_children_native(ctx, [s.step for s in steps]) == challenges
+    raw = bytearray(steps[2].proof)           # the native path reads the proof BYTES: flip the same bit there
+    raw[steps[2].proof.index(inner.trace_query_values[:48]) + 9] ^= 4
+    tampered[2] = replace(tampered[2], proof=replace(tampered[2].proof, inner_bytes=bytes(raw), inner=ST.InnerProof.parse(bytes(raw))))
     with pytest.raises(ST.InvalidInput, match="child 2: trace openings"):
         zkl.replay.replay_children_native(ctx, tampered)
     assert zkl.replay.replay_children_native(ctx, tampered, verify_openings=False) == challenges
