@@ -236,3 +236,39 @@ def test_poseidon_levels_match_trace_builder(ctx, zkl):
             assert [cell(out, i, 32 * lvl + r) for i in range(12)] == fin
     assert not out[12:].any()
     dt.free()
+
+
+def test_native_replay_with_partitions_and_mixed_children(ctx, zkl):
+    """zkl_replay_children on children of different sizes and partitionings in one batch: partitioned row leaves
+    (merge_many of partition digests, agg/child.rs:1031-1044), duplicate query draws (40 queries over 512 rows), different
+    numbers of FRI layers. Python replay on the same device hasher is the reference."""
+    if ctx.hash_mode not in ("default", "int-pipe"):
+        pytest.skip("covered by two hashing modes")
+    from dataclasses import replace
+    from util import single_segment_step
+    R = zkl.replay
+    kids = []
+    for n, seed, queries, parts, grind in ((32, 9, 40, (4, 8), 0), (64, 7, 8, None, 4), (128, 5, 16, (2, 16), 3)):
+        trace, air_pi, opts = synth.valid_segment(n=n, queries=queries, blowup=16, grind=grind, seed=seed)
+        if parts:
+            opts = replace(opts, num_partitions=parts[0], hash_rate=parts[1])
+        proof = zkl.ZkProver(ctx, opts, air_pi).prove(trace)
+        kids.append(single_segment_step(zkl, air_pi, opts, n, proof))
+    fss = [R.replay_fs_from_step(ctx, k) for k in kids]
+    assert len(fss[0].query_positions) < 40                      # duplicates were drawn and removed
+    R.verify_children_openings(ctx, kids, fss)
+    assert R.replay_fs_from_steps(ctx, kids) == fss
+    assert R.replay_children_native(ctx, kids) == fss
+    # a flipped bit in a partitioned child's opened constraint row
+    v = kids[0].proof.inner
+    raw = bytearray(kids[0].proof.inner_bytes)
+    raw[kids[0].proof.inner_bytes.index(v.constraint_query_values[:32]) + 5] ^= 2
+    bad = replace(kids[0], proof=replace(kids[0].proof, inner_bytes=bytes(raw), inner=zkl.step.InnerProof.parse(bytes(raw))))
+    with pytest.raises(zkl.step.InvalidInput, match="child 1: constraint openings"):
+        R.replay_children_native(ctx, [kids[1], bad, kids[2]])
+    with pytest.raises(zkl.step.InvalidInput, match="child 1: constraint openings"):
+        R.verify_children_openings(ctx, [kids[1], bad, kids[2]], [fss[1], fss[0], fss[2]])
+    # garbage instead of a proof is a per-child verdict, not a crash
+    junk = replace(kids[1], proof=replace(kids[1].proof, inner_bytes=bytes(kids[1].proof.inner_bytes[:100])))
+    with pytest.raises(zkl.step.InvalidInput, match="child 0: failed to decode"):
+        R.replay_children_native(ctx, [junk, kids[2]])
