@@ -276,3 +276,28 @@ def test_segment_features_and_masks(zkl):
     assert not m & (A.FM_RAM | A.FM_MERKLE | A.FM_SPONGE | A.FM_POSEIDON) and m & A.FM_VM and m & A.FM_VM_EXPECT
     core = A.FM_VM | A.FM_VM_EXPECT
     assert SG.compute_segment_feature_mask(core, SG.SegmentFeatures(vm=True, ram=True, sponge=True, merkle=True)) == core
+
+
+def test_planner_properties_random_programs(zkl):
+    """Invariants the reference's planner tests assert on one program (segment_planner.rs:370-414), over random block tables:
+    contiguous, level aligned, covering the padded trace, never above the row budget, and all full except possibly the last."""
+    from hypothesis import given, settings, strategies as st
+    PL = zkl.planner
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.integers(1, 3000), st.lists(st.tuples(st.integers(0, 2999), st.integers(0, 400)), max_size=6), st.integers(1, 300))
+    def check(base_levels, raw_blocks, budget_levels):
+        blocks = [(s, min(ln, base_levels - s)) for s, ln in raw_blocks if s < base_levels]
+        max_rows = budget_levels * 32
+        segs = PL.plan_segments(base_levels, blocks, max_segment_rows=max_rows)
+        total = PL.next_power_of_two(base_levels) * 32
+        assert segs[0].r_start == 0 and segs[-1].r_end == total
+        for a, b in zip(segs, segs[1:]):
+            assert a.r_end == b.r_start
+        if len(segs) == 1:
+            assert total <= max_rows or budget_levels >= total // 32
+        else:
+            assert all(s.r_end - s.r_start == max_rows for s in segs[:-1]) and 0 < segs[-1].r_end - segs[-1].r_start <= max_rows
+        assert all(s.r_start % 32 == 0 and s.r_end % 32 == 0 for s in segs)
+
+    check()
