@@ -259,6 +259,10 @@ typedef struct {
 int zkl_replay_children(zkl_ctx *ctx, const zkl_child_proof *children, size_t count, int verify_openings,
                         zkl_child_challenges *out, zkl_fe *out_deep, size_t deep_stride);
 const char *zkl_replay_status_name(int status);
+/* ProverChannel::grind on its own: smallest nonce >= 1 with trailing_zeros(u64_le(merge_with_int(seed, nonce)[0..8])) >= bits
+ * (check restated at agg/fs.rs:202-207). For provers that stay on the CPU (the aggregation proof) but whose proof-of-work
+ * search is 2^bits calls of the CPU hasher. bits = 0 returns nonce 0 like Winterfell. */
+int zkl_grind(zkl_ctx *ctx, const uint8_t seed[32], uint32_t bits, uint64_t *out_nonce);
 
 /* ---- segment driver helpers (callers of the hot path: prove.rs:954-1175) ------------
  * The reference builds the full trace once and, per segment, slices it on the host

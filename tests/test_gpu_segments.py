@@ -254,8 +254,14 @@ def test_native_replay_with_partitions_and_mixed_children(ctx, zkl):
             opts = replace(opts, num_partitions=parts[0], hash_rate=parts[1])
         proof = zkl.ZkProver(ctx, opts, air_pi).prove(trace)
         kids.append(single_segment_step(zkl, air_pi, opts, n, proof))
-    fss = [R.replay_fs_from_step(ctx, k) for k in kids]
+    seeds = [{} for _ in kids]
+    fss = [R.replay_fs_from_step(ctx, k, cap) for k, cap in zip(kids, seeds)]
     assert len(fss[0].query_positions) < 40                      # duplicates were drawn and removed
+    # zkl_grind on the replayed coin seed finds the prover's nonce (the smallest one), for every grinding factor incl. 0
+    assert [ctx.grind(cap["grinding_seed"], k.proof.inner.grinding) for k, cap in zip(kids, seeds)] == [f.pow_nonce for f in fss]
+    n12 = ctx.grind(seeds[1]["grinding_seed"], 12)
+    head = lambda v: int.from_bytes(ctx.merge_with_int(seeds[1]["grinding_seed"], [v])[0].tobytes()[:8], "little")
+    assert n12 >= 1 and head(n12) % (1 << 12) == 0 and all(head(v) % (1 << 12) for v in range(max(1, n12 - 300), n12))
     R.verify_children_openings(ctx, kids, fss)
     assert R.replay_fs_from_steps(ctx, kids) == fss
     assert R.replay_children_native(ctx, kids) == fss

@@ -128,6 +128,36 @@ struct rp_plan {
 };
 
 #ifndef ZKL_REPLAY_HOST_ONLY   // tests/host_replay.cc compiles the parser and the plan builder above with g++
+// Proof-of-work search on its own (ProverChannel::grind [WF-mem]; check restated at agg/fs.rs:202-207): the smallest nonce >= 1 with
+// trailing_zeros(u64_le(merge_with_int(seed, nonce)[0..8])) >= bits. The aggregation proof of the reference stays on the CPU prover,
+// but its grinding is 2^bits sponge calls on the slow CPU hasher — the one step of that proof worth sending to the device.
+extern "C" int zkl_grind(zkl_ctx *ctx, const uint8_t seed[32], uint32_t bits, uint64_t *out_nonce) {
+  ZKL_TRY(need_suite(ctx));
+  if (bits > 40) { ctx->set_error("grinding factor too large"); return 1; }
+  if (bits == 0) { *out_nonce = 0; return 0; }
+  fe sd = fold_digest_host(seed);
+  dev_buf<fe> coin; dev_buf<unsigned long long> nonce;
+  ZKL_CHECK(ctx, coin.alloc(1)); ZKL_CHECK(ctx, nonce.alloc(1));
+  ZKL_CHECK(ctx, cudaMemcpyAsync(coin.p, &sd, sizeof(fe), cudaMemcpyHostToDevice, ctx->stream));
+  ZKL_CHECK(ctx, cudaMemsetAsync(nonce.p, 0xFF, 8, ctx->stream));
+  unsigned long long nonce_h = ~0ull;
+  for (uint64_t base = 1;;) {
+    const uint64_t target = std::min<uint64_t>((uint64_t)16 << bits, (uint64_t)1 << 30);   // 16x the expected nonce per submission
+    if (ctx->hash_path == 0) { LAUNCH_TC_TILES(ctx, k_tc_grind, target, coin.p, base, (uint32_t)target, bits, nonce.p); base += target; }
+    else {
+      const uint32_t batch = 1u << 15;
+      int nb = (int)std::min<uint64_t>(std::max<uint64_t>(target / batch, 1), 512);
+      for (int b = 0; b < nb; b++, base += batch)
+        LAUNCH(ctx, k_grind, ceil_div((size_t)batch * ZKL_COOP_GROUP, ZKL_COOP_THREADS), ZKL_COOP_THREADS, 0, coin.p, base, batch, bits, nonce.p);
+    }
+    ZKL_CHECK(ctx, cudaMemcpyAsync(&nonce_h, nonce.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    ZKL_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (nonce_h != ~0ull) break;
+  }
+  *out_nonce = nonce_h;
+  return 0;
+}
+
 enum { RP_OK = 0, RP_MALFORMED = 1, RP_COMMITMENTS = 2, RP_OOD = 3, RP_FRI_DEGREE = 4, RP_POW = 5, RP_UNIQUE = 6, RP_TRACE_OPENING = 10,
        RP_CONSTRAINT_OPENING = 11, RP_FRI_OPENING = 12, RP_REMAINDER = 13, RP_BATCH_PROOF = 14 };
 extern "C" const char *zkl_replay_status_name(int status) {

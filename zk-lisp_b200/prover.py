@@ -107,6 +107,13 @@ class Context:
         self._check(self.lib.zkl_merge_with_int_pairs(self.h, s.ctypes.data, v.ctypes.data, v.shape[0], out.ctypes.data))
         return out
 
+    def grind(self, seed: bytes, bits: int) -> int:
+        """ProverChannel::grind: the smallest nonce >= 1 whose merge_with_int(seed, nonce) has `bits` trailing zero bits."""
+        s = np.frombuffer(bytes(seed), dtype=np.uint8).copy()
+        nonce = C.c_uint64()
+        self._check(self.lib.zkl_grind(self.h, s.ctypes.data, bits, C.byref(nonce)))
+        return int(nonce.value)
+
     def hash_bytes(self, data: bytes) -> bytes:
         d = np.frombuffer(bytes(data), dtype=np.uint8).copy() if data else np.zeros(1, dtype=np.uint8)
         out = np.zeros(32, dtype=np.uint8)

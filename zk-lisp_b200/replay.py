@@ -98,9 +98,10 @@ def _options_of(v: InnerProof) -> A.ProofOptions:
                           field_extension=v.field_extension)
 
 
-def replay_fs_from_step(hasher, step: StepProof) -> FsChallenges:
+def replay_fs_from_step(hasher, step: StepProof, capture: dict = None) -> FsChallenges:
     """agg/fs.rs:37-245. Everything comes from the step-proof bytes: the context elements from the proof's own context,
-    the number of composition columns from the width of the opened constraint rows."""
+    the number of composition columns from the width of the opened constraint rows. `capture`, when given, receives the coin
+    seed the prover ground against ("grinding_seed")."""
     v = step.proof.inner
     if v.aux_width != 0:
         raise InvalidInput("multi-segment trace must provide at least two trace commitments")
@@ -134,6 +135,8 @@ def replay_fs_from_step(hasher, step: StepProof) -> FsChallenges:
             raise InvalidInput("FRI degree truncation detected while replaying FS challenges")
         max_degree_plus_1 //= v.fri_folding
     # 6) proof of work, query positions
+    if capture is not None:
+        capture["grinding_seed"] = coin.seed
     if coin.check_leading_zeros(v.pow_nonce) < v.grinding:
         raise InvalidInput("pow_nonce does not satisfy grinding factor in FS replay")
     positions = sorted(set(coin.draw_integers(v.num_queries, v.lde_domain_size, v.pow_nonce)))
