@@ -54,3 +54,10 @@ print(f"fs replay, lockstep  {1e3 * (t1b - t1a) / children:8.2f} ms/child  (all 
 print(f"openings, per child  {1e3 * (t2 - t1) / children:8.2f} ms/child  ({(l1 - l0) // children} launches/child)")
 print(f"openings, one plan   {1e3 * (t4 - t3) / children:8.2f} ms/child  ({(l2 - l1) // 2} launches for all children; first call {1e3 * (t3 - t2):.1f} ms)")
 print(f"native, everything   {1e3 * (t6 - t5) / children:8.2f} ms/child  (zkl_replay_children: transcripts + openings, {(l3 - l2) // 2} launches for all children)")
+cap = {}
+zkl.replay.replay_fs_from_step(ctx, steps[0], cap)
+for bits in (16, 20):
+    ctx.grind(cap["grinding_seed"], bits)
+    t7 = time.time()
+    nonce = ctx.grind(cap["grinding_seed"], bits)
+    print(f"zkl_grind bits={bits}: nonce {nonce} in {1e3 * (time.time() - t7):.2f} ms")
