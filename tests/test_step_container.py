@@ -301,3 +301,41 @@ def test_planner_properties_random_programs(zkl):
         assert all(s.r_start % 32 == 0 and s.r_end % 32 == 0 for s in segs)
 
     check()
+
+
+def test_recursion_public_inputs_and_zklrc1_codec(zkl, proven):
+    """lib.rs:395-480 (build_public) and the ZKLRC1 artifact codec lib.rs:483-774 over a chain of step proofs."""
+    from dataclasses import replace
+    S, RC = zkl.step, zkl.recursion
+    steps = [_container(zkl, proven, i, 3) for i in range(3)]
+    core = steps[0].pi_core
+    rc = RC.build_recursion_public(core, steps)
+    assert rc.children_count == 3 and rc.children_ms == [64, 64, 64] and rc.v_units_total == 3 * 64 * 8
+    assert rc.pi_digest == S.public_inputs_digest(core) and rc.suite_id == core.program_id
+    assert rc.children_root == S.children_root_from_steps(steps)
+    assert (rc.vm_state_initial, rc.vm_state_final) == (steps[0].state_in_hash(), steps[-1].state_out_hash())
+    assert rc.rom_s_final == (steps[-1].proof.pi.rom_s_out_0, steps[-1].proof.pi.rom_s_out_1, steps[-1].proof.pi.rom_s_out_2)
+    assert (rc.profile_meta.m, rc.profile_meta.q, rc.profile_fri.lde_blowup, rc.profile_fri.num_layers) == (64, 8, 16, 1)
+    one = RC.from_step_proof(steps[1])
+    assert one.children_count == 1 and one.profile_fri.num_layers == len(steps[1].proof.inner.fri_layers)
+    assert one.children_root == S.children_root(core.program_id, [(steps[1].digest(), steps[1].proof.root_trace)])
+    els = rc.to_elements()
+    assert len(els) == 32 and els[18] == 3 and els[0] == zkl.field.fold_bytes32_to_fe(core.program_id)
+    assert els != replace(rc, vm_state_final=bytes(32)).to_elements()
+    with pytest.raises(RC.RecursionInvalid, match="at least one step"):
+        RC.build_recursion_public(core, [])
+    with pytest.raises(RC.RecursionInvalid, match="share the same program_id"):
+        RC.build_recursion_public(replace(core, main_args=[("u64", 1)]), steps)
+    blob = RC.encode(b"\x01\x02\x03 aggregation proof bytes", rc)
+    assert blob[:6] == b"ZKLRC1"
+    proof, back = RC.decode(blob)
+    assert proof == b"\x01\x02\x03 aggregation proof bytes" and back == rc and RC.encode(proof, back) == blob
+    with pytest.raises(S.InvalidInput, match="magic"):
+        RC.decode(b"ZKLRC2" + blob[6:])
+    with pytest.raises(S.InvalidInput, match="proof bytes truncated"):
+        RC.decode(blob[:-1])
+    with pytest.raises(S.InvalidInput, match="pi_digest truncated"):
+        RC.decode(blob[:6 + 70])
+    for cut in range(0, len(blob), 5):
+        with pytest.raises(S.InvalidInput):
+            RC.decode(blob[:cut])
