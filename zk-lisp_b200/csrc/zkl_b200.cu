@@ -18,7 +18,7 @@
 #include "kernels_tc.cuh"
 #include "kernels_tcntt.cuh"
 
-static std::string g_create_error;
+static thread_local std::string g_create_error;   // zkl_last_error(NULL) reports the calling thread's failed zkl_ctx_create
 static std::mutex g_suite_mutex;
 
 #define LAUNCH(ctx, kernel, grid, block, smem, ...)                                 \
