@@ -46,3 +46,16 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".inl", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.lower(), f
+
+
+def test_public_header_is_plain_c(tmp_path):
+    """The drop-in boundary is a C ABI: include/zkl_b200.h must compile as C99 (what cgo / bindgen / ctypes-style binders read)
+    and as C++, with nothing but plain pointers and sizes in the signatures."""
+    import subprocess
+    src = tmp_path / "h.c"
+    src.write_text('#include "zkl_b200.h"\nint main(void) { zkl_child_challenges c; (void)c; return (int)sizeof(zkl_fe) - 16; }\n')
+    inc = os.path.join(ROOT, "include")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-I", inc, str(src)])
+    subprocess.check_call(["g++", "-std=c++17", "-fsyntax-only", "-x", "c++", "-I", inc, str(src)])
+    header = open(os.path.join(inc, "zkl_b200.h")).read()
+    assert "torch" not in header.lower() and "std::" not in header
