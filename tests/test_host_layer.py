@@ -58,4 +58,5 @@ def test_public_header_is_plain_c(tmp_path):
     subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-I", inc, str(src)])
     subprocess.check_call(["g++", "-std=c++17", "-fsyntax-only", "-x", "c++", "-I", inc, str(src)])
     header = open(os.path.join(inc, "zkl_b200.h")).read()
-    assert "torch" not in header.lower() and "std::" not in header
+    code = re.sub(r"/\*.*?\*/", "", header, flags=re.S)          # comments may mention callers; declarations may not
+    assert "torch" not in code.lower() and "std::" not in code and "at::" not in code
