@@ -105,3 +105,43 @@ def test_prove_program_host_logic(zkl, oracle):
         raise RuntimeError("expected a failure")
     except ValueError as e:
         assert "no segments" in str(e)
+
+
+def test_apply_levels_absorb_marshalling(zkl):
+    """segments.apply_levels_absorb: inputs are zero padded to 10 per level, the PROGRAM suite (suite_id = program_id) is the one
+    handed to the C ABI; checked by restating zkl_poseidon_levels_dev in Python behind the stand-in library."""
+    SG, P = zkl.segments, zkl.field.P
+    seen = {}
+
+    class Lib:
+        def zkl_poseidon_levels_dev(self, h, trace_dev, n_rows, lanes_start, suite, levels, inputs, count):
+            lv = np.ctypeslib.as_array((C.c_uint32 * count).from_address(levels))
+            ins = np.ctypeslib.as_array((C.c_uint64 * (20 * count)).from_address(inputs)).reshape(count, 10, 2)
+            s = suite._obj
+            seen.update(levels=list(map(int, lv)), n_rows=n_rows, lanes_start=lanes_start, dom=[s.dom[0].int(), s.dom[1].int()],
+                        mds00=s.mds[0][0].int(), rc_last=s.rc[26][11].int(),
+                        inputs=[[int(a) | (int(b) << 64) for a, b in row] for row in ins])
+            return 0
+
+    class Ctx:
+        lib, h = Lib(), None
+
+        def _check(self, rc):
+            assert rc == 0
+
+    sid = bytes([3]) * 32
+    SG.apply_levels_absorb(Ctx(), 0xBEEF, 256, sid, [0, 5], [[1, 2], list(range(100, 112))], lanes_start=0)
+    suite = zkl.params.get_poseidon_suite(sid)
+    assert seen["levels"] == [0, 5] and seen["n_rows"] == 256 and seen["dom"] == list(suite.dom)
+    assert seen["mds00"] == suite.mds[0][0] and seen["rc_last"] == suite.rc[26][11]
+    assert seen["inputs"] == [[1, 2] + [0] * 8, list(range(100, 110))]          # padded to 10, extra inputs dropped (poseidon.rs:38-49)
+    assert suite.dom != zkl.params.get_poseidon_suite(bytes(32)).dom              # not the commitment hasher's suite
+    seen.clear()
+    SG.apply_levels_absorb(Ctx(), 0, 32, sid, [], [])
+    assert not seen
+    try:
+        SG.apply_levels_absorb(Ctx(), 0, 32, sid, [0], [])
+        raise RuntimeError("expected a failure")
+    except ValueError:
+        pass
+    assert all(0 <= x < P for x in seen.get("inputs", [[0]])[0])
