@@ -199,3 +199,41 @@ def test_children_openings_in_one_merge_plan(zkl, oracle, child):
         with pytest.raises(S.InvalidInput, match=msg):
             R.verify_children_openings(h, bad, fss)
     R.verify_children_openings(h, [], [])
+
+
+def test_deep_and_fri_arithmetic_of_a_child(zkl, oracle, child):
+    """agg/trace.rs:752-950, 1076-1193 on host integers: layer 0 is the DEEP composition of the opened rows, layers fold with
+    the replayed alphas, the remainder closes the chain; any moved value breaks exactly the link it belongs to."""
+    R, S = zkl.replay, zkl.step
+    step = child[0]
+    fs = R.verify_child(oracle, step)
+    for other in (_step(zkl, oracle, 32, 9, queries=40, parts=(4, 8), grind=0)[0], _step(zkl, oracle, 128, 5, queries=16)[0]):
+        R.verify_child(oracle, other)
+    v = step.proof.inner
+
+    def with_inner(**kw):
+        return replace(step, proof=replace(step.proof, inner=replace(v, **kw)))
+
+    def bump(b, i):                      # +1 on element i (stays a field element)
+        x = (int.from_bytes(b[16 * i:16 * i + 16], "little") + 1) % zkl.field.P
+        return b[:16 * i] + x.to_bytes(16, "little") + b[16 * i + 16:]
+
+    layers = list(v.fri_layers)
+    moved0 = [(bump(layers[0][0], 0), layers[0][1])] + layers[1:]
+    moved3 = layers[:3] + [(bump(layers[3][0], 1), layers[3][1])] + layers[4:]
+    cases = [("DEEP composition", dict(trace_query_values=bump(v.trace_query_values, 3))),
+             ("DEEP composition", dict(constraint_query_values=bump(v.constraint_query_values, 0))),
+             ("DEEP composition", dict(ood_trace=bump(v.ood_trace, 7))),
+             ("DEEP composition", dict(ood_constraints=bump(v.ood_constraints, 1))),
+             ("DEEP composition", dict(fri_layers=moved0)),
+             ("FRI layer [34] values", dict(fri_layers=moved3)),
+             ("remainder does not continue", dict(fri_remainder=bump(v.fri_remainder, 1)))]
+    for msg, kw in cases:
+        with pytest.raises(S.InvalidInput, match=msg):
+            R.verify_child_deep_and_fri(with_inner(**kw), fs)
+    with pytest.raises(S.InvalidInput, match="DEEP composition"):
+        R.verify_child_deep_and_fri(step, replace(fs, z_ood=fs.z_ood + 1))
+    with pytest.raises(S.InvalidInput):
+        R.verify_child_deep_and_fri(step, replace(fs, fri_alphas=[fs.fri_alphas[0] + 1] + fs.fri_alphas[1:]))
+    with pytest.raises(S.InvalidInput, match="degree exceeds"):
+        R.verify_child_deep_and_fri(with_inner(fri_remainder=v.fri_remainder + bytes(16)), fs)

@@ -222,6 +222,7 @@ def test_full_size_segment_properties(ctx, zkl):
     assert fs.query_positions == pos and fs.pow_nonce == nonce1 and fs.z_ood == int.from_bytes(bytes(s1.z), "little")
     assert len(fs.fri_alphas) == 12 and len(fs.deep_coeffs) == 204 + 7
     zkl.replay.verify_child_openings(ctx, step, fs)
+    zkl.replay.verify_child_deep_and_fri(step, fs)                        # 64 positions, 11 folds, remainder
     zkl.replay.verify_children_openings(ctx, [step, step], [fs, fs])      # the same through one device merge plan
     assert zkl.replay.replay_fs_from_steps(ctx, [step, step]) == [fs, fs]   # and the transcripts replayed in lockstep
     assert zkl.replay.replay_children_native(ctx, [step, step]) == [fs, fs]  # transcripts + openings, host side in native code

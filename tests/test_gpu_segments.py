@@ -129,6 +129,7 @@ def test_prove_program_multi_segment(ctx, zkl, oracle):
         assert fs.z_ood == int.from_bytes(bytes(summ.z), "little") and fs.pow_nonce == summ.pow_nonce
         assert fs.query_positions == list(summ.positions[:summ.num_unique_queries])
         zkl.replay.verify_child_openings(ctx, back, fs)
+        zkl.replay.verify_child_deep_and_fri(back, fs)         # DEEP composition and FRI folding arithmetic (agg/trace.rs:752-1193)
         challenges.append(fs)
     # ... and all four children at once: leaves in three hashing batches, every tree in ONE device merge plan (zkl_merge_plan)
     before = ctx.launches

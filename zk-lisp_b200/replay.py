@@ -504,6 +504,74 @@ def verify_children_openings(hasher, steps: Sequence[StepProof], challenges: Seq
     plan.run(hasher)
 
 
+def verify_child_deep_and_fri(step: StepProof, fs: FsChallenges) -> None:
+    """The arithmetic half of the child check the aggregation trace replays (agg/trace.rs:1076-1193 DEEP composition at the
+    query positions, :752-950 FRI folding and remainder): the values opened in FRI layer 0 must be the DEEP composition of
+    the opened trace / constraint rows and the OOD frame, every layer must fold into the next with the replayed alphas, and
+    the last layer must agree with the remainder polynomial. Host integers — 64 positions x (W + 7) products and 11 small
+    folds per child; the hashing half is `verify_child(ren)_openings`."""
+    from .field import GENERATOR, inv, root_of_unity
+    v = step.proof.inner
+    W, n, N = v.main_width, v.trace_len, v.lde_domain_size
+    fe = lambda b, i: int.from_bytes(b[16 * i:16 * i + 16], "little")
+    C = len(v.ood_constraints) // 32
+    if len(v.ood_trace) != 32 * W or C == 0 or len(fs.deep_coeffs) != W + C:
+        raise InvalidInput("invalid OOD frame layout in FS replay")
+    t_z, t_zg = [fe(v.ood_trace, c) for c in range(W)], [fe(v.ood_trace, W + c) for c in range(W)]
+    h_z, h_zg = [fe(v.ood_constraints, c) for c in range(C)], [fe(v.ood_constraints, C + c) for c in range(C)]
+    dc, z = fs.deep_coeffs, fs.z_ood
+    zg = z * root_of_unity(n.bit_length() - 1) % P
+    a_z = (sum(d * t for d, t in zip(dc, t_z)) + sum(d * h for d, h in zip(dc[W:], h_z))) % P
+    a_zg = (sum(d * t for d, t in zip(dc, t_zg)) + sum(d * h for d, h in zip(dc[W:], h_zg))) % P
+    trows, crows = v.trace_rows(), v.constraint_rows()
+    pos = fs.query_positions
+    if len(trows) != len(pos) or len(crows) != len(pos) or len(crows[0]) != C:
+        raise InvalidInput("invalid trace queries layout in ZlChildTranscript")
+    w_n = root_of_unity(N.bit_length() - 1)
+    evals = []
+    for p, tr, cr in zip(pos, trows, crows):
+        x = GENERATOR * pow(w_n, p, P) % P
+        a = (sum(d * t for d, t in zip(dc, tr)) + sum(d * h for d, h in zip(dc[W:], cr))) % P
+        evals.append(((a - a_z) * inv((x - z) % P) + (a - a_zg) * inv((x - zg) % P)) % P)
+    if len(fs.fri_alphas) != len(v.fri_layers) + 1:
+        raise InvalidInput("FRI layer count does not match the proof options")
+    positions, domain, w_d = list(pos), N, w_n
+    for d, (values, _) in enumerate(v.fri_layers):
+        folded = fold_positions(positions, domain, 2)
+        half = domain // 2
+        if len(values) != 32 * len(folded):
+            raise InvalidInput("FRI layer value count does not match the folded positions")
+        vals = [fe(values, i) for i in range(2 * len(folded))]
+        for p, e in zip(positions, evals):
+            if vals[2 * folded.index(p % half) + p // half] != e:
+                raise InvalidInput(f"FRI layer {d} values do not continue the previous layer" if d else
+                                   "FRI layer 0 values are not the DEEP composition of the opened rows")
+        alpha, nxt = fs.fri_alphas[d], []
+        for i, q in enumerate(folded):      # agg/trace.rs:803-820
+            x0 = GENERATOR * pow(w_d, q, P) % P
+            x1 = P - x0
+            v0, v1 = vals[2 * i], vals[2 * i + 1]
+            nxt.append((v1 * (alpha - x0) - v0 * (alpha - x1)) % P * inv((x1 - x0) % P) % P)
+        positions, evals, domain, w_d = folded, nxt, half, w_d * w_d % P
+    rem = v.fri_remainder_coeffs()          # highest degree first (agg/trace.rs:941-945)
+    if not rem or len(rem) > (n >> len(v.fri_layers)):
+        raise InvalidInput("FRI remainder degree exceeds the bound")
+    for p, e in zip(positions, evals):
+        x, acc = GENERATOR * pow(w_d, p, P) % P, 0
+        for c in rem:
+            acc = (acc * x + c) % P
+        if acc != e:
+            raise InvalidInput("FRI remainder does not continue the last layer")
+
+
+def verify_child(hasher, step: StepProof) -> FsChallenges:
+    """Everything the aggregation layer re-checks of one child: transcript, every Merkle opening, DEEP and FRI arithmetic."""
+    fs = replay_fs_from_step(hasher, step)
+    verify_child_openings(hasher, step, fs)
+    verify_child_deep_and_fri(step, fs)
+    return fs
+
+
 def replay_children_native(ctx, steps: Sequence[StepProof], verify_openings: bool = True) -> List[FsChallenges]:
     """`replay_fs_from_steps` + `verify_children_openings` in ONE C-ABI call (`zkl_replay_children`, csrc/api_replay.inl): proof
     parsing, transcript bookkeeping and plan building run in native code, the hashing on the device. `ctx` must be a GPU Context."""
