@@ -237,3 +237,34 @@ def test_deep_and_fri_arithmetic_of_a_child(zkl, oracle, child):
         R.verify_child_deep_and_fri(step, replace(fs, fri_alphas=[fs.fri_alphas[0] + 1] + fs.fri_alphas[1:]))
     with pytest.raises(S.InvalidInput, match="degree exceeds"):
         R.verify_child_deep_and_fri(with_inner(fri_remainder=v.fri_remainder + bytes(16)), fs)
+
+
+def test_per_query_merkle_paths(zkl, oracle, child):
+    """agg/child.rs:230-400 + tests/agg_child.rs:60-146: every extracted path folds back to its commitment through
+    merkle_root_from_leaf; leaf digests follow the partition convention; FRI entries carry folded positions and the opened pairs."""
+    R = zkl.replay
+    for step in (child[0], _step(zkl, oracle, 32, 9, queries=40, parts=(4, 8), grind=0)[0]):
+        fs = R.replay_fs_from_step(oracle, step)
+        v = step.proof.inner
+        mp = R.child_merkle_proofs(oracle, step, fs)
+        troots, croot, froots = v.parse_commitments()
+        depth = v.lde_domain_size.bit_length() - 1
+        assert len(mp.trace_paths) == len(mp.constraint_paths) == len(fs.query_positions)
+        for p, tp, cp in zip(fs.query_positions, mp.trace_paths, mp.constraint_paths):
+            assert len(tp.siblings) == len(cp.siblings) == depth
+            assert R.merkle_root_from_leaf(oracle, tp.leaf, p, tp.siblings) == troots[0]
+            assert R.merkle_root_from_leaf(oracle, cp.leaf, p, cp.siblings) == croot
+        assert R.merkle_root_from_leaf(oracle, mp.trace_paths[0].leaf, fs.query_positions[0] ^ 1, mp.trace_paths[0].siblings) != troots[0]
+        assert len(mp.fri_layers) == v.num_fri_layers
+        positions, domain = list(fs.query_positions), v.lde_domain_size
+        for d, layer in enumerate(mp.fri_layers):
+            positions = R.fold_positions(positions, domain)
+            assert [e.idx for e in layer] == positions and len(layer[0].path.siblings) == depth - 1 - d
+            for e in layer:
+                assert R.merkle_root_from_leaf(oracle, e.path.leaf, e.idx, e.path.siblings) == froots[d]
+                assert e.path.leaf == oracle.hash_elements(zkl.prover.ints_to_fe(list(e.values)).reshape(1, 2, 2))[0].tobytes()
+            domain //= 2
+    bad = replace(child[0], proof=replace(child[0].proof, inner=replace(child[0].proof.inner,
+                  trace_query_values=bytes([child[0].proof.inner.trace_query_values[0] ^ 1]) + child[0].proof.inner.trace_query_values[1:])))
+    with pytest.raises(zkl.step.InvalidInput, match="trace openings"):
+        R.child_merkle_proofs(oracle, bad, R.replay_fs_from_step(oracle, child[0]))

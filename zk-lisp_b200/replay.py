@@ -291,9 +291,9 @@ def hash_rows(hasher, rows: np.ndarray, psize: int) -> List[bytes]:
     return [hasher.merge_many(np.stack([d[q] for d in digests])) for q in range(k)]
 
 
-def batch_root(hasher, depth: int, lists: List[List[bytes]], leaves: Sequence[bytes], positions: Sequence[int]) -> bytes:
-    """BatchMerkleProof::get_root [WF-mem]: the root implied by `leaves` opened at `positions`; the merges of one tree level
-    are ONE batch."""
+def _walk_batch_opening(hasher, depth: int, lists: List[List[bytes]], leaves: Sequence[bytes], positions: Sequence[int]):
+    """BatchMerkleProof::get_root [WF-mem] with every digest it touches kept under its heap index (leaf i = 2^depth + i, root = 1);
+    the merges of one tree level are ONE batch."""
     if depth < 1 or len(leaves) != len(positions) or not positions:
         raise InvalidInput("malformed batch Merkle opening")
     n = 1 << depth
@@ -302,6 +302,7 @@ def batch_root(hasher, depth: int, lists: List[List[bytes]], leaves: Sequence[by
     if len(norm) != len(lists) or max(positions) >= n:
         raise InvalidInput("malformed batch Merkle opening")
     ptr = [0] * len(lists)
+    nodes = {}
 
     def take(s):
         if ptr[s] >= len(lists[s]):
@@ -316,6 +317,7 @@ def batch_root(hasher, depth: int, lists: List[List[bytes]], leaves: Sequence[by
     for i, e in enumerate(norm):
         lo = known[e] if e in known else take(i)
         hi = known[e + 1] if e + 1 in known else take(i)
+        nodes[n + e], nodes[n + e + 1] = lo, hi
         pairs.append(lo + hi)
     cur, vals = [(e + n) >> 1 for e in norm], merge(pairs)
     for _ in range(1, depth):
@@ -327,13 +329,105 @@ def batch_root(hasher, depth: int, lists: List[List[bytes]], leaves: Sequence[by
                 i += 1
             else:
                 sv = take(used)
+            nodes[cur[used]], nodes[sib] = me, sv
             pairs.append(sv + me if cur[used] & 1 else me + sv)
             ncur.append(sib >> 1)
             i += 1
         cur, vals = ncur, merge(pairs)
     if cur != [1] or any(ptr[s] != len(lists[s]) for s in range(len(lists))):
         raise InvalidInput("malformed batch Merkle opening")
-    return vals[0]
+    nodes[1] = vals[0]
+    return nodes
+
+
+def batch_root(hasher, depth: int, lists: List[List[bytes]], leaves: Sequence[bytes], positions: Sequence[int]) -> bytes:
+    """The root implied by `leaves` opened at `positions`."""
+    return _walk_batch_opening(hasher, depth, lists, leaves, positions)[1]
+
+
+def opening_paths(hasher, depth: int, lists: List[List[bytes]], leaves: Sequence[bytes], positions: Sequence[int]):
+    """BatchMerkleProof::into_openings [WF-mem]: (root, [siblings of position p, leaf level first]) — the individual authentication
+    paths `ZlMerklePath` carries (agg/child.rs:84-88, extracted at :250-292, folded by `merkle_root_from_leaf` :1049-1068)."""
+    nodes = _walk_batch_opening(hasher, depth, lists, leaves, positions)
+    paths = []
+    for p in positions:
+        idx, sibs = (1 << depth) + p, []
+        while idx > 1:
+            sibs.append(nodes[idx ^ 1])
+            idx >>= 1
+        paths.append(sibs)
+    return nodes[1], paths
+
+
+@dataclass
+class MerklePath:
+    """agg/child.rs:84-88 ZlMerklePath."""
+    leaf: bytes
+    siblings: List[bytes]
+
+
+@dataclass
+class FriLayerProof:
+    """agg/child.rs:92-97 ZlFriLayerProof: folded position, the opened pair, its path in the layer tree."""
+    idx: int
+    values: tuple
+    path: MerklePath
+
+
+@dataclass
+class MerkleProofs:
+    """agg/child.rs:101-110 ZlMerkleProofs."""
+    trace_paths: List[MerklePath]
+    constraint_paths: List[MerklePath]
+    fri_layers: List[List[FriLayerProof]]
+
+
+def merkle_root_from_leaf(hasher, leaf: bytes, index: int, siblings: Sequence[bytes]) -> bytes:
+    """agg/child.rs:1049-1068."""
+    acc = bytes(leaf)
+    for s in siblings:
+        pair = (s + acc) if index & 1 else (acc + s)
+        acc = hasher.merge(np.frombuffer(pair, dtype=np.uint8).reshape(1, 64))[0].tobytes()
+        index >>= 1
+    return acc
+
+
+def child_merkle_proofs(hasher, step: StepProof, fs: FsChallenges) -> MerkleProofs:
+    """agg/child.rs:230-400: per-query authentication paths of the trace, constraint and FRI layer trees, each checked against
+    its commitment while it is extracted."""
+    v = step.proof.inner
+    trace_roots, constraint_root, fri_roots = v.parse_commitments()
+    pos = fs.query_positions
+    k = len(pos)
+
+    def row_paths(values, width, paths_bytes, expected, what):
+        rows = np.frombuffer(values, dtype=np.uint64)
+        if k == 0 or width == 0 or rows.size != k * width * 2:
+            raise InvalidInput("invalid trace queries layout in ZlChildTranscript")
+        leaves = hash_rows(hasher, rows.reshape(k, width, 2), partition_size(v.num_partitions, v.hash_rate, width))
+        root, paths = opening_paths(hasher, *read_batch_proof(paths_bytes), leaves, pos)
+        if root != expected:
+            raise InvalidInput(what)
+        return [MerklePath(l, p) for l, p in zip(leaves, paths)]
+
+    trace = row_paths(v.trace_query_values, v.main_width, v.trace_query_paths, trace_roots[0], "trace openings do not match the trace commitment")
+    cons = row_paths(v.constraint_query_values, len(v.constraint_query_values) // (16 * k) if k else 0, v.constraint_query_paths,
+                     constraint_root, "constraint openings do not match the constraint commitment")
+    layers, positions, domain = [], list(pos), v.lde_domain_size
+    for d, (values, paths_bytes) in enumerate(v.fri_layers):
+        positions = fold_positions(positions, domain, v.fri_folding)
+        pairs = np.frombuffer(values, dtype=np.uint64)
+        if pairs.size != len(positions) * 4:
+            raise InvalidInput("FRI layer value count does not match the folded positions")
+        pairs = pairs.reshape(len(positions), 2, 2)
+        leaves = [x.tobytes() for x in hasher.hash_elements(pairs)]
+        root, paths = opening_paths(hasher, *read_batch_proof(paths_bytes), leaves, positions)
+        if root != fri_roots[d]:
+            raise InvalidInput(f"FRI layer {d} openings do not match the layer commitment")
+        ints = lambda e: int(e[0]) | (int(e[1]) << 64)
+        layers.append([FriLayerProof(q, (ints(pr[0]), ints(pr[1])), MerklePath(l, p)) for q, pr, l, p in zip(positions, pairs, leaves, paths)])
+        domain //= v.fri_folding
+    return MerkleProofs(trace, cons, layers)
 
 
 class MergePlan:
