@@ -268,3 +268,37 @@ def test_per_query_merkle_paths(zkl, oracle, child):
                   trace_query_values=bytes([child[0].proof.inner.trace_query_values[0] ^ 1]) + child[0].proof.inner.trace_query_values[1:])))
     with pytest.raises(zkl.step.InvalidInput, match="trace openings"):
         R.child_merkle_proofs(oracle, bad, R.replay_fs_from_step(oracle, child[0]))
+
+
+def test_child_compact_and_transcript_views(zkl, oracle, child):
+    """tests/transcript_basic.rs:48-178 and tests/agg_child.rs restated: the transcript's commitments recombine into the compact
+    root, shapes are consistent, tampering with a root is caught."""
+    AC, S = zkl.agg_child, zkl.step
+    step = child[0]
+    compact = AC.child_compact_from_step(oracle, step)
+    tx = AC.child_transcript_from_step(oracle, step, compact)
+    AC.verify_child_transcript(tx)
+    v = step.proof.inner
+    assert compact.step_digest == step.digest() and compact.trace_root == step.proof.root_trace and compact.pow_nonce == v.pow_nonce
+    assert compact.fs_challenges.query_positions == child[1].positions[:child[1].num_unique_queries]
+    assert len(compact.merkle_proofs.trace_paths) == tx.num_queries == len(tx.trace_main_openings) == len(tx.constraint_openings)
+    assert tx.fri_final.coeffs and tx.fri_final.deg <= len(tx.fri_final.coeffs) - 1
+    assert all(len(r) == tx.main_trace_width for r in tx.trace_main_openings)
+    assert tx.constraint_frame_width > 0 and all(len(r) == tx.constraint_frame_width for r in tx.constraint_openings)
+    assert len(tx.ood_main_current) == len(tx.ood_main_next) == tx.main_trace_width
+    assert len(tx.ood_quotient_current) == len(tx.ood_quotient_next) == tx.constraint_frame_width
+    assert len(tx.fri_layers) == v.num_fri_layers and all(tx.fri_layers)
+    assert [p.values for p in compact.merkle_proofs.fri_layers[0]] == tx.fri_layers[0]
+    # transcript_basic.rs: a tampered root no longer recombines
+    bad = replace(tx, trace_roots=[bytes([tx.trace_roots[0][0] ^ 1]) + tx.trace_roots[0][1:]])
+    with pytest.raises(S.InvalidInput, match="do not match compact trace_root"):
+        AC.verify_child_transcript(bad)
+    for kw, msg in ((dict(trace_main_openings=tx.trace_main_openings[:-1]), "trace_main_openings length"),
+                    (dict(constraint_openings=[r[:-1] for r in tx.constraint_openings]), "row width"),
+                    (dict(fri_layers=[[]] + tx.fri_layers[1:]), "empty FRI layer"),
+                    (dict(fri_final=AC.FriFinal(5, tx.fri_final.coeffs)), "deg exceeds"),
+                    (dict(fri_final=AC.FriFinal(0, [])), "must be non-empty"),
+                    (dict(num_queries=0), "must not contain trace openings")):
+        with pytest.raises(S.InvalidInput, match=msg):
+            AC.verify_child_transcript(replace(tx, **kw))
+    assert tx.fri_final.deg == max((i for i, c in enumerate(tx.fri_final.coeffs) if c), default=0)
