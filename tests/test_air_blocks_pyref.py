@@ -1,0 +1,39 @@
+"""CPU test: four blocks of the constraint system restated independently in Python (tests/pyair.py, from the reference text)
+against the checker's evaluate_transition on random frames with random periodic values — value by value, index by index."""
+import random
+
+import pytest
+
+import pyair
+import synth
+from util import P, from_fe, rand_fe, to_fe
+
+
+@pytest.mark.parametrize("cfg", [dict(), dict(usage_mask=0x7F, ram_bits=0), dict(ram=False, merkle=False), dict(merkle=False, ram_bits=0x80000001)])
+def test_poseidon_ram_merkle_rom_blocks_match_python_restatement(zkl, oracle, cfg):
+    trace, air_pi, opts = synth.random_segment(seed=13, **cfg)
+    a = zkl.air.Air(trace.shape[0], trace.shape[1], air_pi, opts)
+    ac = a.to_c()
+    rng = random.Random(17)
+    w0, w1 = zkl.params.rom_weights_for_seed(zkl.params.ROM_W_SEED_0), zkl.params.rom_weights_for_seed(zkl.params.ROM_W_SEED_1)
+    root_fe = zkl.field.be_from_le8(air_pi.core.merkle_root)
+    for trial in range(3):
+        cur, nxt, per = rand_fe(rng, a.width), rand_fe(rng, a.width), rand_fe(rng, 32)
+        if trial == 2:       # structured values: selector / flag columns as bits, a quiet periodic row
+            cur = [v & 1 if i % 3 else v for i, v in enumerate(cur)]
+            per = [1] + [0] * 31
+        got = from_fe(oracle.eval_transition_frame(ac, to_fe(cur), to_fe(nxt), to_fe(per)))
+        assert len(got) == len(a.degrees)
+        rom = pyair.rom_block(a, cur, nxt, per, w0, w1)
+        assert got[-len(rom):] == rom and len(rom) == 86
+        end = len(got) - len(rom)
+        if a.fm & zkl.air.FM_MERKLE:
+            mk = pyair.merkle_block(a, cur, nxt, per, root_fe)
+            assert got[end - 7:end] == mk
+            end -= 7
+        if a.fm & zkl.air.FM_RAM:
+            ram = pyair.ram_block(a, cur, nxt, per)
+            assert got[end - len(ram):end] == ram, [i for i, (x, y) in enumerate(zip(got[end - len(ram):end], ram)) if x != y]
+        pose = pyair.poseidon_block(a, cur, nxt, per)
+        assert got[:len(pose)] == pose and len(pose) in (336, 346)
+    assert all(0 <= x < P for x in got)
