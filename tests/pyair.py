@@ -118,3 +118,135 @@ def rom_block(a, cur, nxt, per, w0, w1):
     out.append(p_map * (s[1] - rom_encode(a, cur, w0)) % P)
     out.append(p_map * (s[2] - rom_encode(a, cur, w1)) % P)
     return out
+
+
+# ---- VmCtrlAir (ctrl.rs:114-390) and VmAluAir (alu.rs:108-354) -----------------------------------------------------
+OP_ORDER = ["const", "mov", "add", "sub", "mul", "neg", "eq", "select", "sponge", "assert", "assert_bit", "assert_range",
+            "divmod", "div128", "mulwide", "load", "store"]          # the order of the op booleanity / ROM lists (ctrl.rs:262-340)
+
+
+def _low(per):                       # mixers.rs:19-24
+    return per[1 + R + 3] * per[0] % P
+
+
+def ctrl_block(a, cur, nxt, per, rom_enabled):
+    c = a.cols
+    p_map = per[0]
+    pi_prog = cur[c.pi_prog]
+    s_low, s_high = _low(per), _low(per) * pi_prog % P
+    b = {name: cur[getattr(c, "op_" + name)] for name in OP_ORDER}
+    out = []
+    sums = [0] * 5
+    starts = (c.sel_dst0_start, c.sel_a_start, c.sel_b_start, c.sel_c_start, c.sel_dst1_start)
+    for i in range(NR):
+        for k, st in enumerate(starts):
+            v = cur[st + i]
+            sums[k] += v
+            out.append((p_map * v * (v - 1) + s_high) % P)
+    uses_a = sum(b[k] for k in ("mov", "add", "sub", "mul", "neg", "eq", "select", "divmod", "div128", "mulwide", "load", "store"))
+    uses_b = sum(b[k] for k in ("add", "sub", "mul", "eq", "select", "divmod", "div128", "mulwide", "store"))
+    uses_c = b["select"] + b["assert"] + b["assert_bit"] + b["assert_range"]
+    op_any = sum(b[k] for k in OP_ORDER[:15])
+    uses_dst0 = op_any - b["sponge"] + b["load"]
+    uses_dst1 = b["divmod"] + b["div128"] + b["mulwide"]
+    for total, uses in zip(sums, (uses_dst0, uses_a, uses_b, uses_c, uses_dst1)):
+        out.append((p_map * (total - uses) + s_low) % P)
+    for i in range(NR):
+        out.append((p_map * cur[c.sel_dst0_start + i] * cur[c.sel_dst1_start + i] + s_high) % P)
+    if a.fm & 32 and (a.air_pi.vm_usage_mask >> 7) & 1:       # FM_SPONGE and sponge used
+        for lane in range(10):
+            for k in range(3):
+                v = cur[c.sel_s_bits_start + 3 * lane + k]
+                out.append((p_map * v * (v - 1) + s_high) % P)
+            act = cur[c.sel_s_active_start + lane]
+            out.append((p_map * act * (act - 1) + s_high) % P)
+    out.append(s_high)
+    for name in OP_ORDER:
+        out.append((p_map * b[name] * (b[name] - 1) + s_high) % P)
+    op_sum = sum(b.values())
+    out.append((p_map * op_sum * (op_sum - 1) + s_high) % P)
+    for k, name in enumerate(OP_ORDER):
+        out.append((rom_enabled * p_map * (b[name] - cur[c.rom_op_start + k]) + s_high) % P)
+    g_carry = p_map + (per[1 + R + 1] - per[1 + R + 2]) + sum(per[1 + j] for j in range(R - 1))
+    out.append((rom_enabled * (g_carry * (nxt[c.pc] - cur[c.pc])) + s_low) % P)
+    out.append((rom_enabled * (per[1 + R + 2] * (nxt[c.pc] - (cur[c.pc] + 1))) + s_low) % P)
+    return out
+
+
+def alu_block(a, cur, nxt, per):
+    c = a.cols
+    mask = a.air_pi.vm_usage_mask
+    use = lambda bit: (mask >> bit) & 1               # layout.rs VM_USAGE_*: assert 0, assert_bit 1, assert_range 2, divmod 3,
+    use_assert, use_assert_bit, use_assert_range = use(0), use(1), use(2)        # mulwide 4, div128 5, eq 6
+    use_divmod, use_mulwide, use_div128, use_eq = use(3), use(4), use(5), use(6)
+    p_map, p_final, p_pad, p_pad_last = per[0], per[1 + R], per[1 + R + 1], per[1 + R + 2]
+    pi = cur[c.pi_prog]
+    s_low = _low(per)
+    s_write, s_eq = s_low * pow(pi, 6, P) % P, s_low * pow(pi, 4, P) % P
+    g_carry = p_map + (p_pad - p_pad_last) + sum(per[1 + j] for j in range(R - 1))
+    regs = [cur[c.r_index(i)] for i in range(NR)]
+    a_val = sum(cur[c.sel_a_start + i] * regs[i] for i in range(NR))
+    b_val = sum(cur[c.sel_b_start + i] * regs[i] for i in range(NR))
+    c_val = sum(cur[c.sel_c_start + i] * regs[i] for i in range(NR))
+    out = [(g_carry * (nxt[c.r_index(i)] - regs[i]) + s_low) % P for i in range(NR)]
+    imm = cur[c.imm]
+    b = {name: cur[getattr(c, "op_" + name)] for name in OP_ORDER}
+    mode64 = cur[c.eq_inv]
+    dst0_next = sum(cur[c.sel_dst0_start + i] * nxt[c.r_index(i)] for i in range(NR))
+    dst0_cur = sum(cur[c.sel_dst0_start + i] * regs[i] for i in range(NR))
+    dst1_next = sum(cur[c.sel_dst1_start + i] * nxt[c.r_index(i)] for i in range(NR))
+    res = (b["const"] * imm + b["mov"] * a_val + b["add"] * (a_val + b_val) + b["sub"] * (a_val - b_val) + b["mul"] * (a_val * b_val)
+           + b["neg"] * (-a_val) + b["select"] * (c_val * a_val + (1 - c_val) * b_val) + b["sponge"] * cur[c.lane_l]
+           + (b["eq"] * dst0_next if use_eq else 0) + (b["assert"] if use_assert else 0) + (b["assert_bit"] if use_assert_bit else 0)
+           + b["load"] * imm)
+    bits_sum = sum((1 << i) * cur[c.gadget_b_start + i] for i in range(32))
+    if use_assert_range:
+        res += b["assert_range"] * ((1 - imm) * bits_sum + imm)
+    b_two = (b["divmod"] + b["mulwide"] + b["div128"]) if (use_divmod or use_mulwide or use_div128) else 0
+    for i in range(NR):
+        sd0, sd1 = cur[c.sel_dst0_start + i], cur[c.sel_dst1_start + i]
+        keep = 1 - sd0 - sd1
+        w0 = (1 - b_two) * res + b_two * dst0_next
+        w1 = b_two * dst1_next
+        out.append((p_final * (nxt[c.r_index(i)] - (keep * regs[i] + sd0 * w0 + sd1 * w1)) + s_write) % P)
+    diff, inv_ = a_val - b_val, cur[c.eq_inv]
+    if use_eq:
+        out.append((p_final * b["eq"] * (dst0_next * diff) + s_eq) % P)
+        out.append((p_final * b["eq"] * ((1 - dst0_next) - diff * inv_) + s_eq) % P)
+    if use_divmod:
+        out.append((p_final * b["divmod"] * (a_val - b_val * dst0_next - dst1_next) + s_eq) % P)
+        out.append((p_final * b["divmod"] * (b_val * inv_ - 1) + s_eq) % P)
+    p2_64 = 1 << 64
+    if use_mulwide:
+        out.append((p_final * b["mulwide"] * (a_val * b_val - (dst0_next + dst1_next * p2_64)) + s_eq) % P)
+    if use_div128:
+        out.append((p_final * b["div128"] * ((a_val * p2_64 + imm) - (b_val * dst0_next + dst1_next)) + s_eq) % P)
+        out.append((p_final * b["div128"] * (b_val * inv_ - 1) + s_eq) % P)
+    if use_assert:
+        out.append((p_final * (b["assert"] * (c_val - 1) + b["select"] * (c_val * (c_val - 1))) + s_eq) % P)
+    if use_assert_bit:
+        out.append((p_final * b["assert_bit"] * (c_val * (c_val - 1)) + s_eq) % P)
+    if use_assert_range:
+        for i in range(32):
+            bi = cur[c.gadget_b_start + i]
+            out.append((p_final * b["assert_range"] * (bi * (bi - 1)) + s_eq) % P)
+        eq32 = c_val - bits_sum
+        eq64 = c_val - (dst0_cur + bits_sum * (1 << 32))
+        out.append((p_final * b["assert_range"] * (imm * (mode64 * eq64 + (1 - mode64) * eq32)) + s_eq) % P)
+    return out
+
+
+def evaluate_transition(a, cur, nxt, per, w0, w1, merkle_root_fe, rom_enabled=1):
+    """vm/air/mod.rs:324-357: the whole vector in block order."""
+    out = []
+    if a.fm & 1:
+        out += poseidon_block(a, cur, nxt, per)
+    if a.fm & 2:
+        out += ctrl_block(a, cur, nxt, per, rom_enabled) + alu_block(a, cur, nxt, per)
+    if a.fm & 128:
+        out += ram_block(a, cur, nxt, per)
+    if a.fm & 64:
+        out += merkle_block(a, cur, nxt, per, merkle_root_fe)
+    if rom_enabled:
+        out += rom_block(a, cur, nxt, per, w0, w1)
+    return out

@@ -37,3 +37,25 @@ def test_poseidon_ram_merkle_rom_blocks_match_python_restatement(zkl, oracle, cf
         pose = pyair.poseidon_block(a, cur, nxt, per)
         assert got[:len(pose)] == pose and len(pose) in (336, 346)
     assert all(0 <= x < P for x in got)
+
+
+@pytest.mark.parametrize("cfg", [dict(), dict(usage_mask=0x7F, ram_bits=0), dict(usage_mask=0, ram=False, merkle=False),
+                                 dict(usage_mask=0x155, merkle=False, ram_bits=0x80000001), dict(usage_mask=0xAA, ram=False),
+                                 dict(sponge=False, usage_mask=0x1FF), dict(poseidon=False, sponge=False, merkle=False, usage_mask=0x3F)])
+def test_whole_transition_vector_matches_python_restatement(zkl, oracle, cfg):
+    """All six blocks (Poseidon, VM control, VM ALU, RAM, Merkle, ROM) in evaluate_transition order, every usage-mask-dependent
+    constraint set, against the checker — the complete constraint vector, index by index."""
+    trace, air_pi, opts = synth.random_segment(seed=29, **cfg)
+    a = zkl.air.Air(trace.shape[0], trace.shape[1], air_pi, opts)
+    ac = a.to_c()
+    rng = random.Random(31)
+    w0, w1 = zkl.params.rom_weights_for_seed(zkl.params.ROM_W_SEED_0), zkl.params.rom_weights_for_seed(zkl.params.ROM_W_SEED_1)
+    root_fe = zkl.field.be_from_le8(air_pi.core.merkle_root)
+    for trial in range(3):
+        cur, nxt, per = rand_fe(rng, a.width), rand_fe(rng, a.width), rand_fe(rng, 32)
+        if trial == 1:
+            per = [0] * 28 + [1, 0, 0, 0]       # the final row of a level: the write and gadget constraints are live
+        got = from_fe(oracle.eval_transition_frame(ac, to_fe(cur), to_fe(nxt), to_fe(per)))
+        exp = pyair.evaluate_transition(a, cur, nxt, per, w0, w1, root_fe)
+        assert len(got) == len(exp) == len(a.degrees)
+        assert got == exp, [i for i, (x, y) in enumerate(zip(got, exp)) if x != y][:8]
