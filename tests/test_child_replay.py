@@ -302,3 +302,32 @@ def test_child_compact_and_transcript_views(zkl, oracle, child):
         with pytest.raises(S.InvalidInput, match=msg):
             AC.verify_child_transcript(replace(tx, **kw))
     assert tx.fri_final.deg == max((i for i, c in enumerate(tx.fri_final.coeffs) if c), default=0)
+
+
+def test_python_verifier_ood_consistency(zkl, oracle, child):
+    """The last link of an independent verifier: constraints evaluated at z from the OOD frame (Python restatement of the AIR),
+    divided and combined with the composition coefficients of the replayed transcript, equal the composition columns at z —
+    and any moved OOD value, public input or constraint breaks the equality."""
+    import pyverify
+    from util import P, from_fe
+    n = 64
+    for x in (3, 0x1234567 << 70 | 5, P - 2):
+        assert pyverify.periodic_at(n, x) == from_fe(oracle.periodic_at(n, x))
+    step, _, air = child
+    lhs, rhs, z = pyverify.ood_check(zkl, oracle, step, air)
+    assert lhs == rhs and z == zkl.replay.replay_fs_from_step(oracle, step).z_ood
+    good = rhs
+    v = step.proof.inner
+    bump = lambda b, i: b[:16 * i] + ((int.from_bytes(b[16 * i:16 * i + 16], "little") + 1) % P).to_bytes(16, "little") + b[16 * i + 16:]
+    for kw in (dict(ood_trace=bump(v.ood_trace, 45)), dict(ood_trace=bump(v.ood_trace, v.main_width + 45)), dict(ood_constraints=bump(v.ood_constraints, 2))):
+        bad = replace(step, proof=replace(step.proof, inner=replace(v, **kw)))
+        lhs, rhs, _ = pyverify.ood_check(zkl, oracle, bad, air)
+        assert lhs != rhs
+    # (a schedule column's NEXT-row value enters no transition constraint: moving it must leave the left side alone)
+    quiet = replace(step, proof=replace(step.proof, inner=replace(v, ood_trace=bump(v.ood_trace, v.main_width + 12))))
+    assert pyverify.ood_check(zkl, oracle, quiet, air)[0] == good
+    # a proof of another shape: RAM-less layout with more queries and partitions
+    step2, _, air2 = _step(zkl, oracle, 32, 9, queries=40, parts=(4, 8), grind=0)
+    lhs, rhs, _ = pyverify.ood_check(zkl, oracle, step2, air2)
+    assert lhs == rhs
+    zkl.replay.verify_child(oracle, step2)
