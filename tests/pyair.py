@@ -250,3 +250,49 @@ def evaluate_transition(a, cur, nxt, per, w0, w1, merkle_root_fe, rom_enabled=1)
     if rom_enabled:
         out += rom_block(a, cur, nxt, per, w0, w1)
     return out
+
+
+def assertions(cols, n, air_pi, fm):
+    """get_assertions (vm/air/mod.rs:380-504) with ScheduleAir (schedule.rs:42-140) and RomAir (rom.rs:122-147), restated from the
+    reference text: (column, row, value) in emission order, first occurrence of a (column, row) kept."""
+    from zk_lisp_b200 import params
+    from zk_lisp_b200.air import encode_main_args_to_slots
+    from zk_lisp_b200.field import be_from_le8
+    core = air_pi.core
+    last = n - 1
+    dom = params.get_poseidon_suite(bytes(core.program_id)).dom
+    rom = any(core.program_commitment)
+    out = []
+    for lvl in range((last + 1) // 32):
+        base = lvl * 32
+        row_map, row_final = base, base + 1 + R
+        out += [(cols.lane_c0, row_map, dom[0]), (cols.lane_c1, row_map, dom[1]), (cols.g_map, row_map, 1), (cols.g_final, row_final, 1)]
+        out += [(cols.g_r_index(j), base + 1 + j, 1) for j in range(R)]
+        out.append((cols.g_final, row_map, 0))
+        out += [(cols.g_r_index(j), row_map, 0) for j in range(R)]
+        out.append((cols.g_map, row_final, 0))
+        out += [(cols.g_r_index(j), row_final, 0) for j in range(R)]
+        for j in range(R):
+            out += [(cols.g_map, base + 1 + j, 0), (cols.g_final, base + 1 + j, 0)]
+        if lvl == 0 and fm & 2:
+            if air_pi.pc_init == 0 and rom:
+                out.append((cols.pi_prog, row_map, be_from_le8(core.program_commitment)))
+            out.append((cols.pc, row_map, air_pi.pc_init))
+    if fm & 2:
+        if fm & 16:      # FM_VM_EXPECT
+            out.append((cols.r_index(min(core.vm_out_reg, NR - 1)), min(core.vm_out_row, last), be_from_le8(core.vm_expected_bytes)))
+        slots = encode_main_args_to_slots(core.main_args)
+        if air_pi.pc_init == 0 and slots:
+            assert len(slots) <= NR
+            out += [(cols.r_index(NR - len(slots) + j), 0, v) for j, v in enumerate(slots)]
+    if rom:
+        out += [(cols.rom_s_index(i), 0, air_pi.rom_s_in[i]) for i in range(3)]
+        out += [(cols.rom_s_index(i), last, air_pi.rom_s_out[i]) for i in range(3)]
+    if not out:
+        out.append((cols.mask, last, 0))
+    seen, dedup = set(), []
+    for col, row, val in out:
+        if (col, row) not in seen:
+            seen.add((col, row))
+            dedup.append((col, row, val % P))
+    return dedup

@@ -59,3 +59,19 @@ def test_whole_transition_vector_matches_python_restatement(zkl, oracle, cfg):
         exp = pyair.evaluate_transition(a, cur, nxt, per, w0, w1, root_fe)
         assert len(got) == len(exp) == len(a.degrees)
         assert got == exp, [i for i, (x, y) in enumerate(zip(got, exp)) if x != y][:8]
+
+
+@pytest.mark.parametrize("cfg", [dict(), dict(pc_init=5), dict(vm_expect=True, main_args=(("u64", 7), ("bytes32", bytes(range(32))))),
+                                 dict(vm=False, sponge=False, ram=False, merkle=False), dict(ram=False, merkle=False, n=128)])
+def test_assertions_match_python_restatement(zkl, cfg):
+    """Boundary assertions of the host AIR mirror (air.py) against a second restatement of get_assertions: same (column, row,
+    value) set, same count — the count enters the proof context and the coin seed, the sorted order the coefficient indices."""
+    trace, air_pi, opts = synth.random_segment(seed=41, **cfg)
+    a = zkl.air.Air(trace.shape[0], trace.shape[1], air_pi, opts)
+    exp = pyair.assertions(a.cols, trace.shape[1], air_pi, a.fm)
+    key = lambda t: (t[1], t[0])
+    assert sorted(a.assertions, key=key) == sorted(exp, key=key)
+    assert len(a.assertions) == len({(c, r) for c, r, _ in a.assertions}) == len(exp)
+    assert a.num_constraints == len(a.degrees) + len(exp)
+    per_level = 4 + 27 + 1 + 27 + 1 + 27 + 54
+    assert len(exp) >= per_level * (trace.shape[1] // 32)
