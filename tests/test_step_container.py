@@ -2,7 +2,6 @@
 They read like the reference's tests/step_serialization.rs, tests/transcript_basic.rs:48-115 and the unit tests at
 segment_planner.rs:336-475. Proof bytes come from the CPU checker (tests only); the GPU suite repeats the container
 checks on GPU proofs (test_gpu_segments.py)."""
-import numpy as np
 import pytest
 
 import synth
