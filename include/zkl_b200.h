@@ -259,6 +259,11 @@ typedef struct {
 int zkl_replay_children(zkl_ctx *ctx, const zkl_child_proof *children, size_t count, int verify_openings,
                         zkl_child_challenges *out, zkl_fe *out_deep, size_t deep_stride);
 const char *zkl_replay_status_name(int status);
+/* poseidon_hash_two_lanes (poseidon/mod.rs:255-291) under an arbitrary suite, computed on the host with the kernels' limb
+ * arithmetic: out[i] = lane 0 of the permutation of [left[i], right[i], 0 x 8, dom0, dom1]. Used by the step digest
+ * (proof/digest.rs:15-68) and the children root (agg/child.rs:853-895), which run under the PROGRAM's suite. Inputs must be
+ * canonical (< p). Needs no context and no device. */
+int zkl_hash_two_lanes_host(const zkl_suite *suite, const zkl_fe *left, const zkl_fe *right, size_t count, zkl_fe *out);
 /* ProverChannel::grind on its own: smallest nonce >= 1 with trailing_zeros(u64_le(merge_with_int(seed, nonce)[0..8])) >= bits
  * (check restated at agg/fs.rs:202-207). For provers that stay on the CPU (the aggregation proof) but whose proof-of-work
  * search is 2^bits calls of the CPU hasher. bits = 0 returns nonce 0 like Winterfell. */

@@ -338,3 +338,23 @@ def test_recursion_public_inputs_and_zklrc1_codec(zkl, proven):
     for cut in range(0, len(blob), 5):
         with pytest.raises(S.InvalidInput):
             RC.decode(blob[:cut])
+
+
+def test_native_two_lane_hash_matches_python(zkl):
+    """zkl_hash_two_lanes_host (the kernels' limb arithmetic compiled for the host) against the Python-integer permutation,
+    under the hasher suite and a program suite, incl. edge values; batches keep their order."""
+    import random
+    import time
+    S, P = zkl.step, zkl.field.P
+    rng = random.Random(3)
+    for sid in (bytes(32), bytes([7]) * 32):
+        pairs = [(0, 0), (1, 0), (0, 1), (P - 1, P - 1), (P - 1, 1), ((1 << 127) + 12345, (1 << 64) - 1)]
+        pairs += [(rng.randrange(P), rng.randrange(P)) for _ in range(20)]
+        got = S.hash_two_lanes_batch(sid, pairs)
+        assert got == [S.poseidon_hash_two_lanes_py(sid, l, r) for l, r in pairs]
+        assert S.poseidon_hash_two_lanes(sid, *pairs[7]) == got[7] and all(0 <= x < P for x in got)
+        assert S.hash_two_lanes_batch(sid, [(l + P, r + 2 * P) for l, r in pairs[:3]]) == got[:3]      # reduced before the call
+    assert S.hash_two_lanes_batch(bytes(32), []) == []
+    t = time.time()
+    S.hash_two_lanes_batch(bytes(32), [(i, i + 1) for i in range(200)])
+    assert time.time() - t < 2.0

@@ -185,6 +185,7 @@ def load_library():
     sig("zkl_merge_with_int_pairs", C.c_int, vp, vp, vp, sz, vp)
     sig("zkl_replay_children", C.c_int, vp, C.POINTER(ChildProof), sz, C.c_int, C.POINTER(ChildChallenges), vp, sz)
     sig("zkl_replay_status_name", C.c_char_p, C.c_int)
+    sig("zkl_hash_two_lanes_host", C.c_int, C.POINTER(Suite), vp, vp, sz, vp)
     sig("zkl_grind", C.c_int, vp, vp, C.c_uint32, C.POINTER(C.c_uint64))
     sig("zkl_merge_plan", C.c_int, vp, vp, sz, vp, vp, vp, sz, vp, sz, vp)
     sig("zkl_set_bulk_threshold", C.c_int, vp, C.c_long)
@@ -204,5 +205,5 @@ EXPORTED_SYMBOLS = [
     "zkl_trace_query", "zkl_eval_constraints", "zkl_constraint_commit",
     "zkl_constraint_commitment_free", "zkl_constraint_query", "zkl_prove_segment",
     "zkl_prove_segment_dev", "zkl_stage_name", "zkl_dev_alloc", "zkl_dev_free", "zkl_dev_upload",
-    "zkl_sync", "zkl_slice_segment_dev", "zkl_usage_mask_dev", "zkl_read_cells_dev", "zkl_timer_start", "zkl_timer_stop", "zkl_imad_peak", "zkl_set_bulk_threshold", "zkl_set_hash_path", "zkl_set_ntt_path", "zkl_set_coop_path", "zkl_bench_permute", "zkl_partition_size", "zkl_lde_dev", "zkl_hash_partitions_dev", "zkl_merge_partition_digests_dev", "zkl_merkle_dev", "zkl_dev_download", "zkl_merge_plan", "zkl_poseidon_levels_dev", "zkl_merge_with_int_pairs", "zkl_replay_children", "zkl_replay_status_name", "zkl_grind",
+    "zkl_sync", "zkl_slice_segment_dev", "zkl_usage_mask_dev", "zkl_read_cells_dev", "zkl_timer_start", "zkl_timer_stop", "zkl_imad_peak", "zkl_set_bulk_threshold", "zkl_set_hash_path", "zkl_set_ntt_path", "zkl_set_coop_path", "zkl_bench_permute", "zkl_partition_size", "zkl_lde_dev", "zkl_hash_partitions_dev", "zkl_merge_partition_digests_dev", "zkl_merkle_dev", "zkl_dev_download", "zkl_merge_plan", "zkl_poseidon_levels_dev", "zkl_merge_with_int_pairs", "zkl_replay_children", "zkl_replay_status_name", "zkl_grind", "zkl_hash_two_lanes_host",
 ]

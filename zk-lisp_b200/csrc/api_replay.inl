@@ -128,6 +128,37 @@ struct rp_plan {
 };
 
 #ifndef ZKL_REPLAY_HOST_ONLY   // tests/host_replay.cc compiles the parser and the plan builder above with g++
+// poseidon_hash_two_lanes (poseidon/mod.rs:255-291) under an ARBITRARY suite, on the host: out[i] = lane 0 of the permutation of
+// [left[i], right[i], 0 x 8, dom0, dom1]. The step digest (proof/digest.rs: 6 calls) and the children root (agg/child.rs:853-895:
+// 2k-1 calls) use the PROGRAM's suite, not the commitment hasher's that lives in device constant memory; a handful of calls per
+// proof — the same limb arithmetic as the kernels (f128.cuh compiles for the host), no device round trip, no context.
+extern "C" int zkl_hash_two_lanes_host(const zkl_suite *suite, const zkl_fe *left, const zkl_fe *right, size_t count, zkl_fe *out) {
+  if (!suite || (count && (!left || !right || !out))) return 1;
+  fe mds[12][12], rc[ZKL_ROUNDS][12], dom[2];
+  for (int i = 0; i < 2; i++) dom[i] = fe_from_abi(suite->dom[i]);
+  for (int i = 0; i < 12; i++) for (int j = 0; j < 12; j++) mds[i][j] = fe_from_abi(suite->mds[i][j]);
+  for (int r = 0; r < ZKL_ROUNDS; r++) for (int j = 0; j < 12; j++) rc[r][j] = fe_from_abi(suite->rc[r][j]);
+  for (size_t q = 0; q < count; q++) {
+    fe st[12];
+    st[0] = fe_from_abi(left[q]); st[1] = fe_from_abi(right[q]);
+    for (int i = 2; i < 10; i++) st[i] = fe_zero();
+    st[10] = dom[0]; st[11] = dom[1];
+    for (int r = 0; r < ZKL_ROUNDS; r++) {
+      fe c3[12], y[12];
+      for (int i = 0; i < 12; i++) c3[i] = fe_cube(st[i]);
+      for (int i = 0; i < 12; i++) {
+        wide_acc w; wacc_zero(w);
+        for (int k = 0; k < 12; k++) wacc_mad(w, c3[k], mds[i][k]);
+        y[i] = fe_add(wacc_reduce(w), rc[r][i]);
+      }
+      for (int i = 0; i < 12; i++) st[i] = y[i];
+    }
+    out[q].lo = (uint64_t)st[0].l[0] | ((uint64_t)st[0].l[1] << 32);
+    out[q].hi = (uint64_t)st[0].l[2] | ((uint64_t)st[0].l[3] << 32);
+  }
+  return 0;
+}
+
 // Proof-of-work search on its own (ProverChannel::grind [WF-mem]; check restated at agg/fs.rs:202-207): the smallest nonce >= 1 with
 // trailing_zeros(u64_le(merge_with_int(seed, nonce)[0..8])) >= bits. The aggregation proof of the reference stays on the CPU prover,
 // but its grinding is 2^bits sponge calls on the slow CPU hasher — the one step of that proof worth sending to the device.

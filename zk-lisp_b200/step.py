@@ -11,6 +11,7 @@ The inner Winterfell proof is NOT re-encoded: `InnerProof` is a read-only view o
 returned (layout written in csrc/api_stark.inl, winter-air 0.13 `Proof::to_bytes` [WF-mem]).
 """
 from dataclasses import dataclass, field
+from functools import lru_cache
 from typing import List, Sequence, Tuple
 
 from . import air as A
@@ -39,11 +40,40 @@ def fe_from_bytes_fold(b32: bytes) -> int:
     return int.from_bytes(b32[0:16], "little") % P
 
 
-def poseidon_hash_two_lanes(suite_id: bytes, left: int, right: int) -> int:
-    """poseidon/mod.rs:255-291: one permutation of [left, right, 0 x 8, dom0, dom1] under the suite of `suite_id`."""
+def poseidon_hash_two_lanes_py(suite_id: bytes, left: int, right: int) -> int:
+    """poseidon/mod.rs:255-291 on Python integers: one permutation of [left, right, 0 x 8, dom0, dom1] under the suite of
+    `suite_id` (second implementation, used by the tests to check the native one)."""
     suite = params.get_poseidon_suite(bytes(suite_id))
     state = [left % P, right % P] + [0] * 8 + list(suite.dom)
     return params.permute(suite, state)[0]
+
+
+@lru_cache(maxsize=64)
+def _suite_struct(suite_id: bytes):
+    from . import capi
+    return capi.suite_to_c(params.get_poseidon_suite(suite_id))
+
+
+def hash_two_lanes_batch(suite_id: bytes, pairs: Sequence[Tuple[int, int]]) -> List[int]:
+    """poseidon_hash_two_lanes for a batch of (left, right) in native code (`zkl_hash_two_lanes_host`: the kernels' limb
+    arithmetic compiled for the host; no device involved)."""
+    import ctypes as C
+    from . import capi
+    k = len(pairs)
+    if k == 0:
+        return []
+    lib = capi.load_library()
+    left = (capi.Fe * k)(*[capi.Fe.of(l % P) for l, _ in pairs])
+    right = (capi.Fe * k)(*[capi.Fe.of(r % P) for _, r in pairs])
+    out = (capi.Fe * k)()
+    if lib.zkl_hash_two_lanes_host(C.byref(_suite_struct(bytes(suite_id))), left, right, k, out):
+        raise InvalidInput("zkl_hash_two_lanes_host failed")
+    return [o.int() for o in out]
+
+
+def poseidon_hash_two_lanes(suite_id: bytes, left: int, right: int) -> int:
+    """poseidon/mod.rs:255-291."""
+    return hash_two_lanes_batch(suite_id, [(left, right)])[0]
 
 
 def vm_state_hash(registers: Sequence[int]) -> bytes:
@@ -446,12 +476,12 @@ def children_root(suite_id: bytes, children: Sequence[Tuple[bytes, bytes]]) -> b
     """agg/child.rs:853-895 over (step_digest, root_trace) pairs: sorted leaves, odd nodes paired with themselves."""
     if not children:
         return _Z32
-    items = sorted(fe_to_bytes_fold(poseidon_hash_two_lanes(suite_id, fold_bytes32_to_fe(d), fold_bytes32_to_fe(t)))
-                   for d, t in children)
+    items = sorted(fe_to_bytes_fold(x) for x in hash_two_lanes_batch(suite_id, [(fold_bytes32_to_fe(d), fold_bytes32_to_fe(t))
+                                                                                for d, t in children]))
     layer = [fold_bytes32_to_fe(b) for b in items]
     while len(layer) > 1:
-        layer = [poseidon_hash_two_lanes(suite_id, layer[i], layer[i + 1] if i + 1 < len(layer) else layer[i])
-                 for i in range(0, len(layer), 2)]
+        layer = hash_two_lanes_batch(suite_id, [(layer[i], layer[i + 1] if i + 1 < len(layer) else layer[i])
+                                                for i in range(0, len(layer), 2)])
     return fe_to_bytes_fold(layer[0])
 
 
