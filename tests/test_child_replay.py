@@ -331,3 +331,24 @@ def test_python_verifier_ood_consistency(zkl, oracle, child):
     lhs, rhs, _ = pyverify.ood_check(zkl, oracle, step2, air2)
     assert lhs == rhs
     zkl.replay.verify_child(oracle, step2)
+
+
+def test_host_verifier_accepts_and_rejects(zkl, oracle, child):
+    """verify.verify_step: the whole verification of a step proof from its ZKLSTP1 bytes (the AIR instance is rebuilt from the
+    proof), accepting valid proofs of several shapes and naming the failing check for tampered ones."""
+    V, S = zkl.verify, zkl.step
+    step = S.StepProof.from_bytes(child[0].to_bytes())
+    fs = V.verify_step(oracle, step)
+    assert fs.query_positions == child[1].positions[:child[1].num_unique_queries]
+    V.verify_step(oracle, _step(zkl, oracle, 32, 9, queries=40, parts=(4, 8), grind=0)[0])
+    v = step.proof.inner
+    bump = lambda b, i: b[:16 * i] + ((int.from_bytes(b[16 * i:16 * i + 16], "little") + 1) % zkl.field.P).to_bytes(16, "little") + b[16 * i + 16:]
+    with_inner = lambda **kw: replace(step, proof=replace(step.proof, inner=replace(v, **kw)))
+    for kw, msg in ((dict(ood_trace=bump(v.ood_trace, 45)), "out-of-domain"), (dict(ood_constraints=bump(v.ood_constraints, 0)), "out-of-domain"),
+                    (dict(trace_query_values=bump(v.trace_query_values, 9)), "trace openings"),
+                    (dict(pow_nonce=v.pow_nonce + 1), "grinding factor|unique query|openings"),
+                    (dict(fri_remainder=bump(v.fri_remainder, 0)), "remainder")):
+        with pytest.raises(S.InvalidInput, match=msg):
+            V.verify_step(oracle, with_inner(**kw))
+    with pytest.raises(S.InvalidInput):
+        V.verify_step(oracle, replace(step, vm_usage_mask=step.vm_usage_mask ^ 4))     # another AIR: constraint count / seed differ

@@ -91,6 +91,7 @@ def test_prove_program_host_logic(zkl, oracle):
         assert back.digest() == c.digest() and back.proof.pi == c.proof.pi and back.proof.meta == c.proof.meta
         fs = R.replay_fs_from_step(ctxs[0], back)
         R.verify_child_openings(ctxs[0], back, fs)
+        assert zkl.verify.verify_step(ctxs[0], back) == fs          # the whole host verifier on the ZKLSTP1 bytes of a driver-made step
     ST.verify_chain([s.step for s in steps])
     assert len({s.step.digest() for s in steps}) == len(steps)
     # a failing worker surfaces its error to the caller (prove.rs: Error::Backend)
