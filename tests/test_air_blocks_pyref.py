@@ -75,3 +75,28 @@ def test_assertions_match_python_restatement(zkl, cfg):
     assert a.num_constraints == len(a.degrees) + len(exp)
     per_level = 4 + 27 + 1 + 27 + 1 + 27 + 54
     assert len(exp) >= per_level * (trace.shape[1] // 32)
+
+
+@pytest.mark.parametrize("full_layout", [False, True])
+def test_synthetic_trace_satisfies_python_air(zkl, full_layout):
+    """The AIR-valid synthetic trace (tests/synth.py) under the Python-integer AIR: every transition constraint vanishes on every
+    row but the exempt last one, every assertion holds, and the periodic columns are the 0/1 schedule on the trace domain."""
+    n = 64
+    trace, air_pi, opts = synth.valid_segment(n=n, seed=3, full_layout=full_layout, start_level=0)
+    a = zkl.air.Air(trace.shape[0], n, air_pi, opts)
+    t = [[int(trace[c, r, 0]) | (int(trace[c, r, 1]) << 64) for c in range(trace.shape[0])] for r in range(n)]
+    w0, w1 = zkl.params.rom_weights_for_seed(zkl.params.ROM_W_SEED_0), zkl.params.rom_weights_for_seed(zkl.params.ROM_W_SEED_1)
+    root_fe = zkl.field.be_from_le8(air_pi.core.merkle_root)
+    g = zkl.field.root_of_unity(6)
+    for row in range(n - 1):
+        per = zkl.verify.periodic_at(n, pow(g, row, P))
+        assert set(per) <= {0, 1} and per[0] == int(row % 32 == 0) and per[31] == 0
+        res = pyair.evaluate_transition(a, t[row], t[row + 1], per, w0, w1, root_fe)
+        assert not any(res), (row, [i for i, v in enumerate(res) if v][:5])
+    assert zkl.verify.periodic_at(n, pow(g, n - 1, P))[31] == 1
+    for col, row, val in pyair.assertions(a.cols, n, air_pi, a.fm):
+        assert t[row][col] == val, (col, row)
+    # and a broken trace is noticed: a register changed on a carry row
+    bad = list(t[5])
+    bad[a.cols.r_index(2)] = (bad[a.cols.r_index(2)] + 1) % P
+    assert any(pyair.evaluate_transition(a, t[4], bad, zkl.verify.periodic_at(n, pow(g, 4, P)), w0, w1, root_fe))

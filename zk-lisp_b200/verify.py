@@ -18,11 +18,17 @@ def periodic_at(n: int, x: int) -> List[int]:
     """The 31 cycle-32 periodic columns (vm/air/mod.rs:520-592, vm/schedule.rs:35-80; evaluated at x^(n/32)) and p_last (cycle n)."""
     y = pow(x, n // 32, P)
     w32 = root_of_unity(5)
-    num = (pow(y, 32, P) - 1) * inv(32) % P
-    L = [num * pow(w32, p, P) % P * inv((y - pow(w32, p, P)) % P) % P for p in range(32)]
+    if pow(y, 32, P) == 1:                  # x on the trace domain: the Lagrange basis degenerates to the 0/1 schedule itself
+        L = [int(y == pow(w32, p, P)) for p in range(32)]
+    else:
+        num = (pow(y, 32, P) - 1) * inv(32) % P
+        L = [num * pow(w32, p, P) % P * inv((y - pow(w32, p, P)) % P) % P for p in range(32)]
     cols = [L[0]] + [L[1 + j] for j in range(27)] + [L[28], (L[29] + L[30] + L[31]) % P, L[31]]
     last = pow(root_of_unity(n.bit_length() - 1), n - 1, P)
-    cols.append(last * inv(n) % P * (pow(x, n, P) - 1) % P * inv((x - last) % P) % P)
+    if pow(x, n, P) == 1:
+        cols.append(int(x == last))
+    else:
+        cols.append(last * inv(n) % P * (pow(x, n, P) - 1) % P * inv((x - last) % P) % P)
     return cols
 
 
