@@ -100,3 +100,38 @@ def test_synthetic_trace_satisfies_python_air(zkl, full_layout):
     bad = list(t[5])
     bad[a.cols.r_index(2)] = (bad[a.cols.r_index(2)] + 1) % P
     assert any(pyair.evaluate_transition(a, t[4], bad, zkl.verify.periodic_at(n, pow(g, 4, P)), w0, w1, root_fe))
+
+
+def test_preflight_mode_of_the_prover_mirror(zkl, capsys):
+    """prove.rs:186-211 / preflight.rs: a valid trace passes, a broken one aborts with the reference's message, the row, the
+    constraint index and the block it belongs to; off by default."""
+    PF = zkl.preflight
+    n = 64
+    trace, air_pi, opts = synth.valid_segment(n=n, seed=3)
+    a = zkl.air.Air(trace.shape[0], n, air_pi, opts)
+    assert PF.run(PF.OFF, a, trace) is None and PF.run(PF.CONSOLE, a, trace) is None
+    assert "preflight: OK (rows=64" in capsys.readouterr().out
+    bad = trace.copy()
+    bad[a.cols.r_index(2), 37, 0] ^= 1                      # register r2 changes between two carry rows of level 1
+    with pytest.raises(PF.PreflightError, match=r"preflight: constraint \d+ non-zero at row 36") as e:
+        PF.run(PF.JSON, a, bad)
+    rep = e.value.report
+    assert rep.row == 36 and rep.pos == 4 and rep.block == "vm-alu" and not rep.gates_map and rep.rounds[3]
+    assert '"row": 36' in capsys.readouterr().out
+    lanes = trace.copy()
+    lanes[a.cols.lane_index(5), 32 + 7, 0] ^= 1             # a Poseidon lane inside the active level 1 (round rows 33..59)
+    with pytest.raises(PF.PreflightError) as e:
+        PF.run(PF.CONSOLE, a, lanes)
+    assert e.value.report.block == "poseidon" and e.value.report.row == 32 + 6 and e.value.report.lanes_exp is not None
+    assert "FAILED row 38" in capsys.readouterr().out
+    # the prover mirror: off by default, rejects unknown modes, refuses device-resident traces in preflight mode
+    class NoCtx:
+        pass
+    pv = zkl.ZkProver(NoCtx(), opts, air_pi)
+    assert pv.preflight == "off" and pv.with_preflight_mode("json") is pv
+    with pytest.raises(ValueError):
+        pv.with_preflight_mode("verbose")
+    with pytest.raises(PF.PreflightError):
+        pv.prove(bad)                                        # aborts before any device call (NoCtx has none)
+    with pytest.raises(ValueError, match="host trace"):
+        pv.prove(None, dev_ptr=1, shape=(trace.shape[0], n))

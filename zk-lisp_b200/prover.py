@@ -242,6 +242,14 @@ class ZkProver:
         self.ctx, self.options, self.air_pi = ctx, options, air_pi
         self.last_summary = None
         self._cache = {}
+        self.preflight = "off"
+
+    def with_preflight_mode(self, mode: str) -> "ZkProver":
+        """prove.rs:160-163: "off" | "console" | "json" (zk-lisp-proof/src/frontend.rs:23-27)."""
+        if mode not in ("off", "console", "json"):
+            raise ValueError("preflight mode must be off, console or json")
+        self.preflight = mode
+        return self
 
     def _air(self, width, n):
         """(Air, zkl_air_params, seed elements) for this trace shape; built once per prover like `Air::new`."""
@@ -293,6 +301,11 @@ class ZkProver:
         else:
             width, n = shape
         a, ap, seed = self._air(width, n)
+        if self.preflight != "off":                  # prove.rs:186-211: check the trace against the AIR first
+            if dev_ptr is not None:
+                raise ValueError("preflight walks the host trace: pass the trace array, not a device pointer")
+            from . import preflight
+            preflight.run(self.preflight, a, t)
         o = self.options.to_c()
         cap = C.c_size_t(4 << 20)
         buf = np.zeros(cap.value, dtype=np.uint8)
