@@ -3,16 +3,24 @@
 
 A "step" is one pass of the hot path over one batch: the 16 execution segments of rollup-bench
 (n = 4096 trace rows, W = 204 columns, blowup 16, 64 queries, grinding 16; README.md:186-194 of the
-reference) are proven, i.e. 65 536 trace rows per step per GPU. Segments are independent
-(prove.rs:1020-1048), so with N GPUs every rank proves its own 16 segments (weak scaling, no collective
-on the data path). The synthetic traces satisfy the zk-lisp VM AIR (tests/synth.py), so every proof is
-a real, verifiable proof.
+reference) are proven, i.e. 65 536 trace rows per step per GPU. The 16 segments belong to ONE
+program (one program id / commitment, consecutive pc ranges), like the reference run. Segments are independent
+(prove.rs:1020-1048), so with N GPUs every rank proves its own 16 segments (weak scaling, no collective on
+the data path); the strong-scaling figure (ONE 16-segment job split over the N GPUs = BASELINE's "prove wall-time
+at 1/2/4/8") is measured in the same run and reported under `prove_wall_ms`. The synthetic traces satisfy the
+zk-lisp VM AIR (tests/synth.py), so every proof is a real, verifiable proof.
 
-  value : trace rows / s, traces already resident in HBM when the timed region starts
-  e2e   : same through the C-ABI call with HOST buffers (pinned), H2D of the trace and D2H of the proof
-          bytes inside the timed region
+  value    : trace rows / s, traces already resident in HBM when the timed region starts
+  e2e      : same through the C-ABI call with HOST buffers (pinned), H2D of the trace and D2H of the proof
+             bytes inside the timed region. The per-segment AIR instance (assertions, degrees, coin seed) is built
+             inside every call from the public inputs (zkl_prove_segment_pi); nothing about a segment is cached.
+  e2e_cold : same, and additionally every prover object is new and the per-program constants (blake3-derived
+             suites, Cauchy MDS) are re-derived for every segment: a first-ever prove through the public API.
 Timing: CUDA events on the proving streams (max over streams, then max over ranks), barrier +
 synchronize on both sides; wall clock is reported beside it as a cross-check.
+
+--impl reference: the CPU restatement of the same pipeline (oracle/, the reference itself is Rust and cannot be built
+here) at the SAME configuration — n = 4096, grind 16, one thread per segment, min(16, cores) in flight.
 """
 import argparse
 import ctypes as C
@@ -31,8 +39,9 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np  # noqa: E402
 
 SEGMENTS, ROWS, QUERIES, BLOWUP, GRIND = 16, 4096, 64, 16, 16
+PROGRAM_SEED = 0x5A4B4C
 METRIC, UNIT = "rollup-bench prove throughput (trace rows/s)", "trace rows/s"
-WORKLOAD = "rollup-bench: 16 segments x (n=4096, W=204, blowup=16, q=64, grind=16), synthetic AIR-valid traces"
+WORKLOAD = "rollup-bench: 16 segments x (n=4096, W=204, blowup=16, q=64, grind=16) of one program, synthetic AIR-valid traces"
 # algorithmic work of the dominant kernel (trace row hashing, k_tc_hash_rows), SURVEY.md §8(d):
 # W=204 -> 1 + 102 absorbs -> 11 permutations per LDE row; one permutation = 27 rounds; per round the 12x12 MDS
 # product over f128 runs on the tensor cores as a u8 x u8 -> s32 GEMM tile: 192 output byte-rows x 384 cube bytes
@@ -40,12 +49,14 @@ WORKLOAD = "rollup-bench: 16 segments x (n=4096, W=204, blowup=16, q=64, grind=1
 PERMS_PER_ROW = 11
 TENSOR_OPS_PER_PERM = 27 * 2 * 192 * 384
 FIELD_PRODUCTS_PER_PERM = 27 * (24 + 144)
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture under profiles/
-# (r01 prof_tc_hash_rows: 214.3 MB + 5.7 MB; algorithmic 16*204*65536 = 213.9 MB read + 1 MB written)
-TRAFFIC_HASH_ROWS_BYTES = 220.0e6
-# r01b prof_tc_lde4096_v2: 15.8 MB read (the 13.4 MB coefficient matrix is re-read from L2 by the 16 cosets) + 156.0 MB written inside
-# the kernel's window (the rest of the 213.9 MB output is still in the 126 MB L2 when the kernel ends); algorithmic 227.3 MB
-TRAFFIC_LDE_BYTES = 171.8e6
+WIDE_MACS_PER_FIELD_PRODUCT = 16      # 4x4 32-bit limb products of one 128x128-bit multiplication (reduction not counted)
+# dram__bytes_read.sum + dram__bytes_write.sum per launch, read from the ncu --set full captures committed under profiles/
+# (not measured in this run: ncu replays kernels, a bench run under it is not a bench run)
+TRAFFIC = {
+    "k_tc_hash_rows": (220.0e6, "profiles/prof_tc_hash_rows_r01_details.txt: 214.3 MB read + 5.7 MB written; algorithmic 16*204*65536 = 213.9 MB read + 1 MB written"),
+    "k_tc_lde4096_v2": (171.8e6, "profiles/prof_tc_lde4096_v2_r01b_details.txt: 15.8 MB read + 156.0 MB written inside the kernel's window (the rest of the "
+                                 "213.9 MB output is still in the 126 MB L2 when the kernel ends); algorithmic 227.3 MB"),
+}
 
 
 def parse_args():
@@ -59,6 +70,7 @@ def parse_args():
                     help="weak: 16 segments per GPU per step; strong: the 16 segments of one rollup-bench split over the GPUs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--bulk-threshold", type=int, default=0)
+    ap.add_argument("--reference-sample", action="store_true", help="--impl reference on the bounded n=512 / grind 13 sample instead of the full configuration")
     return ap.parse_args()
 
 
@@ -67,6 +79,18 @@ def dist_env():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     return rank, world, local
+
+
+def pin_rank_to_cores(local, world):
+    """Each rank keeps to its own share of the host cores: the proving threads of 8 ranks otherwise migrate over all cores."""
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+        per = len(cores) // world
+        if world > 1 and per >= 1:
+            os.sched_setaffinity(0, cores[local * per:(local + 1) * per])
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
 
 
 class ClockSampler:
@@ -108,14 +132,11 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def make_workload(zkl, count, rows, grind=GRIND, seed0=0x5A4B4C):
+def make_segment(i, rows=ROWS, grind=GRIND):
+    """Segment i of the synthetic rollup-bench program: its own data, the program's id, pc range [i * levels, (i + 1) * levels)."""
     import synth
-    segs = []
-    for i in range(count):
-        trace, air_pi, opts = synth.valid_segment(n=rows, queries=QUERIES, blowup=BLOWUP, grind=grind, seed=seed0 + i,
-                                                  start_level=(i * (rows // 32)))
-        segs.append((trace, air_pi, opts))
-    return segs
+    return synth.valid_segment(n=rows, queries=QUERIES, blowup=BLOWUP, grind=grind, seed=PROGRAM_SEED + i, start_level=(i % SEGMENTS) * (rows // 32),
+                               program_seed=PROGRAM_SEED)
 
 
 def cpu_reference_run(zkl, threads, rows, grind):
@@ -123,42 +144,40 @@ def cpu_reference_run(zkl, threads, rows, grind):
     flight — the shape of the reference's rayon pool over segments (prove.rs:1020-1048)."""
     import oracle_lib
     oracle_lib.build()
-    segs = make_workload(zkl, threads, rows, grind=grind)
-    a = zkl.air.Air(segs[0][0].shape[0], rows, segs[0][1], segs[0][2])
-    # all segments share the AIR shape; each has its own public inputs -> run them as separate calls in threads
-    times = []
+    segs = [make_segment(i, rows, grind) for i in range(threads)]
+    airs = [zkl.air.Air(t.shape[0], rows, pi, o) for t, pi, o in segs]
+    inputs = [(a.to_c(), zkl.prover.ints_to_fe(a.seed_elements())) for a in airs]
 
     def work(i):
-        trace, air_pi, opts = segs[i]
-        ai = zkl.air.Air(trace.shape[0], rows, air_pi, opts)
-        oracle_lib.prove_segment(trace, ai.to_c(), zkl.prover.ints_to_fe(ai.seed_elements()), opts.to_c())
+        trace, _, opts = segs[i]
+        oracle_lib.prove_segment(trace, inputs[i][0], inputs[i][1], opts.to_c())
 
     t0 = time.time()
     th = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
     [t.start() for t in th]
     [t.join() for t in th]
     dt = time.time() - t0
-    del a, times
     return threads * rows / dt, dt
 
 
 def run_reference(args, zkl, rank, world):
+    """bench.py --impl reference: the CPU port at the b200 arm's configuration. One step = min(16, cores) segments of
+    n = 4096 / grind 16 in flight, one thread each (the reference's Winterfell is single-threaded per segment, SURVEY.md §0.3);
+    a step is minutes of CPU time, so ONE step is timed whatever --steps says."""
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    threads = min(cores, 256)
-    rows, grind = 512, 13
-    vals = []
-    for _ in range(max(1, min(args.steps, 2))):
-        v, dt = cpu_reference_run(zkl, threads, rows, grind)
-        vals.append((v, dt))
-    v = float(np.mean([x[0] for x in vals]))
-    sample = (f"{threads} segments in flight (one thread each), n={rows} rows, W=204, blowup=16, q=64, grind={grind} "
-              f"(grinding work per row kept proportional to the n=4096/grind=16 workload); CPU port of the reference pipeline")
+    full = not args.reference_sample
+    rows, grind = (ROWS, GRIND) if full else (512, 13)
+    threads = min(cores, SEGMENTS) if full else min(cores, 256)
+    v, dt = cpu_reference_run(zkl, threads, rows, grind)
+    sample = (f"{threads} of the step's {SEGMENTS} segments in flight (one thread each), n={rows}, W=204, blowup=16, q=64, grind={grind}: "
+              + ("the b200 arm's configuration" if full else "bounded sample, grinding work per row kept proportional") + f"; {dt:.1f} s of wall time; "
+              "CPU port of the reference pipeline (oracle/; the Rust reference cannot be built in this image)")
     line = {
-        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals), "warmup": 0,
-        "ms_per_step": float(np.mean([x[1] for x in vals])) * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "u128 (f128 field)", "data": "synthetic", "config": {"workload": WORKLOAD, "reference_sample": sample},
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": 1, "warmup": 0,
+        "ms_per_step": dt * 1e3 * (SEGMENTS / threads), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u128 (f128 field)", "data": "synthetic", "config": {"workload": WORKLOAD, "reference_sample": sample, "same_config": bool(full)},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -181,31 +200,37 @@ class Worker:
             self.ctx._check(self.ctx.lib.zkl_dev_upload(self.ctx.h, dev, trace.ctypes.data, trace.nbytes))
             self.items.append((prover, trace, dev))
         self.ms, self.summaries, self.proof_bytes, self.digests = 0.0, [], 0, []
+        self.active = len(self.items)
 
-    def run(self, resident: bool):
+    def run(self, mode: str):
+        """mode: "resident" (trace in HBM), "host" (host buffers through the C ABI), "cold" (host buffers, new prover objects and
+        re-derived program constants for every segment)."""
         ms = C.c_float()
         self.summaries, self.proof_bytes = [], 0
         proofs = []
         self.ctx._check(self.ctx.lib.zkl_timer_start(self.ctx.h))
-        for prover, trace, dev in self.items:
-            proof = prover.prove(None, dev_ptr=dev, shape=trace.shape[:2]) if resident else prover.prove(trace)
+        for prover, trace, dev in self.items[:self.active]:
+            if mode == "cold":
+                prover = self.zkl.ZkProver(self.ctx, prover.options, prover.air_pi, cache_program=False)
+            proof = prover.prove(None, dev_ptr=dev, shape=trace.shape[:2]) if mode == "resident" else prover.prove(trace)
             self.proof_bytes += len(proof)
             self.summaries.append(prover.last_summary)
             proofs.append(proof)
         self.ctx._check(self.ctx.lib.zkl_timer_stop(self.ctx.h, C.byref(ms)))
         self.ms = ms.value
-        # outside the timed region: the same segment must give the same bytes in every step and through both entry points
+        # outside the timed region: the same segment must give the same bytes in every step and through every entry point
         # (8 streams share the GPU: a racy kernel shows up here as proofs that differ from run to run)
         self.digests = [hashlib.blake2b(p, digest_size=16).hexdigest() for p in proofs]
 
 
-def run_step(workers, resident):
-    th = [threading.Thread(target=w.run, args=(resident,)) for w in workers]
+def run_step(workers, mode):
+    live = [w for w in workers if w.active]
+    th = [threading.Thread(target=w.run, args=(mode,)) for w in live]
     t0 = time.time()
     [t.start() for t in th]
     [t.join() for t in th]
     wall = (time.time() - t0) * 1e3
-    return max(w.ms for w in workers), wall
+    return max(w.ms for w in live), wall
 
 
 def main():
@@ -216,6 +241,7 @@ def main():
     if args.impl == "reference":
         run_reference(args, zkl, rank, world)
         return
+    host_cores = pin_rank_to_cores(local, world)
     import torch
     import torch.distributed as dist
     if world > 1:
@@ -229,9 +255,7 @@ def main():
         my_ids = zkl.sharding.weak_scaling_segments(SEGMENTS, rank)
     else:
         my_ids = zkl.sharding.segments_for_rank(SEGMENTS, rank, world)
-    import synth
-    segs = [synth.valid_segment(n=ROWS, queries=QUERIES, blowup=BLOWUP, grind=GRIND, seed=0x5A4B4C + i, start_level=(i % 16) * (ROWS // 32))
-            for i in my_ids]
+    segs = [make_segment(i) for i in my_ids]
     S = max(1, min(args.streams, len(segs)))
     workers = [Worker(zkl, device, segs[i::S], args.bulk_threshold) for i in range(S)]
     # pinned host buffers for the e2e leg
@@ -245,7 +269,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(resident, steps, sampler=None):
+    def timed(mode, steps, sampler=None, check=True):
         barrier()
         if sampler:
             sampler.start()
@@ -253,9 +277,9 @@ def main():
         launches0 = sum(w.ctx.launches for w in workers)
         nonlocal deterministic
         for _ in range(steps):
-            e, wl = run_step(workers, resident)
+            e, wl = run_step(workers, mode)
             ev_ms.append(e); wall_ms.append(wl)
-            if reference_digests and reference_digests[0]:
+            if check and reference_digests and reference_digests[0]:
                 deterministic = deterministic and [list(w.digests) for w in workers] == reference_digests
         barrier()
         clocks = sampler.stop() if sampler else None
@@ -267,19 +291,21 @@ def main():
         return tot_ev, tot_wall, sum(w.ctx.launches for w in workers) - launches0, clocks
 
     for _ in range(args.warmup):
-        run_step(workers, True)
+        run_step(workers, "resident")
     reference_digests = [list(w.digests) for w in workers]   # from the last warm-up step
     deterministic = True
     sampler = ClockSampler(device)
-    ev_total, wall_total, launches, clocks = timed(True, args.steps, sampler)
+    ev_total, wall_total, launches, clocks = timed("resident", args.steps, sampler)
     stage = np.zeros(12)
     cnt = 0
     for w in workers:
         for s in w.summaries:
             stage += np.array(list(s.stage_ms)); cnt += 1
     stage /= max(cnt, 1)
-    run_step(workers, False)  # warm the host-buffer path
-    e2e_ev, e2e_wall, _, _ = timed(False, args.steps)
+    run_step(workers, "host")  # warm the host-buffer path
+    e2e_ev, e2e_wall, _, _ = timed("host", args.steps)
+    cold_steps = max(1, min(args.steps, 3))
+    cold_ev, cold_wall, _, _ = timed("cold", cold_steps)
     h2d = sum(t.nbytes for w in workers for _, t, _ in w.items)
     d2h = sum(w.proof_bytes for w in workers)
 
@@ -287,12 +313,40 @@ def main():
     rows_total, _ = zkl.sharding.aggregate(rows_local, 0.0, dist if world > 1 else None, "cuda")
     value = rows_total / (ev_total * 1e-3)
     e2e_value = rows_total / (e2e_ev * 1e-3)
+    cold_value = rows_total / args.steps * cold_steps / (cold_ev * 1e-3)
+
+    # strong scaling: ONE 16-segment rollup-bench job split over the ranks (rank r proves segments r, r + world, ...), host buffers.
+    # Fewer than 4 busy streams per GPU: the lowest-latency small-sponge kernels (a pool takes the 16-thread groups).
+    strong_ms = None
+    if args.scaling == "weak":
+        share = len(zkl.sharding.segments_for_rank(SEGMENTS, rank, world))
+        per = [share // S + (1 if i < share % S else 0) for i in range(S)]
+        busy = sum(1 for p in per if p)
+        for w, p in zip(workers, per):
+            w.active = p
+            w.ctx._check(w.ctx.lib.zkl_set_coop_path(w.ctx.h, 2 if busy < 4 else 0))
+        run_step(workers, "host")
+        s_ev, s_wall, _, _ = timed("host", max(3, min(args.steps, 10)), check=False)
+        strong_ms = {"events": s_ev / max(3, min(args.steps, 10)), "wall": s_wall / max(3, min(args.steps, 10)), "segments_per_gpu": share}
+        for w in workers:
+            w.active = len(w.items)
+            w.ctx._check(w.ctx.lib.zkl_set_coop_path(w.ctx.h, 0))
+
     # stream-exclusive pass (nothing else on the GPU) for the per-kernel roofline numbers
     barrier()
-    workers[0].items = workers[0].items[:1]
+    for w in workers:
+        w.active = 0
+    workers[0].active = 1
     workers[0].ctx._check(workers[0].ctx.lib.zkl_set_coop_path(workers[0].ctx.h, 2))  # a lone prover: lowest-latency small-sponge kernels
-    workers[0].run(True)
+    workers[0].run("resident")
     excl = np.array(list(workers[0].summaries[0].stage_ms))
+    lone_wall = []
+    for _ in range(3):
+        t0 = time.time(); workers[0].run("host"); lone_wall.append((time.time() - t0) * 1e3)
+    # measured peaks of the two pipes the sponge kernels run on (this GPU, this run)
+    i8 = C.c_double(); imad = C.c_double()
+    workers[0].ctx._check(workers[0].ctx.lib.zkl_tc_i8_peak(workers[0].ctx.h, C.byref(i8)))
+    workers[0].ctx._check(workers[0].ctx.lib.zkl_imad_peak(workers[0].ctx.h, C.byref(imad)))
     barrier()
 
     if rank == 0:
@@ -307,52 +361,68 @@ def main():
         perms = N * PERMS_PER_ROW
         lde_bytes = 16 * 204 * ROWS * (1 + BLOWUP)
         tensor_ops = perms * TENSOR_OPS_PER_PERM
-        # int8 dense tensor peak = 2 x the bf16 dense peak on B200 (4.5 vs 2.25 PFLOP/s nominal); the bf16 figure is measured
-        bf16_peak = peaks.get("bf16_tflops")
-        int8_peak, int8_src = (2.0 * bf16_peak, "2 x measured cuBLAS bf16 burst (MEASURED_PEAKS.json); int8 dense = 2 x bf16 on sm_100") if bf16_peak \
-            else (2.0 * 1590.0, "2 x fallback bf16 (B200_PROFILING.md)")
+        int8_peak = i8.value / 1e12
+        products_per_s = perms * FIELD_PRODUCTS_PER_PERM / (hash_ms * 1e-3)
         roofline = {
             "kernel": "k_tc_hash_rows (trace row hashing: 11 sponge permutations per LDE row, MDS product on tcgen05 kind::i8)",
             "bound": "tensor",
             "achieved": tensor_ops / (hash_ms * 1e-3) / 1e12, "peak": int8_peak, "unit": "TOP/s (int8 dense)",
-            "frac": tensor_ops / (hash_ms * 1e-3) / 1e12 / int8_peak, "peak_source": int8_src,
-            "traffic": TRAFFIC_HASH_ROWS_BYTES, "ms_per_launch": hash_ms, "ms_per_launch_in_timed_region": float(stage[10]),
+            "frac": tensor_ops / (hash_ms * 1e-3) / 1e12 / int8_peak,
+            "peak_source": "measured in this run: zkl_tc_i8_peak, a saturating tcgen05.mma kind::i8 loop (M128 N256 K32 from shared memory, one CTA per SM)",
+            "peak_cublas_bf16_x2": 2.0 * peaks["bf16_tflops"] if peaks.get("bf16_tflops") else None,
+            "traffic": TRAFFIC["k_tc_hash_rows"][0], "traffic_source": TRAFFIC["k_tc_hash_rows"][1],
+            "ms_per_launch": hash_ms, "ms_per_launch_in_timed_region": float(stage[10]),
             "permutations_per_s": perms / (hash_ms * 1e-3),
-            "field_products_per_s": perms * FIELD_PRODUCTS_PER_PERM / (hash_ms * 1e-3),
-            "co_bound": "integer issue: the S-box cubes and the accumulator carry propagation stay on the CUDA cores; ncu (profiles/) shows "
-                        "issue slots 49-52 % busy, at the 0.5 warp-instruction/clk/scheduler rate of half-rate 32-bit integer ops, tensor pipe 24-28 % active",
+            "field_products_per_s": products_per_s,
+            "integer_pipe": {
+                "imad_wide_peak_macs_per_s": imad.value,
+                "peak_source": "measured in this run: zkl_imad_peak, dependency-free IMAD.WIDE.U32 chains on every SM",
+                "field_products_per_s_if_all_on_imad_pipe": imad.value / WIDE_MACS_PER_FIELD_PRODUCT,
+                "achieved_over_imad_only_bound": products_per_s / (imad.value / WIDE_MACS_PER_FIELD_PRODUCT),
+                "note": "144 of the 168 field products of a round run on the tensor cores; a ratio above 1 is that win: more field "
+                        "products per second than the wide-multiply pipe alone could deliver (reductions not even counted)",
+            },
+            "co_bound": "the S-box cubes (IMAD.WIDE.U32, 5.2 clk per warp instruction) and the accumulator carry propagation stay on the CUDA cores",
             "timing": "ms_per_launch is taken on an otherwise idle GPU right after the timed region; inside it the kernel shares the SMs with the other streams",
         }
         roofline_lde = {
             "kernel": "k_tc_lde4096_v2 (trace coset LDE, 204 columns x 16 cosets of 4096 rows: three radix-16 stages as u8 GEMM tiles on tcgen05, "
                       "coset shift folded into per-coset byte matrices, columns fetched by TMA bulk copies; one pass over HBM)",
             "bound": "hbm", "achieved": lde_bytes / (lde_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-            "frac": lde_bytes / (lde_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src, "traffic": TRAFFIC_LDE_BYTES, "ms_per_launch": lde_ms,
-            "note": "f128: per 16-byte element written the CUDA cores still run 3 accumulator carry propagations and 2 modular products "
-                    "(~400 integer instructions), so the kernel is integer-issue-bound far below the HBM roof; the radix-2 integer-pipe kernel it replaced ran at 0.735 ms",
+            "frac": lde_bytes / (lde_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src,
+            "traffic": TRAFFIC["k_tc_lde4096_v2"][0], "traffic_source": TRAFFIC["k_tc_lde4096_v2"][1], "ms_per_launch": lde_ms,
         }
         cpu = None
         if not args.no_cpu_baseline and world == 1:
             cores = min(os.cpu_count() or 1, 256)
             v, dt = cpu_reference_run(zkl, cores, 512, 13)
             cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": f"{cores} segments in flight, n=512, W=204, blowup=16, q=64, grind=13 ({dt:.1f} s of wall time)"}
+                   "sample": f"bounded sample: {cores} segments in flight, n=512, W=204, blowup=16, q=64, grind=13 ({dt:.1f} s of wall time); "
+                             "the full configuration (n=4096, grind 16) is what `--impl reference` times"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ev_total / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "u128 (f128 field, 4x u32 limbs)", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "segments_per_gpu_per_step": len(segs), "streams_per_gpu": S,
+            "config": {"workload": WORKLOAD, "segments_per_gpu_per_step": len(segs), "streams_per_gpu": S, "host_cores_per_rank": host_cores,
                        "l2": "per-step working set 16 x 250 MB LDE matrices >> 126 MB L2 (no flush needed)",
                        "published_reference": "109.567 s on Apple M3 Max for the same 65536 rows (BASELINE.md), different hardware"},
             "wall_ms_per_step": wall_total / args.steps,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ev / args.steps, "wall_ms_per_step": e2e_wall / args.steps},
+                    "ms_per_step": e2e_ev / args.steps, "wall_ms_per_step": e2e_wall / args.steps,
+                    "per_segment_air_build": "inside every call (zkl_prove_segment_pi): assertions, degrees and coin seed from the public inputs; no per-segment cache",
+                    "host_air_build_ms_per_segment": float(stage[11])},
+            "e2e_cold": {"value": cold_value, "unit": UNIT, "ms_per_step": cold_ev / cold_steps, "wall_ms_per_step": cold_wall / cold_steps, "steps": cold_steps,
+                         "what": "host buffers, a new prover object per segment, per-program constants re-derived for every segment (zkl_program_derive), "
+                                 "AIR instance built inside the call"},
             "gpu_launches": int(launches),
             "proofs_identical_across_steps_and_entry_points": bool(deterministic),
-            "prove_wall_ms": {"step_of_16_segments": ev_total / args.steps, "one_segment_alone_on_the_gpu": float(np.sum(excl[:9]))},
+            "prove_wall_ms": {"step_of_16_segments": ev_total / args.steps, "one_segment_alone_on_the_gpu": float(np.sum(excl[:9])),
+                              "one_segment_alone_host_wall": float(np.min(lone_wall)),
+                              "rollup_bench_over_N_gpus": strong_ms,
+                              "rollup_bench_over_N_gpus_what": "ONE job of 16 segments split over the N GPUs (strong scaling), host buffers, max over ranks"},
             "clocks": clocks,
             "roofline": roofline, "roofline_lde": roofline_lde,
-            "stage_ms_per_segment": {zkl.capi.load_library().zkl_stage_name(i).decode(): float(stage[i]) for i in range(11)},
+            "stage_ms_per_segment": {zkl.capi.load_library().zkl_stage_name(i).decode(): float(stage[i]) for i in range(12)},
             "cpu_baseline": cpu,
         }
         print(json.dumps(line))

@@ -114,8 +114,11 @@ typedef struct zkl_constraint_commitment zkl_constraint_commitment; /* DefaultCo
 int zkl_ctx_create(int device, zkl_ctx **out);
 void zkl_ctx_destroy(zkl_ctx *ctx);
 const char *zkl_last_error(const zkl_ctx *ctx); /* ctx may be NULL: last create error */
-/* Commitment/coin hasher constants: suite_id = [0;32] (poseidon/hasher.rs:23). The host
- * computes them exactly as poseidon/mod.rs does and hands them over. */
+/* Commitment/coin hasher constants: suite_id = [0;32] (poseidon/hasher.rs:23). The host computes them exactly as
+ * poseidon/mod.rs does (or calls zkl_suite_derive) and hands them over. The suite is PER DEVICE, shared by every context
+ * on it (the reference has one process-wide hasher suite too): loading the same constants again is a no-op, loading
+ * different ones while another context on the device holds a suite fails. zkl_ctx_create refuses to run when the
+ * reference's ZKL_POSEIDON_HASHER_ROUNDS (hasher.rs:235-241) selects anything but the 27 rounds implemented here. */
 int zkl_suite_load(zkl_ctx *ctx, const zkl_suite *suite);
 /* number of kernels launched on this ctx since creation (bench.py's gpu_launches) */
 uint64_t zkl_launch_count(const zkl_ctx *ctx);
@@ -215,8 +218,8 @@ typedef struct {
   uint32_t num_unique_queries;
   uint32_t positions[256];
   float stage_ms[12];           /* [0..8] device ms per stage, [9] trace k_lde ms, [10] trace k_hash_rows ms,
-                                   [11] -1 if the composition polynomial overflowed its degree (invalid trace);
-                                   see zkl_stage_name */
+                                   [11] host ms spent building the AIR parameters (zkl_prove_segment_pi*); see zkl_stage_name */
+  uint32_t constraints_violated; /* 1 = the trace does not satisfy the AIR (call returned ZKL_ERR_CONSTRAINTS_VIOLATED) */
 } zkl_proof_summary;
 int zkl_prove_segment(zkl_ctx *ctx, const zkl_fe *trace, size_t width, size_t n,
                       const zkl_air_params *air, const zkl_fe *seed_elems, size_t num_seed,
@@ -228,6 +231,65 @@ int zkl_prove_segment_dev(zkl_ctx *ctx, const void *trace_dev, size_t width, siz
                           const zkl_options *opts, uint8_t *out_proof, size_t *out_len,
                           zkl_proof_summary *summary);
 const char *zkl_stage_name(int stage);
+/* zkl_prove_segment* return codes beyond 0 / 1: the proof buffer was too small (*out_len holds the size needed) and the trace
+ * does not satisfy the AIR (the composition polynomial overflowed its degree: Winterfell panics on this in debug builds and
+ * emits an unverifiable proof in release builds; here the bytes are still written, summary->constraints_violated is set and
+ * the call fails so that no caller ships such a proof by accident). */
+#define ZKL_ERR_BUFFER_TOO_SMALL 2
+#define ZKL_ERR_CONSTRAINTS_VIOLATED 3
+
+/* ---- ZkLispAir::new on this side of the boundary (vm/air/mod.rs:114-318, 380-504; lib.rs:116-160) ------------------
+ * The per-segment AIR data is formulaic: 141 schedule assertions per 32-row level (vm/air/schedule.rs:57-139), at most 16
+ * that depend on the public inputs (vm/air/mod.rs:388-446, rom.rs:122-147), the constraint degrees of the enabled modules
+ * and the public-coin seed Context::to_elements() ++ AirPublicInputs::to_elements(). The library derives all of it from the
+ * public inputs, so a caller hands over what `prove_segment` (prove.rs:1057-1175) has at hand and nothing else. */
+/* Per-program constants (one derivation per program, shared by all of its segments; the reference keeps them in a
+ * process-global cache, poseidon/mod.rs:47). zkl_program_derive computes them exactly as poseidon/mod.rs:52-251,
+ * utils.rs:114-141 and commit.rs:31-79 do (blake3-derived round constants, Cauchy MDS); host only, needs no context. */
+typedef struct {
+  uint8_t program_id[32];
+  uint8_t program_commitment[32];
+  zkl_suite pose;                        /* get_poseidon_suite(program_id) */
+  zkl_rom_suite rom;                     /* derive_rom_mds_cauchy_3x3 / derive_rom_round_constants_3 (program_id) */
+  zkl_fe rom_w_enc0[59], rom_w_enc1[59]; /* rom_weights_for_seed(ROM_W_SEED_0 / _1) */
+  zkl_fe program_fe[2];                  /* program_field_commitment(program_id), zero when program_id is zero */
+  zkl_fe commitment_fe[2];               /* program_field_commitment(program_commitment), zero when it is zero */
+} zkl_program;
+int zkl_program_derive(const uint8_t program_id[32], const uint8_t program_commitment[32], zkl_program *out);
+/* get_poseidon_suite(suite_id) alone (poseidon/mod.rs:52-75); suite_id = [0;32] gives the commitment hasher's suite
+ * (poseidon/hasher.rs:23) for zkl_suite_load. */
+int zkl_suite_derive(const uint8_t suite_id[32], zkl_suite *out);
+
+#define ZKL_MAX_MAIN_SLOTS 16
+/* AirPublicInputs (lib.rs:74-96) + the CorePublicInputs fields the AIR reads (zk-lisp-proof/src/pi.rs) */
+typedef struct {
+  uint64_t feature_mask;           /* core.feature_mask */
+  uint64_t segment_feature_mask;   /* 0 = use core.feature_mask (vm/air/mod.rs:119-124) */
+  uint8_t merkle_root[32];
+  uint8_t vm_expected_bytes[32];
+  uint32_t vm_out_reg, vm_out_row;
+  uint32_t num_main_slots;         /* utils::encode_main_args_to_slots(core.main_args) (utils.rs:79-109) */
+  uint32_t vm_usage_mask, ram_delta_clk_bits, pad_;
+  zkl_fe main_slots[ZKL_MAX_MAIN_SLOTS];
+  zkl_fe pc_init;
+  zkl_fe ram_gp_unsorted_in, ram_gp_unsorted_out, ram_gp_sorted_in, ram_gp_sorted_out;
+  zkl_fe rom_s_in[3], rom_s_out[3];
+} zkl_public_inputs;
+/* Fills *out_params (its `assertions` pointer is set to out_assertions), the assertions in get_assertions() order
+ * (de-duplicated by (column, step), first kept) and the public-coin seed elements. Capacities in, counts out; a too small
+ * buffer fails with the needed counts stored. Host only. Errors (width/layout mismatch, declared vs produced assertion count,
+ * program_id / program_commitment not both zero or both non-zero) are reported through `err` (may be NULL). */
+int zkl_air_build(const zkl_program *program, const zkl_public_inputs *pi, size_t width, size_t n, const zkl_options *opts,
+                  zkl_air_params *out_params, zkl_assertion *out_assertions, size_t *num_assertions /* in: capacity */,
+                  zkl_fe *out_seed, size_t *num_seed /* in: capacity */, char *err, size_t err_cap);
+/* zkl_prove_segment with the AIR parameters and the coin seed built inside (zkl_air_build), per call: nothing about a
+ * segment is cached between calls. */
+int zkl_prove_segment_pi(zkl_ctx *ctx, const zkl_fe *trace, size_t width, size_t n, const zkl_program *program,
+                         const zkl_public_inputs *pi, const zkl_options *opts, uint8_t *out_proof, size_t *out_len,
+                         zkl_proof_summary *summary);
+int zkl_prove_segment_pi_dev(zkl_ctx *ctx, const void *trace_dev, size_t width, size_t n, const zkl_program *program,
+                             const zkl_public_inputs *pi, const zkl_options *opts, uint8_t *out_proof, size_t *out_len,
+                             zkl_proof_summary *summary);
 
 /* device memory helpers for callers that keep traces resident (torch tensors' data_ptr()
  * can be passed instead) */
@@ -313,6 +375,9 @@ int zkl_dev_download(zkl_ctx *ctx, void *host, const void *dev, size_t bytes);
 int zkl_timer_start(zkl_ctx *ctx);             /* CUDA event on the ctx stream */
 int zkl_timer_stop(zkl_ctx *ctx, float *ms);   /* second event, synchronised; elapsed device time */
 int zkl_imad_peak(zkl_ctx *ctx, double *wide_macs_per_s); /* dependency-free IMAD.WIDE.U32 probe */
+/* saturating tcgen05.mma kind::i8 loop (M 128, N 256, K 32 from shared memory, one CTA per SM): dense u8 x u8 -> s32 tensor
+ * operations per second (2 per multiply-accumulate) — the measured denominator of the sponge kernels' tensor roofline */
+int zkl_tc_i8_peak(zkl_ctx *ctx, double *ops_per_s);
 /* sponge count from which the bulk (tensor-core) sponge kernels replace the small-batch ones; 0 = automatic
  * (4096 for a lone prover on the 64-thread groups, 1024 when several contexts share the device) */
 int zkl_set_bulk_threshold(zkl_ctx *ctx, long sponges);

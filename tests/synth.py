@@ -73,10 +73,13 @@ def _to_np(t, n):
     return t.to_np()
 
 
-def valid_segment(n=64, queries=8, blowup=16, grind=4, seed=1, poseidon_levels=True, start_level=0, full_layout=False):
+def valid_segment(n=64, queries=8, blowup=16, grind=4, seed=1, poseidon_levels=True, start_level=0, full_layout=False, program_seed=None):
+    """`program_seed` names the program (its id and commitment; default: `seed`): segments of ONE program — the rollup-bench shape —
+    share it and differ in `seed` (their data) and `start_level` (their first pc)."""
     rng = random.Random(seed)
-    program_id = blake3(b"zkl-b200/synth/program-id/%d" % seed)
-    program_commitment = blake3(b"zkl-b200/synth/program-commitment/%d" % seed)
+    program_seed = seed if program_seed is None else program_seed
+    program_id = blake3(b"zkl-b200/synth/program-id/%d" % program_seed)
+    program_commitment = blake3(b"zkl-b200/synth/program-commitment/%d" % program_seed)
     fm = A.FM_POSEIDON | A.FM_VM | A.FM_SPONGE
     cfg = A.LayoutConfig() if full_layout else A.LayoutConfig(vm=True, ram=False, sponge=True, merkle=False, rom=True)
     cols = A.Columns(cfg)

@@ -1,10 +1,10 @@
-"""CPU test: four blocks of the constraint system restated independently in Python (tests/pyair.py, from the reference text)
+"""CPU test: four blocks of the constraint system restated independently in Python (zk-lisp_b200/air_eval.py, from the reference text)
 against the checker's evaluate_transition on random frames with random periodic values — value by value, index by index."""
 import random
 
 import pytest
 
-import pyair
+from zk_lisp_b200 import air_eval as pyair
 import synth
 from util import P, from_fe, rand_fe, to_fe
 

@@ -308,27 +308,27 @@ def test_python_verifier_ood_consistency(zkl, oracle, child):
     """The last link of an independent verifier: constraints evaluated at z from the OOD frame (Python restatement of the AIR),
     divided and combined with the composition coefficients of the replayed transcript, equal the composition columns at z —
     and any moved OOD value, public input or constraint breaks the equality."""
-    import pyverify
+    V = zkl.verify
     from util import P, from_fe
     n = 64
     for x in (3, 0x1234567 << 70 | 5, P - 2):
-        assert pyverify.periodic_at(n, x) == from_fe(oracle.periodic_at(n, x))
+        assert V.periodic_at(n, x) == from_fe(oracle.periodic_at(n, x))
     step, _, air = child
-    lhs, rhs, z = pyverify.ood_check(zkl, oracle, step, air)
+    lhs, rhs, z = V.ood_consistency(oracle, step, air)
     assert lhs == rhs and z == zkl.replay.replay_fs_from_step(oracle, step).z_ood
     good = rhs
     v = step.proof.inner
     bump = lambda b, i: b[:16 * i] + ((int.from_bytes(b[16 * i:16 * i + 16], "little") + 1) % P).to_bytes(16, "little") + b[16 * i + 16:]
     for kw in (dict(ood_trace=bump(v.ood_trace, 45)), dict(ood_trace=bump(v.ood_trace, v.main_width + 45)), dict(ood_constraints=bump(v.ood_constraints, 2))):
         bad = replace(step, proof=replace(step.proof, inner=replace(v, **kw)))
-        lhs, rhs, _ = pyverify.ood_check(zkl, oracle, bad, air)
+        lhs, rhs, _ = V.ood_consistency(oracle, bad, air)
         assert lhs != rhs
     # (a schedule column's NEXT-row value enters no transition constraint: moving it must leave the left side alone)
     quiet = replace(step, proof=replace(step.proof, inner=replace(v, ood_trace=bump(v.ood_trace, v.main_width + 12))))
-    assert pyverify.ood_check(zkl, oracle, quiet, air)[0] == good
+    assert V.ood_consistency(oracle, quiet, air)[0] == good
     # a proof of another shape: RAM-less layout with more queries and partitions
     step2, _, air2 = _step(zkl, oracle, 32, 9, queries=40, parts=(4, 8), grind=0)
-    lhs, rhs, _ = pyverify.ood_check(zkl, oracle, step2, air2)
+    lhs, rhs, _ = V.ood_consistency(oracle, step2, air2)
     assert lhs == rhs
     zkl.replay.verify_child(oracle, step2)
 
@@ -338,9 +338,15 @@ def test_host_verifier_accepts_and_rejects(zkl, oracle, child):
     proof), accepting valid proofs of several shapes and naming the failing check for tampered ones."""
     V, S = zkl.verify, zkl.step
     step = S.StepProof.from_bytes(child[0].to_bytes())
-    fs = V.verify_step(oracle, step)
+    # 8 queries at blowup 16 = 32 query bits (grinding only counts from 80 up, prove.rs:1185) -> 31 bits of conjectured security
+    assert V.conjectured_security_bits(8, 16, 4, 1, 64 * 16) == 31 and V.conjectured_security_bits(64, 16, 16, 1, 65536) == 111
+    assert V.conjectured_security_bits(64, 16, 16, 2, 1 << 16) == 128 and V.conjectured_security_bits(1, 2, 0, 1, 128) == 0
+    fs = V.verify_step(oracle, step, 31)
     assert fs.query_positions == child[1].positions[:child[1].num_unique_queries]
-    V.verify_step(oracle, _step(zkl, oracle, 32, 9, queries=40, parts=(4, 8), grind=0)[0])
+    V.verify_step(oracle, _step(zkl, oracle, 32, 9, queries=40, parts=(4, 8), grind=0)[0], 100)   # 160 query bits, field-bound: 128 - 9 - 1
+    # the proof's self-declared options are not trusted: below the caller's minimum nothing else is looked at
+    with pytest.raises(S.InvalidInput, match="31 bits of conjectured security, below the required 64"):
+        V.verify_step(oracle, step, 64)
     v = step.proof.inner
     bump = lambda b, i: b[:16 * i] + ((int.from_bytes(b[16 * i:16 * i + 16], "little") + 1) % zkl.field.P).to_bytes(16, "little") + b[16 * i + 16:]
     with_inner = lambda **kw: replace(step, proof=replace(step.proof, inner=replace(v, **kw)))
@@ -349,6 +355,15 @@ def test_host_verifier_accepts_and_rejects(zkl, oracle, child):
                     (dict(pow_nonce=v.pow_nonce + 1), "grinding factor|unique query|openings"),
                     (dict(fri_remainder=bump(v.fri_remainder, 0)), "remainder")):
         with pytest.raises(S.InvalidInput, match=msg):
-            V.verify_step(oracle, with_inner(**kw))
+            V.verify_step(oracle, with_inner(**kw), 31)
     with pytest.raises(S.InvalidInput):
-        V.verify_step(oracle, replace(step, vm_usage_mask=step.vm_usage_mask ^ 4))     # another AIR: constraint count / seed differ
+        V.verify_step(oracle, replace(step, vm_usage_mask=step.vm_usage_mask ^ 4), 31)     # another AIR: constraint count / seed differ
+    # a forged context: fewer queries / no grinding / another extension or batching declared -> refused before any replay
+    P = zkl.field.P
+    noncanon = lambda b, i: b[:16 * i] + (P + 5).to_bytes(16, "little") + b[16 * i + 16:]   # an encoding winter-math's reader rejects
+    for kw, msg in ((dict(num_queries=1), "below the required"), (dict(blowup=2), "below the required"), (dict(num_queries=0), "no queries"),
+                    (dict(field_extension=2), "FieldExtension::None"), (dict(batching=(1, 0)), "Linear batching"), (dict(fri_folding=4), "folding factor 2"),
+                    (dict(ood_trace=noncanon(v.ood_trace, 3)), "non-canonical"), (dict(trace_query_values=noncanon(v.trace_query_values, 0)), "non-canonical"),
+                    (dict(fri_remainder=v.fri_remainder[:-1]), "multiple of 16")):
+        with pytest.raises(S.InvalidInput, match=msg):
+            V.verify_step(oracle, with_inner(**kw), 31)

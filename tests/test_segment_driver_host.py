@@ -51,6 +51,20 @@ class _StandInLib:
         return 0
 
 
+    def zkl_prove_segment_pi_dev(self, h, dev, W, n, program, pi, opts, buf, cap, summ):
+        """The AIR instance comes from the library's own host-side builder (zkl_air_build needs no device), the proof from the checker."""
+        from zk_lisp_b200 import capi
+        from zk_lisp_b200.prover import NativeAir
+        from zk_lisp_b200.air import ProofOptions
+        o = opts._obj
+        po = ProofOptions(o.num_queries, o.blowup, o.grinding, o.num_partitions, o.hash_rate, o.fri_folding, o.fri_remainder_max_degree)
+        a = NativeAir(program._obj, pi._obj, W, n, po)
+        p = self.oracle.prove_segment(self.bufs[dev.value].reshape(W, n, 2), a.params, np.ascontiguousarray(a.seed), o, summ._obj)
+        C.memmove(buf, p, len(p))
+        cap._obj.value = len(p)
+        return 0
+
+
 class _StandInContext:
     def __init__(self, oracle, usage_mask, device=0):
         self.lib, self.h, self.device = _StandInLib(oracle, usage_mask), None, device
@@ -91,11 +105,11 @@ def test_prove_program_host_logic(zkl, oracle):
         assert back.digest() == c.digest() and back.proof.pi == c.proof.pi and back.proof.meta == c.proof.meta
         fs = R.replay_fs_from_step(ctxs[0], back)
         R.verify_child_openings(ctxs[0], back, fs)
-        assert zkl.verify.verify_step(ctxs[0], back) == fs          # the whole host verifier on the ZKLSTP1 bytes of a driver-made step
+        assert zkl.verify.verify_step(ctxs[0], back, 16) == fs          # the whole host verifier on the ZKLSTP1 bytes of a driver-made step
     ST.verify_chain([s.step for s in steps])
     assert len({s.step.digest() for s in steps}) == len(steps)
     # a failing worker surfaces its error to the caller (prove.rs: Error::Backend)
-    ctxs[1].lib.zkl_prove_segment_dev = lambda *a: 1
+    ctxs[1].lib.zkl_prove_segment_pi_dev = lambda *a: 1
     try:
         SG.prove_program(ctxs, full, segs, core, feats, opts)
         raise RuntimeError("expected a failure")

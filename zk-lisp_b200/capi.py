@@ -79,8 +79,27 @@ class ProofSummary(C.Structure):
         ("trace_root", C.c_uint8 * 32), ("constraint_root", C.c_uint8 * 32),
         ("fri_roots", C.c_uint8 * (32 * 40)), ("num_fri_roots", C.c_uint32),
         ("z", Fe), ("pow_nonce", C.c_uint64), ("num_unique_queries", C.c_uint32),
-        ("positions", C.c_uint32 * 256), ("stage_ms", C.c_float * 12),
+        ("positions", C.c_uint32 * 256), ("stage_ms", C.c_float * 12), ("constraints_violated", C.c_uint32),
     ]
+
+
+ERR_BUFFER_TOO_SMALL, ERR_CONSTRAINTS_VIOLATED = 2, 3
+MAX_MAIN_SLOTS = 16
+
+
+class Program(C.Structure):
+    """zkl_program: per-program constants (zkl_program_derive)."""
+    _fields_ = [("program_id", C.c_uint8 * 32), ("program_commitment", C.c_uint8 * 32), ("pose", Suite), ("rom", RomSuite),
+                ("rom_w_enc0", Fe * 59), ("rom_w_enc1", Fe * 59), ("program_fe", Fe * 2), ("commitment_fe", Fe * 2)]
+
+
+class PublicInputsC(C.Structure):
+    """zkl_public_inputs: AirPublicInputs (lib.rs:74-96) + the core fields the AIR reads."""
+    _fields_ = [("feature_mask", C.c_uint64), ("segment_feature_mask", C.c_uint64), ("merkle_root", C.c_uint8 * 32),
+                ("vm_expected_bytes", C.c_uint8 * 32), ("vm_out_reg", C.c_uint32), ("vm_out_row", C.c_uint32),
+                ("num_main_slots", C.c_uint32), ("vm_usage_mask", C.c_uint32), ("ram_delta_clk_bits", C.c_uint32), ("pad_", C.c_uint32),
+                ("main_slots", Fe * MAX_MAIN_SLOTS), ("pc_init", Fe), ("ram_gp_unsorted_in", Fe), ("ram_gp_unsorted_out", Fe),
+                ("ram_gp_sorted_in", Fe), ("ram_gp_sorted_out", Fe), ("rom_s_in", Fe * 3), ("rom_s_out", Fe * 3)]
 
 
 class ChildProof(C.Structure):
@@ -165,6 +184,14 @@ def load_library():
     sig("zkl_prove_segment_dev", C.c_int, vp, vp, sz, sz, C.POINTER(AirParams), vp, sz, C.POINTER(Options), vp,
         C.POINTER(sz), C.POINTER(ProofSummary))
     sig("zkl_stage_name", C.c_char_p, C.c_int)
+    sig("zkl_program_derive", C.c_int, vp, vp, C.POINTER(Program))
+    sig("zkl_suite_derive", C.c_int, vp, C.POINTER(Suite))
+    sig("zkl_air_build", C.c_int, C.POINTER(Program), C.POINTER(PublicInputsC), sz, sz, C.POINTER(Options), C.POINTER(AirParams), vp,
+        C.POINTER(sz), vp, C.POINTER(sz), C.c_char_p, sz)
+    sig("zkl_prove_segment_pi", C.c_int, vp, vp, sz, sz, C.POINTER(Program), C.POINTER(PublicInputsC), C.POINTER(Options), vp,
+        C.POINTER(sz), C.POINTER(ProofSummary))
+    sig("zkl_prove_segment_pi_dev", C.c_int, vp, vp, sz, sz, C.POINTER(Program), C.POINTER(PublicInputsC), C.POINTER(Options), vp,
+        C.POINTER(sz), C.POINTER(ProofSummary))
     sig("zkl_dev_alloc", C.c_int, vp, sz, C.POINTER(vp))
     sig("zkl_dev_free", C.c_int, vp, vp)
     sig("zkl_dev_upload", C.c_int, vp, vp, vp, sz)
@@ -175,6 +202,7 @@ def load_library():
     sig("zkl_timer_start", C.c_int, vp)
     sig("zkl_timer_stop", C.c_int, vp, C.POINTER(C.c_float))
     sig("zkl_imad_peak", C.c_int, vp, C.POINTER(C.c_double))
+    sig("zkl_tc_i8_peak", C.c_int, vp, C.POINTER(C.c_double))
     sig("zkl_partition_size", sz, C.POINTER(Options), sz)
     sig("zkl_lde_dev", C.c_int, vp, vp, sz, sz, sz, vp, vp)
     sig("zkl_hash_partitions_dev", C.c_int, vp, vp, sz, sz, sz, sz, vp)
@@ -206,4 +234,5 @@ EXPORTED_SYMBOLS = [
     "zkl_constraint_commitment_free", "zkl_constraint_query", "zkl_prove_segment",
     "zkl_prove_segment_dev", "zkl_stage_name", "zkl_dev_alloc", "zkl_dev_free", "zkl_dev_upload",
     "zkl_sync", "zkl_slice_segment_dev", "zkl_usage_mask_dev", "zkl_read_cells_dev", "zkl_timer_start", "zkl_timer_stop", "zkl_imad_peak", "zkl_set_bulk_threshold", "zkl_set_hash_path", "zkl_set_ntt_path", "zkl_set_coop_path", "zkl_bench_permute", "zkl_partition_size", "zkl_lde_dev", "zkl_hash_partitions_dev", "zkl_merge_partition_digests_dev", "zkl_merkle_dev", "zkl_dev_download", "zkl_merge_plan", "zkl_poseidon_levels_dev", "zkl_merge_with_int_pairs", "zkl_replay_children", "zkl_replay_status_name", "zkl_grind", "zkl_hash_two_lanes_host",
+    "zkl_program_derive", "zkl_suite_derive", "zkl_air_build", "zkl_prove_segment_pi", "zkl_prove_segment_pi_dev", "zkl_tc_i8_peak",
 ]

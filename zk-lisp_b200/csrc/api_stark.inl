@@ -32,6 +32,8 @@ static int check_opts(zkl_ctx *ctx, const zkl_options *o, size_t n) {
   if (o->fri_folding != 2) { ctx->set_error("only FRI folding factor 2 is supported (prove.rs:968)"); return 1; }
   if (o->blowup < 2 || (o->blowup & (o->blowup - 1)) || o->blowup > 128) { ctx->set_error("blowup must be a power of two in [2,128]"); return 1; }
   if (n < 8 || n > NTT_MAX || (n & (n - 1))) { ctx->set_error("trace length must be a power of two in [8, 2^24]"); return 1; }
+  // the FRI remainder is interpolated by one CTA (k_fri_remainder): its domain (max degree + 1) * blowup is bounded
+  if ((size_t)(o->fri_remainder_max_degree + 1) * o->blowup > 256) { ctx->set_error("FRI remainder domain (fri_remainder_max_degree + 1) * blowup must be <= 256"); return 1; }
   return 0;
 }
 
@@ -179,74 +181,58 @@ extern "C" int zkl_constraint_query(zkl_ctx *ctx, const zkl_constraint_commitmen
 // ------------------------------------------------------------------------------------------------
 // constraint evaluation (hook 2)
 // ------------------------------------------------------------------------------------------------
-// AIR parameters on the device. The static part (constants, sorted assertions) depends only on the AIR instance and
-// is cached per context, keyed by a hash of the parameter bytes: proving many segments of one program re-uses it.
-struct air_static {
-  air_dev *air = nullptr;
-  assertion_dev *as = nullptr;
-  uint32_t *group_start = nullptr, *slot_col = nullptr;
-  int nslots = 0, ngroups = 0;
-};
+// AIR parameters on the device. Nothing is cached between calls: the constants (11 KB) and the assertion table (32 B per
+// assertion, 0.58 MB for a 4096-row segment) are rebuilt in the context's pinned staging buffer and uploaded per call, so a
+// segment can never be proven with another instance's constants. Assertions are ordered as Winterfell orders them (by step,
+// then column: single assertions have stride 0 [WF-mem]) with two counting sorts.
 struct air_device_state {
-  air_static s;
+  dev_buf<uint8_t> blob;   // air_dev | assertion_dev[na] | group_start[ng + 1] | slot_col[nslots]
   struct view { air_dev *p; } air;
   struct view_as { assertion_dev *p; } as;
   struct view_u32 { uint32_t *p; } group_start, slot_col;
   dev_buf<fe> coset_consts, u, bpoly;
   int nslots = 0, ngroups = 0;
 };
-static std::mutex g_air_cache_mutex;
-static std::map<std::pair<const zkl_ctx *, uint64_t>, air_static> g_air_cache;
-static uint64_t fnv1a(uint64_t h, const void *p, size_t n) {
-  const uint8_t *b = (const uint8_t *)p;
-  for (size_t i = 0; i < n; i++) { h ^= b[i]; h *= 0x100000001b3ull; }
-  return h;
-}
-static void air_cache_drop(const zkl_ctx *ctx) {
-  std::lock_guard<std::mutex> g(g_air_cache_mutex);
-  for (auto it = g_air_cache.begin(); it != g_air_cache.end();) {
-    if (it->first.first == ctx) {
-      cudaFree(it->second.air); cudaFree(it->second.as); cudaFree(it->second.group_start); cudaFree(it->second.slot_col);
-      it = g_air_cache.erase(it);
-    } else ++it;
-  }
-}
-
-static int upload_air_static(zkl_ctx *ctx, const zkl_air_params *a, size_t n, air_static &st);
-static int upload_air(zkl_ctx *ctx, const zkl_air_params *a, size_t n, air_device_state &st) {
-  uint64_t h = 0xcbf29ce484222325ull;
-  zkl_air_params tmp = *a; tmp.assertions = nullptr;
-  h = fnv1a(h, &tmp, sizeof tmp);
-  h = fnv1a(h, a->assertions, sizeof(zkl_assertion) * a->num_assertions);
-  h = fnv1a(h, &n, sizeof n);
-  {
-    std::lock_guard<std::mutex> g(g_air_cache_mutex);
-    auto it = g_air_cache.find({ctx, h});
-    if (it != g_air_cache.end()) st.s = it->second;
-  }
-  if (!st.s.air) {
-    ZKL_TRY(upload_air_static(ctx, a, n, st.s));
-    std::lock_guard<std::mutex> g(g_air_cache_mutex);
-    size_t mine = 0;
-    for (auto &kv : g_air_cache) mine += kv.first.first == ctx;
-    if (mine >= 64) {  // bounded: drop this context's entries (all in-flight work on its stream is ordered before reuse)
-      cudaStreamSynchronize(ctx->stream);
-      for (auto it = g_air_cache.begin(); it != g_air_cache.end();) {
-        if (it->first.first == ctx) {
-          cudaFree(it->second.air); cudaFree(it->second.as); cudaFree(it->second.group_start); cudaFree(it->second.slot_col);
-          it = g_air_cache.erase(it);
-        } else ++it;
-      }
-    }
-    g_air_cache[{ctx, h}] = st.s;
-  }
-  st.air.p = st.s.air; st.as.p = st.s.as; st.group_start.p = st.s.group_start; st.slot_col.p = st.s.slot_col;
-  st.nslots = st.s.nslots; st.ngroups = st.s.ngroups;
+// Host wait for everything enqueued on the context's stream. A lone prover spins (lowest wake-up latency); when several
+// contexts share the device — a pool of proving threads, several ranks per box — the thread blocks on an event created with
+// cudaEventBlockingSync, so waiting provers do not burn the cores the other provers' host code needs.
+static int ctx_wait(zkl_ctx *ctx) {
+  const bool block = ctx->wait_mode == 2 || (ctx->wait_mode == 0 && g_ctx_per_device[ctx->device & 63].load(std::memory_order_relaxed) > 1);
+  if (!block) { ZKL_CHECK(ctx, cudaStreamSynchronize(ctx->stream)); return 0; }
+  if (!ctx->wait_ev) ZKL_CHECK(ctx, cudaEventCreateWithFlags(&ctx->wait_ev, cudaEventBlockingSync | cudaEventDisableTiming));
+  ZKL_CHECK(ctx, cudaEventRecord(ctx->wait_ev, ctx->stream));
+  ZKL_CHECK(ctx, cudaEventSynchronize(ctx->wait_ev));
   return 0;
 }
-static int upload_air_static(zkl_ctx *ctx, const zkl_air_params *a, size_t n, air_static &st) {
+// Pinned host staging, one region per context, handed out by a bump pointer that restarts with every entry point:
+// parameter uploads and result downloads of a call never pass through pageable memory (a cudaMemcpyAsync on pageable memory
+// is staged by the driver and may wait for the stream). A region may only be (re)used when nothing enqueued earlier still
+// refers to it: every entry point that stages ends with a host wait.
+static void *stage_alloc(zkl_ctx *ctx, size_t bytes) {
+  const size_t off = (ctx->stage_used + 63) & ~(size_t)63;
+  if (off + bytes > ctx->stage_cap) return nullptr;
+  ctx->stage_used = off + bytes;
+  return (uint8_t *)ctx->stage_h + off;
+}
+static int stage_reserve(zkl_ctx *ctx, size_t bytes) {
+  ctx->stage_used = 0;
+  if (ctx->stage_cap >= bytes) return 0;
+  if (ctx->stage_h) { ZKL_CHECK(ctx, cudaStreamSynchronize(ctx->stream)); cudaFreeHost(ctx->stage_h); ctx->stage_h = nullptr; ctx->stage_cap = 0; }
+  size_t cap = std::max<size_t>(bytes + bytes / 4, (size_t)1 << 20);
+  ZKL_CHECK(ctx, cudaHostAlloc(&ctx->stage_h, cap, cudaHostAllocDefault));
+  ctx->stage_cap = cap;
+  return 0;
+}
+static int upload_air(zkl_ctx *ctx, const zkl_air_params *a, size_t n, air_device_state &st) {
   if (a->cols.width > 255) { ctx->set_error("trace width must fit in u8 (winterfell TraceInfo)"); return 1; }
-  air_dev h; memset(&h, 0, sizeof h);
+  const size_t na = a->num_assertions;
+  auto al = [](size_t x) { return (x + 15) & ~(size_t)15; };
+  const size_t off_as = al(sizeof(air_dev)), off_gs = off_as + al(std::max<size_t>(na, 1) * sizeof(assertion_dev));
+  // group count is known only after the pass over the steps: reserve the worst case (one group per assertion)
+  const size_t off_sc = off_gs + al((na + 1) * 4), total = off_sc + al(256 * 4);
+  uint8_t *hb = (uint8_t *)stage_alloc(ctx, total);
+  if (!hb) { ZKL_TRY(stage_reserve(ctx, total)); hb = (uint8_t *)stage_alloc(ctx, total); }   // hook-level call: the region is free (each ends with a wait)
+  air_dev &h = *(air_dev *)hb; memset(&h, 0, sizeof h);
   h.cols = a->cols;
   h.f_poseidon = a->f_poseidon; h.f_vm = a->f_vm; h.f_sponge = a->f_sponge; h.f_merkle = a->f_merkle; h.f_ram = a->f_ram;
   h.rom_enabled = a->rom_enabled; h.vm_usage_mask = a->vm_usage_mask; h.ram_delta_clk_bits = a->ram_delta_clk_bits;
@@ -257,38 +243,36 @@ static int upload_air_static(zkl_ctx *ctx, const zkl_air_params *a, size_t n, ai
   for (int r = 0; r < ZKL_ROUNDS; r++) for (int j = 0; j < 3; j++) h.rom_rc[r][j] = fe_from_abi(a->rom.rc[r][j]);
   for (int k = 0; k < 59; k++) { h.rom_w0[k] = fe_from_abi(a->rom_w_enc0[k]); h.rom_w1[k] = fe_from_abi(a->rom_w_enc1[k]); }
   h.program_fe0 = fe_from_abi(a->program_fe0); h.merkle_root_fe = fe_from_abi(a->merkle_root_fe);
-  ZKL_CHECK(ctx, cudaMalloc((void **)&st.air, sizeof h));
-  ZKL_CHECK(ctx, cudaMemcpyAsync(st.air, &h, sizeof h, cudaMemcpyHostToDevice, ctx->stream));
-  // assertions: Winterfell order = sorted by (stride, first_step, column); single assertions have stride 0 [WF-mem]
-  std::vector<uint32_t> order(a->num_assertions);
-  for (uint32_t i = 0; i < a->num_assertions; i++) order[i] = i;
-  std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) {
-    const zkl_assertion &p = a->assertions[x], &q = a->assertions[y];
-    return p.step != q.step ? p.step < q.step : p.column < q.column;
-  });
-  std::map<uint32_t, uint32_t> slot_of;  // column -> slot
-  std::vector<uint32_t> slot_col;
-  std::vector<assertion_dev> as(a->num_assertions);
-  std::vector<uint32_t> gs;
-  for (uint32_t q = 0; q < a->num_assertions; q++) {
+  // order[] = assertion indices sorted by (step, column), stable: counting sort by column, then by step
+  for (size_t i = 0; i < na; i++)
+    if (a->assertions[i].column >= a->cols.width || a->assertions[i].step >= n) { ctx->set_error("assertion outside the trace"); return 1; }
+  std::vector<uint32_t> &by_col = ctx->sort_a, &order = ctx->sort_b, &cnt = ctx->sort_cnt;
+  by_col.resize(na); order.resize(na);
+  cnt.assign(257, 0);
+  for (size_t i = 0; i < na; i++) cnt[a->assertions[i].column + 1]++;
+  for (int c = 0; c < 256; c++) cnt[c + 1] += cnt[c];
+  for (size_t i = 0; i < na; i++) by_col[cnt[a->assertions[i].column]++] = (uint32_t)i;
+  cnt.assign(n + 1, 0);
+  for (size_t i = 0; i < na; i++) cnt[a->assertions[i].step + 1]++;
+  for (size_t r = 0; r < n; r++) cnt[r + 1] += cnt[r];
+  for (size_t i = 0; i < na; i++) order[cnt[a->assertions[by_col[i]].step]++] = by_col[i];
+  assertion_dev *as = (assertion_dev *)(hb + off_as);
+  uint32_t *gs = (uint32_t *)(hb + off_gs), *slot_col = (uint32_t *)(hb + off_sc);
+  int slot_of[256]; for (int c = 0; c < 256; c++) slot_of[c] = -1;
+  int nslots = 0, ng = 0;
+  for (size_t q = 0; q < na; q++) {
     const zkl_assertion &x = a->assertions[order[q]];
-    if (x.column >= a->cols.width || x.step >= n) { ctx->set_error("assertion outside the trace"); return 1; }
-    auto it = slot_of.find(x.column);
-    if (it == slot_of.end()) { it = slot_of.emplace(x.column, (uint32_t)slot_col.size()).first; slot_col.push_back(x.column); }
-    as[q].slot = it->second; as[q].step = x.step; as[q].cc_index = a->num_transition + q; as[q].pad = 0;
+    if (slot_of[x.column] < 0) { slot_of[x.column] = nslots; slot_col[nslots++] = x.column; }
+    as[q].slot = (uint32_t)slot_of[x.column]; as[q].step = x.step; as[q].cc_index = a->num_transition + (uint32_t)q; as[q].pad = 0;
     as[q].value = fe_from_abi(x.value);
-    if (q == 0 || x.step != a->assertions[order[q - 1]].step) gs.push_back(q);
+    if (q == 0 || x.step != a->assertions[order[q - 1]].step) gs[ng++] = (uint32_t)q;
   }
-  gs.push_back(a->num_assertions);
-  st.nslots = (int)slot_col.size(); st.ngroups = (int)gs.size() - 1;
-  ZKL_CHECK(ctx, cudaMalloc((void **)&st.as, std::max<size_t>(as.size(), 1) * sizeof(assertion_dev)));
-  ZKL_CHECK(ctx, cudaMalloc((void **)&st.group_start, gs.size() * 4));
-  ZKL_CHECK(ctx, cudaMalloc((void **)&st.slot_col, std::max<size_t>(slot_col.size(), 1) * 4));
-  if (!as.empty()) ZKL_CHECK(ctx, cudaMemcpyAsync(st.as, as.data(), as.size() * sizeof(assertion_dev), cudaMemcpyHostToDevice, ctx->stream));
-  ZKL_CHECK(ctx, cudaMemcpyAsync(st.group_start, gs.data(), gs.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
-  if (!slot_col.empty()) ZKL_CHECK(ctx, cudaMemcpyAsync(st.slot_col, slot_col.data(), slot_col.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
-  // the host vectors must outlive the async copies
-  ZKL_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  gs[ng] = (uint32_t)na;
+  st.nslots = nslots; st.ngroups = ng;
+  ZKL_CHECK(ctx, st.blob.alloc(total));
+  ZKL_CHECK(ctx, cudaMemcpyAsync(st.blob.p, hb, total, cudaMemcpyHostToDevice, ctx->stream));
+  st.air.p = (air_dev *)st.blob.p; st.as.p = (assertion_dev *)(st.blob.p + off_as);
+  st.group_start.p = (uint32_t *)(st.blob.p + off_gs); st.slot_col.p = (uint32_t *)(st.blob.p + off_sc);
   return 0;
 }
 
@@ -477,6 +461,7 @@ static size_t fri_num_layers(size_t domain, const zkl_options &o) {  // FriOptio
   while (domain > max_rem) { domain /= o.fri_folding; r++; }
   return r;
 }
+static size_t rem_cap_of(const zkl_options &o) { return (size_t)o.fri_remainder_max_degree + 1; }
 static std::vector<uint32_t> fold_positions_host(const std::vector<uint32_t> &pos, size_t src_domain) {  // agg/child.rs:1072-1099
   size_t tgt = src_domain / 2;
   std::vector<uint32_t> r;
@@ -486,7 +471,7 @@ static std::vector<uint32_t> fold_positions_host(const std::vector<uint32_t> &po
 
 static const char *k_stage_names[12] = {"coin_seed", "trace_lde_commit", "constraint_eval", "constraint_commit", "ood", "deep",
                                         "fri", "grind", "queries_serialize", "kernel:k_lde(trace)", "kernel:k_hash_rows(trace)",
-                                        "flag:composition_degree_overflow"};
+                                        "host:air_build"};
 extern "C" const char *zkl_stage_name(int s) { return (s >= 0 && s < 12) ? k_stage_names[s] : ""; }
 
 // ------------------------------------------------------------------------------------------------
@@ -503,6 +488,13 @@ static int prove_segment_impl(zkl_ctx *ctx, const fe *trace_dev, size_t W, size_
   const size_t nl = fri_num_layers(N, *o);
   if (nl + 1 > 40) { ctx->set_error("too many FRI layers"); return 1; }
   while (ctx->ev.size() < 16) { cudaEvent_t e; ZKL_CHECK(ctx, cudaEventCreate(&e)); ctx->ev.push_back(e); }
+  // pinned staging for everything this proof moves between host and device besides the trace: AIR parameters, seed,
+  // the opening plan (one pointer + one index per opened element) and the opened elements themselves
+  const size_t logN = (size_t)ilog2_sz(N);
+  const size_t max_open = (size_t)o->num_queries * (W + C + 2 * logN + nl * (2 + logN)) + 64;
+  const size_t stage_need = sizeof(air_dev) + ((size_t)air->num_assertions + 2) * (sizeof(assertion_dev) + 4) + 256 * 4 + num_seed * sizeof(fe) +
+                            max_open * (sizeof(fe *) + 4 + sizeof(fe)) + (2 * (W + C) + nl + rem_cap_of(*o) + 64) * sizeof(fe) + 8192;
+  ZKL_TRY(stage_reserve(ctx, stage_need));
   domain_tables *tN; ZKL_TRY(get_tables(ctx, N, &tN));
   fe *opow; ZKL_TRY(get_offset_powers(ctx, n, &opow)); (void)opow;
   cudaStream_t st = ctx->stream;
@@ -528,7 +520,11 @@ static int prove_segment_impl(zkl_ctx *ctx, const fe *trace_dev, size_t W, size_
   // ---- 1. public coin seed (agg/fs.rs:69-73)
   dev_buf<fe> seed_in, tmp;
   ZKL_CHECK(ctx, seed_in.alloc(num_seed)); ZKL_CHECK(ctx, coin.alloc(1)); ZKL_CHECK(ctx, tmp.alloc(8));
-  ZKL_CHECK(ctx, cudaMemcpyAsync(seed_in.p, seed_elems, num_seed * sizeof(fe), cudaMemcpyHostToDevice, st));
+  {
+    void *sh = stage_alloc(ctx, num_seed * sizeof(fe));
+    memcpy(sh, seed_elems, num_seed * sizeof(fe));
+    ZKL_CHECK(ctx, cudaMemcpyAsync(seed_in.p, sh, num_seed * sizeof(fe), cudaMemcpyHostToDevice, st));
+  }
   if (quad) LAUNCH(ctx, k_quad_coin_init, 1, ZKL_QUAD_GROUP, 0, seed_in.p, (int)num_seed, coin.p);
   else LAUNCH(ctx, k_coin_init, 1, ZKL_COOP_GROUP, 0, seed_in.p, (int)num_seed, coin.p);
   STAGE_MARK();
@@ -599,7 +595,6 @@ static int prove_segment_impl(zkl_ctx *ctx, const fe *trace_dev, size_t W, size_
   }
   size_t rem_len = nd;  // (B*nd)/B coefficients
   ZKL_CHECK(ctx, rem_rev.alloc(rem_len));
-  if (nd * B > 256) { ctx->set_error("FRI remainder domain too large"); return 1; }
   LAUNCH(ctx, k_fri_remainder, 1, 32 > (int)nd ? 32 : (int)nd, 0, cur_ev, (int)nd, (int)B, tN->wpow, N, fe_inv(fe_from_u64(3)),
          fe_inv(fe_from_u64(nd * B)), rem_rev.p);
   if (quad) LAUNCH(ctx, k_quad_hash_elements_single, 1, ZKL_QUAD_GROUP, 0, rem_rev.p, (int)rem_len, fri_roots.p + nl);
@@ -607,16 +602,26 @@ static int prove_segment_impl(zkl_ctx *ctx, const fe *trace_dev, size_t W, size_
   ZKL_TRY(reseed_draw(fri_roots.p + nl, nullptr, 0, nullptr));
   STAGE_MARK();
 
-  // ---- 10. grinding (smallest nonce >= 1)
+  // ---- 10. grinding (smallest nonce >= 1) and 11. query positions: enqueued back to back, ONE host wait for both.
+  // The search window is 16x the expected nonce (miss probability e^-16): the positions are drawn right behind it from the
+  // nonce on the device; the host only looks at the nonce after the wait and repeats with the next window on a miss.
   dev_buf<unsigned long long> nonce;
   ZKL_CHECK(ctx, nonce.alloc(1));
   unsigned long long nonce_h = 0;
-  if (o->grinding > 0) {
-    if (o->grinding > 40) { ctx->set_error("grinding factor too large"); return 1; }
-    ZKL_CHECK(ctx, cudaMemsetAsync(nonce.p, 0xFF, 8, st));
-    uint64_t base = 1;
-    for (;;) {
-      // search window = 16x the expected nonce, without a host round trip
+  if (o->grinding > 40) { ctx->set_error("grinding factor too large"); return 1; }
+  dev_buf<uint32_t> pos_dev, pos_cnt;
+  ZKL_CHECK(ctx, pos_dev.alloc(256)); ZKL_CHECK(ctx, pos_cnt.alloc(1));
+  dev_buf<fe> qseed, qdraw;
+  ZKL_CHECK(ctx, qseed.alloc(1)); ZKL_CHECK(ctx, qdraw.alloc(o->num_queries));
+  struct mailbox { unsigned long long nonce; uint32_t cnt, pad; uint32_t pos[256]; fe troot, croot, z, flag; };
+  mailbox *mb = (mailbox *)stage_alloc(ctx, sizeof(mailbox));
+  fe *ood_h = (fe *)stage_alloc(ctx, 2 * (W + C) * sizeof(fe)), *roots_h = (fe *)stage_alloc(ctx, (nl + 1) * sizeof(fe));
+  fe *rem_h = (fe *)stage_alloc(ctx, rem_len * sizeof(fe));
+  if (!mb || !ood_h || !roots_h || !rem_h) { ctx->set_error("staging buffer exhausted"); return 1; }
+  uint64_t base = 1;
+  for (int attempt = 0;; attempt++) {
+    if (o->grinding > 0) {
+      if (attempt == 0) ZKL_CHECK(ctx, cudaMemsetAsync(nonce.p, 0xFF, 8, st));
       uint64_t target = std::min<uint64_t>((uint64_t)16 << o->grinding, (uint64_t)1 << 30);
       if (ctx->hash_path == 0) {
         // one persistent launch; CTAs stop at the first tile above the best nonce found so far
@@ -628,21 +633,11 @@ static int prove_segment_impl(zkl_ctx *ctx, const fe *trace_dev, size_t W, size_
         for (int b = 0; b < nb; b++, base += batch)
           LAUNCH(ctx, k_grind, ceil_div((size_t)batch * ZKL_COOP_GROUP, ZKL_COOP_THREADS), ZKL_COOP_THREADS, 0, coin.p, base, batch, o->grinding, nonce.p);
       }
-      ZKL_CHECK(ctx, cudaMemcpyAsync(&nonce_h, nonce.p, 8, cudaMemcpyDeviceToHost, st));
-      ZKL_CHECK(ctx, cudaStreamSynchronize(st));
-      if (nonce_h != ~0ull) break;
+    } else {
+      ZKL_CHECK(ctx, cudaMemsetAsync(nonce.p, 0, 8, st));
     }
-  } else {
-    ZKL_CHECK(ctx, cudaMemsetAsync(nonce.p, 0, 8, st));
-  }
-  STAGE_MARK();
-
-  // ---- 11. query positions, openings, serialization
-  dev_buf<uint32_t> pos_dev, pos_cnt;
-  ZKL_CHECK(ctx, pos_dev.alloc(256)); ZKL_CHECK(ctx, pos_cnt.alloc(1));
-  {  // seed' = merge_with_int(seed, nonce); the draws in parallel; mask + sort + de-duplicate
-    dev_buf<fe> qseed, qdraw;
-    ZKL_CHECK(ctx, qseed.alloc(1)); ZKL_CHECK(ctx, qdraw.alloc(o->num_queries));
+    if (attempt == 0) STAGE_MARK();
+    // seed' = merge_with_int(seed, nonce); the draws in parallel; mask + sort + de-duplicate
     if (quad) {
       LAUNCH(ctx, k_seed_with_nonce<ZKL_QUAD_GROUP>, 1, ZKL_QUAD_GROUP, 0, coin.p, nonce.p, qseed.p);
       LAUNCH_QUAD(ctx, k_quad_coin_draw, o->num_queries, qseed.p, (uint64_t)0, (int)o->num_queries, qdraw.p);
@@ -651,26 +646,35 @@ static int prove_segment_impl(zkl_ctx *ctx, const fe *trace_dev, size_t W, size_
       LAUNCH_COOP(ctx, k_coin_draw, o->num_queries, qseed.p, (uint64_t)0, (int)o->num_queries, qdraw.p);
     }
     LAUNCH(ctx, k_positions_finish, 1, 64, 0, qdraw.p, (int)o->num_queries, (uint32_t)(N - 1), pos_dev.p, pos_cnt.p);
+    ZKL_CHECK(ctx, cudaMemcpyAsync(&mb->nonce, nonce.p, 8, cudaMemcpyDeviceToHost, st));
+    ZKL_CHECK(ctx, cudaMemcpyAsync(mb->pos, pos_dev.p, sizeof mb->pos, cudaMemcpyDeviceToHost, st));
+    ZKL_CHECK(ctx, cudaMemcpyAsync(&mb->cnt, pos_cnt.p, 4, cudaMemcpyDeviceToHost, st));
+    if (attempt == 0) {
+      ZKL_CHECK(ctx, cudaMemcpyAsync(ood_h, ood.p, 2 * (W + C) * sizeof(fe), cudaMemcpyDeviceToHost, st));
+      ZKL_CHECK(ctx, cudaMemcpyAsync(roots_h, fri_roots.p, (nl + 1) * sizeof(fe), cudaMemcpyDeviceToHost, st));
+      ZKL_CHECK(ctx, cudaMemcpyAsync(rem_h, rem_rev.p, rem_len * sizeof(fe), cudaMemcpyDeviceToHost, st));
+      ZKL_CHECK(ctx, cudaMemcpyAsync(&mb->troot, tl.m.nodes.p + 1, sizeof(fe), cudaMemcpyDeviceToHost, st));
+      ZKL_CHECK(ctx, cudaMemcpyAsync(&mb->croot, cmt.m.nodes.p + 1, sizeof(fe), cudaMemcpyDeviceToHost, st));
+      ZKL_CHECK(ctx, cudaMemcpyAsync(&mb->z, z.p, sizeof(fe), cudaMemcpyDeviceToHost, st));
+      ZKL_CHECK(ctx, cudaMemcpyAsync(&mb->flag, flag.p, sizeof(fe), cudaMemcpyDeviceToHost, st));
+    }
+    ZKL_TRY(ctx_wait(ctx));
+    nonce_h = mb->nonce;
+    if (o->grinding == 0 || nonce_h != ~0ull) break;
   }
-  uint32_t pos_h[256], cnt_h = 0;
-  std::vector<fe> ood_h(2 * (W + C)), roots_h(nl + 1), rem_h(rem_len);
-  fe troot, croot, z_h, flag_h;
-  ZKL_CHECK(ctx, cudaMemcpyAsync(pos_h, pos_dev.p, sizeof pos_h, cudaMemcpyDeviceToHost, st));
-  ZKL_CHECK(ctx, cudaMemcpyAsync(&cnt_h, pos_cnt.p, 4, cudaMemcpyDeviceToHost, st));
-  ZKL_CHECK(ctx, cudaMemcpyAsync(ood_h.data(), ood.p, ood_h.size() * sizeof(fe), cudaMemcpyDeviceToHost, st));
-  ZKL_CHECK(ctx, cudaMemcpyAsync(roots_h.data(), fri_roots.p, roots_h.size() * sizeof(fe), cudaMemcpyDeviceToHost, st));
-  ZKL_CHECK(ctx, cudaMemcpyAsync(rem_h.data(), rem_rev.p, rem_len * sizeof(fe), cudaMemcpyDeviceToHost, st));
-  ZKL_CHECK(ctx, cudaMemcpyAsync(&troot, tl.m.nodes.p + 1, sizeof(fe), cudaMemcpyDeviceToHost, st));
-  ZKL_CHECK(ctx, cudaMemcpyAsync(&croot, cmt.m.nodes.p + 1, sizeof(fe), cudaMemcpyDeviceToHost, st));
-  ZKL_CHECK(ctx, cudaMemcpyAsync(&z_h, z.p, sizeof(fe), cudaMemcpyDeviceToHost, st));
-  ZKL_CHECK(ctx, cudaMemcpyAsync(&flag_h, flag.p, sizeof(fe), cudaMemcpyDeviceToHost, st));
-  ZKL_CHECK(ctx, cudaStreamSynchronize(st));
+  const uint32_t *pos_h = mb->pos; const uint32_t cnt_h = mb->cnt;
+  const fe troot = mb->troot, croot = mb->croot, z_h = mb->z, flag_h = mb->flag;
   std::vector<uint32_t> pos(pos_h, pos_h + cnt_h);
 
   // One gather for everything the proof opens: queried rows, FRI layer values and all Merkle nodes.
   // Phase 1 lists (source buffer, element index) in the exact order the serializer consumes them.
-  std::vector<const fe *> g_src; std::vector<uint32_t> g_idx;
-  auto want = [&](const fe *src, uint32_t idx) { g_src.push_back(src); g_idx.push_back(idx); };
+  const fe **g_src = (const fe **)stage_alloc(ctx, max_open * sizeof(fe *));
+  uint32_t *g_idx = (uint32_t *)stage_alloc(ctx, max_open * 4);
+  fe *got = (fe *)stage_alloc(ctx, max_open * sizeof(fe));
+  if (!g_src || !g_idx || !got) { ctx->set_error("staging buffer exhausted"); return 1; }
+  size_t g_cnt = 0;
+  bool g_overflow = false;
+  auto want = [&](const fe *src, uint32_t idx) { if (g_cnt < max_open) { g_src[g_cnt] = src; g_idx[g_cnt] = idx; g_cnt++; } else g_overflow = true; };
   struct tree_job { std::vector<std::vector<node_ref>> plan; int depth; };
   auto plan_matrix = [&](const committed_matrix &m, tree_job &tj) {
     for (uint32_t p : pos) {
@@ -699,15 +703,15 @@ static int prove_segment_impl(zkl_ctx *ctx, const fe *trace_dev, size_t W, size_
       ev = f_ev[d + 1].p; dom = half; ndl = half_rows;
     }
   }
-  std::vector<fe> got(g_idx.size());
+  if (g_overflow) { ctx->set_error("opening plan larger than its bound"); return 1; }
   {
     dev_buf<const fe *> dsrc; dev_buf<uint32_t> didx; dev_buf<fe> dout;
-    ZKL_CHECK(ctx, dsrc.alloc(g_src.size())); ZKL_CHECK(ctx, didx.alloc(g_idx.size())); ZKL_CHECK(ctx, dout.alloc(g_idx.size()));
-    ZKL_CHECK(ctx, cudaMemcpyAsync(dsrc.p, g_src.data(), g_src.size() * sizeof(fe *), cudaMemcpyHostToDevice, st));
-    ZKL_CHECK(ctx, cudaMemcpyAsync(didx.p, g_idx.data(), g_idx.size() * 4, cudaMemcpyHostToDevice, st));
-    LAUNCH(ctx, k_gather_multi, ceil_div(g_idx.size(), 256), 256, 0, dsrc.p, didx.p, (int)g_idx.size(), dout.p);
-    ZKL_CHECK(ctx, cudaMemcpyAsync(got.data(), dout.p, got.size() * sizeof(fe), cudaMemcpyDeviceToHost, st));
-    ZKL_CHECK(ctx, cudaStreamSynchronize(st));
+    ZKL_CHECK(ctx, dsrc.alloc(g_cnt)); ZKL_CHECK(ctx, didx.alloc(g_cnt)); ZKL_CHECK(ctx, dout.alloc(g_cnt));
+    ZKL_CHECK(ctx, cudaMemcpyAsync(dsrc.p, g_src, g_cnt * sizeof(fe *), cudaMemcpyHostToDevice, st));
+    ZKL_CHECK(ctx, cudaMemcpyAsync(didx.p, g_idx, g_cnt * 4, cudaMemcpyHostToDevice, st));
+    LAUNCH(ctx, k_gather_multi, ceil_div(g_cnt, 256), 256, 0, dsrc.p, didx.p, (int)g_cnt, dout.p);
+    ZKL_CHECK(ctx, cudaMemcpyAsync(got, dout.p, g_cnt * sizeof(fe), cudaMemcpyDeviceToHost, st));
+    ZKL_TRY(ctx_wait(ctx));
   }
   size_t gp = 0;  // consumption cursor
 
@@ -716,15 +720,15 @@ static int prove_segment_impl(zkl_ctx *ctx, const fe *trace_dev, size_t W, size_
   wr.u8((uint8_t)pos.size());
   wr.u16((uint16_t)(32 * (2 + nl + 1)));
   wr.digest(troot); wr.digest(croot);
-  for (auto &r : roots_h) wr.digest(r);
+  for (size_t i = 0; i <= nl; i++) wr.digest(roots_h[i]);
   auto take_lists = [&](const tree_job &tj) {
     std::vector<std::vector<fe>> lists;
-    for (auto &l : tj.plan) { lists.emplace_back(got.begin() + gp, got.begin() + gp + l.size()); gp += l.size(); }
+    for (auto &l : tj.plan) { lists.emplace_back(got + gp, got + gp + l.size()); gp += l.size(); }
     return lists;
   };
   auto write_queries = [&](const committed_matrix &m, const tree_job &tj) {
     size_t cnt = pos.size() * m.width;
-    const fe *rows = got.data() + gp; gp += cnt;
+    const fe *rows = got + gp; gp += cnt;
     byte_writer pw; write_batch_proof_bytes(pw, tj.depth, take_lists(tj));
     wr.usize(cnt * 16); wr.bytes(rows, cnt * 16);
     wr.usize(pw.b.size()); wr.bytes(pw.b.data(), pw.b.size());
@@ -733,20 +737,20 @@ static int prove_segment_impl(zkl_ctx *ctx, const fe *trace_dev, size_t W, size_
   write_queries(cmt.m, tj_cons);
   // OodFrame: trace states (current || next), constraint evaluations (current || next)
   wr.u16((uint16_t)(2 * W * 16));
-  wr.bytes(ood_h.data(), W * 16); wr.bytes(ood_h.data() + W + C, W * 16);
+  wr.bytes(ood_h, W * 16); wr.bytes(ood_h + W + C, W * 16);
   wr.u16((uint16_t)(2 * C * 16));
-  wr.bytes(ood_h.data() + W, C * 16); wr.bytes(ood_h.data() + 2 * W + C, C * 16);
+  wr.bytes(ood_h + W, C * 16); wr.bytes(ood_h + 2 * W + C, C * 16);
   // FriProof
   wr.u8((uint8_t)nl);
   for (size_t d = 0; d < nl; d++) {
     size_t cnt = 2 * fri_counts[d];
-    const fe *vals = got.data() + gp; gp += cnt;
+    const fe *vals = got + gp; gp += cnt;
     byte_writer pw; write_batch_proof_bytes(pw, tj_fri[d].depth, take_lists(tj_fri[d]));
     wr.u32((uint32_t)(cnt * 16)); wr.bytes(vals, cnt * 16);
     wr.u32((uint32_t)pw.b.size()); wr.bytes(pw.b.data(), pw.b.size());
   }
   wr.u16((uint16_t)(rem_len * 16));
-  for (auto &c : rem_h) wr.felt(c);
+  for (size_t i = 0; i < rem_len; i++) wr.felt(rem_h[i]);
   wr.u8(1);
   wr.u64(nonce_h);
   STAGE_MARK();
@@ -766,14 +770,15 @@ static int prove_segment_impl(zkl_ctx *ctx, const fe *trace_dev, size_t W, size_
     for (int i = 0; i + 1 < evi && i < 9; i++) cudaEventElapsedTime(&summary->stage_ms[i], ctx->ev[i], ctx->ev[i + 1]);
     cudaEventElapsedTime(&summary->stage_ms[9], ctx->ev[12], ctx->ev[13]);   // trace LDE kernel alone
     cudaEventElapsedTime(&summary->stage_ms[10], ctx->ev[13], ctx->ev[14]);  // trace row-hash kernel alone
-    // composition degree overflow (constraints not satisfied): reported, not fatal — Winterfell only checks it in debug builds
-    if (!fe_is_zero(flag_h)) summary->stage_ms[11] = -1.0f;
+    summary->constraints_violated = fe_is_zero(flag_h) ? 0 : 1;
   }
   if (out_len) {
-    if (out_proof && wr.b.size() > *out_len) { *out_len = wr.b.size(); ctx->set_error("proof buffer too small"); return 2; }
+    if (out_proof && wr.b.size() > *out_len) { *out_len = wr.b.size(); ctx->set_error("proof buffer too small"); return ZKL_ERR_BUFFER_TOO_SMALL; }
     if (out_proof) memcpy(out_proof, wr.b.data(), wr.b.size());
     *out_len = wr.b.size();
   }
+  // composition degree overflow = some constraint does not vanish on the trace domain: the bytes above do not verify
+  if (!fe_is_zero(flag_h)) { ctx->set_error("the trace does not satisfy the AIR (composition polynomial degree overflow): the proof will not verify"); return ZKL_ERR_CONSTRAINTS_VIOLATED; }
   return 0;
 }
 
@@ -788,6 +793,32 @@ extern "C" int zkl_prove_segment(zkl_ctx *ctx, const zkl_fe *trace, size_t width
   dev_buf<fe> tr; ZKL_CHECK(ctx, tr.alloc(width * n));
   ZKL_CHECK(ctx, cudaMemcpyAsync(tr.p, trace, width * n * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream));
   return prove_segment_impl(ctx, tr.p, width, n, air, seed_elems, num_seed, opts, out_proof, out_len, summary);
+}
+
+// the same with ZkLispAir::new on this side of the boundary (host_air.inl): nothing about a segment is cached between calls
+static int prove_segment_pi_impl(zkl_ctx *ctx, const fe *trace_dev, size_t width, size_t n, const zkl_program *program, const zkl_public_inputs *pi,
+                                 const zkl_options *opts, uint8_t *out_proof, size_t *out_len, zkl_proof_summary *summary) {
+  auto t0 = std::chrono::steady_clock::now();
+  built_air b;
+  if (build_air_host(program, pi, width, n, opts, b)) { ctx->set_error(b.err); return 1; }
+  const float host_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  int rc = prove_segment_impl(ctx, trace_dev, width, n, &b.p, b.seed.data(), b.seed.size(), opts, out_proof, out_len, summary);
+  if (summary && (rc == 0 || rc == ZKL_ERR_CONSTRAINTS_VIOLATED)) summary->stage_ms[11] = host_ms;
+  return rc;
+}
+extern "C" int zkl_prove_segment_pi_dev(zkl_ctx *ctx, const void *trace_dev, size_t width, size_t n, const zkl_program *program,
+                                        const zkl_public_inputs *pi, const zkl_options *opts, uint8_t *out_proof, size_t *out_len,
+                                        zkl_proof_summary *summary) {
+  return prove_segment_pi_impl(ctx, (const fe *)trace_dev, width, n, program, pi, opts, out_proof, out_len, summary);
+}
+extern "C" int zkl_prove_segment_pi(zkl_ctx *ctx, const zkl_fe *trace, size_t width, size_t n, const zkl_program *program,
+                                    const zkl_public_inputs *pi, const zkl_options *opts, uint8_t *out_proof, size_t *out_len,
+                                    zkl_proof_summary *summary) {
+  ZKL_TRY(enter(ctx));
+  dev_buf<fe> tr; ZKL_CHECK(ctx, tr.alloc(width * n));
+  // the trace goes first so that its transfer overlaps the host-side AIR construction
+  ZKL_CHECK(ctx, cudaMemcpyAsync(tr.p, trace, width * n * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream));
+  return prove_segment_pi_impl(ctx, tr.p, width, n, program, pi, opts, out_proof, out_len, summary);
 }
 
 extern "C" int zkl_dev_alloc(zkl_ctx *ctx, size_t bytes, void **out_dev) { ZKL_CHECK(ctx, cudaSetDevice(ctx->device)); ZKL_CHECK(ctx, cudaMalloc(out_dev, bytes)); return 0; }
@@ -882,6 +913,61 @@ extern "C" int zkl_imad_peak(zkl_ctx *ctx, double *wide_macs_per_s) {
     if (rep && ms < best) best = ms;
   }
   *wide_macs_per_s = (double)blocks * 256.0 * iters * 8.0 / (best * 1e-3);
+  return 0;
+}
+// Saturating tcgen05.mma kind::i8 loop: the tensor-pipe roofline denominator of the sponge kernels, measured instead of derived.
+// One 128-thread CTA per SM; one thread issues `iters` MMAs (M 128, N 256, K 32, u8 x u8 -> s32, operands in shared memory,
+// K-major, no swizzle — the same operand path as tcperm.cuh) alternating between two TMEM accumulators, one commit at the end.
+#define TCPK_N 256
+#define TCPK_IDESC ((2u << 4) | ((uint32_t)(TCPK_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24))
+__global__ void __launch_bounds__(128) k_tc_i8_peak(int iters, unsigned int *sink) {
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
+  unsigned char *gen = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t a_tile = base, b_tile = base + 128 * 32, ctl = b_tile + TCPK_N * 32;
+  uint32_t *fill = reinterpret_cast<uint32_t *>(gen);
+  for (int i = threadIdx.x; i < (128 * 32 + TCPK_N * 32) / 4; i += 128) fill[i] = (uint32_t)(i + 1) * 2654435761u + blockIdx.x;
+  uint32_t *ctl_gen = reinterpret_cast<uint32_t *>(gen + 128 * 32 + TCPK_N * 32);
+  if (threadIdx.x < 32) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ctl + 16), "n"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (threadIdx.x == 32) { mbar_init(ctl, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = ctl_gen[4];
+  if (threadIdx.x == 0) {
+    const uint64_t adesc = tc_smem_desc(a_tile, 128 * 16, 128), bdesc = tc_smem_desc(b_tile, TCPK_N * 16, 128);
+#pragma unroll 4
+    for (int i = 0; i < iters; i++) tc_mma_i8(tmem + 256 * (i & 1), adesc, bdesc, TCPK_IDESC, i > 1);
+    tc_commit(ctl);
+  }
+  mbar_wait(ctl, 0);
+  tc_fence_after();
+  uint32_t v[16];
+  tmem_ld16(tmem + ((uint32_t)(32 * (threadIdx.x >> 5)) << 16), v);
+  tmem_wait_ld(v);
+  if (v[threadIdx.x & 15] == 0x7fffffffu) *sink = v[0];
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");
+}
+// returns dense u8 x u8 -> s32 tensor operations per second (2 per multiply-accumulate, whole GPU)
+extern "C" int zkl_tc_i8_peak(zkl_ctx *ctx, double *ops_per_s) {
+  ZKL_TRY(enter(ctx));
+  dev_buf<unsigned int> sink; ZKL_CHECK(ctx, sink.alloc(1));
+  const int iters = 16384, blocks = ctx->num_sms;
+  const size_t smem = 128 * 32 + TCPK_N * 32 + 256;
+  float best = 1e30f, ms = 0;
+  for (int rep = 0; rep < 4; rep++) {
+    ZKL_TRY(zkl_timer_start(ctx));
+    LAUNCH(ctx, k_tc_i8_peak, blocks, 128, smem, iters, sink.p);
+    ZKL_TRY(zkl_timer_stop(ctx, &ms));
+    if (rep && ms < best) best = ms;
+  }
+  *ops_per_s = (double)blocks * iters * 2.0 * 128.0 * TCPK_N * 32.0 / (best * 1e-3);
   return 0;
 }
 extern "C" int zkl_set_bulk_threshold(zkl_ctx *ctx, long sponges) { ctx->bulk_threshold = sponges; return 0; }

@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <array>
 #include <atomic>
+#include <chrono>
 #include <map>
 #include <mutex>
 
@@ -20,6 +21,8 @@
 
 static thread_local std::string g_create_error;   // zkl_last_error(NULL) reports the calling thread's failed zkl_ctx_create
 static std::mutex g_suite_mutex;
+struct device_suite { suite_consts consts; bool loaded = false; int users = 0; };
+static device_suite g_device_suite[64];
 
 #define LAUNCH(ctx, kernel, grid, block, smem, ...)                                 \
   do {                                                                              \
@@ -87,6 +90,17 @@ extern "C" int zkl_ctx_create(int device, zkl_ctx **out) {
     return 1;
   }
   if (device < 0 || device >= count) { g_create_error = "device index out of range"; return 1; }
+  // poseidon/hasher.rs:235-241: the reference reads the commitment hasher's round count from ZKL_POSEIDON_HASHER_ROUNDS
+  // (positive integers only, anything else means 27). The kernels are built for 27 rounds: refuse to run under another value
+  // rather than emit commitments the reference process would not reproduce.
+  if (const char *hr = getenv("ZKL_POSEIDON_HASHER_ROUNDS")) {
+    char *end = nullptr; unsigned long long v = strtoull(hr, &end, 10);
+    const bool parses = *hr && end && *end == 0 && hr[0] != '-' && hr[0] != '+' && hr[0] != ' ';
+    if (parses && v > 0 && v != ZKL_ROUNDS) {
+      g_create_error = std::string("ZKL_POSEIDON_HASHER_ROUNDS=") + hr + " is set: this library implements the 27-round commitment hasher only";
+      return 1;
+    }
+  }
   zkl_ctx *c = new zkl_ctx();
   c->device = device;
   if ((e = cudaSetDevice(device)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete c; return 1; }
@@ -97,6 +111,7 @@ extern "C" int zkl_ctx_create(int device, zkl_ctx **out) {
   if (const char *e = getenv("ZKL_TC_GRID_CAP")) { int v = atoi(e); if (v > 0 && v <= c->num_sms) c->tc_grid_cap = v; }   // experiment knob
   if (const char *e = getenv("ZKL_COOP_PATH")) { int v = atoi(e); if (v >= 0 && v <= 2) c->coop_path = v; }   // experiment knobs (A/B runs of bench.py)
   if (const char *e = getenv("ZKL_TC_HALF_TILES")) c->tc_half_tiles = atoi(e) != 0;
+  if (const char *e = getenv("ZKL_WAIT_MODE")) { int v = atoi(e); if (v >= 0 && v <= 2) c->wait_mode = v; }
   if (const char *e = getenv("ZKL_NTT_PATH")) { int v = atoi(e); if (v >= 0 && v <= 2) c->ntt_path = v; }
   if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) {
     g_create_error = cudaGetErrorString(e); delete c; return 1;
@@ -155,13 +170,14 @@ extern "C" int zkl_ctx_create(int device, zkl_ctx **out) {
   return 0;
 }
 
-static void air_cache_drop(const zkl_ctx *ctx);
 extern "C" void zkl_ctx_destroy(zkl_ctx *ctx) {
   if (!ctx) return;
   g_ctx_per_device[ctx->device & 63]--;
+  if (ctx->suite_loaded) { std::lock_guard<std::mutex> g(g_suite_mutex); g_device_suite[ctx->device & 63].users--; }
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  air_cache_drop(ctx);
+  if (ctx->stage_h) cudaFreeHost(ctx->stage_h);
+  if (ctx->wait_ev) cudaEventDestroy(ctx->wait_ev);
   if (tl_stream == ctx->stream) { tl_stream = nullptr; tl_pool = nullptr; tl_stream_set = false; }
   cudaStreamSynchronize(ctx->stream);
   for (auto &kv : ctx->tables) { cudaFree(kv.second.wpow); }
@@ -183,16 +199,27 @@ extern "C" int zkl_suite_load(zkl_ctx *ctx, const zkl_suite *s) {
   for (int i = 0; i < 12; i++) for (int j = 0; j < 12; j++) h.mds[i][j] = fe_from_abi(s->mds[i][j]);
   for (int r = 0; r < ZKL_ROUNDS; r++) for (int j = 0; j < 12; j++) h.rc[r][j] = fe_from_abi(s->rc[r][j]);
   std::lock_guard<std::mutex> g(g_suite_mutex);
-  ZKL_CHECK(ctx, cudaMemcpyToSymbol(c_suite, &h, sizeof h));
-  ZKL_CHECK(ctx, cudaMemcpyToSymbol(g_suite, &h, sizeof h));
   // tc_epilogue packs accumulator pairs into 32 bits: verify the bound for these constants, else use the integer pipe
   ctx->tc_ok = tc_max_accumulator(h) <= TC_ACC_MAX;
   if (!ctx->tc_ok) ctx->hash_path = 1;
+  // The suite lives in device-global symbols shared by every context of a device (the commitment hasher has ONE suite,
+  // suite_id = [0;32], hasher.rs:23). The same constants again: nothing is rewritten under kernels other contexts may have
+  // in flight. Different constants while other contexts hold the first suite: refused.
+  device_suite &ds = g_device_suite[ctx->device & 63];
+  if (ds.loaded && memcmp(&ds.consts, &h, sizeof h) == 0) { ds.users += ctx->suite_loaded ? 0 : 1; ctx->suite_loaded = true; return 0; }
+  if (ds.loaded && ds.users > (ctx->suite_loaded ? 1 : 0)) {
+    ctx->set_error("another context on this device holds a different hasher suite: the suite is per device (include/zkl_b200.h)");
+    return 1;
+  }
+  ZKL_CHECK(ctx, cudaDeviceSynchronize());   // no kernel of this (only) user may still read the old constants
+  ZKL_CHECK(ctx, cudaMemcpyToSymbol(c_suite, &h, sizeof h));
+  ZKL_CHECK(ctx, cudaMemcpyToSymbol(g_suite, &h, sizeof h));
   {  // byte image of the MDS matrix for the tensor-core permutation (tcperm.cuh)
     suite_consts *gs; ZKL_CHECK(ctx, cudaGetSymbolAddress((void **)&gs, g_suite));
     LAUNCH(ctx, k_build_mds_bytes, ceil_div(TC_KCH * TC_N, 128), 128, 0, gs);
     ZKL_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
   }
+  ds.consts = h; ds.loaded = true; ds.users = 1;
   ctx->suite_loaded = true;
   return 0;
 }
@@ -610,5 +637,6 @@ extern "C" int zkl_evaluate_columns(zkl_ctx *ctx, const zkl_fe *polys, size_t nc
   return 0;
 }
 
+#include "host_air.inl"
 #include "api_stark.inl"
 #include "api_replay.inl"

@@ -14,8 +14,87 @@ from . import capi, params
 
 
 def hasher_suite():
-    """Commitment/coin suite, suite_id = [0;32] (poseidon/hasher.rs:23)."""
+    """Commitment/coin suite, suite_id = [0;32] (poseidon/hasher.rs:23), Python-integer derivation (params.py)."""
     return params.get_poseidon_suite(params.HASHER_SUITE_ID)
+
+
+_HASHER_SUITE_C = None
+_PROGRAMS = {}
+_PROGRAMS_LOCK = threading.Lock()
+
+
+def hasher_suite_c() -> capi.Suite:
+    """The same suite derived in native code (`zkl_suite_derive`); computed once per process."""
+    global _HASHER_SUITE_C
+    if _HASHER_SUITE_C is None:
+        s = capi.Suite()
+        if capi.load_library().zkl_suite_derive((C.c_uint8 * 32)(), C.byref(s)):
+            raise capi.ZklError("zkl_suite_derive failed")
+        _HASHER_SUITE_C = s
+    return _HASHER_SUITE_C
+
+
+def program_constants(program_id: bytes, program_commitment: bytes, cache: bool = True) -> capi.Program:
+    """`zkl_program_derive`: the per-program constants ZkLispAir::new needs (vm/air/mod.rs:129-176). One derivation per
+    program, shared by all of its segments (the reference keeps the suites in a process-global cache, poseidon/mod.rs:47)."""
+    key = (bytes(program_id), bytes(program_commitment))
+    if cache:
+        with _PROGRAMS_LOCK:
+            if key in _PROGRAMS:
+                return _PROGRAMS[key]
+    prog = capi.Program()
+    a = (C.c_uint8 * 32).from_buffer_copy(key[0])
+    b = (C.c_uint8 * 32).from_buffer_copy(key[1])
+    if capi.load_library().zkl_program_derive(a, b, C.byref(prog)):
+        raise capi.ZklError("zkl_program_derive failed (no valid 12x12 MDS for this program id)")
+    if cache:
+        with _PROGRAMS_LOCK:
+            _PROGRAMS[key] = prog
+    return prog
+
+
+def public_inputs_to_c(air_pi: "air_mod.AirPublicInputs") -> capi.PublicInputsC:
+    """AirPublicInputs (lib.rs:74-96) as the plain struct the C ABI takes."""
+    core = air_pi.core
+    p = capi.PublicInputsC()
+    p.feature_mask, p.segment_feature_mask = core.feature_mask, air_pi.segment_feature_mask
+    p.merkle_root[:] = bytes(core.merkle_root)
+    p.vm_expected_bytes[:] = bytes(core.vm_expected_bytes)
+    p.vm_out_reg, p.vm_out_row = core.vm_out_reg, core.vm_out_row
+    slots = air_mod.encode_main_args_to_slots(core.main_args)
+    if len(slots) > capi.MAX_MAIN_SLOTS:
+        raise ValueError("too many main_args slots")
+    p.num_main_slots = len(slots)
+    for j, v in enumerate(slots):
+        p.main_slots[j] = capi.Fe.of(v)
+    p.vm_usage_mask, p.ram_delta_clk_bits = air_pi.vm_usage_mask, air_pi.ram_delta_clk_bits
+    p.pc_init = capi.Fe.of(air_pi.pc_init)
+    p.ram_gp_unsorted_in, p.ram_gp_unsorted_out = capi.Fe.of(air_pi.ram_gp_unsorted_in), capi.Fe.of(air_pi.ram_gp_unsorted_out)
+    p.ram_gp_sorted_in, p.ram_gp_sorted_out = capi.Fe.of(air_pi.ram_gp_sorted_in), capi.Fe.of(air_pi.ram_gp_sorted_out)
+    for i in range(3):
+        p.rom_s_in[i], p.rom_s_out[i] = capi.Fe.of(air_pi.rom_s_in[i]), capi.Fe.of(air_pi.rom_s_out[i])
+    return p
+
+
+class NativeAir:
+    """`zkl_air_build`: the data ZkLispAir::new derives, built by the library from the public inputs."""
+
+    def __init__(self, program: capi.Program, pi: capi.PublicInputsC, width: int, n: int, options: "air_mod.ProofOptions"):
+        lib = capi.load_library()
+        cap_a = (n // 32) * 141 + 64
+        self.assertions = (capi.Assertion * cap_a)()
+        self.seed = np.zeros((64, 2), dtype=np.uint64)
+        self.params = capi.AirParams()
+        na, ns = C.c_size_t(cap_a), C.c_size_t(64)
+        err = C.create_string_buffer(256)
+        o = options.to_c()
+        if lib.zkl_air_build(C.byref(program), C.byref(pi), width, n, C.byref(o), C.byref(self.params), self.assertions, C.byref(na),
+                             self.seed.ctypes.data, C.byref(ns), err, 256):
+            raise ValueError(err.value.decode())
+        self.num_assertions, self.seed = na.value, self.seed[:ns.value]
+        self.num_transition, self.ce_blowup = self.params.num_transition, self.params.ce_blowup
+        self.num_composition_cols = self.params.num_composition_cols
+        self.num_constraints = self.num_transition + self.num_assertions
 
 
 def as_fe_array(a) -> np.ndarray:
@@ -50,8 +129,7 @@ class Context:
         self.device = device
         self._lock = threading.Lock()
         if load_suite:
-            s = capi.suite_to_c(hasher_suite())
-            self._check(self.lib.zkl_suite_load(self.h, C.byref(s)))
+            self._check(self.lib.zkl_suite_load(self.h, C.byref(hasher_suite_c())))
 
     def _check(self, rc):
         if rc:
@@ -238,11 +316,14 @@ def _query(ctx, fn, handle, positions, width):
 class ZkProver:
     """Mirror of `ZkProver` / `ZkWinterfellProver` (prove.rs:104-242, 425-517) over the GPU path."""
 
-    def __init__(self, ctx: Context, options: air_mod.ProofOptions, air_pi: air_mod.AirPublicInputs):
+    def __init__(self, ctx: Context, options: air_mod.ProofOptions, air_pi: air_mod.AirPublicInputs, cache_program: bool = True):
+        """`cache_program=False` re-derives the per-program constants on every call instead of sharing them across the
+        program's segments (measurement of a first-ever prove, bench.py `e2e_cold`)."""
         self.ctx, self.options, self.air_pi = ctx, options, air_pi
         self.last_summary = None
-        self._cache = {}
         self.preflight = "off"
+        self._buf = None
+        self._cache_program = cache_program
 
     def with_preflight_mode(self, mode: str) -> "ZkProver":
         """prove.rs:160-163: "off" | "console" | "json" (zk-lisp-proof/src/frontend.rs:23-27)."""
@@ -251,13 +332,13 @@ class ZkProver:
         self.preflight = mode
         return self
 
-    def _air(self, width, n):
-        """(Air, zkl_air_params, seed elements) for this trace shape; built once per prover like `Air::new`."""
-        key = (width, n)
-        if key not in self._cache:
-            a = air_mod.Air(width, n, self.air_pi, self.options)
-            self._cache[key] = (a, a.to_c(), ints_to_fe(a.seed_elements()))
-        return self._cache[key]
+    def _program(self) -> capi.Program:
+        core = self.air_pi.core
+        return program_constants(core.program_id, core.program_commitment, cache=self._cache_program)
+
+    def native_air(self, width, n) -> NativeAir:
+        """`ZkLispAir::new` for this trace shape through `zkl_air_build` (hook-level calls; `prove` builds it inside the library)."""
+        return NativeAir(self._program(), public_inputs_to_c(self.air_pi), width, n, self.options)
 
     # hook 1 (prove.rs:454-474)
     def new_trace_lde(self, trace: np.ndarray):
@@ -273,11 +354,11 @@ class ZkProver:
 
     # hook 2 (prove.rs:476-492) + ConstraintEvaluator::evaluate
     def evaluate_constraints(self, trace_lde: TraceLde, coeffs: np.ndarray) -> np.ndarray:
-        a, ap, _ = self._air(trace_lde.width, trace_lde.n)
+        a = self.native_air(trace_lde.width, trace_lde.n)
         cc = as_fe_array(coeffs)
         assert cc.shape[0] == a.num_constraints
         out = np.zeros((trace_lde.n * a.ce_blowup, 2), dtype=np.uint64)
-        self.ctx._check(self.ctx.lib.zkl_eval_constraints(self.ctx.h, trace_lde.h, C.byref(ap), cc.ctypes.data, out.ctypes.data))
+        self.ctx._check(self.ctx.lib.zkl_eval_constraints(self.ctx.h, trace_lde.h, C.byref(a.params), cc.ctypes.data, out.ctypes.data))
         return out
 
     # hook 3 (prove.rs:494-516)
@@ -292,30 +373,39 @@ class ZkProver:
         return ConstraintCommitment(self.ctx, h, num_cols, root.tobytes(), poly), poly
 
     # whole proof (prove.rs:174-242)
-    def prove(self, trace, dev_ptr=None, shape=None) -> bytes:
+    def prove(self, trace, dev_ptr=None, shape=None, allow_invalid: bool = False) -> bytes:
         """`trace`: (W, n, 2) uint64 host array, column-major like winterfell's ColMatrix; or pass
-        `dev_ptr` + `shape=(W, n)` for a trace already resident in device memory."""
+        `dev_ptr` + `shape=(W, n)` for a trace already resident in device memory. The AIR instance and the coin seed are
+        built inside the library from the public inputs, per call (`zkl_prove_segment_pi`). A trace that violates the AIR
+        raises (the reference's debug builds panic in Winterfell's degree check) unless `allow_invalid`."""
         if dev_ptr is None:
             t = as_fe_array(trace)
             width, n = t.shape[0], t.shape[1]
         else:
             width, n = shape
-        a, ap, seed = self._air(width, n)
         if self.preflight != "off":                  # prove.rs:186-211: check the trace against the AIR first
             if dev_ptr is not None:
                 raise ValueError("preflight walks the host trace: pass the trace array, not a device pointer")
             from . import preflight
-            preflight.run(self.preflight, a, t)
-        o = self.options.to_c()
-        cap = C.c_size_t(4 << 20)
-        buf = np.zeros(cap.value, dtype=np.uint8)
+            preflight.run(self.preflight, air_mod.Air(width, n, self.air_pi, self.options), t)
+        prog, pi, o = self._program(), public_inputs_to_c(self.air_pi), self.options.to_c()
+        if self._buf is None:
+            self._buf = np.empty(1 << 20, dtype=np.uint8)   # reused across calls; grown when the library asks for more
         summ = capi.ProofSummary()
-        if dev_ptr is None:
-            rc = self.ctx.lib.zkl_prove_segment(self.ctx.h, t.ctypes.data, width, n, C.byref(ap), seed.ctypes.data,
-                                                seed.shape[0], C.byref(o), buf.ctypes.data, C.byref(cap), C.byref(summ))
-        else:
-            rc = self.ctx.lib.zkl_prove_segment_dev(self.ctx.h, dev_ptr, width, n, C.byref(ap), seed.ctypes.data,
-                                                    seed.shape[0], C.byref(o), buf.ctypes.data, C.byref(cap), C.byref(summ))
-        self.ctx._check(rc)
+        lib = self.ctx.lib
+        for _ in range(2):
+            cap = C.c_size_t(self._buf.shape[0])
+            if dev_ptr is None:
+                rc = lib.zkl_prove_segment_pi(self.ctx.h, t.ctypes.data, width, n, C.byref(prog), C.byref(pi), C.byref(o),
+                                              self._buf.ctypes.data, C.byref(cap), C.byref(summ))
+            else:
+                rc = lib.zkl_prove_segment_pi_dev(self.ctx.h, dev_ptr, width, n, C.byref(prog), C.byref(pi), C.byref(o),
+                                                  self._buf.ctypes.data, C.byref(cap), C.byref(summ))
+            if rc != capi.ERR_BUFFER_TOO_SMALL:
+                break
+            self._buf = np.empty(cap.value + (cap.value >> 2), dtype=np.uint8)
         self.last_summary = summ
-        return buf[:cap.value].tobytes()
+        if rc == capi.ERR_CONSTRAINTS_VIOLATED and allow_invalid:
+            rc = 0
+        self.ctx._check(rc)
+        return self._buf[:cap.value].tobytes()

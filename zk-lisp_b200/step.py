@@ -163,6 +163,7 @@ class InnerProof:
     fri_remainder: bytes
     fri_num_partitions: int
     pow_nonce: int
+    batching: Tuple[int, int] = (0, 0)
 
     @property
     def lde_domain_size(self) -> int:
@@ -212,7 +213,7 @@ class InnerProof:
         r.take(r.u8())                                      # field modulus bytes
         num_constraints = r.usize()
         q, blowup, grind, ext, folding, rem_deg = (r.u8() for _ in range(6))
-        r.take(2)                                           # batching methods (constraints, DEEP)
+        batching = tuple(r.take(2))                         # batching methods (constraints, DEEP); 0 = Linear
         num_partitions, hash_rate = r.u8(), r.u8()
         if blowup == 0 or folding < 2:
             raise InvalidInput("failed to decode inner Winterfell proof in step proof")
@@ -233,9 +234,11 @@ class InnerProof:
         nonce = r.uint(8)
         if r.i != len(r.b):
             raise InvalidInput("failed to decode inner Winterfell proof in step proof")
-        return InnerProof(main_width, aux_width, 1 << log_n, num_constraints, q, blowup, grind, ext, folding, rem_deg,
-                          num_partitions, hash_rate, unique, commitments, tq_values, tq_paths, cq_values, cq_paths,
-                          ood_trace, ood_cons, layers, remainder, fri_parts, nonce)
+        p = InnerProof(main_width, aux_width, 1 << log_n, num_constraints, q, blowup, grind, ext, folding, rem_deg,
+                       num_partitions, hash_rate, unique, commitments, tq_values, tq_paths, cq_values, cq_paths,
+                       ood_trace, ood_cons, layers, remainder, fri_parts, nonce)
+        p.batching = batching
+        return p
 
 
 def _rows(values: bytes, width: int, count: int) -> List[List[int]]:

@@ -74,8 +74,58 @@ def ood_consistency(hasher, step: StepProof, air: A.Air):
     return lhs, rhs, z
 
 
-def verify_step(hasher, step: StepProof, segment_feature_mask: int = 0) -> R.FsChallenges:
-    """Full verification of one step proof; raises InvalidInput naming the first check that fails."""
+HASHER_COLLISION_RESISTANCE = 128   # poseidon/hasher.rs:60
+GRINDING_CONTRIBUTION_FLOOR = 80    # prove.rs:1185
+
+
+def conjectured_security_bits(num_queries: int, blowup: int, grinding: int, extension_degree: int, lde_domain_size: int) -> int:
+    """Conjectured security of a set of proof options, the quantity `AcceptableOptions::MinConjecturedSecurity(min_bits)` bounds
+    when the reference verifies (prove.rs:738, 814). zk-lisp restates the estimate at prove.rs:1177-1195 (128 field bits per
+    extension degree, log2(blowup) bits per query, grinding counted only from 80 query bits up, minus one, capped by the hasher's
+    collision resistance); winter-air additionally charges the field for the LDE domain size (field bits - log2(N)) [WF-mem].
+    The stricter of the two is returned."""
+    if blowup < 2 or blowup & (blowup - 1) or lde_domain_size < 1:
+        return 0
+    field_security = 128 * extension_degree - (lde_domain_size.bit_length() - 1)
+    query_security = (blowup.bit_length() - 1) * num_queries
+    if query_security >= GRINDING_CONTRIBUTION_FLOOR:
+        query_security += grinding
+    return max(min(min(field_security, query_security) - 1, HASHER_COLLISION_RESISTANCE), 0)
+
+
+def check_acceptable(step: StepProof, min_bits: int) -> int:
+    """What the stock verifier settles before any cryptography: the proof's self-declared options must reach `min_bits` of
+    conjectured security (a forged proof declaring q = 1, grind = 0, blowup = 2 replays consistently otherwise), must be the
+    options zk-lisp proves steps with (FieldExtension::None, prove.rs:967; Linear batching, :970-971; folding factor 2, :968) and
+    every field element of the proof must be canonical (winter-math's reader rejects values >= p). Returns the security level."""
+    v = step.proof.inner
+    if v.num_queries == 0 or v.num_unique_queries == 0:
+        raise InvalidInput("proof declares no queries")
+    if v.field_extension != 1:
+        raise InvalidInput("step proofs use FieldExtension::None")
+    if tuple(v.batching) != (0, 0):
+        raise InvalidInput("step proofs use Linear batching")
+    if v.fri_folding != 2:
+        raise InvalidInput("step proofs use FRI folding factor 2")
+    if v.blowup < 2 or v.blowup & (v.blowup - 1):
+        raise InvalidInput("blowup factor must be a power of two >= 2")
+    bits = conjectured_security_bits(v.num_queries, v.blowup, v.grinding, 1, v.lde_domain_size)
+    if bits < min_bits:
+        raise InvalidInput(f"proof options give {bits} bits of conjectured security, below the required {min_bits}")
+    blobs = [v.trace_query_values, v.constraint_query_values, v.ood_trace, v.ood_constraints, v.fri_remainder] + [vals for vals, _ in v.fri_layers]
+    for blob in blobs:
+        if len(blob) % 16:
+            raise InvalidInput("field element section of the proof is not a multiple of 16 bytes")
+        for i in range(0, len(blob), 16):
+            if int.from_bytes(blob[i:i + 16], "little") >= P:
+                raise InvalidInput("non-canonical field element in the proof")
+    return bits
+
+
+def verify_step(hasher, step: StepProof, min_bits: int, segment_feature_mask: int = 0) -> R.FsChallenges:
+    """Full verification of one step proof; raises InvalidInput naming the first check that fails. `min_bits` is mandatory, like
+    the reference's `min_security_bits` (zk-lisp-proof/src/lib.rs:44,59: 128 in release builds, 64 in debug builds)."""
+    check_acceptable(step, min_bits)
     # the order of winter-verifier: the OOD frame is checked against the constraints BEFORE it is absorbed by the coin
     lhs, rhs, z = ood_consistency(hasher, step, air_of(step, segment_feature_mask))
     if lhs != rhs:
