@@ -429,3 +429,55 @@ def test_lde_4096_on_tensor_cores(ctx, oracle):
     ctx._check(ctx.lib.zkl_set_ntt_path(ctx.h, 1)); b = ctx.interpolate_columns(wide)
     ctx._check(ctx.lib.zkl_set_ntt_path(ctx.h, 0))
     assert np.array_equal(a, b)
+
+
+# ---- full-size byte parity: the configuration bench.py times, and a RAM-on trace with every gadget live ------------------------
+def test_full_size_proof_bytes_match_the_checker(ctx, zkl):
+    """n = 4096, W = 204, q = 64, blowup 16, grind 16 (segment 0 of bench.py's program) and n = 4096, W = 212 with RAM on, all nine
+    vm_usage_mask bits and the delta_clk gadget (tests/rollup_bench_ram.rs:402 shape), plus the full 219-column layout with a Merkle
+    path: the GPU proof must be the checker's proof byte for byte. The checker's side is minutes of CPU per case, so it comes from
+    tests/golden/segment_golden.json (tests/golden/make_segment_golden.py; the CPU suite checks the fixture against the generators)."""
+    import hashlib
+    import json
+    import os
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "segment_golden.json")))
+    for name, rec in gold.items():
+        trace, air_pi, opts = getattr(synth, rec["gen"])(**rec["kw"])
+        prover = zkl.ZkProver(ctx, opts, air_pi)
+        proof = prover.prove(trace)
+        s = prover.last_summary
+        assert s.constraints_violated == 0, name
+        assert bytes(s.trace_root).hex() == rec["trace_root"], name
+        assert bytes(s.constraint_root).hex() == rec["constraint_root"], name
+        assert s.pow_nonce == rec["pow_nonce"] and list(s.positions[:s.num_unique_queries]) == rec["positions"], name
+        assert len(proof) == rec["proof_len"] and hashlib.blake2b(proof, digest_size=16).hexdigest() == rec["proof_blake2b"], name
+
+
+def test_rich_segment_live_against_the_checker(ctx, zkl, oracle):
+    """RAM + Merkle + every ALU gadget, proven on the GPU and by the checker in the same run (n = 1024, fresh seed): bytes equal,
+    the restated verifier accepts, and the usage-mask scan kernel finds the masks the trace generator recorded."""
+    import ctypes as C
+    if ctx.hash_mode != "default":
+        pytest.skip("one hashing mode is enough for the live run (the golden cases run under all four)")
+    n = 1024
+    trace, air_pi, opts = synth.rich_segment(n=n, seed=23, merkle=True, queries=16, grind=6)
+    a, ac, oc, seed = _air(zkl, trace, air_pi, opts)
+    prover = zkl.ZkProver(ctx, opts, air_pi)
+    proof = prover.prove(trace)
+    assert proof == oracle.prove_segment(trace, ac, seed, oc)
+    rc, msg = oracle.verify_segment(proof, trace.shape[0], n, ac, seed, oc)
+    assert rc == 0, msg
+    dev = C.c_void_p()
+    ctx._check(ctx.lib.zkl_dev_alloc(ctx.h, trace.nbytes, C.byref(dev)))
+    ctx._check(ctx.lib.zkl_dev_upload(ctx.h, dev, trace.ctypes.data, trace.nbytes))
+    m, b = C.c_uint32(), C.c_uint32()
+    cc = a.cols.to_c()
+    ctx._check(ctx.lib.zkl_usage_mask_dev(ctx.h, dev, trace.shape[0], n, C.byref(cc), 1, C.byref(m), C.byref(b)))
+    ctx._check(ctx.lib.zkl_dev_free(ctx.h, dev))
+    assert (m.value, b.value) == (air_pi.vm_usage_mask, air_pi.ram_delta_clk_bits) == (0x1FF, air_pi.ram_delta_clk_bits)
+    # a RAM witness off by one: the composition polynomial overflows its degree and the call refuses to hand out the proof
+    bad = trace.copy()
+    first_sorted = next(r for r in range(n) if trace[a.cols.ram_start, r, 0] == 1)
+    bad[a.cols.ram_start + 3, first_sorted, 0] ^= np.uint64(1)
+    with pytest.raises(zkl.capi.ZklError, match="does not satisfy the AIR"):
+        prover.prove(bad)
