@@ -197,7 +197,9 @@ struct air_device_state {
 // contexts share the device — a pool of proving threads, several ranks per box — the thread blocks on an event created with
 // cudaEventBlockingSync, so waiting provers do not burn the cores the other provers' host code needs.
 static int ctx_wait(zkl_ctx *ctx) {
-  const bool block = ctx->wait_mode == 2 || (ctx->wait_mode == 0 && g_ctx_per_device[ctx->device & 63].load(std::memory_order_relaxed) > 1);
+  // automatic: block when this process runs more proving contexts than half the cores it may use (spinning waiters would then
+  // take the cores the other provers' host code needs); a blocking wait costs ~0.3 ms of wake-up latency per proof otherwise
+  const bool block = ctx->wait_mode == 2 || (ctx->wait_mode == 0 && 2 * g_ctx_total.load(std::memory_order_relaxed) > g_host_cores);
   if (!block) { ZKL_CHECK(ctx, cudaStreamSynchronize(ctx->stream)); return 0; }
   if (!ctx->wait_ev) ZKL_CHECK(ctx, cudaEventCreateWithFlags(&ctx->wait_ev, cudaEventBlockingSync | cudaEventDisableTiming));
   ZKL_CHECK(ctx, cudaEventRecord(ctx->wait_ev, ctx->stream));

@@ -1,6 +1,7 @@
 // zkl_b200.cu — C ABI (include/zkl_b200.h) over the sm_100a kernels. Single translation unit so the
 // __constant__ hasher suite is shared by every kernel without relocatable device code.
 // No CPU fallback: every entry point launches device work; a missing device fails at ctx creation.
+#include <sched.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -53,6 +54,8 @@ static device_suite g_device_suite[64];
 // Which low-latency sponge a context uses (coop_path 0 = decide by how many contexts share the device: a lone prover is
 // latency-bound and takes the 64-thread groups, a pool of provers is SM-time-bound and takes the 16-thread groups).
 static std::atomic<int> g_ctx_per_device[64];
+static std::atomic<int> g_ctx_total{0};
+static int g_host_cores = 1;   // cores this process may run on (sched_getaffinity), read at context creation
 static inline bool use_quad(const zkl_ctx *ctx) {
   if (ctx->coop_path == 1) return false;
   if (ctx->coop_path == 2) return true;
@@ -166,6 +169,8 @@ extern "C" int zkl_ctx_create(int device, zkl_ctx **out) {
     if ((e = cudaStreamSynchronize(c->stream)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete c; return 1; }
   }
   g_ctx_per_device[device & 63]++;
+  g_ctx_total++;
+  { cpu_set_t set; CPU_ZERO(&set); g_host_cores = sched_getaffinity(0, sizeof set, &set) == 0 ? std::max(CPU_COUNT(&set), 1) : 1; }
   *out = c;
   return 0;
 }
@@ -173,6 +178,7 @@ extern "C" int zkl_ctx_create(int device, zkl_ctx **out) {
 extern "C" void zkl_ctx_destroy(zkl_ctx *ctx) {
   if (!ctx) return;
   g_ctx_per_device[ctx->device & 63]--;
+  g_ctx_total--;
   if (ctx->suite_loaded) { std::lock_guard<std::mutex> g(g_suite_mutex); g_device_suite[ctx->device & 63].users--; }
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
