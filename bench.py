@@ -286,10 +286,14 @@ def main():
         tot_ev, tot_wall = float(np.sum(ev_ms)), float(np.sum(wall_ms))
         if world > 1:
             t = torch.tensor([tot_ev, tot_wall], device="cuda", dtype=torch.float64)
+            every = [torch.zeros_like(t) for _ in range(world)]
+            dist.all_gather(every, t)
+            per_rank[mode] = [round(float(x[0]) / steps, 2) for x in every]
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             tot_ev, tot_wall = float(t[0]), float(t[1])
         return tot_ev, tot_wall, sum(w.ctx.launches for w in workers) - launches0, clocks
 
+    per_rank = {}
     for _ in range(args.warmup):
         run_step(workers, "resident")
     reference_digests = [list(w.digests) for w in workers]   # from the last warm-up step
@@ -413,6 +417,7 @@ def main():
                        "l2": "per-step working set 16 x 250 MB LDE matrices >> 126 MB L2 (no flush needed)",
                        "published_reference": "109.567 s on Apple M3 Max for the same 65536 rows (BASELINE.md), different hardware"},
             "wall_ms_per_step": wall_total / args.steps,
+            "ms_per_step_per_rank": per_rank.get("resident"),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ev / args.steps, "wall_ms_per_step": e2e_wall / args.steps,
                     "per_segment_air_build": "inside every call (zkl_prove_segment_pi): assertions, degrees and coin seed from the public inputs; no per-segment cache",

@@ -193,18 +193,26 @@ struct air_device_state {
   dev_buf<fe> coset_consts, u, bpoly;
   int nslots = 0, ngroups = 0;
 };
-// Host wait for everything enqueued on the context's stream. A lone prover spins (lowest wake-up latency); when several
-// contexts share the device — a pool of proving threads, several ranks per box — the thread blocks on an event created with
-// cudaEventBlockingSync, so waiting provers do not burn the cores the other provers' host code needs.
+// Host wait for everything enqueued on the context's stream (ZKL_WAIT_MODE / ctx->wait_mode): 1 = spin (cudaStreamSynchronize:
+// lowest latency, one core per waiting prover), 2 = block on a cudaEventBlockingSync event (no core, ~0.3 ms of wake-up latency per
+// wait), 3 = poll the event and sched_yield() between polls. 0 = automatic: spin while this process has at least two cores per
+// proving context, poll-and-yield otherwise (a pool of provers or several ranks sharing the host's cores).
 static int ctx_wait(zkl_ctx *ctx) {
   // automatic: block when this process runs more proving contexts than half the cores it may use (spinning waiters would then
   // take the cores the other provers' host code needs); a blocking wait costs ~0.3 ms of wake-up latency per proof otherwise
-  const bool block = ctx->wait_mode == 2 || (ctx->wait_mode == 0 && 2 * g_ctx_total.load(std::memory_order_relaxed) > g_host_cores);
-  if (!block) { ZKL_CHECK(ctx, cudaStreamSynchronize(ctx->stream)); return 0; }
+  const bool crowded = 2 * g_ctx_total.load(std::memory_order_relaxed) > g_host_cores;
+  const int mode = ctx->wait_mode ? ctx->wait_mode : (crowded ? 3 : 1);
+  if (mode == 1) { ZKL_CHECK(ctx, cudaStreamSynchronize(ctx->stream)); return 0; }
   if (!ctx->wait_ev) ZKL_CHECK(ctx, cudaEventCreateWithFlags(&ctx->wait_ev, cudaEventBlockingSync | cudaEventDisableTiming));
   ZKL_CHECK(ctx, cudaEventRecord(ctx->wait_ev, ctx->stream));
-  ZKL_CHECK(ctx, cudaEventSynchronize(ctx->wait_ev));
-  return 0;
+  if (mode == 2) { ZKL_CHECK(ctx, cudaEventSynchronize(ctx->wait_ev)); return 0; }
+  // mode 3: poll and yield — no wake-up latency while cores are free, and a waiting prover hands its core to any runnable one
+  for (;;) {
+    cudaError_t e = cudaEventQuery(ctx->wait_ev);
+    if (e == cudaSuccess) return 0;
+    if (e != cudaErrorNotReady) { ZKL_CHECK(ctx, e); }
+    sched_yield();
+  }
 }
 // Pinned host staging, one region per context, handed out by a bump pointer that restarts with every entry point:
 // parameter uploads and result downloads of a call never pass through pageable memory (a cudaMemcpyAsync on pageable memory

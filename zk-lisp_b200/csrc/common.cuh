@@ -57,7 +57,7 @@ struct zkl_ctx {
   std::map<size_t, std::pair<void *, void *>> lde16;   // tensor-core LDE constants (byte matrices, twiddles) by (blowup, direction)
   std::map<size_t, fe *> periodic;         // periodic-column tables by (n << 8 | ce)
   std::vector<cudaEvent_t> ev;             // stage timing events
-  int wait_mode = 0;                       // host waits: 0 = spin when alone on the device, block otherwise; 1 = spin; 2 = block (ZKL_WAIT_MODE)
+  int wait_mode = 0;                       // host waits: 0 = automatic, 1 = spin, 2 = block, 3 = poll + yield (ZKL_WAIT_MODE; api_stark.inl: ctx_wait)
   cudaEvent_t wait_ev = nullptr;           // cudaEventBlockingSync event of the blocking wait
   void *stage_h = nullptr; size_t stage_cap = 0, stage_used = 0;   // pinned host staging for per-call parameter uploads (api_stark.inl: upload_air)
   std::vector<uint32_t> sort_a, sort_b, sort_cnt;  // scratch of the assertion ordering

@@ -114,7 +114,7 @@ extern "C" int zkl_ctx_create(int device, zkl_ctx **out) {
   if (const char *e = getenv("ZKL_TC_GRID_CAP")) { int v = atoi(e); if (v > 0 && v <= c->num_sms) c->tc_grid_cap = v; }   // experiment knob
   if (const char *e = getenv("ZKL_COOP_PATH")) { int v = atoi(e); if (v >= 0 && v <= 2) c->coop_path = v; }   // experiment knobs (A/B runs of bench.py)
   if (const char *e = getenv("ZKL_TC_HALF_TILES")) c->tc_half_tiles = atoi(e) != 0;
-  if (const char *e = getenv("ZKL_WAIT_MODE")) { int v = atoi(e); if (v >= 0 && v <= 2) c->wait_mode = v; }
+  if (const char *e = getenv("ZKL_WAIT_MODE")) { int v = atoi(e); if (v >= 0 && v <= 3) c->wait_mode = v; }
   if (const char *e = getenv("ZKL_NTT_PATH")) { int v = atoi(e); if (v >= 0 && v <= 2) c->ntt_path = v; }
   if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) {
     g_create_error = cudaGetErrorString(e); delete c; return 1;
