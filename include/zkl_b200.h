@@ -93,7 +93,14 @@ typedef struct {
   zkl_fe rom_w_enc0[59], rom_w_enc1[59]; /* utils.rs:114-141 */
   zkl_fe program_fe0;                /* RAM compressor pi (vm/air/ram.rs:109) */
   zkl_fe merkle_root_fe;             /* be_from_le8(merkle_root) (vm/air/merkle.rs:121) */
+  uint32_t air_kind;                 /* ZKL_AIR_ZKLISP (0): ZkLispAir, everything above; ZKL_AIR_AGG (1): ZlAggAir (agg/air.rs:22-332), only
+                                        cols.width (31), num_transition (24), ce_blowup, num_composition_cols and the assertions are read */
+  uint32_t pad_;
 } zkl_air_params;
+#define ZKL_AIR_ZKLISP 0
+#define ZKL_AIR_AGG 1
+#define ZKL_AGG_WIDTH 31             /* agg/layout.rs:97-180 AggColumns::baseline().width() */
+#define ZKL_AGG_TRANSITIONS 24       /* agg/air.rs:69-94 */
 
 /* winterfell::ProofOptions as zk-lisp builds them (prove.rs:963-972, :1106-1107) */
 typedef struct {
@@ -104,6 +111,11 @@ typedef struct {
   uint32_t hash_rate;
   uint32_t fri_folding;      /* 2  (only 2 is supported) */
   uint32_t fri_remainder_max_degree; /* 1 */
+  uint32_t field_extension;  /* winterfell::FieldExtension: 0 or 1 = None (step proofs, prove.rs:967), 2 = Quadratic (the aggregation
+                                proof when min_security_bits >= 128, prove.rs:647-651). With this hasher every drawn extension element
+                                has a zero second coordinate (a digest is 16 bytes + 16 zero bytes, utils.rs:375-381, and
+                                RandomCoin::draw reads E::ELEMENT_BYTES = 32 of them [WF-mem]), so all arithmetic stays in the base
+                                field and the extension only changes what is hashed and serialized: E elements are (a, 0). */
 } zkl_options;
 
 typedef struct zkl_ctx zkl_ctx;
@@ -284,6 +296,10 @@ int zkl_air_build(const zkl_program *program, const zkl_public_inputs *pi, size_
                   zkl_fe *out_seed, size_t *num_seed /* in: capacity */, char *err, size_t err_cap);
 /* zkl_prove_segment with the AIR parameters and the coin seed built inside (zkl_air_build), per call: nothing about a
  * segment is cached between calls. */
+/* ZlAggAir::new (agg/air.rs:32-113) + get_assertions (:274-305): the parameters of the 31-column aggregation AIR over a trace of
+ * n rows (one row per child, padded to a power of two >= 8, agg/trace.rs:396-399). out_assertions: room for 5. Host only. */
+int zkl_agg_air_params(size_t n, uint64_t v_units_total, uint32_t children_count, zkl_air_params *out_params,
+                       zkl_assertion *out_assertions);
 int zkl_prove_segment_pi(zkl_ctx *ctx, const zkl_fe *trace, size_t width, size_t n, const zkl_program *program,
                          const zkl_public_inputs *pi, const zkl_options *opts, uint8_t *out_proof, size_t *out_len,
                          zkl_proof_summary *summary);

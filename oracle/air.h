@@ -47,8 +47,31 @@ struct PeriodicPolys {
 
 static inline F sq(F a) { return f_mul(a, a); }
 
+// ZlAggAir::evaluate_transition (agg/air.rs:112-272, columns agg/layout.rs:97-180): 24 values; per[P_LAST] is the AIR's one periodic
+// column (is_last, cycle n).
+static inline void eval_transition_agg(const F *cur, const F *next, const F *per, F *r) {
+  enum { OK = 0, V0_SUM, V1_SUM, VNEXT_SUM, FRI_V0, FRI_V1, FRI_VNEXT, FRI_ALPHA, FRI_X0, FRI_X1, FRI_Q1, COMP_SUM, ALPHA_DIV_ZM, MAP_L0, FINAL_LLAST,
+         R_, ALPHA, BETA, GAMMA, SEG_FIRST, TRACE_ROOT_ERR, CONS_ROOT_ERR, V_UNITS_ACC, V_UNITS_CHILD, CHILD_COUNT_ACC, VM_ERR, RAM_U_ERR, RAM_S_ERR,
+         ROM_ERR0, ROM_ERR1, ROM_ERR2 };
+  const F not_last = f_sub(f_one(), per[P_LAST]);
+  r[0] = cur[OK];
+  r[1] = f_mul(not_last, f_sub(next[V_UNITS_ACC], f_add(cur[V_UNITS_ACC], f_mul(cur[V_UNITS_CHILD], cur[SEG_FIRST]))));
+  r[2] = cur[TRACE_ROOT_ERR];
+  r[3] = cur[CONS_ROOT_ERR];
+  const int chained[7] = {R_, ALPHA, BETA, GAMMA, V0_SUM, V1_SUM, VNEXT_SUM};
+  for (int k = 0; k < 7; k++) r[4 + k] = f_mul(not_last, f_sub(next[chained[k]], cur[chained[k]]));
+  r[11] = f_mul(not_last, f_sub(next[CHILD_COUNT_ACC], f_add(cur[CHILD_COUNT_ACC], cur[SEG_FIRST])));
+  const F lhs = f_mul(cur[FRI_VNEXT], f_sub(cur[FRI_X1], cur[FRI_X0]));
+  const F rhs = f_sub(f_mul(cur[FRI_V1], f_sub(cur[FRI_ALPHA], cur[FRI_X0])), f_mul(cur[FRI_V0], f_sub(cur[FRI_ALPHA], cur[FRI_X1])));
+  r[12] = f_sub(lhs, rhs);
+  r[13] = f_sub(cur[FRI_VNEXT], cur[FRI_Q1]);
+  r[14] = cur[COMP_SUM]; r[15] = cur[ALPHA_DIV_ZM]; r[16] = cur[MAP_L0]; r[17] = cur[FINAL_LLAST];
+  r[18] = cur[VM_ERR]; r[19] = cur[RAM_U_ERR]; r[20] = cur[RAM_S_ERR]; r[21] = cur[ROM_ERR0]; r[22] = cur[ROM_ERR1]; r[23] = cur[ROM_ERR2];
+}
+
 // writes air.num_transition values
 static inline void eval_transition(const zkl_air_params &air, const F *cur, const F *next, const F *per, F *result) {
+  if (air.air_kind == ZKL_AIR_AGG) { eval_transition_agg(cur, next, per, result); return; }
   const zkl_columns &c = air.cols;
   size_t ix = 0;
   const F one = f_one(), zero = f_zero();

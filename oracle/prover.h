@@ -119,8 +119,18 @@ struct ConstraintCommitment {
 };
 // CompositionPoly::new + DefaultConstraintCommitment::new [WF-mem]: interpolate over the CE coset,
 // split coefficients into num_cols chunks of n (column i = coefficients [i*n,(i+1)*n)), LDE, commit.
+// Extension degree E = 2 (FieldExtension::Quadratic, the aggregation proof from 128 bits up, prove.rs:647-651): every drawn
+// extension element is (a, 0) with this hasher (a digest is 16 bytes + 16 zero bytes, RandomCoin::draw reads 32 [WF-mem]), so all
+// values stay in the base field; what changes is what gets hashed and serialized: an E element is the base-element pair (a, 0)
+// (E::slice_as_base_elements), partition sizes count E columns with hash_rate / E.
+static inline std::vector<F> as_base_elements(const std::vector<F> &v, size_t E) {
+  if (E == 1) return v;
+  std::vector<F> out(2 * v.size(), f_zero());
+  for (size_t i = 0; i < v.size(); i++) out[2 * i] = v[i];
+  return out;
+}
 static inline ConstraintCommitment commit_constraints(const Hasher &h, std::vector<F> ce_evals, size_t n, size_t num_cols,
-                                                      size_t blowup, size_t num_partitions, size_t hash_rate) {
+                                                      size_t blowup, size_t num_partitions, size_t hash_rate, size_t E = 1) {
   ConstraintCommitment cm;
   interpolate(ce_evals, f_generator());
   size_t N = n * blowup;
@@ -129,7 +139,12 @@ static inline ConstraintCommitment commit_constraints(const Hasher &h, std::vect
     cm.polys[c].assign(ce_evals.begin() + c * n, ce_evals.begin() + (c + 1) * n);
     cm.lde[c] = evaluate_over(cm.polys[c], N, f_generator());
   }
-  cm.tree = MerkleTree(h, hash_rows(h, cm.lde, N, partition_size(num_partitions, hash_rate, num_cols)));
+  if (E == 1) cm.tree = MerkleTree(h, hash_rows(h, cm.lde, N, partition_size(num_partitions, hash_rate, num_cols)));
+  else {   // rows of E elements: (v_0, 0, v_1, 0, ...)
+    std::vector<std::vector<F>> wide(2 * num_cols, std::vector<F>(N, f_zero()));
+    for (size_t c = 0; c < num_cols; c++) wide[2 * c] = cm.lde[c];
+    cm.tree = MerkleTree(h, hash_rows(h, wide, N, E * partition_size(num_partitions, hash_rate, num_cols, E)));
+  }
   return cm;
 }
 
@@ -239,7 +254,7 @@ static inline void write_context(Writer &w, size_t W, size_t n, const zkl_option
   w.u8(16); w.bytes(&P, 16);                 // field modulus bytes (LE)
   w.usize(num_constraints);
   w.u8((uint8_t)o.num_queries); w.u8((uint8_t)o.blowup); w.u8((uint8_t)o.grinding);
-  w.u8(1);                                   // FieldExtension::None
+  w.u8(o.field_extension == 2 ? 2 : 1);      // FieldExtension::None = 1, Quadratic = 2
   w.u8((uint8_t)o.fri_folding); w.u8((uint8_t)o.fri_remainder_max_degree);
   w.u8(0); w.u8(0);                          // BatchingMethod::Linear x2
   w.u8((uint8_t)o.num_partitions); w.u8((uint8_t)o.hash_rate);
@@ -262,6 +277,7 @@ static inline ProofOut prove_segment(const Hasher &h, const F *trace, size_t W, 
                                      const std::vector<F> &seed_elems, const zkl_options &o) {
   ProofOut po; memset(&po.summary, 0, sizeof po.summary);
   size_t N = n * o.blowup, ncc = air.num_composition_cols;
+  const size_t E = o.field_extension == 2 ? 2 : 1;
   Timer tm;
   // 1. public coin (agg/fs.rs:69-73)
   Coin coin(h, seed_elems);
@@ -277,7 +293,7 @@ static inline ProofOut prove_segment(const Hasher &h, const F *trace, size_t W, 
   std::vector<F> ce = evaluate_constraints(air, tc, n, o.blowup, cc);
   po.summary.stage_ms[2] = tm.lap();
   // 6. constraint commitment (hook build_constraint_commitment)
-  ConstraintCommitment cm = commit_constraints(h, ce, n, ncc, o.blowup, o.num_partitions, o.hash_rate);
+  ConstraintCommitment cm = commit_constraints(h, ce, n, ncc, o.blowup, o.num_partitions, o.hash_rate, E);
   coin.reseed(cm.tree.root());
   po.summary.stage_ms[3] = tm.lap();
   // 7. OOD point and evaluations (agg/fs.rs:134-164)
@@ -288,7 +304,7 @@ static inline ProofOut prove_segment(const Hasher &h, const F *trace, size_t W, 
   for (size_t c = 0; c < ncc; c++) { h_z[c] = poly_eval(cm.polys[c].data(), n, z); h_zg[c] = poly_eval(cm.polys[c].data(), n, zg); }
   std::vector<F> ood; ood.insert(ood.end(), t_z.begin(), t_z.end()); ood.insert(ood.end(), h_z.begin(), h_z.end());
   ood.insert(ood.end(), t_zg.begin(), t_zg.end()); ood.insert(ood.end(), h_zg.begin(), h_zg.end());
-  coin.reseed(h.hash_elements(ood.data(), ood.size()));
+  { std::vector<F> oe = as_base_elements(ood, E); coin.reseed(h.hash_elements(oe.data(), oe.size())); }
   po.summary.stage_ms[4] = tm.lap();
   // 8. DEEP composition (agg/trace.rs:1134-1193), evaluated over the LDE domain
   std::vector<F> dc(W + ncc); for (auto &x : dc) x = coin.draw();
@@ -326,7 +342,7 @@ static inline ProofOut prove_segment(const Hasher &h, const F *trace, size_t W, 
   for (size_t d = 0; d < nl; d++) {
     size_t half = ev.size() / 2;
     std::vector<Digest> leaves(half);
-    for (size_t i = 0; i < half; i++) { F pr[2] = {ev[i], ev[i + half]}; leaves[i] = h.hash_elements(pr, 2); }
+    for (size_t i = 0; i < half; i++) { F pr[4] = {ev[i], E == 2 ? f_zero() : ev[i + half], ev[i + half], f_zero()}; leaves[i] = h.hash_elements(pr, 2 * E); }
     MerkleTree t(h, leaves);
     coin.reseed(t.root()); fri_roots.push_back(t.root());
     F alpha = coin.draw();
@@ -351,7 +367,8 @@ static inline ProofOut prove_segment(const Hasher &h, const F *trace, size_t W, 
   std::vector<F> rem = ev; interpolate(rem, f_generator());
   size_t rem_len = rem.size() / o.blowup;
   std::vector<F> rem_rev(rem.begin(), rem.begin() + rem_len); std::reverse(rem_rev.begin(), rem_rev.end());
-  Digest rem_commit = h.hash_elements(rem_rev.data(), rem_rev.size());
+  Digest rem_commit;
+  { std::vector<F> re = as_base_elements(rem_rev, E); rem_commit = h.hash_elements(re.data(), re.size()); }
   coin.reseed(rem_commit); fri_roots.push_back(rem_commit);
   po.summary.stage_ms[6] = tm.lap();
   // 10. grinding: smallest nonce >= 1 (agg/fs.rs:202-207)
@@ -373,17 +390,18 @@ static inline ProofOut prove_segment(const Hasher &h, const F *trace, size_t W, 
     for (auto &d : fri_roots) cb.insert(cb.end(), d.b, d.b + 32);
     wr.u16((uint16_t)cb.size()); wr.bytes(cb.data(), cb.size());
   }
-  auto write_queries = [&](const std::vector<std::vector<F>> &cols, const MerkleTree &t) {
-    Writer v; for (size_t p : pos) for (size_t c = 0; c < cols.size(); c++) v.fe(cols[c][p]);
+  auto fe_ext = [&](Writer &w, F x, size_t deg) { w.fe(x); if (deg == 2) w.fe(f_zero()); };   // an E element on the wire: (a, 0)
+  auto write_queries = [&](const std::vector<std::vector<F>> &cols, const MerkleTree &t, size_t deg) {
+    Writer v; for (size_t p : pos) for (size_t c = 0; c < cols.size(); c++) fe_ext(v, cols[c][p], deg);
     Writer pw; write_batch_proof(pw, prove_batch(t, pos));
     wr.usize(v.b.size()); wr.bytes(v.b.data(), v.b.size());
     wr.usize(pw.b.size()); wr.bytes(pw.b.data(), pw.b.size());
   };
-  write_queries(tc.lde, tc.tree);  // trace_queries (one segment)
-  write_queries(cm.lde, cm.tree);  // constraint_queries
+  write_queries(tc.lde, tc.tree, 1);  // trace_queries (one segment): base field
+  write_queries(cm.lde, cm.tree, E);  // constraint_queries: E elements
   {  // OodFrame: trace states (current || next), constraint evaluations (current || next)
-    Writer ts; for (auto &x : t_z) ts.fe(x); for (auto &x : t_zg) ts.fe(x);
-    Writer evs; for (auto &x : h_z) evs.fe(x); for (auto &x : h_zg) evs.fe(x);
+    Writer ts; for (auto &x : t_z) fe_ext(ts, x, E); for (auto &x : t_zg) fe_ext(ts, x, E);
+    Writer evs; for (auto &x : h_z) fe_ext(evs, x, E); for (auto &x : h_zg) fe_ext(evs, x, E);
     wr.u16((uint16_t)ts.b.size()); wr.bytes(ts.b.data(), ts.b.size());
     wr.u16((uint16_t)evs.b.size()); wr.bytes(evs.b.data(), evs.b.size());
   }
@@ -393,13 +411,13 @@ static inline ProofOut prove_segment(const Hasher &h, const F *trace, size_t W, 
     for (size_t d = 0; d < nl; d++) {
       fp = fold_positions(fp, dom, 2);
       size_t half = dom / 2;
-      Writer v; for (size_t p : fp) { v.fe(layer_evals[d][p]); v.fe(layer_evals[d][p + half]); }
+      Writer v; for (size_t p : fp) { fe_ext(v, layer_evals[d][p], E); fe_ext(v, layer_evals[d][p + half], E); }
       Writer pw; write_batch_proof(pw, prove_batch(layer_trees[d], fp));
       wr.u32((uint32_t)v.b.size()); wr.bytes(v.b.data(), v.b.size());
       wr.u32((uint32_t)pw.b.size()); wr.bytes(pw.b.data(), pw.b.size());
       dom = half;
     }
-    wr.u16((uint16_t)(rem_rev.size() * 16)); for (auto &x : rem_rev) wr.fe(x);
+    wr.u16((uint16_t)(rem_rev.size() * 16 * E)); for (auto &x : rem_rev) fe_ext(wr, x, E);
     wr.u8(1);  // num_partitions
   }
   wr.u64(nonce);
@@ -424,7 +442,10 @@ static inline int verify_segment(const Hasher &h, const uint8_t *proof, size_t l
                                  const zkl_air_params &air, const std::vector<F> &seed_elems, const zkl_options &o,
                                  std::string &msg) {
   size_t N = n * o.blowup, ncc = air.num_composition_cols, nl = num_fri_layers(N, o);
+  const size_t E = o.field_extension == 2 ? 2 : 1;
   Reader r(proof, len);
+  bool ext_ok = true;
+  auto fe_ext = [&](size_t deg) { F x = r.fe(); if (deg == 2) { F hi = r.fe(); if (!f_eq(hi, f_zero())) ext_ok = false; } return x; };   // (a, 0)
   {  // context must match what the verifier derives
     Writer cw; write_context(cw, W, n, o, air.num_transition + air.num_assertions);
     std::vector<uint8_t> got(cw.b.size()); r.bytes(got.data(), got.size());
@@ -435,33 +456,34 @@ static inline int verify_segment(const Hasher &h, const uint8_t *proof, size_t l
   if (clen != 32 * (2 + nl + 1)) { msg = "commitments length"; return 2; }
   Digest trace_root = r.digest(), cons_root = r.digest();
   std::vector<Digest> fri_roots(nl + 1); for (auto &d : fri_roots) d = r.digest();
-  auto read_queries = [&](size_t width, std::vector<std::vector<F>> &rows, BatchMerkleProof &bp) -> bool {
-    size_t vl = r.usize(); if (!r.ok || vl != nq * width * 16) return false;
+  auto read_queries = [&](size_t width, size_t deg, std::vector<std::vector<F>> &rows, BatchMerkleProof &bp) -> bool {
+    size_t vl = r.usize(); if (!r.ok || vl != nq * width * 16 * deg) return false;
     rows.assign(nq, std::vector<F>(width));
-    for (auto &row : rows) for (auto &x : row) x = r.fe();
+    for (auto &row : rows) for (auto &x : row) x = fe_ext(deg);
     size_t pl = r.usize(); size_t start = r.off;
     if (!read_batch_proof(r, bp)) return false;
     return r.off - start == pl;
   };
   std::vector<std::vector<F>> trows, crows; BatchMerkleProof tbp, cbp;
-  if (!read_queries(W, trows, tbp)) { msg = "trace queries"; return 3; }
-  if (!read_queries(ncc, crows, cbp)) { msg = "constraint queries"; return 4; }
-  if (r.u16() != 2 * W * 16) { msg = "ood trace len"; return 5; }
+  if (!read_queries(W, 1, trows, tbp)) { msg = "trace queries"; return 3; }
+  if (!read_queries(ncc, E, crows, cbp)) { msg = "constraint queries"; return 4; }
+  if (r.u16() != 2 * W * 16 * E) { msg = "ood trace len"; return 5; }
   std::vector<F> t_z(W), t_zg(W), h_z(ncc), h_zg(ncc);
-  for (auto &x : t_z) x = r.fe();
-  for (auto &x : t_zg) x = r.fe();
-  if (r.u16() != 2 * ncc * 16) { msg = "ood eval len"; return 5; }
-  for (auto &x : h_z) x = r.fe();
-  for (auto &x : h_zg) x = r.fe();
+  for (auto &x : t_z) x = fe_ext(E);
+  for (auto &x : t_zg) x = fe_ext(E);
+  if (r.u16() != 2 * ncc * 16 * E) { msg = "ood eval len"; return 5; }
+  for (auto &x : h_z) x = fe_ext(E);
+  for (auto &x : h_zg) x = fe_ext(E);
   if (r.u8() != nl) { msg = "fri layer count"; return 6; }
   std::vector<std::vector<F>> fvals(nl); std::vector<BatchMerkleProof> fbp(nl);
   for (size_t d = 0; d < nl; d++) {
-    size_t vl = r.u32(); if (!r.ok || vl % 32) { msg = "fri values"; return 6; }
-    fvals[d].resize(vl / 16); for (auto &x : fvals[d]) x = r.fe();
+    size_t vl = r.u32(); if (!r.ok || vl % (32 * E)) { msg = "fri values"; return 6; }
+    fvals[d].resize(vl / (16 * E)); for (auto &x : fvals[d]) x = fe_ext(E);
     size_t pl = r.u32(); size_t start = r.off;
     if (!read_batch_proof(r, fbp[d]) || r.off - start != pl) { msg = "fri paths"; return 6; }
   }
-  size_t reml = r.u16(); std::vector<F> rem(reml / 16); for (auto &x : rem) x = r.fe();
+  size_t reml = r.u16(); std::vector<F> rem(reml / (16 * E)); for (auto &x : rem) x = fe_ext(E);
+  if (!ext_ok) { msg = "extension element with a non-zero second coordinate"; return 8; }
   if (r.u8() != 1) { msg = "fri num_partitions"; return 6; }
   uint64_t nonce = r.u64();
   if (!r.ok || r.off != len) { msg = "trailing/short proof"; return 7; }
@@ -497,7 +519,7 @@ static inline int verify_segment(const Hasher &h, const uint8_t *proof, size_t l
   }
   std::vector<F> ood; ood.insert(ood.end(), t_z.begin(), t_z.end()); ood.insert(ood.end(), h_z.begin(), h_z.end());
   ood.insert(ood.end(), t_zg.begin(), t_zg.end()); ood.insert(ood.end(), h_zg.begin(), h_zg.end());
-  coin.reseed(h.hash_elements(ood.data(), ood.size()));
+  { std::vector<F> oe = as_base_elements(ood, E); coin.reseed(h.hash_elements(oe.data(), oe.size())); }
   std::vector<F> dc(W + ncc); for (auto &x : dc) x = coin.draw();
   std::vector<F> alphas;
   for (auto &d : fri_roots) { coin.reseed(d); alphas.push_back(coin.draw()); }
@@ -510,7 +532,10 @@ static inline int verify_segment(const Hasher &h, const uint8_t *proof, size_t l
     std::vector<Digest> lv(nq); Digest root;
     for (size_t i = 0; i < nq; i++) lv[i] = hash_row(h, trows[i].data(), W, partition_size(o.num_partitions, o.hash_rate, W));
     if (!batch_root(h, tbp, lv, pos, root) || memcmp(root.b, trace_root.b, 32)) { msg = "trace opening"; return 13; }
-    for (size_t i = 0; i < nq; i++) lv[i] = hash_row(h, crows[i].data(), ncc, partition_size(o.num_partitions, o.hash_rate, ncc));
+    for (size_t i = 0; i < nq; i++) {
+      std::vector<F> row = as_base_elements(crows[i], E);
+      lv[i] = hash_row(h, row.data(), row.size(), E * partition_size(o.num_partitions, o.hash_rate, ncc, E));
+    }
     if (!batch_root(h, cbp, lv, pos, root) || memcmp(root.b, cons_root.b, 32)) { msg = "constraint opening"; return 14; }
   }
   // ---- DEEP evaluations at the queried positions
@@ -536,7 +561,10 @@ static inline int verify_segment(const Hasher &h, const uint8_t *proof, size_t l
       size_t half = dom / 2;
       if (fvals[d].size() != 2 * fp.size()) { msg = "fri layer value count"; return 20; }
       std::vector<Digest> lv(fp.size()); Digest root;
-      for (size_t i = 0; i < fp.size(); i++) lv[i] = h.hash_elements(&fvals[d][2 * i], 2);
+      for (size_t i = 0; i < fp.size(); i++) {
+        F pr[4] = {fvals[d][2 * i], E == 2 ? f_zero() : fvals[d][2 * i + 1], fvals[d][2 * i + 1], f_zero()};
+        lv[i] = h.hash_elements(pr, 2 * E);
+      }
       if (!batch_root(h, fbp[d], lv, fp, root) || memcmp(root.b, fri_roots[d].b, 32)) { msg = "fri layer opening"; return 21; }
       // the queried evaluations must match the values claimed by the previous layer
       for (size_t i = 0; i < positions.size(); i++) {
@@ -553,7 +581,7 @@ static inline int verify_segment(const Hasher &h, const uint8_t *proof, size_t l
       }
       positions = fp; evals = nx; dom = half; wd = f_sqr(wd);
     }
-    Digest rc = h.hash_elements(rem.data(), rem.size());
+    Digest rc; { std::vector<F> re = as_base_elements(rem, E); rc = h.hash_elements(re.data(), re.size()); }
     if (memcmp(rc.b, fri_roots[nl].b, 32)) { msg = "remainder commitment"; return 23; }
     if (rem.size() > (n >> nl)) { msg = "remainder degree"; return 24; }
     for (size_t i = 0; i < positions.size(); i++) {

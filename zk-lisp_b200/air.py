@@ -181,7 +181,7 @@ class ProofOptions:
 
     def to_c(self) -> capi.Options:
         return capi.Options(self.num_queries, self.blowup, self.grinding, self.num_partitions, self.hash_rate,
-                            self.fri_folding, self.fri_remainder_max_degree)
+                            self.fri_folding, self.fri_remainder_max_degree, self.field_extension)
 
     def to_elements(self) -> List[int]:
         """winter-air ProofOptions::to_elements [WF-mem]."""

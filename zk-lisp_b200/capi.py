@@ -59,14 +59,17 @@ class AirParams(C.Structure):
         ("assertions", C.POINTER(Assertion)),
         ("pose", Suite), ("rom", RomSuite),
         ("rom_w_enc0", Fe * 59), ("rom_w_enc1", Fe * 59),
-        ("program_fe0", Fe), ("merkle_root_fe", Fe),
+        ("program_fe0", Fe), ("merkle_root_fe", Fe), ("air_kind", C.c_uint32), ("pad_", C.c_uint32),
     ]
+
+
+AIR_ZKLISP, AIR_AGG, AGG_WIDTH, AGG_TRANSITIONS = 0, 1, 31, 24
 
 
 class Options(C.Structure):
     _fields_ = [(n, C.c_uint32) for n in (
         "num_queries", "blowup", "grinding", "num_partitions", "hash_rate", "fri_folding",
-        "fri_remainder_max_degree")]
+        "fri_remainder_max_degree", "field_extension")]
 
 
 class BatchProof(C.Structure):
@@ -188,6 +191,7 @@ def load_library():
     sig("zkl_suite_derive", C.c_int, vp, C.POINTER(Suite))
     sig("zkl_air_build", C.c_int, C.POINTER(Program), C.POINTER(PublicInputsC), sz, sz, C.POINTER(Options), C.POINTER(AirParams), vp,
         C.POINTER(sz), vp, C.POINTER(sz), C.c_char_p, sz)
+    sig("zkl_agg_air_params", C.c_int, sz, C.c_uint64, C.c_uint32, C.POINTER(AirParams), C.POINTER(Assertion))
     sig("zkl_prove_segment_pi", C.c_int, vp, vp, sz, sz, C.POINTER(Program), C.POINTER(PublicInputsC), C.POINTER(Options), vp,
         C.POINTER(sz), C.POINTER(ProofSummary))
     sig("zkl_prove_segment_pi_dev", C.c_int, vp, vp, sz, sz, C.POINTER(Program), C.POINTER(PublicInputsC), C.POINTER(Options), vp,
@@ -234,5 +238,5 @@ EXPORTED_SYMBOLS = [
     "zkl_constraint_commitment_free", "zkl_constraint_query", "zkl_prove_segment",
     "zkl_prove_segment_dev", "zkl_stage_name", "zkl_dev_alloc", "zkl_dev_free", "zkl_dev_upload",
     "zkl_sync", "zkl_slice_segment_dev", "zkl_usage_mask_dev", "zkl_read_cells_dev", "zkl_timer_start", "zkl_timer_stop", "zkl_imad_peak", "zkl_set_bulk_threshold", "zkl_set_hash_path", "zkl_set_ntt_path", "zkl_set_coop_path", "zkl_bench_permute", "zkl_partition_size", "zkl_lde_dev", "zkl_hash_partitions_dev", "zkl_merge_partition_digests_dev", "zkl_merkle_dev", "zkl_dev_download", "zkl_merge_plan", "zkl_poseidon_levels_dev", "zkl_merge_with_int_pairs", "zkl_replay_children", "zkl_replay_status_name", "zkl_grind", "zkl_hash_two_lanes_host",
-    "zkl_program_derive", "zkl_suite_derive", "zkl_air_build", "zkl_prove_segment_pi", "zkl_prove_segment_pi_dev", "zkl_tc_i8_peak",
+    "zkl_program_derive", "zkl_suite_derive", "zkl_air_build", "zkl_prove_segment_pi", "zkl_prove_segment_pi_dev", "zkl_tc_i8_peak", "zkl_agg_air_params",
 ]

@@ -337,3 +337,25 @@ extern "C" int zkl_air_build(const zkl_program *program, const zkl_public_inputs
   *out_params = b.p; out_params->assertions = out_assertions;
   return 0;
 }
+
+// ---- ZlAggAir (agg/air.rs:22-332): 31 columns, 24 transition constraints, 5 assertions, one periodic column of cycle n ----
+// Degrees (agg/air.rs:69-94): constraint 1 has base degree 2 and one cycle-n periodic factor, constraint 11 base 1 and one
+// periodic factor, the rest are linear. AirContext [WF-mem]: ce_blowup = next_pow2(2 + 1) = 4; a cycle-n periodic column has
+// degree n - 1, so the highest evaluation degree is 3 (n - 1) and the composition polynomial has (3(n-1) - (n-1) + n - 1) / n columns.
+extern "C" int zkl_agg_air_params(size_t n, uint64_t v_units_total, uint32_t children_count, zkl_air_params *p, zkl_assertion *as) {
+  if (n < 8 || (n & (n - 1)) || n > ((size_t)1 << 24)) return 1;   // agg/trace.rs:35,396-399: max(children, 8) rounded up to a power of two
+  memset(p, 0, sizeof *p);
+  p->air_kind = ZKL_AIR_AGG;
+  p->cols.width = ZKL_AGG_WIDTH;
+  p->num_transition = ZKL_AGG_TRANSITIONS;
+  p->ce_blowup = 4;
+  p->num_composition_cols = (uint32_t)std::max<uint64_t>((3 * (uint64_t)(n - 1) - (n - 1) + n - 1) / n, 1);
+  const uint32_t last = (uint32_t)n - 1, ok = 0, v_units_acc = 22, child_count_acc = 24;   // agg/layout.rs:97-180
+  as[0] = zkl_assertion{ok, 0, abi_u64(0)};
+  as[1] = zkl_assertion{v_units_acc, 0, abi_u64(0)};
+  as[2] = zkl_assertion{v_units_acc, last, abi_u64(v_units_total)};
+  as[3] = zkl_assertion{child_count_acc, 0, abi_u64(0)};
+  as[4] = zkl_assertion{child_count_acc, last, abi_u64(children_count)};
+  p->num_assertions = 5; p->assertions = as;
+  return 0;
+}
