@@ -10,6 +10,7 @@ struct committed_matrix {
   dev_buf<fe> leaves;  // N digests (as elements), natural row order
   dev_buf<fe> nodes;   // N entries, nodes[1] = root
   dev_buf<fe> scratch;
+  size_t ext = 1;      // rows are E elements stored as `ext` base columns each ((a, 0) pairs for the quadratic extension)
 };
 struct zkl_trace_lde { committed_matrix m; };
 struct zkl_constraint_commitment { committed_matrix m; };
@@ -23,7 +24,7 @@ static int commit_matrix(zkl_ctx *ctx, committed_matrix &m, const zkl_options *o
   if (kev) ZKL_CHECK(ctx, cudaEventRecord(kev[0], ctx->stream));
   ZKL_TRY(dev_lde(ctx, m.polys.p, m.lde.p, m.width, m.n, m.blowup));
   if (kev) ZKL_CHECK(ctx, cudaEventRecord(kev[1], ctx->stream));
-  ZKL_TRY(dev_hash_rows(ctx, m.lde.p, m.width, m.n, m.blowup, o, m.leaves.p, m.scratch));
+  ZKL_TRY(dev_hash_rows(ctx, m.lde.p, m.width, m.n, m.blowup, o, m.leaves.p, m.scratch, m.ext));
   if (kev) ZKL_CHECK(ctx, cudaEventRecord(kev[2], ctx->stream));
   ZKL_TRY(dev_merkle(ctx, m.leaves.p, m.nodes.p, m.N));
   return 0;
@@ -31,6 +32,7 @@ static int commit_matrix(zkl_ctx *ctx, committed_matrix &m, const zkl_options *o
 static int check_opts(zkl_ctx *ctx, const zkl_options *o, size_t n) {
   if (o->fri_folding != 2) { ctx->set_error("only FRI folding factor 2 is supported (prove.rs:968)"); return 1; }
   if (o->blowup < 2 || (o->blowup & (o->blowup - 1)) || o->blowup > 128) { ctx->set_error("blowup must be a power of two in [2,128]"); return 1; }
+  if (o->field_extension > 2) { ctx->set_error("field_extension must be 0/1 (None) or 2 (Quadratic); zk-lisp never asks for Cubic (prove.rs:647-651,967)"); return 1; }
   if (n < 8 || n > NTT_MAX || (n & (n - 1))) { ctx->set_error("trace length must be a power of two in [8, 2^24]"); return 1; }
   // the FRI remainder is interpolated by one CTA (k_fri_remainder): its domain (max degree + 1) * blowup is bounded
   if ((size_t)(o->fri_remainder_max_degree + 1) * o->blowup > 256) { ctx->set_error("FRI remainder domain (fri_remainder_max_degree + 1) * blowup must be <= 256"); return 1; }
@@ -246,7 +248,11 @@ static int upload_air(zkl_ctx *ctx, const zkl_air_params *a, size_t n, air_devic
   h.cols = a->cols;
   h.f_poseidon = a->f_poseidon; h.f_vm = a->f_vm; h.f_sponge = a->f_sponge; h.f_merkle = a->f_merkle; h.f_ram = a->f_ram;
   h.rom_enabled = a->rom_enabled; h.vm_usage_mask = a->vm_usage_mask; h.ram_delta_clk_bits = a->ram_delta_clk_bits;
-  h.num_transition = a->num_transition;
+  h.num_transition = a->num_transition; h.air_kind = a->air_kind;
+  if (a->air_kind > ZKL_AIR_AGG) { ctx->set_error("unknown air_kind"); return 1; }
+  if (a->air_kind == ZKL_AIR_AGG && (a->cols.width != ZKL_AGG_WIDTH || a->num_transition != ZKL_AGG_TRANSITIONS)) {
+    ctx->set_error("ZlAggAir has 31 columns and 24 transition constraints (agg/layout.rs, agg/air.rs:69-94)"); return 1;
+  }
   for (int i = 0; i < 12; i++) for (int j = 0; j < 12; j++) h.pose_mds[i][j] = fe_from_abi(a->pose.mds[i][j]);
   for (int r = 0; r < ZKL_ROUNDS; r++) for (int j = 0; j < 12; j++) h.pose_rc[r][j] = fe_from_abi(a->pose.rc[r][j]);
   for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) h.rom_mds[i][j] = fe_from_abi(a->rom.mds[i][j]);
@@ -291,13 +297,14 @@ static int dev_eval_constraints(zkl_ctx *ctx, const committed_matrix &t, const z
                                 fe *ce_out) {
   size_t n = t.n, ce = a->ce_blowup, M = n * ce, N = t.N;
   if (ce > t.blowup || ce > 16 || (ce & (ce - 1))) { ctx->set_error("ce_blowup must be a power of two <= min(blowup, 16)"); return 1; }
-  if (n < 32) { ctx->set_error("trace length must be >= 32 (one schedule level)"); return 1; }
+  const bool agg = a->air_kind == ZKL_AIR_AGG;
+  if (n < 32 && !agg) { ctx->set_error("trace length must be >= 32 (one schedule level)"); return 1; }
   domain_tables *tN, *tM, *tn;
   ZKL_TRY(get_tables(ctx, N, &tN)); ZKL_TRY(get_tables(ctx, M, &tM)); ZKL_TRY(get_tables(ctx, n, &tn));
-  // periodic table: data independent, cached per (n, ce)
+  // periodic table: data independent, cached per (n, ce) (the 31 cycle-32 schedule columns of ZkLispAir; ZlAggAir has none)
   fe g = fe_from_u64(3);
-  fe *per_tab;
-  {
+  fe *per_tab = nullptr;
+  if (!agg) {
     size_t key = (n << 8) | ce;
     auto it = ctx->periodic.find(key);
     if (it == ctx->periodic.end()) {
@@ -381,12 +388,22 @@ extern "C" int zkl_eval_constraints(zkl_ctx *ctx, const zkl_trace_lde *h, const 
 // constraint commitment (hook 3)
 // ------------------------------------------------------------------------------------------------
 // ce_cm: coset-major CE evaluations (ce x n) on device; fills m.polys (num_cols x n) and commits.
+// E = 2 (quadratic extension): every composition column is an E column (v, 0); it is committed, opened and evaluated as the two
+// base columns v and 0, so m.width = 2 * num_cols with the odd columns identically zero.
+__global__ void k_spread_columns(const fe *__restrict__ src, size_t n, size_t ncols, fe *__restrict__ dst) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 2 * ncols * n) return;
+  size_t c = t / n, i = t - c * n;
+  st_fe(dst + t, (c & 1) ? fe_zero() : ld_fe(src + (c >> 1) * n + i));
+}
 static int dev_constraint_commit(zkl_ctx *ctx, fe *ce_cm, size_t n, size_t ce, size_t num_cols, const zkl_options *o, committed_matrix &m,
-                                 fe *overflow_flag) {
+                                 fe *overflow_flag, size_t E = 1) {
   size_t M = n * ce;
   domain_tables *tM; ZKL_TRY(get_tables(ctx, M, &tM));
-  m.width = num_cols; m.n = n; m.blowup = o->blowup; m.N = n * o->blowup;
-  ZKL_CHECK(ctx, m.polys.alloc(num_cols * n));
+  m.width = num_cols * E; m.n = n; m.blowup = o->blowup; m.N = n * o->blowup; m.ext = E;
+  dev_buf<fe> narrow;
+  if (E == 2) ZKL_CHECK(ctx, narrow.alloc(num_cols * n));
+  ZKL_CHECK(ctx, m.polys.alloc(m.width * n));
   ZKL_TRY(dev_interpolate(ctx, ce_cm, ce_cm, ce, n));  // per-coset inverse NTT in place
   auto it = ctx->opow.find(n | ((size_t)1 << 62));
   if (it == ctx->opow.end()) {
@@ -396,7 +413,8 @@ static int dev_constraint_commit(zkl_ctx *ctx, fe *ce_cm, size_t n, size_t ce, s
   }
   fe ginv_n = fe_pow(fe_inv(fe_from_u64(3)), n);
   LAUNCH(ctx, k_composition_finish, ceil_div(n, 128), 128, 0, ce_cm, (int)n, (int)ce, (int)num_cols, tM->wpow, M, it->second, ginv_n,
-         fe_inv(fe_from_u64(ce)), m.polys.p, overflow_flag);
+         fe_inv(fe_from_u64(ce)), E == 2 ? narrow.p : m.polys.p, overflow_flag);
+  if (E == 2) LAUNCH(ctx, k_spread_columns, ceil_div(2 * num_cols * n, 256), 256, 0, narrow.p, n, num_cols, m.polys.p);
   return commit_matrix(ctx, m, o);
 }
 
@@ -462,7 +480,7 @@ static void write_context_bytes(byte_writer &w, size_t W, size_t n, const zkl_op
   w.u8((uint8_t)W); w.u8(0); w.u8((uint8_t)ilog2_sz(n)); w.u16(0);
   w.u8(16); w.bytes(modulus_le, 16);
   w.usize(num_constraints);
-  w.u8((uint8_t)o.num_queries); w.u8((uint8_t)o.blowup); w.u8((uint8_t)o.grinding); w.u8(1);
+  w.u8((uint8_t)o.num_queries); w.u8((uint8_t)o.blowup); w.u8((uint8_t)o.grinding); w.u8(o.field_extension == 2 ? 2 : 1);
   w.u8((uint8_t)o.fri_folding); w.u8((uint8_t)o.fri_remainder_max_degree); w.u8(0); w.u8(0);
   w.u8((uint8_t)o.num_partitions); w.u8((uint8_t)o.hash_rate);
 }
@@ -479,6 +497,27 @@ static std::vector<uint32_t> fold_positions_host(const std::vector<uint32_t> &po
   return r;
 }
 
+// internal OOD layout [T(z): W | H(z): C | T(zg): W | H(zg): C] (C already counts the zero halves) -> the wire layout of the
+// quadratic extension: trace values widened to (a, 0)
+__global__ void k_ood_wire(const fe *__restrict__ ood, int W, int C, fe *__restrict__ out) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int half = 2 * W + C;
+  if (t >= 2 * half) return;
+  int h = t / half, r = t - h * half;
+  fe v;
+  if (r < 2 * W) v = (r & 1) ? fe_zero() : ld_fe(ood + h * (W + C) + (r >> 1));
+  else v = ld_fe(ood + h * (W + C) + W + (r - 2 * W));
+  st_fe(out + t, v);
+}
+// FRI leaves of an extension-field layer: leaf i = k + B i' hashes (ev[k][i'], 0, ev[k][i' + nd/2], 0); out is column-major [4][half]
+__global__ void k_fri_pairs_ext(const fe *__restrict__ ev, int nd, int B, fe *__restrict__ out) {
+  size_t half_rows = (size_t)nd / 2, total = half_rows * B;
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  size_t k = t / half_rows, ip = t - k * half_rows, leaf = k + (size_t)B * ip;
+  st_fe(out + leaf, ld_fe(ev + k * nd + ip)); st_fe(out + total + leaf, fe_zero());
+  st_fe(out + 2 * total + leaf, ld_fe(ev + k * nd + ip + half_rows)); st_fe(out + 3 * total + leaf, fe_zero());
+}
 static const char *k_stage_names[12] = {"coin_seed", "trace_lde_commit", "constraint_eval", "constraint_commit", "ood", "deep",
                                         "fri", "grind", "queries_serialize", "kernel:k_lde(trace)", "kernel:k_hash_rows(trace)",
                                         "host:air_build"};
@@ -493,7 +532,11 @@ static int prove_segment_impl(zkl_ctx *ctx, const fe *trace_dev, size_t W, size_
   ZKL_TRY(check_opts(ctx, o, n));
   if (air->cols.width != W) { ctx->set_error("air width does not match the trace"); return 1; }
   if (o->num_queries == 0 || o->num_queries > 255) { ctx->set_error("num_queries must be in [1,255]"); return 1; }
-  const size_t B = o->blowup, N = n * B, ce = air->ce_blowup, M = n * ce, C = air->num_composition_cols;
+  // E = 2: the quadratic extension. Every drawn E element is (a, 0) with this hasher (zkl_options.field_extension), so the arithmetic
+  // below is the base-field arithmetic of a step proof; C E-columns of the composition polynomial travel as Cw = 2 C base columns
+  // (odd ones zero), and wherever Winterfell hashes or serializes E elements the pairs (a, 0) are hashed / written.
+  const size_t E = o->field_extension == 2 ? 2 : 1;
+  const size_t B = o->blowup, N = n * B, ce = air->ce_blowup, M = n * ce, C = (size_t)air->num_composition_cols * E, Wt = W * E;
   const size_t ncc = (size_t)air->num_transition + air->num_assertions;
   const size_t nl = fri_num_layers(N, *o);
   if (nl + 1 > 40) { ctx->set_error("too many FRI layers"); return 1; }
@@ -503,7 +546,7 @@ static int prove_segment_impl(zkl_ctx *ctx, const fe *trace_dev, size_t W, size_
   const size_t logN = (size_t)ilog2_sz(N);
   const size_t max_open = (size_t)o->num_queries * (W + C + 2 * logN + nl * (2 + logN)) + 64;
   const size_t stage_need = sizeof(air_dev) + ((size_t)air->num_assertions + 2) * (sizeof(assertion_dev) + 4) + 256 * 4 + num_seed * sizeof(fe) +
-                            max_open * (sizeof(fe *) + 4 + sizeof(fe)) + (2 * (W + C) + nl + rem_cap_of(*o) + 64) * sizeof(fe) + 8192;
+                            max_open * (sizeof(fe *) + 4 + sizeof(fe)) + (4 * (W + C) + nl + rem_cap_of(*o) + 64) * sizeof(fe) + 8192;
   ZKL_TRY(stage_reserve(ctx, stage_need));
   domain_tables *tN; ZKL_TRY(get_tables(ctx, N, &tN));
   fe *opow; ZKL_TRY(get_offset_powers(ctx, n, &opow)); (void)opow;
@@ -556,7 +599,7 @@ static int prove_segment_impl(zkl_ctx *ctx, const fe *trace_dev, size_t W, size_
 
   // ---- 6. constraint commitment (hook build_constraint_commitment), reseed
   zkl_constraint_commitment cmt;
-  ZKL_TRY(dev_constraint_commit(ctx, ce_ev.p, n, ce, C, o, cmt.m, flag.p));
+  ZKL_TRY(dev_constraint_commit(ctx, ce_ev.p, n, ce, air->num_composition_cols, o, cmt.m, flag.p, E));
   STAGE_MARK();
 
   // ---- 7. OOD point z, evaluations at z and z*g, reseed with hash_elements(cur(z)||quot(z)||next(zg)||quot(zg))
@@ -570,14 +613,28 @@ static int prove_segment_impl(zkl_ctx *ctx, const fe *trace_dev, size_t W, size_
   LAUNCH(ctx, k_poly_eval, (unsigned)C, 256, 0, cmt.m.polys.p, (int)n, zpow.p, ood.p + W);
   LAUNCH(ctx, k_poly_eval, (unsigned)W, 256, 0, tl.m.polys.p, (int)n, zpow.p + n, ood.p + W + C);
   LAUNCH(ctx, k_poly_eval, (unsigned)C, 256, 0, cmt.m.polys.p, (int)n, zpow.p + n, ood.p + 2 * W + C);
-  if (quad) LAUNCH(ctx, k_quad_hash_elements_single, 1, ZKL_QUAD_GROUP, 0, ood.p, (int)(2 * (W + C)), ood_digest.p);
-  else LAUNCH(ctx, k_hash_elements_single, 1, ZKL_COOP_GROUP, 0, ood.p, (int)(2 * (W + C)), ood_digest.p);
+  // what is hashed and sent: the frame as E elements, [T(z) | H(z) | T(zg) | H(zg)] with every trace value widened to (a, 0)
+  dev_buf<fe> ood_wide;
+  const fe *ood_w = ood.p;
+  if (E == 2) {
+    ZKL_CHECK(ctx, ood_wide.alloc(2 * (Wt + C)));
+    LAUNCH(ctx, k_ood_wire, ceil_div(2 * (Wt + C), 128), 128, 0, ood.p, (int)W, (int)C, ood_wide.p);
+    ood_w = ood_wide.p;
+  }
+  if (quad) LAUNCH(ctx, k_quad_hash_elements_single, 1, ZKL_QUAD_GROUP, 0, ood_w, (int)(2 * (Wt + C)), ood_digest.p);
+  else LAUNCH(ctx, k_hash_elements_single, 1, ZKL_COOP_GROUP, 0, ood_w, (int)(2 * (Wt + C)), ood_digest.p);
   STAGE_MARK();
 
   // ---- 8. DEEP coefficients + composition over the LDE domain
   dev_buf<fe> dc, az, deep;
   ZKL_CHECK(ctx, dc.alloc(W + C)); ZKL_CHECK(ctx, az.alloc(2)); ZKL_CHECK(ctx, deep.alloc(N));
-  ZKL_TRY(reseed_draw(ood_digest.p, nullptr, W + C, dc.p));   // reseed with the OOD digest, draw the DEEP coefficients
+  if (E == 1) ZKL_TRY(reseed_draw(ood_digest.p, nullptr, W + C, dc.p));   // reseed with the OOD digest, draw the DEEP coefficients
+  else {   // one coefficient per E column: the zero halves of the composition columns get none
+    dev_buf<fe> drawn; ZKL_CHECK(ctx, drawn.alloc(W + C / 2));
+    ZKL_TRY(reseed_draw(ood_digest.p, nullptr, W + C / 2, drawn.p));
+    ZKL_CHECK(ctx, cudaMemcpyAsync(dc.p, drawn.p, W * sizeof(fe), cudaMemcpyDeviceToDevice, st));
+    LAUNCH(ctx, k_spread_columns, ceil_div(C, 256), 256, 0, drawn.p + W, (size_t)1, C / 2, dc.p + W);
+  }
   LAUNCH(ctx, k_deep_consts, 1, 32, 0, ood.p, dc.p, (int)W, (int)C, az.p);
   dev_buf<fe> deep_inv; ZKL_CHECK(ctx, deep_inv.alloc(N));
   LAUNCH(ctx, k_deep_inverses, ceil_div(N, 256 * DEEP_INV_PER_THREAD), 256, 0, N, (int)n, (int)B, z.p, g_n, tN->wpow, deep_inv.p);
@@ -594,7 +651,12 @@ static int prove_segment_impl(zkl_ctx *ctx, const fe *trace_dev, size_t W, size_
   for (size_t d = 0; d < nl; d++) {
     size_t half = nd * B / 2;
     ZKL_CHECK(ctx, f_leaves[d].alloc(half)); ZKL_CHECK(ctx, f_nodes[d].alloc(half)); ZKL_CHECK(ctx, f_ev[d + 1].alloc(half));
-    if (half >= bulk_min(ctx) && ctx->hash_path == 0) LAUNCH_TC(ctx, k_tc_fri_leaves, half, cur_ev, (int)nd, (int)B, f_leaves[d].p);
+    if (E == 2) {   // a leaf hashes two E elements: (v0, 0, v1, 0) — laid out as a 4-column matrix in natural leaf order
+      dev_buf<fe> pairs; ZKL_CHECK(ctx, pairs.alloc(4 * half));
+      LAUNCH(ctx, k_fri_pairs_ext, ceil_div(half, 256), 256, 0, cur_ev, (int)nd, (int)B, pairs.p);
+      ZKL_TRY(dev_hash_partitions(ctx, pairs.p, 4, half, 1, 4, f_leaves[d].p));
+    }
+    else if (half >= bulk_min(ctx) && ctx->hash_path == 0) LAUNCH_TC(ctx, k_tc_fri_leaves, half, cur_ev, (int)nd, (int)B, f_leaves[d].p);
     else if (quad) LAUNCH_QUAD(ctx, k_quad_fri_leaves, half, cur_ev, (int)nd, (int)B, f_leaves[d].p);
     else LAUNCH_COOP(ctx, k_fri_leaves, half, cur_ev, (int)nd, (int)B, f_leaves[d].p);
     ZKL_TRY(dev_merkle(ctx, f_leaves[d].p, f_nodes[d].p, half));
@@ -607,8 +669,15 @@ static int prove_segment_impl(zkl_ctx *ctx, const fe *trace_dev, size_t W, size_
   ZKL_CHECK(ctx, rem_rev.alloc(rem_len));
   LAUNCH(ctx, k_fri_remainder, 1, 32 > (int)nd ? 32 : (int)nd, 0, cur_ev, (int)nd, (int)B, tN->wpow, N, fe_inv(fe_from_u64(3)),
          fe_inv(fe_from_u64(nd * B)), rem_rev.p);
-  if (quad) LAUNCH(ctx, k_quad_hash_elements_single, 1, ZKL_QUAD_GROUP, 0, rem_rev.p, (int)rem_len, fri_roots.p + nl);
-  else LAUNCH(ctx, k_hash_elements_single, 1, ZKL_COOP_GROUP, 0, rem_rev.p, (int)rem_len, fri_roots.p + nl);
+  dev_buf<fe> rem_wide;
+  const fe *rem_w = rem_rev.p;
+  if (E == 2) {
+    ZKL_CHECK(ctx, rem_wide.alloc(2 * rem_len));
+    LAUNCH(ctx, k_spread_columns, ceil_div(2 * rem_len, 256), 256, 0, rem_rev.p, (size_t)1, rem_len, rem_wide.p);
+    rem_w = rem_wide.p;
+  }
+  if (quad) LAUNCH(ctx, k_quad_hash_elements_single, 1, ZKL_QUAD_GROUP, 0, rem_w, (int)(rem_len * E), fri_roots.p + nl);
+  else LAUNCH(ctx, k_hash_elements_single, 1, ZKL_COOP_GROUP, 0, rem_w, (int)(rem_len * E), fri_roots.p + nl);
   ZKL_TRY(reseed_draw(fri_roots.p + nl, nullptr, 0, nullptr));
   STAGE_MARK();
 
@@ -625,7 +694,7 @@ static int prove_segment_impl(zkl_ctx *ctx, const fe *trace_dev, size_t W, size_
   ZKL_CHECK(ctx, qseed.alloc(1)); ZKL_CHECK(ctx, qdraw.alloc(o->num_queries));
   struct mailbox { unsigned long long nonce; uint32_t cnt, pad; uint32_t pos[256]; fe troot, croot, z, flag; };
   mailbox *mb = (mailbox *)stage_alloc(ctx, sizeof(mailbox));
-  fe *ood_h = (fe *)stage_alloc(ctx, 2 * (W + C) * sizeof(fe)), *roots_h = (fe *)stage_alloc(ctx, (nl + 1) * sizeof(fe));
+  fe *ood_h = (fe *)stage_alloc(ctx, 2 * (Wt + C) * sizeof(fe)), *roots_h = (fe *)stage_alloc(ctx, (nl + 1) * sizeof(fe));
   fe *rem_h = (fe *)stage_alloc(ctx, rem_len * sizeof(fe));
   if (!mb || !ood_h || !roots_h || !rem_h) { ctx->set_error("staging buffer exhausted"); return 1; }
   uint64_t base = 1;
@@ -660,7 +729,7 @@ static int prove_segment_impl(zkl_ctx *ctx, const fe *trace_dev, size_t W, size_
     ZKL_CHECK(ctx, cudaMemcpyAsync(mb->pos, pos_dev.p, sizeof mb->pos, cudaMemcpyDeviceToHost, st));
     ZKL_CHECK(ctx, cudaMemcpyAsync(&mb->cnt, pos_cnt.p, 4, cudaMemcpyDeviceToHost, st));
     if (attempt == 0) {
-      ZKL_CHECK(ctx, cudaMemcpyAsync(ood_h, ood.p, 2 * (W + C) * sizeof(fe), cudaMemcpyDeviceToHost, st));
+      ZKL_CHECK(ctx, cudaMemcpyAsync(ood_h, ood_w, 2 * (Wt + C) * sizeof(fe), cudaMemcpyDeviceToHost, st));
       ZKL_CHECK(ctx, cudaMemcpyAsync(roots_h, fri_roots.p, (nl + 1) * sizeof(fe), cudaMemcpyDeviceToHost, st));
       ZKL_CHECK(ctx, cudaMemcpyAsync(rem_h, rem_rev.p, rem_len * sizeof(fe), cudaMemcpyDeviceToHost, st));
       ZKL_CHECK(ctx, cudaMemcpyAsync(&mb->troot, tl.m.nodes.p + 1, sizeof(fe), cudaMemcpyDeviceToHost, st));
@@ -746,21 +815,23 @@ static int prove_segment_impl(zkl_ctx *ctx, const fe *trace_dev, size_t W, size_
   write_queries(tl.m, tj_trace);
   write_queries(cmt.m, tj_cons);
   // OodFrame: trace states (current || next), constraint evaluations (current || next)
-  wr.u16((uint16_t)(2 * W * 16));
-  wr.bytes(ood_h, W * 16); wr.bytes(ood_h + W + C, W * 16);
+  wr.u16((uint16_t)(2 * Wt * 16));
+  wr.bytes(ood_h, Wt * 16); wr.bytes(ood_h + Wt + C, Wt * 16);
   wr.u16((uint16_t)(2 * C * 16));
-  wr.bytes(ood_h + W, C * 16); wr.bytes(ood_h + 2 * W + C, C * 16);
+  wr.bytes(ood_h + Wt, C * 16); wr.bytes(ood_h + 2 * Wt + C, C * 16);
   // FriProof
   wr.u8((uint8_t)nl);
   for (size_t d = 0; d < nl; d++) {
     size_t cnt = 2 * fri_counts[d];
     const fe *vals = got + gp; gp += cnt;
     byte_writer pw; write_batch_proof_bytes(pw, tj_fri[d].depth, take_lists(tj_fri[d]));
-    wr.u32((uint32_t)(cnt * 16)); wr.bytes(vals, cnt * 16);
+    wr.u32((uint32_t)(cnt * 16 * E));
+    if (E == 1) wr.bytes(vals, cnt * 16);
+    else for (size_t i = 0; i < cnt; i++) wr.digest(vals[i]);    // an E element (a, 0): 16 bytes + 16 zero bytes
     wr.u32((uint32_t)pw.b.size()); wr.bytes(pw.b.data(), pw.b.size());
   }
-  wr.u16((uint16_t)(rem_len * 16));
-  for (size_t i = 0; i < rem_len; i++) wr.felt(rem_h[i]);
+  wr.u16((uint16_t)(rem_len * 16 * E));
+  for (size_t i = 0; i < rem_len; i++) { if (E == 1) wr.felt(rem_h[i]); else wr.digest(rem_h[i]); }
   wr.u8(1);
   wr.u64(nonce_h);
   STAGE_MARK();

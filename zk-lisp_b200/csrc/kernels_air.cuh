@@ -24,6 +24,7 @@ struct air_dev {
   uint32_t f_poseidon, f_vm, f_sponge, f_merkle, f_ram, rom_enabled;
   uint32_t vm_usage_mask, ram_delta_clk_bits;
   uint32_t num_transition;
+  uint32_t air_kind;        // ZKL_AIR_ZKLISP / ZKL_AIR_AGG
   fe pose_mds[12][12];
   fe pose_rc[ZKL_ROUNDS][12];
   fe rom_mds[3][3];
@@ -399,6 +400,33 @@ __device__ __noinline__ fe eval_transition_combined(const air_dev *__restrict__ 
 #undef ADD
 #undef SUB
 
+// ZlAggAir::evaluate_transition (agg/air.rs:112-272; columns agg/layout.rs:97-180), combined with the coefficients: 24 constraints
+// over 31 columns, `p_last` is the AIR's one periodic column (is_last, cycle n).
+__device__ __noinline__ fe eval_transition_combined_agg(const frame_reader &f, fe p_last, const fe *__restrict__ cc) {
+  enum { OK = 0, V0_SUM, V1_SUM, VNEXT_SUM, FRI_V0, FRI_V1, FRI_VNEXT, FRI_ALPHA, FRI_X0, FRI_X1, FRI_Q1, COMP_SUM, ALPHA_DIV_ZM, MAP_L0, FINAL_LLAST,
+         R_, ALPHA, BETA, GAMMA, SEG_FIRST, TRACE_ROOT_ERR, CONS_ROOT_ERR, V_UNITS_ACC, V_UNITS_CHILD, CHILD_COUNT_ACC, VM_ERR, RAM_U_ERR, RAM_S_ERR,
+         ROM_ERR0, ROM_ERR1, ROM_ERR2 };
+  cc_acc out; out.cc = cc; out.ix = 0; out.acc = fe_zero(); wacc_zero(out.w); out.pending = 0;
+  const fe not_last = fe_sub(fe_one(), p_last);
+  out.emit(f.cur(OK));
+  out.emit(fe_mul(not_last, fe_sub(f.next(V_UNITS_ACC), fe_add(f.cur(V_UNITS_ACC), fe_mul(f.cur(V_UNITS_CHILD), f.cur(SEG_FIRST))))));
+  out.emit(f.cur(TRACE_ROOT_ERR));
+  out.emit(f.cur(CONS_ROOT_ERR));
+  const int chained[7] = {R_, ALPHA, BETA, GAMMA, V0_SUM, V1_SUM, VNEXT_SUM};
+#pragma unroll
+  for (int k = 0; k < 7; k++) out.emit(fe_mul(not_last, fe_sub(f.next(chained[k]), f.cur(chained[k]))));
+  out.emit(fe_mul(not_last, fe_sub(f.next(CHILD_COUNT_ACC), fe_add(f.cur(CHILD_COUNT_ACC), f.cur(SEG_FIRST)))));
+  const fe x0 = f.cur(FRI_X0), x1 = f.cur(FRI_X1), al = f.cur(FRI_ALPHA), vn = f.cur(FRI_VNEXT);
+  const fe rhs = fe_sub(fe_mul(f.cur(FRI_V1), fe_sub(al, x0)), fe_mul(f.cur(FRI_V0), fe_sub(al, x1)));
+  out.emit(fe_sub(fe_mul(vn, fe_sub(x1, x0)), rhs));
+  out.emit(fe_sub(vn, f.cur(FRI_Q1)));
+  const int zero_cols[10] = {COMP_SUM, ALPHA_DIV_ZM, MAP_L0, FINAL_LLAST, VM_ERR, RAM_U_ERR, RAM_S_ERR, ROM_ERR0, ROM_ERR1, ROM_ERR2};
+#pragma unroll
+  for (int k = 0; k < 10; k++) out.emit(f.cur(zero_cols[k]));
+  out.flush();
+  return out.acc;
+}
+
 // boundary data for the kernel: `slots` asserted columns, bpoly[(slot) * M + s] = P_c over the CE domain
 // (coset-major, M = ce*n), slot == nslots is P_S.
 struct boundary_dev {
@@ -440,8 +468,12 @@ __global__ void __launch_bounds__(128) k_eval_constraints(const air_dev *__restr
   // p_last(x) = L_{n-1}(x) = g_last * (x^n - 1) / (n * (x - g_last))   (k_plast_table)
   fe p_last = ld_fe(plast + t);
   (void)xn1;
-  const fe *per31 = per + ((size_t)kp * 32 + (i & 31)) * 31;
-  fe tr = eval_transition_combined(air, f, per31, p_last, cc);
+  fe tr;
+  if (air->air_kind == ZKL_AIR_AGG) tr = eval_transition_combined_agg(f, p_last, cc);
+  else {
+    const fe *per31 = per + ((size_t)kp * 32 + (i & 31)) * 31;
+    tr = eval_transition_combined(air, f, per31, p_last, cc);
+  }
   // transition divisor z(x) = (x^n - 1)/(x - g^(n-1))
   fe res = fe_mul(fe_mul(tr, xm), zinv);
   // boundary part: n/(x^n-1) * (sum_c T_c(x) P_c(x) - P_S(x))

@@ -420,10 +420,10 @@ static int dev_lde(zkl_ctx *ctx, const fe *polys, fe *out, size_t ncols, size_t 
   return 0;
 }
 // leaves[r] for the coset-major matrix `lde` (ncols x N); partition size per PartitionOptions
-static size_t partition_size_of(const zkl_options *o, size_t cols) {  // [WF-mem] PartitionOptions::partition_size
+static size_t partition_size_of(const zkl_options *o, size_t cols, size_t ext = 1) {  // [WF-mem] PartitionOptions::partition_size::<E>
   if (o->num_partitions == 1 && o->hash_rate == 0) return cols;
   size_t ps = (cols + o->num_partitions - 1) / o->num_partitions;
-  return std::max<size_t>(ps, o->hash_rate);
+  return std::max<size_t>(ps, o->hash_rate / ext);
 }
 // partition digests of a coset-major matrix: out[q * N + r] = hash_elements(row r, columns [q*ps, min(ncols, (q+1)*ps)))
 static int dev_hash_partitions(zkl_ctx *ctx, const fe *lde, size_t ncols, size_t n, size_t blowup, size_t ps, fe *out) {
@@ -446,8 +446,9 @@ static int dev_merge_partitions(zkl_ctx *ctx, const fe *parts, size_t stride, si
   return 0;
 }
 static int dev_hash_rows(zkl_ctx *ctx, const fe *lde, size_t ncols, size_t n, size_t blowup, const zkl_options *o, fe *leaves,
-                         dev_buf<fe> &scratch) {
-  size_t N = n * blowup, ps = partition_size_of(o, ncols);
+                         dev_buf<fe> &scratch, size_t ext = 1) {
+  // rows of E elements (ext base columns each): PartitionOptions::partition_size::<E> counts E columns, minimum hash_rate / E [WF-mem]
+  size_t N = n * blowup, ps = ext * partition_size_of(o, ncols / ext, ext);
   size_t nchunks = (ncols + ps - 1) / ps;
   if (nchunks == 1) return dev_hash_partitions(ctx, lde, ncols, n, blowup, ps, leaves);
   ZKL_CHECK(ctx, scratch.alloc(N * nchunks));
