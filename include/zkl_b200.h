@@ -387,6 +387,36 @@ int zkl_merge_partition_digests_dev(zkl_ctx *ctx, const void *digests_dev, size_
 int zkl_merkle_dev(zkl_ctx *ctx, const void *leaves_dev, size_t count, void *out_nodes_dev);
 int zkl_dev_download(zkl_ctx *ctx, void *host, const void *dev, size_t bytes);
 
+/* ---- column-sharded proof of ONE segment across the GPUs of a box (SURVEY.md §8e "single huge segment") ---------------------------
+ * Rank r owns whole column partitions (zkl_shard_columns; PartitionOptions must ask for >= world partitions). Per rank the flow is
+ * the single-GPU prover's, with four exchanges: (1) all-gather of the 16-byte partition digests (row leaves = merge_many of them),
+ * (2) all-to-all of the constraint-evaluation cosets — rank r evaluates CE cosets [r ce/world, (r+1) ce/world) on full-width rows and
+ * the evaluations are all-gathered, (3) sums of values with disjoint support (out-of-domain trace evaluations, opened trace rows) and
+ * of the DEEP partial sums, as 64-bit limb lanes, (4) nothing else: composition polynomial, FRI, grinding and query planning are
+ * replicated. Every rank returns the same proof bytes, identical to the single-GPU proof of the same trace and options.
+ * The collectives are the caller's (NCCL through torch.distributed in zk-lisp_b200/sharded.py, ncclComm in a Rust host): callbacks on
+ * DEVICE pointers of the calling rank, collective over all ranks, returning 0 once the result is complete in `recv` / `buf` (the
+ * library synchronises its stream before each call). */
+typedef struct {
+  int rank, world;             /* world must divide the constraint-evaluation blowup (8 for ZkLispAir): 1, 2, 4 or 8 */
+  void *user;
+  int (*all_gather)(void *user, const void *send_dev, void *recv_dev, size_t bytes_per_rank);   /* recv = [world][bytes_per_rank] */
+  int (*all_to_all)(void *user, const void *send_dev, void *recv_dev, size_t bytes_per_pair);   /* send, recv = [world][bytes_per_pair] */
+  int (*all_reduce_sum_u64)(void *user, void *buf_dev, size_t count);                            /* in place */
+} zkl_comm;
+/* [first_col, first_col + local_width) = the columns `rank` owns: contiguous blocks of ceil(P / world) whole partitions, P =
+ * ceil(width / partition_size). Fails unless every rank owns at least one partition. */
+int zkl_shard_columns(const zkl_options *opts, size_t width, int rank, int world, size_t *first_col, size_t *local_width);
+/* local_trace_dev: this rank's columns, local_width x n, column-major, in device memory. air / seed_elems describe the WHOLE trace. */
+int zkl_prove_segment_sharded_dev(zkl_ctx *ctx, const void *local_trace_dev, size_t first_col, size_t local_width, size_t width, size_t n,
+                                  const zkl_air_params *air, const zkl_fe *seed_elems, size_t num_seed, const zkl_options *opts,
+                                  const zkl_comm *comm, uint8_t *out_proof, size_t *out_len, zkl_proof_summary *summary);
+int zkl_prove_segment_sharded_pi_dev(zkl_ctx *ctx, const void *local_trace_dev, size_t first_col, size_t local_width, size_t width, size_t n,
+                                     const zkl_program *program, const zkl_public_inputs *pi, const zkl_options *opts, const zkl_comm *comm,
+                                     uint8_t *out_proof, size_t *out_len, zkl_proof_summary *summary);
+/* world = 1 with device-to-device copies as "collectives": single-GPU runs of the sharded code path (tests) */
+const zkl_comm *zkl_comm_loopback(void);
+
 /* ---- measurement helpers (bench.py) -------------------------------------------------------- */
 int zkl_timer_start(zkl_ctx *ctx);             /* CUDA event on the ctx stream */
 int zkl_timer_stop(zkl_ctx *ctx, float *ms);   /* second event, synchronised; elapsed device time */

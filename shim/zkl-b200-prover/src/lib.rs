@@ -109,6 +109,7 @@ pub fn zkl_options(o: &ProofOptions, p: PartitionOptions) -> sys::ZklOptions {
         hash_rate: 0,
         fri_folding: o.to_fri_options().folding_factor() as u32,
         fri_remainder_max_degree: o.to_fri_options().remainder_max_degree() as u32,
+        field_extension: o.field_extension() as u32, // FieldExtension::None = 1, Quadratic = 2
     }
 }
 
@@ -401,4 +402,36 @@ fn _assert_traits() {
     fn is_hasher<T: ElementHasher<BaseField = BE> + Hasher<Digest = PoseidonDigest>>() {}
     is_hasher::<H>();
     let _ = BE::MODULUS;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// the aggregation proof (prove.rs:526-581 hooks, :629-702 prove_agg_proof): same entry point, air_kind = ZKL_AIR_AGG
+// ------------------------------------------------------------------------------------------------------------------
+/// `trace`: the 31-column aggregation trace (`build_agg_trace_from_transcripts`, agg/trace.rs:155-247); `agg_pi` the aggregation
+/// public inputs; `options` as `prove_agg_proof` builds them (FieldExtension::Quadratic from 128 bits up). The coin seed is
+/// Context::to_elements() ++ AggAirPublicInputs::to_elements() (agg/pi.rs:176-217).
+pub fn prove_agg_full(ctx: &GpuCtx, trace: &ColMatrix<BE>, agg_pi: &zk_lisp_proof_winterfell::agg::pi::AggAirPublicInputs, options: &ProofOptions,
+                      partitions: (usize, usize), num_constraints: usize, trace_info: &TraceInfo) -> Result<Proof, String> {
+    use winterfell::math::ToElements;
+    let (w, n) = (trace.num_cols(), trace.num_rows());
+    let cols = column_major(trace);
+    let mut params: sys::ZklAirParams = unsafe { std::mem::zeroed() };
+    let mut assertions = [sys::ZklAssertion { column: 0, step: 0, value: sys::ZklFe::default() }; 5];
+    let rc = unsafe { sys::zkl_agg_air_params(n, agg_pi.v_units_total, agg_pi.children_count, &mut params, assertions.as_mut_ptr()) };
+    if rc != 0 {
+        return Err("zkl_agg_air_params: trace length must be a power of two >= 8".into());
+    }
+    assert_eq!((params.num_transition + params.num_assertions) as usize, num_constraints);
+    let mut seed: Vec<BE> = winterfell::Context::new::<BE>(trace_info.clone(), options.clone(), num_constraints).to_elements();
+    seed.extend(agg_pi.to_elements());
+    let mut opts = zkl_options(options, PartitionOptions::new(partitions.0, partitions.1));
+    opts.num_partitions = partitions.0 as u32;
+    opts.hash_rate = partitions.1 as u32;
+    let mut buf = vec![0u8; 1 << 20];
+    let mut len = buf.len();
+    let rc = unsafe { sys::zkl_prove_segment(ctx.raw(), cols.as_ptr().cast(), w, n, &params, seed.as_ptr().cast(), seed.len(), &opts, buf.as_mut_ptr(), &mut len, std::ptr::null_mut()) };
+    if rc != 0 {
+        return Err(last_error(ctx.raw()));
+    }
+    Proof::from_bytes(&buf[..len]).map_err(|e| e.to_string())
 }

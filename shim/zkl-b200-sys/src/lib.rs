@@ -97,7 +97,12 @@ pub struct ZklAirParams {
     pub rom_w_enc1: [ZklFe; 59],
     pub program_fe0: ZklFe,
     pub merkle_root_fe: ZklFe,
+    /// ZKL_AIR_ZKLISP (0) or ZKL_AIR_AGG (1)
+    pub air_kind: u32,
+    pub pad_: u32,
 }
+pub const ZKL_AIR_ZKLISP: u32 = 0;
+pub const ZKL_AIR_AGG: u32 = 1;
 #[repr(C)]
 #[derive(Clone, Copy, Default, Debug)]
 pub struct ZklOptions {
@@ -108,6 +113,8 @@ pub struct ZklOptions {
     pub hash_rate: u32,
     pub fri_folding: u32,
     pub fri_remainder_max_degree: u32,
+    /// winterfell::FieldExtension as u8: 1 = None, 2 = Quadratic
+    pub field_extension: u32,
 }
 #[repr(C)]
 pub struct ZklBatchProof {
@@ -190,6 +197,8 @@ extern "C" {
         out_params: *mut ZklAirParams, out_assertions: *mut ZklAssertion, num_assertions: *mut usize, out_seed: *mut ZklFe,
         num_seed: *mut usize, err: *mut c_char, err_cap: usize,
     ) -> c_int;
+
+    pub fn zkl_agg_air_params(n: usize, v_units_total: u64, children_count: u32, out_params: *mut ZklAirParams, out_assertions: *mut ZklAssertion) -> c_int;
 
     pub fn zkl_hash_elements_batch(ctx: *mut zkl_ctx, elems: *const ZklFe, len: usize, count: usize, out: *mut u8) -> c_int;
     pub fn zkl_merge_batch(ctx: *mut zkl_ctx, pairs: *const u8, count: usize, out: *mut u8) -> c_int;

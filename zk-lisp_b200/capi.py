@@ -87,6 +87,15 @@ class ProofSummary(C.Structure):
 
 
 ERR_BUFFER_TOO_SMALL, ERR_CONSTRAINTS_VIOLATED = 2, 3
+
+COMM_MOVE = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t)      # all_gather / all_to_all(user, send, recv, bytes)
+COMM_SUM = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t)                   # all_reduce_sum_u64(user, buf, count)
+
+
+class Comm(C.Structure):
+    """zkl_comm: the caller's collectives for the column-sharded prover."""
+    _fields_ = [("rank", C.c_int), ("world", C.c_int), ("user", C.c_void_p), ("all_gather", COMM_MOVE), ("all_to_all", COMM_MOVE),
+                ("all_reduce_sum_u64", COMM_SUM)]
 MAX_MAIN_SLOTS = 16
 
 
@@ -191,6 +200,12 @@ def load_library():
     sig("zkl_suite_derive", C.c_int, vp, C.POINTER(Suite))
     sig("zkl_air_build", C.c_int, C.POINTER(Program), C.POINTER(PublicInputsC), sz, sz, C.POINTER(Options), C.POINTER(AirParams), vp,
         C.POINTER(sz), vp, C.POINTER(sz), C.c_char_p, sz)
+    sig("zkl_shard_columns", C.c_int, C.POINTER(Options), sz, C.c_int, C.c_int, C.POINTER(sz), C.POINTER(sz))
+    sig("zkl_prove_segment_sharded_dev", C.c_int, vp, vp, sz, sz, sz, sz, C.POINTER(AirParams), vp, sz, C.POINTER(Options), C.POINTER(Comm), vp,
+        C.POINTER(sz), C.POINTER(ProofSummary))
+    sig("zkl_prove_segment_sharded_pi_dev", C.c_int, vp, vp, sz, sz, sz, sz, C.POINTER(Program), C.POINTER(PublicInputsC), C.POINTER(Options),
+        C.POINTER(Comm), vp, C.POINTER(sz), C.POINTER(ProofSummary))
+    sig("zkl_comm_loopback", C.POINTER(Comm))
     sig("zkl_agg_air_params", C.c_int, sz, C.c_uint64, C.c_uint32, C.POINTER(AirParams), C.POINTER(Assertion))
     sig("zkl_prove_segment_pi", C.c_int, vp, vp, sz, sz, C.POINTER(Program), C.POINTER(PublicInputsC), C.POINTER(Options), vp,
         C.POINTER(sz), C.POINTER(ProofSummary))
@@ -239,4 +254,5 @@ EXPORTED_SYMBOLS = [
     "zkl_prove_segment_dev", "zkl_stage_name", "zkl_dev_alloc", "zkl_dev_free", "zkl_dev_upload",
     "zkl_sync", "zkl_slice_segment_dev", "zkl_usage_mask_dev", "zkl_read_cells_dev", "zkl_timer_start", "zkl_timer_stop", "zkl_imad_peak", "zkl_set_bulk_threshold", "zkl_set_hash_path", "zkl_set_ntt_path", "zkl_set_coop_path", "zkl_bench_permute", "zkl_partition_size", "zkl_lde_dev", "zkl_hash_partitions_dev", "zkl_merge_partition_digests_dev", "zkl_merkle_dev", "zkl_dev_download", "zkl_merge_plan", "zkl_poseidon_levels_dev", "zkl_merge_with_int_pairs", "zkl_replay_children", "zkl_replay_status_name", "zkl_grind", "zkl_hash_two_lanes_host",
     "zkl_program_derive", "zkl_suite_derive", "zkl_air_build", "zkl_prove_segment_pi", "zkl_prove_segment_pi_dev", "zkl_tc_i8_peak", "zkl_agg_air_params",
+    "zkl_shard_columns", "zkl_prove_segment_sharded_dev", "zkl_prove_segment_sharded_pi_dev", "zkl_comm_loopback",
 ]

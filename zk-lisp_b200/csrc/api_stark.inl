@@ -293,8 +293,10 @@ static int upload_air(zkl_ctx *ctx, const zkl_air_params *a, size_t n, air_devic
 }
 
 // cc_dev: num_transition + num_assertions coefficients on the device. ce_out: ce*n evaluations, coset-major.
+// `rows` (column-sharded prover): the full-width rows of CE cosets kp0 .. kp0 + ncos - 1 as [W][ncos][n]; only those cosets are written.
+struct ce_rows { const fe *rows; int kp0, ncos; };
 static int dev_eval_constraints(zkl_ctx *ctx, const committed_matrix &t, const zkl_air_params *a, air_device_state &st, const fe *cc_dev,
-                                fe *ce_out) {
+                                fe *ce_out, const ce_rows *rows = nullptr) {
   size_t n = t.n, ce = a->ce_blowup, M = n * ce, N = t.N;
   if (ce > t.blowup || ce > 16 || (ce & (ce - 1))) { ctx->set_error("ce_blowup must be a power of two <= min(blowup, 16)"); return 1; }
   const bool agg = a->air_kind == ZKL_AIR_AGG;
@@ -354,8 +356,10 @@ static int dev_eval_constraints(zkl_ctx *ctx, const committed_matrix &t, const z
   ZKL_TRY(dev_interpolate(ctx, st.u.p, st.u.p, nb, n));
   ZKL_TRY(dev_lde(ctx, st.u.p, st.bpoly.p, nb, n, ce));
   boundary_dev bd{st.slot_col.p, st.bpoly.p, st.nslots};
-  LAUNCH(ctx, k_eval_constraints, ceil_div(M, 128), 128, 0, st.air.p, t.lde.p, N, (int)n, (int)t.blowup, (int)ce, per_tab, tN->wpow, cc_dev, bd,
-         coset_consts, plast, ce_out);
+  if (!rows) LAUNCH(ctx, k_eval_constraints, ceil_div(M, 128), 128, 0, st.air.p, t.lde.p, N, (int)n, (int)t.blowup, (int)ce, per_tab, tN->wpow, cc_dev, bd,
+                    coset_consts, plast, ce_out, N, 0, (int)ce, (int)(t.blowup / ce));
+  else LAUNCH(ctx, k_eval_constraints, ceil_div((size_t)rows->ncos * n, 128), 128, 0, st.air.p, rows->rows, N, (int)n, (int)t.blowup, (int)ce, per_tab, tN->wpow,
+              cc_dev, bd, coset_consts, plast, ce_out, (size_t)rows->ncos * n, rows->kp0, rows->ncos, 1);
   return 0;
 }
 
@@ -518,6 +522,52 @@ __global__ void k_fri_pairs_ext(const fe *__restrict__ ev, int nd, int B, fe *__
   st_fe(out + leaf, ld_fe(ev + k * nd + ip)); st_fe(out + total + leaf, fe_zero());
   st_fe(out + 2 * total + leaf, ld_fe(ev + k * nd + ip + half_rows)); st_fe(out + 3 * total + leaf, fe_zero());
 }
+// ---- column-sharded proving (include/zkl_b200.h: zkl_comm) ----
+struct shard_view { const zkl_comm *comm; size_t first_col, local_width; };
+// send[d][c][j][i] = lde[c][(d * ncl + j) * step][i]: the CE cosets every destination rank evaluates, for this rank's columns (rows of
+// columns beyond `wl` stay zero: every rank sends blocks of the same size)
+__global__ void k_pack_cosets(const fe *__restrict__ lde, size_t N, int n, int step, int wl, int wmax, int ncl, int world, fe *__restrict__ send) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t per_dest = (size_t)wmax * ncl * n;
+  if (t >= per_dest * world) return;
+  int d = (int)(t / per_dest); size_t u = t - (size_t)d * per_dest;
+  int c = (int)(u / ((size_t)ncl * n)); size_t v = u - (size_t)c * ncl * n;
+  int j = (int)(v / n), i = (int)(v - (size_t)j * n);
+  st_fe(send + t, c < wl ? ld_fe(lde + (size_t)c * N + (size_t)((d * ncl + j) * step) * n + i) : fe_zero());
+}
+// partial sums of field elements across ranks travel as four zero-extended 32-bit limbs each (exact under a u64 sum)
+__global__ void k_split_limbs(const fe *__restrict__ in, unsigned long long *__restrict__ out, size_t count) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= count) return;
+  fe v = ld_fe(in + t);
+#pragma unroll
+  for (int l = 0; l < 4; l++) out[4 * t + l] = v.l[l];
+}
+__global__ void k_merge_limbs(const unsigned long long *__restrict__ in, fe *__restrict__ out, size_t count) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= count) return;
+  uint32_t x[9]; unsigned long long carry = 0;
+#pragma unroll
+  for (int l = 0; l < 4; l++) { unsigned long long v = in[4 * t + l] + carry; x[l] = (uint32_t)v; carry = v >> 32; }
+  x[4] = (uint32_t)carry; x[5] = (uint32_t)(carry >> 32); x[6] = x[7] = x[8] = 0;
+  st_fe(out + t, reduce9(x));
+}
+static int shard_geometry(zkl_ctx *ctx, const zkl_options *o, size_t W, const shard_view *sh, size_t ce, size_t *ps_out, size_t *P_out, size_t *ppr_out) {
+  const int R = sh->comm->world, r = sh->comm->rank;
+  if (R < 1 || r < 0 || r >= R) { ctx->set_error("zkl_comm: bad rank / world"); return 1; }
+  if (!sh->comm->all_gather || !sh->comm->all_to_all || !sh->comm->all_reduce_sum_u64) { ctx->set_error("zkl_comm: missing collective callback"); return 1; }
+  if (ce % R) { ctx->set_error("the world size must divide the constraint-evaluation blowup (one or more CE cosets per rank)"); return 1; }
+  size_t f, wl;
+  if (zkl_shard_columns(o, W, r, R, &f, &wl)) { ctx->set_error("column sharding needs at least one whole partition per rank (PartitionOptions with >= world partitions)"); return 1; }
+  if (f != sh->first_col || wl != sh->local_width) { ctx->set_error("first_col / local_width do not match zkl_shard_columns for this rank"); return 1; }
+  const size_t ps = partition_size_of(o, W), P = (W + ps - 1) / ps;
+  *ps_out = ps; *P_out = P; *ppr_out = (P + R - 1) / R;
+  return 0;
+}
+static int comm_call(zkl_ctx *ctx, int rc, const char *what) {
+  if (rc) { ctx->set_error(std::string("collective callback failed: ") + what); return 1; }
+  return 0;
+}
 static const char *k_stage_names[12] = {"coin_seed", "trace_lde_commit", "constraint_eval", "constraint_commit", "ood", "deep",
                                         "fri", "grind", "queries_serialize", "kernel:k_lde(trace)", "kernel:k_hash_rows(trace)",
                                         "host:air_build"};
@@ -527,9 +577,23 @@ extern "C" const char *zkl_stage_name(int s) { return (s >= 0 && s < 12) ? k_sta
 // whole-segment prover: winterfell::Prover::prove, stages 1-11, everything on the device
 // ------------------------------------------------------------------------------------------------
 static int prove_segment_impl(zkl_ctx *ctx, const fe *trace_dev, size_t W, size_t n, const zkl_air_params *air, const zkl_fe *seed_elems,
-                              size_t num_seed, const zkl_options *o, uint8_t *out_proof, size_t *out_len, zkl_proof_summary *summary) {
+                              size_t num_seed, const zkl_options *o, uint8_t *out_proof, size_t *out_len, zkl_proof_summary *summary,
+                              const shard_view *sh = nullptr) {
   ZKL_TRY(need_suite(ctx));
   ZKL_TRY(check_opts(ctx, o, n));
+  // column-sharded mode: trace_dev holds this rank's Wl columns [first_col, first_col + Wl) of the W-column trace
+  const size_t Wl = sh ? sh->local_width : W, col0 = sh ? sh->first_col : 0;
+  const int R = sh ? sh->comm->world : 1, rk = sh ? sh->comm->rank : 0;
+  size_t sh_ps = 0, sh_P = 0, sh_ppr = 0;
+  if (sh) {
+    ZKL_TRY(shard_geometry(ctx, o, W, sh, air->ce_blowup, &sh_ps, &sh_P, &sh_ppr));
+    if (o->field_extension == 2) { ctx->set_error("column sharding is for step proofs (FieldExtension::None)"); return 1; }
+  }
+  auto owned = [&](int s, size_t *first, size_t *count) {   // columns of rank s
+    size_t lo = std::min(W, (size_t)s * sh_ppr * sh_ps), hi = std::min(W, ((size_t)s + 1) * sh_ppr * sh_ps);
+    *first = lo; *count = hi - lo;
+  };
+  auto wait_stream = [&]() -> int { return ctx_wait(ctx); };
   if (air->cols.width != W) { ctx->set_error("air width does not match the trace"); return 1; }
   if (o->num_queries == 0 || o->num_queries > 255) { ctx->set_error("num_queries must be in [1,255]"); return 1; }
   // E = 2: the quadratic extension. Every drawn E element is (a, 0) with this hasher (zkl_options.field_extension), so the arithmetic
@@ -584,7 +648,27 @@ static int prove_segment_impl(zkl_ctx *ctx, const fe *trace_dev, size_t W, size_
 
   // ---- 2. trace LDE + commitment (hook new_trace_lde), reseed with the root
   zkl_trace_lde tl;
-  ZKL_TRY(trace_commit_dev(ctx, trace_dev, W, n, o, &tl, &ctx->ev[12]));
+  if (!sh) ZKL_TRY(trace_commit_dev(ctx, trace_dev, W, n, o, &tl, &ctx->ev[12]));
+  else {
+    // local: iNTT, coset LDE and partition digests of the owned columns; exchange (1): 16 bytes per (row, partition) instead of the rows
+    committed_matrix &m = tl.m;
+    m.width = Wl; m.n = n; m.blowup = B; m.N = N;
+    ZKL_CHECK(ctx, m.polys.alloc(Wl * n)); ZKL_CHECK(ctx, m.lde.alloc(Wl * N)); ZKL_CHECK(ctx, m.leaves.alloc(N)); ZKL_CHECK(ctx, m.nodes.alloc(N));
+    ZKL_TRY(dev_interpolate(ctx, trace_dev, m.polys.p, Wl, n));
+    ZKL_CHECK(ctx, cudaEventRecord(ctx->ev[12], st));
+    ZKL_TRY(dev_lde(ctx, m.polys.p, m.lde.p, Wl, n, B));
+    ZKL_CHECK(ctx, cudaEventRecord(ctx->ev[13], st));
+    dev_buf<fe> mine, all;
+    ZKL_CHECK(ctx, mine.alloc(sh_ppr * N)); ZKL_CHECK(ctx, all.alloc((size_t)R * sh_ppr * N));
+    ZKL_CHECK(ctx, cudaMemsetAsync(mine.p, 0, sh_ppr * N * sizeof(fe), st));
+    ZKL_TRY(dev_hash_partitions(ctx, m.lde.p, Wl, n, B, sh_ps, mine.p));
+    ZKL_CHECK(ctx, cudaEventRecord(ctx->ev[14], st));
+    ZKL_TRY(wait_stream());
+    ZKL_TRY(comm_call(ctx, sh->comm->all_gather(sh->comm->user, mine.p, all.p, sh_ppr * N * sizeof(fe)), "all_gather(partition digests)"));
+    // rank s holds partitions [s ppr, min(P, (s+1) ppr)): slot s ppr + (q - s ppr) = q — the first P slots are the partitions in order
+    ZKL_TRY(dev_merge_partitions(ctx, all.p, N, N, sh_P, m.leaves.p));
+    ZKL_TRY(dev_merkle(ctx, m.leaves.p, m.nodes.p, N));
+  }
   STAGE_MARK();
 
   // ---- 4/5. composition coefficients (transition then boundary) and constraint evaluation
@@ -594,7 +678,27 @@ static int prove_segment_impl(zkl_ctx *ctx, const fe *trace_dev, size_t W, size_
   ZKL_CHECK(ctx, cc.alloc(ncc)); ZKL_CHECK(ctx, ce_ev.alloc(M)); ZKL_CHECK(ctx, flag.alloc(1));
   ZKL_CHECK(ctx, cudaMemsetAsync(flag.p, 0, sizeof(fe), st));
   ZKL_TRY(reseed_draw(tl.m.nodes.p + 1, nullptr, ncc, cc.p));   // reseed with the trace root, draw the composition coefficients
-  ZKL_TRY(dev_eval_constraints(ctx, tl.m, air, ast, cc.p, ce_ev.p));
+  if (!sh) ZKL_TRY(dev_eval_constraints(ctx, tl.m, air, ast, cc.p, ce_ev.p));
+  else {
+    // exchange (2): every rank evaluates ce / R constraint-evaluation cosets on FULL-width rows — the coset-major layout makes a coset
+    // the natural unit: all-to-all of [columns of the sender][cosets of the receiver][n], then all-gather of the evaluations
+    const size_t ncl = ce / R, wmax = sh_ppr * sh_ps, per_pair = wmax * ncl * n;
+    dev_buf<fe> send, recv, rows, ce_all;
+    ZKL_CHECK(ctx, send.alloc(per_pair * R)); ZKL_CHECK(ctx, recv.alloc(per_pair * R)); ZKL_CHECK(ctx, rows.alloc(W * ncl * n)); ZKL_CHECK(ctx, ce_all.alloc(M));
+    LAUNCH(ctx, k_pack_cosets, ceil_div(per_pair * R, 256), 256, 0, tl.m.lde.p, N, (int)n, (int)(B / ce), (int)Wl, (int)wmax, (int)ncl, R, send.p);
+    ZKL_TRY(wait_stream());
+    ZKL_TRY(comm_call(ctx, sh->comm->all_to_all(sh->comm->user, send.p, recv.p, per_pair * sizeof(fe)), "all_to_all(CE cosets)"));
+    for (int s2 = 0; s2 < R; s2++) {
+      size_t f, cnt; owned(s2, &f, &cnt);
+      if (cnt) ZKL_CHECK(ctx, cudaMemcpyAsync(rows.p + f * ncl * n, recv.p + (size_t)s2 * per_pair, cnt * ncl * n * sizeof(fe), cudaMemcpyDeviceToDevice, st));
+    }
+    ce_rows cr{rows.p, (int)(rk * ncl), (int)ncl};
+    ZKL_TRY(dev_eval_constraints(ctx, tl.m, air, ast, cc.p, ce_ev.p, &cr));
+    ZKL_TRY(wait_stream());
+    ZKL_TRY(comm_call(ctx, sh->comm->all_gather(sh->comm->user, ce_ev.p + (size_t)rk * ncl * n, ce_all.p, ncl * n * sizeof(fe)), "all_gather(CE evaluations)"));
+    ZKL_CHECK(ctx, cudaMemcpyAsync(ce_ev.p, ce_all.p, M * sizeof(fe), cudaMemcpyDeviceToDevice, st));
+    ZKL_TRY(wait_stream());   // ce_all, send, recv die at the end of this block: their frees are stream-ordered, the copies above are done
+  }
   STAGE_MARK();
 
   // ---- 6. constraint commitment (hook build_constraint_commitment), reseed
@@ -609,9 +713,15 @@ static int prove_segment_impl(zkl_ctx *ctx, const fe *trace_dev, size_t W, size_
   fe g_n = host_root_of_unity(ilog2_sz(n));
   LAUNCH(ctx, k_powers_dev, ceil_div(n, 128), 128, 0, z.p, fe_one(), zpow.p, (int)n);
   LAUNCH(ctx, k_powers_dev, ceil_div(n, 128), 128, 0, z.p, g_n, zpow.p + n, (int)n);
-  LAUNCH(ctx, k_poly_eval, (unsigned)W, 256, 0, tl.m.polys.p, (int)n, zpow.p, ood.p);
+  if (sh) ZKL_CHECK(ctx, cudaMemsetAsync(ood.p, 0, 2 * (W + C) * sizeof(fe), st));
+  LAUNCH(ctx, k_poly_eval, (unsigned)Wl, 256, 0, tl.m.polys.p, (int)n, zpow.p, ood.p + col0);
+  LAUNCH(ctx, k_poly_eval, (unsigned)Wl, 256, 0, tl.m.polys.p, (int)n, zpow.p + n, ood.p + W + C + col0);
+  if (sh) {   // exchange (3a): every rank evaluated its own columns; the supports are disjoint, so a u64 sum assembles the frame exactly
+    ZKL_TRY(wait_stream());
+    ZKL_TRY(comm_call(ctx, sh->comm->all_reduce_sum_u64(sh->comm->user, ood.p, 2 * W), "all_reduce(OOD trace, z)"));
+    ZKL_TRY(comm_call(ctx, sh->comm->all_reduce_sum_u64(sh->comm->user, ood.p + W + C, 2 * W), "all_reduce(OOD trace, zg)"));
+  }
   LAUNCH(ctx, k_poly_eval, (unsigned)C, 256, 0, cmt.m.polys.p, (int)n, zpow.p, ood.p + W);
-  LAUNCH(ctx, k_poly_eval, (unsigned)W, 256, 0, tl.m.polys.p, (int)n, zpow.p + n, ood.p + W + C);
   LAUNCH(ctx, k_poly_eval, (unsigned)C, 256, 0, cmt.m.polys.p, (int)n, zpow.p + n, ood.p + 2 * W + C);
   // what is hashed and sent: the frame as E elements, [T(z) | H(z) | T(zg) | H(zg)] with every trace value widened to (a, 0)
   dev_buf<fe> ood_wide;
@@ -635,10 +745,33 @@ static int prove_segment_impl(zkl_ctx *ctx, const fe *trace_dev, size_t W, size_
     ZKL_CHECK(ctx, cudaMemcpyAsync(dc.p, drawn.p, W * sizeof(fe), cudaMemcpyDeviceToDevice, st));
     LAUNCH(ctx, k_spread_columns, ceil_div(C, 256), 256, 0, drawn.p + W, (size_t)1, C / 2, dc.p + W);
   }
-  LAUNCH(ctx, k_deep_consts, 1, 32, 0, ood.p, dc.p, (int)W, (int)C, az.p);
   dev_buf<fe> deep_inv; ZKL_CHECK(ctx, deep_inv.alloc(N));
   LAUNCH(ctx, k_deep_inverses, ceil_div(N, 256 * DEEP_INV_PER_THREAD), 256, 0, N, (int)n, (int)B, z.p, g_n, tN->wpow, deep_inv.p);
-  LAUNCH(ctx, k_deep, ceil_div(N, 256), 256, 0, tl.m.lde.p, cmt.m.lde.p, N, (int)n, (int)B, (int)W, (int)C, dc.p, az.p, z.p, g_n, tN->wpow, deep_inv.p, deep.p);
+  if (!sh) {
+    LAUNCH(ctx, k_deep_consts, 1, 32, 0, ood.p, dc.p, (int)W, (int)C, az.p);
+    LAUNCH(ctx, k_deep, ceil_div(N, 256), 256, 0, tl.m.lde.p, cmt.m.lde.p, N, (int)n, (int)B, (int)W, (int)C, dc.p, az.p, z.p, g_n, tN->wpow, deep_inv.p, deep.p);
+  } else {
+    // the DEEP composition is linear in the columns: every rank sums over ITS trace columns (rank 0 adds the composition columns);
+    // exchange (3b): the partial sums are added as 64-bit limb lanes and normalised
+    const size_t Cl = rk == 0 ? C : 0;
+    dev_buf<fe> dcl, oodl; dev_buf<unsigned long long> limbs;
+    ZKL_CHECK(ctx, dcl.alloc(Wl + Cl + 1)); ZKL_CHECK(ctx, oodl.alloc(2 * (Wl + Cl) + 1)); ZKL_CHECK(ctx, limbs.alloc(4 * N));
+    ZKL_CHECK(ctx, cudaMemcpyAsync(dcl.p, dc.p + col0, Wl * sizeof(fe), cudaMemcpyDeviceToDevice, st));
+    ZKL_CHECK(ctx, cudaMemcpyAsync(oodl.p, ood.p + col0, Wl * sizeof(fe), cudaMemcpyDeviceToDevice, st));
+    ZKL_CHECK(ctx, cudaMemcpyAsync(oodl.p + Wl + Cl, ood.p + W + C + col0, Wl * sizeof(fe), cudaMemcpyDeviceToDevice, st));
+    if (Cl) {
+      ZKL_CHECK(ctx, cudaMemcpyAsync(dcl.p + Wl, dc.p + W, C * sizeof(fe), cudaMemcpyDeviceToDevice, st));
+      ZKL_CHECK(ctx, cudaMemcpyAsync(oodl.p + Wl, ood.p + W, C * sizeof(fe), cudaMemcpyDeviceToDevice, st));
+      ZKL_CHECK(ctx, cudaMemcpyAsync(oodl.p + 2 * Wl + Cl, ood.p + 2 * W + C, C * sizeof(fe), cudaMemcpyDeviceToDevice, st));
+    }
+    LAUNCH(ctx, k_deep_consts, 1, 32, 0, oodl.p, dcl.p, (int)Wl, (int)Cl, az.p);
+    LAUNCH(ctx, k_deep, ceil_div(N, 256), 256, 0, tl.m.lde.p, cmt.m.lde.p, N, (int)n, (int)B, (int)Wl, (int)Cl, dcl.p, az.p, z.p, g_n, tN->wpow, deep_inv.p, deep.p);
+    LAUNCH(ctx, k_split_limbs, ceil_div(N, 256), 256, 0, deep.p, limbs.p, N);
+    ZKL_TRY(wait_stream());
+    ZKL_TRY(comm_call(ctx, sh->comm->all_reduce_sum_u64(sh->comm->user, limbs.p, 4 * N), "all_reduce(DEEP partial sums)"));
+    LAUNCH(ctx, k_merge_limbs, ceil_div(N, 256), 256, 0, limbs.p, deep.p, N);
+    ZKL_TRY(wait_stream());
+  }
   STAGE_MARK();
 
   // ---- 9. FRI layers
@@ -755,10 +888,14 @@ static int prove_segment_impl(zkl_ctx *ctx, const fe *trace_dev, size_t W, size_
   bool g_overflow = false;
   auto want = [&](const fe *src, uint32_t idx) { if (g_cnt < max_open) { g_src[g_cnt] = src; g_idx[g_cnt] = idx; g_cnt++; } else g_overflow = true; };
   struct tree_job { std::vector<std::vector<node_ref>> plan; int depth; };
+  dev_buf<fe> zero_fe;
+  if (sh) { ZKL_CHECK(ctx, zero_fe.alloc(1)); ZKL_CHECK(ctx, cudaMemsetAsync(zero_fe.p, 0, sizeof(fe), st)); }
   auto plan_matrix = [&](const committed_matrix &m, tree_job &tj) {
+    const bool sharded_cols = sh && &m == &tl.m;   // the trace matrix holds this rank's columns only: the others are opened as zero and summed in
     for (uint32_t p : pos) {
       uint32_t s = (uint32_t)((p % m.blowup) * m.n + p / m.blowup);
-      for (size_t c = 0; c < m.width; c++) want(m.lde.p + c * m.N, s);   // per-column base: width * N exceeds 32 bits for large segments
+      if (!sharded_cols) for (size_t c = 0; c < m.width; c++) want(m.lde.p + c * m.N, s);   // per-column base: width * N exceeds 32 bits for large segments
+      else for (size_t c = 0; c < W; c++) { if (c >= col0 && c < col0 + Wl) want(m.lde.p + (c - col0) * m.N, s); else want(zero_fe.p, 0); }
     }
     tj.plan = batch_proof_plan(pos, m.N); tj.depth = ilog2_sz(m.N);
     for (auto &l : tj.plan) for (auto &r : l) want(r.leaf ? m.leaves.p : m.nodes.p, r.index);
@@ -789,6 +926,10 @@ static int prove_segment_impl(zkl_ctx *ctx, const fe *trace_dev, size_t W, size_
     ZKL_CHECK(ctx, cudaMemcpyAsync(dsrc.p, g_src, g_cnt * sizeof(fe *), cudaMemcpyHostToDevice, st));
     ZKL_CHECK(ctx, cudaMemcpyAsync(didx.p, g_idx, g_cnt * 4, cudaMemcpyHostToDevice, st));
     LAUNCH(ctx, k_gather_multi, ceil_div(g_cnt, 256), 256, 0, dsrc.p, didx.p, (int)g_cnt, dout.p);
+    if (sh) {   // exchange (3c): the opened trace rows are the first pos x W entries; disjoint supports again
+      ZKL_TRY(wait_stream());
+      ZKL_TRY(comm_call(ctx, sh->comm->all_reduce_sum_u64(sh->comm->user, dout.p, 2 * pos.size() * W), "all_reduce(opened trace rows)"));
+    }
     ZKL_CHECK(ctx, cudaMemcpyAsync(got, dout.p, g_cnt * sizeof(fe), cudaMemcpyDeviceToHost, st));
     ZKL_TRY(ctx_wait(ctx));
   }
@@ -806,7 +947,7 @@ static int prove_segment_impl(zkl_ctx *ctx, const fe *trace_dev, size_t W, size_
     return lists;
   };
   auto write_queries = [&](const committed_matrix &m, const tree_job &tj) {
-    size_t cnt = pos.size() * m.width;
+    size_t cnt = pos.size() * (&m == &tl.m ? W : m.width);
     const fe *rows = got + gp; gp += cnt;
     byte_writer pw; write_batch_proof_bytes(pw, tj.depth, take_lists(tj));
     wr.usize(cnt * 16); wr.bytes(rows, cnt * 16);
@@ -900,6 +1041,44 @@ extern "C" int zkl_prove_segment_pi(zkl_ctx *ctx, const zkl_fe *trace, size_t wi
   // the trace goes first so that its transfer overlaps the host-side AIR construction
   ZKL_CHECK(ctx, cudaMemcpyAsync(tr.p, trace, width * n * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream));
   return prove_segment_pi_impl(ctx, tr.p, width, n, program, pi, opts, out_proof, out_len, summary);
+}
+
+// ---- column-sharded proof of one segment (include/zkl_b200.h: zkl_comm) ----
+extern "C" int zkl_shard_columns(const zkl_options *o, size_t width, int rank, int world, size_t *first_col, size_t *local_width) {
+  if (world < 1 || rank < 0 || rank >= world || width == 0) return 1;
+  const size_t ps = partition_size_of(o, width), P = (width + ps - 1) / ps;
+  if (P < 2 && world > 1) return 1;
+  const size_t ppr = (P + world - 1) / world;
+  const size_t lo = std::min(width, (size_t)rank * ppr * ps), hi = std::min(width, ((size_t)rank + 1) * ppr * ps);
+  if (hi <= lo) return 1;                                      // a rank without a partition
+  if ((size_t)(world - 1) * ppr >= P) return 1;                 // the last rank would own nothing
+  *first_col = lo; *local_width = hi - lo;
+  return 0;
+}
+extern "C" int zkl_prove_segment_sharded_dev(zkl_ctx *ctx, const void *local_trace_dev, size_t first_col, size_t local_width, size_t width, size_t n,
+                                             const zkl_air_params *air, const zkl_fe *seed_elems, size_t num_seed, const zkl_options *opts,
+                                             const zkl_comm *comm, uint8_t *out_proof, size_t *out_len, zkl_proof_summary *summary) {
+  if (!comm) { ctx->set_error("zkl_comm is required"); return 1; }
+  shard_view sh{comm, first_col, local_width};
+  return prove_segment_impl(ctx, (const fe *)local_trace_dev, width, n, air, seed_elems, num_seed, opts, out_proof, out_len, summary, &sh);
+}
+extern "C" int zkl_prove_segment_sharded_pi_dev(zkl_ctx *ctx, const void *local_trace_dev, size_t first_col, size_t local_width, size_t width, size_t n,
+                                                const zkl_program *program, const zkl_public_inputs *pi, const zkl_options *opts,
+                                                const zkl_comm *comm, uint8_t *out_proof, size_t *out_len, zkl_proof_summary *summary) {
+  if (!comm) { ctx->set_error("zkl_comm is required"); return 1; }
+  built_air b;
+  if (build_air_host(program, pi, width, n, opts, b)) { ctx->set_error(b.err); return 1; }
+  shard_view sh{comm, first_col, local_width};
+  return prove_segment_impl(ctx, (const fe *)local_trace_dev, width, n, &b.p, b.seed.data(), b.seed.size(), opts, out_proof, out_len, summary, &sh);
+}
+// world = 1: the "collectives" are device-to-device copies (all_gather / all_to_all of one block) and a no-op (sum over one rank)
+static int loop_copy(void *, const void *send, void *recv, size_t bytes) {
+  return cudaMemcpy(recv, send, bytes, cudaMemcpyDeviceToDevice) == cudaSuccess ? 0 : 1;
+}
+static int loop_sum(void *, void *, size_t) { return 0; }
+extern "C" const zkl_comm *zkl_comm_loopback(void) {
+  static const zkl_comm c{0, 1, nullptr, loop_copy, loop_copy, loop_sum};
+  return &c;
 }
 
 extern "C" int zkl_dev_alloc(zkl_ctx *ctx, size_t bytes, void **out_dev) { ZKL_CHECK(ctx, cudaSetDevice(ctx->device)); ZKL_CHECK(ctx, cudaMalloc(out_dev, bytes)); return 0; }

@@ -448,16 +448,22 @@ __global__ void k_plast_table(const fe *__restrict__ wpowN, size_t N, int n, int
 }
 
 // ce_out[k'*n + i] = transition/Z + boundary   (coset-major over the CE domain)
+// The call covers CE cosets kp0 .. kp0 + ncos - 1. `lde` holds them `cos_step * n` elements apart with column stride `cstride`:
+// the whole coset-major LDE (kp0 = 0, ncos = ce, cos_step = blowup / ce, cstride = N) or, in the column-sharded prover, the rows a
+// rank received for ITS cosets (cos_step = 1, cstride = ncos * n). Tables and the output are indexed by the global (kp, i).
 __global__ void __launch_bounds__(128) k_eval_constraints(const air_dev *__restrict__ air, const fe *__restrict__ lde, size_t N, int n, int blowup,
                                                           int ce, const fe *__restrict__ per, const fe *__restrict__ wpowN,
                                                           const fe *__restrict__ cc, boundary_dev bd, const fe *__restrict__ coset_consts,
-                                                          const fe *__restrict__ plast, fe *__restrict__ ce_out) {
-  int t = blockIdx.x * blockDim.x + threadIdx.x;
+                                                          const fe *__restrict__ plast, fe *__restrict__ ce_out, size_t cstride, int kp0, int ncos,
+                                                          int cos_step) {
+  int tl = blockIdx.x * blockDim.x + threadIdx.x;
   size_t M = (size_t)ce * n;
-  if ((size_t)t >= M) return;
-  int kp = t / n, i = t - kp * n;
+  if ((size_t)tl >= (size_t)ncos * n) return;
+  int j = tl / n, i = tl - j * n, kp = kp0 + j;
+  int t = kp * n + i;
   int step = blowup / ce, k = kp * step;
-  frame_reader f{lde + (size_t)k * n + i, lde + (size_t)k * n + ((i + 1) & (n - 1)), N};
+  const fe *cbase = lde + (size_t)j * cos_step * n;
+  frame_reader f{cbase + i, cbase + ((i + 1) & (n - 1)), cstride};
   // x = g * w_N^(k + blowup*i)
   fe x = fe_mul(fe_from_u64(3), ld_fe(wpowN + ((size_t)k + (size_t)blowup * i)));
   // per-coset constants: [0] = (x^n - 1)^-1, [1] = x^n - 1 ; global: g_n^-1 = w_N^(N - blowup), n^-1

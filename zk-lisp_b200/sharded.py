@@ -137,3 +137,85 @@ class ShardedTraceCommit:
         self.bytes_exchanged = (self.world - 1) * (p.parts_per_rank * N * 16 + per * 16)
         self.bytes_unsharded_rows = (self.world - 1) * ncols * N * 16
         return root.tobytes() + bytes(16), p
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The whole proof on column-sharded data (include/zkl_b200.h: zkl_comm, zkl_prove_segment_sharded_*): the flow lives in the library
+# (csrc/api_stark.inl: prove_segment_impl with a shard_view); this side provides the collectives and the column plan.
+# ---------------------------------------------------------------------------------------------------------------------
+class _DevMem:
+    """A device pointer as a torch tensor (no copy) through __cuda_array_interface__."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
+class TorchComm:
+    """`zkl_comm` over torch.distributed (NCCL): all-gather, all-to-all and a u64 sum on the calling rank's device pointers."""
+
+    def __init__(self, dist, device):
+        import ctypes as C
+        import torch
+        from . import capi
+        self.dist, self.device, self.torch = dist, device, torch
+        self.bytes_moved = 0
+
+        def view(ptr, nbytes):
+            return torch.as_tensor(_DevMem(ptr, nbytes), device=device)
+
+        def guard(fn):
+            def run(*a):
+                try:
+                    fn(*a)
+                    torch.cuda.synchronize(device)
+                    return 0
+                except Exception as e:      # a Python exception must not unwind through the C caller
+                    self.error = repr(e)
+                    return 1
+            return run
+
+        def all_gather(user, send, recv, nbytes):
+            self.bytes_moved += (dist.get_world_size() - 1) * nbytes
+            dist.all_gather_into_tensor(view(recv, nbytes * dist.get_world_size()), view(send, nbytes))
+
+        def all_to_all(user, send, recv, nbytes):
+            w = dist.get_world_size()
+            self.bytes_moved += (w - 1) * nbytes
+            dist.all_to_all_single(view(recv, nbytes * w), view(send, nbytes * w))
+
+        def all_reduce(user, buf, count):
+            self.bytes_moved += 8 * count
+            dist.all_reduce(view(buf, 8 * count).view(torch.int64), op=dist.ReduceOp.SUM)   # two's-complement sum = unsigned sum mod 2^64
+
+        self._keep = (capi.COMM_MOVE(guard(all_gather)), capi.COMM_MOVE(guard(all_to_all)), capi.COMM_SUM(guard(all_reduce)))
+        self.c = capi.Comm(dist.get_rank(), dist.get_world_size(), None, *self._keep)
+        self.error = None
+        del C
+
+
+def shard_columns(lib, opts, width: int, rank: int, world: int):
+    """`zkl_shard_columns`: [first, first + count) of the columns `rank` owns (whole partitions, contiguous blocks)."""
+    import ctypes as C
+    oc = opts.to_c()
+    f, w = C.c_size_t(), C.c_size_t()
+    if lib.zkl_shard_columns(C.byref(oc), width, rank, world, C.byref(f), C.byref(w)):
+        raise ValueError("column sharding needs PartitionOptions with at least one whole partition per rank")
+    return f.value, w.value
+
+
+def prove_segment_sharded(ctx, comm_c, local_trace_dev: int, first_col: int, local_width: int, width: int, n: int, opts, air_pi) -> bytes:
+    """This rank's part of the column-sharded proof of one segment; every rank returns the same bytes — the single-GPU proof.
+    `comm_c`: a capi.Comm (TorchComm(...).c, or `lib.zkl_comm_loopback()` for one rank). `local_trace_dev`: device pointer to the
+    rank's columns (local_width x n, column-major)."""
+    import ctypes as C
+    import numpy as np
+    from . import capi
+    from .prover import program_constants, public_inputs_to_c
+    core = air_pi.core
+    prog, pi, o = program_constants(core.program_id, core.program_commitment), public_inputs_to_c(air_pi), opts.to_c()
+    buf = np.empty(4 << 20, dtype=np.uint8)
+    cap = C.c_size_t(buf.shape[0])
+    summ = capi.ProofSummary()
+    ctx._check(ctx.lib.zkl_prove_segment_sharded_pi_dev(ctx.h, C.c_void_p(local_trace_dev), first_col, local_width, width, n, C.byref(prog), C.byref(pi),
+                                                        C.byref(o), comm_c, buf.ctypes.data, C.byref(cap), C.byref(summ)))
+    return buf[:cap.value].tobytes()
