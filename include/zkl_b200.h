@@ -388,15 +388,21 @@ int zkl_merkle_dev(zkl_ctx *ctx, const void *leaves_dev, size_t count, void *out
 int zkl_dev_download(zkl_ctx *ctx, void *host, const void *dev, size_t bytes);
 
 /* ---- column-sharded proof of ONE segment across the GPUs of a box (SURVEY.md §8e "single huge segment") ---------------------------
- * Rank r owns whole column partitions (zkl_shard_columns; PartitionOptions must ask for >= world partitions). Per rank the flow is
- * the single-GPU prover's, with four exchanges: (1) all-gather of the 16-byte partition digests (row leaves = merge_many of them),
- * (2) all-to-all of the constraint-evaluation cosets — rank r evaluates CE cosets [r ce/world, (r+1) ce/world) on full-width rows and
- * the evaluations are all-gathered, (3) sums of values with disjoint support (out-of-domain trace evaluations, opened trace rows) and
- * of the DEEP partial sums, as 64-bit limb lanes, (4) nothing else: composition polynomial, FRI, grinding and query planning are
- * replicated. Every rank returns the same proof bytes, identical to the single-GPU proof of the same trace and options.
- * The collectives are the caller's (NCCL through torch.distributed in zk-lisp_b200/sharded.py, ncclComm in a Rust host): callbacks on
- * DEVICE pointers of the calling rank, collective over all ranks, returning 0 once the result is complete in `recv` / `buf` (the
- * library synchronises its stream before each call). */
+ * Rank r owns whole column partitions (zkl_shard_columns; PartitionOptions must ask for >= world partitions), the LDE cosets
+ * [r B / R, (r + 1) B / R) of everything that is not column-sharded, and the Merkle sub-tree over the rows [r N / R, (r + 1) N / R).
+ * Per rank the flow is the single-GPU prover's with these exchanges:
+ *  (1) trace commitment: all-to-all of the 16-byte partition digests (every rank receives all partitions of ITS rows and merges them
+ *      into leaves), all-gather of the leaves, all-gather of the per-rank sub-trees;
+ *  (2) constraint evaluation: all-to-all of the constraint-evaluation cosets (rank r evaluates CE cosets [r ce / R, (r + 1) ce / R) on
+ *      full-width rows), all-gather of the evaluations; composition columns on every rank, their row hashes per coset range;
+ *  (3) sums of values with disjoint support (out-of-domain trace evaluations; every opened element) as 64-bit lanes;
+ *  (4) DEEP: partial sums over the owned columns, reduce-scatter by coset range (all-to-all + field addition);
+ *  (5) FRI per coset range: leaves hashed and folded locally, leaves and sub-trees all-gathered, until a layer is smaller than
+ *      zkl_set_shard_min_leaves — from there on (and for grinding and the query plan) every rank does the same work.
+ * Every rank returns the same proof bytes, identical to the single-GPU proof of the same trace and options.
+ * The collectives are the caller's (NCCL through torch.distributed in zk-lisp_b200/sharded.py, ncclComm in a Rust host, or
+ * zkl_comm_local_* below for the threads of one process): callbacks on DEVICE pointers of the calling rank, collective over all ranks,
+ * returning 0 once the result is complete in `recv` / `buf` (the library synchronises its stream before each call). */
 typedef struct {
   int rank, world;             /* world must divide the constraint-evaluation blowup (8 for ZkLispAir): 1, 2, 4 or 8 */
   void *user;
@@ -416,6 +422,15 @@ int zkl_prove_segment_sharded_pi_dev(zkl_ctx *ctx, const void *local_trace_dev, 
                                      uint8_t *out_proof, size_t *out_len, zkl_proof_summary *summary);
 /* world = 1 with device-to-device copies as "collectives": single-GPU runs of the sharded code path (tests) */
 const zkl_comm *zkl_comm_loopback(void);
+/* Collectives for `world` proving THREADS of one process, one zkl_ctx each, on one device or on several devices of a box (peer copies):
+ * publish the pointer, barrier, copy out of the other ranks' buffers, barrier. zkl_comm_local_rank(g, r) is rank r's zkl_comm; a rank
+ * that fails breaks the group (the other ranks' collectives return an error instead of waiting forever). */
+typedef struct zkl_local_group zkl_local_group;
+int zkl_comm_local_create(int world, zkl_local_group **out);
+const zkl_comm *zkl_comm_local_rank(zkl_local_group *g, int rank);
+void zkl_comm_local_destroy(zkl_local_group *g);
+/* Trees and FRI layers with fewer leaves than this are built by every rank instead of exchanged (default 32768; ZKL_SHARD_MIN_LEAVES). */
+int zkl_set_shard_min_leaves(zkl_ctx *ctx, size_t leaves);
 
 /* ---- measurement helpers (bench.py) -------------------------------------------------------- */
 int zkl_timer_start(zkl_ctx *ctx);             /* CUDA event on the ctx stream */

@@ -206,6 +206,10 @@ def load_library():
     sig("zkl_prove_segment_sharded_pi_dev", C.c_int, vp, vp, sz, sz, sz, sz, C.POINTER(Program), C.POINTER(PublicInputsC), C.POINTER(Options),
         C.POINTER(Comm), vp, C.POINTER(sz), C.POINTER(ProofSummary))
     sig("zkl_comm_loopback", C.POINTER(Comm))
+    sig("zkl_comm_local_create", C.c_int, C.c_int, C.POINTER(vp))
+    sig("zkl_comm_local_rank", C.POINTER(Comm), vp, C.c_int)
+    sig("zkl_comm_local_destroy", None, vp)
+    sig("zkl_set_shard_min_leaves", C.c_int, vp, sz)
     sig("zkl_agg_air_params", C.c_int, sz, C.c_uint64, C.c_uint32, C.POINTER(AirParams), C.POINTER(Assertion))
     sig("zkl_prove_segment_pi", C.c_int, vp, vp, sz, sz, C.POINTER(Program), C.POINTER(PublicInputsC), C.POINTER(Options), vp,
         C.POINTER(sz), C.POINTER(ProofSummary))
@@ -255,4 +259,5 @@ EXPORTED_SYMBOLS = [
     "zkl_sync", "zkl_slice_segment_dev", "zkl_usage_mask_dev", "zkl_read_cells_dev", "zkl_timer_start", "zkl_timer_stop", "zkl_imad_peak", "zkl_set_bulk_threshold", "zkl_set_hash_path", "zkl_set_ntt_path", "zkl_set_coop_path", "zkl_bench_permute", "zkl_partition_size", "zkl_lde_dev", "zkl_hash_partitions_dev", "zkl_merge_partition_digests_dev", "zkl_merkle_dev", "zkl_dev_download", "zkl_merge_plan", "zkl_poseidon_levels_dev", "zkl_merge_with_int_pairs", "zkl_replay_children", "zkl_replay_status_name", "zkl_grind", "zkl_hash_two_lanes_host",
     "zkl_program_derive", "zkl_suite_derive", "zkl_air_build", "zkl_prove_segment_pi", "zkl_prove_segment_pi_dev", "zkl_tc_i8_peak", "zkl_agg_air_params",
     "zkl_shard_columns", "zkl_prove_segment_sharded_dev", "zkl_prove_segment_sharded_pi_dev", "zkl_comm_loopback",
+    "zkl_comm_local_create", "zkl_comm_local_rank", "zkl_comm_local_destroy", "zkl_set_shard_min_leaves",
 ]

@@ -401,7 +401,7 @@ __global__ void k_spread_columns(const fe *__restrict__ src, size_t n, size_t nc
   st_fe(dst + t, (c & 1) ? fe_zero() : ld_fe(src + (c >> 1) * n + i));
 }
 static int dev_constraint_commit(zkl_ctx *ctx, fe *ce_cm, size_t n, size_t ce, size_t num_cols, const zkl_options *o, committed_matrix &m,
-                                 fe *overflow_flag, size_t E = 1) {
+                                 fe *overflow_flag, size_t E = 1, bool polys_only = false) {
   size_t M = n * ce;
   domain_tables *tM; ZKL_TRY(get_tables(ctx, M, &tM));
   m.width = num_cols * E; m.n = n; m.blowup = o->blowup; m.N = n * o->blowup; m.ext = E;
@@ -419,6 +419,7 @@ static int dev_constraint_commit(zkl_ctx *ctx, fe *ce_cm, size_t n, size_t ce, s
   LAUNCH(ctx, k_composition_finish, ceil_div(n, 128), 128, 0, ce_cm, (int)n, (int)ce, (int)num_cols, tM->wpow, M, it->second, ginv_n,
          fe_inv(fe_from_u64(ce)), E == 2 ? narrow.p : m.polys.p, overflow_flag);
   if (E == 2) LAUNCH(ctx, k_spread_columns, ceil_div(2 * num_cols * n, 256), 256, 0, narrow.p, n, num_cols, m.polys.p);
+  if (polys_only) return 0;
   return commit_matrix(ctx, m, o);
 }
 
@@ -523,7 +524,23 @@ __global__ void k_fri_pairs_ext(const fe *__restrict__ ev, int nd, int B, fe *__
   st_fe(out + 2 * total + leaf, ld_fe(ev + k * nd + ip + half_rows)); st_fe(out + 3 * total + leaf, fe_zero());
 }
 // ---- column-sharded proving (include/zkl_b200.h: zkl_comm) ----
+// Ownership. Trace COLUMNS: rank s owns the whole partitions [s P / R, (s + 1) P / R) (balanced: X's 14 partitions over 8 ranks are
+// 6 x 2 + 2 x 1). LDE COSETS of everything that is not column-sharded (constraint evaluations, composition columns, DEEP values, FRI
+// layers): rank s owns cosets [s B / R, (s + 1) B / R) — the coset-major layout makes a coset range one contiguous slab per column and
+// FRI folding never leaves a coset. Merkle LEAVES: rank s builds the sub-tree over the natural rows [s N / R, (s + 1) N / R).
 struct shard_view { const zkl_comm *comm; size_t first_col, local_width; };
+struct shard_geo {
+  const zkl_comm *comm = nullptr;
+  int R = 1, rk = 0;
+  size_t ps = 0, P = 0, ppr = 0;   // partition size, partitions, most partitions any rank owns
+  size_t min_leaves = 0;           // trees and FRI layers below this many leaves are built on every rank instead of exchanged
+  void parts_of(int s, size_t *first, size_t *count) const { *first = (size_t)s * P / R; *count = (size_t)(s + 1) * P / R - *first; }
+  void cols_of(int s, size_t W, size_t *first, size_t *count) const {
+    size_t f, c; parts_of(s, &f, &c);
+    size_t lo = std::min(W, f * ps), hi = std::min(W, (f + c) * ps);
+    *first = lo; *count = hi - lo;
+  }
+};
 // send[d][c][j][i] = lde[c][(d * ncl + j) * step][i]: the CE cosets every destination rank evaluates, for this rank's columns (rows of
 // columns beyond `wl` stay zero: every rank sends blocks of the same size)
 __global__ void k_pack_cosets(const fe *__restrict__ lde, size_t N, int n, int step, int wl, int wmax, int ncl, int world, fe *__restrict__ send) {
@@ -535,38 +552,70 @@ __global__ void k_pack_cosets(const fe *__restrict__ lde, size_t N, int n, int s
   int j = (int)(v / n), i = (int)(v - (size_t)j * n);
   st_fe(send + t, c < wl ? ld_fe(lde + (size_t)c * N + (size_t)((d * ncl + j) * step) * n + i) : fe_zero());
 }
-// partial sums of field elements across ranks travel as four zero-extended 32-bit limbs each (exact under a u64 sum)
-__global__ void k_split_limbs(const fe *__restrict__ in, unsigned long long *__restrict__ out, size_t count) {
+// out[t] = sum over s of in[s * count + t] (field addition): the DEEP partial sums of the ranks for the cosets this rank owns
+__global__ void k_sum_slices(const fe *__restrict__ in, int slices, size_t count, fe *__restrict__ out) {
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= count) return;
-  fe v = ld_fe(in + t);
-#pragma unroll
-  for (int l = 0; l < 4; l++) out[4 * t + l] = v.l[l];
+  fe a = ld_fe(in + t);
+  for (int s = 1; s < slices; s++) a = fe_add(a, ld_fe(in + (size_t)s * count + t));
+  st_fe(out + t, a);
 }
-__global__ void k_merge_limbs(const unsigned long long *__restrict__ in, fe *__restrict__ out, size_t count) {
-  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= count) return;
-  uint32_t x[9]; unsigned long long carry = 0;
-#pragma unroll
-  for (int l = 0; l < 4; l++) { unsigned long long v = in[4 * t + l] + carry; x[l] = (uint32_t)v; carry = v >> 32; }
-  x[4] = (uint32_t)carry; x[5] = (uint32_t)(carry >> 32); x[6] = x[7] = x[8] = 0;
-  st_fe(out + t, reduce9(x));
+// gathered[s][k' + Bp i] (every rank's leaves of ITS Bp cosets, natural order inside the rank) -> natural order over all B cosets:
+// out[k + B i] with k = s Bp + k'
+__global__ void k_interleave_leaves(const fe *__restrict__ g, fe *__restrict__ out, int B, int Bp, size_t m) {
+  size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= (size_t)B * m) return;
+  size_t k = p % B, i = p / B;
+  st_fe(out + p, ld_fe(g + (k / Bp) * ((size_t)Bp * m) + (k % Bp) + (size_t)Bp * i));
 }
-static int shard_geometry(zkl_ctx *ctx, const zkl_options *o, size_t W, const shard_view *sh, size_t ce, size_t *ps_out, size_t *P_out, size_t *ppr_out) {
-  const int R = sh->comm->world, r = sh->comm->rank;
-  if (R < 1 || r < 0 || r >= R) { ctx->set_error("zkl_comm: bad rank / world"); return 1; }
-  if (!sh->comm->all_gather || !sh->comm->all_to_all || !sh->comm->all_reduce_sum_u64) { ctx->set_error("zkl_comm: missing collective callback"); return 1; }
-  if (ce % R) { ctx->set_error("the world size must divide the constraint-evaluation blowup (one or more CE cosets per rank)"); return 1; }
-  size_t f, wl;
-  if (zkl_shard_columns(o, W, r, R, &f, &wl)) { ctx->set_error("column sharding needs at least one whole partition per rank (PartitionOptions with >= world partitions)"); return 1; }
-  if (f != sh->first_col || wl != sh->local_width) { ctx->set_error("first_col / local_width do not match zkl_shard_columns for this rank"); return 1; }
-  const size_t ps = partition_size_of(o, W), P = (W + ps - 1) / ps;
-  *ps_out = ps; *P_out = P; *ppr_out = (P + R - 1) / R;
-  return 0;
+// heap node g >= R of the whole tree out of the gathered sub-trees: level lvl = 2^floor(log2 g) holds lvl / R nodes of each rank
+__global__ void k_scatter_subtrees(const fe *__restrict__ gathered, fe *__restrict__ nodes, size_t count, int R) {
+  size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x + R;
+  if (g >= count) return;
+  size_t lvl = (size_t)1 << (63 - __clzll((unsigned long long)g)), j = g - lvl, per = lvl / R, s = j / per;
+  st_fe(nodes + g, ld_fe(gathered + s * (count / R) + per + (j - s * per)));
 }
 static int comm_call(zkl_ctx *ctx, int rc, const char *what) {
   if (rc) { ctx->set_error(std::string("collective callback failed: ") + what); return 1; }
   return 0;
+}
+static int shard_geometry(zkl_ctx *ctx, const zkl_options *o, size_t W, const shard_view *sh, size_t ce, shard_geo &g) {
+  g.comm = sh->comm; g.R = sh->comm->world; g.rk = sh->comm->rank;
+  if (g.R < 1 || g.rk < 0 || g.rk >= g.R) { ctx->set_error("zkl_comm: bad rank / world"); return 1; }
+  if (!sh->comm->all_gather || !sh->comm->all_to_all || !sh->comm->all_reduce_sum_u64) { ctx->set_error("zkl_comm: missing collective callback"); return 1; }
+  if (ce % g.R || o->blowup % g.R) { ctx->set_error("the world size must divide the constraint-evaluation blowup (one or more CE cosets per rank)"); return 1; }
+  size_t f, wl;
+  if (zkl_shard_columns(o, W, g.rk, g.R, &f, &wl)) { ctx->set_error("column sharding needs at least one whole partition per rank (PartitionOptions with >= world partitions)"); return 1; }
+  if (f != sh->first_col || wl != sh->local_width) { ctx->set_error("first_col / local_width do not match zkl_shard_columns for this rank"); return 1; }
+  g.ps = partition_size_of(o, W); g.P = (W + g.ps - 1) / g.ps; g.ppr = (g.P + g.R - 1) / g.R;
+  g.min_leaves = ctx->shard_min_leaves;
+  return 0;
+}
+// MerkleTree::new over `count` leaves that every rank holds: each rank builds the sub-tree over its contiguous share, the sub-trees
+// are all-gathered (count / R nodes per rank), scattered into heap order and topped with the log2(R) levels above them
+static int sharded_merkle(zkl_ctx *ctx, const shard_geo &g, const fe *leaves, fe *nodes, size_t count) {
+  const size_t per = count / g.R;
+  if (g.R == 1 || count < g.min_leaves || per < 2) return dev_merkle(ctx, leaves, nodes, count);
+  dev_buf<fe> sub, all;
+  ZKL_CHECK(ctx, sub.alloc(per)); ZKL_CHECK(ctx, all.alloc(count));
+  ZKL_CHECK(ctx, cudaMemsetAsync(sub.p, 0, sizeof(fe), ctx->stream));   // heap slot 0 is unused; it travels with the rest
+  ZKL_TRY(dev_merkle(ctx, leaves + (size_t)g.rk * per, sub.p, per));
+  ZKL_TRY(ctx_wait(ctx));
+  ZKL_TRY(comm_call(ctx, g.comm->all_gather(g.comm->user, sub.p, all.p, per * sizeof(fe)), "all_gather(sub-trees)"));
+  LAUNCH(ctx, k_scatter_subtrees, ceil_div(count - g.R, 256), 256, 0, all.p, nodes, count, g.R);
+  ZKL_TRY(dev_merkle(ctx, nodes + g.R, nodes, (size_t)g.R));
+  return ctx_wait(ctx);   // `all` is released when this returns: its last reader has run
+}
+// local: the leaves of the Bp = B / R cosets this rank owns, Bp * m of them in the rank's own natural order (k' + Bp i); result: all
+// B * m leaves in natural order and the whole tree on every rank
+static int shard_leaves_to_tree(zkl_ctx *ctx, const shard_geo &g, const fe *local, size_t B, size_t m, fe *leaves, fe *nodes) {
+  const size_t Bp = B / g.R;
+  dev_buf<fe> all; ZKL_CHECK(ctx, all.alloc(B * m));
+  ZKL_TRY(ctx_wait(ctx));
+  ZKL_TRY(comm_call(ctx, g.comm->all_gather(g.comm->user, local, all.p, Bp * m * sizeof(fe)), "all_gather(leaves)"));
+  LAUNCH(ctx, k_interleave_leaves, ceil_div(B * m, 256), 256, 0, all.p, leaves, (int)B, (int)Bp, m);
+  ZKL_TRY(sharded_merkle(ctx, g, leaves, nodes, B * m));
+  return ctx_wait(ctx);
 }
 static const char *k_stage_names[12] = {"coin_seed", "trace_lde_commit", "constraint_eval", "constraint_commit", "ood", "deep",
                                         "fri", "grind", "queries_serialize", "kernel:k_lde(trace)", "kernel:k_hash_rows(trace)",
@@ -584,15 +633,12 @@ static int prove_segment_impl(zkl_ctx *ctx, const fe *trace_dev, size_t W, size_
   // column-sharded mode: trace_dev holds this rank's Wl columns [first_col, first_col + Wl) of the W-column trace
   const size_t Wl = sh ? sh->local_width : W, col0 = sh ? sh->first_col : 0;
   const int R = sh ? sh->comm->world : 1, rk = sh ? sh->comm->rank : 0;
-  size_t sh_ps = 0, sh_P = 0, sh_ppr = 0;
+  shard_geo sg;
   if (sh) {
-    ZKL_TRY(shard_geometry(ctx, o, W, sh, air->ce_blowup, &sh_ps, &sh_P, &sh_ppr));
+    ZKL_TRY(shard_geometry(ctx, o, W, sh, air->ce_blowup, sg));
     if (o->field_extension == 2) { ctx->set_error("column sharding is for step proofs (FieldExtension::None)"); return 1; }
   }
-  auto owned = [&](int s, size_t *first, size_t *count) {   // columns of rank s
-    size_t lo = std::min(W, (size_t)s * sh_ppr * sh_ps), hi = std::min(W, ((size_t)s + 1) * sh_ppr * sh_ps);
-    *first = lo; *count = hi - lo;
-  };
+  const size_t Bp = o->blowup / (size_t)R, k0 = (size_t)rk * Bp;   // the LDE cosets this rank owns: [k0, k0 + Bp)
   auto wait_stream = [&]() -> int { return ctx_wait(ctx); };
   if (air->cols.width != W) { ctx->set_error("air width does not match the trace"); return 1; }
   if (o->num_queries == 0 || o->num_queries > 255) { ctx->set_error("num_queries must be in [1,255]"); return 1; }
@@ -650,7 +696,9 @@ static int prove_segment_impl(zkl_ctx *ctx, const fe *trace_dev, size_t W, size_
   zkl_trace_lde tl;
   if (!sh) ZKL_TRY(trace_commit_dev(ctx, trace_dev, W, n, o, &tl, &ctx->ev[12]));
   else {
-    // local: iNTT, coset LDE and partition digests of the owned columns; exchange (1): 16 bytes per (row, partition) instead of the rows
+    // local: iNTT, coset LDE and partition digests of the owned columns. Exchange (1): 16 bytes per (row, partition) instead of the
+    // rows — an all-to-all that hands every rank all P digests of ITS N / R rows; it merges them into leaves, the leaves are
+    // all-gathered and the tree is built from per-rank sub-trees (sharded_merkle)
     committed_matrix &m = tl.m;
     m.width = Wl; m.n = n; m.blowup = B; m.N = N;
     ZKL_CHECK(ctx, m.polys.alloc(Wl * n)); ZKL_CHECK(ctx, m.lde.alloc(Wl * N)); ZKL_CHECK(ctx, m.leaves.alloc(N)); ZKL_CHECK(ctx, m.nodes.alloc(N));
@@ -658,16 +706,28 @@ static int prove_segment_impl(zkl_ctx *ctx, const fe *trace_dev, size_t W, size_
     ZKL_CHECK(ctx, cudaEventRecord(ctx->ev[12], st));
     ZKL_TRY(dev_lde(ctx, m.polys.p, m.lde.p, Wl, n, B));
     ZKL_CHECK(ctx, cudaEventRecord(ctx->ev[13], st));
-    dev_buf<fe> mine, all;
-    ZKL_CHECK(ctx, mine.alloc(sh_ppr * N)); ZKL_CHECK(ctx, all.alloc((size_t)R * sh_ppr * N));
-    ZKL_CHECK(ctx, cudaMemsetAsync(mine.p, 0, sh_ppr * N * sizeof(fe), st));
-    ZKL_TRY(dev_hash_partitions(ctx, m.lde.p, Wl, n, B, sh_ps, mine.p));
+    size_t pf, pc; sg.parts_of(rk, &pf, &pc);
+    const size_t per = N / R;
+    dev_buf<fe> mine, send, recv, parts, leaves_loc;
+    ZKL_CHECK(ctx, mine.alloc(pc * N)); ZKL_CHECK(ctx, send.alloc((size_t)R * sg.ppr * per)); ZKL_CHECK(ctx, recv.alloc((size_t)R * sg.ppr * per));
+    ZKL_CHECK(ctx, parts.alloc(sg.P * per)); ZKL_CHECK(ctx, leaves_loc.alloc(per));
+    ZKL_TRY(dev_hash_partitions(ctx, m.lde.p, Wl, n, B, sg.ps, mine.p));
     ZKL_CHECK(ctx, cudaEventRecord(ctx->ev[14], st));
+    if (pc < sg.ppr) ZKL_CHECK(ctx, cudaMemsetAsync(send.p, 0, (size_t)R * sg.ppr * per * sizeof(fe), st));   // padded slots travel too
+    for (int d = 0; d < R; d++)   // send[d][q][j] = mine[q][d per + j]
+      ZKL_CHECK(ctx, cudaMemcpy2DAsync(send.p + (size_t)d * sg.ppr * per, per * sizeof(fe), mine.p + (size_t)d * per, N * sizeof(fe), per * sizeof(fe), pc,
+                                       cudaMemcpyDeviceToDevice, st));
     ZKL_TRY(wait_stream());
-    ZKL_TRY(comm_call(ctx, sh->comm->all_gather(sh->comm->user, mine.p, all.p, sh_ppr * N * sizeof(fe)), "all_gather(partition digests)"));
-    // rank s holds partitions [s ppr, min(P, (s+1) ppr)): slot s ppr + (q - s ppr) = q — the first P slots are the partitions in order
-    ZKL_TRY(dev_merge_partitions(ctx, all.p, N, N, sh_P, m.leaves.p));
-    ZKL_TRY(dev_merkle(ctx, m.leaves.p, m.nodes.p, N));
+    ZKL_TRY(comm_call(ctx, sg.comm->all_to_all(sg.comm->user, send.p, recv.p, sg.ppr * per * sizeof(fe)), "all_to_all(partition digests)"));
+    for (int s2 = 0; s2 < R; s2++) {   // parts[q][j], q in global partition order
+      size_t f2, c2; sg.parts_of(s2, &f2, &c2);
+      ZKL_CHECK(ctx, cudaMemcpyAsync(parts.p + f2 * per, recv.p + (size_t)s2 * sg.ppr * per, c2 * per * sizeof(fe), cudaMemcpyDeviceToDevice, st));
+    }
+    ZKL_TRY(dev_merge_partitions(ctx, parts.p, per, per, sg.P, leaves_loc.p));
+    ZKL_TRY(wait_stream());
+    ZKL_TRY(comm_call(ctx, sg.comm->all_gather(sg.comm->user, leaves_loc.p, m.leaves.p, per * sizeof(fe)), "all_gather(trace leaves)"));
+    ZKL_TRY(sharded_merkle(ctx, sg, m.leaves.p, m.nodes.p, N));
+    ZKL_TRY(wait_stream());
   }
   STAGE_MARK();
 
@@ -682,14 +742,14 @@ static int prove_segment_impl(zkl_ctx *ctx, const fe *trace_dev, size_t W, size_
   else {
     // exchange (2): every rank evaluates ce / R constraint-evaluation cosets on FULL-width rows — the coset-major layout makes a coset
     // the natural unit: all-to-all of [columns of the sender][cosets of the receiver][n], then all-gather of the evaluations
-    const size_t ncl = ce / R, wmax = sh_ppr * sh_ps, per_pair = wmax * ncl * n;
+    const size_t ncl = ce / R, wmax = sg.ppr * sg.ps, per_pair = wmax * ncl * n;
     dev_buf<fe> send, recv, rows, ce_all;
     ZKL_CHECK(ctx, send.alloc(per_pair * R)); ZKL_CHECK(ctx, recv.alloc(per_pair * R)); ZKL_CHECK(ctx, rows.alloc(W * ncl * n)); ZKL_CHECK(ctx, ce_all.alloc(M));
     LAUNCH(ctx, k_pack_cosets, ceil_div(per_pair * R, 256), 256, 0, tl.m.lde.p, N, (int)n, (int)(B / ce), (int)Wl, (int)wmax, (int)ncl, R, send.p);
     ZKL_TRY(wait_stream());
     ZKL_TRY(comm_call(ctx, sh->comm->all_to_all(sh->comm->user, send.p, recv.p, per_pair * sizeof(fe)), "all_to_all(CE cosets)"));
     for (int s2 = 0; s2 < R; s2++) {
-      size_t f, cnt; owned(s2, &f, &cnt);
+      size_t f, cnt; sg.cols_of(s2, W, &f, &cnt);
       if (cnt) ZKL_CHECK(ctx, cudaMemcpyAsync(rows.p + f * ncl * n, recv.p + (size_t)s2 * per_pair, cnt * ncl * n * sizeof(fe), cudaMemcpyDeviceToDevice, st));
     }
     ce_rows cr{rows.p, (int)(rk * ncl), (int)ncl};
@@ -703,7 +763,18 @@ static int prove_segment_impl(zkl_ctx *ctx, const fe *trace_dev, size_t W, size_
 
   // ---- 6. constraint commitment (hook build_constraint_commitment), reseed
   zkl_constraint_commitment cmt;
-  ZKL_TRY(dev_constraint_commit(ctx, ce_ev.p, n, ce, air->num_composition_cols, o, cmt.m, flag.p, E));
+  if (!sh) ZKL_TRY(dev_constraint_commit(ctx, ce_ev.p, n, ce, air->num_composition_cols, o, cmt.m, flag.p, E));
+  else {
+    // the composition columns are few: coefficients and LDE on every rank; the row hashes of the cosets this rank owns, leaves
+    // all-gathered, tree from sub-trees
+    committed_matrix &m = cmt.m;
+    ZKL_TRY(dev_constraint_commit(ctx, ce_ev.p, n, ce, air->num_composition_cols, o, m, flag.p, E, true));
+    ZKL_CHECK(ctx, m.lde.alloc(m.width * N)); ZKL_CHECK(ctx, m.leaves.alloc(N)); ZKL_CHECK(ctx, m.nodes.alloc(N));
+    ZKL_TRY(dev_lde(ctx, m.polys.p, m.lde.p, m.width, n, B));
+    dev_buf<fe> loc; ZKL_CHECK(ctx, loc.alloc(Bp * n));
+    ZKL_TRY(dev_hash_rows(ctx, m.lde.p + k0 * n, m.width, n, Bp, o, loc.p, m.scratch, m.ext, N));
+    ZKL_TRY(shard_leaves_to_tree(ctx, sg, loc.p, B, n, m.leaves.p, m.nodes.p));
+  }
   STAGE_MARK();
 
   // ---- 7. OOD point z, evaluations at z and z*g, reseed with hash_elements(cur(z)||quot(z)||next(zg)||quot(zg))
@@ -749,54 +820,81 @@ static int prove_segment_impl(zkl_ctx *ctx, const fe *trace_dev, size_t W, size_
   LAUNCH(ctx, k_deep_inverses, ceil_div(N, 256 * DEEP_INV_PER_THREAD), 256, 0, N, (int)n, (int)B, z.p, g_n, tN->wpow, deep_inv.p);
   if (!sh) {
     LAUNCH(ctx, k_deep_consts, 1, 32, 0, ood.p, dc.p, (int)W, (int)C, az.p);
-    LAUNCH(ctx, k_deep, ceil_div(N, 256), 256, 0, tl.m.lde.p, cmt.m.lde.p, N, (int)n, (int)B, (int)W, (int)C, dc.p, az.p, z.p, g_n, tN->wpow, deep_inv.p, deep.p);
+    LAUNCH(ctx, k_deep, ceil_div(N, 256), 256, 0, tl.m.lde.p, cmt.m.lde.p, N, (int)n, (int)B, (int)W, (int)C, dc.p, az.p, z.p, g_n, tN->wpow, deep_inv.p, deep.p,
+           (size_t)0, N, 0);
   } else {
-    // the DEEP composition is linear in the columns: every rank sums over ITS trace columns (rank 0 adds the composition columns);
-    // exchange (3b): the partial sums are added as 64-bit limb lanes and normalised
-    const size_t Cl = rk == 0 ? C : 0;
-    dev_buf<fe> dcl, oodl; dev_buf<unsigned long long> limbs;
-    ZKL_CHECK(ctx, dcl.alloc(Wl + Cl + 1)); ZKL_CHECK(ctx, oodl.alloc(2 * (Wl + Cl) + 1)); ZKL_CHECK(ctx, limbs.alloc(4 * N));
+    // The DEEP composition is linear in the columns. Every rank sums over ITS trace columns on the whole domain; exchange (3b) is a
+    // reduce-scatter by coset range (an all-to-all of the partial sums and a field addition of the R slices): the rank ends up with
+    // the values on the cosets it owns — where FRI continues — and adds the composition columns' share there.
+    dev_buf<fe> dcl, oodl, recv, oodc, azc;
+    ZKL_CHECK(ctx, dcl.alloc(Wl)); ZKL_CHECK(ctx, oodl.alloc(2 * Wl)); ZKL_CHECK(ctx, recv.alloc(N)); ZKL_CHECK(ctx, oodc.alloc(2 * C)); ZKL_CHECK(ctx, azc.alloc(2));
     ZKL_CHECK(ctx, cudaMemcpyAsync(dcl.p, dc.p + col0, Wl * sizeof(fe), cudaMemcpyDeviceToDevice, st));
     ZKL_CHECK(ctx, cudaMemcpyAsync(oodl.p, ood.p + col0, Wl * sizeof(fe), cudaMemcpyDeviceToDevice, st));
-    ZKL_CHECK(ctx, cudaMemcpyAsync(oodl.p + Wl + Cl, ood.p + W + C + col0, Wl * sizeof(fe), cudaMemcpyDeviceToDevice, st));
-    if (Cl) {
-      ZKL_CHECK(ctx, cudaMemcpyAsync(dcl.p + Wl, dc.p + W, C * sizeof(fe), cudaMemcpyDeviceToDevice, st));
-      ZKL_CHECK(ctx, cudaMemcpyAsync(oodl.p + Wl, ood.p + W, C * sizeof(fe), cudaMemcpyDeviceToDevice, st));
-      ZKL_CHECK(ctx, cudaMemcpyAsync(oodl.p + 2 * Wl + Cl, ood.p + 2 * W + C, C * sizeof(fe), cudaMemcpyDeviceToDevice, st));
-    }
-    LAUNCH(ctx, k_deep_consts, 1, 32, 0, oodl.p, dcl.p, (int)Wl, (int)Cl, az.p);
-    LAUNCH(ctx, k_deep, ceil_div(N, 256), 256, 0, tl.m.lde.p, cmt.m.lde.p, N, (int)n, (int)B, (int)Wl, (int)Cl, dcl.p, az.p, z.p, g_n, tN->wpow, deep_inv.p, deep.p);
-    LAUNCH(ctx, k_split_limbs, ceil_div(N, 256), 256, 0, deep.p, limbs.p, N);
+    ZKL_CHECK(ctx, cudaMemcpyAsync(oodl.p + Wl, ood.p + W + C + col0, Wl * sizeof(fe), cudaMemcpyDeviceToDevice, st));
+    ZKL_CHECK(ctx, cudaMemcpyAsync(oodc.p, ood.p + W, C * sizeof(fe), cudaMemcpyDeviceToDevice, st));
+    ZKL_CHECK(ctx, cudaMemcpyAsync(oodc.p + C, ood.p + 2 * W + C, C * sizeof(fe), cudaMemcpyDeviceToDevice, st));
+    LAUNCH(ctx, k_deep_consts, 1, 32, 0, oodl.p, dcl.p, (int)Wl, 0, az.p);
+    LAUNCH(ctx, k_deep_consts, 1, 32, 0, oodc.p, dc.p + W, 0, (int)C, azc.p);
+    LAUNCH(ctx, k_deep, ceil_div(N, 256), 256, 0, tl.m.lde.p, (const fe *)nullptr, N, (int)n, (int)B, (int)Wl, 0, dcl.p, az.p, z.p, g_n, tN->wpow, deep_inv.p, deep.p,
+           (size_t)0, N, 0);
     ZKL_TRY(wait_stream());
-    ZKL_TRY(comm_call(ctx, sh->comm->all_reduce_sum_u64(sh->comm->user, limbs.p, 4 * N), "all_reduce(DEEP partial sums)"));
-    LAUNCH(ctx, k_merge_limbs, ceil_div(N, 256), 256, 0, limbs.p, deep.p, N);
+    ZKL_TRY(comm_call(ctx, sg.comm->all_to_all(sg.comm->user, deep.p, recv.p, Bp * n * sizeof(fe)), "all_to_all(DEEP partial sums)"));
+    LAUNCH(ctx, k_sum_slices, ceil_div(Bp * n, 256), 256, 0, recv.p, R, Bp * n, deep.p);   // deep[0 .. Bp n): this rank's cosets from here on
+    LAUNCH(ctx, k_deep, ceil_div(Bp * n, 256), 256, 0, (const fe *)nullptr, cmt.m.lde.p, N, (int)n, (int)B, 0, (int)C, dc.p + W, azc.p, z.p, g_n, tN->wpow, deep_inv.p,
+           deep.p, k0 * n, Bp * n, 1);
     ZKL_TRY(wait_stream());
   }
   STAGE_MARK();
 
   // ---- 9. FRI layers
   std::vector<dev_buf<fe>> f_ev(nl + 1), f_leaves(nl), f_nodes(nl);
+  std::vector<const fe *> layer_ev(nl + 1, nullptr);   // where layer d's evaluations are (for the openings)
+  std::vector<char> f_sharded(nl + 1, 0);   // layer d's evaluations live as the Bp cosets this rank owns (column-sharded prover)
   dev_buf<fe> alphas, fri_roots, rem_rev;
   ZKL_CHECK(ctx, alphas.alloc(nl + 1)); ZKL_CHECK(ctx, fri_roots.alloc(nl + 1));
   fe g_inv_half = fe_inv(fe_from_u64(6));
   const fe *cur_ev = deep.p;
   size_t nd = n;
+  bool ev_sharded = sh != nullptr;   // deep.p holds [Bp][n] then
+  dev_buf<fe> ev_full;
+  auto unshard_ev = [&]() -> int {   // all-gather the cosets: [R][Bp][nd] IS the coset-major layer
+    ZKL_CHECK(ctx, ev_full.alloc(B * nd));
+    ZKL_TRY(wait_stream());
+    ZKL_TRY(comm_call(ctx, sg.comm->all_gather(sg.comm->user, cur_ev, ev_full.p, Bp * nd * sizeof(fe)), "all_gather(FRI layer)"));
+    cur_ev = ev_full.p; ev_sharded = false;
+    return 0;
+  };
   for (size_t d = 0; d < nl; d++) {
     size_t half = nd * B / 2;
-    ZKL_CHECK(ctx, f_leaves[d].alloc(half)); ZKL_CHECK(ctx, f_nodes[d].alloc(half)); ZKL_CHECK(ctx, f_ev[d + 1].alloc(half));
+    if (ev_sharded && (half < sg.min_leaves || half / R < 2)) ZKL_TRY(unshard_ev());
+    f_sharded[d] = ev_sharded; layer_ev[d] = cur_ev;
+    const size_t Bd = ev_sharded ? Bp : B, half_d = nd * Bd / 2;   // cosets and leaves this rank works on
+    ZKL_CHECK(ctx, f_leaves[d].alloc(half)); ZKL_CHECK(ctx, f_nodes[d].alloc(half)); ZKL_CHECK(ctx, f_ev[d + 1].alloc(half_d));
+    dev_buf<fe> loc;
+    fe *lv = f_leaves[d].p;
+    if (ev_sharded) { ZKL_CHECK(ctx, loc.alloc(half_d)); lv = loc.p; }
     if (E == 2) {   // a leaf hashes two E elements: (v0, 0, v1, 0) — laid out as a 4-column matrix in natural leaf order
       dev_buf<fe> pairs; ZKL_CHECK(ctx, pairs.alloc(4 * half));
       LAUNCH(ctx, k_fri_pairs_ext, ceil_div(half, 256), 256, 0, cur_ev, (int)nd, (int)B, pairs.p);
       ZKL_TRY(dev_hash_partitions(ctx, pairs.p, 4, half, 1, 4, f_leaves[d].p));
     }
-    else if (half >= bulk_min(ctx) && ctx->hash_path == 0) LAUNCH_TC(ctx, k_tc_fri_leaves, half, cur_ev, (int)nd, (int)B, f_leaves[d].p);
-    else if (quad) LAUNCH_QUAD(ctx, k_quad_fri_leaves, half, cur_ev, (int)nd, (int)B, f_leaves[d].p);
-    else LAUNCH_COOP(ctx, k_fri_leaves, half, cur_ev, (int)nd, (int)B, f_leaves[d].p);
-    ZKL_TRY(dev_merkle(ctx, f_leaves[d].p, f_nodes[d].p, half));
+    else if (half_d >= bulk_min(ctx) && ctx->hash_path == 0) LAUNCH_TC(ctx, k_tc_fri_leaves, half_d, cur_ev, (int)nd, (int)Bd, lv);
+    else if (quad) LAUNCH_QUAD(ctx, k_quad_fri_leaves, half_d, cur_ev, (int)nd, (int)Bd, lv);
+    else LAUNCH_COOP(ctx, k_fri_leaves, half_d, cur_ev, (int)nd, (int)Bd, lv);
+    if (ev_sharded) ZKL_TRY(shard_leaves_to_tree(ctx, sg, loc.p, B, nd / 2, f_leaves[d].p, f_nodes[d].p));
+    else ZKL_TRY(dev_merkle(ctx, f_leaves[d].p, f_nodes[d].p, half));
     ZKL_TRY(reseed_draw(f_nodes[d].p + 1, fri_roots.p + d, 1, alphas.p + d));   // commit the layer root, draw alpha
-    LAUNCH(ctx, k_fri_fold, ceil_div(half, 256), 256, 0, cur_ev, (int)nd, (int)B, (int)d, alphas.p + d, tN->wpow, N, g_inv_half, f_ev[d + 1].p);
+    LAUNCH(ctx, k_fri_fold, ceil_div(half_d, 256), 256, 0, cur_ev, (int)nd, (int)Bd, (int)d, alphas.p + d, tN->wpow, N, g_inv_half, f_ev[d + 1].p,
+           ev_sharded ? (int)k0 : 0, (int)B);
     cur_ev = f_ev[d + 1].p;
     nd /= 2;
+  }
+  dev_buf<fe> ev_last;
+  if (ev_sharded) {   // the remainder is interpolated from the whole last layer
+    ZKL_CHECK(ctx, ev_last.alloc(B * nd));
+    ZKL_TRY(wait_stream());
+    ZKL_TRY(comm_call(ctx, sg.comm->all_gather(sg.comm->user, cur_ev, ev_last.p, Bp * nd * sizeof(fe)), "all_gather(last FRI layer)"));
+    cur_ev = ev_last.p; ev_sharded = false;
   }
   size_t rem_len = nd;  // (B*nd)/B coefficients
   ZKL_CHECK(ctx, rem_rev.alloc(rem_len));
@@ -886,37 +984,46 @@ static int prove_segment_impl(zkl_ctx *ctx, const fe *trace_dev, size_t W, size_
   if (!g_src || !g_idx || !got) { ctx->set_error("staging buffer exhausted"); return 1; }
   size_t g_cnt = 0;
   bool g_overflow = false;
-  auto want = [&](const fe *src, uint32_t idx) { if (g_cnt < max_open) { g_src[g_cnt] = src; g_idx[g_cnt] = idx; g_cnt++; } else g_overflow = true; };
-  struct tree_job { std::vector<std::vector<node_ref>> plan; int depth; };
   dev_buf<fe> zero_fe;
   if (sh) { ZKL_CHECK(ctx, zero_fe.alloc(1)); ZKL_CHECK(ctx, cudaMemsetAsync(zero_fe.p, 0, sizeof(fe), st)); }
+  auto want = [&](const fe *src, uint32_t idx) { if (g_cnt < max_open) { g_src[g_cnt] = src; g_idx[g_cnt] = idx; g_cnt++; } else g_overflow = true; };
+  // column-sharded prover: every opened element is contributed by exactly ONE rank and the others put a zero — its owner for sharded
+  // data, rank 0 for what every rank holds — so that a single sum over the ranks assembles the openings (exchange 3c)
+  auto want_rep = [&](const fe *src, uint32_t idx) { if (!sh || rk == 0) want(src, idx); else want(zero_fe.p, 0); };
+  struct tree_job { std::vector<std::vector<node_ref>> plan; int depth; };
   auto plan_matrix = [&](const committed_matrix &m, tree_job &tj) {
     const bool sharded_cols = sh && &m == &tl.m;   // the trace matrix holds this rank's columns only: the others are opened as zero and summed in
     for (uint32_t p : pos) {
       uint32_t s = (uint32_t)((p % m.blowup) * m.n + p / m.blowup);
-      if (!sharded_cols) for (size_t c = 0; c < m.width; c++) want(m.lde.p + c * m.N, s);   // per-column base: width * N exceeds 32 bits for large segments
+      if (!sharded_cols) for (size_t c = 0; c < m.width; c++) want_rep(m.lde.p + c * m.N, s);   // per-column base: width * N exceeds 32 bits for large segments
       else for (size_t c = 0; c < W; c++) { if (c >= col0 && c < col0 + Wl) want(m.lde.p + (c - col0) * m.N, s); else want(zero_fe.p, 0); }
     }
     tj.plan = batch_proof_plan(pos, m.N); tj.depth = ilog2_sz(m.N);
-    for (auto &l : tj.plan) for (auto &r : l) want(r.leaf ? m.leaves.p : m.nodes.p, r.index);
+    for (auto &l : tj.plan) for (auto &r : l) want_rep(r.leaf ? m.leaves.p : m.nodes.p, r.index);
   };
   tree_job tj_trace, tj_cons; std::vector<tree_job> tj_fri(nl);
   std::vector<size_t> fri_counts(nl);
   plan_matrix(tl.m, tj_trace);
   plan_matrix(cmt.m, tj_cons);
   {
-    std::vector<uint32_t> fp = pos; size_t dom = N; const fe *ev = deep.p; size_t ndl = n;
+    std::vector<uint32_t> fp = pos; size_t dom = N; size_t ndl = n;
     for (size_t d = 0; d < nl; d++) {
       fp = fold_positions_host(fp, dom);
       size_t half = dom / 2, half_rows = ndl / 2;
+      const fe *ev = layer_ev[d];
       for (uint32_t p : fp) {  // values ev[p], ev[p + half]; storage index of natural r: (r % B)*ndl + r / B
-        uint32_t s0 = (uint32_t)((p % B) * ndl + p / B);
-        want(ev, s0); want(ev, s0 + (uint32_t)half_rows);
+        if (!f_sharded[d]) {
+          uint32_t s0 = (uint32_t)((p % B) * ndl + p / B);
+          want_rep(ev, s0); want_rep(ev, s0 + (uint32_t)half_rows);
+        } else if (p % B >= k0 && p % B < k0 + Bp) {   // the rank that owns the coset holds both values
+          uint32_t s0 = (uint32_t)((p % B - k0) * ndl + p / B);
+          want(ev, s0); want(ev, s0 + (uint32_t)half_rows);
+        } else { want(zero_fe.p, 0); want(zero_fe.p, 0); }
       }
       fri_counts[d] = fp.size();
       tj_fri[d].plan = batch_proof_plan(fp, half); tj_fri[d].depth = ilog2_sz(half);
-      for (auto &l : tj_fri[d].plan) for (auto &r : l) want(r.leaf ? f_leaves[d].p : f_nodes[d].p, r.index);
-      ev = f_ev[d + 1].p; dom = half; ndl = half_rows;
+      for (auto &l : tj_fri[d].plan) for (auto &r : l) want_rep(r.leaf ? f_leaves[d].p : f_nodes[d].p, r.index);
+      dom = half; ndl = half_rows;
     }
   }
   if (g_overflow) { ctx->set_error("opening plan larger than its bound"); return 1; }
@@ -926,9 +1033,9 @@ static int prove_segment_impl(zkl_ctx *ctx, const fe *trace_dev, size_t W, size_
     ZKL_CHECK(ctx, cudaMemcpyAsync(dsrc.p, g_src, g_cnt * sizeof(fe *), cudaMemcpyHostToDevice, st));
     ZKL_CHECK(ctx, cudaMemcpyAsync(didx.p, g_idx, g_cnt * 4, cudaMemcpyHostToDevice, st));
     LAUNCH(ctx, k_gather_multi, ceil_div(g_cnt, 256), 256, 0, dsrc.p, didx.p, (int)g_cnt, dout.p);
-    if (sh) {   // exchange (3c): the opened trace rows are the first pos x W entries; disjoint supports again
+    if (sh) {   // exchange (3c): one contributor per element, zeros elsewhere: a u64 sum assembles all openings exactly
       ZKL_TRY(wait_stream());
-      ZKL_TRY(comm_call(ctx, sh->comm->all_reduce_sum_u64(sh->comm->user, dout.p, 2 * pos.size() * W), "all_reduce(opened trace rows)"));
+      ZKL_TRY(comm_call(ctx, sh->comm->all_reduce_sum_u64(sh->comm->user, dout.p, 2 * g_cnt), "all_reduce(openings)"));
     }
     ZKL_CHECK(ctx, cudaMemcpyAsync(got, dout.p, g_cnt * sizeof(fe), cudaMemcpyDeviceToHost, st));
     ZKL_TRY(ctx_wait(ctx));
@@ -1047,14 +1154,14 @@ extern "C" int zkl_prove_segment_pi(zkl_ctx *ctx, const zkl_fe *trace, size_t wi
 extern "C" int zkl_shard_columns(const zkl_options *o, size_t width, int rank, int world, size_t *first_col, size_t *local_width) {
   if (world < 1 || rank < 0 || rank >= world || width == 0) return 1;
   const size_t ps = partition_size_of(o, width), P = (width + ps - 1) / ps;
-  if (P < 2 && world > 1) return 1;
-  const size_t ppr = (P + world - 1) / world;
-  const size_t lo = std::min(width, (size_t)rank * ppr * ps), hi = std::min(width, ((size_t)rank + 1) * ppr * ps);
-  if (hi <= lo) return 1;                                      // a rank without a partition
-  if ((size_t)(world - 1) * ppr >= P) return 1;                 // the last rank would own nothing
+  if (P < (size_t)world || (world > 1 && P < 2)) return 1;   // every rank owns at least one whole partition
+  const size_t f = (size_t)rank * P / world, l = (size_t)(rank + 1) * P / world;
+  const size_t lo = std::min(width, f * ps), hi = std::min(width, l * ps);
+  if (hi <= lo) return 1;
   *first_col = lo; *local_width = hi - lo;
   return 0;
 }
+extern "C" int zkl_set_shard_min_leaves(zkl_ctx *ctx, size_t leaves) { ctx->shard_min_leaves = leaves; return 0; }
 extern "C" int zkl_prove_segment_sharded_dev(zkl_ctx *ctx, const void *local_trace_dev, size_t first_col, size_t local_width, size_t width, size_t n,
                                              const zkl_air_params *air, const zkl_fe *seed_elems, size_t num_seed, const zkl_options *opts,
                                              const zkl_comm *comm, uint8_t *out_proof, size_t *out_len, zkl_proof_summary *summary) {
@@ -1073,7 +1180,8 @@ extern "C" int zkl_prove_segment_sharded_pi_dev(zkl_ctx *ctx, const void *local_
 }
 // world = 1: the "collectives" are device-to-device copies (all_gather / all_to_all of one block) and a no-op (sum over one rank)
 static int loop_copy(void *, const void *send, void *recv, size_t bytes) {
-  return cudaMemcpy(recv, send, bytes, cudaMemcpyDeviceToDevice) == cudaSuccess ? 0 : 1;
+  // a device-to-device cudaMemcpy returns before the copy has run: wait for the legacy stream it was put on
+  return cudaMemcpy(recv, send, bytes, cudaMemcpyDeviceToDevice) == cudaSuccess && cudaStreamSynchronize(cudaStreamLegacy) == cudaSuccess ? 0 : 1;
 }
 static int loop_sum(void *, void *, size_t) { return 0; }
 extern "C" const zkl_comm *zkl_comm_loopback(void) {

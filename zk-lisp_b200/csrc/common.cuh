@@ -61,6 +61,7 @@ struct zkl_ctx {
   cudaEvent_t wait_ev = nullptr;           // cudaEventBlockingSync event of the blocking wait
   void *stage_h = nullptr; size_t stage_cap = 0, stage_used = 0;   // pinned host staging for per-call parameter uploads (api_stark.inl: upload_air)
   std::vector<uint32_t> sort_a, sort_b, sort_cnt;  // scratch of the assertion ordering
+  size_t shard_min_leaves = (size_t)1 << 15;       // column-sharded prover: smaller trees / FRI layers are built on every rank (zkl_set_shard_min_leaves)
   void set_error(const std::string &e) { err = e; }
 };
 

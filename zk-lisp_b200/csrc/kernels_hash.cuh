@@ -88,15 +88,16 @@ __device__ __forceinline__ fe merge_many_dev(const fe *d, size_t stride, int cou
 // ---------------------------------------------------------------- kernels
 // Row hashing over a coset-major LDE: column c lives at lde + c*N, storage index s = k*n + i holds
 // the natural LDE row r = k + blowup*i. Thread (s, q) hashes columns [q*psize, min(W,(q+1)*psize))
-// of row r and writes digest to out[q*N + r].
+// of row r and writes digest to out[q*N + r]. `cstride` = distance between columns (N for a whole matrix; the column-sharded prover
+// hashes the rows of a coset range of a larger matrix: lde offset to the first coset, N = rows in the range, cstride = the whole N).
 __global__ void __launch_bounds__(ZKL_HASH_THREADS) k_hash_rows(const fe *__restrict__ lde, size_t N, size_t n, int blowup, int W, int psize,
-                                                   int nchunks, fe *__restrict__ out) {
+                                                   int nchunks, fe *__restrict__ out, size_t cstride) {
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= N * (size_t)nchunks) return;
   size_t s = t % N; int q = (int)(t / N);
   size_t r = (s / n) + (size_t)blowup * (s % n);
   int first = q * psize, len = min(psize, W - first);
-  fe d = hash_elements_dev(lde + (size_t)first * N + s, N, len);
+  fe d = hash_elements_dev(lde + (size_t)first * cstride + s, cstride, len);
   st_fe(out + (size_t)q * N + r, d);
 }
 // leaf = merge_many(partition digests) (agg/child.rs:1040-1044)
@@ -222,14 +223,14 @@ __global__ void __launch_bounds__(ZKL_COOP_THREADS) k_coop_merkle_level(const fe
 }
 // coset-major row hashing, one group per (row, chunk) — same contract as k_hash_rows
 __global__ void __launch_bounds__(ZKL_COOP_THREADS) k_coop_hash_rows(const fe *__restrict__ lde, size_t N, size_t n, int blowup, int W, int psize,
-                                                                     int nchunks, fe *__restrict__ out) {
+                                                                     int nchunks, fe *__restrict__ out, size_t cstride) {
   size_t total = N * (size_t)nchunks;
   size_t g = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) / ZKL_COOP_GROUP;
   size_t t = g < total ? g : total - 1;
   size_t s = t % N; int q = (int)(t / N);
   size_t r = (s / n) + (size_t)blowup * (s % n);
   int first = q * psize, len = min(psize, W - first);
-  fe d = coop_hash_elements(lde + (size_t)first * N + s, N, len);
+  fe d = coop_hash_elements(lde + (size_t)first * cstride + s, cstride, len);
   if (g < total && (threadIdx.x & (ZKL_COOP_GROUP - 1)) == 0) st_fe(out + (size_t)q * N + r, d);
 }
 __global__ void __launch_bounds__(ZKL_COOP_THREADS) k_coop_merge_many_rows(const fe *__restrict__ parts, size_t stride, size_t rows, int nchunks, fe *__restrict__ out) {

@@ -140,13 +140,13 @@ __global__ void __launch_bounds__(ZKL_QUAD_THREADS) k_quad_merge_many_rows(const
 }
 // coset-major row hashing, one group per (row, chunk) — same contract as k_hash_rows
 __global__ void __launch_bounds__(ZKL_QUAD_THREADS) k_quad_hash_rows(const fe *__restrict__ lde, size_t N, size_t n, int blowup, int W, int psize,
-                                                                     int nchunks, fe *__restrict__ out) {
+                                                                     int nchunks, fe *__restrict__ out, size_t cstride) {
   size_t total = N * (size_t)nchunks;
   size_t g = quad_index(), t = g < total ? g : total - 1;
   size_t s = t % N; int q = (int)(t / N);
   size_t r = (s / n) + (size_t)blowup * (s % n);
   int first = q * psize, len = min(psize, W - first);
-  fe d = quad_hash_elements(lde + (size_t)first * N + s, N, len);
+  fe d = quad_hash_elements(lde + (size_t)first * cstride + s, cstride, len);
   if (g < total && quad_leader()) st_fe(out + (size_t)q * N + r, d);
 }
 // FRI layer leaves — same contract as k_fri_leaves (kernels_stark.cuh)

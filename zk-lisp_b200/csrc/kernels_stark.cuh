@@ -184,11 +184,15 @@ __global__ void __launch_bounds__(256) k_deep_inverses(size_t N, int n, int blow
     if (s0 + j < N) st_fe(inv + s0 + j, iv);
   }
 }
+// Covers storage indices s_base .. s_base + count - 1 and writes deep[s - s_base] (the whole domain: s_base = 0, count = N); with
+// `accumulate` the value is added to what deep[] holds (the column-sharded prover: partial sums over the columns a rank owns).
 __global__ void __launch_bounds__(256) k_deep(const fe *__restrict__ tlde, const fe *__restrict__ clde, size_t N, int n, int blowup, int W, int C,
                                               const fe *__restrict__ dc, const fe *__restrict__ az, const fe *__restrict__ z, fe g_n,
-                                              const fe *__restrict__ wpowN, const fe *__restrict__ inv, fe *__restrict__ deep) {
-  size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= N) return;
+                                              const fe *__restrict__ wpowN, const fe *__restrict__ inv, fe *__restrict__ deep, size_t s_base,
+                                              size_t count, int accumulate) {
+  size_t tl = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tl >= count) return;
+  size_t s = s_base + tl;
   size_t r = (s / n) + (size_t)blowup * (s % n);
   fe x = fe_mul(fe_from_u64(3), ld_fe(wpowN + r));
   fe a = fe_zero();
@@ -206,7 +210,8 @@ __global__ void __launch_bounds__(256) k_deep(const fe *__restrict__ tlde, const
   fe inv12 = ld_fe(inv + s);   // 1 / (d1 d2), k_deep_inverses
   fe i1 = fe_mul(inv12, d2), i2 = fe_mul(inv12, d1);
   fe y = fe_add(fe_mul(fe_sub(a, ld_fe(az)), i1), fe_mul(fe_sub(a, ld_fe(az + 1)), i2));
-  st_fe(deep + s, y);
+  if (accumulate) y = fe_add(y, ld_fe(deep + tl));
+  st_fe(deep + tl, y);
 }
 
 // ---------------------------------------------------------------- FRI (agg/trace.rs:803-820, winter-fri [WF-mem])
@@ -222,13 +227,16 @@ __global__ void __launch_bounds__(ZKL_COOP_THREADS) k_fri_leaves(const fe *__res
   if (g < total && (threadIdx.x & (ZKL_COOP_GROUP - 1)) == 0) st_fe(leaves + (k + (size_t)B * ip), d);
 }
 // next[k][i'] = (v0 (a + x0) - v1 (a - x0)) / (2 x0), x0 = g * w_N^((k + B i') << depth)   [x1 = -x0]
+// `ev` holds B cosets; they are cosets kofs .. kofs + B - 1 of a layer with Bg cosets (the whole layer: kofs = 0, Bg = B; the
+// column-sharded prover folds the cosets a rank owns)
 __global__ void __launch_bounds__(256) k_fri_fold(const fe *__restrict__ ev, int nd, int B, int depth, const fe *__restrict__ alpha,
-                                                  const fe *__restrict__ wpowN, size_t N, fe g_inv_half /* (2g)^-1 */, fe *__restrict__ out) {
+                                                  const fe *__restrict__ wpowN, size_t N, fe g_inv_half /* (2g)^-1 */, fe *__restrict__ out,
+                                                  int kofs, int Bg) {
   size_t half_rows = (size_t)nd / 2, total = half_rows * B;
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= total) return;
   size_t k = t / half_rows, ip = t % half_rows;
-  size_t e = ((k + (size_t)B * ip) << depth) & (N - 1);
+  size_t e = ((k + kofs + (size_t)Bg * ip) << depth) & (N - 1);
   fe w = ld_fe(wpowN + e), winv = ld_fe(wpowN + (e ? N - e : 0));
   fe x0 = fe_mul(fe_from_u64(3), w);
   fe a = ld_fe(alpha);

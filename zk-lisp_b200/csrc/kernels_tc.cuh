@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_permute_batch(fe *states, 
 // tile index = q * tiles_per_part + tile_in_part.
 template <bool HALF>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_hash_rows(const fe *__restrict__ lde, size_t N, size_t n, int blowup, int W, int psize,
-                                                                int nchunks, fe *__restrict__ out) {
+                                                                int nchunks, fe *__restrict__ out, size_t cstride) {
   extern __shared__ unsigned char tc_smem[];
   tc_ctx c = tc_setup(tc_smem);
   size_t tiles_per_part = (N + tc_tile_sponges<HALF>() - 1) / tc_tile_sponges<HALF>();
@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_hash_rows(const fe *__rest
     int q = (int)(tile / tiles_per_part);
     size_t s = tc_index<HALF>(c, tile % tiles_per_part), sc = s < N ? s : N - 1;
     int first = q * psize, len = min(psize, W - first);
-    elems_src src{lde + (size_t)first * N + sc, N, len};
+    elems_src src{lde + (size_t)first * cstride + sc, cstride, len};
     fe d = tc_sponge_run<HALF>(src, 1 + (len + 1) / 2, c);
     if (tc_active<HALF>(c) && s < N && c.half == 0) {
       size_t r = (s / n) + (size_t)blowup * (s % n);

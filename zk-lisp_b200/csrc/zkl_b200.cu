@@ -115,6 +115,7 @@ extern "C" int zkl_ctx_create(int device, zkl_ctx **out) {
   if (const char *e = getenv("ZKL_COOP_PATH")) { int v = atoi(e); if (v >= 0 && v <= 2) c->coop_path = v; }   // experiment knobs (A/B runs of bench.py)
   if (const char *e = getenv("ZKL_TC_HALF_TILES")) c->tc_half_tiles = atoi(e) != 0;
   if (const char *e = getenv("ZKL_WAIT_MODE")) { int v = atoi(e); if (v >= 0 && v <= 3) c->wait_mode = v; }
+  if (const char *e = getenv("ZKL_SHARD_MIN_LEAVES")) { long long v = atoll(e); if (v >= 0) c->shard_min_leaves = (size_t)v; }
   if (const char *e = getenv("ZKL_NTT_PATH")) { int v = atoi(e); if (v >= 0 && v <= 2) c->ntt_path = v; }
   if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) {
     g_create_error = cudaGetErrorString(e); delete c; return 1;
@@ -426,15 +427,16 @@ static size_t partition_size_of(const zkl_options *o, size_t cols, size_t ext = 
   return std::max<size_t>(ps, o->hash_rate / ext);
 }
 // partition digests of a coset-major matrix: out[q * N + r] = hash_elements(row r, columns [q*ps, min(ncols, (q+1)*ps)))
-static int dev_hash_partitions(zkl_ctx *ctx, const fe *lde, size_t ncols, size_t n, size_t blowup, size_t ps, fe *out) {
+static int dev_hash_partitions(zkl_ctx *ctx, const fe *lde, size_t ncols, size_t n, size_t blowup, size_t ps, fe *out, size_t cstride = 0) {
+  if (!cstride) cstride = n * blowup;
   size_t N = n * blowup, nchunks = (ncols + ps - 1) / ps;
   // bulk (tensor-core or thread-per-sponge) kernel when the sponges fill SMs, the 16-thread cooperative one otherwise
   size_t sponges = N * nchunks;
   bool bulk = sponges >= bulk_min(ctx);
-  if (bulk && ctx->hash_path == 0) LAUNCH_TC(ctx, k_tc_hash_rows, sponges, lde, N, n, (int)blowup, (int)ncols, (int)ps, (int)nchunks, out);
-  else if (bulk) LAUNCH(ctx, k_hash_rows, ceil_div(sponges, ZKL_HASH_THREADS), ZKL_HASH_THREADS, 0, lde, N, n, (int)blowup, (int)ncols, (int)ps, (int)nchunks, out);
-  else if (use_quad(ctx)) LAUNCH_QUAD(ctx, k_quad_hash_rows, sponges, lde, N, n, (int)blowup, (int)ncols, (int)ps, (int)nchunks, out);
-  else LAUNCH_COOP(ctx, k_coop_hash_rows, sponges, lde, N, n, (int)blowup, (int)ncols, (int)ps, (int)nchunks, out);
+  if (bulk && ctx->hash_path == 0) LAUNCH_TC(ctx, k_tc_hash_rows, sponges, lde, N, n, (int)blowup, (int)ncols, (int)ps, (int)nchunks, out, cstride);
+  else if (bulk) LAUNCH(ctx, k_hash_rows, ceil_div(sponges, ZKL_HASH_THREADS), ZKL_HASH_THREADS, 0, lde, N, n, (int)blowup, (int)ncols, (int)ps, (int)nchunks, out, cstride);
+  else if (use_quad(ctx)) LAUNCH_QUAD(ctx, k_quad_hash_rows, sponges, lde, N, n, (int)blowup, (int)ncols, (int)ps, (int)nchunks, out, cstride);
+  else LAUNCH_COOP(ctx, k_coop_hash_rows, sponges, lde, N, n, (int)blowup, (int)ncols, (int)ps, (int)nchunks, out, cstride);
   return 0;
 }
 // leaves[r] = merge_many(parts[0][r0 + r], ..., parts[nchunks-1][r0 + r]), r < rows (agg/child.rs:1040-1044); parts[q] at parts + q*stride
@@ -446,13 +448,13 @@ static int dev_merge_partitions(zkl_ctx *ctx, const fe *parts, size_t stride, si
   return 0;
 }
 static int dev_hash_rows(zkl_ctx *ctx, const fe *lde, size_t ncols, size_t n, size_t blowup, const zkl_options *o, fe *leaves,
-                         dev_buf<fe> &scratch, size_t ext = 1) {
+                         dev_buf<fe> &scratch, size_t ext = 1, size_t cstride = 0) {
   // rows of E elements (ext base columns each): PartitionOptions::partition_size::<E> counts E columns, minimum hash_rate / E [WF-mem]
   size_t N = n * blowup, ps = ext * partition_size_of(o, ncols / ext, ext);
   size_t nchunks = (ncols + ps - 1) / ps;
-  if (nchunks == 1) return dev_hash_partitions(ctx, lde, ncols, n, blowup, ps, leaves);
+  if (nchunks == 1) return dev_hash_partitions(ctx, lde, ncols, n, blowup, ps, leaves, cstride);
   ZKL_CHECK(ctx, scratch.alloc(N * nchunks));
-  ZKL_TRY(dev_hash_partitions(ctx, lde, ncols, n, blowup, ps, scratch.p));
+  ZKL_TRY(dev_hash_partitions(ctx, lde, ncols, n, blowup, ps, scratch.p, cstride));
   return dev_merge_partitions(ctx, scratch.p, N, N, nchunks, leaves);
 }
 // MerkleTree::new: nodes[count + i] = leaves[i] conceptually; we store nodes[1..count) and keep leaves
@@ -645,5 +647,6 @@ extern "C" int zkl_evaluate_columns(zkl_ctx *ctx, const zkl_fe *polys, size_t nc
 }
 
 #include "host_air.inl"
+#include "comm_local.inl"
 #include "api_stark.inl"
 #include "api_replay.inl"

@@ -194,7 +194,7 @@ class TorchComm:
 
 
 def shard_columns(lib, opts, width: int, rank: int, world: int):
-    """`zkl_shard_columns`: [first, first + count) of the columns `rank` owns (whole partitions, contiguous blocks)."""
+    """`zkl_shard_columns`: [first, first + count) of the columns `rank` owns (whole partitions, balanced contiguous blocks)."""
     import ctypes as C
     oc = opts.to_c()
     f, w = C.c_size_t(), C.c_size_t()
@@ -203,10 +203,11 @@ def shard_columns(lib, opts, width: int, rank: int, world: int):
     return f.value, w.value
 
 
-def prove_segment_sharded(ctx, comm_c, local_trace_dev: int, first_col: int, local_width: int, width: int, n: int, opts, air_pi) -> bytes:
+def prove_segment_sharded(ctx, comm_c, local_trace_dev: int, first_col: int, local_width: int, width: int, n: int, opts, air_pi,
+                          summary=None) -> bytes:
     """This rank's part of the column-sharded proof of one segment; every rank returns the same bytes — the single-GPU proof.
-    `comm_c`: a capi.Comm (TorchComm(...).c, or `lib.zkl_comm_loopback()` for one rank). `local_trace_dev`: device pointer to the
-    rank's columns (local_width x n, column-major)."""
+    `comm_c`: a capi.Comm (TorchComm(...).c, `lib.zkl_comm_local_rank(group, r)` for the threads of one process, or
+    `lib.zkl_comm_loopback()` for one rank). `local_trace_dev`: device pointer to the rank's columns (local_width x n, column-major)."""
     import ctypes as C
     import numpy as np
     from . import capi
@@ -215,7 +216,70 @@ def prove_segment_sharded(ctx, comm_c, local_trace_dev: int, first_col: int, loc
     prog, pi, o = program_constants(core.program_id, core.program_commitment), public_inputs_to_c(air_pi), opts.to_c()
     buf = np.empty(4 << 20, dtype=np.uint8)
     cap = C.c_size_t(buf.shape[0])
-    summ = capi.ProofSummary()
+    summ = summary if summary is not None else capi.ProofSummary()
     ctx._check(ctx.lib.zkl_prove_segment_sharded_pi_dev(ctx.h, C.c_void_p(local_trace_dev), first_col, local_width, width, n, C.byref(prog), C.byref(pi),
                                                         C.byref(o), comm_c, buf.ctypes.data, C.byref(cap), C.byref(summ)))
     return buf[:cap.value].tobytes()
+
+
+class DeviceColumns:
+    """The columns [first, first + count) of a host trace (W, n, 2) uint64 in device memory of `ctx` (freed on close())."""
+
+    def __init__(self, ctx, trace, first: int, count: int):
+        import ctypes as C
+        import numpy as np
+        self.ctx = ctx
+        host = np.ascontiguousarray(trace[first:first + count], dtype=np.uint64)
+        p = C.c_void_p()
+        ctx._check(ctx.lib.zkl_dev_alloc(ctx.h, host.nbytes, C.byref(p)))
+        self.ptr = p.value
+        ctx._check(ctx.lib.zkl_dev_upload(ctx.h, C.c_void_p(self.ptr), host.ctypes.data, host.nbytes))
+
+    def close(self):
+        import ctypes as C
+        if self.ptr:
+            self.ctx.lib.zkl_dev_free(self.ctx.h, C.c_void_p(self.ptr))
+            self.ptr = None
+
+
+def prove_segment_thread_ranks(contexts, trace, opts, air_pi, min_leaves=None):
+    """The column-sharded proof with one THREAD per rank inside this process (`zkl_comm_local_*`): contexts[r] is rank r's context —
+    all on one device (several shards of a segment on one GPU) or one per device of a box. Returns the list of per-rank proofs (they
+    are all the same bytes)."""
+    import ctypes as C
+    import threading
+    world = len(contexts)
+    lib = contexts[0].lib
+    W, n = trace.shape[0], trace.shape[1]
+    group = C.c_void_p()
+    if lib.zkl_comm_local_create(world, C.byref(group)):
+        raise RuntimeError("zkl_comm_local_create failed")
+    out, errs = [None] * world, [None] * world
+
+    def run(r):
+        cols = None
+        try:
+            ctx = contexts[r]
+            if min_leaves is not None:
+                ctx._check(lib.zkl_set_shard_min_leaves(ctx.h, min_leaves))
+            first, cnt = shard_columns(lib, opts, W, r, world)
+            cols = DeviceColumns(ctx, trace, first, cnt)
+            out[r] = prove_segment_sharded(ctx, lib.zkl_comm_local_rank(group, r), cols.ptr, first, cnt, W, n, opts, air_pi)
+        except Exception as e:   # noqa: BLE001 - reported to the caller below
+            errs[r] = e
+        finally:
+            if cols is not None:
+                cols.close()
+
+    try:
+        # a rank that fails before its first collective leaves the others waiting: the group's barrier times out after 600 s; columns
+        # that cannot be sharded fail on every rank alike, before any collective
+        ts = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+    finally:
+        lib.zkl_comm_local_destroy(group)
+    for e in errs:
+        if e is not None:
+            raise e
+    return out
