@@ -71,6 +71,9 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--bulk-threshold", type=int, default=0)
     ap.add_argument("--reference-sample", action="store_true", help="--impl reference on the bounded n=512 / grind 13 sample instead of the full configuration")
+    ap.add_argument("--config", default="rollup-bench", choices=["rollup-bench", "x-synth"],
+                    help="x-synth: ONE large segment (W = 219, partitions (16, 16)) column-sharded over the N GPUs (BASELINE.json configs[4]; strong scaling)")
+    ap.add_argument("--x-logn", type=int, default=20, help="x-synth: log2 of the trace length (22 = BASELINE's size; the Python trace generator needs ~45 us per row)")
     return ap.parse_args()
 
 
@@ -185,6 +188,157 @@ def run_reference(args, zkl, rank, world):
     print(json.dumps(line))
 
 
+def run_x_synth(args, zkl, rank, world, local):
+    """BASELINE.json configs[4]: ONE large synthetic zk-lisp VM segment (full 219-column layout, PartitionOptions (16, 16) = 14 column
+    partitions), column-sharded over the N GPUs of the box (include/zkl_b200.h: zkl_prove_segment_sharded_*; NCCL through
+    zk-lisp_b200/sharded.py: TorchComm). Strong scaling: the segment is the same at every N; N = 1 is the plain single-GPU prover.
+    value: columns resident in HBM; e2e: every rank's columns start in pinned host memory and the proof bytes end on the host.
+    Rank 0 generates the AIR-valid trace (tests/synth.py) and hands every rank its columns over NCCL before the timed region."""
+    import dataclasses
+    import torch
+    import torch.distributed as dist
+    import synth
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the proving path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n, W = 1 << args.x_logn, 219
+    ctx = zkl.Context(local)
+    lib = ctx.lib
+    t0 = time.time()
+    if rank == 0:
+        trace, air_pi, opts = synth.valid_segment(n=n, queries=QUERIES, blowup=BLOWUP, grind=GRIND, seed=PROGRAM_SEED, full_layout=True, poseidon_levels=False)
+        opts = dataclasses.replace(opts, num_partitions=16, hash_rate=16)
+        assert trace.shape == (W, n, 2)
+        meta = [air_pi, opts]
+    else:
+        trace, meta = None, [None, None]
+    if world > 1:
+        dist.broadcast_object_list(meta, src=0)
+    air_pi, opts = meta
+    gen_s = time.time() - t0
+    if world > 1:
+        first, cnt = zkl.sharded.shard_columns(lib, opts, W, rank, world)
+    else:
+        first, cnt = 0, W
+    cols = torch.empty(cnt * n * 16, dtype=torch.uint8, device=dev)
+    if rank == 0:
+        for r in range(world - 1, -1, -1):
+            f, c = zkl.sharded.shard_columns(lib, opts, W, r, world) if world > 1 else (0, W)
+            t = torch.from_numpy(np.ascontiguousarray(trace[f:f + c]).view(np.uint8).reshape(-1))
+            if r == 0:
+                cols.copy_(t)
+            else:
+                stage = t.to(dev)
+                dist.send(stage, dst=r)
+                del stage
+        del trace
+    else:
+        dist.recv(cols, src=0)
+    torch.cuda.synchronize()
+    host = torch.empty(cols.shape, dtype=torch.uint8, pin_memory=True)
+    host.copy_(cols)
+    comm = zkl.sharded.TorchComm(dist, dev) if world > 1 else None
+    summ = zkl.capi.ProofSummary()
+    prover = zkl.ZkProver(ctx, opts, air_pi)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def prove(from_host):
+        if from_host:
+            cols.copy_(host, non_blocking=True)
+            torch.cuda.synchronize()
+        if world > 1:
+            return zkl.sharded.prove_segment_sharded(ctx, comm.c, cols.data_ptr(), first, cnt, W, n, opts, air_pi, summary=summ), summ
+        p = prover.prove(None, dev_ptr=C.c_void_p(cols.data_ptr()), shape=(W, n))
+        return p, prover.last_summary
+
+    def timed(from_host, steps, sampler=None):
+        barrier()
+        if sampler:
+            sampler.start()
+        launches0 = ctx.launches
+        ev, wall, stages, digests = 0.0, 0.0, np.zeros(12), []
+        for _ in range(steps):
+            if world > 1:
+                dist.barrier()
+            t1 = time.time()
+            proof, s = prove(from_host)
+            wall += (time.time() - t1) * 1e3
+            # device time of the proof: the library's own CUDA events on ITS stream, first stage mark to the last one (the collectives
+            # run inside that window); torch.cuda.Event would only see torch's stream. The e2e leg is reported on the host wall clock.
+            ev += float(sum(s.stage_ms[:9]))
+            stages += np.array(list(s.stage_ms))
+            digests.append(hashlib.blake2b(proof, digest_size=16).hexdigest())
+        barrier()
+        clocks = sampler.stop() if sampler else None
+        t = torch.tensor([ev, wall], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]), float(t[1]), stages / steps, digests, len(proof), ctx.launches - launches0, clocks
+
+    for _ in range(max(args.warmup, 1)):
+        first_proof, _ = prove(False)
+    ref_digest = hashlib.blake2b(first_proof, digest_size=16).hexdigest()
+    sampler = ClockSampler(local) if rank == 0 else None
+    ev, wall, stages, digests, plen, launches, clocks = timed(False, args.steps, sampler)
+    e_ev, e_wall, _, e_digests, _, _, _ = timed(True, args.steps)
+    same = all(d == ref_digest for d in digests + e_digests)
+    if world > 1:
+        every = [None] * world
+        dist.all_gather_object(every, (ref_digest, same, comm.bytes_moved, comm.calls, float(stages[10]), cnt, dict(comm.seconds)))
+    else:
+        every = [(ref_digest, same, 0, 0, float(stages[10]), cnt, {})]
+    i8 = C.c_double()
+    ctx._check(lib.zkl_tc_i8_peak(ctx.h, C.byref(i8)))
+    if rank == 0:
+        N = n * BLOWUP
+        same_everywhere = all(e[0] == ref_digest and e[1] for e in every)
+        # dominant kernel: partition hashing of the rank's columns, one permutation per (LDE row, 16-column partition)
+        my_parts = -(-cnt // 16)
+        hash_ms = float(stages[10])
+        tensor_ops = N * my_parts * TENSOR_OPS_PER_PERM
+        h2d = int(cols.numel())
+        total_steps = max(args.warmup, 1) + 2 * args.steps
+        line = {
+            "metric": "x-synth single-segment prove throughput (trace rows/s)", "value": n * args.steps / (ev * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": ev / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u128 (f128 field, 4x u32 limbs)", "data": "synthetic",
+            "config": {"workload": f"x-synth: ONE segment, n=2^{args.x_logn}, W=219, blowup=16, q=64, grind=16, partitions (16,16) -> 14 column partitions, "
+                                   f"column-sharded over {world} GPU(s); AIR-valid synthetic VM trace", "columns_per_rank": [e[5] for e in every],
+                       "l2": f"the rank's LDE alone is {cnt * N * 16 / 1e9:.1f} GB >> 126 MB L2 (no flush needed)",
+                       "trace_generation_s": round(gen_s, 1)},
+            "wall_ms_per_step": wall / args.steps,
+            "e2e": {"value": n * args.steps / (e_wall * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": plen,
+                    "wall_ms_per_step": e_wall / args.steps, "device_ms_per_step_without_h2d": e_ev / args.steps,
+                    "what": "every rank's columns start in pinned host memory, H2D copy + column-sharded proof + proof bytes on the host; host wall clock, max over ranks"},
+            "gpu_launches": int(launches),
+            "proof_bytes": plen, "proofs_identical_across_ranks_steps_and_legs": bool(same_everywhere),
+            "proof_blake2b": ref_digest,
+            "collectives": {"calls_per_proof": every[0][3] / total_steps, "bytes_sent_per_rank_per_proof": [e[2] / total_steps for e in every],
+                            "host_ms_per_proof_rank0": {k: 1e3 * v / total_steps for k, v in every[0][6].items()},
+                            "raw_rows_would_be": (world - 1) * cnt * N * 16 if world > 1 else 0},
+            "clocks": clocks,
+            "roofline": {"kernel": "k_tc_hash_rows (partition digests of the rank's columns: one sponge permutation per LDE row and 16-column partition)",
+                         "bound": "tensor", "achieved": tensor_ops / (hash_ms * 1e-3) / 1e12, "peak": i8.value / 1e12, "unit": "TOP/s (int8 dense)",
+                         "frac": tensor_ops / (hash_ms * 1e-3) / 1e12 / (i8.value / 1e12),
+                         "peak_source": "measured in this run: zkl_tc_i8_peak", "traffic": None, "ms_per_launch": hash_ms,
+                         "ms_per_launch_per_rank": [e[4] for e in every], "permutations_per_s": N * my_parts / (hash_ms * 1e-3)},
+            "stage_ms_rank0": {lib.zkl_stage_name(i).decode(): float(stages[i]) for i in range(12)},
+            "cpu_baseline": None,
+            "cpu_baseline_note": "no CPU run exists at this size: Winterfell's boundary-divisor table is O(n^2) (SURVEY.md §8a row C); the rollup-bench line carries the CPU arm",
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 class Worker:
     """One CUDA stream (zkl_ctx) proving a share of the step's segments."""
 
@@ -240,6 +394,9 @@ def main():
     zkl = graft.import_zkl()
     if args.impl == "reference":
         run_reference(args, zkl, rank, world)
+        return
+    if args.config == "x-synth":
+        run_x_synth(args, zkl, rank, world, local)
         return
     host_cores = pin_rank_to_cores(local, world)
     import torch

@@ -87,6 +87,23 @@ def test_sharded_proof_is_the_single_gpu_proof(ctx, zkl, case, world):
             c.close()
 
 
+def test_sharded_proof_two_pass_sizes(ctx, zkl):
+    """n = 2^17: the transforms run as two passes over HBM and the boundary polynomials are extended over the rank's CE cosets only
+    (dev_lde_cosets); millions of composition coefficients are drawn by the bulk coin kernel. 4 ranks, production thresholds."""
+    if ctx.hash_mode != "default":
+        pytest.skip("one hashing mode is enough at this size")
+    trace, air_pi, opts = synth.valid_segment(n=1 << 17, queries=32, blowup=16, grind=8, seed=77, full_layout=True, poseidon_levels=False)
+    opts = dataclasses.replace(opts, num_partitions=16, hash_rate=16)
+    single = zkl.ZkProver(ctx, opts, air_pi).prove(trace)
+    ranks = _rank_contexts(zkl, 4, ctx.hash_mode)
+    try:
+        proofs = zkl.sharded.prove_segment_thread_ranks(ranks, trace, opts, air_pi)
+        assert all(p == single for p in proofs)
+    finally:
+        for c in ranks:
+            c.close()
+
+
 def test_sharded_refuses_what_it_cannot_shard(ctx, zkl):
     import ctypes as C
     trace, air_pi, opts = synth.valid_segment(n=64, queries=8, blowup=16, grind=4)

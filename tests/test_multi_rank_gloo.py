@@ -105,3 +105,61 @@ def test_sharding_uneven():
     assert sorted(sum(parts, [])) == list(range(16))
     assert max(map(len, parts)) - min(map(len, parts)) <= 1
     assert zkl.sharding.aggregate(10, 5.0) == (10, 5.0)
+
+
+def _comm_worker(rank, world, port, out):
+    """The `zkl_comm` callbacks of TorchComm (zk-lisp_b200/sharded.py) on HOST buffers over gloo: the semantics the column-sharded prover
+    relies on — all_gather: recv[s] = send of rank s; all_to_all: recv[s] = block `rank` of rank s's send; all_reduce_sum_u64 in place,
+    exact modulo 2^64."""
+    import ctypes as C
+    import numpy as np
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    zkl = graft.import_zkl()
+    comm = zkl.sharded.TorchComm(dist, torch.device("cpu"))
+    ok = comm.c.rank == rank and comm.c.world == world
+    nb = 48
+    send = (np.arange(nb) + 50 * rank).astype(np.uint8)
+    recv = np.zeros(world * nb, dtype=np.uint8)
+    ok &= comm.c.all_gather(None, send.ctypes.data, recv.ctypes.data, nb) == 0
+    ok &= all((recv[s * nb:(s + 1) * nb] == (np.arange(nb) + 50 * s).astype(np.uint8)).all() for s in range(world))
+    send2 = np.concatenate([np.full(nb, 10 * rank + d, dtype=np.uint8) for d in range(world)])
+    recv2 = np.zeros(world * nb, dtype=np.uint8)
+    ok &= comm.c.all_to_all(None, send2.ctypes.data, recv2.ctypes.data, nb) == 0
+    ok &= all((recv2[s * nb:(s + 1) * nb] == 10 * s + rank).all() for s in range(world))
+    buf = np.array([2**63 + rank, 7, 2**64 - 1 if rank == 0 else 1], dtype=np.uint64)
+    ok &= comm.c.all_reduce_sum_u64(None, buf.ctypes.data, buf.shape[0]) == 0
+    want = [(sum(2**63 + r for r in range(world))) % 2**64, 7 * world, (2**64 - 1 + (world - 1)) % 2**64]
+    ok &= [int(x) for x in buf] == want
+    ok &= comm.calls == 3 and comm.error is None
+    # column ownership as the library computes it (pure host code of the CUDA library): a disjoint cover by whole partitions
+    lib = zkl.capi.load_library()
+    for width, parts in ((219, (16, 16)), (204, (16, 16)), (204, (32, 8))):
+        oc = zkl.air.ProofOptions(num_partitions=parts[0], hash_rate=parts[1]).to_c()
+        ps = int(lib.zkl_partition_size(C.byref(oc), width))
+        f, w = C.c_size_t(), C.c_size_t()
+        ok &= lib.zkl_shard_columns(C.byref(oc), width, rank, world, C.byref(f), C.byref(w)) == 0
+        cover = [None] * world
+        dist.all_gather_object(cover, (f.value, w.value))
+        ok &= cover[0][0] == 0 and all(cover[r][0] + cover[r][1] == cover[r + 1][0] for r in range(world - 1)) and sum(c[1] for c in cover) == width
+        ok &= all(c[0] % ps == 0 and c[1] > 0 for c in cover)
+        ok &= max(-(-c[1] // ps) for c in cover) - min(-(-c[1] // ps) for c in cover) <= 1   # balanced: X's 14 partitions over 8 ranks
+    gathered = [None] * world
+    dist.all_gather_object(gathered, bool(ok))
+    if rank == 0:
+        out.put(all(gathered))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_torch_comm_callbacks_world2_and_4():
+    for world in (2, 4):
+        ctx = mp.get_context("spawn")
+        q = ctx.Queue()
+        port = _free_port()
+        procs = [ctx.Process(target=_comm_worker, args=(r, world, port, q)) for r in range(world)]
+        [p.start() for p in procs]
+        assert q.get(timeout=60) is True
+        [p.join(timeout=60) for p in procs]
+        assert all(p.exitcode == 0 for p in procs)

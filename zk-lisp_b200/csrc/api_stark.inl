@@ -350,12 +350,14 @@ static int dev_eval_constraints(zkl_ctx *ctx, const committed_matrix &t, const z
   }
   // boundary polynomials: scatter -> iNTT -> coset LDE over the CE domain
   size_t nb = (size_t)st.nslots + 1;
-  ZKL_CHECK(ctx, st.u.alloc(nb * n)); ZKL_CHECK(ctx, st.bpoly.alloc(nb * M));
+  const size_t bcos = rows ? (size_t)rows->ncos : ce;   // the column-sharded prover extends the boundary polynomials over ITS cosets only
+  ZKL_CHECK(ctx, st.u.alloc(nb * n)); ZKL_CHECK(ctx, st.bpoly.alloc(nb * bcos * n));
   ZKL_CHECK(ctx, cudaMemsetAsync(st.u.p, 0, nb * n * sizeof(fe), ctx->stream));
   if (st.ngroups) LAUNCH(ctx, k_boundary_scatter, ceil_div(st.ngroups, 128), 128, 0, st.as.p, st.group_start.p, st.ngroups, cc_dev, tn->wpow, (int)n, st.nslots, st.u.p);
   ZKL_TRY(dev_interpolate(ctx, st.u.p, st.u.p, nb, n));
-  ZKL_TRY(dev_lde(ctx, st.u.p, st.bpoly.p, nb, n, ce));
-  boundary_dev bd{st.slot_col.p, st.bpoly.p, st.nslots};
+  if (!rows) ZKL_TRY(dev_lde(ctx, st.u.p, st.bpoly.p, nb, n, ce));
+  else ZKL_TRY(dev_lde_cosets(ctx, st.u.p, st.bpoly.p, nb, n, ce, (size_t)rows->kp0, bcos));
+  boundary_dev bd{st.slot_col.p, st.bpoly.p, st.nslots, bcos * n, rows ? 1 : 0};
   if (!rows) LAUNCH(ctx, k_eval_constraints, ceil_div(M, 128), 128, 0, st.air.p, t.lde.p, N, (int)n, (int)t.blowup, (int)ce, per_tab, tN->wpow, cc_dev, bd,
                     coset_consts, plast, ce_out, N, 0, (int)ce, (int)(t.blowup / ce));
   else LAUNCH(ctx, k_eval_constraints, ceil_div((size_t)rows->ncos * n, 128), 128, 0, st.air.p, rows->rows, N, (int)n, (int)t.blowup, (int)ce, per_tab, tN->wpow,
@@ -640,6 +642,16 @@ static int prove_segment_impl(zkl_ctx *ctx, const fe *trace_dev, size_t W, size_
   }
   const size_t Bp = o->blowup / (size_t)R, k0 = (size_t)rk * Bp;   // the LDE cosets this rank owns: [k0, k0 + Bp)
   auto wait_stream = [&]() -> int { return ctx_wait(ctx); };
+  // ZKL_SHARD_TRACE=1: rank 0 prints the host wall time between the marked points of the column-sharded flow (each mark drains the stream)
+  const bool shard_trace = sh && rk == 0 && getenv("ZKL_SHARD_TRACE");
+  auto trace_t0 = std::chrono::steady_clock::now();
+  auto mark = [&](const char *what) {
+    if (!shard_trace) return;
+    ctx_wait(ctx);
+    auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[shard] %-44s %9.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - trace_t0).count());
+    trace_t0 = t1;
+  };
   if (air->cols.width != W) { ctx->set_error("air width does not match the trace"); return 1; }
   if (o->num_queries == 0 || o->num_queries > 255) { ctx->set_error("num_queries must be in [1,255]"); return 1; }
   // E = 2: the quadratic extension. Every drawn E element is (a, 0) with this hasher (zkl_options.field_extension), so the arithmetic
@@ -671,7 +683,8 @@ static int prove_segment_impl(zkl_ctx *ctx, const fe *trace_dev, size_t W, size_
     if (quad) LAUNCH(ctx, k_reseed_draw<ZKL_QUAD_GROUP>, 1, groups * ZKL_QUAD_GROUP, 0, coin.p, digest, copy_to, (int)fused, out);
     else LAUNCH(ctx, k_reseed_draw<ZKL_COOP_GROUP>, 1, groups * ZKL_COOP_GROUP, 0, coin.p, digest, copy_to, (int)fused, out);
     if (draws > fused) {
-      if (quad) LAUNCH_QUAD(ctx, k_quad_coin_draw, draws, coin.p, (uint64_t)0, (int)draws, out);
+      if (draws >= bulk_min(ctx) && ctx->hash_path == 0) LAUNCH_TC(ctx, k_tc_coin_draw, draws, coin.p, (uint64_t)0, draws, out);
+      else if (quad) LAUNCH_QUAD(ctx, k_quad_coin_draw, draws, coin.p, (uint64_t)0, (int)draws, out);
       else LAUNCH_COOP(ctx, k_coin_draw, draws, coin.p, (uint64_t)0, (int)draws, out);
     }
     return 0;
@@ -694,6 +707,7 @@ static int prove_segment_impl(zkl_ctx *ctx, const fe *trace_dev, size_t W, size_
 
   // ---- 2. trace LDE + commitment (hook new_trace_lde), reseed with the root
   zkl_trace_lde tl;
+  air_device_state ast;
   if (!sh) ZKL_TRY(trace_commit_dev(ctx, trace_dev, W, n, o, &tl, &ctx->ev[12]));
   else {
     // local: iNTT, coset LDE and partition digests of the owned columns. Exchange (1): 16 bytes per (row, partition) instead of the
@@ -702,10 +716,13 @@ static int prove_segment_impl(zkl_ctx *ctx, const fe *trace_dev, size_t W, size_
     committed_matrix &m = tl.m;
     m.width = Wl; m.n = n; m.blowup = B; m.N = N;
     ZKL_CHECK(ctx, m.polys.alloc(Wl * n)); ZKL_CHECK(ctx, m.lde.alloc(Wl * N)); ZKL_CHECK(ctx, m.leaves.alloc(N)); ZKL_CHECK(ctx, m.nodes.alloc(N));
+    mark("start, allocations");
     ZKL_TRY(dev_interpolate(ctx, trace_dev, m.polys.p, Wl, n));
+    mark("trace: interpolate");
     ZKL_CHECK(ctx, cudaEventRecord(ctx->ev[12], st));
     ZKL_TRY(dev_lde(ctx, m.polys.p, m.lde.p, Wl, n, B));
     ZKL_CHECK(ctx, cudaEventRecord(ctx->ev[13], st));
+    mark("trace: coset LDE");
     size_t pf, pc; sg.parts_of(rk, &pf, &pc);
     const size_t per = N / R;
     dev_buf<fe> mine, send, recv, parts, leaves_loc;
@@ -713,12 +730,16 @@ static int prove_segment_impl(zkl_ctx *ctx, const fe *trace_dev, size_t W, size_
     ZKL_CHECK(ctx, parts.alloc(sg.P * per)); ZKL_CHECK(ctx, leaves_loc.alloc(per));
     ZKL_TRY(dev_hash_partitions(ctx, m.lde.p, Wl, n, B, sg.ps, mine.p));
     ZKL_CHECK(ctx, cudaEventRecord(ctx->ev[14], st));
+    // the host orders and stages the assertion list (millions of entries for a large segment) while the device extends and hashes
+    if (!shard_trace) ZKL_TRY(upload_air(ctx, air, n, ast));
+    mark("trace: partition digests");
     if (pc < sg.ppr) ZKL_CHECK(ctx, cudaMemsetAsync(send.p, 0, (size_t)R * sg.ppr * per * sizeof(fe), st));   // padded slots travel too
     for (int d = 0; d < R; d++)   // send[d][q][j] = mine[q][d per + j]
       ZKL_CHECK(ctx, cudaMemcpy2DAsync(send.p + (size_t)d * sg.ppr * per, per * sizeof(fe), mine.p + (size_t)d * per, N * sizeof(fe), per * sizeof(fe), pc,
                                        cudaMemcpyDeviceToDevice, st));
     ZKL_TRY(wait_stream());
     ZKL_TRY(comm_call(ctx, sg.comm->all_to_all(sg.comm->user, send.p, recv.p, sg.ppr * per * sizeof(fe)), "all_to_all(partition digests)"));
+    mark("trace: pack + all_to_all(digests)");
     for (int s2 = 0; s2 < R; s2++) {   // parts[q][j], q in global partition order
       size_t f2, c2; sg.parts_of(s2, &f2, &c2);
       ZKL_CHECK(ctx, cudaMemcpyAsync(parts.p + f2 * per, recv.p + (size_t)s2 * sg.ppr * per, c2 * per * sizeof(fe), cudaMemcpyDeviceToDevice, st));
@@ -726,18 +747,21 @@ static int prove_segment_impl(zkl_ctx *ctx, const fe *trace_dev, size_t W, size_
     ZKL_TRY(dev_merge_partitions(ctx, parts.p, per, per, sg.P, leaves_loc.p));
     ZKL_TRY(wait_stream());
     ZKL_TRY(comm_call(ctx, sg.comm->all_gather(sg.comm->user, leaves_loc.p, m.leaves.p, per * sizeof(fe)), "all_gather(trace leaves)"));
+    mark("trace: merge_many + all_gather(leaves)");
     ZKL_TRY(sharded_merkle(ctx, sg, m.leaves.p, m.nodes.p, N));
     ZKL_TRY(wait_stream());
+    mark("trace: tree (sub-trees + all_gather)");
   }
   STAGE_MARK();
 
   // ---- 4/5. composition coefficients (transition then boundary) and constraint evaluation
-  air_device_state ast;
-  ZKL_TRY(upload_air(ctx, air, n, ast));
+  if (!sh || shard_trace) ZKL_TRY(upload_air(ctx, air, n, ast));
   dev_buf<fe> cc, ce_ev, flag;
   ZKL_CHECK(ctx, cc.alloc(ncc)); ZKL_CHECK(ctx, ce_ev.alloc(M)); ZKL_CHECK(ctx, flag.alloc(1));
   ZKL_CHECK(ctx, cudaMemsetAsync(flag.p, 0, sizeof(fe), st));
+  mark("air upload (host: assertions sorted, staged)");
   ZKL_TRY(reseed_draw(tl.m.nodes.p + 1, nullptr, ncc, cc.p));   // reseed with the trace root, draw the composition coefficients
+  mark("draw composition coefficients");
   if (!sh) ZKL_TRY(dev_eval_constraints(ctx, tl.m, air, ast, cc.p, ce_ev.p));
   else {
     // exchange (2): every rank evaluates ce / R constraint-evaluation cosets on FULL-width rows — the coset-major layout makes a coset
@@ -748,6 +772,7 @@ static int prove_segment_impl(zkl_ctx *ctx, const fe *trace_dev, size_t W, size_
     LAUNCH(ctx, k_pack_cosets, ceil_div(per_pair * R, 256), 256, 0, tl.m.lde.p, N, (int)n, (int)(B / ce), (int)Wl, (int)wmax, (int)ncl, R, send.p);
     ZKL_TRY(wait_stream());
     ZKL_TRY(comm_call(ctx, sh->comm->all_to_all(sh->comm->user, send.p, recv.p, per_pair * sizeof(fe)), "all_to_all(CE cosets)"));
+    mark("ce: pack + all_to_all(CE cosets)");
     for (int s2 = 0; s2 < R; s2++) {
       size_t f, cnt; sg.cols_of(s2, W, &f, &cnt);
       if (cnt) ZKL_CHECK(ctx, cudaMemcpyAsync(rows.p + f * ncl * n, recv.p + (size_t)s2 * per_pair, cnt * ncl * n * sizeof(fe), cudaMemcpyDeviceToDevice, st));
@@ -755,9 +780,11 @@ static int prove_segment_impl(zkl_ctx *ctx, const fe *trace_dev, size_t W, size_
     ce_rows cr{rows.p, (int)(rk * ncl), (int)ncl};
     ZKL_TRY(dev_eval_constraints(ctx, tl.m, air, ast, cc.p, ce_ev.p, &cr));
     ZKL_TRY(wait_stream());
+    mark("ce: boundary polys + constraint kernel");
     ZKL_TRY(comm_call(ctx, sh->comm->all_gather(sh->comm->user, ce_ev.p + (size_t)rk * ncl * n, ce_all.p, ncl * n * sizeof(fe)), "all_gather(CE evaluations)"));
     ZKL_CHECK(ctx, cudaMemcpyAsync(ce_ev.p, ce_all.p, M * sizeof(fe), cudaMemcpyDeviceToDevice, st));
     ZKL_TRY(wait_stream());   // ce_all, send, recv die at the end of this block: their frees are stream-ordered, the copies above are done
+    mark("ce: all_gather(evaluations)");
   }
   STAGE_MARK();
 
@@ -774,6 +801,7 @@ static int prove_segment_impl(zkl_ctx *ctx, const fe *trace_dev, size_t W, size_
     dev_buf<fe> loc; ZKL_CHECK(ctx, loc.alloc(Bp * n));
     ZKL_TRY(dev_hash_rows(ctx, m.lde.p + k0 * n, m.width, n, Bp, o, loc.p, m.scratch, m.ext, N));
     ZKL_TRY(shard_leaves_to_tree(ctx, sg, loc.p, B, n, m.leaves.p, m.nodes.p));
+    mark("constraint commitment");
   }
   STAGE_MARK();
 
@@ -816,6 +844,7 @@ static int prove_segment_impl(zkl_ctx *ctx, const fe *trace_dev, size_t W, size_
     ZKL_CHECK(ctx, cudaMemcpyAsync(dc.p, drawn.p, W * sizeof(fe), cudaMemcpyDeviceToDevice, st));
     LAUNCH(ctx, k_spread_columns, ceil_div(C, 256), 256, 0, drawn.p + W, (size_t)1, C / 2, dc.p + W);
   }
+  mark("ood frame");
   dev_buf<fe> deep_inv; ZKL_CHECK(ctx, deep_inv.alloc(N));
   LAUNCH(ctx, k_deep_inverses, ceil_div(N, 256 * DEEP_INV_PER_THREAD), 256, 0, N, (int)n, (int)B, z.p, g_n, tN->wpow, deep_inv.p);
   if (!sh) {
@@ -843,6 +872,7 @@ static int prove_segment_impl(zkl_ctx *ctx, const fe *trace_dev, size_t W, size_
     LAUNCH(ctx, k_deep, ceil_div(Bp * n, 256), 256, 0, (const fe *)nullptr, cmt.m.lde.p, N, (int)n, (int)B, 0, (int)C, dc.p + W, azc.p, z.p, g_n, tN->wpow, deep_inv.p,
            deep.p, k0 * n, Bp * n, 1);
     ZKL_TRY(wait_stream());
+    mark("deep (partial sums, all_to_all, add)");
   }
   STAGE_MARK();
 
@@ -896,6 +926,7 @@ static int prove_segment_impl(zkl_ctx *ctx, const fe *trace_dev, size_t W, size_
     ZKL_TRY(comm_call(ctx, sg.comm->all_gather(sg.comm->user, cur_ev, ev_last.p, Bp * nd * sizeof(fe)), "all_gather(last FRI layer)"));
     cur_ev = ev_last.p; ev_sharded = false;
   }
+  mark("fri layers");
   size_t rem_len = nd;  // (B*nd)/B coefficients
   ZKL_CHECK(ctx, rem_rev.alloc(rem_len));
   LAUNCH(ctx, k_fri_remainder, 1, 32 > (int)nd ? 32 : (int)nd, 0, cur_ev, (int)nd, (int)B, tN->wpow, N, fe_inv(fe_from_u64(3)),

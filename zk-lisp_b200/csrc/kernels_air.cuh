@@ -431,8 +431,9 @@ __device__ __noinline__ fe eval_transition_combined_agg(const frame_reader &f, f
 // (coset-major, M = ce*n), slot == nslots is P_S.
 struct boundary_dev {
   const uint32_t *slot_col;  // nslots entries: trace column of each slot
-  const fe *bpoly;           // (nslots + 1) x M
+  const fe *bpoly;           // (nslots + 1) x M, or (nslots + 1) x (ncos * n) for the cosets of the call when `compact`
   int nslots;
+  size_t stride; int compact;
 };
 
 // p_last table (data independent, cached per (n, ce)): plast[k'*n + i] = L_{n-1}(x) = g_last (x^n - 1) / (n (x - g_last)) at the
@@ -457,7 +458,6 @@ __global__ void __launch_bounds__(128) k_eval_constraints(const air_dev *__restr
                                                           const fe *__restrict__ plast, fe *__restrict__ ce_out, size_t cstride, int kp0, int ncos,
                                                           int cos_step) {
   int tl = blockIdx.x * blockDim.x + threadIdx.x;
-  size_t M = (size_t)ce * n;
   if ((size_t)tl >= (size_t)ncos * n) return;
   int j = tl / n, i = tl - j * n, kp = kp0 + j;
   int t = kp * n + i;
@@ -484,14 +484,15 @@ __global__ void __launch_bounds__(128) k_eval_constraints(const air_dev *__restr
   fe res = fe_mul(fe_mul(tr, xm), zinv);
   // boundary part: n/(x^n-1) * (sum_c T_c(x) P_c(x) - P_S(x))
   fe b = fe_zero();
+  const size_t bt = bd.compact ? (size_t)tl : (size_t)t;
   for (int s0 = 0; s0 < bd.nslots; s0 += 12) {   // unreduced accumulation, 12 products per reduction
     wide_acc w; wacc_zero(w);
     int s1 = min(bd.nslots, s0 + 12);
-    for (int s = s0; s < s1; s++) wacc_mad(w, f.cur(bd.slot_col[s]), ld_fe(bd.bpoly + (size_t)s * M + t));
+    for (int s = s0; s < s1; s++) wacc_mad(w, f.cur(bd.slot_col[s]), ld_fe(bd.bpoly + (size_t)s * bd.stride + bt));
     wacc_add_fe(w, b);
     b = wacc_reduce(w);
   }
-  b = fe_sub(b, ld_fe(bd.bpoly + (size_t)bd.nslots * M + t));
+  b = fe_sub(b, ld_fe(bd.bpoly + (size_t)bd.nslots * bd.stride + bt));
   res = fe_add(res, fe_mul(fe_mul(b, nfe), zinv));
   st_fe(ce_out + t, res);
 }

@@ -163,6 +163,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_merge_with_int_batch(fe se
   tc_teardown(tc_smem);
 }
 
+// coin draws in bulk (same contract as k_coin_draw, kernels_stark.cuh): out[i] = merge_with_int(*seed, counter_base + 1 + i). The
+// composition coefficients of a large segment are millions of draws (one per assertion).
+template <bool HALF>
+__global__ void __launch_bounds__(TC_THREADS, 1) k_tc_coin_draw(const fe *__restrict__ seed, uint64_t counter_base, size_t count, fe *__restrict__ out) {
+  extern __shared__ unsigned char tc_smem[];
+  tc_ctx c = tc_setup(tc_smem);
+  size_t tiles = (count + tc_tile_sponges<HALF>() - 1) / tc_tile_sponges<HALF>();
+  if (c.is_mma) tc_mma_loop(c, tc_my_tiles(tiles) * ZKL_ROUNDS);
+  else {
+    const fe sd = ld_fe(seed);
+    for (size_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      size_t i = tc_index<HALF>(c, tile), ic = i < count ? i : count - 1;
+      mwi_src src{sd, counter_base + 1 + (uint64_t)ic};
+      fe d = tc_sponge_run<HALF>(src, 3, c);
+      if (tc_active<HALF>(c) && i < count && c.half == 0) st_fe(out + i, d);
+    }
+  }
+  tc_teardown(tc_smem);
+}
+
 // FRI layer leaves (same contract as k_fri_leaves, kernels_stark.cuh): leaf[k + B*i'] = hash_elements([ev[k][i'], ev[k][i' + nd/2]])
 template <bool HALF>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_fri_leaves(const fe *__restrict__ ev, int nd, int B, fe *__restrict__ leaves) {

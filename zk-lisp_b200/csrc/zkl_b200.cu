@@ -156,6 +156,8 @@ extern "C" int zkl_ctx_create(int device, zkl_ctx **out) {
   cudaFuncSetAttribute(k_tc_fri_leaves<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
   cudaFuncSetAttribute(k_tc_fri_leaves<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
   cudaFuncSetAttribute(k_tc_grind, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+  cudaFuncSetAttribute(k_tc_coin_draw<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+  cudaFuncSetAttribute(k_tc_coin_draw<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
   label_consts lc;
   lc.elements = host_label("winter/hash/elements");
   lc.merge = host_label("zkl/winter/hash/merge");
@@ -370,7 +372,8 @@ static int dev_interpolate(zkl_ctx *ctx, const fe *src, fe *dst, size_t ncols, s
   return 0;
 }
 // polys (ncols x n) -> coset-major LDE (ncols x blowup x n) over GENERATOR * <w_N>
-static int dev_lde(zkl_ctx *ctx, const fe *polys, fe *out, size_t ncols, size_t n, size_t blowup) {
+static int dev_lde(zkl_ctx *ctx, const fe *polys, fe *out, size_t ncols, size_t n, size_t blowup, size_t k0 = 0, size_t nk = 0) {
+  if (!nk) nk = blowup;
   if (n > NTT_MAX || (n & (n - 1)) || n < 2) { ctx->set_error("trace length must be a power of two in [2, 2^24]"); return 1; }
   size_t N = n * blowup;
   domain_tables *t; ZKL_TRY(get_tables(ctx, N, &t));
@@ -382,6 +385,14 @@ static int dev_lde(zkl_ctx *ctx, const fe *polys, fe *out, size_t ncols, size_t 
     fe *p; ZKL_CHECK(ctx, cudaMalloc((void **)&p, N * sizeof(fe)));
     LAUNCH(ctx, k_lde_scale_table, ceil_div(N, 256), 256, 0, opow, t->wpow, N, (int)n, (int)blowup, p);
     it = ctx->opow.emplace(key, p).first;
+  }
+  if (nk != blowup) {   // a coset range (dev_lde_cosets): the two-pass path only, compact output
+    ntt_split sp = split_for(n);
+    size_t smem = (size_t)sp.T * std::max(sp.n1, sp.n2) * sizeof(fe);
+    LAUNCH(ctx, k_ntt_pass1, dim3(sp.n1 / sp.T, (unsigned)ncols, (unsigned)nk), NTT_THREADS, smem, polys, out, sp.n1, sp.n2, ilog2_sz(sp.n2), sp.T, t->wpow, N,
+           it->second + k0 * n, false);
+    LAUNCH(ctx, k_ntt_pass2, dim3(sp.n2 / sp.T, (unsigned)(ncols * nk)), NTT_THREADS, smem, out, sp.n1, sp.n2, ilog2_sz(sp.n1), sp.T, t->wpow, N, false, false, fe_zero());
+    return 0;
   }
   if (n == NTT16_N && ctx->ntt_path == 0) {   // radix-16 stages on the tensor cores, coset shift folded into the matrix (kernels_tcntt.cuh v2)
     const uint4 *bmat; const fe *tw0;
@@ -418,6 +429,19 @@ static int dev_lde(zkl_ctx *ctx, const fe *polys, fe *out, size_t ncols, size_t 
   size_t smem = (size_t)sp.T * std::max(sp.n1, sp.n2) * sizeof(fe);
   LAUNCH(ctx, k_ntt_pass1, dim3(sp.n1 / sp.T, (unsigned)ncols, (unsigned)blowup), NTT_THREADS, smem, polys, out, sp.n1, sp.n2, ilog2_sz(sp.n2), sp.T, t->wpow, N, it->second, false);
   LAUNCH(ctx, k_ntt_pass2, dim3(sp.n2 / sp.T, (unsigned)(ncols * blowup)), NTT_THREADS, smem, out, sp.n1, sp.n2, ilog2_sz(sp.n1), sp.T, t->wpow, N, false, false, fe_zero());
+  return 0;
+}
+// the cosets k0 .. k0 + nk - 1 of the same LDE, compact: out[c][j][i] = LDE[c][k0 + j][i] (column-sharded prover: a rank extends what
+// every rank holds as coefficients only over the cosets it owns). Natively for the two-pass sizes — where it matters —, through the
+// whole LDE and a strided copy otherwise.
+static int dev_lde_cosets(zkl_ctx *ctx, const fe *polys, fe *out, size_t ncols, size_t n, size_t blowup, size_t k0, size_t nk) {
+  if (k0 + nk > blowup || !nk) { ctx->set_error("coset range outside the LDE domain"); return 1; }
+  if (nk == blowup) return dev_lde(ctx, polys, out, ncols, n, blowup);
+  const bool two_pass = n > NTT_SINGLE_PASS_MAX && !(ctx->ntt_path == 0 && cross_radix(n));
+  if (two_pass) return dev_lde(ctx, polys, out, ncols, n, blowup, k0, nk);
+  dev_buf<fe> full; ZKL_CHECK(ctx, full.alloc(ncols * n * blowup));
+  ZKL_TRY(dev_lde(ctx, polys, full.p, ncols, n, blowup));
+  ZKL_CHECK(ctx, cudaMemcpy2DAsync(out, nk * n * sizeof(fe), full.p + k0 * n, blowup * n * sizeof(fe), nk * n * sizeof(fe), ncols, cudaMemcpyDeviceToDevice, ctx->stream));
   return 0;
 }
 // leaves[r] for the coset-major matrix `lde` (ncols x N); partition size per PartitionOptions

@@ -150,24 +150,43 @@ class _DevMem:
         self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
 
 
+def _view(torch, device, ptr: int, nbytes: int):
+    """`nbytes` at `ptr` as a uint8 tensor without a copy: device memory on a CUDA device, host memory otherwise (the gloo tests)."""
+    if getattr(device, "type", "cuda") == "cuda":
+        return torch.as_tensor(_DevMem(ptr, nbytes), device=device)
+    import ctypes as C
+    import numpy as np
+    return torch.from_numpy(np.ctypeslib.as_array((C.c_uint8 * nbytes).from_address(ptr)))
+
+
 class TorchComm:
-    """`zkl_comm` over torch.distributed (NCCL): all-gather, all-to-all and a u64 sum on the calling rank's device pointers."""
+    """`zkl_comm` over torch.distributed: all-gather, all-to-all and a u64 sum on the calling rank's pointers. NCCL with device
+    pointers is the product path (one process per GPU); with `device` = cpu and a gloo group the same callbacks move host memory,
+    which is how the CPU suite checks their semantics against the in-process communicator's (tests/test_multi_rank_gloo.py)."""
 
     def __init__(self, dist, device):
-        import ctypes as C
         import torch
         from . import capi
         self.dist, self.device, self.torch = dist, device, torch
-        self.bytes_moved = 0
+        self.bytes_moved, self.calls, self.error = 0, 0, None
+        self.seconds = {"all_gather": 0.0, "all_to_all": 0.0, "all_reduce_sum_u64": 0.0}   # host wall time inside the callbacks
+        cuda = getattr(device, "type", "cuda") == "cuda"
+        world = dist.get_world_size()
 
         def view(ptr, nbytes):
-            return torch.as_tensor(_DevMem(ptr, nbytes), device=device)
+            return _view(torch, device, ptr, nbytes)
 
-        def guard(fn):
+        def guard(fn, name):
+            import time
+
             def run(*a):
                 try:
+                    t0 = time.perf_counter()
                     fn(*a)
-                    torch.cuda.synchronize(device)
+                    if cuda:
+                        torch.cuda.synchronize(device)
+                    self.seconds[name] += time.perf_counter() - t0
+                    self.calls += 1
                     return 0
                 except Exception as e:      # a Python exception must not unwind through the C caller
                     self.error = repr(e)
@@ -175,22 +194,20 @@ class TorchComm:
             return run
 
         def all_gather(user, send, recv, nbytes):
-            self.bytes_moved += (dist.get_world_size() - 1) * nbytes
-            dist.all_gather_into_tensor(view(recv, nbytes * dist.get_world_size()), view(send, nbytes))
+            self.bytes_moved += (world - 1) * nbytes
+            dist.all_gather_into_tensor(view(recv, nbytes * world), view(send, nbytes))
 
         def all_to_all(user, send, recv, nbytes):
-            w = dist.get_world_size()
-            self.bytes_moved += (w - 1) * nbytes
-            dist.all_to_all_single(view(recv, nbytes * w), view(send, nbytes * w))
+            self.bytes_moved += (world - 1) * nbytes
+            dist.all_to_all_single(view(recv, nbytes * world), view(send, nbytes * world))
 
         def all_reduce(user, buf, count):
             self.bytes_moved += 8 * count
             dist.all_reduce(view(buf, 8 * count).view(torch.int64), op=dist.ReduceOp.SUM)   # two's-complement sum = unsigned sum mod 2^64
 
-        self._keep = (capi.COMM_MOVE(guard(all_gather)), capi.COMM_MOVE(guard(all_to_all)), capi.COMM_SUM(guard(all_reduce)))
-        self.c = capi.Comm(dist.get_rank(), dist.get_world_size(), None, *self._keep)
-        self.error = None
-        del C
+        self._keep = (capi.COMM_MOVE(guard(all_gather, "all_gather")), capi.COMM_MOVE(guard(all_to_all, "all_to_all")),
+                      capi.COMM_SUM(guard(all_reduce, "all_reduce_sum_u64")))
+        self.c = capi.Comm(dist.get_rank(), world, None, *self._keep)
 
 
 def shard_columns(lib, opts, width: int, rank: int, world: int):
