@@ -193,6 +193,7 @@ struct air_device_state {
   struct view_as { assertion_dev *p; } as;
   struct view_u32 { uint32_t *p; } group_start, slot_col;
   dev_buf<fe> coset_consts, u, bpoly;
+  dev_buf<uint8_t> tmpl_blob;   // closed-form assertion list (host_air.inl: sched_assertions) the device expands
   int nslots = 0, ngroups = 0;
 };
 // Host wait for everything enqueued on the context's stream (ZKL_WAIT_MODE / ctx->wait_mode): 1 = spin (cudaStreamSynchronize:
@@ -235,16 +236,48 @@ static int stage_reserve(zkl_ctx *ctx, size_t bytes) {
   ctx->stage_cap = cap;
   return 0;
 }
-static int upload_air(zkl_ctx *ctx, const zkl_air_params *a, size_t n, air_device_state &st) {
-  if (a->cols.width > 255) { ctx->set_error("trace width must fit in u8 (winterfell TraceInfo)"); return 1; }
-  const size_t na = a->num_assertions;
-  auto al = [](size_t x) { return (x + 15) & ~(size_t)15; };
-  const size_t off_as = al(sizeof(air_dev)), off_gs = off_as + al(std::max<size_t>(na, 1) * sizeof(assertion_dev));
-  // group count is known only after the pass over the steps: reserve the worst case (one group per assertion)
-  const size_t off_sc = off_gs + al((na + 1) * 4), total = off_sc + al(256 * 4);
-  uint8_t *hb = (uint8_t *)stage_alloc(ctx, total);
-  if (!hb) { ZKL_TRY(stage_reserve(ctx, total)); hb = (uint8_t *)stage_alloc(ctx, total); }   // hook-level call: the region is free (each ends with a wait)
-  air_dev &h = *(air_dev *)hb; memset(&h, 0, sizeof h);
+// ---- the assertion list from its closed form (host_air.inl: sched_assertions), in Winterfell's order (step, then column) ----
+// Template entry j of level l sits at rank l T + j + (extras ordered before it); a template step's group starts at
+// l T + first_j + (extras at earlier steps). The <= 32 extras and the groups of steps only extras name are ranked on the host.
+struct tmpl_dev { uint32_t slot, pos, col, pad; fe value; };       // sorted by (pos, col)
+struct tgroup_dev { uint32_t pos, first_j; };                        // distinct positions of the template
+struct extra_fix { uint32_t rank, pad[3]; assertion_dev a; };
+struct group_fix { uint32_t gidx, gstart; };
+struct expand_args {
+  uint32_t levels, period, T, G, E, XO, NGF, nt;
+  const tmpl_dev *tmpl; const tgroup_dev *tg; const uint32_t *ex_step, *ex_col, *xo_step; const extra_fix *ef; const group_fix *gf;
+};
+__global__ void k_expand_assertions(expand_args a, assertion_dev *__restrict__ as, uint32_t *__restrict__ gs) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t nT = (size_t)a.levels * a.T, nG = (size_t)a.levels * a.G;
+  if (t < nT) {
+    const uint32_t l = (uint32_t)(t / a.T), j = (uint32_t)(t - (size_t)l * a.T);
+    const tmpl_dev x = a.tmpl[j];
+    const uint32_t step = l * a.period + x.pos;
+    uint32_t eb = 0;
+    for (uint32_t e = 0; e < a.E; e++) eb += (a.ex_step[e] < step || (a.ex_step[e] == step && a.ex_col[e] < x.col)) ? 1 : 0;
+    const size_t rank = t + eb;
+    assertion_dev o; o.slot = x.slot; o.step = step; o.cc_index = a.nt + (uint32_t)rank; o.pad = 0; o.value = x.value;
+    as[rank] = o;
+    return;
+  }
+  t -= nT;
+  if (t < nG) {
+    const uint32_t l = (uint32_t)(t / a.G), k = (uint32_t)(t - (size_t)l * a.G);
+    const uint32_t step = l * a.period + a.tg[k].pos;
+    uint32_t eb = 0, xo = 0;
+    for (uint32_t e = 0; e < a.E; e++) eb += a.ex_step[e] < step ? 1 : 0;
+    for (uint32_t e = 0; e < a.XO; e++) xo += a.xo_step[e] < step ? 1 : 0;
+    gs[t + xo] = l * a.T + a.tg[k].first_j + eb;
+    return;
+  }
+  t -= nG;
+  if (t < a.E) { as[a.ef[t].rank] = a.ef[t].a; return; }
+  t -= a.E;
+  if (t < a.NGF) gs[a.gf[t].gidx] = a.gf[t].gstart;
+}
+static int fill_air_header(zkl_ctx *ctx, const zkl_air_params *a, air_dev &h) {
+  memset(&h, 0, sizeof h);
   h.cols = a->cols;
   h.f_poseidon = a->f_poseidon; h.f_vm = a->f_vm; h.f_sponge = a->f_sponge; h.f_merkle = a->f_merkle; h.f_ram = a->f_ram;
   h.rom_enabled = a->rom_enabled; h.vm_usage_mask = a->vm_usage_mask; h.ram_delta_clk_bits = a->ram_delta_clk_bits;
@@ -259,6 +292,92 @@ static int upload_air(zkl_ctx *ctx, const zkl_air_params *a, size_t n, air_devic
   for (int r = 0; r < ZKL_ROUNDS; r++) for (int j = 0; j < 3; j++) h.rom_rc[r][j] = fe_from_abi(a->rom.rc[r][j]);
   for (int k = 0; k < 59; k++) { h.rom_w0[k] = fe_from_abi(a->rom_w_enc0[k]); h.rom_w1[k] = fe_from_abi(a->rom_w_enc1[k]); }
   h.program_fe0 = fe_from_abi(a->program_fe0); h.merkle_root_fe = fe_from_abi(a->merkle_root_fe);
+  return 0;
+}
+// the closed form: a few KB cross PCIe, the device writes the ordered list (k_expand_assertions)
+static int upload_air_sched(zkl_ctx *ctx, const zkl_air_params *a, size_t n, air_device_state &st, const sched_assertions &sa) {
+  auto al = [](size_t x) { return (x + 15) & ~(size_t)15; };
+  const size_t T = sa.tmpl.size(), E = sa.extras.size(), na = sa.count();
+  if (na != a->num_assertions || (size_t)sa.levels * sa.period != n || !T || E > 64) { ctx->set_error("inconsistent closed-form assertion list"); return 1; }
+  std::vector<zkl_assertion> tm = sa.tmpl, ex = sa.extras;
+  auto by_step_col = [](const zkl_assertion &x, const zkl_assertion &y) { return x.step != y.step ? x.step < y.step : x.column < y.column; };
+  std::sort(tm.begin(), tm.end(), by_step_col); std::sort(ex.begin(), ex.end(), by_step_col);
+  for (const auto &x : tm) if (x.column >= a->cols.width || x.step >= sa.period) { ctx->set_error("assertion outside the trace"); return 1; }
+  for (const auto &x : ex) if (x.column >= a->cols.width || x.step >= n) { ctx->set_error("assertion outside the trace"); return 1; }
+  // distinct positions of the template, slots (dense numbering of the asserted columns)
+  std::vector<tgroup_dev> tg;
+  for (size_t j = 0; j < T; j++) if (!j || tm[j].step != tm[j - 1].step) tg.push_back(tgroup_dev{tm[j].step, (uint32_t)j});
+  const size_t G = tg.size();
+  int slot_of[256]; for (int c = 0; c < 256; c++) slot_of[c] = -1;
+  uint32_t slot_col_h[256]; int nslots = 0;
+  auto slot = [&](uint32_t col) { if (slot_of[col] < 0) { slot_of[col] = nslots; slot_col_h[nslots++] = col; } return (uint32_t)slot_of[col]; };
+  // steps only extras name, the groups they open, the final sentinel
+  auto tmpl_has_pos = [&](uint32_t pos) { for (auto &g : tg) if (g.pos == pos) return true; return false; };
+  std::vector<uint32_t> xo;
+  for (size_t e = 0; e < E; e++) if (!tmpl_has_pos(ex[e].step % sa.period) && (xo.empty() || xo.back() != ex[e].step)) xo.push_back(ex[e].step);
+  const size_t XO = xo.size(), ng = (size_t)sa.levels * G + XO, NGF = XO + 1;
+  const size_t o_t = al(sizeof(air_dev)), o_g = o_t + al(T * sizeof(tmpl_dev)), o_es = o_g + al(G * sizeof(tgroup_dev)), o_ec = o_es + al((E + 1) * 4),
+               o_xo = o_ec + al((E + 1) * 4), o_ef = o_xo + al((XO + 1) * 4), o_gf = o_ef + al((E + 1) * sizeof(extra_fix)), o_sc = o_gf + al(NGF * sizeof(group_fix)),
+               small = o_sc + al(256 * 4);
+  uint8_t *hb = (uint8_t *)stage_alloc(ctx, small);
+  if (!hb) { ZKL_TRY(stage_reserve(ctx, small)); hb = (uint8_t *)stage_alloc(ctx, small); }
+  ZKL_TRY(fill_air_header(ctx, a, *(air_dev *)hb));
+  tmpl_dev *td = (tmpl_dev *)(hb + o_t); tgroup_dev *tgd = (tgroup_dev *)(hb + o_g);
+  uint32_t *es = (uint32_t *)(hb + o_es), *ec = (uint32_t *)(hb + o_ec), *xod = (uint32_t *)(hb + o_xo);
+  extra_fix *ef = (extra_fix *)(hb + o_ef); group_fix *gf = (group_fix *)(hb + o_gf);
+  for (size_t j = 0; j < T; j++) { td[j].slot = slot(tm[j].column); td[j].pos = tm[j].step; td[j].col = tm[j].column; td[j].pad = 0; td[j].value = fe_from_abi(tm[j].value); }
+  memcpy(tgd, tg.data(), G * sizeof(tgroup_dev));
+  for (size_t e = 0; e < E; e++) {
+    const uint32_t lvl = ex[e].step / sa.period, pos = ex[e].step % sa.period;
+    size_t before = 0;   // template entries of the extra's own level ordered before it
+    for (size_t j = 0; j < T; j++) before += (tm[j].step < pos || (tm[j].step == pos && tm[j].column < ex[e].column)) ? 1 : 0;
+    const size_t rank = (size_t)lvl * T + before + e;
+    es[e] = ex[e].step; ec[e] = ex[e].column;
+    memset(&ef[e], 0, sizeof ef[e]);
+    ef[e].rank = (uint32_t)rank;
+    ef[e].a.slot = slot(ex[e].column); ef[e].a.step = ex[e].step; ef[e].a.cc_index = a->num_transition + (uint32_t)rank; ef[e].a.value = fe_from_abi(ex[e].value);
+  }
+  for (size_t x = 0; x < XO; x++) {
+    const uint32_t lvl = xo[x] / sa.period, pos = xo[x] % sa.period;
+    size_t tsteps = 0, tents = 0, eb = 0;
+    for (auto &g : tg) tsteps += g.pos < pos ? 1 : 0;
+    for (size_t j = 0; j < T; j++) tents += tm[j].step < pos ? 1 : 0;
+    for (size_t e = 0; e < E; e++) eb += ex[e].step < xo[x] ? 1 : 0;
+    xod[x] = xo[x];
+    gf[x].gidx = (uint32_t)((size_t)lvl * G + tsteps + x); gf[x].gstart = (uint32_t)((size_t)lvl * T + tents + eb);
+  }
+  gf[XO].gidx = (uint32_t)ng; gf[XO].gstart = (uint32_t)na;
+  memcpy(hb + o_sc, slot_col_h, 256 * 4);
+  // device: the small tables, then the expanded list in the layout the kernels read
+  const size_t off_as = al(sizeof(air_dev)), off_gs = off_as + al(na * sizeof(assertion_dev)), off_sc = off_gs + al((ng + 1) * 4), total = off_sc + al(256 * 4);
+  ZKL_CHECK(ctx, st.tmpl_blob.alloc(small)); ZKL_CHECK(ctx, st.blob.alloc(total));
+  ZKL_CHECK(ctx, cudaMemcpyAsync(st.tmpl_blob.p, hb, small, cudaMemcpyHostToDevice, ctx->stream));
+  ZKL_CHECK(ctx, cudaMemcpyAsync(st.blob.p, st.tmpl_blob.p, sizeof(air_dev), cudaMemcpyDeviceToDevice, ctx->stream));
+  ZKL_CHECK(ctx, cudaMemcpyAsync(st.blob.p + off_sc, st.tmpl_blob.p + o_sc, 256 * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+  st.air.p = (air_dev *)st.blob.p; st.as.p = (assertion_dev *)(st.blob.p + off_as);
+  st.group_start.p = (uint32_t *)(st.blob.p + off_gs); st.slot_col.p = (uint32_t *)(st.blob.p + off_sc);
+  st.nslots = nslots; st.ngroups = (int)ng;
+  const uint8_t *d = st.tmpl_blob.p;
+  expand_args ea{sa.levels, sa.period, (uint32_t)T, (uint32_t)G, (uint32_t)E, (uint32_t)XO, (uint32_t)NGF, a->num_transition,
+                 (const tmpl_dev *)(d + o_t), (const tgroup_dev *)(d + o_g), (const uint32_t *)(d + o_es), (const uint32_t *)(d + o_ec), (const uint32_t *)(d + o_xo),
+                 (const extra_fix *)(d + o_ef), (const group_fix *)(d + o_gf)};
+  const size_t threads = (size_t)sa.levels * (T + G) + E + NGF;
+  LAUNCH(ctx, k_expand_assertions, ceil_div(threads, 256), 256, 0, ea, st.as.p, st.group_start.p);
+  return 0;
+}
+static int upload_air(zkl_ctx *ctx, const zkl_air_params *a, size_t n, air_device_state &st, const sched_assertions *sched = nullptr) {
+  if (a->cols.width > 255) { ctx->set_error("trace width must fit in u8 (winterfell TraceInfo)"); return 1; }
+  if (sched) return upload_air_sched(ctx, a, n, st, *sched);
+  if (!a->assertions && a->num_assertions) { ctx->set_error("zkl_air_params.assertions is NULL"); return 1; }
+  const size_t na = a->num_assertions;
+  auto al = [](size_t x) { return (x + 15) & ~(size_t)15; };
+  const size_t off_as = al(sizeof(air_dev)), off_gs = off_as + al(std::max<size_t>(na, 1) * sizeof(assertion_dev));
+  // group count is known only after the pass over the steps: reserve the worst case (one group per assertion)
+  const size_t off_sc = off_gs + al((na + 1) * 4), total = off_sc + al(256 * 4);
+  uint8_t *hb = (uint8_t *)stage_alloc(ctx, total);
+  if (!hb) { ZKL_TRY(stage_reserve(ctx, total)); hb = (uint8_t *)stage_alloc(ctx, total); }   // hook-level call: the region is free (each ends with a wait)
+  air_dev &h = *(air_dev *)hb;
+  ZKL_TRY(fill_air_header(ctx, a, h));
   // order[] = assertion indices sorted by (step, column), stable: counting sort by column, then by step
   for (size_t i = 0; i < na; i++)
     if (a->assertions[i].column >= a->cols.width || a->assertions[i].step >= n) { ctx->set_error("assertion outside the trace"); return 1; }
@@ -629,7 +748,7 @@ extern "C" const char *zkl_stage_name(int s) { return (s >= 0 && s < 12) ? k_sta
 // ------------------------------------------------------------------------------------------------
 static int prove_segment_impl(zkl_ctx *ctx, const fe *trace_dev, size_t W, size_t n, const zkl_air_params *air, const zkl_fe *seed_elems,
                               size_t num_seed, const zkl_options *o, uint8_t *out_proof, size_t *out_len, zkl_proof_summary *summary,
-                              const shard_view *sh = nullptr) {
+                              const shard_view *sh = nullptr, const sched_assertions *sched = nullptr) {
   ZKL_TRY(need_suite(ctx));
   ZKL_TRY(check_opts(ctx, o, n));
   // column-sharded mode: trace_dev holds this rank's Wl columns [first_col, first_col + Wl) of the W-column trace
@@ -667,7 +786,8 @@ static int prove_segment_impl(zkl_ctx *ctx, const fe *trace_dev, size_t W, size_
   // the opening plan (one pointer + one index per opened element) and the opened elements themselves
   const size_t logN = (size_t)ilog2_sz(N);
   const size_t max_open = (size_t)o->num_queries * (W + C + 2 * logN + nl * (2 + logN)) + 64;
-  const size_t stage_need = sizeof(air_dev) + ((size_t)air->num_assertions + 2) * (sizeof(assertion_dev) + 4) + 256 * 4 + num_seed * sizeof(fe) +
+  const size_t stage_as = sched ? 4096 + (sched->tmpl.size() + 2 * sched->extras.size() + 8) * 64 : ((size_t)air->num_assertions + 2) * (sizeof(assertion_dev) + 4);
+  const size_t stage_need = sizeof(air_dev) + stage_as + 256 * 4 + num_seed * sizeof(fe) +
                             max_open * (sizeof(fe *) + 4 + sizeof(fe)) + (4 * (W + C) + nl + rem_cap_of(*o) + 64) * sizeof(fe) + 8192;
   ZKL_TRY(stage_reserve(ctx, stage_need));
   domain_tables *tN; ZKL_TRY(get_tables(ctx, N, &tN));
@@ -731,7 +851,7 @@ static int prove_segment_impl(zkl_ctx *ctx, const fe *trace_dev, size_t W, size_
     ZKL_TRY(dev_hash_partitions(ctx, m.lde.p, Wl, n, B, sg.ps, mine.p));
     ZKL_CHECK(ctx, cudaEventRecord(ctx->ev[14], st));
     // the host orders and stages the assertion list (millions of entries for a large segment) while the device extends and hashes
-    if (!shard_trace) ZKL_TRY(upload_air(ctx, air, n, ast));
+    if (!shard_trace) ZKL_TRY(upload_air(ctx, air, n, ast, sched));
     mark("trace: partition digests");
     if (pc < sg.ppr) ZKL_CHECK(ctx, cudaMemsetAsync(send.p, 0, (size_t)R * sg.ppr * per * sizeof(fe), st));   // padded slots travel too
     for (int d = 0; d < R; d++)   // send[d][q][j] = mine[q][d per + j]
@@ -755,7 +875,7 @@ static int prove_segment_impl(zkl_ctx *ctx, const fe *trace_dev, size_t W, size_
   STAGE_MARK();
 
   // ---- 4/5. composition coefficients (transition then boundary) and constraint evaluation
-  if (!sh || shard_trace) ZKL_TRY(upload_air(ctx, air, n, ast));
+  if (!sh || shard_trace) ZKL_TRY(upload_air(ctx, air, n, ast, sched));
   dev_buf<fe> cc, ce_ev, flag;
   ZKL_CHECK(ctx, cc.alloc(ncc)); ZKL_CHECK(ctx, ce_ev.alloc(M)); ZKL_CHECK(ctx, flag.alloc(1));
   ZKL_CHECK(ctx, cudaMemsetAsync(flag.p, 0, sizeof(fe), st));
@@ -1160,9 +1280,9 @@ static int prove_segment_pi_impl(zkl_ctx *ctx, const fe *trace_dev, size_t width
                                  const zkl_options *opts, uint8_t *out_proof, size_t *out_len, zkl_proof_summary *summary) {
   auto t0 = std::chrono::steady_clock::now();
   built_air b;
-  if (build_air_host(program, pi, width, n, opts, b)) { ctx->set_error(b.err); return 1; }
+  if (build_air_host(program, pi, width, n, opts, b, false)) { ctx->set_error(b.err); return 1; }   // closed form: the device expands the assertion list
   const float host_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
-  int rc = prove_segment_impl(ctx, trace_dev, width, n, &b.p, b.seed.data(), b.seed.size(), opts, out_proof, out_len, summary);
+  int rc = prove_segment_impl(ctx, trace_dev, width, n, &b.p, b.seed.data(), b.seed.size(), opts, out_proof, out_len, summary, nullptr, &b.sched);
   if (summary && (rc == 0 || rc == ZKL_ERR_CONSTRAINTS_VIOLATED)) summary->stage_ms[11] = host_ms;
   return rc;
 }
@@ -1204,10 +1324,14 @@ extern "C" int zkl_prove_segment_sharded_pi_dev(zkl_ctx *ctx, const void *local_
                                                 const zkl_program *program, const zkl_public_inputs *pi, const zkl_options *opts,
                                                 const zkl_comm *comm, uint8_t *out_proof, size_t *out_len, zkl_proof_summary *summary) {
   if (!comm) { ctx->set_error("zkl_comm is required"); return 1; }
+  auto t0 = std::chrono::steady_clock::now();
   built_air b;
-  if (build_air_host(program, pi, width, n, opts, b)) { ctx->set_error(b.err); return 1; }
+  if (build_air_host(program, pi, width, n, opts, b, false)) { ctx->set_error(b.err); return 1; }
+  const float host_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
   shard_view sh{comm, first_col, local_width};
-  return prove_segment_impl(ctx, (const fe *)local_trace_dev, width, n, &b.p, b.seed.data(), b.seed.size(), opts, out_proof, out_len, summary, &sh);
+  int rc = prove_segment_impl(ctx, (const fe *)local_trace_dev, width, n, &b.p, b.seed.data(), b.seed.size(), opts, out_proof, out_len, summary, &sh, &b.sched);
+  if (summary && (rc == 0 || rc == ZKL_ERR_CONSTRAINTS_VIOLATED)) summary->stage_ms[11] = host_ms;
+  return rc;
 }
 // world = 1: the "collectives" are device-to-device copies (all_gather / all_to_all of one block) and a no-op (sum over one rank)
 static int loop_copy(void *, const void *send, void *recv, size_t bytes) {

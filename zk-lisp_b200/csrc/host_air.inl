@@ -221,9 +221,19 @@ static degree_stats transition_degree_stats(uint64_t fm, bool rom_enabled, uint3
 }
 
 // ---- the whole AIR instance ----
+// The assertion list in closed form: `tmpl` holds the assertions of ONE schedule level (step = position inside the level, 141 of them
+// for ZkLispAir), repeated for every one of `levels` levels of `period` rows; `extras` the few public-input-dependent single
+// assertions at absolute steps. The device expands it in Winterfell's order (api_stark.inl: upload_air) — a 2^22-row segment declares
+// 18.5 M assertions, which the host would otherwise build, order and push through PCIe for every proof.
+struct sched_assertions {
+  uint32_t period = 32, levels = 0;
+  std::vector<zkl_assertion> tmpl, extras;
+  size_t count() const { return (size_t)levels * tmpl.size() + extras.size(); }
+};
 struct built_air {
   zkl_air_params p;
-  std::vector<zkl_assertion> as;
+  std::vector<zkl_assertion> as;   // the explicit list (expand = true), get_assertions order
+  sched_assertions sched;          // the same list in closed form
   std::vector<zkl_fe> seed;
   std::string err;
 };
@@ -231,7 +241,8 @@ static inline zkl_fe abi_u64(uint64_t v) { zkl_fe r; r.lo = v; r.hi = 0; return 
 static inline bool abi_is_zero(const zkl_fe &v) { return (v.lo | v.hi) == 0; }
 static inline zkl_fe be_from_le8_abi(const uint8_t b[32]) { return fe_to_abi(fe_from_le16(b)); }   // utils.rs:346-355
 
-static int build_air_host(const zkl_program *prog, const zkl_public_inputs *pi, size_t width, size_t n, const zkl_options *o, built_air &out) {
+static int build_air_host(const zkl_program *prog, const zkl_public_inputs *pi, size_t width, size_t n, const zkl_options *o, built_air &out,
+                          bool expand = true) {
   if (n < 32 || (n & (n - 1))) { out.err = "trace length must be a power of two >= 32 (one schedule level)"; return 1; }
   if (pi->num_main_slots > ZKL_MAX_MAIN_SLOTS) { out.err = "too many main_args slots"; return 1; }
   const uint64_t fm = pi->segment_feature_mask ? pi->segment_feature_mask : pi->feature_mask;
@@ -253,55 +264,70 @@ static int build_air_host(const zkl_program *prog, const zkl_public_inputs *pi, 
   memcpy(p.rom_w_enc0, prog->rom_w_enc0, sizeof p.rom_w_enc0); memcpy(p.rom_w_enc1, prog->rom_w_enc1, sizeof p.rom_w_enc1);
   p.program_fe0 = prog->program_fe[0]; p.merkle_root_fe = be_from_le8_abi(pi->merkle_root);
 
-  // assertions (vm/air/mod.rs:380-504), de-duplicated by (column, step) keeping the first
+  // assertions (vm/air/mod.rs:380-504), de-duplicated by (column, step) keeping the first. The schedule assertions of a level
+  // (schedule.rs:42-140) are the same for every level: they go into the template once; everything that depends on the public inputs
+  // is an extra. An extra that names a cell the schedule already asserts is dropped (the first one wins), like a repeated extra.
   const uint32_t last = (uint32_t)n - 1, levels = (uint32_t)(n / 32);
   const bool vm = fm & FM_VM, pc0 = abi_is_zero(pi->pc_init);
-  std::vector<zkl_assertion> &as = out.as;
-  as.clear(); as.reserve((size_t)levels * 141 + 24);
-  std::vector<uint64_t> seen((width * n + 63) / 64, 0);
-  auto put = [&](uint32_t col, uint32_t step, const zkl_fe &v) {
-    const size_t k = (size_t)col * n + step;
-    if (seen[k >> 6] >> (k & 63) & 1) return;
-    seen[k >> 6] |= (uint64_t)1 << (k & 63);
-    as.push_back(zkl_assertion{col, step, v});
-  };
+  sched_assertions &sa = out.sched;
+  sa.period = 32; sa.levels = levels; sa.tmpl.clear(); sa.extras.clear();
   const zkl_fe one = abi_u64(1), zero = abi_u64(0);
-  for (uint32_t lvl = 0; lvl < levels; lvl++) {   // schedule.rs:42-140
-    const uint32_t base = lvl * 32, row_map = base, row_final = base + 1 + ZKL_ROUNDS;
-    put(cols.lanes_start + 10, row_map, prog->pose.dom[0]);
-    put(cols.lanes_start + 11, row_map, prog->pose.dom[1]);
-    put(cols.g_map, row_map, one);
-    put(cols.g_final, row_final, one);
-    for (uint32_t j = 0; j < ZKL_ROUNDS; j++) put(cols.g_r_start + j, base + 1 + j, one);
-    put(cols.g_final, row_map, zero);
-    for (uint32_t j = 0; j < ZKL_ROUNDS; j++) put(cols.g_r_start + j, row_map, zero);
-    put(cols.g_map, row_final, zero);
-    for (uint32_t j = 0; j < ZKL_ROUNDS; j++) put(cols.g_r_start + j, row_final, zero);
-    for (uint32_t j = 0; j < ZKL_ROUNDS; j++) { put(cols.g_map, base + 1 + j, zero); put(cols.g_final, base + 1 + j, zero); }
-    if (lvl == 0 && vm) {
-      if (pc0 && has_commit) put(cols.pi_prog, row_map, be_from_le8_abi(prog->program_commitment));
-      put(cols.pc, row_map, pi->pc_init);
-    }
+  auto put_t = [&](uint32_t col, uint32_t pos, const zkl_fe &v) {
+    for (const auto &x : sa.tmpl) if (x.column == col && x.step == pos) return;
+    sa.tmpl.push_back(zkl_assertion{col, pos, v});
+  };
+  {
+    const uint32_t row_map = 0, row_final = 1 + ZKL_ROUNDS;
+    put_t(cols.lanes_start + 10, row_map, prog->pose.dom[0]);
+    put_t(cols.lanes_start + 11, row_map, prog->pose.dom[1]);
+    put_t(cols.g_map, row_map, one);
+    put_t(cols.g_final, row_final, one);
+    for (uint32_t j = 0; j < ZKL_ROUNDS; j++) put_t(cols.g_r_start + j, 1 + j, one);
+    put_t(cols.g_final, row_map, zero);
+    for (uint32_t j = 0; j < ZKL_ROUNDS; j++) put_t(cols.g_r_start + j, row_map, zero);
+    put_t(cols.g_map, row_final, zero);
+    for (uint32_t j = 0; j < ZKL_ROUNDS; j++) put_t(cols.g_r_start + j, row_final, zero);
+    for (uint32_t j = 0; j < ZKL_ROUNDS; j++) { put_t(cols.g_map, 1 + j, zero); put_t(cols.g_final, 1 + j, zero); }
   }
-  if (vm) {
-    if (fm & FM_VM_EXPECT) put(cols.r_start + std::min<uint32_t>(pi->vm_out_reg, ZKL_NR - 1), std::min<uint32_t>(pi->vm_out_row, last), be_from_le8_abi(pi->vm_expected_bytes));
+  auto put_e = [&](uint32_t col, uint32_t step, const zkl_fe &v) {
+    for (const auto &x : sa.tmpl) if (x.column == col && x.step == step % 32) return;
+    for (const auto &x : sa.extras) if (x.column == col && x.step == step) return;
+    sa.extras.push_back(zkl_assertion{col, step, v});
+  };
+  if (vm) {   // level 0 of the schedule loop (schedule.rs), then mod.rs:388-446
+    if (pc0 && has_commit) put_e(cols.pi_prog, 0, be_from_le8_abi(prog->program_commitment));
+    put_e(cols.pc, 0, pi->pc_init);
+    if (fm & FM_VM_EXPECT) put_e(cols.r_start + std::min<uint32_t>(pi->vm_out_reg, ZKL_NR - 1), std::min<uint32_t>(pi->vm_out_row, last), be_from_le8_abi(pi->vm_expected_bytes));
     if (pc0 && pi->num_main_slots) {
       if (pi->num_main_slots > ZKL_NR) { out.err = "main_args must fit into NR registers"; return 1; }
-      for (uint32_t j = 0; j < pi->num_main_slots; j++) put(cols.r_start + ZKL_NR - pi->num_main_slots + j, 0, pi->main_slots[j]);
+      for (uint32_t j = 0; j < pi->num_main_slots; j++) put_e(cols.r_start + ZKL_NR - pi->num_main_slots + j, 0, pi->main_slots[j]);
     }
   }
   if (has_commit) {   // rom.rs:122-147
-    for (uint32_t i = 0; i < 3; i++) put(cols.rom_s_start + i, 0, pi->rom_s_in[i]);
-    for (uint32_t i = 0; i < 3; i++) put(cols.rom_s_start + i, last, pi->rom_s_out[i]);
+    for (uint32_t i = 0; i < 3; i++) put_e(cols.rom_s_start + i, 0, pi->rom_s_in[i]);
+    for (uint32_t i = 0; i < 3; i++) put_e(cols.rom_s_start + i, last, pi->rom_s_out[i]);
   }
-  if (as.empty()) put(cols.mask, last, zero);
+  // the explicit list in get_assertions order: every level's schedule assertions (the level-0 extras right behind level 0's), then the rest
+  std::vector<zkl_assertion> &as = out.as;
+  as.clear();
+  if (expand) {
+    as.reserve(sa.count());
+    size_t lvl0_extras = vm ? (pc0 && has_commit ? 2 : 1) : 0;   // pi_prog / pc sit inside the level loop of the reference
+    lvl0_extras = std::min(lvl0_extras, sa.extras.size());
+    for (uint32_t lvl = 0; lvl < levels; lvl++) {
+      for (const auto &x : sa.tmpl) as.push_back(zkl_assertion{x.column, lvl * 32 + x.step, x.value});
+      if (lvl == 0) for (size_t e = 0; e < lvl0_extras; e++) as.push_back(sa.extras[e]);
+    }
+    for (size_t e = lvl0_extras; e < sa.extras.size(); e++) as.push_back(sa.extras[e]);
+  }
   // the count ZkLispAir::new declares to AirContext (vm/air/mod.rs:240-290); Winterfell panics when get_assertions disagrees
   uint64_t declared = (uint64_t)(2 + ZKL_ROUNDS) * levels + (uint64_t)(4 * ZKL_ROUNDS + 2) * levels + 2 * (uint64_t)levels;
   if (vm) declared += 1 + (pc0 && has_commit ? 1 : 0) + (pc0 ? pi->num_main_slots : 0) + ((fm & FM_VM_EXPECT) ? 1 : 0);
   if (rom_layout) declared += 6;
   declared = std::max<uint64_t>(declared, 1);
-  if (declared != as.size()) { out.err = "declared " + std::to_string(declared) + " assertions but get_assertions yields " + std::to_string(as.size()); return 1; }
-  p.num_assertions = (uint32_t)as.size(); p.assertions = as.data();
+  if (declared != sa.count()) { out.err = "declared " + std::to_string(declared) + " assertions but get_assertions yields " + std::to_string(sa.count()); return 1; }
+  if (sa.count() >> 32) { out.err = "too many assertions"; return 1; }
+  p.num_assertions = (uint32_t)sa.count(); p.assertions = expand ? as.data() : nullptr;
 
   // public-coin seed: Context::to_elements() [WF-mem] ++ AirPublicInputs::to_elements() (lib.rs:116-160)
   std::vector<zkl_fe> &s = out.seed; s.clear();
