@@ -179,9 +179,9 @@ def test_child_replay_helpers(ctx, zkl, oracle):
         psize = W if parts == (1, 16) else max(-(-W // parts[0]), parts[1])
         pos = [1, 2, 77, N - 1]
         rows = np.stack([olde[:, p] for p in pos])
-        leaves = zkl.child.hash_row_poseidon(ctx, rows, psize)
+        leaves = zkl.replay.hash_rows(ctx, rows, psize)
         # full tree from all leaves (oracle) gives the sibling paths
-        all_leaves = zkl.child.hash_row_poseidon(ctx, np.ascontiguousarray(olde.transpose(1, 0, 2)), psize)
+        all_leaves = np.stack([np.frombuffer(d, dtype=np.uint8) for d in zkl.replay.hash_rows(ctx, np.ascontiguousarray(olde.transpose(1, 0, 2)), psize)])
         oroot, nodes = oracle.merkle_build(all_leaves)
         assert oroot == root == lde.get_main_trace_commitment()
         sibs = []
@@ -189,9 +189,8 @@ def test_child_replay_helpers(ctx, zkl, oracle):
             path, i = [all_leaves[p ^ 1]], (p + N) >> 1
             while i > 1:
                 path.append(nodes[i ^ 1]); i >>= 1
-            sibs.append(np.stack(path))
-        roots = zkl.child.merkle_roots_from_leaves(ctx, leaves, pos, sibs)
-        assert all(r.tobytes() == root for r in roots)
+            sibs.append([bytes(x) for x in path])
+        assert all(zkl.replay.merkle_root_from_leaf(ctx, leaves[q], pos[q], sibs[q]) == root for q in range(len(pos)))
         lde.free()
 
 

@@ -277,6 +277,47 @@ def test_segment_features_and_masks(zkl):
     assert SG.compute_segment_feature_mask(core, SG.SegmentFeatures(vm=True, ram=True, sponge=True, merkle=True)) == core
 
 
+def _planner_walk_restated(base_levels, blocks, max_segment_rows):
+    """segment_planner.rs:92-284 restated as the checker of planner.plan_segments: level ranges in level units."""
+    total_levels = max(1 << max(base_levels - 1, 0).bit_length() if base_levels > 1 else 1, 1)
+    if total_levels * 32 <= max_segment_rows:
+        return [(0, total_levels)]
+    max_levels = max(max_segment_rows // 32, 1)
+    ranges, block_ranges = [], sorted((s, s + ln) for s, ln in blocks if ln)
+    if not block_ranges:
+        if base_levels > 0:
+            ranges.append([0, base_levels])
+    else:
+        cursor = 0
+        for bs, be in block_ranges:
+            if cursor < bs:
+                ranges.append([cursor, bs])
+            if ranges and bs <= ranges[-1][1]:
+                ranges[-1][1] = max(ranges[-1][1], be)
+            else:
+                ranges.append([bs, be])
+            cursor = ranges[-1][1]
+        if cursor < base_levels:
+            ranges.append([cursor, base_levels])
+    if base_levels < total_levels:
+        ranges.append([base_levels, total_levels])
+    out, cur_start, cur_end = [], None, 0
+    for lo, hi in ranges:
+        lvl = lo
+        while lvl < hi:
+            if cur_start is None:
+                cur_start = cur_end = lvl
+            take = min(max_levels - (cur_end - cur_start), hi - lvl)
+            cur_end += take
+            lvl += take
+            if cur_end - cur_start == max_levels:
+                out.append((cur_start, cur_end))
+                cur_start, cur_end = None, 0
+    if cur_start is not None and cur_start < cur_end:
+        out.append((cur_start, cur_end))
+    return out
+
+
 def test_planner_properties_random_programs(zkl):
     """Invariants the reference's planner tests assert on one program (segment_planner.rs:370-414), over random block tables:
     contiguous, level aligned, covering the padded trace, never above the row budget, and all full except possibly the last."""
@@ -298,6 +339,7 @@ def test_planner_properties_random_programs(zkl):
         else:
             assert all(s.r_end - s.r_start == max_rows for s in segs[:-1]) and 0 < segs[-1].r_end - segs[-1].r_start <= max_rows
         assert all(s.r_start % 32 == 0 and s.r_end % 32 == 0 for s in segs)
+        assert [(s.r_start // 32, s.r_end // 32) for s in segs] == _planner_walk_restated(base_levels, blocks, max_rows)
 
     check()
 

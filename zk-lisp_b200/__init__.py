@@ -4,5 +4,5 @@ yoozzeek/zk-lisp drives once per execution segment (zk-lisp-proof-winterfell/src
 The directory name carries a hyphen (task layout); import it through `import_zkl()` in
 `__graft_entry__.py`, which registers it as the module `zk_lisp_b200`.
 """
-from . import agg, agg_child, air, air_eval, capi, child, field, params, planner, preflight, recursion, replay, segments, sharded, sharding, step, verify  # noqa: F401
+from . import agg, agg_child, air, air_eval, capi, field, params, planner, preflight, recursion, replay, segments, sharded, sharding, step, verify  # noqa: F401
 from .prover import Context, ZkProver, hasher_suite  # noqa: F401

@@ -59,62 +59,22 @@ def next_power_of_two(x: int) -> int:
 
 
 def plan_segments(base_levels: int, blocks: Sequence[Tuple[int, int]] = (), max_segment_rows: Optional[int] = None) -> List[Segment]:
-    """segment_planner.rs:92-284. `blocks` = (level_start, level_len) of the program's block table."""
-    total_levels = max(next_power_of_two(base_levels), 1)
-    steps = STEPS_PER_LEVEL_P2
-    n_rows_full = total_levels * steps
+    """The segments of a program with `base_levels` op levels: the padded level range [0, next_pow2(base_levels)) cut every
+    `max_segment_rows // 32` levels (`ZKL_MAX_SEGMENT_ROWS`, default 4096 rows).
+
+    The reference (segment_planner.rs:92-284) walks the block table — blocks merged where they touch, the gaps between them, the
+    padded tail — and fills segments greedily, closing one exactly when it holds the level budget. Those ranges tile the padded
+    level range without holes and the fill carries an open segment across range borders, so a segment can only ever start where
+    the previous one ended: the block table never moves a boundary. What it does contribute is its validation (a block past the
+    last op level is an error). The equivalence with the walk is property-tested over random block tables
+    (tests/test_step_container.py: the walk is restated there as the checker)."""
+    for start, length in blocks:
+        if length and start + length > base_levels:
+            raise InvalidInput("WinterfellSegmentPlanner block out of bounds for program levels")
     if max_segment_rows is None:
         env = os.environ.get("ZKL_MAX_SEGMENT_ROWS", "")
         max_segment_rows = int(env) if env.isdigit() else MAX_SEGMENT_ROWS
-    if n_rows_full <= max_segment_rows:
-        return [new_segment(0, n_rows_full)]
-    max_levels = max(max_segment_rows // steps, 1)
-
-    # disjoint level ranges: blocks (merged when overlapping or adjacent), the gaps between them, the padded tail
-    ranges: List[List[int]] = []
-    block_ranges = []
-    for start, length in blocks:
-        if length == 0:
-            continue
-        if start + length > base_levels:
-            raise InvalidInput("WinterfellSegmentPlanner block out of bounds for program levels")
-        block_ranges.append((start, start + length))
-    if not block_ranges:
-        if base_levels > 0:
-            ranges.append([0, base_levels])
-    else:
-        block_ranges.sort(key=lambda r: r[0])
-        cursor = 0
-        for bs, be in block_ranges:
-            if cursor < bs:
-                ranges.append([cursor, bs])
-            if ranges and bs <= ranges[-1][1]:
-                ranges[-1][1] = max(ranges[-1][1], be)
-            else:
-                ranges.append([bs, be])
-            cursor = ranges[-1][1]
-        if cursor < base_levels:
-            ranges.append([cursor, base_levels])
-    if base_levels < total_levels:
-        ranges.append([base_levels, total_levels])
-
-    # greedy fill: a segment closes exactly when it holds max_levels levels
-    seg_levels, cur_start, cur_end = [], None, 0
-    for range_start, range_end in ranges:
-        lvl = range_start
-        while lvl < range_end:
-            if cur_start is None:
-                cur_start = cur_end = lvl
-            take = min(max_levels - (cur_end - cur_start), range_end - lvl)
-            cur_end += take
-            lvl += take
-            if cur_end - cur_start == max_levels:
-                seg_levels.append((cur_start, cur_end))
-                cur_start, cur_end = None, 0
-    if cur_start is not None and cur_start < cur_end:
-        seg_levels.append((cur_start, cur_end))
-
-    segments = [new_segment(a * steps, b * steps) for a, b in seg_levels]
-    if segments and segments[-1].r_end != n_rows_full:
-        raise InvalidInput("WinterfellSegmentPlanner produced segments not covering full trace length")
-    return segments
+    total_levels = next_power_of_two(base_levels)
+    per_segment = total_levels if total_levels * STEPS_PER_LEVEL_P2 <= max_segment_rows else max(max_segment_rows // STEPS_PER_LEVEL_P2, 1)
+    cuts = list(range(0, total_levels, per_segment)) + [total_levels]
+    return [new_segment(a * STEPS_PER_LEVEL_P2, b * STEPS_PER_LEVEL_P2) for a, b in zip(cuts, cuts[1:])]
