@@ -335,6 +335,32 @@ def test_lde_65536_on_tensor_cores(ctx):
     assert np.array_equal(a, b)
 
 
+@pytest.mark.parametrize("logn", [17, 18, 20, 21])
+def test_lde_above_65536_on_tensor_cores(ctx, logn):
+    """n = R_1 ... R_L * 4096 with two and three cross levels (2^17 = 2 x 16, 2^18 = 4 x 16, 2^20 = 16 x 16, 2^21 = 2 x 16 x 16: the X
+    configuration's sizes): every level on the tensor cores, against the radix-2 two-pass kernels (pinned to the oracle at 16 384 rows
+    and up by the tests above). Interpolation (in place), the blowup-16 and blowup-8 coset LDE, and the closed forms of the zero and
+    the constant column."""
+    if ctx.hash_mode != "default":
+        pytest.skip("NTT test, independent of the hashing mode")
+    n = 1 << logn
+    cols = fast_random_trace(3, n, seed=logn)
+    cols[0] = 0
+    cols[1, :, 0] = 1; cols[1, :, 1] = 0
+    ctx._check(ctx.lib.zkl_set_ntt_path(ctx.h, 0)); polys = ctx.interpolate_columns(cols)
+    ctx._check(ctx.lib.zkl_set_ntt_path(ctx.h, 1)); polys_r2 = ctx.interpolate_columns(cols)
+    ctx._check(ctx.lib.zkl_set_ntt_path(ctx.h, 0))
+    assert np.array_equal(polys, polys_r2)
+    assert not polys[0].any() and int(polys[1, 0, 0]) == 1 and not polys[1, 1:].any()
+    for blowup in ((16, 8) if logn <= 18 else (16,)):
+        few = polys[1:] if logn >= 20 else polys
+        ctx._check(ctx.lib.zkl_set_ntt_path(ctx.h, 0)); a = ctx.evaluate_columns(few, blowup)
+        ctx._check(ctx.lib.zkl_set_ntt_path(ctx.h, 1)); b = ctx.evaluate_columns(few, blowup)
+        ctx._check(ctx.lib.zkl_set_ntt_path(ctx.h, 0))
+        assert np.array_equal(a, b), blowup
+        del a, b
+
+
 def test_large_segment_commit_and_proof(ctx, zkl, oracle):
     """A 16384-row segment (4x the reference's segment cap): trace commitment of a narrow trace is
     bit-identical to the oracle's, and the full proof of a wide AIR-valid trace is accepted by the restated verifier."""

@@ -933,15 +933,22 @@ static int prove_segment_impl(zkl_ctx *ctx, const fe *trace_dev, size_t W, size_
   LAUNCH(ctx, k_powers_dev, ceil_div(n, 128), 128, 0, z.p, fe_one(), zpow.p, (int)n);
   LAUNCH(ctx, k_powers_dev, ceil_div(n, 128), 128, 0, z.p, g_n, zpow.p + n, (int)n);
   if (sh) ZKL_CHECK(ctx, cudaMemsetAsync(ood.p, 0, 2 * (W + C) * sizeof(fe), st));
-  LAUNCH(ctx, k_poly_eval, (unsigned)Wl, 256, 0, tl.m.polys.p, (int)n, zpow.p, ood.p + col0);
-  LAUNCH(ctx, k_poly_eval, (unsigned)Wl, 256, 0, tl.m.polys.p, (int)n, zpow.p + n, ood.p + W + C + col0);
+  // T(z), T(z g) of the (owned) trace columns and H(z), H(z g): both points in one pass over the coefficients
+  const size_t ev_chunks = (n + POLY_EVAL_CHUNK - 1) / POLY_EVAL_CHUNK;
+  dev_buf<fe> ev_part;
+  if (ev_chunks > 1) ZKL_CHECK(ctx, ev_part.alloc(2 * ev_chunks * std::max(Wl, C)));
+  auto eval_two_points = [&](const fe *polys, size_t count, fe *at_z, fe *at_zg) -> int {
+    LAUNCH(ctx, k_poly_eval2, dim3((unsigned)ev_chunks, (unsigned)count), 256, 0, polys, (int)n, zpow.p, ev_part.p, at_z, at_zg);
+    if (ev_chunks > 1) LAUNCH(ctx, k_poly_eval2_finish, ceil_div(2 * count, 128), 128, 0, ev_part.p, (int)ev_chunks, (int)count, at_z, at_zg);
+    return 0;
+  };
+  ZKL_TRY(eval_two_points(tl.m.polys.p, Wl, ood.p + col0, ood.p + W + C + col0));
   if (sh) {   // exchange (3a): every rank evaluated its own columns; the supports are disjoint, so a u64 sum assembles the frame exactly
     ZKL_TRY(wait_stream());
     ZKL_TRY(comm_call(ctx, sh->comm->all_reduce_sum_u64(sh->comm->user, ood.p, 2 * W), "all_reduce(OOD trace, z)"));
     ZKL_TRY(comm_call(ctx, sh->comm->all_reduce_sum_u64(sh->comm->user, ood.p + W + C, 2 * W), "all_reduce(OOD trace, zg)"));
   }
-  LAUNCH(ctx, k_poly_eval, (unsigned)C, 256, 0, cmt.m.polys.p, (int)n, zpow.p, ood.p + W);
-  LAUNCH(ctx, k_poly_eval, (unsigned)C, 256, 0, cmt.m.polys.p, (int)n, zpow.p + n, ood.p + 2 * W + C);
+  ZKL_TRY(eval_two_points(cmt.m.polys.p, C, ood.p + W, ood.p + 2 * W + C));
   // what is hashed and sent: the frame as E elements, [T(z) | H(z) | T(zg) | H(zg)] with every trace value widened to (a, 0)
   dev_buf<fe> ood_wide;
   const fe *ood_w = ood.p;

@@ -99,27 +99,47 @@ __global__ void k_powers_dev(const fe *__restrict__ base, fe mulc, fe *__restric
   if (j >= n) return;
   st_fe(out + j, fe_pow(fe_mul(ld_fe(base), mulc), (uint64_t)j));
 }
-// out[p] = sum_j polys[p][j] * xpow[j] ; one block per polynomial
-__global__ void __launch_bounds__(256) k_poly_eval(const fe *__restrict__ polys, int n, const fe *__restrict__ xpow, fe *__restrict__ out) {
-  __shared__ fe s_part[256];
-  const fe *poly = polys + (size_t)blockIdx.x * n;
-  fe acc = fe_zero();
-  for (int j0 = threadIdx.x; j0 < n; j0 += blockDim.x * 8) {
-    wide_acc w; wacc_zero(w);
+// Two out-of-domain points at once: part[(p * chunks + ch) * 2 + q] = sum over chunk ch of polys[p][j] * xpow[q * n + j], q = 0 (z), 1 (z g).
+// grid = (chunks, polynomials): every coefficient is read ONCE for both points, and a long column is spread over many SMs (a
+// 2^20-row column on one CTA is 16 MB through one SM). chunks == 1 writes the results straight to out0[p] / out1[p].
+#define POLY_EVAL_CHUNK 16384
+__global__ void __launch_bounds__(256) k_poly_eval2(const fe *__restrict__ polys, int n, const fe *__restrict__ xpow, fe *__restrict__ part,
+                                                    fe *__restrict__ out0, fe *__restrict__ out1) {
+  __shared__ fe s_part[2][256];
+  const int chunks = gridDim.x, ch = blockIdx.x;
+  const fe *poly = polys + (size_t)blockIdx.y * n;
+  const int j_lo = ch * POLY_EVAL_CHUNK, j_hi = min(n, j_lo + POLY_EVAL_CHUNK);
+  fe acc0 = fe_zero(), acc1 = fe_zero();
+  for (int j0 = j_lo + threadIdx.x; j0 < j_hi; j0 += blockDim.x * 8) {
+    wide_acc w0, w1; wacc_zero(w0); wacc_zero(w1);
 #pragma unroll
     for (int u = 0; u < 8; u++) {
       int j = j0 + u * blockDim.x;
-      if (j < n) wacc_mad(w, ld_fe(poly + j), ld_fe(xpow + j));
+      if (j < j_hi) { fe c = ld_fe(poly + j); wacc_mad(w0, c, ld_fe(xpow + j)); wacc_mad(w1, c, ld_fe(xpow + n + j)); }
     }
-    acc = fe_add(acc, wacc_reduce(w));
+    acc0 = fe_add(acc0, wacc_reduce(w0)); acc1 = fe_add(acc1, wacc_reduce(w1));
   }
-  s_part[threadIdx.x] = acc;
+  s_part[0][threadIdx.x] = acc0; s_part[1][threadIdx.x] = acc1;
   __syncthreads();
   for (int s = blockDim.x / 2; s > 0; s >>= 1) {
-    if (threadIdx.x < s) s_part[threadIdx.x] = fe_add(s_part[threadIdx.x], s_part[threadIdx.x + s]);
+    if (threadIdx.x < s) {
+      s_part[0][threadIdx.x] = fe_add(s_part[0][threadIdx.x], s_part[0][threadIdx.x + s]);
+      s_part[1][threadIdx.x] = fe_add(s_part[1][threadIdx.x], s_part[1][threadIdx.x + s]);
+    }
     __syncthreads();
   }
-  if (threadIdx.x == 0) st_fe(out + blockIdx.x, s_part[0]);
+  if (threadIdx.x == 0) {
+    if (chunks == 1) { st_fe(out0 + blockIdx.y, s_part[0][0]); st_fe(out1 + blockIdx.y, s_part[1][0]); }
+    else { st_fe(part + ((size_t)blockIdx.y * chunks + ch) * 2, s_part[0][0]); st_fe(part + ((size_t)blockIdx.y * chunks + ch) * 2 + 1, s_part[1][0]); }
+  }
+}
+__global__ void k_poly_eval2_finish(const fe *__restrict__ part, int chunks, int npolys, fe *__restrict__ out0, fe *__restrict__ out1) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 2 * npolys) return;
+  const int p = t >> 1, q = t & 1;
+  fe a = fe_zero();
+  for (int ch = 0; ch < chunks; ch++) a = fe_add(a, ld_fe(part + ((size_t)p * chunks + ch) * 2 + q));
+  st_fe((q ? out1 : out0) + p, a);
 }
 
 // ---------------------------------------------------------------- DEEP composition (agg/trace.rs:1158-1193)

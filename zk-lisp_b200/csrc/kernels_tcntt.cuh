@@ -214,7 +214,8 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 
 // grid >= blowup CTAs; CTA b serves coset b % blowup and every (gridDim.x / blowup)-th column of it.
 __global__ void __launch_bounds__(NTT16_THREADS, 1) k_tc_lde4096_v2(const fe *polys, int ncols, int blowup, const uint4 *__restrict__ bmat,
-                                                                   const fe *__restrict__ tw0, const fe *__restrict__ wpow, fe *out, bool inverse, int cross, size_t Ntab /* entries of wpow: w_Ntab^e */) {
+                                                                   const fe *__restrict__ tw0, const fe *__restrict__ wpow, fe *out, bool inverse, int cross, size_t Ntab /* entries of wpow: w_Ntab^e */,
+                                                                   uint32_t radices /* 4 bits per cross level: log2 R_1 (lowest nibble) .. log2 R_L; 0 = the one level `cross` */) {
   extern __shared__ unsigned char ntt_smem[];
   const uint32_t base = (smem_u32(ntt_smem) + 127u) & ~127u;
   unsigned char *gen = ntt_smem + (base - smem_u32(ntt_smem));
@@ -252,7 +253,27 @@ __global__ void __launch_bounds__(NTT16_THREADS, 1) k_tc_lde4096_v2(const fe *po
   uint32_t src = buf0, dst = buf1;
   // column c as 16 chunks of 256 coefficients: chunk jD -> src + jD * PITCH (instance m1 = j & 255 at 16 B pitch)
   // cross mode (columns of R * 4096 rows, second pass; cross = R): problem q = R c + i2 reads block i2 of slab (c, k) of the first
-  // pass's output and writes y[i2 + R i1] of the slab's transform
+  // pass's output and writes y[i2 + R i1] of the slab's transform.
+  // Several cross levels (n = R_1 ... R_L 4096, `radices`): q = ((c R_1 + i2_1) R_2 + i2_2 ...) R_L + i2_L, `cross` = R_L; the block's
+  // outputs i1 go to y[i2_1 + R_1 (i2_2 + R_2 (... + R_L i1))] of column c.
+  if (!radices) radices = cross ? (uint32_t)(31 - __clz(cross)) : 0;
+  int prod_log = 0;
+  for (uint32_t r = radices; r; r >>= 4) prod_log += (int)(r & 15);
+  auto out_base = [&](int q, size_t *stride) -> fe * {
+    const size_t P = (size_t)1 << prod_log;
+    size_t rem = (size_t)q & (P - 1), off = 0;
+    int shift = prod_log;
+    // digits from the last level (least significant in q) to the first
+    int nl = 0; for (uint32_t r = radices; r; r >>= 4) nl++;
+    for (int l = nl - 1; l >= 0; l--) {
+      const int lg = (int)((radices >> (4 * l)) & 15);
+      shift -= lg;                                        // log2 (R_1 ... R_{l})
+      off += (rem & (((size_t)1 << lg) - 1)) << shift;
+      rem >>= lg;
+    }
+    *stride = P;
+    return out + (((size_t)q >> prod_log) * blowup + k) * (P * NTT16_N) + off;
+  };
   auto in_block = [&](int q) -> const fe * {
     return cross ? polys + ((size_t)((q / cross) * blowup + k) * cross + (q % cross)) * NTT16_N : polys + (size_t)q * NTT16_N;
   };
@@ -306,7 +327,7 @@ __global__ void __launch_bounds__(NTT16_THREADS, 1) k_tc_lde4096_v2(const fe *po
             { size_t e = (size_t)(iB * jA) * s4096; if (inverse && e) e = N - e; v = lazy_mul(v, ld_fe(wpow + e)); }
             sts_u4(dst + (uint32_t)jA * NTT16_PITCH + (uint32_t)iB * 16, v.l[0], v.l[1], v.l[2], v.l[3]);
           } else {                   // m = iB, i = iA
-            if (cross) st_fe(out + ((size_t)(c / cross) * blowup + k) * ((size_t)cross * NTT16_N) + (c % cross) + (size_t)cross * (256 * i + m), lazy_canon(v));
+            if (cross) { size_t stride; fe *ob = out_base(c, &stride); st_fe(ob + stride * (size_t)(256 * i + m), lazy_canon(v)); }
             else st_fe(out + ((size_t)c * blowup + k) * NTT16_N + 256 * i + m, lazy_canon(v));
           }
         }
@@ -332,7 +353,7 @@ __global__ void __launch_bounds__(NTT16_THREADS, 1) k_tc_lde4096_v2(const fe *po
 // pass 2 (k_tc_lde4096_v2, cross = 1): the coset LDE of every block — its B_k / tw0_k carry exactly the s^j1 factor —
 //   scattered to y[i2 + 16 i1].
 // Inverse (interpolation): s = 1, inverse roots, 1/n folded into C.
-__global__ void k_build_cross16_consts(const fe *__restrict__ scale /* [blowup][R m] or null */, const fe *__restrict__ wpow, size_t N, size_t m, int R,
+__global__ void k_build_cross16_consts(const fe *__restrict__ scale /* [blowup][kstride] or null */, size_t kstride, const fe *__restrict__ wpow, size_t N, size_t m, int R,
                                        int blowup, bool inverse, fe factor, uint4 *__restrict__ cmat) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= blowup * 4096) return;
@@ -342,7 +363,7 @@ __global__ void k_build_cross16_consts(const fe *__restrict__ scale /* [blowup][
   if (i < R && j < R) {   // a radix-R stage (R | 16) is the radix-16 tile with zero rows / columns: unused inputs may hold anything
     size_t ex = (size_t)((i * j) % R) * (N / R); if (inverse && ex) ex = N - ex;
     fe cur = ld_fe(wpow + ex);
-    if (scale) cur = fe_mul(cur, ld_fe(scale + (size_t)k * R * m + m * j));
+    if (scale) cur = fe_mul(cur, ld_fe(scale + (size_t)k * kstride + m * j));
     if (inverse) cur = fe_mul(cur, factor);
     const fe two8 = fe_from_u64(256);
     for (int b = 0; b < 16; b++) {
@@ -357,7 +378,9 @@ __global__ void k_build_cross16_consts(const fe *__restrict__ scale /* [blowup][
 // src: ncols columns of n = R m elements (column stride n), R in {2, 4, 8, 16}. dst: slabs (c, k) of n elements, block i2 at offset i2 * m.
 // wpow: w_Ntab^e; wstep = Ntab / n (w_n = w_Ntab^wstep). grid >= blowup CTAs, CTA b serves coset b % blowup.
 __global__ void __launch_bounds__(NTT16_THREADS, 1) k_tc_cross16(const fe *__restrict__ src, int ncols, int blowup, size_t m, int R, const uint4 *__restrict__ cmat,
-                                                                const fe *__restrict__ wpow, size_t Ntab, size_t wstep, fe *__restrict__ dst, bool inverse) {
+                                                                const fe *__restrict__ wpow, size_t Ntab, size_t wstep, fe *__restrict__ dst, bool inverse,
+                                                                bool src_per_coset /* src = [column][coset][n] (the output of a level above) */,
+                                                                bool dst_blocks_outer /* dst = [column R + i2][coset][m]: the columns of the level below */) {
   extern __shared__ unsigned char ntt_smem[];
   const uint32_t base = (smem_u32(ntt_smem) + 127u) & ~127u;
   unsigned char *gen = ntt_smem + (base - smem_u32(ntt_smem));
@@ -394,7 +417,7 @@ __global__ void __launch_bounds__(NTT16_THREADS, 1) k_tc_cross16(const fe *__res
   auto fetch = [&](int p, int which) {   // slice p -> buffer `which`: chunk j2 = 256 coefficients of block j2
     const uint32_t to = which ? buf1 : buf0, bar = ctl + 16 + 8 * which;
     mbar_expect_tx(bar, (uint32_t)R * 4096);
-    const fe *col = src + (size_t)(p / slices) * n + (size_t)(p % slices) * 256;
+    const fe *col = src + (src_per_coset ? ((size_t)(p / slices) * blowup + k) : (size_t)(p / slices)) * n + (size_t)(p % slices) * 256;
 #pragma unroll 1
     for (int j2 = 0; j2 < R; j2++) bulk_g2s(to + (uint32_t)j2 * NTT16_PITCH, col + m * j2, 4096, bar);
   };
@@ -439,7 +462,9 @@ __global__ void __launch_bounds__(NTT16_THREADS, 1) k_tc_cross16(const fe *__res
         size_t e = (j1 * (size_t)i2 * wstep) & (Ntab - 1);
         if (inverse && e) e = Ntab - e;
         if (i2) v = lazy_mul(v, ld_fe(wpow + e));
-        st_fe(slab + (size_t)i2 * m + j1, v);   // any 128-bit representative: pass 2 feeds the bytes to the tensor cores
+        // any 128-bit representative: the next pass feeds the bytes to the tensor cores
+        if (dst_blocks_outer) st_fe(dst + (((size_t)c * R + i2) * blowup + k) * m + j1, v);
+        else st_fe(slab + (size_t)i2 * m + j1, v);
       }
     }
   }

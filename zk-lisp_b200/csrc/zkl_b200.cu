@@ -309,13 +309,15 @@ static int get_lde16_consts(zkl_ctx *ctx, size_t blowup, bool inverse, const fe 
   return 0;
 }
 // per-coset matrices of the cross stage of a 65536-point transform (k_tc_cross16)
-static int get_cross16_consts(zkl_ctx *ctx, size_t blowup, bool inverse, const fe *scale, size_t m, int R, const domain_tables *t, fe factor, const uint4 **cmat) {
-  const size_t key = (t->N << 10) | (blowup << 3) | (3u << 1) | (inverse ? 1 : 0);
+static int get_cross16_consts(zkl_ctx *ctx, size_t blowup, bool inverse, const fe *scale, size_t kstride, size_t m, int R, const domain_tables *t, fe factor,
+                              bool top, const uint4 **cmat) {
+  // one entry per (domain, blowup, direction, block size m, radix, top level or not: the top level of an inverse transform carries 1/n)
+  const size_t key = ((size_t)1 << 63) | (t->N << 24) | ((size_t)ilog2_sz(m) << 16) | ((size_t)R << 10) | (blowup << 2) | (top ? 2 : 0) | (inverse ? 1 : 0);
   auto it = ctx->lde16.find(key);
   if (it == ctx->lde16.end()) {
     void *b;
     ZKL_CHECK(ctx, cudaMalloc(&b, blowup * 4096 * sizeof(uint4)));
-    LAUNCH(ctx, k_build_cross16_consts, ceil_div(blowup * 4096, 256), 256, 0, scale, t->wpow, t->N, m, R, (int)blowup, inverse, factor, (uint4 *)b);
+    LAUNCH(ctx, k_build_cross16_consts, ceil_div(blowup * 4096, 256), 256, 0, scale, kstride, t->wpow, t->N, m, R, (int)blowup, inverse, factor, (uint4 *)b);
     it = ctx->lde16.emplace(key, std::make_pair(b, (void *)nullptr)).first;
   }
   *cmat = (const uint4 *)it->second.first;
@@ -325,10 +327,56 @@ static unsigned lde16_grid(const zkl_ctx *ctx, size_t ncols, size_t blowup) {
   return (unsigned)std::min<size_t>(ncols * blowup, std::max<size_t>((size_t)ctx->num_sms, blowup));
 }
 
-// n = R * 4096 with R in {4, 8, 16}: the two-pass tensor-core transform applies (returns R, else 0); 8192 rows still fit one
-// CTA's shared memory and stay on the single-pass kernel
-static int cross_radix(size_t n) {
-  for (int R = 4; R <= NTT16_CROSS_MAX_R; R <<= 1) if (n == (size_t)R * NTT16_N) return R;
+// n = R_1 ... R_L * 4096 with R_i in {2, 4, 8, 16}: L cross stages (k_tc_cross16) and the 4096-point transforms, all on the tensor
+// cores and L + 1 passes over HBM. 16 384 rows and up (8192 still fit one CTA's shared memory and stay on the single-pass kernel).
+// The odd bits go to the TOP radix, the levels below are radix 16.
+struct tc_plan { int L = 0; int R[4] = {0, 0, 0, 0}; uint32_t radices = 0; };
+static bool tc_plan_for(size_t n, tc_plan &p) {
+  if (n < 4 * (size_t)NTT16_N || (n & (n - 1))) return false;
+  int e = ilog2_sz(n / NTT16_N);
+  p = tc_plan();
+  if (e % 4) { p.R[p.L++] = 1 << (e % 4); e -= e % 4; }
+  for (; e > 0; e -= 4) { if (p.L == 4) return false; p.R[p.L++] = 16; }
+  for (int l = 0; l < p.L; l++) p.radices |= (uint32_t)ilog2_sz((size_t)p.R[l]) << (4 * l);
+  return true;
+}
+static int cross_radix(size_t n) { tc_plan p; return tc_plan_for(n, p) ? p.R[0] : 0; }   // non-zero: the tensor-core multi-pass transform applies
+
+// src: ncols columns of n elements; out: [column][coset][n] (blowup = 1 for the inverse transform). `scale` = [blowup][n] coset-shift
+// powers or null; `factor` = 1/n for the inverse transform (folded into the top level's matrices).
+// A coset range k0 .. k0 + nk - 1 (nk = 0: all) comes out compact, [column][nk][n]: the kernels index their per-coset constants by the
+// coset they serve, so a range is the same launch with the constants offset to k0 and nk in place of the blowup.
+static int dev_tc_multilevel(zkl_ctx *ctx, const fe *src, fe *out, size_t ncols, size_t n, size_t blowup, bool inverse, const fe *scale, const domain_tables *t,
+                             fe factor, size_t k0 = 0, size_t nk = 0) {
+  if (!nk) nk = blowup;
+  tc_plan pl; if (!tc_plan_for(n, pl)) { ctx->set_error("no tensor-core plan for this transform size"); return 1; }
+  const uint4 *cmat[4], *bmat; const fe *tw0;
+  size_t m = n;
+  for (int l = 0; l < pl.L; l++) {
+    m /= (size_t)pl.R[l];
+    ZKL_TRY(get_cross16_consts(ctx, blowup, inverse, scale, n, m, pl.R[l], t, l == 0 ? factor : fe_one(), l == 0, &cmat[l]));
+  }
+  ZKL_TRY(get_lde16_consts(ctx, blowup, inverse, scale, n, t, inverse ? fe_one() : fe_zero(), inverse ? 1 : 0, &bmat, &tw0));
+  for (int l = 0; l < pl.L; l++) cmat[l] += k0 * 4096;
+  bmat += k0 * 4096; tw0 += k0 * 4096;
+  blowup = nk;   // from here on: the cosets of the call
+  const size_t chunk = std::min(ncols, std::max<size_t>(1, ((size_t)1 << 31) / (blowup * n * sizeof(fe))));   // columns per round: <= 2 GB per scratch buffer
+  dev_buf<fe> sa, sb; ZKL_CHECK(ctx, sa.alloc(chunk * blowup * n));
+  if (pl.L > 1) ZKL_CHECK(ctx, sb.alloc(chunk * blowup * n));
+  for (size_t c0 = 0; c0 < ncols; c0 += chunk) {
+    const size_t nc = std::min(chunk, ncols - c0);
+    const fe *in = src + c0 * n; fe *to = sa.p;
+    size_t cols = nc, len = n;   // level l: `cols` columns of `len` elements
+    for (int l = 0; l < pl.L; l++) {
+      const size_t sub = len / (size_t)pl.R[l];
+      LAUNCH(ctx, k_tc_cross16, lde16_grid(ctx, cols * 16, blowup), NTT16_THREADS, NTT16_SMEM_BYTES, in, (int)cols, (int)blowup, sub, pl.R[l], cmat[l], t->wpow, t->N,
+             t->N / len, to, inverse, l > 0, l + 1 < pl.L);
+      in = to; to = (to == sa.p) ? sb.p : sa.p;
+      if (l + 1 < pl.L) { cols *= (size_t)pl.R[l]; len = sub; }
+    }
+    LAUNCH(ctx, k_tc_lde4096_v2, lde16_grid(ctx, cols * (size_t)pl.R[pl.L - 1], blowup), NTT16_THREADS, NTT16_SMEM_BYTES, in, (int)(cols * (size_t)pl.R[pl.L - 1]), (int)blowup, bmat,
+           tw0, t->wpow, out + c0 * blowup * n, inverse, pl.R[pl.L - 1], t->N, pl.radices);
+  }
   return 0;
 }
 
@@ -340,18 +388,11 @@ static int dev_interpolate(zkl_ctx *ctx, const fe *src, fe *dst, size_t ncols, s
   if (n == NTT16_N && ctx->ntt_path == 0) {   // inverse radix-16 stages on the tensor cores, 1/n folded into the matrix (kernels_tcntt.cuh v2)
     const uint4 *bmat; const fe *tw0;
     ZKL_TRY(get_lde16_consts(ctx, 1, true, nullptr, 0, t, n_inv, 0, &bmat, &tw0));
-    LAUNCH(ctx, k_tc_lde4096_v2, lde16_grid(ctx, ncols, 1), NTT16_THREADS, NTT16_SMEM_BYTES, src, (int)ncols, 1, bmat, tw0, t->wpow, dst, true, 0, t->N);
+    LAUNCH(ctx, k_tc_lde4096_v2, lde16_grid(ctx, ncols, 1), NTT16_THREADS, NTT16_SMEM_BYTES, src, (int)ncols, 1, bmat, tw0, t->wpow, dst, true, 0, t->N, 0u);
     return 0;
   }
-  if (const int R = ctx->ntt_path == 0 ? cross_radix(n) : 0) {   // 8192..65536 rows: cross stage + 4096-point transforms, both on the tensor cores
-    const uint4 *cmat, *bmat; const fe *tw0;
-    ZKL_TRY(get_cross16_consts(ctx, 1, true, nullptr, NTT16_N, R, t, n_inv, &cmat));
-    ZKL_TRY(get_lde16_consts(ctx, 1, true, nullptr, 0, t, fe_one(), 1, &bmat, &tw0));
-    dev_buf<fe> scratch; ZKL_CHECK(ctx, scratch.alloc(ncols * n));
-    LAUNCH(ctx, k_tc_cross16, lde16_grid(ctx, ncols * 16, 1), NTT16_THREADS, NTT16_SMEM_BYTES, src, (int)ncols, 1, (size_t)NTT16_N, R, cmat, t->wpow, t->N, (size_t)1, scratch.p, true);
-    LAUNCH(ctx, k_tc_lde4096_v2, lde16_grid(ctx, ncols * R, 1), NTT16_THREADS, NTT16_SMEM_BYTES, scratch.p, (int)(ncols * R), 1, bmat, tw0, t->wpow, dst, true, R, t->N);
-    return 0;
-  }
+  if (ctx->ntt_path == 0 && cross_radix(n))   // 16 384 rows and up: cross stages + 4096-point transforms, all on the tensor cores
+    return dev_tc_multilevel(ctx, src, dst, ncols, n, 1, true, nullptr, t, n_inv);
   if (n == NTT16_N && ctx->ntt_path == 2) {   // v1: separate 1/n product
     LAUNCH(ctx, k_tc_lde4096, (unsigned)std::min<size_t>(ncols, (size_t)ctx->num_sms), NTT16_THREADS, NTT16_SMEM_BYTES, src, (int)ncols, 1, (const fe *)nullptr,
            t->wpow, dst, true, n_inv);
@@ -386,7 +427,7 @@ static int dev_lde(zkl_ctx *ctx, const fe *polys, fe *out, size_t ncols, size_t 
     LAUNCH(ctx, k_lde_scale_table, ceil_div(N, 256), 256, 0, opow, t->wpow, N, (int)n, (int)blowup, p);
     it = ctx->opow.emplace(key, p).first;
   }
-  if (nk != blowup) {   // a coset range (dev_lde_cosets): the two-pass path only, compact output
+  if (nk != blowup && !(ctx->ntt_path == 0 && cross_radix(n))) {   // a coset range (dev_lde_cosets) on the radix-2 two-pass path, compact output
     ntt_split sp = split_for(n);
     size_t smem = (size_t)sp.T * std::max(sp.n1, sp.n2) * sizeof(fe);
     LAUNCH(ctx, k_ntt_pass1, dim3(sp.n1 / sp.T, (unsigned)ncols, (unsigned)nk), NTT_THREADS, smem, polys, out, sp.n1, sp.n2, ilog2_sz(sp.n2), sp.T, t->wpow, N,
@@ -397,24 +438,11 @@ static int dev_lde(zkl_ctx *ctx, const fe *polys, fe *out, size_t ncols, size_t 
   if (n == NTT16_N && ctx->ntt_path == 0) {   // radix-16 stages on the tensor cores, coset shift folded into the matrix (kernels_tcntt.cuh v2)
     const uint4 *bmat; const fe *tw0;
     ZKL_TRY(get_lde16_consts(ctx, blowup, false, it->second, n, t, fe_zero(), 0, &bmat, &tw0));
-    LAUNCH(ctx, k_tc_lde4096_v2, lde16_grid(ctx, ncols, blowup), NTT16_THREADS, NTT16_SMEM_BYTES, polys, (int)ncols, (int)blowup, bmat, tw0, t->wpow, out, false, 0, t->N);
+    LAUNCH(ctx, k_tc_lde4096_v2, lde16_grid(ctx, ncols, blowup), NTT16_THREADS, NTT16_SMEM_BYTES, polys, (int)ncols, (int)blowup, bmat, tw0, t->wpow, out, false, 0, t->N, 0u);
     return 0;
   }
-  if (const int R = ctx->ntt_path == 0 ? cross_radix(n) : 0) {   // 8192..65536 rows: cross stage + coset LDE of the R blocks, both on the tensor cores
-    const uint4 *cmat, *bmat; const fe *tw0;
-    ZKL_TRY(get_cross16_consts(ctx, blowup, false, it->second, NTT16_N, R, t, fe_zero(), &cmat));
-    ZKL_TRY(get_lde16_consts(ctx, blowup, false, it->second, n, t, fe_zero(), 0, &bmat, &tw0));
-    const size_t chunk = std::max<size_t>(1, ((size_t)1 << 30) / (blowup * n * sizeof(fe)));   // columns per pass: <= 1 GB of scratch
-    dev_buf<fe> scratch; ZKL_CHECK(ctx, scratch.alloc(std::min(chunk, ncols) * blowup * n));
-    for (size_t c0 = 0; c0 < ncols; c0 += chunk) {
-      const size_t nc = std::min(chunk, ncols - c0);
-      LAUNCH(ctx, k_tc_cross16, lde16_grid(ctx, nc * 16, blowup), NTT16_THREADS, NTT16_SMEM_BYTES, polys + c0 * n, (int)nc, (int)blowup, (size_t)NTT16_N, R, cmat, t->wpow, t->N,
-             blowup, scratch.p, false);
-      LAUNCH(ctx, k_tc_lde4096_v2, lde16_grid(ctx, nc * R, blowup), NTT16_THREADS, NTT16_SMEM_BYTES, scratch.p, (int)(nc * R), (int)blowup, bmat, tw0, t->wpow,
-             out + c0 * blowup * n, false, R, t->N);
-    }
-    return 0;
-  }
+  if (ctx->ntt_path == 0 && cross_radix(n))   // 16 384 rows and up: cross stages + coset LDE of the 4096-row blocks, all on the tensor cores
+    return dev_tc_multilevel(ctx, polys, out, ncols, n, blowup, false, it->second, t, fe_zero(), k0, nk);
   if (n == NTT16_N && ctx->ntt_path == 2) {   // v1: separate coset-shift product
     LAUNCH(ctx, k_tc_lde4096, (unsigned)std::min<size_t>(ncols * blowup, (size_t)ctx->num_sms), NTT16_THREADS, NTT16_SMEM_BYTES, polys, (int)ncols, (int)blowup,
            it->second, t->wpow, out, false, fe_zero());
@@ -437,8 +465,8 @@ static int dev_lde(zkl_ctx *ctx, const fe *polys, fe *out, size_t ncols, size_t 
 static int dev_lde_cosets(zkl_ctx *ctx, const fe *polys, fe *out, size_t ncols, size_t n, size_t blowup, size_t k0, size_t nk) {
   if (k0 + nk > blowup || !nk) { ctx->set_error("coset range outside the LDE domain"); return 1; }
   if (nk == blowup) return dev_lde(ctx, polys, out, ncols, n, blowup);
-  const bool two_pass = n > NTT_SINGLE_PASS_MAX && !(ctx->ntt_path == 0 && cross_radix(n));
-  if (two_pass) return dev_lde(ctx, polys, out, ncols, n, blowup, k0, nk);
+  const bool native = n > NTT_SINGLE_PASS_MAX;   // tensor-core multi-pass or radix-2 two-pass transforms: both take a coset range
+  if (native) return dev_lde(ctx, polys, out, ncols, n, blowup, k0, nk);
   dev_buf<fe> full; ZKL_CHECK(ctx, full.alloc(ncols * n * blowup));
   ZKL_TRY(dev_lde(ctx, polys, full.p, ncols, n, blowup));
   ZKL_CHECK(ctx, cudaMemcpy2DAsync(out, nk * n * sizeof(fe), full.p + k0 * n, blowup * n * sizeof(fe), nk * n * sizeof(fe), ncols, cudaMemcpyDeviceToDevice, ctx->stream));
