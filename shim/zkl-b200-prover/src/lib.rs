@@ -435,3 +435,41 @@ pub fn prove_agg_full(ctx: &GpuCtx, trace: &ColMatrix<BE>, agg_pi: &zk_lisp_proo
     }
     Proof::from_bytes(&buf[..len]).map_err(|e| e.to_string())
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// one large segment over the GPUs of a box (include/zkl_b200.h: zkl_comm)
+// ------------------------------------------------------------------------------------------------------------------
+/// This rank's share of the column-sharded proof of ONE segment: `trace` is the whole `ColMatrix` on the host (every rank of a
+/// single-process prover sees it; a multi-process prover passes a matrix that holds valid data in its own columns only), the rank
+/// uploads the columns `zkl_shard_columns` assigns it and proves with the caller's collectives. Every rank returns the same
+/// `Proof`, byte-identical to `prove_segment_full` on one GPU. `partitions` must give at least `comm.world` partitions.
+pub fn prove_segment_sharded(ctx: &GpuCtx, comm: &sys::ZklComm, trace: &ColMatrix<BE>, program: &sys::ZklProgram, pi: &sys::ZklPublicInputs,
+                             options: &ProofOptions, partitions: (usize, usize)) -> Result<Proof, String> {
+    let (w, n) = (trace.num_cols(), trace.num_rows());
+    let mut opts = zkl_options(options, PartitionOptions::new(partitions.0, partitions.1));
+    opts.num_partitions = partitions.0 as u32;
+    opts.hash_rate = partitions.1 as u32;
+    let (mut first, mut count) = (0usize, 0usize);
+    if unsafe { sys::zkl_shard_columns(&opts, w, comm.rank, comm.world, &mut first, &mut count) } != 0 {
+        return Err("column sharding needs PartitionOptions with at least one whole partition per rank".into());
+    }
+    let mut local: Vec<BE> = Vec::with_capacity(count * n);
+    for c in first..first + count {
+        local.extend_from_slice(trace.get_column(c));
+    }
+    let bytes = local.len() * std::mem::size_of::<BE>();
+    let mut dev: *mut std::ffi::c_void = std::ptr::null_mut();
+    if unsafe { sys::zkl_dev_alloc(ctx.raw(), bytes, &mut dev) } != 0 || unsafe { sys::zkl_dev_upload(ctx.raw(), dev, local.as_ptr().cast(), bytes) } != 0 {
+        return Err(last_error(ctx.raw()));
+    }
+    let mut buf = vec![0u8; 4 << 20];
+    let mut len = buf.len();
+    let rc = unsafe {
+        sys::zkl_prove_segment_sharded_pi_dev(ctx.raw(), dev, first, count, w, n, program, pi, &opts, comm, buf.as_mut_ptr(), &mut len, std::ptr::null_mut())
+    };
+    unsafe { sys::zkl_dev_free(ctx.raw(), dev) };
+    if rc != 0 {
+        return Err(last_error(ctx.raw()));
+    }
+    Proof::from_bytes(&buf[..len]).map_err(|e| e.to_string())
+}

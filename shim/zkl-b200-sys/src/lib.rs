@@ -236,4 +236,41 @@ extern "C" {
     pub fn zkl_sync(ctx: *mut zkl_ctx) -> c_int;
     pub fn zkl_dev_alloc(ctx: *mut zkl_ctx, bytes: usize, out_dev: *mut *mut c_void) -> c_int;
     pub fn zkl_dev_free(ctx: *mut zkl_ctx, dev: *mut c_void) -> c_int;
+    pub fn zkl_dev_upload(ctx: *mut zkl_ctx, dev: *mut c_void, host: *const c_void, bytes: usize) -> c_int;
+
+    // ---- one large segment column-sharded over the GPUs of a box (include/zkl_b200.h: zkl_comm) ----
+    pub fn zkl_shard_columns(opts: *const ZklOptions, width: usize, rank: c_int, world: c_int, first_col: *mut usize, local_width: *mut usize) -> c_int;
+    pub fn zkl_prove_segment_sharded_pi_dev(
+        ctx: *mut zkl_ctx, local_trace_dev: *const c_void, first_col: usize, local_width: usize, width: usize, n: usize, program: *const ZklProgram,
+        pi: *const ZklPublicInputs, opts: *const ZklOptions, comm: *const ZklComm, out_proof: *mut u8, out_len: *mut usize, summary: *mut ZklProofSummary,
+    ) -> c_int;
+    pub fn zkl_prove_segment_sharded_dev(
+        ctx: *mut zkl_ctx, local_trace_dev: *const c_void, first_col: usize, local_width: usize, width: usize, n: usize, air: *const ZklAirParams,
+        seed_elems: *const ZklFe, num_seed: usize, opts: *const ZklOptions, comm: *const ZklComm, out_proof: *mut u8, out_len: *mut usize,
+        summary: *mut ZklProofSummary,
+    ) -> c_int;
+    pub fn zkl_comm_loopback() -> *const ZklComm;
+    pub fn zkl_comm_local_create(world: c_int, out: *mut *mut zkl_local_group) -> c_int;
+    pub fn zkl_comm_local_rank(g: *mut zkl_local_group, rank: c_int) -> *const ZklComm;
+    pub fn zkl_comm_local_destroy(g: *mut zkl_local_group);
+    pub fn zkl_set_shard_min_leaves(ctx: *mut zkl_ctx, leaves: usize) -> c_int;
+}
+
+/// The caller's collectives for the column-sharded prover: callbacks on DEVICE pointers of the calling rank, collective over all
+/// ranks, returning 0 once the result is complete (the library drains its stream before every call).
+#[repr(C)]
+pub struct ZklComm {
+    pub rank: c_int,
+    pub world: c_int,
+    pub user: *mut c_void,
+    /// recv = [world][bytes_per_rank]
+    pub all_gather: Option<unsafe extern "C" fn(user: *mut c_void, send_dev: *const c_void, recv_dev: *mut c_void, bytes_per_rank: usize) -> c_int>,
+    /// send, recv = [world][bytes_per_pair]
+    pub all_to_all: Option<unsafe extern "C" fn(user: *mut c_void, send_dev: *const c_void, recv_dev: *mut c_void, bytes_per_pair: usize) -> c_int>,
+    /// in place, exact modulo 2^64
+    pub all_reduce_sum_u64: Option<unsafe extern "C" fn(user: *mut c_void, buf_dev: *mut c_void, count: usize) -> c_int>,
+}
+#[repr(C)]
+pub struct zkl_local_group {
+    _private: [u8; 0],
 }
