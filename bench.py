@@ -286,6 +286,9 @@ def run_x_synth(args, zkl, rank, world, local):
     for _ in range(max(args.warmup, 1)):
         first_proof, _ = prove(False)
     ref_digest = hashlib.blake2b(first_proof, digest_size=16).hexdigest()
+    if comm is not None:   # the warm-up proof also set up NCCL's peer connections: count the timed proofs only
+        comm.bytes_moved, comm.calls = 0, 0
+        comm.seconds = {k: 0.0 for k in comm.seconds}
     sampler = ClockSampler(local) if rank == 0 else None
     ev, wall, stages, digests, plen, launches, clocks = timed(False, args.steps, sampler)
     e_ev, e_wall, _, e_digests, _, _, _ = timed(True, args.steps)
@@ -305,7 +308,7 @@ def run_x_synth(args, zkl, rank, world, local):
         hash_ms = float(stages[10])
         tensor_ops = N * my_parts * TENSOR_OPS_PER_PERM
         h2d = int(cols.numel())
-        total_steps = max(args.warmup, 1) + 2 * args.steps
+        total_steps = 2 * args.steps   # both timed legs (the counters restart after the warm-up)
         line = {
             "metric": "x-synth single-segment prove throughput (trace rows/s)", "value": n * args.steps / (ev * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": ev / args.steps, "higher_is_better": True, "scaling": "strong",
