@@ -877,10 +877,20 @@ static int prove_segment_impl(zkl_ctx *ctx, const fe *trace_dev, size_t W, size_
   // ---- 4/5. composition coefficients (transition then boundary) and constraint evaluation
   if (!sh || shard_trace) ZKL_TRY(upload_air(ctx, air, n, ast, sched));
   dev_buf<fe> cc, ce_ev, flag;
-  ZKL_CHECK(ctx, cc.alloc(ncc)); ZKL_CHECK(ctx, ce_ev.alloc(M)); ZKL_CHECK(ctx, flag.alloc(1));
+  // column-sharded prover with millions of coefficients (one per assertion): every rank draws 1 / R of them, all-gathered
+  const size_t cc_per = (ncc + (size_t)R - 1) / (size_t)R;
+  const bool cc_sharded = sh && R > 1 && ncc >= sg.min_leaves && ctx->hash_path == 0 && cc_per >= bulk_min(ctx);
+  ZKL_CHECK(ctx, cc.alloc(cc_sharded ? cc_per * (size_t)R : ncc)); ZKL_CHECK(ctx, ce_ev.alloc(M)); ZKL_CHECK(ctx, flag.alloc(1));
   ZKL_CHECK(ctx, cudaMemsetAsync(flag.p, 0, sizeof(fe), st));
   mark("air upload (host: assertions sorted, staged)");
-  ZKL_TRY(reseed_draw(tl.m.nodes.p + 1, nullptr, ncc, cc.p));   // reseed with the trace root, draw the composition coefficients
+  if (!cc_sharded) ZKL_TRY(reseed_draw(tl.m.nodes.p + 1, nullptr, ncc, cc.p));   // reseed with the trace root, draw the composition coefficients
+  else {
+    dev_buf<fe> mine; ZKL_CHECK(ctx, mine.alloc(cc_per));
+    ZKL_TRY(reseed_draw(tl.m.nodes.p + 1, nullptr, 0, nullptr));
+    LAUNCH_TC(ctx, k_tc_coin_draw, cc_per, coin.p, (uint64_t)((size_t)rk * cc_per), cc_per, mine.p);   // draws rk cc_per + 1 ... (past ncc: unused)
+    ZKL_TRY(wait_stream());
+    ZKL_TRY(comm_call(ctx, sg.comm->all_gather(sg.comm->user, mine.p, cc.p, cc_per * sizeof(fe)), "all_gather(composition coefficients)"));
+  }
   mark("draw composition coefficients");
   if (!sh) ZKL_TRY(dev_eval_constraints(ctx, tl.m, air, ast, cc.p, ce_ev.p));
   else {
