@@ -926,10 +926,11 @@ static int prove_segment_impl(zkl_ctx *ctx, const fe *trace_dev, size_t W, size_
     // all-gathered, tree from sub-trees
     committed_matrix &m = cmt.m;
     ZKL_TRY(dev_constraint_commit(ctx, ce_ev.p, n, ce, air->num_composition_cols, o, m, flag.p, E, true));
-    ZKL_CHECK(ctx, m.lde.alloc(m.width * N)); ZKL_CHECK(ctx, m.leaves.alloc(N)); ZKL_CHECK(ctx, m.nodes.alloc(N));
-    ZKL_TRY(dev_lde(ctx, m.polys.p, m.lde.p, m.width, n, B));
+    // m.lde holds THIS RANK'S cosets only, compact: [column][Bp][n]
+    ZKL_CHECK(ctx, m.lde.alloc(m.width * Bp * n)); ZKL_CHECK(ctx, m.leaves.alloc(N)); ZKL_CHECK(ctx, m.nodes.alloc(N));
+    ZKL_TRY(dev_lde_cosets(ctx, m.polys.p, m.lde.p, m.width, n, B, k0, Bp));
     dev_buf<fe> loc; ZKL_CHECK(ctx, loc.alloc(Bp * n));
-    ZKL_TRY(dev_hash_rows(ctx, m.lde.p + k0 * n, m.width, n, Bp, o, loc.p, m.scratch, m.ext, N));
+    ZKL_TRY(dev_hash_rows(ctx, m.lde.p, m.width, n, Bp, o, loc.p, m.scratch, m.ext));
     ZKL_TRY(shard_leaves_to_tree(ctx, sg, loc.p, B, n, m.leaves.p, m.nodes.p));
     mark("constraint commitment");
   }
@@ -987,7 +988,7 @@ static int prove_segment_impl(zkl_ctx *ctx, const fe *trace_dev, size_t W, size_
   if (!sh) {
     LAUNCH(ctx, k_deep_consts, 1, 32, 0, ood.p, dc.p, (int)W, (int)C, az.p);
     LAUNCH(ctx, k_deep, ceil_div(N, 256), 256, 0, tl.m.lde.p, cmt.m.lde.p, N, (int)n, (int)B, (int)W, (int)C, dc.p, az.p, z.p, g_n, tN->wpow, deep_inv.p, deep.p,
-           (size_t)0, N, 0);
+           (size_t)0, N, 0, N, (size_t)0);
   } else {
     // The DEEP composition is linear in the columns. Every rank sums over ITS trace columns on the whole domain; exchange (3b) is a
     // reduce-scatter by coset range (an all-to-all of the partial sums and a field addition of the R slices): the rank ends up with
@@ -1002,12 +1003,12 @@ static int prove_segment_impl(zkl_ctx *ctx, const fe *trace_dev, size_t W, size_
     LAUNCH(ctx, k_deep_consts, 1, 32, 0, oodl.p, dcl.p, (int)Wl, 0, az.p);
     LAUNCH(ctx, k_deep_consts, 1, 32, 0, oodc.p, dc.p + W, 0, (int)C, azc.p);
     LAUNCH(ctx, k_deep, ceil_div(N, 256), 256, 0, tl.m.lde.p, (const fe *)nullptr, N, (int)n, (int)B, (int)Wl, 0, dcl.p, az.p, z.p, g_n, tN->wpow, deep_inv.p, deep.p,
-           (size_t)0, N, 0);
+           (size_t)0, N, 0, N, (size_t)0);
     ZKL_TRY(wait_stream());
     ZKL_TRY(comm_call(ctx, sg.comm->all_to_all(sg.comm->user, deep.p, recv.p, Bp * n * sizeof(fe)), "all_to_all(DEEP partial sums)"));
     LAUNCH(ctx, k_sum_slices, ceil_div(Bp * n, 256), 256, 0, recv.p, R, Bp * n, deep.p);   // deep[0 .. Bp n): this rank's cosets from here on
     LAUNCH(ctx, k_deep, ceil_div(Bp * n, 256), 256, 0, (const fe *)nullptr, cmt.m.lde.p, N, (int)n, (int)B, 0, (int)C, dc.p + W, azc.p, z.p, g_n, tN->wpow, deep_inv.p,
-           deep.p, k0 * n, Bp * n, 1);
+           deep.p, k0 * n, Bp * n, 1, Bp * n, k0 * n);
     ZKL_TRY(wait_stream());
     mark("deep (partial sums, all_to_all, add)");
   }
@@ -1161,9 +1162,15 @@ static int prove_segment_impl(zkl_ctx *ctx, const fe *trace_dev, size_t W, size_
   struct tree_job { std::vector<std::vector<node_ref>> plan; int depth; };
   auto plan_matrix = [&](const committed_matrix &m, tree_job &tj) {
     const bool sharded_cols = sh && &m == &tl.m;   // the trace matrix holds this rank's columns only: the others are opened as zero and summed in
+    const bool sharded_cosets = sh && &m == &cmt.m;   // the composition matrix holds this rank's cosets only, compact
     for (uint32_t p : pos) {
       uint32_t s = (uint32_t)((p % m.blowup) * m.n + p / m.blowup);
-      if (!sharded_cols) for (size_t c = 0; c < m.width; c++) want_rep(m.lde.p + c * m.N, s);   // per-column base: width * N exceeds 32 bits for large segments
+      if (sharded_cosets) {
+        const size_t kc = p % m.blowup;
+        const bool mine = kc >= k0 && kc < k0 + Bp;
+        for (size_t c = 0; c < m.width; c++) { if (mine) want(m.lde.p + c * (Bp * m.n), (uint32_t)((kc - k0) * m.n + p / m.blowup)); else want(zero_fe.p, 0); }
+      }
+      else if (!sharded_cols) for (size_t c = 0; c < m.width; c++) want_rep(m.lde.p + c * m.N, s);   // per-column base: width * N exceeds 32 bits for large segments
       else for (size_t c = 0; c < W; c++) { if (c >= col0 && c < col0 + Wl) want(m.lde.p + (c - col0) * m.N, s); else want(zero_fe.p, 0); }
     }
     tj.plan = batch_proof_plan(pos, m.N); tj.depth = ilog2_sz(m.N);

@@ -209,7 +209,8 @@ __global__ void __launch_bounds__(256) k_deep_inverses(size_t N, int n, int blow
 __global__ void __launch_bounds__(256) k_deep(const fe *__restrict__ tlde, const fe *__restrict__ clde, size_t N, int n, int blowup, int W, int C,
                                               const fe *__restrict__ dc, const fe *__restrict__ az, const fe *__restrict__ z, fe g_n,
                                               const fe *__restrict__ wpowN, const fe *__restrict__ inv, fe *__restrict__ deep, size_t s_base,
-                                              size_t count, int accumulate) {
+                                              size_t count, int accumulate, size_t cstride_c /* column stride of clde */,
+                                              size_t c_off /* storage index of clde's first element: a coset range of the composition LDE */) {
   size_t tl = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (tl >= count) return;
   size_t s = s_base + tl;
@@ -224,7 +225,7 @@ __global__ void __launch_bounds__(256) k_deep(const fe *__restrict__ tlde, const
     a = fe_add(a, wacc_reduce(w));
   }
   for (; i < W; i++) a = fe_add(a, fe_mul(ld_fe(tlde + (size_t)i * N + s), ld_fe(dc + i)));
-  for (int j = 0; j < C; j++) a = fe_add(a, fe_mul(ld_fe(clde + (size_t)j * N + s), ld_fe(dc + W + j)));
+  for (int j = 0; j < C; j++) a = fe_add(a, fe_mul(ld_fe(clde + (size_t)j * cstride_c + (s - c_off)), ld_fe(dc + W + j)));
   fe zz = ld_fe(z);
   fe d1 = fe_sub(x, zz), d2 = fe_sub(x, fe_mul(zz, g_n));
   fe inv12 = ld_fe(inv + s);   // 1 / (d1 d2), k_deep_inverses
