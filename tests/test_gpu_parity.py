@@ -181,6 +181,30 @@ def test_prove_segment_bytes_and_verify(ctx, zkl, oracle, n, blowup, queries, gr
     assert s.constraints_violated == 0  # no composition degree overflow
 
 
+@pytest.mark.parametrize("kw", [dict(vm_expect=True, main_args=[("u64", 9), ("u64", 4)]), dict(vm_expect=True, pc_init=3, ram=False, usage_mask=0x0FF),
+                                dict(n=256, merkle=False, usage_mask=0x155, vm_expect=True, main_args=[("u64", 1)])])
+def test_closed_form_assertions_equal_the_explicit_list(ctx, zkl, kw):
+    """`zkl_prove_segment_pi` hands the device a 141-entry level template + the public-input extras and lets it expand the list
+    (k_expand_assertions); `zkl_prove_segment` takes the explicit list and orders it on the host. With every kind of extra present —
+    vm_expect at position 29 of a level (a step no schedule assertion names: its own divisor group), main_args registers and pc at row
+    0, the ROM state at the first and last row — both must give the same proof bytes. The columns are random, so the proof does not
+    verify (rc 3): only the bytes matter here."""
+    import ctypes as C
+    if ctx.hash_mode != "default":
+        pytest.skip("host / device ordering logic, independent of the hashing mode")
+    trace, air_pi, opts = synth.random_segment(seed=71, **kw)
+    a, ac, oc, seed = _air(zkl, trace, air_pi, opts)
+    closed = zkl.ZkProver(ctx, opts, air_pi).prove(trace, allow_invalid=True)
+    buf = np.empty(4 << 20, dtype=np.uint8)
+    cap = C.c_size_t(buf.shape[0])
+    summ = zkl.capi.ProofSummary()
+    t = zkl.prover.as_fe_array(trace)
+    rc = ctx.lib.zkl_prove_segment(ctx.h, t.ctypes.data, t.shape[0], t.shape[1], C.byref(ac), seed.ctypes.data, seed.shape[0], C.byref(oc),
+                                   buf.ctypes.data, C.byref(cap), C.byref(summ))
+    assert rc in (0, zkl.capi.ERR_CONSTRAINTS_VIOLATED)
+    assert buf[:cap.value].tobytes() == closed
+
+
 def test_prove_segment_device_resident_matches_host_path(ctx, zkl):
     import ctypes as C
     trace, air_pi, opts = synth.valid_segment(n=64, queries=8, blowup=16, grind=4)
