@@ -215,7 +215,8 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 // grid >= blowup CTAs; CTA b serves coset b % blowup and every (gridDim.x / blowup)-th column of it.
 __global__ void __launch_bounds__(NTT16_THREADS, 1) k_tc_lde4096_v2(const fe *polys, int ncols, int blowup, const uint4 *__restrict__ bmat,
                                                                    const fe *__restrict__ tw0, const fe *__restrict__ wpow, fe *out, bool inverse, int cross, size_t Ntab /* entries of wpow: w_Ntab^e */,
-                                                                   uint32_t radices /* 4 bits per cross level: log2 R_1 (lowest nibble) .. log2 R_L; 0 = the one level `cross` */) {
+                                                                   uint32_t radices /* 4 bits per cross level: log2 R_1 (lowest nibble) .. log2 R_L; 0 = the one level `cross` */,
+                                                                   bool block_major_out /* cross mode: block q's outputs stay together (k_tc_unscatter finishes) */) {
   extern __shared__ unsigned char ntt_smem[];
   const uint32_t base = (smem_u32(ntt_smem) + 127u) & ~127u;
   unsigned char *gen = ntt_smem + (base - smem_u32(ntt_smem));
@@ -327,7 +328,8 @@ __global__ void __launch_bounds__(NTT16_THREADS, 1) k_tc_lde4096_v2(const fe *po
             { size_t e = (size_t)(iB * jA) * s4096; if (inverse && e) e = N - e; v = lazy_mul(v, ld_fe(wpow + e)); }
             sts_u4(dst + (uint32_t)jA * NTT16_PITCH + (uint32_t)iB * 16, v.l[0], v.l[1], v.l[2], v.l[3]);
           } else {                   // m = iB, i = iA
-            if (cross) { size_t stride; fe *ob = out_base(c, &stride); st_fe(ob + stride * (size_t)(256 * i + m), lazy_canon(v)); }
+            if (cross && block_major_out) st_fe(out + ((((size_t)c >> prod_log) * blowup + k) << prod_log) * NTT16_N + ((size_t)c & (((size_t)1 << prod_log) - 1)) * NTT16_N + 256 * i + m, lazy_canon(v));
+            else if (cross) { size_t stride; fe *ob = out_base(c, &stride); st_fe(ob + stride * (size_t)(256 * i + m), lazy_canon(v)); }
             else st_fe(out + ((size_t)c * blowup + k) * NTT16_N + 256 * i + m, lazy_canon(v));
           }
         }
@@ -342,6 +344,30 @@ __global__ void __launch_bounds__(NTT16_THREADS, 1) k_tc_lde4096_v2(const fe *po
   if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
 }
 
+
+// The last step of a transform with P = R_1 ... R_L >= 32 blocks per column: slab (column, coset) holds block b's 4096 outputs
+// together (tmp[b][i1], the 4096-point kernel's unit-stride stores); y[o + P i1] = tmp[b(o)][i1] where o's digits are b's in
+// reverse order (o = i2_1 + R_1 (i2_2 + ...), b = ((i2_1 R_2 + i2_2) R_3 ...)). Scattering straight from the 4096-point kernel puts
+// every 16-byte element 16 P bytes from its neighbour — at P = 256 the capture showed 2.6x the algorithmic DRAM reads (sector
+// read-modify-write) — so the transpose goes through shared memory: 32 x 32 tiles, 512-byte runs on both sides.
+__global__ void __launch_bounds__(256) k_tc_unscatter(const fe *__restrict__ tmp, fe *__restrict__ out, int prod_log, uint32_t radices) {
+  __shared__ fe tile[32][33];
+  const size_t P = (size_t)1 << prod_log;
+  const size_t slab = blockIdx.z;
+  const size_t o0 = (size_t)blockIdx.y * 32, i0 = (size_t)blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 8 rows of 32 per pass
+  const fe *src = tmp + slab * P * NTT16_N;
+  fe *dst = out + slab * P * NTT16_N;
+#pragma unroll
+  for (int r = ty; r < 32; r += 8) {
+    size_t o = o0 + r, b = 0;
+    for (uint32_t rd = radices; rd; rd >>= 4) { const int lg = (int)(rd & 15); b = (b << lg) | (o & (((size_t)1 << lg) - 1)); o >>= lg; }
+    tile[r][tx] = ld_fe(src + b * NTT16_N + i0 + tx);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = ty; r < 32; r += 8) st_fe(dst + (i0 + r) * P + o0 + tx, tile[tx][r]);
+}
 
 // ================================================================= 65536-row columns: two passes, both on the tensor cores
 // n = 16 m, m = 4096, j = j1 + m j2, i = i2 + 16 i1:

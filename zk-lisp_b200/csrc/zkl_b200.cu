@@ -374,8 +374,13 @@ static int dev_tc_multilevel(zkl_ctx *ctx, const fe *src, fe *out, size_t ncols,
       in = to; to = (to == sa.p) ? sb.p : sa.p;
       if (l + 1 < pl.L) { cols *= (size_t)pl.R[l]; len = sub; }
     }
+    // the last pass scatters to y[o + P i1]; from P = 32 blocks per column on it keeps blocks together and a tiled transpose finishes
+    int prod_log = 0; for (int l = 0; l < pl.L; l++) prod_log += ilog2_sz((size_t)pl.R[l]);
+    const bool unscatter = pl.L > 1 && prod_log >= 5;
     LAUNCH(ctx, k_tc_lde4096_v2, lde16_grid(ctx, cols * (size_t)pl.R[pl.L - 1], blowup), NTT16_THREADS, NTT16_SMEM_BYTES, in, (int)(cols * (size_t)pl.R[pl.L - 1]), (int)blowup, bmat,
-           tw0, t->wpow, out + c0 * blowup * n, inverse, pl.R[pl.L - 1], t->N, pl.radices);
+           tw0, t->wpow, unscatter ? to : out + c0 * blowup * n, inverse, pl.R[pl.L - 1], t->N, pl.radices, unscatter);
+    if (unscatter)
+      LAUNCH(ctx, k_tc_unscatter, dim3(NTT16_N / 32, (unsigned)(((size_t)1 << prod_log) / 32), (unsigned)(nc * blowup)), 256, 0, to, out + c0 * blowup * n, prod_log, pl.radices);
   }
   return 0;
 }
@@ -388,7 +393,7 @@ static int dev_interpolate(zkl_ctx *ctx, const fe *src, fe *dst, size_t ncols, s
   if (n == NTT16_N && ctx->ntt_path == 0) {   // inverse radix-16 stages on the tensor cores, 1/n folded into the matrix (kernels_tcntt.cuh v2)
     const uint4 *bmat; const fe *tw0;
     ZKL_TRY(get_lde16_consts(ctx, 1, true, nullptr, 0, t, n_inv, 0, &bmat, &tw0));
-    LAUNCH(ctx, k_tc_lde4096_v2, lde16_grid(ctx, ncols, 1), NTT16_THREADS, NTT16_SMEM_BYTES, src, (int)ncols, 1, bmat, tw0, t->wpow, dst, true, 0, t->N, 0u);
+    LAUNCH(ctx, k_tc_lde4096_v2, lde16_grid(ctx, ncols, 1), NTT16_THREADS, NTT16_SMEM_BYTES, src, (int)ncols, 1, bmat, tw0, t->wpow, dst, true, 0, t->N, 0u, false);
     return 0;
   }
   if (ctx->ntt_path == 0 && cross_radix(n))   // 16 384 rows and up: cross stages + 4096-point transforms, all on the tensor cores
@@ -438,7 +443,7 @@ static int dev_lde(zkl_ctx *ctx, const fe *polys, fe *out, size_t ncols, size_t 
   if (n == NTT16_N && ctx->ntt_path == 0) {   // radix-16 stages on the tensor cores, coset shift folded into the matrix (kernels_tcntt.cuh v2)
     const uint4 *bmat; const fe *tw0;
     ZKL_TRY(get_lde16_consts(ctx, blowup, false, it->second, n, t, fe_zero(), 0, &bmat, &tw0));
-    LAUNCH(ctx, k_tc_lde4096_v2, lde16_grid(ctx, ncols, blowup), NTT16_THREADS, NTT16_SMEM_BYTES, polys, (int)ncols, (int)blowup, bmat, tw0, t->wpow, out, false, 0, t->N, 0u);
+    LAUNCH(ctx, k_tc_lde4096_v2, lde16_grid(ctx, ncols, blowup), NTT16_THREADS, NTT16_SMEM_BYTES, polys, (int)ncols, (int)blowup, bmat, tw0, t->wpow, out, false, 0, t->N, 0u, false);
     return 0;
   }
   if (ctx->ntt_path == 0 && cross_radix(n))   // 16 384 rows and up: cross stages + coset LDE of the 4096-row blocks, all on the tensor cores
