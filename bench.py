@@ -73,6 +73,7 @@ def parse_args():
     ap.add_argument("--reference-sample", action="store_true", help="--impl reference on the bounded n=512 / grind 13 sample instead of the full configuration")
     ap.add_argument("--config", default="rollup-bench", choices=["rollup-bench", "x-synth"],
                     help="x-synth: ONE large segment (W = 219, partitions (16, 16)) column-sharded over the N GPUs (BASELINE.json configs[4]; strong scaling)")
+    ap.add_argument("--no-large-segment", action="store_true", help="skip the 65 536-row single-segment leg (prove_wall_ms.one_65536_row_segment)")
     ap.add_argument("--x-logn", type=int, default=20, help="x-synth: log2 of the trace length (22 = BASELINE's size; the Python trace generator needs ~45 us per row)")
     return ap.parse_args()
 
@@ -518,6 +519,21 @@ def main():
     workers[0].ctx._check(workers[0].ctx.lib.zkl_tc_i8_peak(workers[0].ctx.h, C.byref(i8)))
     workers[0].ctx._check(workers[0].ctx.lib.zkl_imad_peak(workers[0].ctx.h, C.byref(imad)))
     barrier()
+    # one LARGE segment on the same stream (with the O(n^2) boundary table gone, fewer and larger segments are an
+    # operating point the reference cannot reach): 65 536 rows = 16x the reference's segment cap, every transform on the tensor cores
+    large = None
+    if rank == 0 and not args.no_large_segment:
+        import synth
+        ltrace, lpi, lopts = synth.valid_segment(n=65536, queries=QUERIES, blowup=BLOWUP, grind=GRIND, seed=PROGRAM_SEED + 99, program_seed=PROGRAM_SEED)
+        lprover = zkl.ZkProver(workers[0].ctx, lopts, lpi)
+        lproof = lprover.prove(ltrace)                                   # warm-up: tables of this size
+        lms = []
+        for _ in range(2):
+            lproof = lprover.prove(ltrace)
+            lms.append(float(sum(lprover.last_summary.stage_ms[:9])))
+        large = {"rows": 65536, "width": int(ltrace.shape[0]), "device_ms": min(lms), "rows_per_s": 65536 / (min(lms) * 1e-3), "proof_bytes": len(lproof),
+                 "constraints_violated": int(lprover.last_summary.constraints_violated), "what": "host trace -> proof bytes on ONE stream; device time of the proof"}
+        del ltrace, lproof
 
     if rank == 0:
         peaks = {}
@@ -589,6 +605,7 @@ def main():
             "proofs_identical_across_steps_and_entry_points": bool(deterministic),
             "prove_wall_ms": {"step_of_16_segments": ev_total / args.steps, "one_segment_alone_on_the_gpu": float(np.sum(excl[:9])),
                               "one_segment_alone_host_wall": float(np.min(lone_wall)),
+                              "one_65536_row_segment": large,
                               "rollup_bench_over_N_gpus": strong_ms,
                               "rollup_bench_over_N_gpus_what": "ONE job of 16 segments split over the N GPUs (strong scaling), host buffers, max over ranks"},
             "clocks": clocks,
