@@ -53,8 +53,8 @@ WIDE_MACS_PER_FIELD_PRODUCT = 16      # 4x4 32-bit limb products of one 128x128-
 # dram__bytes_read.sum + dram__bytes_write.sum per launch, read from the ncu --set full captures committed under profiles/
 # (not measured in this run: ncu replays kernels, a bench run under it is not a bench run)
 TRAFFIC = {
-    "k_tc_hash_rows": (220.0e6, "profiles/prof_tc_hash_rows_r01_details.txt: 214.3 MB read + 5.7 MB written; algorithmic 16*204*65536 = 213.9 MB read + 1 MB written"),
-    "k_tc_lde4096_v2": (171.8e6, "profiles/prof_tc_lde4096_v2_r01b_details.txt: 15.8 MB read + 156.0 MB written inside the kernel's window (the rest of the "
+    "k_tc_hash_rows": (218.7e6, "profiles/prof_tc_hash_rows_r02_details.txt: 214.1 MB read + 4.6 MB written; algorithmic 16*204*65536 = 213.9 MB read + 1 MB written"),
+    "k_tc_lde4096_v2": (172.0e6, "profiles/prof_tc_lde4096_v2_r02_details.txt: 15.7 MB read + 156.3 MB written inside the kernel's window (the rest of the "
                                  "213.9 MB output is still in the 126 MB L2 when the kernel ends); algorithmic 227.3 MB"),
 }
 
