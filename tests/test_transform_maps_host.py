@@ -151,3 +151,125 @@ def test_batch_inversion_prefix_suffix():
             if j:
                 r = r * v[t][j] % P
             assert iv * v[t][j] % P == 1
+
+
+def _multilevel(a, s, wn, radices, m):
+    """dev_tc_multilevel for one coset, modelled on Python integers: the column of n = R_1 ... R_L m coefficients goes through L cross
+    stages (per level: matrix entry (s^sub)^j2 w_R^(i2 j2), twiddle w_len^(j1 i2), block-major destination = the columns of the level
+    below) and the m-point coset transform of every block; block b's outputs land at y[o(b) + P i1] with o the digit reversal
+    k_tc_lde4096_v2 (scatter) and k_tc_unscatter (tiled transpose) both implement. Returns (y, the o(b) map)."""
+    n = len(a)
+    cols, length = [a[:]], n              # level l: `cols` columns of `length` elements
+    w_len = wn
+    for R in radices:
+        sub = length // R
+        s_sub, wR = pow(s, sub, P), pow(w_len, sub, P)
+        nxt = []
+        for col in cols:                  # column c -> columns c R + i2 of the level below
+            for i2 in range(R):
+                nxt.append([sum(col[j1 + sub * j2] * pow(s_sub, j2, P) * pow(wR, j2 * i2, P) for j2 in range(R)) % P * pow(w_len, j1 * i2, P) % P
+                            for j1 in range(sub)])
+        cols, length, w_len = nxt, sub, pow(w_len, R, P)
+    assert length == m
+    Pblocks = len(cols)
+    y, omap = [0] * n, []
+    for b, col in enumerate(cols):
+        # o(b): b = ((i2_1 R_2 + i2_2) R_3 ...) + i2_L, o = i2_1 + R_1 (i2_2 + R_2 (...))
+        digits, rem = [], b
+        for R in reversed(radices):
+            digits.append(rem % R); rem //= R
+        digits.reverse()                  # i2_1 .. i2_L
+        o, weight = 0, 1
+        for d, R in zip(digits, radices):
+            o += d * weight; weight *= R
+        omap.append(o)
+        blk = _dft([col[j1] * pow(s, j1, P) % P for j1 in range(m)], w_len)
+        for i1 in range(m):
+            y[o + Pblocks * i1] = blk[i1]
+    return y, omap
+
+
+def test_multilevel_cross_stages_and_the_digit_reversed_scatter():
+    """n = R_1 ... R_L m with two and three cross levels (the radices of 2^17, 2^18, 2^20 and 2^21 rows; m = 8 stands in for 4096: the
+    structure does not depend on m): the recursion of cross stages equals the coset DFT, and the block -> offset map is the one the
+    kernels compute from the packed radices (low nibble = R_1)."""
+    rnd = random.Random(11)
+    m = 8
+    for radices in ((2, 16), (4, 16), (16, 16), (2, 16, 16)):
+        n = m
+        for R in radices:
+            n *= R
+        logn = n.bit_length() - 1
+        wN = root_of_unity(logn + 1)                  # blowup 2
+        wn, s = pow(wN, 2, P), GENERATOR * wN % P      # coset 1
+        a = [rnd.randrange(P) for _ in range(n)]
+        y, omap = _multilevel(a, s, wn, radices, m)
+        assert y == _dft([a[j] * pow(s, j, P) % P for j in range(n)], wn), radices
+        # the kernels' version of the map (k_tc_lde4096_v2: out_base, k_tc_unscatter: b from o)
+        packed = 0
+        for l, R in enumerate(radices):
+            packed |= (R.bit_length() - 1) << (4 * l)
+        Pblocks = len(omap)
+        prod_log = Pblocks.bit_length() - 1
+        for q in range(Pblocks):                       # out_base: digits from the last level (least significant in q) to the first
+            rem, off, shift = q, 0, prod_log
+            for l in reversed(range(len(radices))):
+                lg = (packed >> (4 * l)) & 15
+                shift -= lg
+                off += (rem & ((1 << lg) - 1)) << shift
+                rem >>= lg
+            assert off == omap[q]
+        for o in range(Pblocks):                       # k_tc_unscatter: b from o, nibble by nibble
+            b, oo, rd = 0, o, packed
+            while rd:
+                lg = rd & 15
+                b = (b << lg) | (oo & ((1 << lg) - 1)); oo >>= lg; rd >>= 4
+            assert omap[b] == o
+
+
+def test_sharded_tree_and_leaf_index_maps():
+    """The column-sharded prover's index maps (csrc/api_stark.inl) on a toy hash: k_scatter_subtrees puts the all-gathered per-rank
+    sub-trees into the heap order of MerkleTree::new, k_interleave_leaves turns the all-gathered per-rank leaves (each rank's cosets
+    in its own natural order) into natural order over all cosets."""
+    rnd = random.Random(5)
+    M = (1 << 61) - 1
+
+    def h(a, b):
+        return (a * 0x9E3779B97F4A7C15 + b * 0xC2B2AE3D27D4EB4F + 1) % M
+
+    def heap(leaves):                                   # nodes[1] = root, nodes[count + i] would be leaf i
+        count = len(leaves)
+        nodes = [0] * count
+        level = leaves
+        lvl = count // 2
+        while lvl >= 1:
+            level = [h(level[2 * i], level[2 * i + 1]) for i in range(lvl)]
+            nodes[lvl:2 * lvl] = level
+            lvl //= 2
+        return nodes
+
+    for R in (2, 4, 8):
+        count = 64 * R
+        leaves = [rnd.randrange(M) for _ in range(count)]
+        full = heap(leaves)
+        per = count // R
+        gathered = []
+        for s in range(R):
+            gathered += heap(leaves[s * per:(s + 1) * per])         # per entries each, entry 0 unused
+        nodes = [0] * count
+        for g in range(R, count):                                   # k_scatter_subtrees
+            lvl = 1 << (g.bit_length() - 1)
+            j, p = g - lvl, lvl // R
+            s = j // p
+            nodes[g] = gathered[s * per + p + (j - s * p)]
+        top = heap(nodes[R:2 * R])                                  # dev_merkle(nodes + R, nodes, R)
+        nodes[1:R] = top[1:R]
+        assert nodes[1:] == full[1:]
+    for R, B, m in ((2, 16, 8), (8, 16, 4), (4, 8, 16)):
+        Bp = B // R
+        natural = [rnd.randrange(M) for _ in range(B * m)]          # leaf of natural row k + B i
+        gathered = []
+        for s in range(R):                                          # rank s: its cosets k' < Bp in its own natural order k' + Bp i
+            gathered += [natural[(s * Bp + (j % Bp)) + B * (j // Bp)] for j in range(Bp * m)]
+        out = [gathered[(k // Bp) * (Bp * m) + (k % Bp) + Bp * i] for p in range(B * m) for k, i in [(p % B, p // B)]]   # k_interleave_leaves
+        assert out == natural
