@@ -854,9 +854,14 @@ static int prove_segment_impl(zkl_ctx *ctx, const fe *trace_dev, size_t W, size_
     if (!shard_trace) ZKL_TRY(upload_air(ctx, air, n, ast, sched));
     mark("trace: partition digests");
     if (pc < sg.ppr) ZKL_CHECK(ctx, cudaMemsetAsync(send.p, 0, (size_t)R * sg.ppr * per * sizeof(fe), st));   // padded slots travel too
-    for (int d = 0; d < R; d++)   // send[d][q][j] = mine[q][d per + j]
-      ZKL_CHECK(ctx, cudaMemcpy2DAsync(send.p + (size_t)d * sg.ppr * per, per * sizeof(fe), mine.p + (size_t)d * per, N * sizeof(fe), per * sizeof(fe), pc,
-                                       cudaMemcpyDeviceToDevice, st));
+    for (int d = 0; d < R; d++) {   // send[d][q][j] = mine[q][d per + j]
+      if (N * sizeof(fe) <= 0x7FFFFFFFull)   // a strided copy while the source pitch fits cudaMemcpy2D's limit (2^22 rows at blowup 16 do)
+        ZKL_CHECK(ctx, cudaMemcpy2DAsync(send.p + (size_t)d * sg.ppr * per, per * sizeof(fe), mine.p + (size_t)d * per, N * sizeof(fe), per * sizeof(fe), pc,
+                                         cudaMemcpyDeviceToDevice, st));
+      else
+        for (size_t q = 0; q < pc; q++)
+          ZKL_CHECK(ctx, cudaMemcpyAsync(send.p + ((size_t)d * sg.ppr + q) * per, mine.p + q * N + (size_t)d * per, per * sizeof(fe), cudaMemcpyDeviceToDevice, st));
+    }
     ZKL_TRY(wait_stream());
     ZKL_TRY(comm_call(ctx, sg.comm->all_to_all(sg.comm->user, send.p, recv.p, sg.ppr * per * sizeof(fe)), "all_to_all(partition digests)"));
     mark("trace: pack + all_to_all(digests)");
