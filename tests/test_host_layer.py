@@ -102,6 +102,60 @@ def test_native_air_build_matches_python_mirror(zkl):
         assert PV.fe_to_ints(nat.seed) == [v % zkl.field.P for v in a.seed_elements()], name
 
 
+def test_closed_form_assertion_ranks_model(zkl):
+    """The arithmetic behind csrc/api_stark.inl: upload_air_sched + k_expand_assertions on Python integers: from ONE level's template
+    and the extras, template entry j of level l gets rank l T + j + (extras ordered before it), a template step's group starts at
+    l T + first_j + (extras at earlier steps), extras and extra-only steps are ranked on the host — and the result is the explicit
+    list sorted by (step, column) with one group per distinct step. The explicit list comes from the native `zkl_air_build` (every
+    kind of extra in `_air_cases`: vm_expect on position 29, main_args, pc_init, ROM state at both ends). The GPU suite checks the
+    kernel itself (`test_closed_form_assertions_equal_the_explicit_list`)."""
+    from zk_lisp_b200 import prover as PV
+    graft.build()
+    for name, (trace, air_pi, opts) in _air_cases(zkl):
+        W, n = trace.shape[0], trace.shape[1]
+        nat = PV.ZkProver(None, opts, air_pi).native_air(W, n)
+        explicit = [(nat.assertions[i].column, nat.assertions[i].step) for i in range(nat.num_assertions)]
+        levels, period = n // 32, 32
+        # the closed form: cells asserted at the same position of EVERY level are the template, the rest are extras
+        per_pos = {}
+        for col, step in explicit:
+            per_pos.setdefault((step % period, col), set()).add(step // period)
+        tmpl = sorted(k for k, lv in per_pos.items() if len(lv) == levels)                    # (pos, col), sorted
+        tset = set(tmpl)
+        extras = sorted((step, col) for col, step in explicit if (step % period, col) not in tset)   # (step, col), sorted
+        T, E = len(tmpl), len(extras)
+        assert levels * T + E == len(explicit), name
+        tg = [(pos, j) for j, (pos, col) in enumerate(tmpl) if j == 0 or tmpl[j - 1][0] != pos]   # distinct positions, first_j
+        G = len(tg)
+        tpos = {pos for pos, _ in tg}
+        xo = sorted({step for step, _ in extras if step % period not in tpos})                # steps only extras name
+        ranked = [None] * len(explicit)
+        ng = levels * G + len(xo)
+        gs = [None] * (ng + 1)
+        for l in range(levels):                                                               # k_expand_assertions
+            for j, (pos, col) in enumerate(tmpl):
+                step = l * period + pos
+                eb = sum(1 for es, ec in extras if es < step or (es == step and ec < col))
+                assert ranked[l * T + j + eb] is None
+                ranked[l * T + j + eb] = (step, col)
+            for k, (pos, first_j) in enumerate(tg):
+                step = l * period + pos
+                gs[l * G + k + sum(1 for x in xo if x < step)] = l * T + first_j + sum(1 for es, _ in extras if es < step)
+        for e, (step, col) in enumerate(extras):                                              # upload_air_sched, host side
+            before = sum(1 for pos, c in tmpl if pos < step % period or (pos == step % period and c < col))
+            rank = (step // period) * T + before + e
+            assert ranked[rank] is None
+            ranked[rank] = (step, col)
+        for x, step in enumerate(xo):
+            lvl, pos = step // period, step % period
+            gs[lvl * G + sum(1 for p_, _ in tg if p_ < pos) + x] = lvl * T + sum(1 for p_, _ in tmpl if p_ < pos) + sum(1 for es, _ in extras if es < step)
+        gs[ng] = len(explicit)
+        want = sorted((step, col) for col, step in explicit)
+        assert ranked == want, name
+        starts = [i for i in range(len(want)) if i == 0 or want[i][0] != want[i - 1][0]] + [len(want)]
+        assert gs == starts, name
+
+
 def test_native_air_build_rejects_what_the_mirror_rejects(zkl):
     import synth
     from zk_lisp_b200 import prover as PV
